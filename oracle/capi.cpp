@@ -1,0 +1,183 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).  Parity status: UNPINNED.
+// Plain-C entry points so that tests/, smoke() and bench.py's cpu_baseline / --impl reference legs can
+// drive the CPU restatement through ctypes (oracle/oracle.py).  Never linked into the product.
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "registration.hpp"
+
+using namespace orc;
+
+extern "C" {
+
+// Same field order as elm_reg_config in include/elimaloc_b200.h (kept independent on purpose).
+struct orc_reg_config {
+    int32_t icp_method, max_iteration, max_thread, use_radar_cov, debug_print, reserved0;
+    double max_search_dist, lm_lambda, icp_termination_threshold_m, min_overlap_ratio, max_fitness_score;
+    double range_variance_m, azimuth_variance_deg, elevation_variance_deg;
+};
+
+static RegistrationConfig to_cfg(const orc_reg_config* c) {
+    RegistrationConfig r;
+    r.icp_method = c->icp_method;
+    r.max_iteration = c->max_iteration;
+    r.i_max_thread = c->max_thread > 0 ? c->max_thread : 1;
+    r.use_radar_cov = c->use_radar_cov != 0;
+    r.b_debug_print = c->debug_print != 0;
+    r.max_search_dist = c->max_search_dist;
+    r.lm_lambda = c->lm_lambda;
+    r.icp_termination_threshold_m = c->icp_termination_threshold_m;
+    r.min_overlap_ratio = c->min_overlap_ratio;
+    r.max_fitness_score = c->max_fitness_score;
+    r.range_variance_m = c->range_variance_m;
+    r.azimuth_variance_deg = c->azimuth_variance_deg;
+    r.elevation_variance_deg = c->elevation_variance_deg;
+    return r;
+}
+
+// pcm.hpp:205-220 Pcl2PointStruct: float fields widened to double, local = pose.
+static std::vector<PointStruct> to_points(const float* xyz, size_t n) {
+    std::vector<PointStruct> v(n);
+    for (size_t i = 0; i < n; ++i) {
+        v[i].pose = V3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        v[i].local = v[i].pose;
+    }
+    return v;
+}
+static M4 to_m4(const double* t) { M4 m; std::memcpy(m.m, t, sizeof m.m); return m; }
+
+void* orc_map_create(double voxel_size, int max_pts) {
+    auto* m = new VoxelHashMap();
+    m->Init(voxel_size, max_pts);
+    return m;
+}
+void orc_map_destroy(void* m) { delete static_cast<VoxelHashMap*>(m); }
+void orc_map_add_points(void* m, const float* xyz, size_t n) { static_cast<VoxelHashMap*>(m)->AddPoints(to_points(xyz, n)); }
+void orc_map_cal_voxel_cov(void* m) { static_cast<VoxelHashMap*>(m)->CalVoxelCovAll(); }
+void orc_map_cal_point_cov(void* m, double d) { static_cast<VoxelHashMap*>(m)->CalPointCovAll(d); }
+size_t orc_map_num_voxels(void* m) { return static_cast<VoxelHashMap*>(m)->map_.size(); }
+size_t orc_map_num_points(void* m) { return static_cast<VoxelHashMap*>(m)->NumPoints(); }
+
+// Canonical dump: voxels sorted by key (x, then y, then z), points in insertion order inside a voxel.
+// Any pointer may be NULL.
+void orc_map_export(void* mp, int32_t* keys, int32_t* counts, double* vmean, double* vcov, float* pxyz, double* pmean,
+                    double* pcov) {
+    auto* m = static_cast<VoxelHashMap*>(mp);
+    std::vector<const std::pair<const Voxel, VoxelHashMap::VoxelBlock>*> v;
+    v.reserve(m->map_.size());
+    for (const auto& kv : m->map_) v.push_back(&kv);
+    std::sort(v.begin(), v.end(), [](auto a, auto b) {
+        if (a->first.x != b->first.x) return a->first.x < b->first.x;
+        if (a->first.y != b->first.y) return a->first.y < b->first.y;
+        return a->first.z < b->first.z;
+    });
+    size_t p = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        const auto& vb = v[i]->second;
+        if (keys) { keys[3 * i] = v[i]->first.x; keys[3 * i + 1] = v[i]->first.y; keys[3 * i + 2] = v[i]->first.z; }
+        if (counts) counts[i] = static_cast<int32_t>(vb.points.size());
+        if (vmean) { vmean[3 * i] = vb.covariance.mean.x; vmean[3 * i + 1] = vb.covariance.mean.y; vmean[3 * i + 2] = vb.covariance.mean.z; }
+        if (vcov) std::memcpy(vcov + 9 * i, vb.covariance.cov.m, 9 * sizeof(double));
+        for (const auto& pt : vb.points) {
+            if (pxyz) { pxyz[3 * p] = (float)pt.pose.x; pxyz[3 * p + 1] = (float)pt.pose.y; pxyz[3 * p + 2] = (float)pt.pose.z; }
+            if (pmean) { pmean[3 * p] = pt.covariance.mean.x; pmean[3 * p + 1] = pt.covariance.mean.y; pmean[3 * p + 2] = pt.covariance.mean.z; }
+            if (pcov) std::memcpy(pcov + 9 * p, pt.covariance.cov.m, 9 * sizeof(double));
+            ++p;
+        }
+    }
+}
+
+void* orc_reg_create() { return new Registration(); }
+void orc_reg_destroy(void* r) { delete static_cast<Registration*>(r); }
+
+// RunRegister (reg.cpp:274-418).  Trace arrays (may be NULL) hold up to max_trace iterations.
+void orc_run_register(void* reg, void* map, const float* src, size_t n, const double* T_init, const orc_reg_config* c,
+                      double* T_out, int32_t* is_success, double* fitness, double* local_cov, int32_t max_trace,
+                      int32_t* n_iter, double* tr_pose_in, double* tr_JTJ, double* tr_JTr, double* tr_res,
+                      double* tr_ncorr, double* tr_pose_out) {
+    auto* R = static_cast<Registration*>(reg);
+    auto* M = static_cast<VoxelHashMap*>(map);
+    const auto pts = to_points(src, n);
+    bool ok = (*is_success != 0);
+    M6 cov;
+    std::vector<IterTrace> trace;
+    const M4 T = R->RunRegister(pts, *M, to_m4(T_init), to_cfg(c), ok, *fitness, cov, &trace);
+    std::memcpy(T_out, T.m, sizeof T.m);
+    *is_success = ok ? 1 : 0;
+    std::memcpy(local_cov, cov.m, sizeof cov.m);
+    if (n_iter) *n_iter = static_cast<int32_t>(trace.size());
+    for (int i = 0; i < (int)trace.size() && i < max_trace; ++i) {
+        if (tr_pose_in) std::memcpy(tr_pose_in + 16 * i, trace[i].pose_in.m, 16 * sizeof(double));
+        if (tr_JTJ) std::memcpy(tr_JTJ + 36 * i, trace[i].lin.JTJ.m, 36 * sizeof(double));
+        if (tr_JTr) std::memcpy(tr_JTr + 6 * i, trace[i].lin.JTr.v, 6 * sizeof(double));
+        if (tr_res) tr_res[i] = trace[i].lin.residual_sum;
+        if (tr_ncorr) tr_ncorr[i] = (double)trace[i].lin.n_corr;
+        if (tr_pose_out) std::memcpy(tr_pose_out + 16 * i, trace[i].pose_out.m, 16 * sizeof(double));
+    }
+}
+
+void orc_linearize(void* reg, void* map, const float* src, size_t n, const double* T, const orc_reg_config* c,
+                   double* JTJ, double* JTr, double* res_sum, long long* n_corr) {
+    auto* R = static_cast<Registration*>(reg);
+    auto* M = static_cast<VoxelHashMap*>(map);
+    const auto pts = to_points(src, n);
+    const Linearization lin = R->LinearizeOnce(pts, *M, to_m4(T), to_cfg(c));
+    std::memcpy(JTJ, lin.JTJ.m, 36 * sizeof(double));
+    std::memcpy(JTr, lin.JTr.v, 6 * sizeof(double));
+    *res_sum = lin.residual_sum;
+    *n_corr = lin.n_corr;
+}
+
+// Correspondence dump for index-level parity.  K = 1 (P2P/GICP/VGICP) or 7 (AVGICP).
+// count[i] = pairs emitted for scan point i; target[(i*K + j)*3 ..] = matched position
+// (P2P: matched point pose; GICP: same search, pose reported; VGICP/AVGICP: voxel mean).
+void orc_correspondences(void* map, const float* src, size_t n, const double* Tp, int method, double max_dist,
+                         int32_t* count, double* target) {
+    auto* M = static_cast<VoxelHashMap*>(map);
+    const M4 T = to_m4(Tp);
+    const int K = (method == AVGICP) ? 7 : 1;
+    std::vector<PointStruct> one(1), sc, tc;
+    std::vector<CovStruct> tcc;
+    for (size_t i = 0; i < n; ++i) {
+        one[0].local = V3(src[3 * i], src[3 * i + 1], src[3 * i + 2]);
+        one[0].pose = apply(T, one[0].local);
+        for (int j = 0; j < K * 3; ++j) target[i * K * 3 + j] = 0.0;
+        if (method == P2P || method == GICP) {
+            std::tie(sc, tc) = M->GetCorrespondencePoints(one, max_dist, 1);
+            count[i] = (int32_t)sc.size();
+            if (!tc.empty()) { target[i * 3] = tc[0].pose.x; target[i * 3 + 1] = tc[0].pose.y; target[i * 3 + 2] = tc[0].pose.z; }
+        } else {
+            if (method == VGICP) std::tie(sc, tcc) = M->GetCorrespondencesCov(one, max_dist, 1);
+            else std::tie(sc, tcc) = M->GetCorrespondencesAllCov(one, max_dist, 1);
+            count[i] = (int32_t)sc.size();
+            for (size_t j = 0; j < tcc.size(); ++j) {
+                target[(i * K + j) * 3] = tcc[j].mean.x;
+                target[(i * K + j) * 3 + 1] = tcc[j].mean.y;
+                target[(i * K + j) * 3 + 2] = tcc[j].mean.z;
+            }
+        }
+    }
+}
+
+// Timed CPU baseline: `iters` full ICP iterations (search parallel over `threads`, accumulate + transform serial,
+// exactly the reference's structure).  Returns wall seconds of the RunRegister call.
+double orc_time_register(void* reg, void* map, const float* src, size_t n, const double* T_init,
+                         const orc_reg_config* c, int32_t* iters_done) {
+    auto* R = static_cast<Registration*>(reg);
+    auto* M = static_cast<VoxelHashMap*>(map);
+    const auto pts = to_points(src, n);
+    bool ok = false;
+    double fit = 0.0;
+    M6 cov;
+    std::vector<IterTrace> trace;
+    const auto t0 = std::chrono::steady_clock::now();
+    R->RunRegister(pts, *M, to_m4(T_init), to_cfg(c), ok, fit, cov, &trace);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (iters_done) *iters_done = (int32_t)trace.size();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"

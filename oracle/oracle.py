@@ -1,0 +1,187 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: UNPINNED (the reference ships no golden vectors).
+
+ctypes front-end of oracle/liboracle.so, the CPU restatement of the reference's
+pcm_matching hot path (registration.cpp / voxel_hash_map.{hpp,cpp}).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+P2P, GICP, VGICP, AVGICP = 0, 1, 2, 3
+
+
+class RegConfig(C.Structure):
+    """Field-for-field mirror of orc_reg_config (oracle/capi.cpp); reg.hpp:62-85 subset."""
+    _fields_ = [("icp_method", C.c_int32), ("max_iteration", C.c_int32), ("max_thread", C.c_int32),
+                ("use_radar_cov", C.c_int32), ("debug_print", C.c_int32), ("reserved0", C.c_int32),
+                ("max_search_dist", C.c_double), ("lm_lambda", C.c_double),
+                ("icp_termination_threshold_m", C.c_double), ("min_overlap_ratio", C.c_double),
+                ("max_fitness_score", C.c_double), ("range_variance_m", C.c_double),
+                ("azimuth_variance_deg", C.c_double), ("elevation_variance_deg", C.c_double)]
+
+
+def make_config(**kw):
+    """Defaults are config/localization.ini:80-109 of the reference."""
+    d = dict(icp_method=GICP, max_iteration=10, max_thread=1, use_radar_cov=0, debug_print=0, reserved0=0,
+             max_search_dist=5.0, lm_lambda=0.5, icp_termination_threshold_m=0.02, min_overlap_ratio=0.4,
+             max_fitness_score=0.5, range_variance_m=1.0, azimuth_variance_deg=0.4, elevation_variance_deg=0.4)
+    d.update(kw)
+    return RegConfig(**d)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp")) or f == "Makefile"]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.orc_map_create.restype = C.c_void_p
+        L.orc_map_create.argtypes = [C.c_double, C.c_int]
+        L.orc_map_destroy.argtypes = [C.c_void_p]
+        L.orc_map_add_points.argtypes = [C.c_void_p, fp, C.c_size_t]
+        L.orc_map_cal_voxel_cov.argtypes = [C.c_void_p]
+        L.orc_map_cal_point_cov.argtypes = [C.c_void_p, C.c_double]
+        L.orc_map_num_voxels.restype = C.c_size_t
+        L.orc_map_num_voxels.argtypes = [C.c_void_p]
+        L.orc_map_num_points.restype = C.c_size_t
+        L.orc_map_num_points.argtypes = [C.c_void_p]
+        L.orc_map_export.argtypes = [C.c_void_p, ip, ip, dp, dp, fp, dp, dp]
+        L.orc_reg_create.restype = C.c_void_p
+        L.orc_reg_destroy.argtypes = [C.c_void_p]
+        L.orc_run_register.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_size_t, dp, C.POINTER(RegConfig), dp, ip, dp,
+                                       dp, C.c_int32, ip, dp, dp, dp, dp, dp, dp]
+        L.orc_linearize.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_size_t, dp, C.POINTER(RegConfig), dp, dp, dp,
+                                    C.POINTER(C.c_longlong)]
+        L.orc_correspondences.argtypes = [C.c_void_p, fp, C.c_size_t, dp, C.c_int, C.c_double, ip, dp]
+        L.orc_time_register.restype = C.c_double
+        L.orc_time_register.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_size_t, dp, C.POINTER(RegConfig), ip]
+        _LIB = L
+    return _LIB
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _xyz(a):
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)
+    return a
+
+
+class VoxelHashMap:
+    """Mirror of the reference's VoxelHashMap (vhm.hpp:89-335) over the oracle."""
+
+    def __init__(self, voxel_size=1.0, max_points_per_voxel=30):
+        self._h = lib().orc_map_create(float(voxel_size), int(max_points_per_voxel))
+        self.voxel_size = float(voxel_size)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_map_destroy(self._h)
+            self._h = None
+
+    def AddPoints(self, xyz):
+        xyz = _xyz(xyz)
+        lib().orc_map_add_points(self._h, _f(xyz), xyz.shape[0])
+
+    def CalVoxelCovAll(self):
+        lib().orc_map_cal_voxel_cov(self._h)
+
+    def CalPointCovAll(self, d):
+        lib().orc_map_cal_point_cov(self._h, float(d))
+
+    def num_voxels(self):
+        return lib().orc_map_num_voxels(self._h)
+
+    def num_points(self):
+        return lib().orc_map_num_points(self._h)
+
+    def Empty(self):
+        return self.num_voxels() == 0
+
+    def export(self):
+        V, P = self.num_voxels(), self.num_points()
+        out = dict(keys=np.zeros((V, 3), np.int32), counts=np.zeros(V, np.int32), vmean=np.zeros((V, 3)),
+                   vcov=np.zeros((V, 3, 3)), pxyz=np.zeros((P, 3), np.float32), pmean=np.zeros((P, 3)),
+                   pcov=np.zeros((P, 3, 3)))
+        lib().orc_map_export(self._h, _i(out["keys"]), _i(out["counts"]), _d(out["vmean"]), _d(out["vcov"]),
+                             _f(out["pxyz"]), _d(out["pmean"]), _d(out["pcov"]))
+        return out
+
+
+class Registration:
+    """Mirror of the reference's Registration (reg.hpp:101-230) over the oracle."""
+
+    def __init__(self):
+        self._h = lib().orc_reg_create()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_reg_destroy(self._h)
+            self._h = None
+
+    def RunRegister(self, source_local, voxel_map, initial_guess, cfg, fitness_in=0.0, max_trace=64):
+        src = _xyz(source_local)
+        T0 = np.ascontiguousarray(initial_guess, dtype=np.float64).reshape(4, 4)
+        T = np.zeros((4, 4))
+        ok = np.zeros(1, np.int32)
+        fit = np.array([fitness_in], np.float64)
+        cov = np.zeros((6, 6))
+        nit = np.zeros(1, np.int32)
+        tr = dict(pose_in=np.zeros((max_trace, 4, 4)), JTJ=np.zeros((max_trace, 6, 6)), JTr=np.zeros((max_trace, 6)),
+                  res=np.zeros(max_trace), ncorr=np.zeros(max_trace), pose_out=np.zeros((max_trace, 4, 4)))
+        lib().orc_run_register(self._h, voxel_map._h, _f(src), src.shape[0], _d(T0), C.byref(cfg), _d(T), _i(ok),
+                               _d(fit), _d(cov), max_trace, _i(nit), _d(tr["pose_in"]), _d(tr["JTJ"]), _d(tr["JTr"]),
+                               _d(tr["res"]), _d(tr["ncorr"]), _d(tr["pose_out"]))
+        n = int(nit[0])
+        tr = {k: v[:min(n, max_trace)] for k, v in tr.items()}
+        return dict(pose=T, is_success=bool(ok[0]), fitness_score=float(fit[0]), local_cov=cov, n_iter=n, trace=tr)
+
+    def linearize(self, source_local, voxel_map, pose, cfg):
+        src = _xyz(source_local)
+        T0 = np.ascontiguousarray(pose, dtype=np.float64).reshape(4, 4)
+        JTJ, JTr, res = np.zeros((6, 6)), np.zeros(6), np.zeros(1)
+        nc = C.c_longlong(0)
+        lib().orc_linearize(self._h, voxel_map._h, _f(src), src.shape[0], _d(T0), C.byref(cfg), _d(JTJ), _d(JTr),
+                            _d(res), C.byref(nc))
+        return dict(JTJ=JTJ, JTr=JTr, residual_sum=float(res[0]), n_corr=int(nc.value))
+
+    def time_register(self, source_local, voxel_map, initial_guess, cfg):
+        src = _xyz(source_local)
+        T0 = np.ascontiguousarray(initial_guess, dtype=np.float64).reshape(4, 4)
+        it = np.zeros(1, np.int32)
+        sec = lib().orc_time_register(self._h, voxel_map._h, _f(src), src.shape[0], _d(T0), C.byref(cfg), _i(it))
+        return sec, int(it[0])
+
+
+def correspondences(voxel_map, source_local, pose, method, max_dist):
+    src = _xyz(source_local)
+    T0 = np.ascontiguousarray(pose, dtype=np.float64).reshape(4, 4)
+    K = 7 if method == AVGICP else 1
+    cnt = np.zeros(src.shape[0], np.int32)
+    tgt = np.zeros((src.shape[0], K, 3))
+    lib().orc_correspondences(voxel_map._h, _f(src), src.shape[0], _d(T0), int(method), float(max_dist), _i(cnt),
+                              _d(tgt))
+    return cnt, tgt
