@@ -1,0 +1,81 @@
+"""ctypes binding of libelimaloc_b200.so (include/elimaloc_b200.h).
+
+The library is the product; this file only declares its C ABI.  There is no fallback: if the shared object is
+missing the import fails loudly (build it with `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C elimaloc_b200/csrc`)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libelimaloc_b200.so")
+
+ELM_OK, ELM_ERR_INVALID, ELM_ERR_CUDA, ELM_ERR_NCCL, ELM_ERR_UNSUPPORTED, ELM_ERR_RANGE, ELM_ERR_STATE = range(7)
+P2P, GICP, VGICP, AVGICP = 0, 1, 2, 3
+
+
+class RegConfig(C.Structure):
+    """elm_reg_config — RegistrationConfig of the reference (registration.hpp:62-85), solver-read fields only."""
+    _fields_ = [("icp_method", C.c_int32), ("max_iteration", C.c_int32), ("max_thread", C.c_int32),
+                ("use_radar_cov", C.c_int32), ("debug_print", C.c_int32), ("reserved0", C.c_int32),
+                ("max_search_dist", C.c_double), ("lm_lambda", C.c_double),
+                ("icp_termination_threshold_m", C.c_double), ("min_overlap_ratio", C.c_double),
+                ("max_fitness_score", C.c_double), ("range_variance_m", C.c_double),
+                ("azimuth_variance_deg", C.c_double), ("elevation_variance_deg", C.c_double)]
+
+
+class ElmError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"elimaloc_b200 status {status}: {message}")
+        self.status = status
+
+
+_dp, _fp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+# name -> (restype, argtypes); every symbol include/elimaloc_b200.h declares
+SIGNATURES = {
+    "elm_last_error": (C.c_char_p, []),
+    "elm_device_count": (C.c_int, []),
+    "elm_map_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_double, C.c_int, C.c_int]),
+    "elm_map_destroy": (None, [C.c_void_p]),
+    "elm_map_add_points": (C.c_int, [C.c_void_p, _fp, C.c_size_t]),
+    "elm_map_cal_voxel_cov": (C.c_int, [C.c_void_p]),
+    "elm_map_cal_point_cov": (C.c_int, [C.c_void_p, C.c_double]),
+    "elm_map_empty": (C.c_int, [C.c_void_p]),
+    "elm_map_num_voxels": (C.c_size_t, [C.c_void_p]),
+    "elm_map_num_points": (C.c_size_t, [C.c_void_p]),
+    "elm_map_export": (C.c_int, [C.c_void_p, _ip, _ip, _dp, _dp, _fp, _dp, _dp]),
+    "elm_registration_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    "elm_registration_destroy": (None, [C.c_void_p]),
+    "elm_run_register": (C.c_int, [C.c_void_p, C.c_void_p, _fp, C.c_size_t, _dp, C.POINTER(RegConfig), _dp, _ip, _dp, _dp]),
+    "elm_register_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _dp, C.POINTER(RegConfig)]),
+    "elm_register_fetch": (C.c_int, [C.c_void_p, _dp, _ip, _dp, _dp, _ip]),
+    "elm_linearize": (C.c_int, [C.c_void_p, C.c_void_p, _fp, C.c_size_t, _dp, C.POINTER(RegConfig), _dp, _dp, _dp,
+                                C.POINTER(C.c_int64)]),
+    "elm_correspondences": (C.c_int, [C.c_void_p, C.c_void_p, _fp, C.c_size_t, _dp, C.c_int, C.c_double, _ip, _dp]),
+    "elm_registration_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "elm_comm_unique_id": (C.c_int, [_u8p]),
+    "elm_registration_set_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
+}
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                              "(run __graft_entry__.build() or `make -C elimaloc_b200/csrc`); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(status):
+    if status != ELM_OK:
+        raise ElmError(status, lib().elm_last_error().decode("utf-8", "replace"))

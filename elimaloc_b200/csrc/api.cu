@@ -1,0 +1,509 @@
+// C ABI of elimaloc_b200 (include/elimaloc_b200.h): the device-resident VoxelHashMap, the Registration handle that owns
+// the ICP loop, and the NCCL plumbing for the scan-sharded multi-GPU mode.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/elimaloc_b200.h"
+#include "host_map.hpp"
+#include "icp_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define ELM_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            return fail(ELM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+        }                                                                                                \
+    } while (0)
+
+template <class T>
+cudaError_t upload(T** dptr, const void* src, size_t count) {
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dptr, src, count * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// ---- NCCL through dlopen: the single-GPU path has no link-time dependency on it ---------------------------------
+struct NcclApi {
+    struct Uid { char b[128]; };  // ncclUniqueId is passed by value: 128 bytes
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Uid, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return false;
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(h, "ncclAllReduce"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;      // ncclSum
+
+}  // namespace
+
+// ======================================================================================================================
+struct elm_map {
+    elm::HostMap host;
+    int device = -1;  // -1: host-only map (builder tests without a GPU)
+    uint4* d_slots = nullptr;
+    float4* d_pts = nullptr;
+    double* d_prec = nullptr;
+    double4* d_vslots = nullptr;
+    double* d_vcov = nullptr;
+
+    elm::MapView view() const {
+        elm::MapView v;
+        v.slots = d_slots; v.pts = d_pts; v.prec = d_prec; v.vslots = d_vslots; v.vcov = d_vcov;
+        v.mask = host.mask; v.voxel_size = host.voxel_size;
+        return v;
+    }
+    int publish_points() {
+        if (device < 0) return ELM_OK;
+        ELM_CUDA(cudaSetDevice(device));
+        const size_t P = host.P();
+        std::vector<float4> p4(P);
+        for (size_t i = 0; i < P; ++i) {
+            p4[i].x = host.pxyz[3 * i]; p4[i].y = host.pxyz[3 * i + 1]; p4[i].z = host.pxyz[3 * i + 2];
+            p4[i].w = __int_as_float_host(host.porig[i]);
+        }
+        ELM_CUDA(upload(&d_pts, p4.data(), P));
+        ELM_CUDA(upload(&d_slots, host.slots.data(), host.slots.size()));
+        if (d_prec) { cudaFree(d_prec); d_prec = nullptr; }
+        if (d_vslots) { cudaFree(d_vslots); d_vslots = nullptr; }
+        if (d_vcov) { cudaFree(d_vcov); d_vcov = nullptr; }
+        return ELM_OK;
+    }
+    static float __int_as_float_host(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+    int publish_voxel_cov() {
+        if (device < 0) return ELM_OK;
+        ELM_CUDA(cudaSetDevice(device));
+        const size_t S = host.slots.size();
+        std::vector<double> vs(4 * S, 0.0), vc(12 * S, 0.0);
+        for (size_t s = 0; s < S; ++s) {
+            const int32_t v = host.slot_voxel[s];
+            if (v < 0) continue;
+            std::memcpy(&vs[4 * s], &host.vkey[v], 8);
+            for (int k = 0; k < 3; ++k) vs[4 * s + 1 + k] = host.vmean[3 * v + k];
+            for (int k = 0; k < 9; ++k) vc[12 * s + k] = host.vcov[9 * v + k];
+        }
+        ELM_CUDA(upload(reinterpret_cast<double**>(&d_vslots), vs.data(), 4 * S));
+        ELM_CUDA(upload(&d_vcov, vc.data(), 12 * S));
+        return ELM_OK;
+    }
+    int publish_point_cov() {
+        if (device < 0) return ELM_OK;
+        ELM_CUDA(cudaSetDevice(device));
+        const size_t P = host.P();
+        std::vector<double> rec(16 * P, 0.0);
+        for (size_t p = 0; p < P; ++p) {
+            for (int k = 0; k < 3; ++k) rec[16 * p + k] = host.pmean[3 * p + k];
+            for (int k = 0; k < 9; ++k) rec[16 * p + 3 + k] = host.pcov[9 * p + k];
+            for (int k = 0; k < 3; ++k) rec[16 * p + 12 + k] = host.pnormal[3 * p + k];
+        }
+        ELM_CUDA(upload(&d_prec, rec.data(), 16 * P));
+        return ELM_OK;
+    }
+    ~elm_map() {
+        if (device >= 0) {
+            cudaSetDevice(device);
+            cudaFree(d_slots); cudaFree(d_pts); cudaFree(d_prec); cudaFree(d_vslots); cudaFree(d_vcov);
+        }
+    }
+};
+
+struct elm_registration {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    elm::IcpState* d_state = nullptr;
+    elm::IcpState* h_state = nullptr;  // pinned
+    double* d_partials = nullptr;
+    int partial_rows = 0;
+    float* d_scan = nullptr;
+    size_t scan_cap = 0;
+    int* d_count = nullptr;
+    double* d_target = nullptr;
+    size_t hook_cap = 0;
+    int64_t launches = 0;
+    // last enqueue
+    bool pending = false, trivial = false;  // trivial: empty map or n == 0 -> no kernels ran
+    elm_reg_config cfg{};
+    double T_init[16];
+    // NCCL
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+
+    ~elm_registration() {
+        cudaSetDevice(device);
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int ensure_scan(elm_registration* r, size_t n) {
+    if (n > r->scan_cap) {
+        if (r->d_scan) cudaFree(r->d_scan);
+        r->d_scan = nullptr;
+        const size_t cap = (n + 1023) / 1024 * 1024;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_scan), cap * 3 * sizeof(float)));
+        r->scan_cap = cap;
+    }
+    return ELM_OK;
+}
+
+int ensure_partials(elm_registration* r, int rows) {
+    if (rows > r->partial_rows) {
+        if (r->d_partials) cudaFree(r->d_partials);
+        r->d_partials = nullptr;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_partials), static_cast<size_t>(rows) * elm::kAcc * sizeof(double)));
+        r->partial_rows = rows;
+    }
+    return ELM_OK;
+}
+
+int check_method(const elm_map* map, const elm_reg_config* cfg) {
+    if (cfg->icp_method < ELM_P2P || cfg->icp_method > ELM_AVGICP) return fail(ELM_ERR_INVALID, "unknown icp_method");
+    if (cfg->use_radar_cov) return fail(ELM_ERR_UNSUPPORTED, "use_radar_cov = 1 is out of scope (reference quirk Q14)");
+    if (map->device < 0) return fail(ELM_ERR_CUDA, "map is host-only (device = -1): no CUDA device to run on");
+    if (!map->host.vkey.empty()) {
+        if (cfg->icp_method == ELM_GICP && !map->d_prec) return fail(ELM_ERR_STATE, "GICP needs elm_map_cal_point_cov first");
+        if ((cfg->icp_method == ELM_VGICP || cfg->icp_method == ELM_AVGICP) && !map->d_vslots)
+            return fail(ELM_ERR_STATE, "VGICP/AVGICP need elm_map_cal_voxel_cov first");
+    }
+    return ELM_OK;
+}
+
+// Largest queries-per-warp in {32,16,8,4} that still leaves >= 90 % of the last wave of tiles busy.
+int pick_queries_per_warp(int n, int num_sms) {
+    const int slots = 2 * num_sms;
+    int best = 4;
+    double best_eff = -1.0;
+    for (int B = 32; B >= 4; B >>= 1) {
+        const int tiles = (n + elm::kIcpWarps * B - 1) / (elm::kIcpWarps * B);
+        const int waves = (tiles + slots - 1) / slots;
+        const double eff = static_cast<double>(tiles) / (static_cast<double>(waves) * slots);
+        if (eff >= 0.9) return B;
+        if (eff > best_eff) { best_eff = eff; best = B; }
+    }
+    return best;
+}
+
+elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg, size_t n) {
+    elm::IcpParams p;
+    p.method = cfg->icp_method;
+    p.n = static_cast<int>(n);
+    p.queries_per_warp = pick_queries_per_warp(p.n, r->num_sms);
+    p.max_dist2 = cfg->max_search_dist * cfg->max_search_dist;
+    p.th = cfg->max_search_dist;
+    p.lm_lambda = cfg->lm_lambda;
+    p.term_thr = cfg->icp_termination_threshold_m;
+    p.min_overlap = cfg->min_overlap_ratio;
+    return p;
+}
+
+// one linearisation: kernel -> fixed-order reduction -> (allreduce over ranks)
+int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm) {
+    const int grid = elm::icp_linearize_grid(prm, r->num_sms);
+    int rc = ensure_partials(r, grid);
+    if (rc) return rc;
+    ELM_CUDA(elm::launch_icp_linearize(map->view(), d_scan, prm, r->d_state, r->d_partials, grid, r->stream));
+    ELM_CUDA(elm::launch_icp_reduce(r->d_state, r->d_partials, grid, r->stream));
+    r->launches += 2;
+    if (r->comm) {
+        const int e = g_nccl.AllReduce(r->d_state->acc, r->d_state->acc, elm::kAcc, kNcclFloat64, kNcclSum, r->comm, r->stream);
+        if (e != 0) return fail(ELM_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(e));
+        r->launches += 1;
+    }
+    return ELM_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================================
+extern "C" {
+
+const char* elm_last_error(void) { return g_err.c_str(); }
+
+int elm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int elm_map_create(elm_map** out, double voxel_size, int max_points_per_voxel, int device) {
+    if (!out || !(voxel_size > 0.0) || max_points_per_voxel < 1) return fail(ELM_ERR_INVALID, "elm_map_create: bad argument");
+    if (device >= 0) {
+        if (device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_map_create: no such CUDA device");
+        ELM_CUDA(cudaSetDevice(device));
+    }
+    elm_map* m = new (std::nothrow) elm_map();
+    if (!m) return fail(ELM_ERR_INVALID, "out of memory");
+    m->host.voxel_size = voxel_size;
+    m->host.cap = max_points_per_voxel;
+    m->device = device;
+    *out = m;
+    return ELM_OK;
+}
+
+void elm_map_destroy(elm_map* map) { delete map; }
+
+int elm_map_add_points(elm_map* map, const float* xyz, size_t n) {
+    if (!map || (!xyz && n)) return fail(ELM_ERR_INVALID, "elm_map_add_points: bad argument");
+    const std::string e = map->host.add_points(xyz, n);
+    if (!e.empty()) return fail(ELM_ERR_RANGE, e);
+    return map->publish_points();
+}
+
+int elm_map_cal_voxel_cov(elm_map* map) {
+    if (!map) return fail(ELM_ERR_INVALID, "null map");
+    map->host.cal_voxel_cov();
+    return map->publish_voxel_cov();
+}
+
+int elm_map_cal_point_cov(elm_map* map, double search_dist) {
+    if (!map) return fail(ELM_ERR_INVALID, "null map");
+    map->host.cal_point_cov(search_dist);
+    return map->publish_point_cov();
+}
+
+int elm_map_empty(const elm_map* map) { return (!map || map->host.vkey.empty()) ? 1 : 0; }
+size_t elm_map_num_voxels(const elm_map* map) { return map ? map->host.V() : 0; }
+size_t elm_map_num_points(const elm_map* map) { return map ? map->host.P() : 0; }
+
+int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* vmean, double* vcov, float* pxyz,
+                   double* pmean, double* pcov) {
+    if (!map) return fail(ELM_ERR_INVALID, "null map");
+    const elm::HostMap& h = map->host;
+    if ((vmean || vcov) && !h.has_vcov) return fail(ELM_ERR_STATE, "voxel covariances not computed");
+    if ((pmean || pcov) && !h.has_pcov) return fail(ELM_ERR_STATE, "point covariances not computed");
+    for (size_t v = 0; v < h.V(); ++v) {
+        if (keys) elm::unpack_key(h.vkey[v], keys[3 * v], keys[3 * v + 1], keys[3 * v + 2]);
+        if (counts) counts[v] = static_cast<int32_t>(h.vstart[v + 1] - h.vstart[v]);
+    }
+    if (vmean) std::memcpy(vmean, h.vmean.data(), h.vmean.size() * sizeof(double));
+    if (vcov) std::memcpy(vcov, h.vcov.data(), h.vcov.size() * sizeof(double));
+    if (pxyz) std::memcpy(pxyz, h.pxyz.data(), h.pxyz.size() * sizeof(float));
+    if (pmean) std::memcpy(pmean, h.pmean.data(), h.pmean.size() * sizeof(double));
+    if (pcov) std::memcpy(pcov, h.pcov.data(), h.pcov.size() * sizeof(double));
+    return ELM_OK;
+}
+
+int elm_registration_create(elm_registration** out, int device, void* stream) {
+    if (!out) return fail(ELM_ERR_INVALID, "null out");
+    if (device < 0 || device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_registration_create: no such CUDA device");
+    ELM_CUDA(cudaSetDevice(device));
+    elm_registration* r = new (std::nothrow) elm_registration();
+    if (!r) return fail(ELM_ERR_INVALID, "out of memory");
+    r->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) r->num_sms = prop.multiProcessorCount;
+    if (stream) { r->stream = static_cast<cudaStream_t>(stream); }
+    else {
+        if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) { delete r; return fail(ELM_ERR_CUDA, "cudaStreamCreate failed"); }
+        r->own_stream = true;
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&r->d_state), sizeof(elm::IcpState)) != cudaSuccess ||
+        cudaMemset(r->d_state, 0, sizeof(elm::IcpState)) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&r->h_state), sizeof(elm::IcpState)) != cudaSuccess) {
+        delete r;
+        return fail(ELM_ERR_CUDA, "state allocation failed");
+    }
+    std::memset(r->h_state, 0, sizeof(elm::IcpState));
+    *out = r;
+    return ELM_OK;
+}
+
+void elm_registration_destroy(elm_registration* reg) { delete reg; }
+
+int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float* d_src_xyz, size_t n, const double T_init[16],
+                         const elm_reg_config* cfg) {
+    if (!reg || !map || !T_init || !cfg || (!d_src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_register_enqueue: bad argument");
+    if (n > 0x7fffffffull / 8) return fail(ELM_ERR_INVALID, "scan too large");
+    int rc = check_method(map, cfg);
+    if (rc) return rc;
+    if (map->device != reg->device) return fail(ELM_ERR_INVALID, "map and registration live on different devices");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    reg->cfg = *cfg;
+    std::memcpy(reg->T_init, T_init, sizeof reg->T_init);
+    reg->launches = 0;
+    reg->pending = true;
+    // reg.cpp:291-295 (empty map) and the n == 0 guard: nothing to run.  In the sharded mode a rank with an empty shard
+    // still has to take part in the allreduces, so only the single-rank case short-circuits on n == 0.
+    reg->trivial = map->host.vkey.empty() || (n == 0 && !reg->comm);
+    if (reg->trivial) return ELM_OK;
+    const elm::IcpParams prm = make_params(reg, cfg, n);
+    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->stream));
+    reg->launches += 1;
+    for (int j = 0; j < cfg->max_iteration; ++j) {  // reg.cpp:310
+        rc = enqueue_linearize(reg, map, d_src_xyz, prm);
+        if (rc) return rc;
+        ELM_CUDA(elm::launch_icp_solve(reg->d_state, prm, reg->stream));
+        reg->launches += 1;
+    }
+    ELM_CUDA(cudaMemcpyAsync(reg->h_state, reg->d_state, sizeof(elm::IcpState), cudaMemcpyDeviceToHost, reg->stream));
+    return ELM_OK;
+}
+
+int elm_register_fetch(elm_registration* reg, double T_out[16], int32_t* is_success, double* fitness_score, double local_cov[36],
+                       int32_t* iterations_run) {
+    if (!reg || !T_out || !is_success) return fail(ELM_ERR_INVALID, "elm_register_fetch: bad argument");
+    if (!reg->pending) return fail(ELM_ERR_STATE, "elm_register_fetch without elm_register_enqueue");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    reg->pending = false;
+    if (reg->trivial) {
+        std::memcpy(T_out, reg->T_init, 16 * sizeof(double));
+        *is_success = 0;
+        if (local_cov) for (int i = 0; i < 36; ++i) local_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+        if (iterations_run) *iterations_run = 0;
+        return ELM_OK;
+    }
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    const elm::IcpState& st = *reg->h_state;
+    std::memcpy(T_out, st.T, 16 * sizeof(double));
+    if (local_cov) std::memcpy(local_cov, st.local_cov, 36 * sizeof(double));
+    if (iterations_run) *iterations_run = st.iterations;
+    if (st.overlap_fail) {                                   // reg.cpp:352-356
+        *is_success = 0;
+    } else if (st.fitness > reg->cfg.max_fitness_score) {    // reg.cpp:405-409
+        *is_success = 0;
+    } else {                                                 // reg.cpp:415-417
+        if (fitness_score) *fitness_score = st.fitness;
+        *is_success = 1;
+    }
+    if (reg->cfg.debug_print)
+        std::printf("[elimaloc_b200] RunRegister: %d iterations, fitness %.6f, success %d\n", st.iterations, st.fitness, *is_success);
+    return ELM_OK;
+}
+
+int elm_run_register(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T_init[16],
+                     const elm_reg_config* cfg, double T_out[16], int32_t* is_success, double* fitness_score, double local_cov[36]) {
+    if (!reg || !map || !T_init || !cfg || !T_out || !is_success || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_run_register: bad argument");
+    int rc = check_method(map, cfg);
+    if (rc) return rc;
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (n && !map->host.vkey.empty()) {
+        rc = ensure_scan(reg, n);
+        if (rc) return rc;
+        ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    }
+    rc = elm_register_enqueue(reg, map, reg->d_scan, n, T_init, cfg);
+    if (rc) return rc;
+    return elm_register_fetch(reg, T_out, is_success, fitness_score, local_cov, nullptr);
+}
+
+int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
+                  const elm_reg_config* cfg, double JTJ[36], double JTr[6], double* residual_sum, int64_t* n_corr) {
+    if (!reg || !map || !T || !cfg || !JTJ || !JTr || !residual_sum || !n_corr || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_linearize: bad argument");
+    int rc = check_method(map, cfg);
+    if (rc) return rc;
+    if (map->device != reg->device) return fail(ELM_ERR_INVALID, "map and registration live on different devices");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    std::memset(JTJ, 0, 36 * sizeof(double));
+    std::memset(JTr, 0, 6 * sizeof(double));
+    *residual_sum = 0.0;
+    *n_corr = 0;
+    if (map->host.vkey.empty() || (n == 0 && !reg->comm)) return ELM_OK;
+    rc = ensure_scan(reg, n);
+    if (rc) return rc;
+    if (n) ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    const elm::IcpParams prm = make_params(reg, cfg, n);
+    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->stream));
+    rc = enqueue_linearize(reg, map, reg->d_scan, prm);
+    if (rc) return rc;
+    ELM_CUDA(cudaMemcpyAsync(reg->h_state, reg->d_state, sizeof(elm::IcpState), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    const double* a = reg->h_state->acc;
+    int k = 0;
+    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { JTJ[6 * i + j] = a[k]; JTJ[6 * j + i] = a[k]; ++k; }
+    for (int i = 0; i < 6; ++i) JTr[i] = a[elm::kIdxJtr + i];
+    *residual_sum = a[elm::kIdxRes];
+    *n_corr = static_cast<int64_t>(std::llround(a[elm::kIdxNcorr]));
+    return ELM_OK;
+}
+
+int elm_correspondences(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
+                        int method, double max_search_dist, int32_t* count, double* target) {
+    if (!reg || !map || !T || !count || !target || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_correspondences: bad argument");
+    elm_reg_config c{};
+    c.icp_method = method;
+    int rc = check_method(map, &c);
+    if (rc) return rc;
+    const int K = (method == ELM_AVGICP) ? 7 : 1;
+    std::memset(count, 0, n * sizeof(int32_t));
+    std::memset(target, 0, n * K * 3 * sizeof(double));
+    if (map->host.vkey.empty() || n == 0) return ELM_OK;
+    ELM_CUDA(cudaSetDevice(reg->device));
+    rc = ensure_scan(reg, n);
+    if (rc) return rc;
+    if (n * 7 > reg->hook_cap) {
+        cudaFree(reg->d_count); cudaFree(reg->d_target);
+        reg->d_count = nullptr; reg->d_target = nullptr;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_count), n * sizeof(int)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_target), n * 21 * sizeof(double)));
+        reg->hook_cap = n * 7;
+    }
+    ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    ELM_CUDA(elm::launch_icp_match(map->view(), reg->d_scan, static_cast<int>(n), T, method, max_search_dist * max_search_dist,
+                                   reg->d_count, reg->d_target, reg->num_sms, reg->stream));
+    ELM_CUDA(cudaMemcpyAsync(count, reg->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaMemcpyAsync(target, reg->d_target, n * K * 3 * sizeof(double), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    return ELM_OK;
+}
+
+int elm_registration_launch_count(const elm_registration* reg, int64_t* launches) {
+    if (!reg || !launches) return fail(ELM_ERR_INVALID, "bad argument");
+    *launches = reg->launches;
+    return ELM_OK;
+}
+
+int elm_comm_unique_id(uint8_t unique_id[128]) {
+    if (!unique_id) return fail(ELM_ERR_INVALID, "null id");
+    if (!g_nccl.load()) return fail(ELM_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    const int e = g_nccl.GetUniqueId(unique_id);
+    if (e != 0) return fail(ELM_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(e));
+    return ELM_OK;
+}
+
+int elm_registration_set_comm(elm_registration* reg, const uint8_t unique_id[128], int rank, int world_size) {
+    if (!reg || !unique_id || world_size < 1 || rank < 0 || rank >= world_size) return fail(ELM_ERR_INVALID, "elm_registration_set_comm: bad argument");
+    if (!g_nccl.load()) return fail(ELM_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (reg->comm) { g_nccl.CommDestroy(reg->comm); reg->comm = nullptr; }
+    NcclApi::Uid id;
+    std::memcpy(id.b, unique_id, 128);
+    const int e = g_nccl.CommInitRank(&reg->comm, world_size, id, rank);
+    if (e != 0) { reg->comm = nullptr; return fail(ELM_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(e)); }
+    reg->rank = rank;
+    reg->world = world_size;
+    return ELM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,289 @@
+// Host-side voxel-map builder (see host_map.hpp).  Reference behaviour followed:
+//   AddPoints            pcm_matching/src/voxel_hash_map.cpp:270-285
+//   AddPointWithSpacing  pcm_matching/include/voxel_hash_map.hpp:106-113
+//   CalVoxelCov          pcm_matching/include/voxel_hash_map.hpp:114-148
+//   ProcessVoxelBlock    pcm_matching/include/voxel_hash_map.hpp:195-250
+#include "host_map.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <atomic>
+#include <thread>
+
+namespace elm {
+
+namespace {
+
+template <class F>
+void parallel_for(size_t n, size_t grain, F f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    size_t nt = std::min<size_t>(hw, (n + grain - 1) / std::max<size_t>(grain, 1));
+    if (nt <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t b = n * t / nt, e = n * (t + 1) / nt;
+        th.emplace_back([=]() { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// Jacobi rotations on a symmetric 3x3 held as a[6] = {xx, xy, xz, yy, yz, zz}; v = eigenvectors (columns).
+void eig_sym3(const double a_in[6], double w[3], double v[3][3]) {
+    double a[3][3] = {{a_in[0], a_in[1], a_in[2]}, {a_in[1], a_in[3], a_in[4]}, {a_in[2], a_in[4], a_in[5]}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    static const int pairs[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        if (a[0][1] == 0.0 && a[0][2] == 0.0 && a[1][2] == 0.0) break;
+        for (const auto& pq : pairs) {
+            const int p = pq[0], q = pq[1];
+            const double apq = a[p][q];
+            if (apq == 0.0) continue;
+            const double tau = (a[q][q] - a[p][p]) / (2.0 * apq);
+            const double t = std::copysign(1.0, tau) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+            const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+            for (int k = 0; k < 3; ++k) {
+                const double x = a[k][p], y = a[k][q];
+                a[k][p] = c * x - s * y;
+                a[k][q] = s * x + c * y;
+            }
+            for (int k = 0; k < 3; ++k) {
+                const double x = a[p][k], y = a[q][k];
+                a[p][k] = c * x - s * y;
+                a[q][k] = s * x + c * y;
+            }
+            a[p][q] = a[q][p] = 0.0;
+            for (int k = 0; k < 3; ++k) {
+                const double x = v[k][p], y = v[k][q];
+                v[k][p] = c * x - s * y;
+                v[k][q] = s * x + c * y;
+            }
+        }
+    }
+    w[0] = a[0][0]; w[1] = a[1][1]; w[2] = a[2][2];
+    // ascending, first-of-equals kept in place
+    for (int i = 0; i < 2; ++i) {
+        int k = i;
+        for (int j = i + 1; j < 3; ++j) if (w[j] < w[k]) k = j;
+        if (k != i) {
+            std::swap(w[i], w[k]);
+            for (int r = 0; r < 3; ++r) std::swap(v[r][i], v[r][k]);
+        }
+    }
+}
+
+// mean + sample covariance /(n-1) of a multiset of positions, then the regularisation.
+void mean_cov_regularized(const double* pts, size_t n, double mean[3], double cov_out[9], double normal[3]) {
+    double s[3] = {0, 0, 0};
+    for (size_t i = 0; i < n; ++i) { s[0] += pts[3 * i]; s[1] += pts[3 * i + 1]; s[2] += pts[3 * i + 2]; }
+    const double dn = static_cast<double>(n);
+    mean[0] = s[0] / dn; mean[1] = s[1] / dn; mean[2] = s[2] / dn;
+    double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < n; ++i) {
+        const double d[3] = {pts[3 * i] - mean[0], pts[3 * i + 1] - mean[1], pts[3 * i + 2] - mean[2]};
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) c[a * 3 + b] += d[a] * d[b];
+    }
+    for (int i = 0; i < 9; ++i) c[i] /= (dn - 1.0);
+    plane_regularize(c, cov_out, normal);
+}
+
+}  // namespace
+
+void plane_regularize(const double cov[9], double out[9], double normal[3]) {
+    const double a[6] = {cov[0], 0.5 * (cov[1] + cov[3]), 0.5 * (cov[2] + cov[6]), cov[4], 0.5 * (cov[5] + cov[7]), cov[8]};
+    double w[3], v[3][3];
+    eig_sym3(a, w, v);
+    const double lmax = std::max(std::fabs(w[2]), std::fabs(w[0]));
+    const double tol = 1e-9 * std::max(lmax, 1e-300);
+    double n[3];
+    if (std::fabs(w[2] - w[0]) <= tol) {  // isotropic (or zero): Eigen's JacobiSVD leaves U = I
+        n[0] = 0; n[1] = 0; n[2] = 1;
+    } else if (std::fabs(w[1] - w[0]) <= tol) {  // rank-1-like: null space is a plane -> fixed completion
+        const double u[3] = {v[0][2], v[1][2], v[2][2]};
+        int k = 0;
+        double best = std::fabs(u[0]);
+        if (std::fabs(u[1]) < best) { best = std::fabs(u[1]); k = 1; }
+        if (std::fabs(u[2]) < best) { best = std::fabs(u[2]); k = 2; }
+        double e[3] = {0, 0, 0};
+        e[k] = 1.0;
+        const double d = u[k];
+        double t[3] = {e[0] - d * u[0], e[1] - d * u[1], e[2] - d * u[2]};
+        const double l = std::sqrt((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]);
+        n[0] = t[0] / l; n[1] = t[1] / l; n[2] = t[2] / l;
+    } else {
+        n[0] = v[0][0]; n[1] = v[1][0]; n[2] = v[2][0];
+    }
+    const double k = 1.0 - 1e-3;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) out[i * 3 + j] = ((i == j) ? 1.0 : 0.0) - k * n[i] * n[j];
+    if (normal) { normal[0] = n[0]; normal[1] = n[1]; normal[2] = n[2]; }
+}
+
+std::string HostMap::add_points(const float* xyz, size_t n) {
+    if (n == 0) return "";
+    const size_t P0 = P();
+    const size_t total = P0 + n;
+    if (total >= (1ull << 32)) return "more than 2^32 points";
+    // 1. keys: stored points keep their voxel; new points: static_cast<int>(p / voxel_size) — truncation toward zero.
+    struct Rec { uint64_t key; uint32_t idx; };
+    std::vector<Rec> recs(total);
+    for (size_t v = 0; v < V(); ++v)
+        for (uint32_t p = vstart[v]; p < vstart[v + 1]; ++p) recs[p] = Rec{vkey[v], p};
+    std::atomic<bool> bad{false};
+    const double vs = voxel_size;
+    parallel_for(n, 1 << 16, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            const double qx = static_cast<double>(xyz[3 * i]) / vs, qy = static_cast<double>(xyz[3 * i + 1]) / vs,
+                         qz = static_cast<double>(xyz[3 * i + 2]) / vs;
+            if (!(std::fabs(qx) < kKeyBias && std::fabs(qy) < kKeyBias && std::fabs(qz) < kKeyBias)) { bad = true; continue; }
+            recs[P0 + i] = Rec{pack_key(static_cast<int32_t>(qx), static_cast<int32_t>(qy), static_cast<int32_t>(qz)),
+                               static_cast<uint32_t>(P0 + i)};
+        }
+    });
+    if (bad) return "map point outside +-2^20 voxels per axis (or not finite)";
+    // 2. stable order: (key, arrival index).  Stored points precede new ones inside their voxel.
+    std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.key != b.key ? a.key < b.key : a.idx < b.idx; });
+    // 3. voxel groups
+    std::vector<size_t> gstart;
+    for (size_t i = 0; i < total; ++i) if (i == 0 || recs[i].key != recs[i - 1].key) gstart.push_back(i);
+    const size_t G = gstart.size();
+    gstart.push_back(total);
+    auto coord = [&](uint32_t idx, int c) -> float { return idx < P0 ? pxyz[3 * idx + c] : xyz[3 * (idx - P0) + c]; };
+    // 4. per-voxel sequential spacing filter (AddPointWithSpacing), voxels in parallel
+    const double map_resolution = std::sqrt(voxel_size * voxel_size / cap);
+    std::vector<uint8_t> keep(total, 0);
+    std::vector<uint32_t> gcount(G, 0);
+    parallel_for(G, 4096, [&](size_t gb, size_t ge) {
+        std::vector<double> kept;
+        for (size_t g = gb; g < ge; ++g) {
+            kept.clear();
+            for (size_t i = gstart[g]; i < gstart[g + 1]; ++i) {
+                const uint32_t idx = recs[i].idx;
+                const double x = coord(idx, 0), y = coord(idx, 1), z = coord(idx, 2);
+                bool ok = true;
+                if (idx >= P0 && !kept.empty()) {          // first point of a voxel is always kept (vhm.cpp:281-283)
+                    if (kept.size() / 3 >= static_cast<size_t>(cap)) break;  // full: nothing later can enter
+                    for (size_t k = 0; k < kept.size(); k += 3) {
+                        const double dx = kept[k] - x, dy = kept[k + 1] - y, dz = kept[k + 2] - z;
+                        if (std::sqrt((dx * dx + dy * dy) + dz * dz) < map_resolution) { ok = false; break; }
+                    }
+                }
+                if (ok) { keep[i] = 1; kept.push_back(x); kept.push_back(y); kept.push_back(z); }
+            }
+            gcount[g] = static_cast<uint32_t>(kept.size() / 3);
+        }
+    });
+    // 5. compact into the canonical arrays
+    std::vector<uint64_t> nkey(G);
+    std::vector<uint32_t> nstart(G + 1, 0);
+    for (size_t g = 0; g < G; ++g) { nkey[g] = recs[gstart[g]].key; nstart[g + 1] = nstart[g] + gcount[g]; }
+    const size_t P1 = nstart[G];
+    std::vector<float> nxyz(3 * P1);
+    std::vector<uint32_t> norig(P1);
+    parallel_for(G, 4096, [&](size_t gb, size_t ge) {
+        for (size_t g = gb; g < ge; ++g) {
+            uint32_t o = nstart[g];
+            for (size_t i = gstart[g]; i < gstart[g + 1]; ++i) {
+                if (!keep[i]) continue;
+                const uint32_t idx = recs[i].idx;
+                nxyz[3 * o] = coord(idx, 0); nxyz[3 * o + 1] = coord(idx, 1); nxyz[3 * o + 2] = coord(idx, 2);
+                norig[o] = idx < P0 ? porig[idx] : static_cast<uint32_t>(n_raw_seen + (idx - P0));
+                ++o;
+            }
+        }
+    });
+    vkey.swap(nkey); vstart.swap(nstart); pxyz.swap(nxyz); porig.swap(norig);
+    n_raw_seen += n;
+    has_vcov = has_pcov = false;
+    vmean.clear(); vcov.clear(); pmean.clear(); pcov.clear(); pnormal.clear();
+    build_table();
+    return "";
+}
+
+void HostMap::build_table() {
+    size_t capacity = 16;
+    while (capacity < 2 * V()) capacity <<= 1;
+    mask = static_cast<uint32_t>(capacity - 1);
+    slots.assign(capacity, Slot{0xffffffffu, 0xffffffffu, 0, 0});
+    slot_voxel.assign(capacity, -1);
+    for (size_t v = 0; v < V(); ++v) {
+        uint32_t h = static_cast<uint32_t>(mix_key(vkey[v])) & mask;
+        while (slot_voxel[h] >= 0) h = (h + 1) & mask;
+        slots[h] = Slot{static_cast<uint32_t>(vkey[v]), static_cast<uint32_t>(vkey[v] >> 32), vstart[v], vstart[v + 1] - vstart[v]};
+        slot_voxel[h] = static_cast<int32_t>(v);
+    }
+}
+
+int64_t HostMap::find(uint64_t key) const {
+    if (slots.empty()) return -1;
+    uint32_t h = static_cast<uint32_t>(mix_key(key)) & mask;
+    for (;;) {
+        const int32_t v = slot_voxel[h];
+        if (v < 0) return -1;
+        if (vkey[v] == key) return v;
+        h = (h + 1) & mask;
+    }
+}
+
+// CalVoxelCovAll: n == 0 -> (I, 0) [cannot occur: a voxel exists only with >= 1 point]; n == 1 -> (I, p);
+// n >= 2 -> sample covariance /(n-1), regularised, with the mean.
+void HostMap::cal_voxel_cov() {
+    const size_t nv = V();
+    vmean.assign(3 * nv, 0.0);
+    vcov.assign(9 * nv, 0.0);
+    parallel_for(nv, 4096, [&](size_t b, size_t e) {
+        std::vector<double> buf;
+        for (size_t v = b; v < e; ++v) {
+            const uint32_t s = vstart[v], cnt = vstart[v + 1] - s;
+            double* m = &vmean[3 * v];
+            double* c = &vcov[9 * v];
+            if (cnt == 1) {
+                m[0] = pxyz[3 * s]; m[1] = pxyz[3 * s + 1]; m[2] = pxyz[3 * s + 2];
+                c[0] = c[4] = c[8] = 1.0;
+                continue;
+            }
+            buf.resize(3 * cnt);
+            for (uint32_t i = 0; i < 3 * cnt; ++i) buf[i] = pxyz[3 * s + i];
+            mean_cov_regularized(buf.data(), cnt, m, c, nullptr);
+        }
+    });
+    has_vcov = true;
+}
+
+// CalPointCovAll: per stored point, neighbours = {self} U {stored points of the 27 voxels around FLOOR(p / vs)
+// with d^2 <= r^2}; self is in that set too, so it is counted twice and n >= 2 always.
+void HostMap::cal_point_cov(double search_dist) {
+    const size_t np = P();
+    const double r2 = search_dist * search_dist;
+    pmean.assign(3 * np, 0.0);
+    pcov.assign(9 * np, 0.0);
+    pnormal.assign(3 * np, 0.0);
+    const double vs = voxel_size;
+    parallel_for(np, 8192, [&](size_t b, size_t e) {
+        std::vector<double> nb;
+        for (size_t p = b; p < e; ++p) {
+            const double x = pxyz[3 * p], y = pxyz[3 * p + 1], z = pxyz[3 * p + 2];
+            nb.clear();
+            nb.push_back(x); nb.push_back(y); nb.push_back(z);
+            const int32_t kx = static_cast<int32_t>(std::floor(x / vs)), ky = static_cast<int32_t>(std::floor(y / vs)),
+                          kz = static_cast<int32_t>(std::floor(z / vs));
+            for (int i = kx - 1; i <= kx + 1; ++i)
+                for (int j = ky - 1; j <= ky + 1; ++j)
+                    for (int k = kz - 1; k <= kz + 1; ++k) {
+                        if (!key_in_range(i) || !key_in_range(j) || !key_in_range(k)) continue;
+                        const int64_t v = find(pack_key(i, j, k));
+                        if (v < 0) continue;
+                        for (uint32_t q = vstart[v]; q < vstart[v + 1]; ++q) {
+                            const double dx = pxyz[3 * q] - x, dy = pxyz[3 * q + 1] - y, dz = pxyz[3 * q + 2] - z;
+                            if ((dx * dx + dy * dy) + dz * dz <= r2) { nb.push_back(pxyz[3 * q]); nb.push_back(pxyz[3 * q + 1]); nb.push_back(pxyz[3 * q + 2]); }
+                        }
+                    }
+            mean_cov_regularized(nb.data(), nb.size() / 3, &pmean[3 * p], &pcov[9 * p], &pnormal[3 * p]);
+        }
+    });
+    has_pcov = true;
+}
+
+}  // namespace elm

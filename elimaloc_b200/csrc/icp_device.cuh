@@ -1,0 +1,60 @@
+// Device-side data layout of the registration hot path (sm_100a).
+//
+// HBM layout of the map (built by host_map.cpp, uploaded by device_map.cu):
+//   slots   uint4[capacity]      open-addressed table, 16 B/slot {key_lo, key_hi, first point, count}; capacity = 2^k
+//                                >= 2 V; key = 3 x 21-bit biased voxel coordinates; empty = all ones; linear probing
+//   pts     float4[P]            stored points in canonical order (voxels sorted by (x,y,z), insertion order inside):
+//                                the voxels (x,y,z-1..z+1) of one column are ONE contiguous run; w = raw-index bits
+//   prec    double[16 P]         GICP record per stored point: mean[3] cov[9] normal[3] pad  (128 B, one line)
+//   vslots  double4[capacity]    VGICP/AVGICP: 32 B/slot {key bits, mean[3]} parallel to `slots` (same slot index)
+//   vcov    double[12 capacity]  VGICP/AVGICP: 96 B/slot {cov[9], pad[3]}
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace elm {
+
+struct MapView {
+    const uint4* slots;
+    const float4* pts;
+    const double* prec;
+    const double4* vslots;
+    const double* vcov;
+    uint32_t mask;
+    double voxel_size;
+};
+
+constexpr int kAcc = 32;       // accumulator vector: 21 JtJ (upper, row-major) + 6 Jtr + residual + n_corr + n_total + pad
+constexpr int kAccUsed = 30;
+constexpr int kIdxJtr = 21, kIdxRes = 27, kIdxNcorr = 28, kIdxNtotal = 29;
+
+struct IcpParams {
+    int method;
+    int n;              // scan points of THIS rank
+    int queries_per_warp;
+    double max_dist2;   // max_search_dist^2
+    double th;          // trans_th == max_search_dist (reg.cpp:360-373)
+    double lm_lambda;
+    double term_thr;
+    double min_overlap;
+};
+
+// Lives in HBM for the whole ICP loop; the host reads it back once at the end.
+struct IcpState {
+    double T[16];       // last_icp_pose
+    double Tinv[16];    // last_icp_pose.inverse()
+    double Rinv[9];     // last_icp_pose.block<3,3>(0,0).inverse()
+    double acc[kAcc];   // reduced accumulators of the current iteration (allreduced across ranks)
+    double JTJ[36];     // last linearisation, full symmetric (test hook)
+    double JTr[6];
+    double residual_sum;
+    double n_corr;
+    double fitness;     // Registration::d_fitness_score_ (persists across calls, reg.hpp:229)
+    double local_cov[36];
+    int iterations;     // AlignClouds* calls executed
+    int done;           // loop left (termination, overlap failure)
+    int overlap_fail;   // reg.cpp:352-356
+    int pad;
+};
+
+}  // namespace elm

@@ -1,0 +1,190 @@
+"""Host-side mirror of the reference's registration interface over the C ABI.
+
+Names, argument meaning and failure behaviour follow the reference
+(src/app/localization/pcm_matching/include/{registration,voxel_hash_map}.hpp):
+
+    VoxelHashMap.Init / AddPoints / CalVoxelCovAll / CalPointCovAll / Empty / Pointcloud / Covariances
+    Registration.Init / RunRegister
+
+so the parity tests read like tests of the reference.  All compute happens in libelimaloc_b200.so on the GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import AVGICP, GICP, P2P, VGICP, RegConfig, check, lib  # noqa: F401
+
+
+def RegistrationConfig(**kw):
+    """RegistrationConfig (registration.hpp:62-85); defaults = config/localization.ini:80-109 of the reference."""
+    d = dict(icp_method=GICP, max_iteration=10, max_thread=10, use_radar_cov=0, debug_print=0, reserved0=0,
+             max_search_dist=5.0, lm_lambda=0.5, icp_termination_threshold_m=0.02, min_overlap_ratio=0.4,
+             max_fitness_score=0.5, range_variance_m=1.0, azimuth_variance_deg=0.4, elevation_variance_deg=0.4)
+    d.update(kw)
+    return RegConfig(**d)
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _xyz(a):
+    return np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)
+
+
+def _pose(a):
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(4, 4)
+
+
+class VoxelHashMap:
+    """voxel_hash_map.hpp:89-335.  device=-1 builds a host-only map (builder tests on a machine without a GPU)."""
+
+    def __init__(self, voxel_size=1.0, max_points_per_voxel=30, device=0):
+        self._h = C.c_void_p()
+        self.device = device
+        self.Init(voxel_size, max_points_per_voxel)
+
+    def Init(self, voxel_size, max_points_per_voxel):
+        if self._h:
+            lib().elm_map_destroy(self._h)
+            self._h = C.c_void_p()
+        check(lib().elm_map_create(C.byref(self._h), float(voxel_size), int(max_points_per_voxel), int(self.device)))
+        self.voxel_size_ = float(voxel_size)
+        self.max_points_per_voxel_ = int(max_points_per_voxel)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().elm_map_destroy(self._h)
+            self._h = None
+
+    def AddPoints(self, xyz):
+        xyz = _xyz(xyz)
+        check(lib().elm_map_add_points(self._h, _f(xyz), xyz.shape[0]))
+
+    def CalVoxelCovAll(self):
+        check(lib().elm_map_cal_voxel_cov(self._h))
+
+    def CalPointCovAll(self, d_search_dist):
+        check(lib().elm_map_cal_point_cov(self._h, float(d_search_dist)))
+
+    def Empty(self):
+        return bool(lib().elm_map_empty(self._h))
+
+    def num_voxels(self):
+        return lib().elm_map_num_voxels(self._h)
+
+    def num_points(self):
+        return lib().elm_map_num_points(self._h)
+
+    def export(self, voxel_cov=False, point_cov=False):
+        V, P = self.num_voxels(), self.num_points()
+        out = dict(keys=np.zeros((V, 3), np.int32), counts=np.zeros(V, np.int32), pxyz=np.zeros((P, 3), np.float32))
+        vmean = vcov = pmean = pcov = None
+        if voxel_cov:
+            out["vmean"], out["vcov"] = np.zeros((V, 3)), np.zeros((V, 3, 3))
+            vmean, vcov = _d(out["vmean"]), _d(out["vcov"])
+        if point_cov:
+            out["pmean"], out["pcov"] = np.zeros((P, 3)), np.zeros((P, 3, 3))
+            pmean, pcov = _d(out["pmean"]), _d(out["pcov"])
+        check(lib().elm_map_export(self._h, _i(out["keys"]), _i(out["counts"]), vmean, vcov, _f(out["pxyz"]), pmean, pcov))
+        return out
+
+    def Pointcloud(self):
+        """voxel_hash_map.cpp:245-255 (canonical order instead of unordered_map iteration order)."""
+        return self.export()["pxyz"]
+
+    def Covariances(self):
+        """voxel_hash_map.cpp:257-265: covariances of voxels holding more than two points."""
+        e = self.export(voxel_cov=True)
+        keep = e["counts"] > 2
+        return e["vmean"][keep], e["vcov"][keep]
+
+
+class Registration:
+    """registration.hpp:101-230.  Holds the device scratch of the ICP loop and d_fitness_score_."""
+
+    def __init__(self, config=None, device=0, stream=None):
+        self._h = C.c_void_p()
+        self.device = device
+        check(lib().elm_registration_create(C.byref(self._h), int(device), C.c_void_p(stream) if stream else None))
+        self.config_ = config
+
+    def Init(self, config):
+        self.config_ = config
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().elm_registration_destroy(self._h)
+            self._h = None
+
+    def RunRegister(self, source_local, voxel_map, initial_guess, m_config=None, fitness_score=0.0):
+        """Returns (pose 4x4, is_success, fitness_score, local_cov 6x6); fitness_score is passed through
+        untouched on failure exactly like the reference's out-parameter (registration.cpp:415)."""
+        cfg = m_config if m_config is not None else self.config_
+        src = _xyz(source_local)
+        T0 = _pose(initial_guess)
+        T = np.zeros((4, 4))
+        ok = np.zeros(1, np.int32)
+        fit = np.array([fitness_score], np.float64)
+        cov = np.zeros((6, 6))
+        check(lib().elm_run_register(self._h, voxel_map._h, _f(src), src.shape[0], _d(T0), C.byref(cfg), _d(T), _i(ok),
+                                     _d(fit), _d(cov)))
+        return T, bool(ok[0]), float(fit[0]), cov
+
+    # ---- device-resident variant (what bench.py times as `value`) ----
+    def enqueue(self, d_src_ptr, n, voxel_map, initial_guess, cfg):
+        T0 = _pose(initial_guess)
+        check(lib().elm_register_enqueue(self._h, voxel_map._h, C.c_void_p(d_src_ptr), int(n), _d(T0), C.byref(cfg)))
+
+    def fetch(self, fitness_score=0.0):
+        T = np.zeros((4, 4))
+        ok = np.zeros(1, np.int32)
+        fit = np.array([fitness_score], np.float64)
+        cov = np.zeros((6, 6))
+        it = np.zeros(1, np.int32)
+        check(lib().elm_register_fetch(self._h, _d(T), _i(ok), _d(fit), _d(cov), _i(it)))
+        return T, bool(ok[0]), float(fit[0]), cov, int(it[0])
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        check(lib().elm_registration_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    # ---- test hooks ----
+    def linearize(self, source_local, voxel_map, pose, cfg):
+        src = _xyz(source_local)
+        T0 = _pose(pose)
+        JTJ, JTr, res = np.zeros((6, 6)), np.zeros(6), np.zeros(1)
+        nc = C.c_int64(0)
+        check(lib().elm_linearize(self._h, voxel_map._h, _f(src), src.shape[0], _d(T0), C.byref(cfg), _d(JTJ), _d(JTr),
+                                  _d(res), C.byref(nc)))
+        return dict(JTJ=JTJ, JTr=JTr, residual_sum=float(res[0]), n_corr=int(nc.value))
+
+    def correspondences(self, source_local, voxel_map, pose, method, max_dist):
+        src = _xyz(source_local)
+        T0 = _pose(pose)
+        K = 7 if method == AVGICP else 1
+        cnt = np.zeros(src.shape[0], np.int32)
+        tgt = np.zeros((src.shape[0], K, 3))
+        check(lib().elm_correspondences(self._h, voxel_map._h, _f(src), src.shape[0], _d(T0), int(method), float(max_dist),
+                                        _i(cnt), _d(tgt)))
+        return cnt, tgt
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib().elm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def set_comm(self, unique_id, rank, world_size):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().elm_registration_set_comm(self._h, buf, int(rank), int(world_size)))

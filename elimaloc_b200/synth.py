@@ -1,0 +1,60 @@
+"""Synthetic maps, scans and poses of BASELINE.md section 4 (numpy.random.default_rng; seeds: map 1234, scan 5678,
+pose 91011).  Shared by the tests and bench.py so both sides of every comparison see identical inputs."""
+import numpy as np
+
+SEED_MAP, SEED_SCAN, SEED_POSE = 1234, 5678, 91011
+
+
+def exp_so3(w):
+    w = np.asarray(w, dtype=np.float64)
+    th = np.linalg.norm(w)
+    if th < 1e-15:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def se3(t, w):
+    T = np.eye(4)
+    T[:3, :3] = exp_so3(w)
+    T[:3, 3] = t
+    return T
+
+
+def map_u(m_raw, box, seed=SEED_MAP, origin=0.0):
+    """Map-U: m_raw float32 points ~ U[origin, origin + box)^3 (about 10 raw points per 1 m voxel at the canonical
+    sizes: 100 k -> 21.5 m, 10 M -> 100 m, 50 M -> 171 m)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((m_raw, 3), dtype=np.float32)
+    step = 1 << 22
+    for i in range(0, m_raw, step):
+        n = min(step, m_raw - i)
+        out[i:i + n] = (rng.random((n, 3), dtype=np.float32) * np.float32(box) + np.float32(origin))
+    return out
+
+
+def scan_u(n, half_width, seed=SEED_SCAN):
+    """Scan-U (throughput): n float32 points uniform in a cube of the given half width around the sensor."""
+    rng = np.random.default_rng(seed)
+    return ((rng.random((n, 3), dtype=np.float32) * 2 - 1) * np.float32(half_width)).astype(np.float32)
+
+
+def scan_m(stored_xyz, n, T_true, noise=0.02, seed=SEED_SCAN):
+    """Scan-M (parity): n points drawn from the stored map points + N(0, noise^2), seen from pose T_true."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, stored_xyz.shape[0], n)
+    pts = stored_xyz[idx].astype(np.float64) + rng.normal(0.0, noise, (n, 3))
+    Ti = np.linalg.inv(T_true)
+    return (pts @ Ti[:3, :3].T + Ti[:3, 3]).astype(np.float32)
+
+
+def canonical_offset():
+    """initial_guess = T_true * Exp([0.30, -0.20, 0.10 m ; 0.5, -0.5, 1.0 deg])"""
+    return se3([0.30, -0.20, 0.10], np.deg2rad([0.5, -0.5, 1.0]))
+
+
+def timing_knobs():
+    """Knobs that force every iteration to run."""
+    return dict(icp_termination_threshold_m=0.0, min_overlap_ratio=0.0, max_fitness_score=1e30, lm_lambda=0.5,
+                max_search_dist=5.0, use_radar_cov=0, debug_print=0)

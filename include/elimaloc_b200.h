@@ -1,0 +1,145 @@
+/* elimaloc_b200 — C ABI of the B200-native pcm_matching registration hot path.
+ *
+ * Drop-in boundary for jaeyoungjo99/ELiMaLoc's per-scan registration.  The reference has no FFI layer:
+ * the boundary is the C++ member call
+ *     Eigen::Matrix4d Registration::RunRegister(const std::vector<PointStruct>&, const VoxelHashMap&,
+ *             const Eigen::Matrix4d&, RegistrationConfig, bool&, double&, Eigen::Matrix6d&)
+ *     (src/app/localization/pcm_matching/include/registration.hpp:122-124, src/registration.cpp:274-418)
+ * plus the map-side calls the node makes once at start-up (src/pcm_matching.cpp:82-101).
+ * shim/registration_shim.hpp re-declares those C++ types on top of this header so pcm_matching.cpp
+ * compiles unchanged; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every matrix is ROW-major double (Eigen is column-major: the shim transposes);
+ *   - every function returns an elm_status (0 = ok); a non-zero status never throws and leaves outputs untouched
+ *     unless stated; elm_last_error() gives the message of the calling thread's last failure;
+ *   - thread-agnostic: any thread may call; calls on one handle must be serialised by the caller (the node
+ *     already does: both call sites hold mutex_pcl_, pcm_matching.cpp:199,357);
+ *   - the product never falls back to a CPU path: without a CUDA device every compute entry point returns
+ *     ELM_ERR_CUDA.
+ * Reference paths below are relative to src/app/localization/ of the reference repository.
+ */
+#ifndef ELIMALOC_B200_H
+#define ELIMALOC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum elm_status {
+    ELM_OK = 0,
+    ELM_ERR_INVALID = 1,     /* bad argument (NULL, negative size, unknown method ...) */
+    ELM_ERR_CUDA = 2,        /* CUDA runtime error or no device */
+    ELM_ERR_NCCL = 3,        /* NCCL error or NCCL library not loadable */
+    ELM_ERR_UNSUPPORTED = 4, /* valid in the reference but out of scope here (use_radar_cov = 1) */
+    ELM_ERR_RANGE = 5,       /* map extent beyond +-2^20 voxels per axis */
+    ELM_ERR_STATE = 6        /* call order (e.g. GICP without elm_map_cal_point_cov) */
+} elm_status;
+
+/* IcpMethod, pcm_matching/include/registration.hpp:60 */
+enum { ELM_P2P = 0, ELM_GICP = 1, ELM_VGICP = 2, ELM_AVGICP = 3 };
+
+/* RegistrationConfig, pcm_matching/include/registration.hpp:62-85 — the fields RunRegister reads
+ * (registration.cpp:302-412).  voxel_search_method, doppler_trans_lambda, gicp_cov_search_dist and the ego_to_*
+ * members are parsed by the node but never read by the solver and are therefore not part of the ABI.
+ * Defaults: config/localization.ini:80-109. */
+typedef struct elm_reg_config {
+    int32_t icp_method;    /* ELM_P2P .. ELM_AVGICP */
+    int32_t max_iteration;
+    int32_t max_thread;    /* i_max_thread: CPU thread cap of the reference; ignored on the GPU */
+    int32_t use_radar_cov; /* must be 0 (ELM_ERR_UNSUPPORTED otherwise) */
+    int32_t debug_print;   /* b_debug_print: per-phase timings to stdout */
+    int32_t reserved0;
+    double max_search_dist;
+    double lm_lambda;
+    double icp_termination_threshold_m;
+    double min_overlap_ratio;
+    double max_fitness_score;
+    double range_variance_m;
+    double azimuth_variance_deg;
+    double elevation_variance_deg;
+} elm_reg_config;
+
+typedef struct elm_map elm_map;                   /* VoxelHashMap, voxel_hash_map.hpp:89-335 (device resident) */
+typedef struct elm_registration elm_registration; /* Registration, registration.hpp:101-230 (+ device scratch) */
+
+const char* elm_last_error(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int elm_device_count(void);
+
+/* ---- VoxelHashMap ------------------------------------------------------------------------------------------ */
+/* VoxelHashMap::Init (voxel_hash_map.cpp:26-29).  device = CUDA ordinal the map lives on. */
+int elm_map_create(elm_map** out, double voxel_size, int max_points_per_voxel, int device);
+void elm_map_destroy(elm_map* map);
+/* VoxelHashMap::AddPoints (voxel_hash_map.cpp:270-285) on packed float xyz[3*n] (Pcl2PointStruct, pcm_matching.hpp:
+ * 205-220, widens float fields to double, so float is lossless).  Same order-dependent semantics: insert key =
+ * truncation toward zero, first point of a voxel always kept, later ones iff below the cap and no stored point within
+ * sqrt(voxel_size^2 / cap).  May be called repeatedly; each call re-publishes the device copy. */
+int elm_map_add_points(elm_map* map, const float* xyz, size_t n);
+/* VoxelHashMap::CalVoxelCovAll (voxel_hash_map.hpp:183-193): needed before VGICP / AVGICP. */
+int elm_map_cal_voxel_cov(elm_map* map);
+/* VoxelHashMap::CalPointCovAll (voxel_hash_map.hpp:252-257): needed before GICP. */
+int elm_map_cal_point_cov(elm_map* map, double search_dist);
+/* VoxelHashMap::Empty (voxel_hash_map.hpp:325) */
+int elm_map_empty(const elm_map* map);
+size_t elm_map_num_voxels(const elm_map* map);
+size_t elm_map_num_points(const elm_map* map);
+/* Canonical dump (test hook; stands in for Pointcloud()/Covariances(), voxel_hash_map.cpp:245-265): voxels sorted
+ * by key (x, y, z), points in insertion order inside a voxel.  Any pointer may be NULL.
+ * keys[3V] counts[V] vmean[3V] vcov[9V] pxyz[3P] pmean[3P] pcov[9P] */
+int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* vmean, double* vcov, float* pxyz,
+                   double* pmean, double* pcov);
+
+/* ---- Registration ------------------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t (as void*) every kernel of this handle is launched on; NULL = a private stream. */
+int elm_registration_create(elm_registration** out, int device, void* stream);
+void elm_registration_destroy(elm_registration* reg);
+
+/* Registration::RunRegister (registration.cpp:274-418) — HOST buffers in, host results out, synchronous.
+ *   src_xyz[3*n]          source_local: sensor-frame points (pose == local on entry, pcm_matching.hpp:213-214)
+ *   T_init[16]            initial_guess
+ *   T_out[16]             return value
+ *   is_success            written on every return path exactly as the reference does
+ *   fitness_score         written only on success (registration.cpp:415)
+ *   local_cov[36]         Identity, overwritten by GICP only (registration.cpp:280,142)
+ * n == 0 is undefined in the reference (0/0 overlap ratio); here: is_success = 0, T_out = T_init. */
+int elm_run_register(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n,
+                     const double T_init[16], const elm_reg_config* cfg, double T_out[16], int32_t* is_success,
+                     double* fitness_score, double local_cov[36]);
+
+/* Same registration with the scan already resident in HBM (d_src_xyz = device pointer to packed float xyz[3*n]).
+ * Enqueues the whole ICP loop on the handle's stream and returns without synchronising; elm_register_fetch
+ * synchronises and returns the results of the last enqueue.  This is what bench.py times as `value`. */
+int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float* d_src_xyz, size_t n,
+                         const double T_init[16], const elm_reg_config* cfg);
+int elm_register_fetch(elm_registration* reg, double T_out[16], int32_t* is_success, double* fitness_score,
+                       double local_cov[36], int32_t* iterations_run);
+
+/* One correspondence search + one AlignClouds* accumulation at a fixed pose, no solve (test hook for per-iteration
+ * parity: registration.cpp:28-51 / 85-132 / 171-208).  Host buffers.  JTJ[36] full symmetric 6x6. */
+int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
+                  const elm_reg_config* cfg, double JTJ[36], double JTr[6], double* residual_sum, int64_t* n_corr);
+
+/* Correspondence dump (test hook for index-level parity of voxel_hash_map.cpp:31-206).  K = 7 for AVGICP else 1.
+ * count[n]; target[n*K*3]: matched map point (P2P/GICP) or voxel mean (VGICP/AVGICP); unmatched entries are 0. */
+int elm_correspondences(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
+                        int method, double max_search_dist, int32_t* count, double* target);
+
+/* Counters of the last enqueue (kernel launches issued on the stream; used by bench.py's gpu_launches). */
+int elm_registration_launch_count(const elm_registration* reg, int64_t* launches);
+
+/* ---- multi-GPU (one process per GPU; scan sharded over ranks, map replicated) --------------------------------- */
+/* unique_id: 128 bytes.  Rank 0 fills it with elm_comm_unique_id and hands it to the other ranks (bench.py uses
+ * torch.distributed for that); every rank then calls elm_registration_set_comm.  After that each RunRegister sums the
+ * 29 accumulators (21 JtJ + 6 Jtr + residual + count) over ranks with one ncclAllReduce per ICP iteration and `n`
+ * is this rank's shard. */
+int elm_comm_unique_id(uint8_t unique_id[128]);
+int elm_registration_set_comm(elm_registration* reg, const uint8_t unique_id[128], int rank, int world_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELIMALOC_B200_H */

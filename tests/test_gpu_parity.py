@@ -1,0 +1,97 @@
+"""GPU-vs-oracle parity of the registration hot path, called through the C ABI (via the ctypes mirror).
+
+Tolerances (BASELINE.json north_star): 1e-5 relative on JtJ / Jtr entries, 1e-4 relative on the final SE(3) pose;
+correspondences (integer/index work) bit-exact."""
+import numpy as np
+import pytest
+
+import elimaloc_b200 as E
+from elimaloc_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+METHODS = [E.P2P, E.GICP, E.VGICP, E.AVGICP]
+NAMES = {0: "P2P", 1: "GICP", 2: "VGICP", 3: "AVGICP"}
+
+
+def both_cfg(**kw):
+    return E.RegistrationConfig(**kw), O.make_config(**kw)
+
+
+@pytest.fixture(scope="module")
+def world():
+    """config 1 sizes: 100 k raw map points in a 21.5 m box straddling the origin (exercises Q1), 4096-point Scan-M."""
+    raw = synth.map_u(100_000, 21.5, origin=-6.0)
+    gm = E.VoxelHashMap(1.0, 30, device=0)
+    gm.AddPoints(raw)
+    gm.CalVoxelCovAll()
+    gm.CalPointCovAll(0.4)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    om.CalPointCovAll(0.4)
+    stored = gm.Pointcloud()
+    T_true = synth.se3([4.0, 5.0, 3.5], [0.02, -0.01, 0.3])
+    scan = synth.scan_m(stored, 4096, T_true)
+    T0 = T_true @ synth.canonical_offset()
+    return dict(gm=gm, om=om, scan=scan, T_true=T_true, T0=T0, greg=E.Registration(device=0), oreg=O.Registration())
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_map_build_matches_oracle(world):
+    ge, oe = world["gm"].export(True, True), world["om"].export()
+    for k in ("keys", "counts", "pxyz"):
+        assert np.array_equal(ge[k], oe[k]), k
+    for k in ("vmean", "vcov", "pmean", "pcov"):
+        assert np.abs(ge[k] - oe[k]).max() < 1e-9, k
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_correspondences_bit_exact(world, method):
+    for T in (world["T0"], world["T_true"]):
+        gc, gt = world["greg"].correspondences(world["scan"], world["gm"], T, method, 5.0)
+        oc, ot = O.correspondences(world["om"], world["scan"], T, method, 5.0)
+        assert np.array_equal(gc, oc), NAMES[method]
+        assert np.array_equal(gt, ot), NAMES[method]
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_single_iteration_linearization(world, method):
+    gcfg, ocfg = both_cfg(icp_method=method, **synth.timing_knobs())
+    g = world["greg"].linearize(world["scan"], world["gm"], world["T0"], gcfg)
+    o = world["oreg"].linearize(world["scan"], world["om"], world["T0"], ocfg)
+    assert g["n_corr"] == o["n_corr"]
+    assert rel_err(g["JTJ"], o["JTJ"]) < 1e-5
+    assert rel_err(g["JTr"], o["JTr"]) < 1e-5
+    assert abs(g["residual_sum"] - o["residual_sum"]) <= 1e-9 * max(1.0, abs(o["residual_sum"]))
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_full_registration_config1(world, method):
+    """BASELINE config 1 (all four methods): 10 forced iterations, final pose within 1e-4 relative of the oracle."""
+    gcfg, ocfg = both_cfg(icp_method=method, max_iteration=10, **synth.timing_knobs())
+    T, ok, fit, cov = world["greg"].RunRegister(world["scan"], world["gm"], world["T0"], gcfg)
+    o = world["oreg"].RunRegister(world["scan"], world["om"], world["T0"], ocfg)
+    assert ok == o["is_success"]
+    assert rel_err(T, o["pose"]) < 1e-4
+    assert abs(fit - o["fitness_score"]) <= 1e-6 * max(1.0, abs(o["fitness_score"]))
+    assert rel_err(cov, o["local_cov"]) < 1e-5
+    if method in (E.P2P, E.GICP):  # converges onto the true pose
+        err = np.linalg.inv(world["T_true"]) @ T
+        assert np.linalg.norm(err[:3, 3]) < 0.02
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_default_ini_config(world, method):
+    """The reference's own knobs (localization.ini): early termination + overlap + fitness gates."""
+    gcfg, ocfg = both_cfg(icp_method=method)
+    T, ok, fit, cov = world["greg"].RunRegister(world["scan"], world["gm"], world["T0"], gcfg, fitness_score=-1.0)
+    o = world["oreg"].RunRegister(world["scan"], world["om"], world["T0"], ocfg, fitness_in=-1.0)
+    assert ok == o["is_success"]
+    assert rel_err(T, o["pose"]) < 1e-4
+    assert abs(fit - o["fitness_score"]) <= 1e-6 * max(1.0, abs(o["fitness_score"]))
