@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the registration hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--method p2p|gicp|vgicp|avgicp]
+
+One "step" = one RunRegister call: 20 forced ICP iterations (search + accumulate + solve) of a 131 072-point
+synthetic Scan-U against the 10 M-raw-point Map-U.  Prints ONE JSON line.
+
+  value      ICP iterations/s with the scan already resident in HBM (CUDA events around K enqueued steps)
+  e2e        the same metric through the host-buffer C-ABI call elm_run_register (pinned host scan, H2D + D2H inside)
+  roofline   dominant kernel (fused search+accumulate) : algorithmic bytes / its CUDA-event time vs measured HBM peak
+  cpu_baseline   the oracle (structure-faithful CPU port of the reference) on the box's host cores, bounded sample
+
+N > 1 (torchrun): the scan is sharded over ranks, the map replicated, one ncclAllReduce of the 30 accumulators per
+iteration (strong scaling of the fixed 131 072-point scan).
+--impl reference: times the oracle port of the reference's CPU path (the reference itself cannot be built here:
+no Eigen/TBB/PCL/ROS), search parallel over host threads + serial accumulate exactly like the reference.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METHOD_IDS = {"p2p": 0, "gicp": 1, "vgicp": 2, "avgicp": 3}
+N_SCAN = 131072
+M_RAW = 10_000_000
+BOX = 100.0
+ITERS = 20
+SCAN_HALF_WIDTH = 40.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--method", default="p2p", choices=list(METHOD_IDS))
+    ap.add_argument("--n-scan", type=int, default=N_SCAN)
+    ap.add_argument("--m-raw", type=int, default=M_RAW)
+    ap.add_argument("--box", type=float, default=BOX)
+    ap.add_argument("--iters", type=int, default=ITERS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=2, help="ICP iterations per CPU-baseline sample")
+    ap.add_argument("--exhaustive", action="store_true",
+                    help="visit all 27 voxels like the reference instead of the exact-pruning search")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload(args):
+    from elimaloc_b200 import synth
+    raw = synth.map_u(args.m_raw, args.box)
+    centre = args.box / 2.0
+    half = min(SCAN_HALF_WIDTH, 0.4 * args.box)
+    T_init = synth.se3([centre, centre, centre], np.deg2rad([1.0, -2.0, 30.0]))
+    return raw, half, T_init
+
+
+def neighbourhood_stats(keys, counts, scan, T, voxel_size):
+    """Measured sum of stored points / non-empty voxels over the 27 (and 7) probed voxels of the actual queries."""
+    p = scan.astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    k = np.floor(p / voxel_size).astype(np.int64)
+    lo = keys.min(axis=0).astype(np.int64) - 2
+    hi = keys.max(axis=0).astype(np.int64) + 3
+    dims = (hi - lo)
+    if np.prod(dims.astype(np.float64)) > 4e8:
+        return None
+    grid = np.zeros(tuple(dims), dtype=np.int32)
+    kk = keys.astype(np.int64) - lo
+    grid[kk[:, 0], kk[:, 1], kk[:, 2]] = counts
+    k = np.clip(k - lo, 1, dims - 2)
+    s27 = np.zeros(len(k), np.int64)
+    v27 = np.zeros(len(k), np.int64)
+    v7 = np.zeros(len(k), np.int64)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                c = grid[k[:, 0] + dx, k[:, 1] + dy, k[:, 2] + dz]
+                s27 += c
+                v27 += (c > 0)
+                if abs(dx) + abs(dy) + abs(dz) <= 1:
+                    v7 += (c > 0)
+    return dict(sum27=float(s27.mean()), v27=float(v27.mean()), v7=float(v7.mean()))
+
+
+def algorithmic_bytes_per_search(method, st):
+    """slot 16 B, scan/map xyz 12 B, mean 24 B, cov 72 B."""
+    if method == 0:
+        return 12 + 27 * 16 + 12 * st["sum27"]
+    if method == 1:
+        return 12 + 27 * 16 + 12 * st["sum27"] + 96
+    if method == 2:
+        return 12 + 27 * 16 + 24 * st["v27"] + 72
+    return 12 + 7 * 16 + 96 * st["v7"]
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_arm(args, raw, scan, T_init, method, steps, warmup, iters_per_sample):
+    """The reference's CPU structure (oracle port): parallel search, serial AlignClouds* and TransformPoints."""
+    from elimaloc_b200 import synth
+    from oracle import oracle as O
+    threads = min(os.cpu_count() or 1, 64)
+    om = O.VoxelHashMap(1.0, 30)
+    t0 = time.time()
+    om.AddPoints(raw)
+    if method in (2, 3):
+        om.CalVoxelCovAll()
+    if method == 1:
+        om.CalPointCovAll(0.4)
+    build_s = time.time() - t0
+    cfg = O.make_config(icp_method=method, max_iteration=iters_per_sample, max_thread=threads, **synth.timing_knobs())
+    reg = O.Registration()
+    for _ in range(warmup):
+        reg.time_register(scan, om, T_init, cfg)
+    tot_s, tot_it = 0.0, 0
+    for _ in range(steps):
+        s, it = reg.time_register(scan, om, T_init, cfg)
+        tot_s += s
+        tot_it += it
+    return dict(value=tot_it / tot_s, seconds=tot_s, iterations=tot_it, threads=threads, build_s=build_s)
+
+
+def main():
+    args = parse()
+    method = METHOD_IDS[args.method]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.method.upper()} ICP, {args.n_scan}-pt Scan-U vs {args.m_raw}-raw-pt Map-U "
+                          f"({args.box:g} m box, voxel 1.0 m, cap 30), {args.iters} forced iterations per step",
+              "n_scan": args.n_scan, "m_raw": args.m_raw, "iterations_per_step": args.iters, "method": args.method}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        raw, half, T_init = workload(args)
+        from elimaloc_b200 import synth
+        scan = synth.scan_u(args.n_scan, half)
+        r = cpu_arm(args, raw, scan, T_init, method, max(1, args.steps), args.warmup, args.cpu_iters)
+        sample = (f"oracle port of the reference CPU path (reference not buildable here: no Eigen/TBB/PCL/ROS); "
+                  f"each step = RunRegister with {args.cpu_iters} forced iterations on the full workload, "
+                  f"{r['threads']} OpenMP threads for the search, serial accumulate as in the reference")
+        out = {"impl": "reference", "metric": "icp_iterations_per_sec", "value": r["value"], "unit": "iterations/s",
+               "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": "port",
+                                "sample": sample},
+               "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import elimaloc_b200 as E
+    from elimaloc_b200 import synth
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    raw, half, T_init = workload(args)
+    t0 = time.time()
+    gmap = E.VoxelHashMap(1.0, 30, device=local_rank)
+    gmap.AddPoints(raw)
+    if method in (2, 3):
+        gmap.CalVoxelCovAll()
+    if method == 1:
+        gmap.CalPointCovAll(0.4)
+    build_s = time.time() - t0
+
+    stream = torch.cuda.Stream(device=local_rank)  # a real (non-NULL) stream: all our kernels and the events share it
+    torch.cuda.set_stream(stream)
+    reg = E.Registration(device=local_rank, stream=stream.cuda_stream)
+    reg.set_exhaustive(args.exhaustive)
+    if world > 1:
+        ids = [E.Registration.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        reg.set_comm(ids[0], rank, world)
+
+    # a different scan per step so that no step re-reads what the previous one left in L2; all resident in HBM
+    n_variants = 4
+    scans_full = [synth.scan_u(args.n_scan, half, seed=synth.SEED_SCAN + i) for i in range(n_variants)]
+    lo = args.n_scan * rank // world
+    hi = args.n_scan * (rank + 1) // world
+    shards = [np.ascontiguousarray(s[lo:hi]) for s in scans_full]
+    d_scans = [torch.from_numpy(s).cuda() for s in shards]
+    h_scans = [torch.from_numpy(s).pin_memory() for s in shards]
+    n_local = hi - lo
+    cfg = E.RegistrationConfig(icp_method=method, max_iteration=args.iters, **synth.timing_knobs())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm (value)
+    for i in range(args.warmup):
+        reg.enqueue(d_scans[i % n_variants].data_ptr(), n_local, gmap, T_init, cfg)
+    res = reg.fetch() if args.warmup > 0 else None
+    launches_per_step = reg.launch_count() if args.warmup > 0 else 1 + 2 * args.iters
+    reg.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record(stream)
+    for i in range(args.steps):
+        reg.enqueue(d_scans[i % n_variants].data_ptr(), n_local, gmap, T_init, cfg)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    res = reg.fetch()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    search_ms, accum_ms, prof_iters = reg.profile()
+    reg.set_profiling(False)
+    # untimed pass with the search counters on: map points the search really had to visit
+    visited_per_search = None
+    if method < 2:
+        reg.set_stats(True)
+        reg.enqueue(d_scans[0].data_ptr(), n_local, gmap, T_init, cfg)
+        reg.fetch()
+        vis, nq = reg.stats()
+        reg.set_stats(False)
+        visited_per_search = vis / max(nq, 1)
+    iters_total = args.steps * args.iters
+    value = iters_total / (ms_total * 1e-3)
+
+    # ---- end-to-end arm: host buffers through elm_run_register (H2D of the scan + D2H of the result every step)
+    import ctypes as C
+    from elimaloc_b200 import _capi
+    lib = _capi.lib()
+    Tin = np.ascontiguousarray(T_init, dtype=np.float64)
+    Tout, ok, fit, cov = np.zeros((4, 4)), np.zeros(1, np.int32), np.zeros(1), np.zeros((6, 6))
+    dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+    def run_host(i):
+        h = h_scans[i % n_variants]
+        _capi.check(lib.elm_run_register(reg._h, gmap._h, C.cast(h.data_ptr(), fp), n_local, Tin.ctypes.data_as(dp),
+                                         C.byref(cfg), Tout.ctypes.data_as(dp), ok.ctypes.data_as(ip),
+                                         fit.ctypes.data_as(dp), cov.ctypes.data_as(dp)))
+
+    for i in range(args.warmup):
+        run_host(i)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        run_host(i)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = iters_total / (e2e_ms * 1e-3)
+    state_bytes = 16 * 8 * 2 + 9 * 8 + 32 * 8 + 36 * 8 + 6 * 8 + 3 * 8 + 36 * 8 + 16  # sizeof(IcpState)
+
+    # ---- roofline of the dominant kernel (rank 0's shard)
+    peak, peak_src = load_peaks()
+    ex = gmap.export()
+    st = neighbourhood_stats(ex["keys"], ex["counts"], shards[0], T_init, 1.0)
+    roofline = None
+    if st and prof_iters:
+        # Algorithmic bytes per search (SURVEY.md 8(d) units: slot 16 B, xyz 12 B, mean 24 B, cov 72 B).  For the
+        # exact-pruning P2P/GICP search the map points that must be read are the ones of the voxels that cannot be
+        # excluded (measured by the kernel's own counter); `exhaustive_*` keeps the reference algorithm's figure.
+        bps_exh = algorithmic_bytes_per_search(method, st)
+        bps = bps_exh
+        if visited_per_search is not None and not args.exhaustive:
+            bps = bps_exh - 12 * st["sum27"] + 12 * visited_per_search
+        dom_ms = (search_ms if method != 3 else accum_ms) / prof_iters
+        achieved = bps * n_local / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None,
+                    "kernel": {0: "icp_search_points_kernel", 1: "icp_search_points_kernel", 2: "icp_search_means_kernel",
+                               3: "icp_accumulate_kernel<3>"}[method],
+                    "kernel_ms_avg": dom_ms, "kernel_launches": prof_iters,
+                    "kernel_share_of_step": (search_ms if method != 3 else accum_ms) / ms_total,
+                    "accumulate_kernel_ms_avg": accum_ms / prof_iters,
+                    "algorithmic_bytes_per_search": bps, "searches_per_launch": n_local,
+                    "search_mode": "exhaustive-27" if args.exhaustive else "exact-pruning",
+                    "map_points_visited_per_search": visited_per_search,
+                    "exhaustive_bytes_per_search": bps_exh,
+                    "exhaustive_equivalent_gbs": bps_exh * n_local / (dom_ms * 1e-3) / 1e9,
+                    "mean_stored_points_in_27_voxels": st["sum27"], "mean_nonempty_voxels_27": st["v27"],
+                    "mean_nonempty_voxels_7": st["v7"], "peak_source": peak_src}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(args, raw, scans_full[0], T_init, method, 2, 1, args.cpu_iters)
+        cpu = {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": "port",
+               "sample": f"2 RunRegister calls x {args.cpu_iters} forced iterations of the same workload "
+                         f"(oracle port; search on {r['threads']} OpenMP threads, accumulate serial as in the reference); "
+                         f"oracle map build {r['build_s']:.1f} s not timed"}
+
+    if rank == 0:
+        out = {"metric": "icp_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": dict(config, parallelism=f"scan sharded over {world} GPU(s), map replicated",
+                              l2_policy="inputs larger than L2 (map + table > 126 MB) and a different scan every step",
+                              searches_per_sec=value * args.n_scan, map_build_s=build_s,
+                              stored_points=int(ex["counts"].sum()), voxels=int(len(ex["counts"])),
+                              iterations_run_last_step=res[4], success_last_step=res[1]),
+               "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": n_local * 12,
+                       "d2h_bytes_per_step": state_bytes, "ms_per_step": e2e_ms / args.steps},
+               "gpu_launches": launches_per_step * args.steps,
+               "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,9 +102,10 @@ struct elm_map {
         ELM_CUDA(cudaSetDevice(device));
         const size_t S = host.slots.size();
         std::vector<double> vs(4 * S, 0.0), vc(12 * S, 0.0);
+        const uint64_t empty = elm::kEmptyKey;
         for (size_t s = 0; s < S; ++s) {
             const int32_t v = host.slot_voxel[s];
-            if (v < 0) continue;
+            if (v < 0) { std::memcpy(&vs[4 * s], &empty, 8); continue; }
             std::memcpy(&vs[4 * s], &host.vkey[v], 8);
             for (int k = 0; k < 3; ++k) vs[4 * s + 1 + k] = host.vmean[3 * v + k];
             for (int k = 0; k < 9; ++k) vc[12 * s + k] = host.vcov[9 * v + k];
@@ -143,12 +144,24 @@ struct elm_registration {
     elm::IcpState* h_state = nullptr;  // pinned
     double* d_partials = nullptr;
     int partial_rows = 0;
+    int* d_match = nullptr;
+    size_t match_cap = 0;
+    unsigned int* d_ticket = nullptr;
+    unsigned long long* d_stats = nullptr;  // [visited map points, queries] when stats are on
+    bool stats_on = false;
+    int prune = 1;  // exact pruning of voxels that cannot hold the nearest neighbour (0 = visit all 27 like the reference)
     float* d_scan = nullptr;
     size_t scan_cap = 0;
     int* d_count = nullptr;
     double* d_target = nullptr;
     size_t hook_cap = 0;
     int64_t launches = 0;
+    // optional per-kernel timing of the linearisation kernel (cudaEvents on the launch stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;
+    int ev_used = 0;
+    double prof_search_ms = 0.0, prof_accum_ms = 0.0;
+    int64_t prof_launches = 0;
     // last enqueue
     bool pending = false, trivial = false;  // trivial: empty map or n == 0 -> no kernels ran
     elm_reg_config cfg{};
@@ -160,7 +173,8 @@ struct elm_registration {
     ~elm_registration() {
         cudaSetDevice(device);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_ticket); cudaFree(d_stats); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -184,6 +198,17 @@ int ensure_partials(elm_registration* r, int rows) {
         r->d_partials = nullptr;
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_partials), static_cast<size_t>(rows) * elm::kAcc * sizeof(double)));
         r->partial_rows = rows;
+    }
+    return ELM_OK;
+}
+
+int ensure_match(elm_registration* r, size_t n) {
+    if (n > r->match_cap) {
+        if (r->d_match) cudaFree(r->d_match);
+        r->d_match = nullptr;
+        const size_t cap = (n + 1023) / 1024 * 1024;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_match), cap * sizeof(int)));
+        r->match_cap = cap;
     }
     return ELM_OK;
 }
@@ -225,23 +250,60 @@ elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg,
     p.lm_lambda = cfg->lm_lambda;
     p.term_thr = cfg->icp_termination_threshold_m;
     p.min_overlap = cfg->min_overlap_ratio;
+    p.stats = r->stats_on ? r->d_stats : nullptr;
     return p;
 }
 
-// one linearisation: kernel -> fixed-order reduction -> (allreduce over ranks)
-int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm) {
-    const int grid = elm::icp_linearize_grid(prm, r->num_sms);
-    int rc = ensure_partials(r, grid);
+// one linearisation: search kernel -> accumulate kernel (its last block reduces in a fixed order and, on a single
+// GPU, also solves) -> multi-GPU: allreduce of the 30 sums over ranks, then the solve kernel
+int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm, bool solve) {
+    const int sgrid = elm::icp_search_grid(prm, r->num_sms);
+    const int agrid = elm::icp_accumulate_grid(prm, r->num_sms);
+    int rc = ensure_partials(r, agrid);
     if (rc) return rc;
-    ELM_CUDA(elm::launch_icp_linearize(map->view(), d_scan, prm, r->d_state, r->d_partials, grid, r->stream));
-    ELM_CUDA(elm::launch_icp_reduce(r->d_state, r->d_partials, grid, r->stream));
-    r->launches += 2;
+    rc = ensure_match(r, prm.n);
+    if (rc) return rc;
+    if (r->profiling) {
+        while (static_cast<int>(r->ev.size()) < r->ev_used + 3) {
+            cudaEvent_t e;
+            ELM_CUDA(cudaEventCreate(&e));
+            r->ev.push_back(e);
+        }
+        ELM_CUDA(cudaEventRecord(r->ev[r->ev_used], r->stream));
+    }
+    if (prm.method != ELM_AVGICP) {
+        ELM_CUDA(elm::launch_icp_search(map->view(), d_scan, prm, r->d_state, r->d_match, sgrid, r->prune, r->stream));
+        r->launches += 1;
+    }
+    if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
+    const int solve_here = (solve && !r->comm) ? 1 : 0;
+    ELM_CUDA(elm::launch_icp_accumulate(map->view(), d_scan, r->d_match, prm, r->d_state, r->d_partials, r->d_ticket, solve_here, agrid, r->stream));
+    r->launches += 1;
+    if (r->profiling) {
+        ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 2], r->stream));
+        r->ev_used += 3;
+    }
     if (r->comm) {
         const int e = g_nccl.AllReduce(r->d_state->acc, r->d_state->acc, elm::kAcc, kNcclFloat64, kNcclSum, r->comm, r->stream);
         if (e != 0) return fail(ELM_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(e));
         r->launches += 1;
+        if (solve) {
+            ELM_CUDA(elm::launch_icp_solve(r->d_state, prm, r->stream));
+            r->launches += 1;
+        }
     }
     return ELM_OK;
+}
+
+void collect_profile(elm_registration* reg) {
+    for (int i = 0; i + 2 < reg->ev_used; i += 3) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, reg->ev[i], reg->ev[i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&b, reg->ev[i + 1], reg->ev[i + 2]) == cudaSuccess) {
+            reg->prof_search_ms += a; reg->prof_accum_ms += b; reg->prof_launches += 1;
+        }
+    }
+    reg->ev_used = 0;
 }
 
 }  // namespace
@@ -329,7 +391,9 @@ int elm_registration_create(elm_registration** out, int device, void* stream) {
         if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) { delete r; return fail(ELM_ERR_CUDA, "cudaStreamCreate failed"); }
         r->own_stream = true;
     }
-    if (cudaMalloc(reinterpret_cast<void**>(&r->d_state), sizeof(elm::IcpState)) != cudaSuccess ||
+    if (cudaMalloc(reinterpret_cast<void**>(&r->d_ticket), sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(r->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&r->d_state), sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMemset(r->d_state, 0, sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&r->h_state), sizeof(elm::IcpState)) != cudaSuccess) {
         delete r;
@@ -359,13 +423,11 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     reg->trivial = map->host.vkey.empty() || (n == 0 && !reg->comm);
     if (reg->trivial) return ELM_OK;
     const elm::IcpParams prm = make_params(reg, cfg, n);
-    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->stream));
+    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->d_ticket, reg->stream));
     reg->launches += 1;
     for (int j = 0; j < cfg->max_iteration; ++j) {  // reg.cpp:310
-        rc = enqueue_linearize(reg, map, d_src_xyz, prm);
+        rc = enqueue_linearize(reg, map, d_src_xyz, prm, true);
         if (rc) return rc;
-        ELM_CUDA(elm::launch_icp_solve(reg->d_state, prm, reg->stream));
-        reg->launches += 1;
     }
     ELM_CUDA(cudaMemcpyAsync(reg->h_state, reg->d_state, sizeof(elm::IcpState), cudaMemcpyDeviceToHost, reg->stream));
     return ELM_OK;
@@ -385,6 +447,7 @@ int elm_register_fetch(elm_registration* reg, double T_out[16], int32_t* is_succ
         return ELM_OK;
     }
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    if (reg->profiling) collect_profile(reg);
     const elm::IcpState& st = *reg->h_state;
     std::memcpy(T_out, st.T, 16 * sizeof(double));
     if (local_cov) std::memcpy(local_cov, st.local_cov, 36 * sizeof(double));
@@ -434,8 +497,8 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     if (rc) return rc;
     if (n) ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
     const elm::IcpParams prm = make_params(reg, cfg, n);
-    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->stream));
-    rc = enqueue_linearize(reg, map, reg->d_scan, prm);
+    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
+    rc = enqueue_linearize(reg, map, reg->d_scan, prm, false);
     if (rc) return rc;
     ELM_CUDA(cudaMemcpyAsync(reg->h_state, reg->d_state, sizeof(elm::IcpState), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
@@ -471,7 +534,7 @@ int elm_correspondences(elm_registration* reg, const elm_map* map, const float* 
     }
     ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
     ELM_CUDA(elm::launch_icp_match(map->view(), reg->d_scan, static_cast<int>(n), T, method, max_search_dist * max_search_dist,
-                                   reg->d_count, reg->d_target, reg->num_sms, reg->stream));
+                                   reg->prune, reg->d_count, reg->d_target, reg->num_sms, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(count, reg->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(target, reg->d_target, n * K * 3 * sizeof(double), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
@@ -481,6 +544,50 @@ int elm_correspondences(elm_registration* reg, const elm_map* map, const float* 
 int elm_registration_launch_count(const elm_registration* reg, int64_t* launches) {
     if (!reg || !launches) return fail(ELM_ERR_INVALID, "bad argument");
     *launches = reg->launches;
+    return ELM_OK;
+}
+
+int elm_registration_set_profiling(elm_registration* reg, int enable) {
+    if (!reg) return fail(ELM_ERR_INVALID, "null registration");
+    reg->profiling = enable != 0;
+    reg->ev_used = 0;
+    reg->prof_search_ms = reg->prof_accum_ms = 0.0;
+    reg->prof_launches = 0;
+    return ELM_OK;
+}
+
+int elm_registration_profile(const elm_registration* reg, double* search_ms, double* accumulate_ms, int64_t* iterations) {
+    if (!reg || !search_ms || !accumulate_ms || !iterations) return fail(ELM_ERR_INVALID, "bad argument");
+    *search_ms = reg->prof_search_ms;
+    *accumulate_ms = reg->prof_accum_ms;
+    *iterations = reg->prof_launches;
+    return ELM_OK;
+}
+
+int elm_registration_set_stats(elm_registration* reg, int enable) {
+    if (!reg) return fail(ELM_ERR_INVALID, "null registration");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (!reg->d_stats) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_stats), 2 * sizeof(unsigned long long)));
+    ELM_CUDA(cudaMemsetAsync(reg->d_stats, 0, 2 * sizeof(unsigned long long), reg->stream));
+    reg->stats_on = enable != 0;
+    return ELM_OK;
+}
+
+int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, uint64_t* queries) {
+    if (!reg || !map_points_visited || !queries) return fail(ELM_ERR_INVALID, "bad argument");
+    if (!reg->d_stats) return fail(ELM_ERR_STATE, "stats were never enabled");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    unsigned long long h[2] = {0, 0};
+    ELM_CUDA(cudaMemcpyAsync(h, reg->d_stats, sizeof h, cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    *map_points_visited = h[0];
+    *queries = h[1];
+    return ELM_OK;
+}
+
+int elm_registration_set_exhaustive(elm_registration* reg, int exhaustive) {
+    if (!reg) return fail(ELM_ERR_INVALID, "null registration");
+    reg->prune = exhaustive ? 0 : 1;
     return ELM_OK;
 }
 

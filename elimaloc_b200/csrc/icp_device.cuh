@@ -37,6 +37,7 @@ struct IcpParams {
     double lm_lambda;
     double term_thr;
     double min_overlap;
+    unsigned long long* stats;  // optional: [0] += map points visited by the search, [1] += queries (NULL = off)
 };
 
 // Lives in HBM for the whole ICP loop; the host reads it back once at the end.

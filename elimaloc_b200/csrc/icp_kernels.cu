@@ -1,20 +1,22 @@
-// Hand-written sm_100a kernels of the ICP hot loop.
+// Hand-written sm_100a kernels of the ICP hot loop.  One ICP iteration = two launches:
 //
-//   icp_begin_kernel        state <- initial guess (+ inverse)                     reg.cpp:298,24,79
-//   icp_points_kernel<M>    P2P / GICP : TransformPoints + GetCorrespondencePoints + AlignCloudsLocal{,PointCov}
-//                           accumulation, fused                                     reg.hpp:136-148, vhm.cpp:31-88,
-//                                                                                   reg.cpp:28-51 / 85-132
-//   icp_voxels_kernel<M>    VGICP / AVGICP : TransformPoints + GetCorrespondences{Cov,AllCov} +
-//                           AlignCloudsLocalVoxelCov accumulation, fused            vhm.cpp:90-206, reg.cpp:171-208
-//   icp_reduce_kernel       per-block partials -> 30 accumulators (fixed order)     (multi-GPU: followed by ncclAllReduce)
-//   icp_solve_kernel        overlap gate, LM-damped LDLT solve, exp map, pose update, termination test
-//                                                                                   reg.cpp:349-356, 53-65, 136-151, 378-387
-//   icp_match_kernel        correspondence dump for the parity tests
+//   icp_search_points_kernel   P2P/GICP  TransformPoints + GetCorrespondencePoints     reg.hpp:136-148, vhm.cpp:31-88
+//   icp_search_means_kernel    VGICP     TransformPoints + GetCorrespondencesCov       vhm.cpp:90-151
+//        -> match[n]: index of the winning map point / voxel slot (4 B per scan point, never the 168-B structs)
+//   icp_accumulate_kernel<M>   AlignCloudsLocal{,PointCov,VoxelCov} accumulation        reg.cpp:28-51 / 85-132 / 171-208
+//        (AVGICP searches its 7 voxels inside this kernel, vhm.cpp:153-206), block tree reduction, and in the LAST
+//        block to finish: fixed-order reduction of all partials + the solve/update step below
+//   icp_solve_kernel           overlap gate, LM-damped LDLT solve, exp map, pose update, termination test
+//        (reg.cpp:349-356, 53-65, 136-151, 378-387) — separate launch only in multi-GPU mode, after the ncclAllReduce
+//   icp_begin_kernel           state <- initial guess (+ inverses)                      reg.cpp:298,24,79
+//   icp_match_kernel           correspondence dump for the parity tests
 //
-// Exactness: the transformed scan point, its voxel key and every candidate distance are computed in fp64 with
-// explicit round-to-nearest mul/add (never contracted into FMA) in the same association order as the CPU reference,
-// so the nearest-neighbour choice — including its first-in-visit-order tie-break — is bit-identical to the reference.
-// The accumulation that follows is plain fp64 (FMA allowed); it is compared with a tolerance.
+// Exactness: the transformed scan point, its voxel key and every candidate distance are computed in fp64 with explicit
+// round-to-nearest mul/add (never contracted into FMA) in the same association order as the CPU reference, so the
+// nearest-neighbour choice — including its first-in-visit-order tie-break — is bit-identical to the reference.
+// The search may skip voxels whose bounding box is provably farther than the best candidate found so far (exact
+// pruning: identical result, fewer bytes); `prune = 0` visits all 27 voxels like the reference does.
+// The accumulation that follows is plain fp64 (FMA allowed) and is compared with a tolerance.
 #include "icp_kernels.cuh"
 
 namespace elm {
@@ -24,6 +26,7 @@ namespace {
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kKeyBits = 21;
 constexpr int kKeyBias = 1 << (kKeyBits - 1);
+constexpr double kDblMax = 1.7976931348623157e308;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -57,10 +60,13 @@ __device__ __forceinline__ double sq3_exact(double dx, double dy, double dz) {  
 __device__ __forceinline__ double row_apply_exact(const double* T, int r, double x, double y, double z) {
     return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4 * r], x), __dmul_rn(T[4 * r + 1], y)), __dmul_rn(T[4 * r + 2], z)), T[4 * r + 3]);
 }
-__device__ __forceinline__ int voxel_floor(double p, double vs) {  // PointToVoxel, vhm.hpp:176-180
-    const double q = floor(__ddiv_rn(p, vs));
+// PointToVoxel (vhm.hpp:176-180): floor(p / vs); also returns the in-cell fraction (for the pruning bound)
+__device__ __forceinline__ int voxel_floor(double p, double vs, float* frac = nullptr) {
+    const double q = __ddiv_rn(p, vs);
+    const double f = floor(q);
+    if (frac) *frac = static_cast<float>(q - f);
     // saturate far outside the table's key range instead of the reference's undefined int overflow
-    return (q >= 2.0e9) ? 2000000000 : ((q <= -2.0e9) ? -2000000000 : static_cast<int>(q));
+    return (f >= 2.0e9) ? 2000000000 : ((f <= -2.0e9) ? -2000000000 : static_cast<int>(f));
 }
 __device__ __forceinline__ bool key_ok(int k) { return k >= -kKeyBias && k < kKeyBias; }
 __device__ __forceinline__ uint64_t pack_key(int x, int y, int z) {
@@ -72,21 +78,48 @@ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {  // murmur3 finaliser
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return static_cast<uint32_t>(k);
 }
-// Linear probe; returns the slot index or -1.  start/count filled on a hit.
+// Linear probe of the 16-B table; returns the slot index or -1.  start/count filled on a hit.
 __device__ __forceinline__ int probe(const uint4* __restrict__ slots, uint32_t mask, uint64_t key, uint32_t& start, uint32_t& count) {
     uint32_t h = hash_key(key) & mask;
     const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
-    for (;;) {
+    for (uint32_t i = 0; i <= mask; ++i) {  // bounded: a corrupt table must never hang the GPU
         const uint4 s = __ldg(slots + h);
         if (s.x == klo && s.y == khi) { start = s.z; count = s.w; return static_cast<int>(h); }
         if ((s.x & s.y) == 0xffffffffu) return -1;
         h = (h + 1) & mask;
     }
+    return -1;
+}
+// Same probe when the first slot has already been fetched (software-pipelined across queries).
+__device__ __forceinline__ void probe_resume(const uint4* __restrict__ slots, uint32_t mask, uint64_t key, uint32_t h, uint4 s,
+                                             uint32_t& start, uint32_t& count) {
+    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
+    for (uint32_t i = 0; i <= mask; ++i) {
+        if (s.x == klo && s.y == khi) { start = s.z; count = s.w; return; }
+        if ((s.x & s.y) == 0xffffffffu) break;
+        h = (h + 1) & mask;
+        s = __ldg(slots + h);
+    }
+    count = 0;
+}
+// Linear probe of the 32-B VGICP table {key, mean}; returns the slot or -1 and the mean.
+__device__ __forceinline__ int probe_mean(const double4* __restrict__ vslots, uint32_t mask, uint64_t key, double& mx, double& my, double& mz) {
+    uint32_t h = hash_key(key) & mask;
+    for (uint32_t i = 0; i <= mask; ++i) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(vslots + h));
+        const double2 b = __ldg(reinterpret_cast<const double2*>(vslots + h) + 1);
+        const uint64_t k = static_cast<uint64_t>(__double_as_longlong(a.x));
+        if (k == key) { mx = a.y; my = b.x; mz = b.y; return static_cast<int>(h); }
+        if (k == ~0ull) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
 }
 
 // ---- warp argmin over (fp64 distance >= 0, visit order) --------------------------------------------------------
-// Returns the lane holding the smallest (d2, ord) pair, or -1 when no lane has a candidate (ord == 0xffffffff).
-__device__ __forceinline__ int warp_argmin(double d2, uint32_t ord) {
+// Returns the lane holding the smallest (d2, ord) pair, or -1 when no lane has a candidate (ord == 0xffffffff);
+// *best_out receives the smallest distance (kDblMax when there is none).
+__device__ __forceinline__ int warp_argmin(double d2, uint32_t ord, double* best_out = nullptr) {
     const uint32_t hi = static_cast<uint32_t>(__double2hiint(d2));
     const uint32_t lo = static_cast<uint32_t>(__double2loint(d2));
     const uint32_t mhi = __reduce_min_sync(kFull, hi);
@@ -94,58 +127,101 @@ __device__ __forceinline__ int warp_argmin(double d2, uint32_t ord) {
     const uint32_t mlo = __reduce_min_sync(kFull, a ? lo : 0xffffffffu);
     const bool b = a && (lo == mlo);
     const uint32_t mord = __reduce_min_sync(kFull, b ? ord : 0xffffffffu);
+    if (best_out) *best_out = __hiloint2double(static_cast<int>(mhi), static_cast<int>(mlo));
     if (mord == 0xffffffffu) return -1;
     const uint32_t who = __ballot_sync(kFull, b && ord == mord);
     return __ffs(who) - 1;
 }
 
-// Nearest stored map point of the 27 voxels around key (kx,ky,kz), warp-cooperative.
-// Visit order of the reference: voxels x-outer / y / z-inner (vhm.cpp:234-240), insertion order inside a voxel, strict <
-// (vhm.cpp:45).  Lane L < 27 probes voxel L; the three z-voxels of a column are one contiguous run of `pts`.
-// Returns the winning point index (warp-uniform) or -1.
-__device__ __forceinline__ int nearest_point_27(const MapView& map, double px, double py, double pz, int kx, int ky, int kz, int lane) {
-    uint32_t start = 0, count = 0;
-    if (lane < 27) {
-        const int x = kx + lane / 9 - 1, y = ky + (lane / 3) % 3 - 1, z = kz + lane % 3 - 1;
-        if (key_ok(x) && key_ok(y) && key_ok(z)) {
-            if (probe(map.slots, map.mask, pack_key(x, y, z), start, count) < 0) count = 0;
-        }
+#define ELM_EVAL_CANDIDATE(Q, ORD, IDX)                                                                                  \
+    {                                                                                                                    \
+        const double d2__ = sq3_exact(static_cast<double>((Q).x) - px, static_cast<double>((Q).y) - py,                   \
+                                      static_cast<double>((Q).z) - pz);                                                   \
+        if (d2__ < best || (d2__ == best && (ORD) < bord)) { best = d2__; bord = (ORD); bidx = (IDX); }                   \
     }
+
+// Per-lane description of "its" voxel of the 27-neighbourhood (lane L < 27 <-> offsets x-outer / y / z-inner, the
+// reference's visit order, vhm.cpp:234-240).
+struct LaneVoxel {
+    int ox, oy, oz;
+    bool active;
+};
+__device__ __forceinline__ LaneVoxel lane_voxel(int lane) {
+    LaneVoxel v;
+    v.active = lane < 27;
+    v.ox = lane / 9 - 1; v.oy = (lane / 3) % 3 - 1; v.oz = lane % 3 - 1;
+    return v;
+}
+
+// Squared lower bound (fp32, in units of voxel_size^2, deliberately under-estimated) of the distance from the query to
+// any point STORED under key (k + o) per axis.  Insert keys truncate toward zero (vhm.cpp:275), so along one axis the
+// voxel with key c holds p/vs in [c, c+1) for c > 0, (c-1, c] for c < 0 and (-1, 1) for c == 0.
+__device__ __forceinline__ float axis_gap(int kq, int o, float f) {
+    const int c = kq + o;
+    const float lo = static_cast<float>(o - (c <= 0 ? 1 : 0));
+    const float hi = static_cast<float>(o + (c >= 0 ? 1 : 0));
+    const float g = fmaxf(fmaxf(lo - f, f - hi), 0.0f);
+    return fmaxf(g - 1e-5f, 0.0f);
+}
+
+// Nearest stored map point of the 27 voxels around the query, warp-cooperative (vhm.cpp:35-53).
+//   start/count : this lane's voxel (count == 0 when absent), already probed
+//   returns the winning point index (warp-uniform) or -1.
+// Visit order of the reference: voxels x-outer / y / z-inner, insertion order inside a voxel, strict < (vhm.cpp:45).
+// The three z-voxels of a column are one contiguous run of `pts`.
+template <bool PRUNE>
+__device__ __forceinline__ int nearest_point_27(const float4* __restrict__ pts, uint32_t start, uint32_t count, double px, double py,
+                                                double pz, int kx, int ky, int kz, float fx, float fy, float fz, float inv_vs2_dn,
+                                                const LaneVoxel& lv, int lane, uint32_t& visited) {
+    double best = kDblMax;
+    uint32_t bord = 0xffffffffu, bidx = 0;
     // column c = lanes 3c..3c+2
     const uint32_t c1 = __shfl_down_sync(kFull, count, 1), c2 = __shfl_down_sync(kFull, count, 2);
     const uint32_t s1 = __shfl_down_sync(kFull, start, 1), s2 = __shfl_down_sync(kFull, start, 2);
     const uint32_t runlen = count + c1 + c2;
     const uint32_t runstart = count ? start : (c1 ? s1 : s2);
-
-    double best = 1.7976931348623157e308;
-    uint32_t bord = 0xffffffffu;
-    uint32_t bidx = 0;
-    uint32_t rs[9], rl[9];
-    float4 m[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-        rs[c] = __shfl_sync(kFull, runstart, 3 * c);
-        rl[c] = __shfl_sync(kFull, runlen, 3 * c);
-    }
-#pragma unroll
-    for (int c = 0; c < 9; ++c)
-        if (static_cast<uint32_t>(lane) < rl[c]) m[c] = __ldg(map.pts + rs[c] + lane);
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-        if (static_cast<uint32_t>(lane) < rl[c]) {
-            const double d2 = sq3_exact(static_cast<double>(m[c].x) - px, static_cast<double>(m[c].y) - py, static_cast<double>(m[c].z) - pz);
-            const uint32_t ord = (static_cast<uint32_t>(c) << 20) | static_cast<uint32_t>(lane);
-            if (d2 < best || (d2 == best && ord < bord)) { best = d2; bord = ord; bidx = rs[c] + lane; }
+    if (PRUNE) {
+        // phase A: the centre column (lanes 12..14) — the query's own voxel and its z-neighbours
+        {
+            const uint32_t rs = __shfl_sync(kFull, runstart, 12), rl = __shfl_sync(kFull, runlen, 12);
+            visited += rl;
+            for (uint32_t o = lane; o < rl; o += 32) {
+                const float4 q = __ldg(pts + rs + o);
+                ELM_EVAL_CANDIDATE(q, (12u << 16) + o, rs + o);
+            }
         }
-    }
-    // runs longer than a warp (more than 32 stored points in one column)
-#pragma unroll 1
-    for (int c = 0; c < 9; ++c) {
-        for (uint32_t o = lane + 32; o < rl[c]; o += 32) {
-            const float4 q = __ldg(map.pts + rs[c] + o);
-            const double d2 = sq3_exact(static_cast<double>(q.x) - px, static_cast<double>(q.y) - py, static_cast<double>(q.z) - pz);
-            const uint32_t ord = (static_cast<uint32_t>(c) << 20) | o;
-            if (d2 < best || (d2 == best && ord < bord)) { best = d2; bord = ord; bidx = rs[c] + o; }
+        double bestA;
+        warp_argmin(best, bord, &bestA);
+        // phase B: every other voxel whose box could still hold a point at least as close
+        bool need = false;
+        if (lv.active && count > 0 && (lane < 12 || lane > 14)) {
+            const float gx = axis_gap(kx, lv.ox, fx), gy = axis_gap(ky, lv.oy, fy), gz = axis_gap(kz, lv.oz, fz);
+            const float lb = (gx * gx + gy * gy + gz * gz) * 0.9999f;
+            need = !(lb > __double2float_ru(bestA) * inv_vs2_dn);  // prune only when provably farther
+        }
+        uint32_t todo = __ballot_sync(kFull, need);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t vs0 = __shfl_sync(kFull, start, src), vc = __shfl_sync(kFull, count, src);
+            visited += vc;
+            for (uint32_t o = lane; o < vc; o += 32) {
+                const float4 q = __ldg(pts + vs0 + o);
+                ELM_EVAL_CANDIDATE(q, (static_cast<uint32_t>(src) << 16) + o, vs0 + o);
+            }
+        }
+    } else {
+        const uint32_t colmask = __ballot_sync(kFull, lv.active && (lane % 3 == 0) && runlen > 0);
+        uint32_t todo = colmask;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t rs = __shfl_sync(kFull, runstart, src), rl = __shfl_sync(kFull, runlen, src);
+            visited += rl;
+            for (uint32_t o = lane; o < rl; o += 32) {
+                const float4 q = __ldg(pts + rs + o);
+                ELM_EVAL_CANDIDATE(q, (static_cast<uint32_t>(src) << 16) + o, rs + o);
+            }
         }
     }
     const int wl = warp_argmin(best, bord);
@@ -153,21 +229,17 @@ __device__ __forceinline__ int nearest_point_27(const MapView& map, double px, d
     return static_cast<int>(__shfl_sync(kFull, bidx, wl));
 }
 
-// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:90-151).  Returns the winning slot index or -1.
+// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115).  Returns the winning slot index or -1.
 __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, double py, double pz, int kx, int ky, int kz, int lane) {
-    double d2 = 1.7976931348623157e308;
+    double d2 = kDblMax;
     uint32_t ord = 0xffffffffu;
     int slot = -1;
     if (lane < 27) {
         const int x = kx + lane / 9 - 1, y = ky + (lane / 3) % 3 - 1, z = kz + lane % 3 - 1;
         if (key_ok(x) && key_ok(y) && key_ok(z)) {
-            uint32_t st, cnt;
-            slot = probe(map.slots, map.mask, pack_key(x, y, z), st, cnt);
-            if (slot >= 0) {
-                const double4 vm = map.vslots[slot];
-                d2 = sq3_exact(vm.y - px, vm.z - py, vm.w - pz);
-                ord = lane;
-            }
+            double mx, my, mz;
+            slot = probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz);
+            if (slot >= 0) { d2 = sq3_exact(mx - px, my - py, mz - pz); ord = lane; }
         }
     }
     const int wl = warp_argmin(d2, ord);
@@ -175,7 +247,153 @@ __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, do
     return __shfl_sync(kFull, slot, wl);
 }
 
-// ---- accumulation ---------------------------------------------------------------------------------------------------
+}  // namespace
+
+// ======================================================================================================================
+// search: P2P / GICP
+// ======================================================================================================================
+template <bool PRUNE>
+__global__ void __launch_bounds__(kIcpThreads, 4)
+icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, int* __restrict__ match) {
+    __shared__ __align__(16) float s_tile[2][kIcpWarps * 32 * 3];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ double s_T[12];
+    __shared__ double s_qp[kIcpWarps][3][32];
+    __shared__ int s_qk[kIcpWarps][3][32];
+    __shared__ float s_qf[kIcpWarps][3][32];
+
+    if (st->done) return;  // loop already left (termination / overlap failure)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 12) s_T[tid] = st->T[tid];
+
+    const int B = prm.queries_per_warp;
+    const int tile_pts = kIcpWarps * B;
+    const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+
+    // scan tile -> shared memory through the TMA bulk-copy engine (packed xyz, 12 B/point)
+    auto tile_count = [&](int t) { return min(tile_pts, prm.n - t * tile_pts); };
+    auto tile_tma_ok = [&](int t) { return base_aligned && ((tile_count(t) * 12) & 15) == 0; };
+    auto issue = [&](int t, int buf) {
+        const uint32_t bytes = tile_count(t) * 12;
+        mbar_expect_tx(&s_bar[buf], bytes);
+        tma_load_1d(s_tile[buf], scan + static_cast<size_t>(t) * tile_pts * 3, bytes, &s_bar[buf]);
+    };
+
+    const LaneVoxel lv = lane_voxel(lane);
+    const float inv_vs2_dn = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
+    const uint4* __restrict__ slots = map.slots;
+    const uint32_t mask = map.mask;
+
+    int tile = blockIdx.x, buf = 0;
+    uint32_t phase[2] = {0, 0};
+    if (tile < ntiles && tid == 0 && tile_tma_ok(tile)) issue(tile, 0);
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles && tile_tma_ok(next)) issue(next, buf ^ 1);  // prefetch the next tile
+        if (tile_tma_ok(tile)) {
+            mbar_wait(&s_bar[buf], phase[buf]);
+            phase[buf] ^= 1;
+        } else {  // ragged last tile / unaligned base: plain cooperative copy
+            const int nf = tile_count(tile) * 3;
+            for (int i = tid; i < nf; i += kIcpThreads) s_tile[buf][i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
+            __syncthreads();
+        }
+        const int nq = min(B, tile_count(tile) - warp * B);  // queries of this warp in this tile (may be <= 0)
+        // stage 1: each lane transforms one query point and publishes it to its warp
+        if (lane < nq) {
+            const float* sp = &s_tile[buf][(warp * B + lane) * 3];
+            const double sx = sp[0], sy = sp[1], sz = sp[2];
+            const double px = row_apply_exact(s_T, 0, sx, sy, sz);
+            const double py = row_apply_exact(s_T, 1, sx, sy, sz);
+            const double pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            float fx, fy, fz;
+            s_qp[warp][0][lane] = px; s_qp[warp][1][lane] = py; s_qp[warp][2][lane] = pz;
+            s_qk[warp][0][lane] = voxel_floor(px, map.voxel_size, &fx);
+            s_qk[warp][1][lane] = voxel_floor(py, map.voxel_size, &fy);
+            s_qk[warp][2][lane] = voxel_floor(pz, map.voxel_size, &fz);
+            s_qf[warp][0][lane] = fx; s_qf[warp][1][lane] = fy; s_qf[warp][2][lane] = fz;
+        }
+        __syncwarp();
+        // stage 2: the warp searches its queries one after another; the first table probe of query q+1 is in flight
+        // while query q scans its candidates
+        int my_idx = -1;
+        uint32_t visited = 0;
+        uint64_t key_n = 0;
+        uint32_t h_n = 0;
+        uint4 slot_n = make_uint4(0xffffffffu, 0xffffffffu, 0, 0);
+        bool ok_n = false;
+        auto first_probe = [&](int q) {
+            const int x = s_qk[warp][0][q] + lv.ox, y = s_qk[warp][1][q] + lv.oy, z = s_qk[warp][2][q] + lv.oz;
+            ok_n = lv.active && key_ok(x) && key_ok(y) && key_ok(z);
+            if (ok_n) {
+                key_n = pack_key(x, y, z);
+                h_n = hash_key(key_n) & mask;
+                slot_n = __ldg(slots + h_n);
+            }
+        };
+        if (nq > 0) first_probe(0);
+        for (int q = 0; q < nq; ++q) {
+            const uint64_t key = key_n;
+            const uint32_t h = h_n;
+            const uint4 sl = slot_n;
+            const bool ok = ok_n;
+            if (q + 1 < nq) first_probe(q + 1);
+            uint32_t start = 0, count = 0;
+            if (ok) probe_resume(slots, mask, key, h, sl, start, count);
+            const int w = nearest_point_27<PRUNE>(map.pts, start, count, s_qp[warp][0][q], s_qp[warp][1][q], s_qp[warp][2][q],
+                                                  s_qk[warp][0][q], s_qk[warp][1][q], s_qk[warp][2][q], s_qf[warp][0][q],
+                                                  s_qf[warp][1][q], s_qf[warp][2][q], inv_vs2_dn, lv, lane, visited);
+            if (lane == q) my_idx = w;
+        }
+        if (prm.stats && lane == 0 && nq > 0) {
+            atomicAdd(prm.stats, static_cast<unsigned long long>(visited));
+            atomicAdd(prm.stats + 1, static_cast<unsigned long long>(nq));
+        }
+        if (lane < nq) match[static_cast<size_t>(tile) * tile_pts + warp * B + lane] = my_idx;
+        __syncthreads();  // every warp is done with s_tile[buf] before it is refilled
+    }
+}
+
+// ======================================================================================================================
+// search: VGICP
+// ======================================================================================================================
+__global__ void __launch_bounds__(kIcpThreads, 4)
+icp_search_means_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, int* __restrict__ match) {
+    __shared__ double s_T[12];
+    if (st->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 12) s_T[tid] = st->T[tid];
+    __syncthreads();
+    const int B = prm.queries_per_warp;
+    const int nbatch = (prm.n + B - 1) / B;
+    for (int b = blockIdx.x * kIcpWarps + warp; b < nbatch; b += gridDim.x * kIcpWarps) {
+        const int i = b * B + lane;
+        double px = 0, py = 0, pz = 0;
+        int kx = 0, ky = 0, kz = 0;
+        const int nq = min(B, prm.n - b * B);
+        if (lane < nq) {
+            const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
+            px = row_apply_exact(s_T, 0, sx, sy, sz); py = row_apply_exact(s_T, 1, sx, sy, sz); pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            kx = voxel_floor(px, map.voxel_size); ky = voxel_floor(py, map.voxel_size); kz = voxel_floor(pz, map.voxel_size);
+        }
+        int my_slot = -1;
+        for (int q = 0; q < nq; ++q) {
+            const double qx = __shfl_sync(kFull, px, q), qy = __shfl_sync(kFull, py, q), qz = __shfl_sync(kFull, pz, q);
+            const int w = nearest_mean_27(map, qx, qy, qz, __shfl_sync(kFull, kx, q), __shfl_sync(kFull, ky, q), __shfl_sync(kFull, kz, q), lane);
+            if (lane == q) my_slot = w;
+        }
+        if (lane < nq) match[i] = my_slot;
+    }
+}
+
+// ======================================================================================================================
+// accumulation + reduction (+ solve)
+// ======================================================================================================================
+namespace {
+
 // P2P keeps 18 structured sums (J = [I | -skew(s)] makes most of JtJ redundant); the others keep all 29.
 //   P2P layout:  0 W=sum w | 1..3 sum w s | 4..9 (33,34,35,44,45,55) of sum w(|s|^2 I - s s^T) | 10..12 sum w r
 //                13..15 sum w (s x r) | 16 residual | 17 count
@@ -196,16 +414,18 @@ __device__ __forceinline__ void acc_p2p(double* a, double sx, double sy, double 
     a[17] += 1.0;
 }
 
-// expand the P2P sums into the canonical 29 (upper JtJ row-major, Jtr, residual, count)
-__device__ __forceinline__ void expand_p2p(const double* a, double* o) {
-    for (int i = 0; i < 29; ++i) o[i] = 0.0;
-    o[0] = a[0]; o[6] = a[0]; o[11] = a[0];            // I block
-    o[4] = a[3]; o[5] = -a[2];                         // -skew(B): (0,4)=bz (0,5)=-by
-    o[8] = -a[3]; o[10] = a[1];                        // (1,3)=-bz (1,5)=bx
-    o[12] = a[2]; o[13] = -a[1];                       // (2,3)=by (2,4)=-bx
-    o[15] = a[4]; o[16] = a[5]; o[17] = a[6]; o[18] = a[7]; o[19] = a[8]; o[20] = a[9];
-    o[21] = a[10]; o[22] = a[11]; o[23] = a[12]; o[24] = a[13]; o[25] = a[14]; o[26] = a[15];
-    o[27] = a[16]; o[28] = a[17];
+// canonical slot k (upper JtJ row-major, Jtr, residual, count) of the P2P sums
+__device__ __forceinline__ double expand_p2p(const double* a, int k) {
+    switch (k) {
+        case 0: case 6: case 11: return a[0];       // I block
+        case 4: return a[3];  case 5: return -a[2];  // -skew(B): (0,4)=bz (0,5)=-by
+        case 8: return -a[3]; case 10: return a[1];  // (1,3)=-bz (1,5)=bx
+        case 12: return a[2]; case 13: return -a[1]; // (2,3)=by (2,4)=-bx
+        case 15: return a[4]; case 16: return a[5]; case 17: return a[6]; case 18: return a[7]; case 19: return a[8]; case 20: return a[9];
+        case 21: return a[10]; case 22: return a[11]; case 23: return a[12]; case 24: return a[13]; case 25: return a[14]; case 26: return a[15];
+        case 27: return a[16]; case 28: return a[17];
+        default: return 0.0;
+    }
 }
 
 // JtJ += w J^T M J, Jtr += w J^T M r with J = [I | A], A = -skew(s)   (reg.cpp:124-125, 204-205)
@@ -252,257 +472,6 @@ __device__ __forceinline__ void mahalanobis_local(const double* Rinv, const doub
     M[6] = c20 * inv; M[7] = c21 * inv; M[8] = c22 * inv;
 }
 
-// block reduction of per-lane accumulators -> partials[block][kAcc], fixed order
-template <int NACC, bool IS_P2P>
-__device__ __forceinline__ void block_reduce_store(double* acc, double (*s_red)[kAcc], double* __restrict__ partials, int n_local) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        acc[k] = v;
-    }
-    if (lane == 0) {
-        if (IS_P2P) {
-            double o[29];
-            expand_p2p(acc, o);
-            for (int k = 0; k < 29; ++k) s_red[warp][k] = o[k];
-        } else {
-            for (int k = 0; k < 29; ++k) s_red[warp][k] = acc[k];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-        double v = 0.0;
-        if (threadIdx.x < 29) {
-            for (int w = 0; w < kIcpWarps; ++w) v += s_red[w][threadIdx.x];
-        } else if (threadIdx.x == kIdxNtotal) {
-            v = (blockIdx.x == 0) ? static_cast<double>(n_local) : 0.0;
-        }
-        partials[blockIdx.x * kAcc + threadIdx.x] = v;
-    }
-}
-
-}  // namespace
-
-// ======================================================================================================================
-// P2P / GICP
-// ======================================================================================================================
-template <int METHOD>
-__global__ void __launch_bounds__(kIcpThreads, 2)
-icp_points_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, double* __restrict__ partials) {
-    constexpr int NACC = AccSize<METHOD>::value;
-    __shared__ __align__(16) float s_tile[2][kIcpWarps * 32 * 3];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ double s_T[16], s_Tinv[16], s_Rinv[9];
-    __shared__ double s_qp[kIcpWarps][3][32];
-    __shared__ int s_qk[kIcpWarps][3][32];
-    __shared__ double s_red[kIcpWarps][kAcc];
-
-    if (st->done) return;  // loop already left (termination / overlap failure): the solve kernel skips too
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 16) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
-    if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
-
-    const int B = prm.queries_per_warp;
-    const int tile_pts = kIcpWarps * B;
-    const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
-    const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-
-    // scan tile -> shared memory through the TMA bulk-copy engine (packed xyz, 12 B/point)
-    auto tile_count = [&](int t) { return min(tile_pts, prm.n - t * tile_pts); };
-    auto tile_tma_ok = [&](int t) { return base_aligned && ((tile_count(t) * 12) & 15) == 0; };
-    auto issue = [&](int t, int buf) {
-        const uint32_t bytes = tile_count(t) * 12;
-        mbar_expect_tx(&s_bar[buf], bytes);
-        tma_load_1d(s_tile[buf], scan + static_cast<size_t>(t) * tile_pts * 3, bytes, &s_bar[buf]);
-    };
-
-    double acc[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-
-    int tile = blockIdx.x, buf = 0;
-    uint32_t phase[2] = {0, 0};
-    if (tile < ntiles && tid == 0 && tile_tma_ok(tile)) issue(tile, 0);
-    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const int next = tile + gridDim.x;
-        if (tid == 0 && next < ntiles && tile_tma_ok(next)) issue(next, buf ^ 1);  // prefetch the next tile
-        if (tile_tma_ok(tile)) {
-            mbar_wait(&s_bar[buf], phase[buf]);
-            phase[buf] ^= 1;
-        } else {  // ragged last tile / unaligned base: plain cooperative copy
-            const int nf = tile_count(tile) * 3;
-            for (int i = tid; i < nf; i += kIcpThreads) s_tile[buf][i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
-            __syncthreads();
-        }
-        const int cnt = tile_count(tile) - warp * B;  // queries of this warp in this tile (may be <= 0)
-        const int nq = min(B, cnt);
-        // stage 1: each lane transforms its own query point, publishes it to the warp
-        double sx = 0, sy = 0, sz = 0, px = 0, py = 0, pz = 0;
-        if (lane < nq) {
-            const float* sp = &s_tile[buf][(warp * B + lane) * 3];
-            sx = sp[0]; sy = sp[1]; sz = sp[2];
-            px = row_apply_exact(s_T, 0, sx, sy, sz);
-            py = row_apply_exact(s_T, 1, sx, sy, sz);
-            pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            s_qp[warp][0][lane] = px; s_qp[warp][1][lane] = py; s_qp[warp][2][lane] = pz;
-            s_qk[warp][0][lane] = voxel_floor(px, map.voxel_size);
-            s_qk[warp][1][lane] = voxel_floor(py, map.voxel_size);
-            s_qk[warp][2][lane] = voxel_floor(pz, map.voxel_size);
-        }
-        __syncwarp();
-        // stage 2: the warp searches the queries one after another
-        int my_idx = -1;
-        for (int q = 0; q < nq; ++q) {
-            const int w = nearest_point_27(map, s_qp[warp][0][q], s_qp[warp][1][q], s_qp[warp][2][q], s_qk[warp][0][q],
-                                           s_qk[warp][1][q], s_qk[warp][2][q], lane);
-            if (lane == q) my_idx = w;
-        }
-        // stage 3: each lane linearises its own correspondence
-        if (lane < nq) {
-            double tx = 0.0, ty = 0.0, tz = 0.0;  // default-constructed neighbour at the origin (Q2, vhm.cpp:37)
-            if (my_idx >= 0) { const float4 t = __ldg(map.pts + my_idx); tx = t.x; ty = t.y; tz = t.z; }
-            const double d2 = sq3_exact(tx - px, ty - py, tz - pz);
-            if (d2 < prm.max_dist2) {  // vhm.cpp:66
-                if (METHOD == 0) {
-                    const double lx = s_Tinv[0] * tx + s_Tinv[1] * ty + s_Tinv[2] * tz + s_Tinv[3];
-                    const double ly = s_Tinv[4] * tx + s_Tinv[5] * ty + s_Tinv[6] * tz + s_Tinv[7];
-                    const double lz = s_Tinv[8] * tx + s_Tinv[9] * ty + s_Tinv[10] * tz + s_Tinv[11];
-                    acc_p2p(acc, sx, sy, sz, lx - sx, ly - sy, lz - sz, prm.th);
-                } else {
-                    double mean[3] = {0.0, 0.0, 0.0}, C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, nrm[3] = {1.0, 0.0, 0.0};
-                    if (my_idx >= 0) {
-                        const double2* r = reinterpret_cast<const double2*>(map.prec + static_cast<size_t>(my_idx) * 16);
-                        const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4),
-                                      r5 = __ldg(r + 5), r6 = __ldg(r + 6), r7 = __ldg(r + 7);
-                        mean[0] = r0.x; mean[1] = r0.y; mean[2] = r1.x;
-                        C[0] = r1.y; C[1] = r2.x; C[2] = r2.y; C[3] = r3.x; C[4] = r3.y; C[5] = r4.x; C[6] = r4.y; C[7] = r5.x; C[8] = r5.y;
-                        nrm[0] = r6.x; nrm[1] = r6.y; nrm[2] = r7.x;
-                    }
-                    // residual to the neighbourhood MEAN, not the matched point (Q4, reg.cpp:97-101)
-                    const double lx = s_Tinv[0] * mean[0] + s_Tinv[1] * mean[1] + s_Tinv[2] * mean[2] + s_Tinv[3];
-                    const double ly = s_Tinv[4] * mean[0] + s_Tinv[5] * mean[1] + s_Tinv[6] * mean[2] + s_Tinv[7];
-                    const double lz = s_Tinv[8] * mean[0] + s_Tinv[9] * mean[1] + s_Tinv[10] * mean[2] + s_Tinv[11];
-                    const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
-                    double M[9];
-                    mahalanobis_local(s_Rinv, C, M);
-                    const double r2 = rx * rx + ry * ry + rz * rz;
-                    const double den = prm.th + r2;
-                    const double w = (prm.th * prm.th) / (den * den) * 0.8 + 0.2;  // reg.cpp:121
-                    acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
-                    // point-to-plane fitness term (reg.cpp:94-95,128-131)
-                    double nx = s_Rinv[0] * nrm[0] + s_Rinv[1] * nrm[1] + s_Rinv[2] * nrm[2];
-                    double ny = s_Rinv[3] * nrm[0] + s_Rinv[4] * nrm[1] + s_Rinv[5] * nrm[2];
-                    double nz = s_Rinv[6] * nrm[0] + s_Rinv[7] * nrm[1] + s_Rinv[8] * nrm[2];
-                    const double nn = nx * nx + ny * ny + nz * nz;
-                    if (nn > 0.0) { const double il = 1.0 / sqrt(nn); nx *= il; ny *= il; nz *= il; }
-                    acc[27] += fabs(rx * nx + ry * ny + rz * nz);
-                    acc[28] += 1.0;
-                }
-            }
-        }
-        __syncthreads();  // every warp is done with s_tile[buf] before it is refilled
-    }
-    block_reduce_store<NACC, METHOD == 0>(acc, s_red, partials, prm.n);
-}
-
-// ======================================================================================================================
-// VGICP / AVGICP
-// ======================================================================================================================
-template <int METHOD>
-__global__ void __launch_bounds__(kIcpThreads, 2)
-icp_voxels_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, double* __restrict__ partials) {
-    __shared__ double s_T[16], s_Tinv[16], s_Rinv[9];
-    __shared__ double s_red[kIcpWarps][kAcc];
-    if (st->done) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 16) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
-    if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
-    __syncthreads();
-
-    double acc[29];
-#pragma unroll
-    for (int k = 0; k < 29; ++k) acc[k] = 0.0;
-
-    // one (scan point, voxel) pair -> accumulators   (reg.cpp:171-208)
-    auto linearize_pair = [&](double sx, double sy, double sz, int slot, double mx, double my, double mz) {
-        double C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        if (slot >= 0) {
-            const double2* r = reinterpret_cast<const double2*>(map.vcov + static_cast<size_t>(slot) * 12);
-            const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
-            const double c8 = __ldg(map.vcov + static_cast<size_t>(slot) * 12 + 8);
-            C[0] = r0.x; C[1] = r0.y; C[2] = r1.x; C[3] = r1.y; C[4] = r2.x; C[5] = r2.y; C[6] = r3.x; C[7] = r3.y; C[8] = c8;
-        }
-        const double lx = s_Tinv[0] * mx + s_Tinv[1] * my + s_Tinv[2] * mz + s_Tinv[3];
-        const double ly = s_Tinv[4] * mx + s_Tinv[5] * my + s_Tinv[6] * mz + s_Tinv[7];
-        const double lz = s_Tinv[8] * mx + s_Tinv[9] * my + s_Tinv[10] * mz + s_Tinv[11];
-        const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
-        const double r2 = rx * rx + ry * ry + rz * rz;
-        const double den = prm.th + r2;
-        const double w = (prm.th * prm.th) / (den * den);  // reg.cpp:199
-        acc[28] += 1.0;                                      // the pair counts in the denominator either way (Q7)
-        if (w < 0.01) return;                                // reg.cpp:201
-        double M[9];
-        mahalanobis_local(s_Rinv, C, M);
-        acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
-        acc[27] += sqrt(r2);  // reg.cpp:207
-    };
-
-    if (METHOD == 2) {
-        // VGICP: one warp searches 32 consecutive scan points, lane q then linearises point q
-        const int nbatch = (prm.n + 31) / 32;
-        for (int b = blockIdx.x * kIcpWarps + warp; b < nbatch; b += gridDim.x * kIcpWarps) {
-            const int i = b * 32 + lane;
-            double sx = 0, sy = 0, sz = 0, px = 0, py = 0, pz = 0;
-            int kx = 0, ky = 0, kz = 0;
-            if (i < prm.n) {
-                sx = scan[3 * static_cast<size_t>(i)]; sy = scan[3 * static_cast<size_t>(i) + 1]; sz = scan[3 * static_cast<size_t>(i) + 2];
-                px = row_apply_exact(s_T, 0, sx, sy, sz); py = row_apply_exact(s_T, 1, sx, sy, sz); pz = row_apply_exact(s_T, 2, sx, sy, sz);
-                kx = voxel_floor(px, map.voxel_size); ky = voxel_floor(py, map.voxel_size); kz = voxel_floor(pz, map.voxel_size);
-            }
-            const int nq = min(32, prm.n - b * 32);
-            int my_slot = -1;
-            for (int q = 0; q < nq; ++q) {
-                const double qx = __shfl_sync(kFull, px, q), qy = __shfl_sync(kFull, py, q), qz = __shfl_sync(kFull, pz, q);
-                const int w = nearest_mean_27(map, qx, qy, qz, __shfl_sync(kFull, kx, q), __shfl_sync(kFull, ky, q), __shfl_sync(kFull, kz, q), lane);
-                if (lane == q) my_slot = w;
-            }
-            if (i < prm.n) {
-                double mx = 0.0, my = 0.0, mz = 0.0;  // default CovStruct (I, 0)  (Q2, vhm.cpp:104)
-                if (my_slot >= 0) { const double4 vm = map.vslots[my_slot]; mx = vm.y; my = vm.z; mz = vm.w; }
-                if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_pair(sx, sy, sz, my_slot, mx, my, mz);  // vhm.cpp:129
-            }
-        }
-    } else {
-        // AVGICP: 8 lanes per scan point; lane j < 7 owns voxel j of {c, +x, -x, +y, -y, +z, -z} (vhm.cpp:224-230)
-        const long long total = static_cast<long long>(prm.n) * 8;
-        for (long long t = static_cast<long long>(blockIdx.x) * kIcpThreads + tid; t < total; t += static_cast<long long>(gridDim.x) * kIcpThreads) {
-            const int i = static_cast<int>(t >> 3), j = static_cast<int>(t & 7);
-            if (j == 7) continue;
-            const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
-            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
-            kx += (j == 1) - (j == 2); ky += (j == 3) - (j == 4); kz += (j == 5) - (j == 6);
-            if (!(key_ok(kx) && key_ok(ky) && key_ok(kz))) continue;
-            uint32_t s0, c0;
-            const int slot = probe(map.slots, map.mask, pack_key(kx, ky, kz), s0, c0);
-            if (slot < 0) continue;
-            const double4 vm = map.vslots[slot];
-            if (sq3_exact(vm.y - px, vm.z - py, vm.w - pz) < prm.max_dist2) linearize_pair(sx, sy, sz, slot, vm.y, vm.z, vm.w);  // vhm.cpp:183
-        }
-    }
-    block_reduce_store<29, false>(acc, s_red, partials, prm.n);
-}
-
-// ======================================================================================================================
-// small fixed-size kernels
-// ======================================================================================================================
-namespace {
-
 // general 4x4 inverse by cofactors (stands in for Matrix4d::inverse(), reg.cpp:24)
 __device__ void inverse4(const double* m, double* o) {
     const double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];
@@ -541,12 +510,11 @@ __device__ void refresh_inverses(IcpState* st) {
     inverse3(R, st->Rinv);
 }
 
-// Symmetric 6x6: pivoted LDL^T (largest remaining diagonal first) with pseudo-inverse of D, like Eigen's
-// ldlt().solve() (reg.cpp:56,138,214).  Optionally also the full inverse (GICP local_cov, reg.cpp:141).
-__device__ void ldlt6(const double* Ain, const double* b, double* x, double* inv_out) {
-    double A[6][6];
-    int perm[6];
-    for (int i = 0; i < 6; ++i) { perm[i] = i; for (int j = 0; j < 6; ++j) A[i][j] = Ain[6 * i + j]; }
+// Symmetric 6x6 in shared memory: pivoted LDL^T (largest remaining diagonal first) with pseudo-inverse of D, like
+// Eigen's ldlt().solve() (reg.cpp:56,138,214).  A is destroyed.  Optionally also the full inverse (GICP local_cov,
+// reg.cpp:141).  Single thread; everything lives in shared memory (no local-memory indexing).
+__device__ void ldlt6(double (*A)[6], const double* b, double* x, double* inv_out, int* perm, double* y) {
+    for (int i = 0; i < 6; ++i) perm[i] = i;
     for (int k = 0; k < 6; ++k) {
         int p = k;
         for (int i = k + 1; i < 6; ++i) if (fabs(A[i][i]) > fabs(A[p][p])) p = i;
@@ -557,14 +525,14 @@ __device__ void ldlt6(const double* Ain, const double* b, double* x, double* inv
         }
         const double d = A[k][k];
         if (d == 0.0) { for (int i = k + 1; i < 6; ++i) A[i][k] = 0.0; continue; }
-        for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
+        const double id = 1.0 / d;
+        for (int i = k + 1; i < 6; ++i) A[i][k] *= id;
         for (int i = k + 1; i < 6; ++i)
             for (int j = k + 1; j <= i; ++j) { A[i][j] -= A[i][k] * d * A[j][k]; A[j][i] = A[i][j]; }
     }
-    const double tol = 1.0 / 1.7976931348623157e308;
+    const double tol = 1.0 / kDblMax;
     const int nrhs = inv_out ? 7 : 1;
     for (int r = 0; r < nrhs; ++r) {
-        double y[6];
         for (int i = 0; i < 6; ++i) y[i] = (r == 0) ? b[perm[i]] : ((perm[i] == r - 1) ? 1.0 : 0.0);
         for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
         for (int i = 0; i < 6; ++i) y[i] = (fabs(A[i][i]) > tol) ? y[i] / A[i][i] : 0.0;
@@ -599,36 +567,14 @@ __device__ double rotation_angle(const double* R) {
     return (n != 0.0) ? 2.0 * atan2(n, fabs(qw)) : 0.0;
 }
 
-}  // namespace
+struct SolveScratch {
+    double A[6][6];
+    double x[6], y[6];
+    int perm[6];
+};
 
-__global__ void icp_begin_kernel(IcpState* st, Pose16 T0) {
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 16; ++i) st->T[i] = T0.m[i];
-        refresh_inverses(st);
-        for (int i = 0; i < 36; ++i) st->local_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;  // reg.cpp:280
-        st->iterations = 0; st->done = 0; st->overlap_fail = 0;
-    }
-}
-
-// partials[nblocks][kAcc] -> st->acc, fixed summation order (bit-reproducible run to run)
-__global__ void __launch_bounds__(256) icp_reduce_kernel(IcpState* st, const double* __restrict__ partials, int nblocks) {
-    __shared__ double s[8][kAcc];
-    if (st->done) return;
-    const int k = threadIdx.x & 31, g = threadIdx.x >> 5;
-    double v = 0.0;
-    for (int b = g; b < nblocks; b += 8) v += partials[b * kAcc + k];
-    s[g][k] = v;
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-        double t = 0.0;
-        for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
-        st->acc[threadIdx.x] = t;
-    }
-}
-
-// One AlignClouds* tail + the RunRegister bookkeeping around it.
-__global__ void icp_solve_kernel(IcpState* st, IcpParams prm) {
-    if (threadIdx.x != 0 || st->done) return;
+// One AlignClouds* tail + the RunRegister bookkeeping around it.  Runs in ONE thread; st->acc holds the sums.
+__device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc) {
     const double* a = st->acc;
     const double n_corr = a[kIdxNcorr], n_total = a[kIdxNtotal];
     // corres_ratio = (float)i_source_corr_num / i_source_total_num   (reg.cpp:351)
@@ -637,53 +583,257 @@ __global__ void icp_solve_kernel(IcpState* st, IcpParams prm) {
         st->overlap_fail = 1; st->done = 1;
         return;
     }
-    double JTJ[36], JTr[6];
     int k = 0;
-    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { JTJ[6 * i + j] = a[k]; JTJ[6 * j + i] = a[k]; ++k; }
-    for (int i = 0; i < 6; ++i) JTr[i] = a[kIdxJtr + i];
-    for (int i = 0; i < 36; ++i) st->JTJ[i] = JTJ[i];
-    for (int i = 0; i < 6; ++i) st->JTr[i] = JTr[i];
+    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { st->JTJ[6 * i + j] = a[k]; st->JTJ[6 * j + i] = a[k]; ++k; }
+    for (int i = 0; i < 6; ++i) st->JTr[i] = a[kIdxJtr + i];
     st->residual_sum = a[kIdxRes];
     st->n_corr = n_corr;
     st->fitness = a[kIdxRes] / n_corr;  // reg.cpp:53,134,210
-    double A[36], x[6];
-    for (int i = 0; i < 36; ++i) A[i] = JTJ[i];
-    for (int i = 0; i < 6; ++i) A[7 * i] = JTJ[7 * i] + prm.lm_lambda * JTJ[7 * i];  // JTJ + lambda diag(JTJ) (Q9)
-    ldlt6(A, JTr, x, (prm.method == 1) ? st->local_cov : nullptr);                    // reg.cpp:137-142
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) sc->A[i][j] = st->JTJ[6 * i + j];
+    for (int i = 0; i < 6; ++i) sc->A[i][i] = st->JTJ[7 * i] + prm.lm_lambda * st->JTJ[7 * i];  // JTJ + lambda diag(JTJ) (Q9)
+    ldlt6(sc->A, st->JTr, sc->x, (prm.method == 1) ? st->local_cov : nullptr, sc->perm, sc->y);  // reg.cpp:137-142
+    const double* x = sc->x;
     // AngleAxisd(|w|, w/|w|).toRotationMatrix()   (reg.cpp:58-62)
     const double wn2 = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
     const double angle = sqrt(wn2);
     double ax = x[3], ay = x[4], az = x[5];
-    if (wn2 > 0.0) { ax /= angle; ay /= angle; az /= angle; }
-    const double s = sin(angle), c = cos(angle), c1 = 1.0 - c;
-    double D[16];
-    D[0] = c1 * ax * ax + c;       D[1] = c1 * ax * ay - s * az;  D[2] = c1 * ax * az + s * ay;  D[3] = x[0];
-    D[4] = c1 * ax * ay + s * az;  D[5] = c1 * ay * ay + c;       D[6] = c1 * ay * az - s * ax;  D[7] = x[1];
-    D[8] = c1 * ax * az - s * ay;  D[9] = c1 * ay * az + s * ax;  D[10] = c1 * az * az + c;      D[11] = x[2];
-    D[12] = 0.0; D[13] = 0.0; D[14] = 0.0; D[15] = 1.0;
-    double Tn[16];
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j)
-            Tn[4 * i + j] = st->T[4 * i] * D[j] + st->T[4 * i + 1] * D[4 + j] + st->T[4 * i + 2] * D[8 + j] + st->T[4 * i + 3] * D[12 + j];
-    for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];  // last_icp_pose * estimation_local (reg.cpp:378)
+    if (wn2 > 0.0) { const double ia = 1.0 / angle; ax *= ia; ay *= ia; az *= ia; }
+    double s, c;
+    sincos(angle, &s, &c);
+    const double c1 = 1.0 - c;
+    const double D0 = c1 * ax * ax + c, D1 = c1 * ax * ay - s * az, D2 = c1 * ax * az + s * ay;
+    const double D4 = c1 * ax * ay + s * az, D5 = c1 * ay * ay + c, D6 = c1 * ay * az - s * ax;
+    const double D8 = c1 * ax * az - s * ay, D9 = c1 * ay * az + s * ax, D10 = c1 * az * az + c;
+    // last_icp_pose * estimation_local (reg.cpp:378)
+    for (int i = 0; i < 3; ++i) {
+        const double t0 = st->T[4 * i], t1 = st->T[4 * i + 1], t2 = st->T[4 * i + 2], t3 = st->T[4 * i + 3];
+        st->T[4 * i] = t0 * D0 + t1 * D4 + t2 * D8;
+        st->T[4 * i + 1] = t0 * D1 + t1 * D5 + t2 * D9;
+        st->T[4 * i + 2] = t0 * D2 + t1 * D6 + t2 * D10;
+        st->T[4 * i + 3] = t0 * x[0] + t1 * x[1] + t2 * x[2] + t3;
+    }
+    {   // bottom row of a general 4x4 product (stays 0 0 0 1 for a rigid initial guess)
+        const double t0 = st->T[12], t1 = st->T[13], t2 = st->T[14], t3 = st->T[15];
+        st->T[12] = t0 * D0 + t1 * D4 + t2 * D8;
+        st->T[13] = t0 * D1 + t1 * D5 + t2 * D9;
+        st->T[14] = t0 * D2 + t1 * D6 + t2 * D10;
+        st->T[15] = t0 * x[0] + t1 * x[1] + t2 * x[2] + t3;
+    }
     st->iterations += 1;
-    const double R[9] = {D[0], D[1], D[2], D[4], D[5], D[6], D[8], D[9], D[10]};
+    const double R[9] = {D0, D1, D2, D4, D5, D6, D8, D9, D10};
     const double tn = rotation_angle(R) + sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);  // reg.cpp:381-384
     if (tn < prm.term_thr) { st->done = 1; return; }                                      // reg.cpp:385-387
     refresh_inverses(st);
 }
 
+}  // namespace
+
+// One thread per scan point (8 threads per point for AVGICP).  partials[gridDim.x][kAcc]; the last block to finish
+// sums them in a fixed order into st->acc and, when `solve_here`, runs the solve/update step.
+template <int METHOD>
+__global__ void __launch_bounds__(kIcpThreads, 2)
+icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ match, IcpParams prm, IcpState* __restrict__ st,
+                      double* __restrict__ partials, unsigned int* __restrict__ ticket, int solve_here) {
+    constexpr int NACC = AccSize<METHOD>::value;
+    __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
+    __shared__ double s_red[kIcpWarps][kAcc];
+    __shared__ SolveScratch s_solve;
+    __shared__ bool s_last;
+    if (st->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
+    if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+    __syncthreads();
+
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+
+    // one (scan point, voxel record) pair -> accumulators   (reg.cpp:171-208)
+    auto linearize_voxel_pair = [&](double sx, double sy, double sz, int slot, double mx, double my, double mz) {
+        double C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (slot >= 0) {
+            const double2* r = reinterpret_cast<const double2*>(map.vcov + static_cast<size_t>(slot) * 12);
+            const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+            const double c8 = __ldg(map.vcov + static_cast<size_t>(slot) * 12 + 8);
+            C[0] = r0.x; C[1] = r0.y; C[2] = r1.x; C[3] = r1.y; C[4] = r2.x; C[5] = r2.y; C[6] = r3.x; C[7] = r3.y; C[8] = c8;
+        }
+        const double lx = s_Tinv[0] * mx + s_Tinv[1] * my + s_Tinv[2] * mz + s_Tinv[3];
+        const double ly = s_Tinv[4] * mx + s_Tinv[5] * my + s_Tinv[6] * mz + s_Tinv[7];
+        const double lz = s_Tinv[8] * mx + s_Tinv[9] * my + s_Tinv[10] * mz + s_Tinv[11];
+        const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
+        const double r2 = rx * rx + ry * ry + rz * rz;
+        const double den = prm.th + r2;
+        const double w = (prm.th * prm.th) / (den * den);  // reg.cpp:199
+        acc[28] += 1.0;                                      // the pair counts in the denominator either way (Q7)
+        if (w < 0.01) return;                                // reg.cpp:201
+        double M[9];
+        mahalanobis_local(s_Rinv, C, M);
+        acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
+        acc[27] += sqrt(r2);  // reg.cpp:207
+    };
+
+    if (METHOD == 3) {
+        // AVGICP: 8 lanes per scan point; lane j < 7 owns voxel j of {c, +x, -x, +y, -y, +z, -z} (vhm.cpp:224-230)
+        const long long total = static_cast<long long>(prm.n) * 8;
+        for (long long t = static_cast<long long>(blockIdx.x) * kIcpThreads + tid; t < total; t += static_cast<long long>(gridDim.x) * kIcpThreads) {
+            const int i = static_cast<int>(t >> 3), j = static_cast<int>(t & 7);
+            if (j == 7) continue;
+            const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
+            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+            kx += (j == 1) - (j == 2); ky += (j == 3) - (j == 4); kz += (j == 5) - (j == 6);
+            if (!(key_ok(kx) && key_ok(ky) && key_ok(kz))) continue;
+            double mx, my, mz;
+            const int slot = probe_mean(map.vslots, map.mask, pack_key(kx, ky, kz), mx, my, mz);
+            if (slot < 0) continue;
+            if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_voxel_pair(sx, sy, sz, slot, mx, my, mz);  // vhm.cpp:183
+        }
+    } else {
+        for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
+            const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
+            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            const int m = match[i];
+            if (METHOD == 2) {
+                double mx = 0.0, my = 0.0, mz = 0.0;  // default CovStruct (I, 0)  (Q2, vhm.cpp:104)
+                if (m >= 0) {
+                    const double2 a = __ldg(reinterpret_cast<const double2*>(map.vslots + m));
+                    const double2 b = __ldg(reinterpret_cast<const double2*>(map.vslots + m) + 1);
+                    mx = a.y; my = b.x; mz = b.y;
+                }
+                if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_voxel_pair(sx, sy, sz, m, mx, my, mz);  // vhm.cpp:129
+            } else {
+                double tx = 0.0, ty = 0.0, tz = 0.0;  // default-constructed neighbour at the origin (Q2, vhm.cpp:37)
+                if (m >= 0) { const float4 t = __ldg(map.pts + m); tx = t.x; ty = t.y; tz = t.z; }
+                if (!(sq3_exact(tx - px, ty - py, tz - pz) < prm.max_dist2)) continue;  // vhm.cpp:66
+                if (METHOD == 0) {
+                    const double lx = s_Tinv[0] * tx + s_Tinv[1] * ty + s_Tinv[2] * tz + s_Tinv[3];
+                    const double ly = s_Tinv[4] * tx + s_Tinv[5] * ty + s_Tinv[6] * tz + s_Tinv[7];
+                    const double lz = s_Tinv[8] * tx + s_Tinv[9] * ty + s_Tinv[10] * tz + s_Tinv[11];
+                    acc_p2p(acc, sx, sy, sz, lx - sx, ly - sy, lz - sz, prm.th);
+                } else {
+                    double mean[3] = {0.0, 0.0, 0.0}, C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, nrm[3] = {1.0, 0.0, 0.0};
+                    if (m >= 0) {
+                        const double2* r = reinterpret_cast<const double2*>(map.prec + static_cast<size_t>(m) * 16);
+                        const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4),
+                                      r5 = __ldg(r + 5), r6 = __ldg(r + 6), r7 = __ldg(r + 7);
+                        mean[0] = r0.x; mean[1] = r0.y; mean[2] = r1.x;
+                        C[0] = r1.y; C[1] = r2.x; C[2] = r2.y; C[3] = r3.x; C[4] = r3.y; C[5] = r4.x; C[6] = r4.y; C[7] = r5.x; C[8] = r5.y;
+                        nrm[0] = r6.x; nrm[1] = r6.y; nrm[2] = r7.x;
+                    }
+                    // residual to the neighbourhood MEAN, not the matched point (Q4, reg.cpp:97-101)
+                    const double lx = s_Tinv[0] * mean[0] + s_Tinv[1] * mean[1] + s_Tinv[2] * mean[2] + s_Tinv[3];
+                    const double ly = s_Tinv[4] * mean[0] + s_Tinv[5] * mean[1] + s_Tinv[6] * mean[2] + s_Tinv[7];
+                    const double lz = s_Tinv[8] * mean[0] + s_Tinv[9] * mean[1] + s_Tinv[10] * mean[2] + s_Tinv[11];
+                    const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
+                    double M[9];
+                    mahalanobis_local(s_Rinv, C, M);
+                    const double r2 = rx * rx + ry * ry + rz * rz;
+                    const double den = prm.th + r2;
+                    const double w = (prm.th * prm.th) / (den * den) * 0.8 + 0.2;  // reg.cpp:121
+                    acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
+                    // point-to-plane fitness term (reg.cpp:94-95,128-131)
+                    double nx = s_Rinv[0] * nrm[0] + s_Rinv[1] * nrm[1] + s_Rinv[2] * nrm[2];
+                    double ny = s_Rinv[3] * nrm[0] + s_Rinv[4] * nrm[1] + s_Rinv[5] * nrm[2];
+                    double nz = s_Rinv[6] * nrm[0] + s_Rinv[7] * nrm[1] + s_Rinv[8] * nrm[2];
+                    const double nn = nx * nx + ny * ny + nz * nz;
+                    if (nn > 0.0) { const double il = 1.0 / sqrt(nn); nx *= il; ny *= il; nz *= il; }
+                    acc[27] += fabs(rx * nx + ry * ny + rz * nz);
+                    acc[28] += 1.0;
+                }
+            }
+        }
+    }
+
+    // block tree: warp shuffles, then the 8 warps in fixed order
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        acc[k] = v;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 29; ++k) s_red[warp][k] = (METHOD == 0) ? expand_p2p(acc, k) : acc[k < NACC ? k : 0];
+    }
+    __syncthreads();
+    if (tid < kAcc) {
+        double v = 0.0;
+        if (tid < 29) { for (int w = 0; w < kIcpWarps; ++w) v += s_red[w][tid]; }
+        else if (tid == kIdxNtotal) v = (blockIdx.x == 0) ? static_cast<double>(prm.n) : 0.0;
+        partials[blockIdx.x * kAcc + tid] = v;
+    }
+    // last block to arrive finishes the job (fixed-order sum => bit-reproducible whichever block is last)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        const int k = tid & 31, g = tid >> 5;
+        double v = 0.0;
+        for (int b = g; b < static_cast<int>(gridDim.x); b += kIcpWarps) v += __ldcg(partials + b * kAcc + k);
+        s_red[g][k] = v;
+    }
+    __syncthreads();
+    if (tid < kAcc) {
+        double t = 0.0;
+        for (int i = 0; i < kIcpWarps; ++i) t += s_red[i][tid];
+        st->acc[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *ticket = 0;
+        if (solve_here) solve_step(st, prm, &s_solve);
+    }
+}
+
+// ======================================================================================================================
+// small fixed-size kernels
+// ======================================================================================================================
+__global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) st->T[i] = T0.m[i];
+        refresh_inverses(st);
+        for (int i = 0; i < 36; ++i) st->local_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;  // reg.cpp:280
+        st->iterations = 0; st->done = 0; st->overlap_fail = 0;
+        *ticket = 0;
+    }
+}
+
+__global__ void icp_solve_kernel(IcpState* st, IcpParams prm) {
+    __shared__ SolveScratch s_solve;
+    if (threadIdx.x != 0 || st->done) return;
+    solve_step(st, prm, &s_solve);
+}
+
 // ---- correspondence dump (test hook) -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kIcpThreads)
-icp_match_kernel(MapView map, const float* __restrict__ scan, int n, Pose16 T, int method, double max_dist2, int* __restrict__ count, double* __restrict__ target) {
+icp_match_kernel(MapView map, const float* __restrict__ scan, int n, Pose16 T, int method, double max_dist2, int prune, int* __restrict__ count,
+                 double* __restrict__ target) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const LaneVoxel lv = lane_voxel(lane);
+    const float inv_vs2_dn = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
     for (int i = gw; i < n; i += nw) {
         const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
         const double px = row_apply_exact(T.m, 0, sx, sy, sz), py = row_apply_exact(T.m, 1, sx, sy, sz), pz = row_apply_exact(T.m, 2, sx, sy, sz);
-        const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+        float fx, fy, fz;
+        const int kx = voxel_floor(px, map.voxel_size, &fx), ky = voxel_floor(py, map.voxel_size, &fy), kz = voxel_floor(pz, map.voxel_size, &fz);
         if (method == 0 || method == 1) {
-            const int w = nearest_point_27(map, px, py, pz, kx, ky, kz, lane);
+            uint32_t start = 0, cnt = 0;
+            if (lv.active) {
+                const int x = kx + lv.ox, y = ky + lv.oy, z = kz + lv.oz;
+                if (key_ok(x) && key_ok(y) && key_ok(z)) { if (probe(map.slots, map.mask, pack_key(x, y, z), start, cnt) < 0) cnt = 0; }
+            }
+            uint32_t visited = 0;
+            const int w = prune ? nearest_point_27<true>(map.pts, start, cnt, px, py, pz, kx, ky, kz, fx, fy, fz, inv_vs2_dn, lv, lane, visited)
+                                : nearest_point_27<false>(map.pts, start, cnt, px, py, pz, kx, ky, kz, fx, fy, fz, inv_vs2_dn, lv, lane, visited);
             double tx = 0, ty = 0, tz = 0;
             if (w >= 0) { const float4 t = map.pts[w]; tx = t.x; ty = t.y; tz = t.z; }
             const bool ok = sq3_exact(tx - px, ty - py, tz - pz) < max_dist2;
@@ -706,13 +856,8 @@ icp_match_kernel(MapView map, const float* __restrict__ scan, int n, Pose16 T, i
             if (lane < 7) {
                 const int x = kx + (lane == 1) - (lane == 2), y = ky + (lane == 3) - (lane == 4), z = kz + (lane == 5) - (lane == 6);
                 if (key_ok(x) && key_ok(y) && key_ok(z)) {
-                    uint32_t s0, c0;
-                    const int slot = probe(map.slots, map.mask, pack_key(x, y, z), s0, c0);
-                    if (slot >= 0) {
-                        const double4 vm = map.vslots[slot];
-                        mx = vm.y; my = vm.z; mz = vm.w;
-                        ok = sq3_exact(mx - px, my - py, mz - pz) < max_dist2;
-                    }
+                    const int slot = probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz);
+                    if (slot >= 0) ok = sq3_exact(mx - px, my - py, mz - pz) < max_dist2;
                 }
             }
             const uint32_t okmask = __ballot_sync(kFull, ok);
@@ -729,39 +874,51 @@ icp_match_kernel(MapView map, const float* __restrict__ scan, int n, Pose16 T, i
 // ======================================================================================================================
 // launch wrappers
 // ======================================================================================================================
-int icp_linearize_grid(const IcpParams& prm, int num_sms) {
+int icp_search_grid(const IcpParams& prm, int num_sms) {
     int blocks;
-    if (prm.method == 0 || prm.method == 1) {
+    if (prm.method <= 1) {
         const int tile_pts = kIcpWarps * prm.queries_per_warp;
         blocks = (prm.n + tile_pts - 1) / tile_pts;
-    } else if (prm.method == 2) {
-        blocks = ((prm.n + 31) / 32 + kIcpWarps - 1) / kIcpWarps;
     } else {
-        blocks = static_cast<int>((static_cast<long long>(prm.n) * 8 + kIcpThreads - 1) / kIcpThreads);
+        blocks = ((prm.n + prm.queries_per_warp - 1) / prm.queries_per_warp + kIcpWarps - 1) / kIcpWarps;
     }
-    const int cap = 2 * num_sms;
+    const int cap = 4 * num_sms;
     return blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
 }
 
-cudaError_t launch_icp_begin(IcpState* st, const double T0[16], cudaStream_t s) {
+int icp_accumulate_grid(const IcpParams& prm, int num_sms) {
+    const long long threads = (prm.method == 3) ? static_cast<long long>(prm.n) * 8 : prm.n;
+    long long blocks = (threads + kIcpThreads - 1) / kIcpThreads;
+    const int cap = 2 * num_sms;
+    return blocks < 1 ? 1 : (blocks > cap ? cap : static_cast<int>(blocks));
+}
+
+cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, cudaStream_t s) {
     Pose16 p;
     for (int i = 0; i < 16; ++i) p.m[i] = T0[i];
-    icp_begin_kernel<<<1, 32, 0, s>>>(st, p);
+    icp_begin_kernel<<<1, 32, 0, s>>>(st, p, ticket);
     return cudaGetLastError();
 }
 
-cudaError_t launch_icp_linearize(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, double* partials, int grid, cudaStream_t s) {
-    switch (prm.method) {
-        case 0: icp_points_kernel<0><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, partials); break;
-        case 1: icp_points_kernel<1><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, partials); break;
-        case 2: icp_voxels_kernel<2><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, partials); break;
-        default: icp_voxels_kernel<3><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, partials); break;
+cudaError_t launch_icp_search(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, int* match, int grid, int prune,
+                              cudaStream_t s) {
+    if (prm.method <= 1) {
+        if (prune) icp_search_points_kernel<true><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
+        else icp_search_points_kernel<false><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
+    } else if (prm.method == 2) {
+        icp_search_means_kernel<<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_icp_reduce(IcpState* st, const double* partials, int nblocks, cudaStream_t s) {
-    icp_reduce_kernel<<<1, 256, 0, s>>>(st, partials, nblocks);
+cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const int* match, const IcpParams& prm, IcpState* st, double* partials,
+                                  unsigned int* ticket, int solve_here, int grid, cudaStream_t s) {
+    switch (prm.method) {
+        case 0: icp_accumulate_kernel<0><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 1: icp_accumulate_kernel<1><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 2: icp_accumulate_kernel<2><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
+        default: icp_accumulate_kernel<3><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
+    }
     return cudaGetLastError();
 }
 
@@ -770,12 +927,13 @@ cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_icp_match(const MapView& map, const float* scan, int n, const double T[16], int method, double max_dist2, int* count, double* target, int num_sms, cudaStream_t s) {
+cudaError_t launch_icp_match(const MapView& map, const float* scan, int n, const double T[16], int method, double max_dist2, int prune,
+                             int* count, double* target, int num_sms, cudaStream_t s) {
     Pose16 p;
     for (int i = 0; i < 16; ++i) p.m[i] = T[i];
     int blocks = (n + kIcpWarps - 1) / kIcpWarps;
     blocks = blocks < 1 ? 1 : (blocks > 8 * num_sms ? 8 * num_sms : blocks);
-    icp_match_kernel<<<blocks, kIcpThreads, 0, s>>>(map, scan, n, p, method, max_dist2, count, target);
+    icp_match_kernel<<<blocks, kIcpThreads, 0, s>>>(map, scan, n, p, method, max_dist2, prune, count, target);
     return cudaGetLastError();
 }
 

@@ -9,15 +9,18 @@ constexpr int kIcpThreads = kIcpWarps * 32;
 
 struct Pose16 { double m[16]; };
 
-// blocks the linearisation kernel is launched with (== rows of `partials`)
-int icp_linearize_grid(const IcpParams& prm, int num_sms);
+int icp_search_grid(const IcpParams& prm, int num_sms);
+// blocks of the accumulation kernel (== rows of `partials`)
+int icp_accumulate_grid(const IcpParams& prm, int num_sms);
 
-cudaError_t launch_icp_begin(IcpState* st, const double T0[16], cudaStream_t s);
-cudaError_t launch_icp_linearize(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st,
-                                 double* partials, int grid, cudaStream_t s);
-cudaError_t launch_icp_reduce(IcpState* st, const double* partials, int nblocks, cudaStream_t s);
+cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, cudaStream_t s);
+// P2P / GICP / VGICP correspondence search -> match[n] (no-op for AVGICP, which searches inside the accumulation)
+cudaError_t launch_icp_search(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, int* match,
+                              int grid, int prune, cudaStream_t s);
+cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const int* match, const IcpParams& prm, IcpState* st,
+                                  double* partials, unsigned int* ticket, int solve_here, int grid, cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);
-cudaError_t launch_icp_match(const MapView& map, const float* scan, int n, const double T[16], int method,
-                             double max_dist2, int* count, double* target, int num_sms, cudaStream_t s);
+cudaError_t launch_icp_match(const MapView& map, const float* scan, int n, const double T[16], int method, double max_dist2,
+                             int prune, int* count, double* target, int num_sms, cudaStream_t s);
 
 }  // namespace elm

@@ -158,6 +158,29 @@ class Registration:
         check(lib().elm_registration_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def set_profiling(self, enable):
+        check(lib().elm_registration_set_profiling(self._h, int(bool(enable))))
+
+    def profile(self):
+        """(ms in the search kernel, ms in the accumulate kernel, iterations timed) since set_profiling(True)."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        n = C.c_int64(0)
+        check(lib().elm_registration_profile(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return float(a.value), float(b.value), int(n.value)
+
+    def set_stats(self, enable):
+        check(lib().elm_registration_set_stats(self._h, int(bool(enable))))
+
+    def stats(self):
+        """(map points visited by the P2P/GICP search, queries searched) since set_stats()."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib().elm_registration_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def set_exhaustive(self, exhaustive):
+        """True: visit all 27 voxels like the reference; False (default): exact pruning."""
+        check(lib().elm_registration_set_exhaustive(self._h, int(bool(exhaustive))))
+
     # ---- test hooks ----
     def linearize(self, source_local, voxel_map, pose, cfg):
         src = _xyz(source_local)

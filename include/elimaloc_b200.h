@@ -131,6 +131,23 @@ int elm_correspondences(elm_registration* reg, const elm_map* map, const float* 
 /* Counters of the last enqueue (kernel launches issued on the stream; used by bench.py's gpu_launches). */
 int elm_registration_launch_count(const elm_registration* reg, int64_t* launches);
 
+/* Per-kernel timing: when enabled, the search kernel and the accumulate(+reduce+solve) kernel of every ICP iteration
+ * are bracketed by cudaEvents on the launch stream and elm_register_fetch accumulates the elapsed times.  bench.py's
+ * roofline uses it; in the reference the matching instrumentation is the per-iteration chrono print of
+ * registration.cpp:307-347. */
+int elm_registration_set_profiling(elm_registration* reg, int enable);
+int elm_registration_profile(const elm_registration* reg, double* search_ms, double* accumulate_ms, int64_t* iterations);
+
+/* Counters of the P2P/GICP search (off by default; bench.py uses them to state the bytes the search actually has to
+ * read): map points visited and queries searched since the last elm_registration_set_stats call. */
+int elm_registration_set_stats(elm_registration* reg, int enable);
+int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, uint64_t* queries);
+
+/* Search strategy of P2P/GICP.  Default (0): exact pruning — a voxel of the 27-neighbourhood is skipped when its bounding
+ * box is provably farther than the best candidate already found, which cannot change the result.  1: visit all 27
+ * voxels exactly like GetCorrespondencePoints (voxel_hash_map.cpp:40-51) — same answers, more bytes. */
+int elm_registration_set_exhaustive(elm_registration* reg, int exhaustive);
+
 /* ---- multi-GPU (one process per GPU; scan sharded over ranks, map replicated) --------------------------------- */
 /* unique_id: 128 bytes.  Rank 0 fills it with elm_comm_unique_id and hands it to the other ranks (bench.py uses
  * torch.distributed for that); every rank then calls elm_registration_set_comm.  After that each RunRegister sums the

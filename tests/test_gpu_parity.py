@@ -51,13 +51,32 @@ def test_map_build_matches_oracle(world):
         assert np.abs(ge[k] - oe[k]).max() < 1e-9, k
 
 
+@pytest.mark.parametrize("exhaustive", [False, True])
 @pytest.mark.parametrize("method", METHODS)
-def test_correspondences_bit_exact(world, method):
-    for T in (world["T0"], world["T_true"]):
-        gc, gt = world["greg"].correspondences(world["scan"], world["gm"], T, method, 5.0)
-        oc, ot = O.correspondences(world["om"], world["scan"], T, method, 5.0)
-        assert np.array_equal(gc, oc), NAMES[method]
-        assert np.array_equal(gt, ot), NAMES[method]
+def test_correspondences_bit_exact(world, method, exhaustive):
+    """index-level parity of the search, both with the exact pruning and visiting all 27 voxels like the reference"""
+    world["greg"].set_exhaustive(exhaustive)
+    try:
+        for T in (world["T0"], world["T_true"]):
+            gc, gt = world["greg"].correspondences(world["scan"], world["gm"], T, method, 5.0)
+            oc, ot = O.correspondences(world["om"], world["scan"], T, method, 5.0)
+            assert np.array_equal(gc, oc), NAMES[method]
+            assert np.array_equal(gt, ot), NAMES[method]
+    finally:
+        world["greg"].set_exhaustive(False)
+
+
+def test_correspondences_random_scan_bit_exact(world):
+    """uniformly random scan (most queries far from any map point, many in empty space): P2P search parity"""
+    scan = synth.scan_u(8192, 14.0, seed=77)
+    T = synth.se3([4.5, 4.5, 4.5], [0.1, 0.2, -0.4])
+    for md in (1.0, 5.0):
+        oc, ot = O.correspondences(world["om"], scan, T, E.P2P, md)
+        for exhaustive in (False, True):
+            world["greg"].set_exhaustive(exhaustive)
+            gc, gt = world["greg"].correspondences(scan, world["gm"], T, E.P2P, md)
+            world["greg"].set_exhaustive(False)
+            assert np.array_equal(gc, oc) and np.array_equal(gt, ot)
 
 
 @pytest.mark.parametrize("method", METHODS)
