@@ -225,26 +225,11 @@ int check_method(const elm_map* map, const elm_reg_config* cfg) {
     return ELM_OK;
 }
 
-// Largest queries-per-warp in {32,16,8,4} that still leaves >= 90 % of the last wave of tiles busy.
-int pick_queries_per_warp(int n, int num_sms) {
-    const int slots = 2 * num_sms;
-    int best = 4;
-    double best_eff = -1.0;
-    for (int B = 32; B >= 4; B >>= 1) {
-        const int tiles = (n + elm::kIcpWarps * B - 1) / (elm::kIcpWarps * B);
-        const int waves = (tiles + slots - 1) / slots;
-        const double eff = static_cast<double>(tiles) / (static_cast<double>(waves) * slots);
-        if (eff >= 0.9) return B;
-        if (eff > best_eff) { best_eff = eff; best = B; }
-    }
-    return best;
-}
-
 elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg, size_t n) {
     elm::IcpParams p;
     p.method = cfg->icp_method;
     p.n = static_cast<int>(n);
-    p.queries_per_warp = pick_queries_per_warp(p.n, r->num_sms);
+    p.queries_per_warp = 1;
     p.max_dist2 = cfg->max_search_dist * cfg->max_search_dist;
     p.th = cfg->max_search_dist;
     p.lm_lambda = cfg->lm_lambda;
@@ -533,8 +518,17 @@ int elm_correspondences(elm_registration* reg, const elm_map* map, const float* 
         reg->hook_cap = n * 7;
     }
     ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
-    ELM_CUDA(elm::launch_icp_match(map->view(), reg->d_scan, static_cast<int>(n), T, method, max_search_dist * max_search_dist,
-                                   reg->prune, reg->d_count, reg->d_target, reg->num_sms, reg->stream));
+    // the hook runs the PRODUCTION search kernel and only converts its match[] into positions
+    c.max_search_dist = max_search_dist;
+    const elm::IcpParams prm = make_params(reg, &c, n);
+    rc = ensure_match(reg, n);
+    if (rc) return rc;
+    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
+    if (method != ELM_AVGICP)
+        ELM_CUDA(elm::launch_icp_search(map->view(), reg->d_scan, prm, reg->d_state, reg->d_match, elm::icp_search_grid(prm, reg->num_sms),
+                                        reg->prune, reg->stream));
+    ELM_CUDA(elm::launch_icp_export(map->view(), reg->d_scan, reg->d_match, static_cast<int>(n), reg->d_state, method,
+                                    max_search_dist * max_search_dist, reg->d_count, reg->d_target, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(count, reg->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(target, reg->d_target, n * K * 3 * sizeof(double), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));

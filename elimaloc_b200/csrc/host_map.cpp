@@ -209,7 +209,7 @@ void HostMap::build_table() {
     slots.assign(capacity, Slot{0xffffffffu, 0xffffffffu, 0, 0});
     slot_voxel.assign(capacity, -1);
     for (size_t v = 0; v < V(); ++v) {
-        uint32_t h = static_cast<uint32_t>(mix_key(vkey[v])) & mask;
+        uint32_t h = home_slot(vkey[v]) & mask;
         while (slot_voxel[h] >= 0) h = (h + 1) & mask;
         slots[h] = Slot{static_cast<uint32_t>(vkey[v]), static_cast<uint32_t>(vkey[v] >> 32), vstart[v], vstart[v + 1] - vstart[v]};
         slot_voxel[h] = static_cast<int32_t>(v);
@@ -218,7 +218,7 @@ void HostMap::build_table() {
 
 int64_t HostMap::find(uint64_t key) const {
     if (slots.empty()) return -1;
-    uint32_t h = static_cast<uint32_t>(mix_key(key)) & mask;
+    uint32_t h = home_slot(key) & mask;
     for (;;) {
         const int32_t v = slot_voxel[h];
         if (v < 0) return -1;

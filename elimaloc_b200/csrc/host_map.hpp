@@ -13,29 +13,9 @@
 #include <string>
 #include <vector>
 
+#include "voxel_key.hpp"
+
 namespace elm {
-
-constexpr int kKeyBits = 21;                       // per-axis field width of a packed key
-constexpr int32_t kKeyBias = 1 << (kKeyBits - 1);  // keys in [-2^20, 2^20) per axis
-constexpr uint64_t kEmptyKey = ~0ull;
-
-inline bool key_in_range(int32_t k) { return k >= -kKeyBias && k < kKeyBias; }
-inline uint64_t pack_key(int32_t x, int32_t y, int32_t z) {
-    return (static_cast<uint64_t>(static_cast<uint32_t>(x + kKeyBias)) << (2 * kKeyBits)) |
-           (static_cast<uint64_t>(static_cast<uint32_t>(y + kKeyBias)) << kKeyBits) |
-           static_cast<uint64_t>(static_cast<uint32_t>(z + kKeyBias));
-}
-inline void unpack_key(uint64_t k, int32_t& x, int32_t& y, int32_t& z) {
-    const uint64_t m = (1ull << kKeyBits) - 1;
-    x = static_cast<int32_t>((k >> (2 * kKeyBits)) & m) - kKeyBias;
-    y = static_cast<int32_t>((k >> kKeyBits) & m) - kKeyBias;
-    z = static_cast<int32_t>(k & m) - kKeyBias;
-}
-// murmur3 finaliser; the reference's 20-bit hash (voxel_hash_map.hpp:150-155) is not observable behaviour.
-inline uint64_t mix_key(uint64_t k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-    return k;
-}
 
 // One open-addressed slot, 16 bytes: {key lo, key hi, first stored point, stored count}.
 struct Slot { uint32_t key_lo, key_hi, start, count; };

@@ -9,7 +9,7 @@
 //   icp_solve_kernel           overlap gate, LM-damped LDLT solve, exp map, pose update, termination test
 //        (reg.cpp:349-356, 53-65, 136-151, 378-387) — separate launch only in multi-GPU mode, after the ncclAllReduce
 //   icp_begin_kernel           state <- initial guess (+ inverses)                      reg.cpp:298,24,79
-//   icp_match_kernel           correspondence dump for the parity tests
+//   icp_export_kernel          match[] -> (count, target) dump for the parity tests
 //
 // Exactness: the transformed scan point, its voxel key and every candidate distance are computed in fp64 with explicit
 // round-to-nearest mul/add (never contracted into FMA) in the same association order as the CPU reference, so the
@@ -18,14 +18,13 @@
 // pruning: identical result, fewer bytes); `prune = 0` visits all 27 voxels like the reference does.
 // The accumulation that follows is plain fp64 (FMA allowed) and is compared with a tolerance.
 #include "icp_kernels.cuh"
+#include "voxel_key.hpp"
 
 namespace elm {
 
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kKeyBits = 21;
-constexpr int kKeyBias = 1 << (kKeyBits - 1);
 constexpr double kDblMax = 1.7976931348623157e308;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -68,69 +67,36 @@ __device__ __forceinline__ int voxel_floor(double p, double vs, float* frac = nu
     // saturate far outside the table's key range instead of the reference's undefined int overflow
     return (f >= 2.0e9) ? 2000000000 : ((f <= -2.0e9) ? -2000000000 : static_cast<int>(f));
 }
-__device__ __forceinline__ bool key_ok(int k) { return k >= -kKeyBias && k < kKeyBias; }
-__device__ __forceinline__ uint64_t pack_key(int x, int y, int z) {
-    return (static_cast<uint64_t>(static_cast<uint32_t>(x + kKeyBias)) << (2 * kKeyBits)) |
-           (static_cast<uint64_t>(static_cast<uint32_t>(y + kKeyBias)) << kKeyBits) |
-           static_cast<uint64_t>(static_cast<uint32_t>(z + kKeyBias));
-}
-__device__ __forceinline__ uint32_t hash_key(uint64_t k) {  // murmur3 finaliser, same as host_map.hpp
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-    return static_cast<uint32_t>(k);
-}
-// Linear probe of the 16-B table; returns the slot index or -1.  start/count filled on a hit.
-__device__ __forceinline__ int probe(const uint4* __restrict__ slots, uint32_t mask, uint64_t key, uint32_t& start, uint32_t& count) {
-    uint32_t h = hash_key(key) & mask;
-    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
-    for (uint32_t i = 0; i <= mask; ++i) {  // bounded: a corrupt table must never hang the GPU
-        const uint4 s = __ldg(slots + h);
-        if (s.x == klo && s.y == khi) { start = s.z; count = s.w; return static_cast<int>(h); }
-        if ((s.x & s.y) == 0xffffffffu) return -1;
-        h = (h + 1) & mask;
-    }
-    return -1;
-}
-// Same probe when the first slot has already been fetched (software-pipelined across queries).
+// Same probe when the home slot has already been fetched (lets the first loads of several probes overlap).
 __device__ __forceinline__ void probe_resume(const uint4* __restrict__ slots, uint32_t mask, uint64_t key, uint32_t h, uint4 s,
                                              uint32_t& start, uint32_t& count) {
     const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
+    count = 0;
     for (uint32_t i = 0; i <= mask; ++i) {
         if (s.x == klo && s.y == khi) { start = s.z; count = s.w; return; }
-        if ((s.x & s.y) == 0xffffffffu) break;
+        if ((s.x & s.y) == 0xffffffffu) return;
         h = (h + 1) & mask;
         s = __ldg(slots + h);
     }
-    count = 0;
 }
 // Linear probe of the 32-B VGICP table {key, mean}; returns the slot or -1 and the mean.
 __device__ __forceinline__ int probe_mean(const double4* __restrict__ vslots, uint32_t mask, uint64_t key, double& mx, double& my, double& mz) {
-    uint32_t h = hash_key(key) & mask;
+    uint32_t h = home_slot(key) & mask;
     for (uint32_t i = 0; i <= mask; ++i) {
         const double2 a = __ldg(reinterpret_cast<const double2*>(vslots + h));
         const double2 b = __ldg(reinterpret_cast<const double2*>(vslots + h) + 1);
         const uint64_t k = static_cast<uint64_t>(__double_as_longlong(a.x));
         if (k == key) { mx = a.y; my = b.x; mz = b.y; return static_cast<int>(h); }
-        if (k == ~0ull) return -1;
+        if (k == kEmptyKey) return -1;
         h = (h + 1) & mask;
     }
     return -1;
 }
 
-// ---- warp argmin over (fp64 distance >= 0, visit order) --------------------------------------------------------
-// Returns the lane holding the smallest (d2, ord) pair, or -1 when no lane has a candidate (ord == 0xffffffff);
-// *best_out receives the smallest distance (kDblMax when there is none).
-__device__ __forceinline__ int warp_argmin(double d2, uint32_t ord, double* best_out = nullptr) {
-    const uint32_t hi = static_cast<uint32_t>(__double2hiint(d2));
-    const uint32_t lo = static_cast<uint32_t>(__double2loint(d2));
-    const uint32_t mhi = __reduce_min_sync(kFull, hi);
-    const bool a = (hi == mhi);
-    const uint32_t mlo = __reduce_min_sync(kFull, a ? lo : 0xffffffffu);
-    const bool b = a && (lo == mlo);
-    const uint32_t mord = __reduce_min_sync(kFull, b ? ord : 0xffffffffu);
-    if (best_out) *best_out = __hiloint2double(static_cast<int>(mhi), static_cast<int>(mlo));
-    if (mord == 0xffffffffu) return -1;
-    const uint32_t who = __ballot_sync(kFull, b && ord == mord);
-    return __ffs(who) - 1;
+// Linear probe of the 16-B table.  count = 0 on a miss.
+__device__ __forceinline__ void probe(const uint4* __restrict__ slots, uint32_t mask, uint64_t key, uint32_t& start, uint32_t& count) {
+    const uint32_t h = home_slot(key) & mask;
+    probe_resume(slots, mask, key, h, __ldg(slots + h), start, count);
 }
 
 #define ELM_EVAL_CANDIDATE(Q, ORD, IDX)                                                                                  \
@@ -140,111 +106,101 @@ __device__ __forceinline__ int warp_argmin(double d2, uint32_t ord, double* best
         if (d2__ < best || (d2__ == best && (ORD) < bord)) { best = d2__; bord = (ORD); bidx = (IDX); }                   \
     }
 
-// Per-lane description of "its" voxel of the 27-neighbourhood (lane L < 27 <-> offsets x-outer / y / z-inner, the
-// reference's visit order, vhm.cpp:234-240).
-struct LaneVoxel {
-    int ox, oy, oz;
-    bool active;
-};
-__device__ __forceinline__ LaneVoxel lane_voxel(int lane) {
-    LaneVoxel v;
-    v.active = lane < 27;
-    v.ox = lane / 9 - 1; v.oy = (lane / 3) % 3 - 1; v.oz = lane % 3 - 1;
-    return v;
-}
-
-// Squared lower bound (fp32, in units of voxel_size^2, deliberately under-estimated) of the distance from the query to
-// any point STORED under key (k + o) per axis.  Insert keys truncate toward zero (vhm.cpp:275), so along one axis the
-// voxel with key c holds p/vs in [c, c+1) for c > 0, (c-1, c] for c < 0 and (-1, 1) for c == 0.
-__device__ __forceinline__ float axis_gap(int kq, int o, float f) {
+// Squared-distance lower bound helper (fp32, units of voxel_size, deliberately under-estimated): gap along one axis
+// between the query and any point STORED under key (kq + o).  Insert keys truncate toward zero (vhm.cpp:275), so along
+// one axis the voxel with key c holds p/vs in [c, c+1) for c > 0, (c-1, c] for c < 0 and (-1, 1) for c == 0.
+__device__ __forceinline__ float axis_gap2(int kq, int o, float f) {
     const int c = kq + o;
     const float lo = static_cast<float>(o - (c <= 0 ? 1 : 0));
     const float hi = static_cast<float>(o + (c >= 0 ? 1 : 0));
-    const float g = fmaxf(fmaxf(lo - f, f - hi), 0.0f);
-    return fmaxf(g - 1e-5f, 0.0f);
+    const float g = fmaxf(fmaxf(fmaxf(lo - f, f - hi), 0.0f) - 1e-5f, 0.0f);
+    return g * g;
 }
 
-// Nearest stored map point of the 27 voxels around the query, warp-cooperative (vhm.cpp:35-53).
-//   start/count : this lane's voxel (count == 0 when absent), already probed
-//   returns the winning point index (warp-uniform) or -1.
-// Visit order of the reference: voxels x-outer / y / z-inner, insertion order inside a voxel, strict < (vhm.cpp:45).
-// The three z-voxels of a column are one contiguous run of `pts`.
+// One query's nearest stored map point among the 27 voxels around it (vhm.cpp:35-53), ONE THREAD PER QUERY: with the
+// exact pruning only ~45 of the ~240 candidates survive, so per-query control (probes, bounds, loop bookkeeping) is
+// what costs, and one thread per query amortises it over the 32 queries of a warp.  Each thread streams contiguous
+// runs of `pts` (the three z-voxels of a column are one run).  Reference visit order = voxels x-outer / y / z-inner
+// (vhm.cpp:234-240), insertion order inside a voxel, strict < (vhm.cpp:45): encoded in `ord`, so any visiting order
+// yields the reference's winner.  Returns the winning point index or -1.
 template <bool PRUNE>
-__device__ __forceinline__ int nearest_point_27(const float4* __restrict__ pts, uint32_t start, uint32_t count, double px, double py,
-                                                double pz, int kx, int ky, int kz, float fx, float fy, float fz, float inv_vs2_dn,
-                                                const LaneVoxel& lv, int lane, uint32_t& visited) {
+__device__ __forceinline__ int search_query(const MapView& map, double px, double py, double pz, int kx, int ky, int kz, float fx, float fy,
+                                            float fz, float inv_vs2_up, uint32_t& visited) {
+    const uint4* __restrict__ slots = map.slots;
+    const float4* __restrict__ pts = map.pts;
+    const uint32_t mask = map.mask;
     double best = kDblMax;
     uint32_t bord = 0xffffffffu, bidx = 0;
-    // column c = lanes 3c..3c+2
-    const uint32_t c1 = __shfl_down_sync(kFull, count, 1), c2 = __shfl_down_sync(kFull, count, 2);
-    const uint32_t s1 = __shfl_down_sync(kFull, start, 1), s2 = __shfl_down_sync(kFull, start, 2);
-    const uint32_t runlen = count + c1 + c2;
-    const uint32_t runstart = count ? start : (c1 ? s1 : s2);
+    // the whole neighbourhood is inside the key range unless the centre sits on its border
+    const bool interior = kx > -kKeyBias && kx < kKeyBias - 1 && ky > -kKeyBias && ky < kKeyBias - 1 && kz > -kKeyBias && kz < kKeyBias - 1;
+    auto in_range = [&](int x, int y, int z) { return interior || (key_in_range(x) && key_in_range(y) && key_in_range(z)); };
+    // one column (x, y, z-1..z+1) = one contiguous run; ord base = index of its first voxel in the visit order
+    auto visit_column = [&](int x, int y, uint32_t L0) {
+        uint32_t s0 = 0, c0 = 0, s1 = 0, c1 = 0, s2 = 0, c2 = 0;
+        if (in_range(x, y, kz - 1)) probe(slots, mask, pack_key(x, y, kz - 1), s0, c0);
+        if (in_range(x, y, kz)) probe(slots, mask, pack_key(x, y, kz), s1, c1);
+        if (in_range(x, y, kz + 1)) probe(slots, mask, pack_key(x, y, kz + 1), s2, c2);
+        const uint32_t rl = c0 + c1 + c2;
+        const uint32_t rs = c0 ? s0 : (c1 ? s1 : s2);
+        visited += rl;
+#pragma unroll 4
+        for (uint32_t o = 0; o < rl; ++o) {
+            const float4 q = __ldg(pts + rs + o);
+            ELM_EVAL_CANDIDATE(q, (L0 << 16) + o, rs + o);
+        }
+    };
     if (PRUNE) {
-        // phase A: the centre column (lanes 12..14) — the query's own voxel and its z-neighbours
-        {
-            const uint32_t rs = __shfl_sync(kFull, runstart, 12), rl = __shfl_sync(kFull, runlen, 12);
-            visited += rl;
-            for (uint32_t o = lane; o < rl; o += 32) {
-                const float4 q = __ldg(pts + rs + o);
-                ELM_EVAL_CANDIDATE(q, (12u << 16) + o, rs + o);
-            }
-        }
-        double bestA;
-        warp_argmin(best, bord, &bestA);
+        // phase A: the centre column — the query's own cell and its z-neighbours
+        visit_column(kx, ky, 12u);
+        const float bound = __double2float_ru(best) * inv_vs2_up;  // best distance so far, in voxel units, rounded up
         // phase B: every other voxel whose box could still hold a point at least as close
-        bool need = false;
-        if (lv.active && count > 0 && (lane < 12 || lane > 14)) {
-            const float gx = axis_gap(kx, lv.ox, fx), gy = axis_gap(ky, lv.oy, fy), gz = axis_gap(kz, lv.oz, fz);
-            const float lb = (gx * gx + gy * gy + gz * gz) * 0.9999f;
-            need = !(lb > __double2float_ru(bestA) * inv_vs2_dn);  // prune only when provably farther
+        const float gx[3] = {axis_gap2(kx, -1, fx), axis_gap2(kx, 0, fx), axis_gap2(kx, 1, fx)};
+        const float gy[3] = {axis_gap2(ky, -1, fy), axis_gap2(ky, 0, fy), axis_gap2(ky, 1, fy)};
+        const float gz[3] = {axis_gap2(kz, -1, fz), axis_gap2(kz, 0, fz), axis_gap2(kz, 1, fz)};
+        uint32_t need = 0;
+#pragma unroll
+        for (int L = 0; L < 27; ++L) {
+            if (L >= 12 && L <= 14) continue;
+            const float lb = (gx[L / 9] + gy[(L / 3) % 3] + gz[L % 3]) * 0.9999f;
+            if (!(lb > bound)) need |= 1u << L;  // prune only when provably farther
         }
-        uint32_t todo = __ballot_sync(kFull, need);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t vs0 = __shfl_sync(kFull, start, src), vc = __shfl_sync(kFull, count, src);
+        while (need) {
+            const int L = __ffs(need) - 1;
+            need &= need - 1;
+            const int x = kx + L / 9 - 1, y = ky + (L / 3) % 3 - 1, z = kz + L % 3 - 1;
+            if (!in_range(x, y, z)) continue;
+            uint32_t vs0 = 0, vc = 0;
+            probe(slots, mask, pack_key(x, y, z), vs0, vc);
             visited += vc;
-            for (uint32_t o = lane; o < vc; o += 32) {
+#pragma unroll 4
+            for (uint32_t o = 0; o < vc; ++o) {
                 const float4 q = __ldg(pts + vs0 + o);
-                ELM_EVAL_CANDIDATE(q, (static_cast<uint32_t>(src) << 16) + o, vs0 + o);
+                ELM_EVAL_CANDIDATE(q, (static_cast<uint32_t>(L) << 16) + o, vs0 + o);
             }
         }
     } else {
-        const uint32_t colmask = __ballot_sync(kFull, lv.active && (lane % 3 == 0) && runlen > 0);
-        uint32_t todo = colmask;
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t rs = __shfl_sync(kFull, runstart, src), rl = __shfl_sync(kFull, runlen, src);
-            visited += rl;
-            for (uint32_t o = lane; o < rl; o += 32) {
-                const float4 q = __ldg(pts + rs + o);
-                ELM_EVAL_CANDIDATE(q, (static_cast<uint32_t>(src) << 16) + o, rs + o);
-            }
-        }
+        // reference-style exhaustive visit: all 9 columns of 3 voxels
+#pragma unroll 1
+        for (int c = 0; c < 9; ++c) visit_column(kx + c / 3 - 1, ky + c % 3 - 1, static_cast<uint32_t>(3 * c));
     }
-    const int wl = warp_argmin(best, bord);
-    if (wl < 0) return -1;
-    return static_cast<int>(__shfl_sync(kFull, bidx, wl));
+    return (bord == 0xffffffffu) ? -1 : static_cast<int>(bidx);
 }
 
-// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115).  Returns the winning slot index or -1.
-__device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, double py, double pz, int kx, int ky, int kz, int lane) {
-    double d2 = kDblMax;
-    uint32_t ord = 0xffffffffu;
+// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115), one thread per query.  Returns the winning slot or -1.
+__device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, double py, double pz, int kx, int ky, int kz) {
+    double best = kDblMax;
     int slot = -1;
-    if (lane < 27) {
-        const int x = kx + lane / 9 - 1, y = ky + (lane / 3) % 3 - 1, z = kz + lane % 3 - 1;
-        if (key_ok(x) && key_ok(y) && key_ok(z)) {
-            double mx, my, mz;
-            slot = probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz);
-            if (slot >= 0) { d2 = sq3_exact(mx - px, my - py, mz - pz); ord = lane; }
-        }
+#pragma unroll 1
+    for (int L = 0; L < 27; ++L) {  // reference visit order; strict < keeps the first of equals
+        const int x = kx + L / 9 - 1, y = ky + (L / 3) % 3 - 1, z = kz + L % 3 - 1;
+        if (!(key_in_range(x) && key_in_range(y) && key_in_range(z))) continue;
+        double mx, my, mz;
+        const int s = probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz);
+        if (s < 0) continue;
+        const double d2 = sq3_exact(mx - px, my - py, mz - pz);
+        if (d2 < best) { best = d2; slot = s; }
     }
-    const int wl = warp_argmin(d2, ord);
-    if (wl < 0) return -1;
-    return __shfl_sync(kFull, slot, wl);
+    return slot;
 }
 
 }  // namespace
@@ -252,28 +208,26 @@ __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, do
 // ======================================================================================================================
 // search: P2P / GICP
 // ======================================================================================================================
+// Block = 256 threads, one scan point each.  A tile of the packed scan (256 points x 12 B) is pulled into shared memory
+// by the TMA bulk-copy engine (double-buffered when a block owns several tiles); each thread transforms its point
+// (TransformPoints fused, reg.hpp:136-148) and searches it.
 template <bool PRUNE>
-__global__ void __launch_bounds__(kIcpThreads, 4)
+__global__ void __launch_bounds__(kIcpThreads, 3)
 icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, int* __restrict__ match) {
-    __shared__ __align__(16) float s_tile[2][kIcpWarps * 32 * 3];
+    __shared__ __align__(16) float s_tile[2][kIcpThreads * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_T[12];
-    __shared__ double s_qp[kIcpWarps][3][32];
-    __shared__ int s_qk[kIcpWarps][3][32];
-    __shared__ float s_qf[kIcpWarps][3][32];
 
     if (st->done) return;  // loop already left (termination / overlap failure)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid < 12) s_T[tid] = st->T[tid];
 
-    const int B = prm.queries_per_warp;
-    const int tile_pts = kIcpWarps * B;
+    constexpr int tile_pts = kIcpThreads;
     const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     __syncthreads();
 
-    // scan tile -> shared memory through the TMA bulk-copy engine (packed xyz, 12 B/point)
     auto tile_count = [&](int t) { return min(tile_pts, prm.n - t * tile_pts); };
     auto tile_tma_ok = [&](int t) { return base_aligned && ((tile_count(t) * 12) & 15) == 0; };
     auto issue = [&](int t, int buf) {
@@ -281,12 +235,9 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams 
         mbar_expect_tx(&s_bar[buf], bytes);
         tma_load_1d(s_tile[buf], scan + static_cast<size_t>(t) * tile_pts * 3, bytes, &s_bar[buf]);
     };
+    const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
 
-    const LaneVoxel lv = lane_voxel(lane);
-    const float inv_vs2_dn = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
-    const uint4* __restrict__ slots = map.slots;
-    const uint32_t mask = map.mask;
-
+    uint32_t visited = 0, searched = 0;
     int tile = blockIdx.x, buf = 0;
     uint32_t phase[2] = {0, 0};
     if (tile < ntiles && tid == 0 && tile_tma_ok(tile)) issue(tile, 0);
@@ -301,59 +252,26 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams 
             for (int i = tid; i < nf; i += kIcpThreads) s_tile[buf][i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
             __syncthreads();
         }
-        const int nq = min(B, tile_count(tile) - warp * B);  // queries of this warp in this tile (may be <= 0)
-        // stage 1: each lane transforms one query point and publishes it to its warp
-        if (lane < nq) {
-            const float* sp = &s_tile[buf][(warp * B + lane) * 3];
+        if (tid < tile_count(tile)) {
+            const float* sp = &s_tile[buf][tid * 3];
             const double sx = sp[0], sy = sp[1], sz = sp[2];
             const double px = row_apply_exact(s_T, 0, sx, sy, sz);
             const double py = row_apply_exact(s_T, 1, sx, sy, sz);
             const double pz = row_apply_exact(s_T, 2, sx, sy, sz);
             float fx, fy, fz;
-            s_qp[warp][0][lane] = px; s_qp[warp][1][lane] = py; s_qp[warp][2][lane] = pz;
-            s_qk[warp][0][lane] = voxel_floor(px, map.voxel_size, &fx);
-            s_qk[warp][1][lane] = voxel_floor(py, map.voxel_size, &fy);
-            s_qk[warp][2][lane] = voxel_floor(pz, map.voxel_size, &fz);
-            s_qf[warp][0][lane] = fx; s_qf[warp][1][lane] = fy; s_qf[warp][2][lane] = fz;
+            const int kx = voxel_floor(px, map.voxel_size, &fx), ky = voxel_floor(py, map.voxel_size, &fy), kz = voxel_floor(pz, map.voxel_size, &fz);
+            match[static_cast<size_t>(tile) * tile_pts + tid] = search_query<PRUNE>(map, px, py, pz, kx, ky, kz, fx, fy, fz, inv_vs2_up, visited);
+            ++searched;
         }
-        __syncwarp();
-        // stage 2: the warp searches its queries one after another; the first table probe of query q+1 is in flight
-        // while query q scans its candidates
-        int my_idx = -1;
-        uint32_t visited = 0;
-        uint64_t key_n = 0;
-        uint32_t h_n = 0;
-        uint4 slot_n = make_uint4(0xffffffffu, 0xffffffffu, 0, 0);
-        bool ok_n = false;
-        auto first_probe = [&](int q) {
-            const int x = s_qk[warp][0][q] + lv.ox, y = s_qk[warp][1][q] + lv.oy, z = s_qk[warp][2][q] + lv.oz;
-            ok_n = lv.active && key_ok(x) && key_ok(y) && key_ok(z);
-            if (ok_n) {
-                key_n = pack_key(x, y, z);
-                h_n = hash_key(key_n) & mask;
-                slot_n = __ldg(slots + h_n);
-            }
-        };
-        if (nq > 0) first_probe(0);
-        for (int q = 0; q < nq; ++q) {
-            const uint64_t key = key_n;
-            const uint32_t h = h_n;
-            const uint4 sl = slot_n;
-            const bool ok = ok_n;
-            if (q + 1 < nq) first_probe(q + 1);
-            uint32_t start = 0, count = 0;
-            if (ok) probe_resume(slots, mask, key, h, sl, start, count);
-            const int w = nearest_point_27<PRUNE>(map.pts, start, count, s_qp[warp][0][q], s_qp[warp][1][q], s_qp[warp][2][q],
-                                                  s_qk[warp][0][q], s_qk[warp][1][q], s_qk[warp][2][q], s_qf[warp][0][q],
-                                                  s_qf[warp][1][q], s_qf[warp][2][q], inv_vs2_dn, lv, lane, visited);
-            if (lane == q) my_idx = w;
-        }
-        if (prm.stats && lane == 0 && nq > 0) {
+        __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
+    }
+    if (prm.stats) {
+        // warp-aggregate, one atomic pair per warp
+        for (int o = 16; o > 0; o >>= 1) { visited += __shfl_xor_sync(kFull, visited, o); searched += __shfl_xor_sync(kFull, searched, o); }
+        if ((tid & 31) == 0 && searched) {
             atomicAdd(prm.stats, static_cast<unsigned long long>(visited));
-            atomicAdd(prm.stats + 1, static_cast<unsigned long long>(nq));
+            atomicAdd(prm.stats + 1, static_cast<unsigned long long>(searched));
         }
-        if (lane < nq) match[static_cast<size_t>(tile) * tile_pts + warp * B + lane] = my_idx;
-        __syncthreads();  // every warp is done with s_tile[buf] before it is refilled
     }
 }
 
@@ -364,28 +282,14 @@ __global__ void __launch_bounds__(kIcpThreads, 4)
 icp_search_means_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, int* __restrict__ match) {
     __shared__ double s_T[12];
     if (st->done) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid < 12) s_T[tid] = st->T[tid];
     __syncthreads();
-    const int B = prm.queries_per_warp;
-    const int nbatch = (prm.n + B - 1) / B;
-    for (int b = blockIdx.x * kIcpWarps + warp; b < nbatch; b += gridDim.x * kIcpWarps) {
-        const int i = b * B + lane;
-        double px = 0, py = 0, pz = 0;
-        int kx = 0, ky = 0, kz = 0;
-        const int nq = min(B, prm.n - b * B);
-        if (lane < nq) {
-            const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
-            px = row_apply_exact(s_T, 0, sx, sy, sz); py = row_apply_exact(s_T, 1, sx, sy, sz); pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            kx = voxel_floor(px, map.voxel_size); ky = voxel_floor(py, map.voxel_size); kz = voxel_floor(pz, map.voxel_size);
-        }
-        int my_slot = -1;
-        for (int q = 0; q < nq; ++q) {
-            const double qx = __shfl_sync(kFull, px, q), qy = __shfl_sync(kFull, py, q), qz = __shfl_sync(kFull, pz, q);
-            const int w = nearest_mean_27(map, qx, qy, qz, __shfl_sync(kFull, kx, q), __shfl_sync(kFull, ky, q), __shfl_sync(kFull, kz, q), lane);
-            if (lane == q) my_slot = w;
-        }
-        if (lane < nq) match[i] = my_slot;
+    for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
+        const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
+        const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+        const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+        match[i] = nearest_mean_27(map, px, py, pz, kx, ky, kz);
     }
 }
 
@@ -683,7 +587,7 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
             const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
             int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
             kx += (j == 1) - (j == 2); ky += (j == 3) - (j == 4); kz += (j == 5) - (j == 6);
-            if (!(key_ok(kx) && key_ok(ky) && key_ok(kz))) continue;
+            if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) continue;
             double mx, my, mz;
             const int slot = probe_mean(map.vslots, map.mask, pack_key(kx, ky, kz), mx, my, mz);
             if (slot < 0) continue;
@@ -812,63 +716,46 @@ __global__ void icp_solve_kernel(IcpState* st, IcpParams prm) {
     solve_step(st, prm, &s_solve);
 }
 
-// ---- correspondence dump (test hook) -----------------------------------------------------------------------------
+// ---- correspondence dump (test hook): turns the production search's match[] into (count, target) ---------------------
 __global__ void __launch_bounds__(kIcpThreads)
-icp_match_kernel(MapView map, const float* __restrict__ scan, int n, Pose16 T, int method, double max_dist2, int prune, int* __restrict__ count,
-                 double* __restrict__ target) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const LaneVoxel lv = lane_voxel(lane);
-    const float inv_vs2_dn = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
-    for (int i = gw; i < n; i += nw) {
+icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ match, int n, const IcpState* __restrict__ st, int method,
+                  double max_dist2, int* __restrict__ count, double* __restrict__ target) {
+    const double* T = st->T;
+    if (method == 3) {
+        // AVGICP: every voxel of {c, +x, -x, +y, -y, +z, -z} whose mean is in range, emitted in that order (vhm.cpp:153-206)
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
         const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
-        const double px = row_apply_exact(T.m, 0, sx, sy, sz), py = row_apply_exact(T.m, 1, sx, sy, sz), pz = row_apply_exact(T.m, 2, sx, sy, sz);
-        float fx, fy, fz;
-        const int kx = voxel_floor(px, map.voxel_size, &fx), ky = voxel_floor(py, map.voxel_size, &fy), kz = voxel_floor(pz, map.voxel_size, &fz);
-        if (method == 0 || method == 1) {
-            uint32_t start = 0, cnt = 0;
-            if (lv.active) {
-                const int x = kx + lv.ox, y = ky + lv.oy, z = kz + lv.oz;
-                if (key_ok(x) && key_ok(y) && key_ok(z)) { if (probe(map.slots, map.mask, pack_key(x, y, z), start, cnt) < 0) cnt = 0; }
-            }
-            uint32_t visited = 0;
-            const int w = prune ? nearest_point_27<true>(map.pts, start, cnt, px, py, pz, kx, ky, kz, fx, fy, fz, inv_vs2_dn, lv, lane, visited)
-                                : nearest_point_27<false>(map.pts, start, cnt, px, py, pz, kx, ky, kz, fx, fy, fz, inv_vs2_dn, lv, lane, visited);
-            double tx = 0, ty = 0, tz = 0;
-            if (w >= 0) { const float4 t = map.pts[w]; tx = t.x; ty = t.y; tz = t.z; }
-            const bool ok = sq3_exact(tx - px, ty - py, tz - pz) < max_dist2;
-            if (lane == 0) {
-                count[i] = ok ? 1 : 0;
-                target[3 * static_cast<size_t>(i)] = ok ? tx : 0.0; target[3 * static_cast<size_t>(i) + 1] = ok ? ty : 0.0; target[3 * static_cast<size_t>(i) + 2] = ok ? tz : 0.0;
-            }
-        } else if (method == 2) {
-            const int w = nearest_mean_27(map, px, py, pz, kx, ky, kz, lane);
-            double mx = 0, my = 0, mz = 0;
-            if (w >= 0) { const double4 vm = map.vslots[w]; mx = vm.y; my = vm.z; mz = vm.w; }
-            const bool ok = sq3_exact(mx - px, my - py, mz - pz) < max_dist2;
-            if (lane == 0) {
-                count[i] = ok ? 1 : 0;
-                target[3 * static_cast<size_t>(i)] = ok ? mx : 0.0; target[3 * static_cast<size_t>(i) + 1] = ok ? my : 0.0; target[3 * static_cast<size_t>(i) + 2] = ok ? mz : 0.0;
-            }
-        } else {
-            bool ok = false;
-            double mx = 0, my = 0, mz = 0;
-            if (lane < 7) {
-                const int x = kx + (lane == 1) - (lane == 2), y = ky + (lane == 3) - (lane == 4), z = kz + (lane == 5) - (lane == 6);
-                if (key_ok(x) && key_ok(y) && key_ok(z)) {
-                    const int slot = probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz);
-                    if (slot >= 0) ok = sq3_exact(mx - px, my - py, mz - pz) < max_dist2;
-                }
-            }
-            const uint32_t okmask = __ballot_sync(kFull, ok);
-            const int pos = __popc(okmask & ((1u << lane) - 1));  // emission order = voxel order
-            double* t = target + static_cast<size_t>(i) * 21;
-            if (lane < 7) { t[3 * lane] = 0.0; t[3 * lane + 1] = 0.0; t[3 * lane + 2] = 0.0; }
-            __syncwarp();
-            if (ok) { t[3 * pos] = mx; t[3 * pos + 1] = my; t[3 * pos + 2] = mz; }
-            if (lane == 0) count[i] = __popc(okmask);
+        const double px = row_apply_exact(T, 0, sx, sy, sz), py = row_apply_exact(T, 1, sx, sy, sz), pz = row_apply_exact(T, 2, sx, sy, sz);
+        const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+        double* t = target + static_cast<size_t>(i) * 21;
+        int c = 0;
+        for (int j = 0; j < 7; ++j) {
+            const int x = kx + (j == 1) - (j == 2), y = ky + (j == 3) - (j == 4), z = kz + (j == 5) - (j == 6);
+            if (!(key_in_range(x) && key_in_range(y) && key_in_range(z))) continue;
+            double mx, my, mz;
+            if (probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz) < 0) continue;
+            if (sq3_exact(mx - px, my - py, mz - pz) < max_dist2) { t[3 * c] = mx; t[3 * c + 1] = my; t[3 * c + 2] = mz; ++c; }
         }
+        count[i] = c;
+        for (; c < 7; ++c) { t[3 * c] = 0.0; t[3 * c + 1] = 0.0; t[3 * c + 2] = 0.0; }
+        return;
     }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
+    const double px = row_apply_exact(T, 0, sx, sy, sz), py = row_apply_exact(T, 1, sx, sy, sz), pz = row_apply_exact(T, 2, sx, sy, sz);
+    const int m = match[i];
+    double tx = 0.0, ty = 0.0, tz = 0.0;  // Q2 default
+    if (m >= 0) {
+        if (method == 2) { const double4 vm = map.vslots[m]; tx = vm.y; ty = vm.z; tz = vm.w; }
+        else { const float4 t = map.pts[m]; tx = t.x; ty = t.y; tz = t.z; }
+    }
+    const bool ok = sq3_exact(tx - px, ty - py, tz - pz) < max_dist2;
+    count[i] = ok ? 1 : 0;
+    target[3 * static_cast<size_t>(i)] = ok ? tx : 0.0;
+    target[3 * static_cast<size_t>(i) + 1] = ok ? ty : 0.0;
+    target[3 * static_cast<size_t>(i) + 2] = ok ? tz : 0.0;
 }
 
 // ======================================================================================================================
@@ -877,10 +764,9 @@ icp_match_kernel(MapView map, const float* __restrict__ scan, int n, Pose16 T, i
 int icp_search_grid(const IcpParams& prm, int num_sms) {
     int blocks;
     if (prm.method <= 1) {
-        const int tile_pts = kIcpWarps * prm.queries_per_warp;
-        blocks = (prm.n + tile_pts - 1) / tile_pts;
+        blocks = (prm.n + kIcpThreads - 1) / kIcpThreads;
     } else {
-        blocks = ((prm.n + prm.queries_per_warp - 1) / prm.queries_per_warp + kIcpWarps - 1) / kIcpWarps;
+        blocks = (prm.n + kIcpThreads - 1) / kIcpThreads;
     }
     const int cap = 4 * num_sms;
     return blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
@@ -927,13 +813,10 @@ cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_icp_match(const MapView& map, const float* scan, int n, const double T[16], int method, double max_dist2, int prune,
-                             int* count, double* target, int num_sms, cudaStream_t s) {
-    Pose16 p;
-    for (int i = 0; i < 16; ++i) p.m[i] = T[i];
-    int blocks = (n + kIcpWarps - 1) / kIcpWarps;
-    blocks = blocks < 1 ? 1 : (blocks > 8 * num_sms ? 8 * num_sms : blocks);
-    icp_match_kernel<<<blocks, kIcpThreads, 0, s>>>(map, scan, n, p, method, max_dist2, prune, count, target);
+cudaError_t launch_icp_export(const MapView& map, const float* scan, const int* match, int n, const IcpState* st, int method, double max_dist2,
+                              int* count, double* target, cudaStream_t s) {
+    const int blocks = (n + kIcpThreads - 1) / kIcpThreads;
+    icp_export_kernel<<<blocks < 1 ? 1 : blocks, kIcpThreads, 0, s>>>(map, scan, match, n, st, method, max_dist2, count, target);
     return cudaGetLastError();
 }
 

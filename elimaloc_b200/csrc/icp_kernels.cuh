@@ -20,7 +20,7 @@ cudaError_t launch_icp_search(const MapView& map, const float* scan, const IcpPa
 cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const int* match, const IcpParams& prm, IcpState* st,
                                   double* partials, unsigned int* ticket, int solve_here, int grid, cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);
-cudaError_t launch_icp_match(const MapView& map, const float* scan, int n, const double T[16], int method, double max_dist2,
-                             int prune, int* count, double* target, int num_sms, cudaStream_t s);
+cudaError_t launch_icp_export(const MapView& map, const float* scan, const int* match, int n, const IcpState* st, int method,
+                              double max_dist2, int* count, double* target, cudaStream_t s);
 
 }  // namespace elm
