@@ -99,12 +99,40 @@ __device__ __forceinline__ void probe(const uint4* __restrict__ slots, uint32_t 
     probe_resume(slots, mask, key, h, __ldg(slots + h), start, count);
 }
 
-#define ELM_EVAL_CANDIDATE(Q, ORD, IDX)                                                                                  \
-    {                                                                                                                    \
-        const double d2__ = sq3_exact(static_cast<double>((Q).x) - px, static_cast<double>((Q).y) - py,                   \
-                                      static_cast<double>((Q).z) - pz);                                                   \
-        if (d2__ < best || (d2__ == best && (ORD) < bord)) { best = d2__; bord = (ORD); bidx = (IDX); }                   \
+// Running best of one search: smallest (d2, ord); ord encodes the reference's visit order so that any visiting order
+// yields the reference's winner (voxels x-outer / y / z-inner, vhm.cpp:234-240; insertion order inside a voxel; strict <,
+// vhm.cpp:45).
+struct Best {
+    double d2 = kDblMax;
+    uint32_t ord = 0xffffffffu, idx = 0;
+};
+// Stream `n` consecutive stored points and fold them into `b`; ord0/idx0 = visit order / index of the first one.
+__device__ __forceinline__ void visit_points(const float4* __restrict__ p, uint32_t n, uint32_t ord0, uint32_t idx0, double px, double py,
+                                             double pz, Best& b) {
+#pragma unroll 4
+    for (uint32_t o = 0; o < n; ++o) {
+        const float4 q = __ldg(p + o);
+        const double d2 = sq3_exact(static_cast<double>(q.x) - px, static_cast<double>(q.y) - py, static_cast<double>(q.z) - pz);
+        if (d2 < b.d2 || (d2 == b.d2 && ord0 + o < b.ord)) { b.d2 = d2; b.ord = ord0 + o; b.idx = idx0 + o; }
     }
+}
+// One column (x, y, kz-1..kz+1) of the neighbourhood = one contiguous run of `pts`; L0 = visit index of its first voxel.
+__device__ __forceinline__ uint32_t visit_column(const MapView& map, int x, int y, int kz, bool interior, uint32_t L0, double px, double py,
+                                                 double pz, Best& b) {
+    uint32_t s0 = 0, c0 = 0, s1 = 0, c1 = 0, s2 = 0, c2 = 0;
+    const bool xy_ok = interior || (key_in_range(x) && key_in_range(y));
+    if (xy_ok && (interior || key_in_range(kz - 1))) probe(map.slots, map.mask, pack_key(x, y, kz - 1), s0, c0);
+    if (xy_ok && (interior || key_in_range(kz))) probe(map.slots, map.mask, pack_key(x, y, kz), s1, c1);
+    if (xy_ok && (interior || key_in_range(kz + 1))) probe(map.slots, map.mask, pack_key(x, y, kz + 1), s2, c2);
+    const uint32_t rl = c0 + c1 + c2;
+    const uint32_t rs = c0 ? s0 : (c1 ? s1 : s2);
+    visit_points(map.pts + rs, rl, L0 << 16, rs, px, py, pz, b);
+    return rl;
+}
+// the whole neighbourhood is inside the key range unless the centre sits on its border
+__device__ __forceinline__ bool neighbourhood_interior(int kx, int ky, int kz) {
+    return kx > -kKeyBias && kx < kKeyBias - 1 && ky > -kKeyBias && ky < kKeyBias - 1 && kz > -kKeyBias && kz < kKeyBias - 1;
+}
 
 // Squared-distance lower bound helper (fp32, units of voxel_size, deliberately under-estimated): gap along one axis
 // between the query and any point STORED under key (kq + o).  Insert keys truncate toward zero (vhm.cpp:275), so along
@@ -116,74 +144,30 @@ __device__ __forceinline__ float axis_gap2(int kq, int o, float f) {
     const float g = fmaxf(fmaxf(fmaxf(lo - f, f - hi), 0.0f) - 1e-5f, 0.0f);
     return g * g;
 }
-
-// One query's nearest stored map point among the 27 voxels around it (vhm.cpp:35-53), ONE THREAD PER QUERY: with the
-// exact pruning only ~45 of the ~240 candidates survive, so per-query control (probes, bounds, loop bookkeeping) is
-// what costs, and one thread per query amortises it over the 32 queries of a warp.  Each thread streams contiguous
-// runs of `pts` (the three z-voxels of a column are one run).  Reference visit order = voxels x-outer / y / z-inner
-// (vhm.cpp:234-240), insertion order inside a voxel, strict < (vhm.cpp:45): encoded in `ord`, so any visiting order
-// yields the reference's winner.  Returns the winning point index or -1.
-template <bool PRUNE>
-__device__ __forceinline__ int search_query(const MapView& map, double px, double py, double pz, int kx, int ky, int kz, float fx, float fy,
-                                            float fz, float inv_vs2_up, uint32_t& visited) {
-    const uint4* __restrict__ slots = map.slots;
-    const float4* __restrict__ pts = map.pts;
-    const uint32_t mask = map.mask;
-    double best = kDblMax;
-    uint32_t bord = 0xffffffffu, bidx = 0;
-    // the whole neighbourhood is inside the key range unless the centre sits on its border
-    const bool interior = kx > -kKeyBias && kx < kKeyBias - 1 && ky > -kKeyBias && ky < kKeyBias - 1 && kz > -kKeyBias && kz < kKeyBias - 1;
-    auto in_range = [&](int x, int y, int z) { return interior || (key_in_range(x) && key_in_range(y) && key_in_range(z)); };
-    // one column (x, y, z-1..z+1) = one contiguous run; ord base = index of its first voxel in the visit order
-    auto visit_column = [&](int x, int y, uint32_t L0) {
-        uint32_t s0 = 0, c0 = 0, s1 = 0, c1 = 0, s2 = 0, c2 = 0;
-        if (in_range(x, y, kz - 1)) probe(slots, mask, pack_key(x, y, kz - 1), s0, c0);
-        if (in_range(x, y, kz)) probe(slots, mask, pack_key(x, y, kz), s1, c1);
-        if (in_range(x, y, kz + 1)) probe(slots, mask, pack_key(x, y, kz + 1), s2, c2);
-        const uint32_t rl = c0 + c1 + c2;
-        const uint32_t rs = c0 ? s0 : (c1 ? s1 : s2);
-        visited += rl;
-#pragma unroll 4
-        for (uint32_t o = 0; o < rl; ++o) {
-            const float4 q = __ldg(pts + rs + o);
-            ELM_EVAL_CANDIDATE(q, (L0 << 16) + o, rs + o);
-        }
-    };
-    if (PRUNE) {
-        // phase A: the centre column — the query's own cell and its z-neighbours
-        visit_column(kx, ky, 12u);
-        const float bound = __double2float_ru(best) * inv_vs2_up;  // best distance so far, in voxel units, rounded up
-        // phase B: every other voxel whose box could still hold a point at least as close
-        const float gx[3] = {axis_gap2(kx, -1, fx), axis_gap2(kx, 0, fx), axis_gap2(kx, 1, fx)};
-        const float gy[3] = {axis_gap2(ky, -1, fy), axis_gap2(ky, 0, fy), axis_gap2(ky, 1, fy)};
-        const float gz[3] = {axis_gap2(kz, -1, fz), axis_gap2(kz, 0, fz), axis_gap2(kz, 1, fz)};
-        uint32_t need = 0;
+// Bit L set <=> voxel L (outside the centre column 12..14) may still hold a point at least as close as `best_d2`:
+// a voxel is dropped only when its box is PROVABLY farther, so dropping can never change the result.
+__device__ __forceinline__ uint32_t voxels_to_visit(int kx, int ky, int kz, float fx, float fy, float fz, double best_d2, float inv_vs2_up) {
+    const float bound = __double2float_ru(best_d2) * inv_vs2_up;  // best distance so far, voxel units, rounded up
+    const float gx[3] = {axis_gap2(kx, -1, fx), axis_gap2(kx, 0, fx), axis_gap2(kx, 1, fx)};
+    const float gy[3] = {axis_gap2(ky, -1, fy), axis_gap2(ky, 0, fy), axis_gap2(ky, 1, fy)};
+    const float gz[3] = {axis_gap2(kz, -1, fz), axis_gap2(kz, 0, fz), axis_gap2(kz, 1, fz)};
+    uint32_t need = 0;
 #pragma unroll
-        for (int L = 0; L < 27; ++L) {
-            if (L >= 12 && L <= 14) continue;
-            const float lb = (gx[L / 9] + gy[(L / 3) % 3] + gz[L % 3]) * 0.9999f;
-            if (!(lb > bound)) need |= 1u << L;  // prune only when provably farther
-        }
-        while (need) {
-            const int L = __ffs(need) - 1;
-            need &= need - 1;
-            const int x = kx + L / 9 - 1, y = ky + (L / 3) % 3 - 1, z = kz + L % 3 - 1;
-            if (!in_range(x, y, z)) continue;
-            uint32_t vs0 = 0, vc = 0;
-            probe(slots, mask, pack_key(x, y, z), vs0, vc);
-            visited += vc;
-#pragma unroll 4
-            for (uint32_t o = 0; o < vc; ++o) {
-                const float4 q = __ldg(pts + vs0 + o);
-                ELM_EVAL_CANDIDATE(q, (static_cast<uint32_t>(L) << 16) + o, vs0 + o);
-            }
-        }
-    } else {
-        // reference-style exhaustive visit: all 9 columns of 3 voxels
-#pragma unroll 1
-        for (int c = 0; c < 9; ++c) visit_column(kx + c / 3 - 1, ky + c % 3 - 1, static_cast<uint32_t>(3 * c));
+    for (int L = 0; L < 27; ++L) {
+        if (L >= 12 && L <= 14) continue;
+        const float lb = (gx[L / 9] + gy[(L / 3) % 3] + gz[L % 3]) * 0.9999f;
+        if (!(lb > bound)) need |= 1u << L;
     }
-    return (bord == 0xffffffffu) ? -1 : static_cast<int>(bidx);
+    return need;
+}
+// Visit ONE voxel L of the neighbourhood of (kx, ky, kz); returns the number of points streamed.
+__device__ __forceinline__ uint32_t visit_voxel(const MapView& map, int kx, int ky, int kz, int L, double px, double py, double pz, Best& b) {
+    const int x = kx + L / 9 - 1, y = ky + (L / 3) % 3 - 1, z = kz + L % 3 - 1;
+    if (!(key_in_range(x) && key_in_range(y) && key_in_range(z))) return 0;
+    uint32_t vs0 = 0, vc = 0;
+    probe(map.slots, map.mask, pack_key(x, y, z), vs0, vc);
+    visit_points(map.pts + vs0, vc, static_cast<uint32_t>(L) << 16, vs0, px, py, pz, b);
+    return vc;
 }
 
 // Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115), one thread per query.  Returns the winning slot or -1.
@@ -208,15 +192,31 @@ __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, do
 // ======================================================================================================================
 // search: P2P / GICP
 // ======================================================================================================================
-// Block = 256 threads, one scan point each.  A tile of the packed scan (256 points x 12 B) is pulled into shared memory
-// by the TMA bulk-copy engine (double-buffered when a block owns several tiles); each thread transforms its point
-// (TransformPoints fused, reg.hpp:136-148) and searches it.
-template <bool PRUNE>
-__global__ void __launch_bounds__(kIcpThreads, 3)
+// Block = 256 threads = one tile of 256 scan points, pulled into shared memory by the TMA bulk-copy engine (packed xyz,
+// 12 B/point; double-buffered when a block owns several tiles).  TransformPoints is fused (reg.hpp:136-148).
+//
+// COOP = true (default, exact pruning), three phases per tile:
+//   A  thread per QUERY : transform, probe + stream the centre column, derive which other voxels cannot be excluded
+//                         and append one work item per such voxel to a block-wide list in shared memory;
+//   B  thread per ITEM  : probe that voxel and stream its points for the item's query (balanced: every lane busy,
+//                         instead of each query thread walking its own 0..24 voxels while its warp-mates idle);
+//   C  merge            : atomicMin on the fp64 distance bits, then on (visit order, index) among the exact minima,
+//                         which reproduces the reference's first-in-visit-order tie-break (vhm.cpp:45).
+// COOP = false: every thread walks all 9 columns of its own query — the reference's exhaustive visit.
+constexpr int kItemCap = 1024;  // work items per tile kept in shared memory (typical: ~600); overflow stays with its owner
+
+template <bool COOP>
+__global__ void __launch_bounds__(kIcpThreads, 4)
 icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, int* __restrict__ match) {
     __shared__ __align__(16) float s_tile[2][kIcpThreads * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_T[12];
+    __shared__ double s_px[COOP ? kIcpThreads : 1], s_py[COOP ? kIcpThreads : 1], s_pz[COOP ? kIcpThreads : 1];
+    __shared__ int s_kx[COOP ? kIcpThreads : 1], s_ky[COOP ? kIcpThreads : 1], s_kz[COOP ? kIcpThreads : 1];
+    __shared__ unsigned long long s_best[COOP ? kIcpThreads : 1], s_win[COOP ? kIcpThreads : 1];
+    __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1], s_item_win[COOP ? kItemCap : 1];
+    __shared__ uint16_t s_items[COOP ? kItemCap : 1];
+    __shared__ int s_nitems;
 
     if (st->done) return;  // loop already left (termination / overlap failure)
     const int tid = threadIdx.x;
@@ -244,26 +244,84 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams 
     for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int next = tile + gridDim.x;
         if (tid == 0 && next < ntiles && tile_tma_ok(next)) issue(next, buf ^ 1);  // prefetch the next tile
+        if (tid == 0) s_nitems = 0;
         if (tile_tma_ok(tile)) {
             mbar_wait(&s_bar[buf], phase[buf]);
             phase[buf] ^= 1;
         } else {  // ragged last tile / unaligned base: plain cooperative copy
             const int nf = tile_count(tile) * 3;
             for (int i = tid; i < nf; i += kIcpThreads) s_tile[buf][i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
-            __syncthreads();
         }
-        if (tid < tile_count(tile)) {
+        __syncthreads();
+        const int cnt = tile_count(tile);
+        const bool mine = tid < cnt;
+        // ---- phase A: one thread per query
+        Best b;
+        double px = 0, py = 0, pz = 0;
+        int kx = 0, ky = 0, kz = 0;
+        uint32_t own_need = 0;
+        if (mine) {
             const float* sp = &s_tile[buf][tid * 3];
             const double sx = sp[0], sy = sp[1], sz = sp[2];
-            const double px = row_apply_exact(s_T, 0, sx, sy, sz);
-            const double py = row_apply_exact(s_T, 1, sx, sy, sz);
-            const double pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            px = row_apply_exact(s_T, 0, sx, sy, sz);
+            py = row_apply_exact(s_T, 1, sx, sy, sz);
+            pz = row_apply_exact(s_T, 2, sx, sy, sz);
             float fx, fy, fz;
-            const int kx = voxel_floor(px, map.voxel_size, &fx), ky = voxel_floor(py, map.voxel_size, &fy), kz = voxel_floor(pz, map.voxel_size, &fz);
-            match[static_cast<size_t>(tile) * tile_pts + tid] = search_query<PRUNE>(map, px, py, pz, kx, ky, kz, fx, fy, fz, inv_vs2_up, visited);
+            kx = voxel_floor(px, map.voxel_size, &fx); ky = voxel_floor(py, map.voxel_size, &fy); kz = voxel_floor(pz, map.voxel_size, &fz);
+            const bool interior = neighbourhood_interior(kx, ky, kz);
             ++searched;
+            if (COOP) {
+                visited += visit_column(map, kx, ky, kz, interior, 12u, px, py, pz, b);
+                own_need = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up);
+                s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
+                s_kx[tid] = kx; s_ky[tid] = ky; s_kz[tid] = kz;
+                s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
+                s_win[tid] = ~0ull;
+                const int k = __popc(own_need);
+                if (k) {
+                    const int pos = atomicAdd(&s_nitems, k);
+                    if (pos + k <= kItemCap) {  // hand the voxels to the block; otherwise they stay with this thread
+                        int w = pos;
+                        for (uint32_t m = own_need; m; m &= m - 1) s_items[w++] = static_cast<uint16_t>((tid << 5) | (__ffs(m) - 1));
+                        own_need = 0;
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 9; ++c)
+                    visited += visit_column(map, kx + c / 3 - 1, ky + c % 3 - 1, kz, interior, static_cast<uint32_t>(3 * c), px, py, pz, b);
+                match[static_cast<size_t>(tile) * tile_pts + tid] = (b.ord == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
+            }
         }
-        __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
+        if (COOP) {
+            __syncthreads();
+            // ---- phase B: one thread per (query, voxel) item
+            const int nitems = min(s_nitems, kItemCap);  // (items beyond the cap were never written: their owners kept them)
+            for (int j = tid; j < nitems; j += kIcpThreads) {
+                const int it = s_items[j], q = it >> 5, L = it & 31;
+                Best ib;
+                visited += visit_voxel(map, s_kx[q], s_ky[q], s_kz[q], L, s_px[q], s_py[q], s_pz[q], ib);
+                const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
+                s_item_d2[j] = bits;
+                s_item_win[j] = (static_cast<unsigned long long>(ib.ord) << 32) | ib.idx;
+                if (ib.ord != 0xffffffffu) atomicMin(&s_best[q], bits);
+            }
+            if (mine) {
+                for (uint32_t m = own_need; m; m &= m - 1) visited += visit_voxel(map, kx, ky, kz, __ffs(m) - 1, px, py, pz, b);
+                if (b.ord != 0xffffffffu) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(b.d2)));
+            }
+            __syncthreads();
+            // ---- phase C: among the exact minima the smallest visit order wins
+            for (int j = tid; j < nitems; j += kIcpThreads) {
+                const int q = s_items[j] >> 5;
+                if (s_item_d2[j] == s_best[q] && (s_item_win[j] >> 32) != 0xffffffffull) atomicMin(&s_win[q], s_item_win[j]);
+            }
+            if (mine && b.ord != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
+                atomicMin(&s_win[tid], (static_cast<unsigned long long>(b.ord) << 32) | b.idx);
+            __syncthreads();
+            if (mine) match[static_cast<size_t>(tile) * tile_pts + tid] = (s_win[tid] == ~0ull) ? -1 : static_cast<int>(s_win[tid] & 0xffffffffu);
+        }
+        if (next < ntiles) __syncthreads();  // everyone is done with the tile's shared state before it is refilled (block-uniform)
     }
     if (prm.stats) {
         // warp-aggregate, one atomic pair per warp
@@ -477,9 +535,66 @@ struct SolveScratch {
     int perm[6];
 };
 
-// One AlignClouds* tail + the RunRegister bookkeeping around it.  Runs in ONE thread; st->acc holds the sums.
-__device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc) {
-    const double* a = st->acc;
+// Register-resident LDL^T of a well-conditioned symmetric 6x6 (every loop fully unrolled, static indexing), the common
+// case of JtJ + lambda diag(JtJ).  Returns false — without touching x — when a pivot is tiny relative to the largest
+// diagonal entry; the caller then takes the pivoted path above, which mirrors Eigen's ldlt() on degenerate input.
+__device__ __forceinline__ bool ldlt6_fast(const double (*Ain)[6], const double* b, double* x, double* inv_out) {
+    double A[6][6];
+    double dmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[i][j] = Ain[i][j];
+        dmax = fmax(dmax, fabs(A[i][i]));
+    }
+    double dinv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double d = A[k][k];
+        if (!(fabs(d) > 1e-13 * dmax)) return false;
+        dinv[k] = 1.0 / d;
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) A[i][k] *= dinv[k];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) A[i][j] -= A[i][k] * d * A[j][k];
+    }
+    auto solve = [&](double* y) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) y[i] *= dinv[i];
+#pragma unroll
+        for (int i = 5; i >= 0; --i)
+#pragma unroll
+            for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
+    };
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = b[i];
+    solve(y);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
+    if (inv_out) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double e[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+            solve(e);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) inv_out[6 * i + c] = e[i];
+        }
+    }
+    return true;
+}
+
+// One AlignClouds* tail + the RunRegister bookkeeping around it.  Runs in ONE thread.
+//   a   : the 30 reduced sums (shared memory)       Tcur : current pose rows 0..2 (shared memory)
+__device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc, const double* a, const double* Tcur) {
     const double n_corr = a[kIdxNcorr], n_total = a[kIdxNtotal];
     // corres_ratio = (float)i_source_corr_num / i_source_total_num   (reg.cpp:351)
     const float ratio = static_cast<float>(n_corr) / static_cast<float>(n_total);
@@ -488,15 +603,19 @@ __device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc)
         return;
     }
     int k = 0;
-    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { st->JTJ[6 * i + j] = a[k]; st->JTJ[6 * j + i] = a[k]; ++k; }
+    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { sc->A[i][j] = a[k]; sc->A[j][i] = a[k]; ++k; }
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) st->JTJ[6 * i + j] = sc->A[i][j];
     for (int i = 0; i < 6; ++i) st->JTr[i] = a[kIdxJtr + i];
     st->residual_sum = a[kIdxRes];
     st->n_corr = n_corr;
     st->fitness = a[kIdxRes] / n_corr;  // reg.cpp:53,134,210
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) sc->A[i][j] = st->JTJ[6 * i + j];
-    for (int i = 0; i < 6; ++i) sc->A[i][i] = st->JTJ[7 * i] + prm.lm_lambda * st->JTJ[7 * i];  // JTJ + lambda diag(JTJ) (Q9)
-    ldlt6(sc->A, st->JTr, sc->x, (prm.method == 1) ? st->local_cov : nullptr, sc->perm, sc->y);  // reg.cpp:137-142
-    const double* x = sc->x;
+    for (int i = 0; i < 6; ++i) sc->A[i][i] += prm.lm_lambda * sc->A[i][i];  // JTJ + lambda diag(JTJ) (Q9)
+    double x[6];
+    double* cov = (prm.method == 1) ? st->local_cov : nullptr;                // reg.cpp:137-142
+    if (!ldlt6_fast(sc->A, a + kIdxJtr, x, cov)) {
+        ldlt6(sc->A, a + kIdxJtr, sc->x, cov, sc->perm, sc->y);
+        for (int i = 0; i < 6; ++i) x[i] = sc->x[i];
+    }
     // AngleAxisd(|w|, w/|w|).toRotationMatrix()   (reg.cpp:58-62)
     const double wn2 = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
     const double angle = sqrt(wn2);
@@ -508,26 +627,37 @@ __device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc)
     const double D0 = c1 * ax * ax + c, D1 = c1 * ax * ay - s * az, D2 = c1 * ax * az + s * ay;
     const double D4 = c1 * ax * ay + s * az, D5 = c1 * ay * ay + c, D6 = c1 * ay * az - s * ax;
     const double D8 = c1 * ax * az - s * ay, D9 = c1 * ay * az + s * ax, D10 = c1 * az * az + c;
-    // last_icp_pose * estimation_local (reg.cpp:378)
+    // last_icp_pose * estimation_local (reg.cpp:378); the bottom row of a rigid pose stays (0 0 0 1)
+    double Tn[16];
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const double t0 = st->T[4 * i], t1 = st->T[4 * i + 1], t2 = st->T[4 * i + 2], t3 = st->T[4 * i + 3];
-        st->T[4 * i] = t0 * D0 + t1 * D4 + t2 * D8;
-        st->T[4 * i + 1] = t0 * D1 + t1 * D5 + t2 * D9;
-        st->T[4 * i + 2] = t0 * D2 + t1 * D6 + t2 * D10;
-        st->T[4 * i + 3] = t0 * x[0] + t1 * x[1] + t2 * x[2] + t3;
+        const double t0 = Tcur[4 * i], t1 = Tcur[4 * i + 1], t2 = Tcur[4 * i + 2], t3 = Tcur[4 * i + 3];
+        Tn[4 * i] = t0 * D0 + t1 * D4 + t2 * D8;
+        Tn[4 * i + 1] = t0 * D1 + t1 * D5 + t2 * D9;
+        Tn[4 * i + 2] = t0 * D2 + t1 * D6 + t2 * D10;
+        Tn[4 * i + 3] = t0 * x[0] + t1 * x[1] + t2 * x[2] + t3;
     }
-    {   // bottom row of a general 4x4 product (stays 0 0 0 1 for a rigid initial guess)
+    {
         const double t0 = st->T[12], t1 = st->T[13], t2 = st->T[14], t3 = st->T[15];
-        st->T[12] = t0 * D0 + t1 * D4 + t2 * D8;
-        st->T[13] = t0 * D1 + t1 * D5 + t2 * D9;
-        st->T[14] = t0 * D2 + t1 * D6 + t2 * D10;
-        st->T[15] = t0 * x[0] + t1 * x[1] + t2 * x[2] + t3;
+        Tn[12] = t0 * D0 + t1 * D4 + t2 * D8;
+        Tn[13] = t0 * D1 + t1 * D5 + t2 * D9;
+        Tn[14] = t0 * D2 + t1 * D6 + t2 * D10;
+        Tn[15] = t0 * x[0] + t1 * x[1] + t2 * x[2] + t3;
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
     st->iterations += 1;
     const double R[9] = {D0, D1, D2, D4, D5, D6, D8, D9, D10};
     const double tn = rotation_angle(R) + sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);  // reg.cpp:381-384
     if (tn < prm.term_thr) { st->done = 1; return; }                                      // reg.cpp:385-387
-    refresh_inverses(st);
+    double Ti[16], Ri[9];
+    inverse4(Tn, Ti);
+    const double Rn[9] = {Tn[0], Tn[1], Tn[2], Tn[4], Tn[5], Tn[6], Tn[8], Tn[9], Tn[10]};
+    inverse3(Rn, Ri);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st->Tinv[i] = Ti[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) st->Rinv[i] = Ri[i];
 }
 
 }  // namespace
@@ -685,15 +815,17 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
         s_red[g][k] = v;
     }
     __syncthreads();
+    __shared__ double s_acc[kAcc];
     if (tid < kAcc) {
         double t = 0.0;
         for (int i = 0; i < kIcpWarps; ++i) t += s_red[i][tid];
         st->acc[tid] = t;
+        s_acc[tid] = t;
     }
     __syncthreads();
     if (tid == 0) {
         *ticket = 0;
-        if (solve_here) solve_step(st, prm, &s_solve);
+        if (solve_here) solve_step(st, prm, &s_solve, s_acc, s_T);
     }
 }
 
@@ -712,8 +844,12 @@ __global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket) 
 
 __global__ void icp_solve_kernel(IcpState* st, IcpParams prm) {
     __shared__ SolveScratch s_solve;
-    if (threadIdx.x != 0 || st->done) return;
-    solve_step(st, prm, &s_solve);
+    __shared__ double s_acc[kAcc], s_T[12];
+    if (st->done) return;
+    if (threadIdx.x < kAcc) s_acc[threadIdx.x] = st->acc[threadIdx.x];
+    if (threadIdx.x < 12) s_T[threadIdx.x] = st->T[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) solve_step(st, prm, &s_solve, s_acc, s_T);
 }
 
 // ---- correspondence dump (test hook): turns the production search's match[] into (count, target) ---------------------
@@ -789,8 +925,9 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
 cudaError_t launch_icp_search(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, int* match, int grid, int prune,
                               cudaStream_t s) {
     if (prm.method <= 1) {
-        if (prune) icp_search_points_kernel<true><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
+if (prune) icp_search_points_kernel<true><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
         else icp_search_points_kernel<false><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
+
     } else if (prm.method == 2) {
         icp_search_means_kernel<<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
     }
