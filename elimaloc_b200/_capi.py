@@ -58,6 +58,7 @@ SIGNATURES = {
     "elm_registration_profile": (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_int64)]),
     "elm_registration_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "elm_registration_set_binning": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_set_exhaustive": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_comm_unique_id": (C.c_int, [_u8p]),
     "elm_registration_set_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),

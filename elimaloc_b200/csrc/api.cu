@@ -147,6 +147,14 @@ struct elm_registration {
     int partial_rows = 0;
     int* d_match = nullptr;
     size_t match_cap = 0;
+    // spatially binned copy of the scan for the search kernels (scan_sort.cu)
+    float* d_sorted = nullptr;
+    int* d_orig = nullptr;
+    uint32_t* d_bin = nullptr;
+    uint32_t* d_hist = nullptr;
+    size_t sort_cap = 0;
+    int binning = 0;          // 1 = search the scan in spatially binned order (measured: no gain on B200)
+    bool use_sorted = false;  // the current enqueue searches d_sorted / d_orig
     unsigned int* d_ticket = nullptr;
     unsigned long long* d_stats = nullptr;  // [visited map points, queries] when stats are on
     bool stats_on = false;
@@ -175,7 +183,8 @@ struct elm_registration {
         cudaSetDevice(device);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_ticket); cudaFree(d_stats); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
+        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_ticket); cudaFree(d_stats);
+        cudaFree(d_sorted); cudaFree(d_orig); cudaFree(d_bin); cudaFree(d_hist); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -211,6 +220,32 @@ int ensure_match(elm_registration* r, size_t n) {
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_match), cap * sizeof(int)));
         r->match_cap = cap;
     }
+    return ELM_OK;
+}
+
+int ensure_sort(elm_registration* r, size_t n) {
+    if (n > r->sort_cap) {
+        cudaFree(r->d_sorted); cudaFree(r->d_orig); cudaFree(r->d_bin);
+        r->d_sorted = nullptr; r->d_orig = nullptr; r->d_bin = nullptr;
+        const size_t cap = (n + 1023) / 1024 * 1024;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_sorted), cap * 3 * sizeof(float)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_orig), cap * sizeof(int)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_bin), cap * sizeof(uint32_t)));
+        r->sort_cap = cap;
+    }
+    if (!r->d_hist) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_hist), (1u << 18) * sizeof(uint32_t)));
+    return ELM_OK;
+}
+
+// Bin the scan under pose T (once per call); afterwards the search kernels read d_sorted / d_orig.
+int enqueue_binning(elm_registration* r, const elm_map* map, const float* d_scan, size_t n, const double T[16], int method) {
+    r->use_sorted = false;
+    if (!r->binning || method == ELM_AVGICP || n < 2048) return ELM_OK;
+    int rc = ensure_sort(r, n);
+    if (rc) return rc;
+    ELM_CUDA(elm::launch_scan_binning(d_scan, static_cast<int>(n), T, map->host.voxel_size, r->d_bin, r->d_hist, r->d_sorted, r->d_orig, r->stream));
+    r->launches += 3;
+    r->use_sorted = true;
     return ELM_OK;
 }
 
@@ -258,7 +293,8 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
         ELM_CUDA(cudaEventRecord(r->ev[r->ev_used], r->stream));
     }
     if (prm.method != ELM_AVGICP) {
-        ELM_CUDA(elm::launch_icp_search(map->view(), d_scan, prm, r->d_state, r->d_match, sgrid, r->prune, r->stream));
+        ELM_CUDA(elm::launch_icp_search(map->view(), r->use_sorted ? r->d_sorted : d_scan, r->use_sorted ? r->d_orig : nullptr, prm, r->d_state,
+                                        r->d_match, sgrid, r->prune, r->stream));
         r->launches += 1;
     }
     if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
@@ -411,6 +447,8 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     const elm::IcpParams prm = make_params(reg, cfg, n);
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->d_ticket, reg->stream));
     reg->launches += 1;
+    rc = enqueue_binning(reg, map, d_src_xyz, n, T_init, cfg->icp_method);
+    if (rc) return rc;
     for (int j = 0; j < cfg->max_iteration; ++j) {  // reg.cpp:310
         rc = enqueue_linearize(reg, map, d_src_xyz, prm, true);
         if (rc) return rc;
@@ -484,6 +522,8 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     if (n) ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
     const elm::IcpParams prm = make_params(reg, cfg, n);
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
+    rc = enqueue_binning(reg, map, reg->d_scan, n, T, cfg->icp_method);
+    if (rc) return rc;
     rc = enqueue_linearize(reg, map, reg->d_scan, prm, false);
     if (rc) return rc;
     ELM_CUDA(cudaMemcpyAsync(reg->h_state, reg->d_state, sizeof(elm::IcpState), cudaMemcpyDeviceToHost, reg->stream));
@@ -525,9 +565,11 @@ int elm_correspondences(elm_registration* reg, const elm_map* map, const float* 
     rc = ensure_match(reg, n);
     if (rc) return rc;
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
+    rc = enqueue_binning(reg, map, reg->d_scan, n, T, method);
+    if (rc) return rc;
     if (method != ELM_AVGICP)
-        ELM_CUDA(elm::launch_icp_search(map->view(), reg->d_scan, prm, reg->d_state, reg->d_match, elm::icp_search_grid(prm, reg->num_sms),
-                                        reg->prune, reg->stream));
+        ELM_CUDA(elm::launch_icp_search(map->view(), reg->use_sorted ? reg->d_sorted : reg->d_scan, reg->use_sorted ? reg->d_orig : nullptr, prm,
+                                        reg->d_state, reg->d_match, elm::icp_search_grid(prm, reg->num_sms), reg->prune, reg->stream));
     ELM_CUDA(elm::launch_icp_export(map->view(), reg->d_scan, reg->d_match, static_cast<int>(n), reg->d_state, method,
                                     max_search_dist * max_search_dist, reg->d_count, reg->d_target, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(count, reg->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
@@ -577,6 +619,12 @@ int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, 
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
     *map_points_visited = h[0];
     *queries = h[1];
+    return ELM_OK;
+}
+
+int elm_registration_set_binning(elm_registration* reg, int enable) {
+    if (!reg) return fail(ELM_ERR_INVALID, "null registration");
+    reg->binning = enable ? 1 : 0;
     return ELM_OK;
 }
 

@@ -203,11 +203,13 @@ __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, do
 //   C  merge            : atomicMin on the fp64 distance bits, then on (visit order, index) among the exact minima,
 //                         which reproduces the reference's first-in-visit-order tie-break (vhm.cpp:45).
 // COOP = false: every thread walks all 9 columns of its own query — the reference's exhaustive visit.
+constexpr int kNoItem = 0xffff;
 constexpr int kItemCap = 1024;  // work items per tile kept in shared memory (typical: ~600); overflow stays with its owner
 
 template <bool COOP>
 __global__ void __launch_bounds__(kIcpThreads, 4)
-icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, int* __restrict__ match) {
+icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, const IcpState* __restrict__ st,
+                         int* __restrict__ match) {
     __shared__ __align__(16) float s_tile[2][kIcpThreads * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_T[12];
@@ -284,13 +286,16 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams 
                         int w = pos;
                         for (uint32_t m = own_need; m; m &= m - 1) s_items[w++] = static_cast<uint16_t>((tid << 5) | (__ffs(m) - 1));
                         own_need = 0;
+                    } else {
+                        for (int w = pos; w < kItemCap; ++w) s_items[w] = kNoItem;  // the tail of the list this claim straddles
                     }
                 }
             } else {
 #pragma unroll 1
                 for (int c = 0; c < 9; ++c)
                     visited += visit_column(map, kx + c / 3 - 1, ky + c % 3 - 1, kz, interior, static_cast<uint32_t>(3 * c), px, py, pz, b);
-                match[static_cast<size_t>(tile) * tile_pts + tid] = (b.ord == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
+                const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
+                match[orig ? orig[gi] : gi] = (b.ord == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
             }
         }
         if (COOP) {
@@ -299,6 +304,7 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams 
             const int nitems = min(s_nitems, kItemCap);  // (items beyond the cap were never written: their owners kept them)
             for (int j = tid; j < nitems; j += kIcpThreads) {
                 const int it = s_items[j], q = it >> 5, L = it & 31;
+                if (it == kNoItem) continue;
                 Best ib;
                 visited += visit_voxel(map, s_kx[q], s_ky[q], s_kz[q], L, s_px[q], s_py[q], s_pz[q], ib);
                 const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
@@ -314,12 +320,16 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams 
             // ---- phase C: among the exact minima the smallest visit order wins
             for (int j = tid; j < nitems; j += kIcpThreads) {
                 const int q = s_items[j] >> 5;
+                if (s_items[j] == kNoItem) continue;
                 if (s_item_d2[j] == s_best[q] && (s_item_win[j] >> 32) != 0xffffffffull) atomicMin(&s_win[q], s_item_win[j]);
             }
             if (mine && b.ord != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
                 atomicMin(&s_win[tid], (static_cast<unsigned long long>(b.ord) << 32) | b.idx);
             __syncthreads();
-            if (mine) match[static_cast<size_t>(tile) * tile_pts + tid] = (s_win[tid] == ~0ull) ? -1 : static_cast<int>(s_win[tid] & 0xffffffffu);
+            if (mine) {
+                const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
+                match[orig ? orig[gi] : gi] = (s_win[tid] == ~0ull) ? -1 : static_cast<int>(s_win[tid] & 0xffffffffu);
+            }
         }
         if (next < ntiles) __syncthreads();  // everyone is done with the tile's shared state before it is refilled (block-uniform)
     }
@@ -337,7 +347,8 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, IcpParams 
 // search: VGICP
 // ======================================================================================================================
 __global__ void __launch_bounds__(kIcpThreads, 4)
-icp_search_means_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, int* __restrict__ match) {
+icp_search_means_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, const IcpState* __restrict__ st,
+                        int* __restrict__ match) {
     __shared__ double s_T[12];
     if (st->done) return;
     const int tid = threadIdx.x;
@@ -347,7 +358,7 @@ icp_search_means_kernel(MapView map, const float* __restrict__ scan, IcpParams p
         const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
         const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
         const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
-        match[i] = nearest_mean_27(map, px, py, pz, kx, ky, kz);
+        match[orig ? orig[i] : i] = nearest_mean_27(map, px, py, pz, kx, ky, kz);
     }
 }
 
@@ -922,14 +933,14 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
     return cudaGetLastError();
 }
 
-cudaError_t launch_icp_search(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, int* match, int grid, int prune,
-                              cudaStream_t s) {
+cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, const IcpState* st, int* match,
+                              int grid, int prune, cudaStream_t s) {
     if (prm.method <= 1) {
-if (prune) icp_search_points_kernel<true><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
-        else icp_search_points_kernel<false><<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
+if (prune) icp_search_points_kernel<true><<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match);
+        else icp_search_points_kernel<false><<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match);
 
     } else if (prm.method == 2) {
-        icp_search_means_kernel<<<grid, kIcpThreads, 0, s>>>(map, scan, prm, st, match);
+        icp_search_means_kernel<<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match);
     }
     return cudaGetLastError();
 }

@@ -15,11 +15,17 @@ int icp_accumulate_grid(const IcpParams& prm, int num_sms);
 
 cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, cudaStream_t s);
 // P2P / GICP / VGICP correspondence search -> match[n] (no-op for AVGICP, which searches inside the accumulation)
-cudaError_t launch_icp_search(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, int* match,
-                              int grid, int prune, cudaStream_t s);
+// `orig` (may be NULL): scan is in binned order and match[] must be written at orig[i]
+cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, const IcpState* st,
+                              int* match, int grid, int prune, cudaStream_t s);
 cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const int* match, const IcpParams& prm, IcpState* st,
                                   double* partials, unsigned int* ticket, int solve_here, int grid, cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);
+// spatial binning of the scan (scan_sort.cu)
+int scan_bin_bits(int n);
+cudaError_t launch_scan_binning(const float* scan, int n, const double T[16], double voxel_size, uint32_t* bin, uint32_t* hist,
+                                float* sorted, int* orig, cudaStream_t s);
+
 cudaError_t launch_icp_export(const MapView& map, const float* scan, const int* match, int n, const IcpState* st, int method,
                               double max_dist2, int* count, double* target, cudaStream_t s);
 

@@ -66,6 +66,21 @@ def test_correspondences_bit_exact(world, method, exhaustive):
         world["greg"].set_exhaustive(False)
 
 
+@pytest.mark.parametrize("method", [E.P2P, E.GICP, E.VGICP])
+def test_binning_does_not_change_results(world, method):
+    """the search walks the scan in spatially binned order; match[] and every sum must be what the caller's order gives"""
+    gcfg, _ = both_cfg(icp_method=method, **synth.timing_knobs())
+    out = []
+    for binning in (True, False):
+        world["greg"].set_binning(binning)
+        c, t = world["greg"].correspondences(world["scan"], world["gm"], world["T0"], method, 5.0)
+        lin = world["greg"].linearize(world["scan"], world["gm"], world["T0"], gcfg)
+        out.append((c, t, lin))
+    world["greg"].set_binning(False)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2]["JTJ"], out[1][2]["JTJ"]) and np.array_equal(out[0][2]["JTr"], out[1][2]["JTr"])
+
+
 def test_correspondences_random_scan_bit_exact(world):
     """uniformly random scan (most queries far from any map point, many in empty space): P2P search parity"""
     scan = synth.scan_u(8192, 14.0, seed=77)
