@@ -1,0 +1,115 @@
+"""Host-side logic of the product, runnable without a GPU: the C-ABI library loads and exports every declared symbol,
+the host map builder (sort-based AddPoints + covariance passes) matches the oracle, and compute entry points refuse
+loudly when there is no CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import elimaloc_b200 as E
+from elimaloc_b200 import _capi, synth
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "elimaloc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(elm_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 25
+    lib = C.CDLL(_capi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/elimaloc_b200.h but not exported"
+    assert set(names) == set(_capi.SIGNATURES), "ctypes binding and header disagree"
+
+
+def test_config_struct_layout_matches_header():
+    assert C.sizeof(_capi.RegConfig) == 6 * 4 + 8 * 8
+    assert _capi.RegConfig.max_search_dist.offset == 24
+    assert C.sizeof(O.RegConfig) == C.sizeof(_capi.RegConfig)
+
+
+@pytest.mark.parametrize("origin", [0.0, -6.0])
+def test_host_map_builder_matches_oracle(origin):
+    raw = synth.map_u(60_000, 18.0, origin=origin)
+    pm = E.VoxelHashMap(1.0, 30, device=-1)
+    pm.AddPoints(raw)
+    pm.CalVoxelCovAll()
+    pm.CalPointCovAll(0.4)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    om.CalPointCovAll(0.4)
+    pe, oe = pm.export(True, True), om.export()
+    for k in ("keys", "counts", "pxyz"):  # integer / order-dependent work: bit exact
+        assert np.array_equal(pe[k], oe[k]), k
+    for k in ("vmean", "vcov", "pmean", "pcov"):
+        assert np.abs(pe[k] - oe[k]).max() < 1e-9, k
+    assert not pm.Empty() and pm.num_points() == om.num_points() and pm.num_voxels() == om.num_voxels()
+
+
+def test_add_points_is_incremental_and_order_dependent():
+    """AddPoints may be called repeatedly (voxel_hash_map.cpp:268-285): two calls == one call on the concatenation,
+    and the spacing filter depends on arrival order."""
+    raw = synth.map_u(30_000, 9.0, origin=-1.0)
+    a = E.VoxelHashMap(0.8, 12, device=-1)
+    a.AddPoints(raw[:10_000])
+    a.AddPoints(raw[10_000:])
+    b = E.VoxelHashMap(0.8, 12, device=-1)
+    b.AddPoints(raw)
+    om = O.VoxelHashMap(0.8, 12)
+    om.AddPoints(raw)
+    ea, eb, eo = a.export(), b.export(), om.export()
+    for k in ("keys", "counts", "pxyz"):
+        assert np.array_equal(ea[k], eb[k]) and np.array_equal(eb[k], eo[k]), k
+    assert eb["counts"].max() <= 12
+    c = E.VoxelHashMap(0.8, 12, device=-1)
+    c.AddPoints(raw[::-1].copy())
+    assert not np.array_equal(np.sort(c.export()["pxyz"], axis=0), np.sort(eb["pxyz"], axis=0))
+
+
+def test_empty_and_degenerate_maps():
+    m = E.VoxelHashMap(1.0, 30, device=-1)
+    assert m.Empty() and m.num_points() == 0
+    m.AddPoints(np.zeros((0, 3), np.float32))
+    assert m.Empty()
+    m.AddPoints(np.array([[0.1, 0.2, 0.3]] * 5, np.float32))  # duplicates: only the first survives the spacing rule
+    assert m.num_points() == 1 and m.num_voxels() == 1
+    m.CalVoxelCovAll()
+    e = m.export(voxel_cov=True)
+    assert np.array_equal(e["vcov"][0], np.eye(3)) and np.allclose(e["vmean"][0], [0.1, 0.2, 0.3], atol=1e-7)
+
+
+def test_error_statuses_without_fallback():
+    m = E.VoxelHashMap(1.0, 30, device=-1)
+    with pytest.raises(E.ElmError) as ei:  # 2^20 voxels per axis is the key range
+        m.AddPoints(np.array([[3.0e6, 0.0, 0.0]], np.float32))
+    assert ei.value.status == _capi.ELM_ERR_RANGE
+    with pytest.raises(E.ElmError) as ei:
+        m.export(voxel_cov=True)
+    assert ei.value.status == _capi.ELM_ERR_STATE
+    with pytest.raises(E.ElmError):
+        E.VoxelHashMap(-1.0, 30, device=-1)
+    if E.device_count() == 0:  # no CUDA device: the product refuses, it never computes on the CPU
+        with pytest.raises(E.ElmError) as ei:
+            E.Registration(device=0)
+        assert ei.value.status == _capi.ELM_ERR_CUDA
+        with pytest.raises(E.ElmError) as ei:
+            E.VoxelHashMap(1.0, 30, device=0)
+        assert ei.value.status == _capi.ELM_ERR_CUDA
+
+
+def test_product_does_not_import_the_oracle():
+    """only tests/, smoke() and bench.py's CPU legs may touch oracle/"""
+    pkg = os.path.join(ROOT, "elimaloc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                assert "oracle" not in open(os.path.join(dirpath, f), errors="replace").read().lower(), os.path.join(dirpath, f)
