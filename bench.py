@@ -339,8 +339,15 @@ def main():
             bps = bps_exh - 12 * st["sum27"] + 12 * visited_per_search
         dom_ms = (search_ms if method != 3 else accum_ms) / prof_iters
         achieved = bps * n_local / (dom_ms * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", f"r01_traffic_{args.method}.json")
+        if os.path.exists(tp) and not args.exhaustive and world == 1 and args.n_scan == N_SCAN and args.m_raw == M_RAW:
+            with open(tp) as f:
+                k = json.load(f)["kernels"].get("icp_search_points_kernel" if method < 2 else "")
+            if k:
+                traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None,
+                    "traffic": traffic,
                     "kernel": {0: "icp_search_points_kernel", 1: "icp_search_points_kernel", 2: "icp_search_means_kernel",
                                3: "icp_accumulate_kernel<3>"}[method],
                     "kernel_ms_avg": dom_ms, "kernel_launches": prof_iters,
