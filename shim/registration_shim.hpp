@@ -1,0 +1,146 @@
+// registration_shim.hpp — drop-in for pcm_matching's registration.hpp / voxel_hash_map.hpp on top of the C ABI of
+// libelimaloc_b200.so, so that pcm_matching.cpp compiles UNCHANGED (it keeps calling local_map_.Init / AddPoints /
+// CalVoxelCovAll / CalPointCovAll and registration_.RunRegister exactly as at pcm_matching.cpp:82-101, 280-282,
+// 412-414).  Header-only; needs Eigen (the node already has it).  It is NOT compiled in this repository's CI because
+// the build image has no Eigen/ROS — the C ABI underneath is what the tests exercise.
+//
+// Reference interface replaced:
+//   struct PointStruct / CovStruct          pcm_matching/include/voxel_hash_map.hpp:41-87   (layout kept)
+//   struct VoxelHashMap                     pcm_matching/include/voxel_hash_map.hpp:89-335
+//   struct RegistrationConfig / Registration pcm_matching/include/registration.hpp:60-230
+#pragma once
+#include <Eigen/Core>
+#include <Eigen/Dense>
+#include <iostream>
+#include <stdexcept>
+#include <vector>
+
+#include "elimaloc_b200.h"
+
+namespace Eigen {
+using Matrix6d = Eigen::Matrix<double, 6, 6>;
+}
+
+struct CovStruct {
+    Eigen::Matrix3d cov;
+    Eigen::Vector3d mean;
+    CovStruct() : cov(Eigen::Matrix3d::Identity()), mean(Eigen::Vector3d::Zero()) {}
+};
+
+struct PointStruct {  // 168 bytes, same field order as the reference
+    Eigen::Vector3d pose;
+    Eigen::Vector3d local;
+    CovStruct covariance;
+    float vel = 0, azi_angle = 0, ele_angle = 0;
+    double intensity = 0;
+    PointStruct() : pose(Eigen::Vector3d::Zero()), local(Eigen::Vector3d::Zero()) {}
+};
+
+typedef enum { P2P, GICP, VGICP, AVGICP } IcpMethod;
+
+struct RegistrationConfig {  // registration.hpp:62-85, every field the node fills
+    int i_max_thread;
+    IcpMethod icp_method;
+    int voxel_search_method;
+    double gicp_cov_search_dist;
+    bool use_radar_cov;
+    int max_iteration;
+    double max_search_dist, lm_lambda, icp_termination_threshold_m, min_overlap_ratio, max_fitness_score;
+    double doppler_trans_lambda, range_variance_m, azimuth_variance_deg, elevation_variance_deg;
+    Eigen::Vector3d ego_to_lidar_trans;
+    Eigen::Matrix3d ego_to_lidar_rot, ego_to_imu_rot;
+    bool b_debug_print;
+};
+
+namespace elm_shim {
+inline std::vector<float> flatten(const std::vector<PointStruct>& pts) {
+    std::vector<float> xyz(3 * pts.size());
+    for (size_t i = 0; i < pts.size(); ++i) {  // Pcl2PointStruct widened float fields: narrowing back is lossless
+        xyz[3 * i] = static_cast<float>(pts[i].pose.x());
+        xyz[3 * i + 1] = static_cast<float>(pts[i].pose.y());
+        xyz[3 * i + 2] = static_cast<float>(pts[i].pose.z());
+    }
+    return xyz;
+}
+inline void check(int status) {
+    // the reference never throws out of these calls; failures degrade to "ICP FAIL" in the caller
+    if (status != ELM_OK) std::cout << "\033[1;33m[elimaloc_b200] " << elm_last_error() << "\033[0m" << std::endl;
+}
+}  // namespace elm_shim
+
+struct VoxelHashMap {
+    VoxelHashMap() {}
+    ~VoxelHashMap() { if (h_) elm_map_destroy(h_); }
+    VoxelHashMap(const VoxelHashMap&) = delete;
+    VoxelHashMap& operator=(const VoxelHashMap&) = delete;
+    void Init(double voxel_size, int max_points_per_voxel) {
+        if (h_) elm_map_destroy(h_);
+        h_ = nullptr;
+        elm_shim::check(elm_map_create(&h_, voxel_size, max_points_per_voxel, /*device=*/0));
+        voxel_size_ = voxel_size;
+        max_points_per_voxel_ = max_points_per_voxel;
+    }
+    void AddPoints(const std::vector<PointStruct>& points) {
+        const std::vector<float> xyz = elm_shim::flatten(points);
+        elm_shim::check(elm_map_add_points(h_, xyz.data(), points.size()));
+    }
+    void CalVoxelCovAll() { elm_shim::check(elm_map_cal_voxel_cov(h_)); }
+    void CalPointCovAll(double d_search_dist) { elm_shim::check(elm_map_cal_point_cov(h_, d_search_dist)); }
+    bool Empty() const { return !h_ || elm_map_empty(h_); }
+    std::vector<PointStruct> Pointcloud() const {  // visualisation only (pcm_matching.cpp:104)
+        std::vector<float> xyz(3 * elm_map_num_points(h_));
+        elm_map_export(h_, nullptr, nullptr, nullptr, nullptr, xyz.data(), nullptr, nullptr);
+        std::vector<PointStruct> out(xyz.size() / 3);
+        for (size_t i = 0; i < out.size(); ++i) out[i].pose = out[i].local = Eigen::Vector3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        return out;
+    }
+    elm_map* h_ = nullptr;
+    double voxel_size_ = 1.0;
+    int max_points_per_voxel_ = 30;
+};
+
+struct Registration {
+    Registration() {}
+    ~Registration() { if (h_) elm_registration_destroy(h_); }
+    void Init(RegistrationConfig config) {
+        config_ = config;
+        if (!h_) elm_shim::check(elm_registration_create(&h_, /*device=*/0, /*stream=*/nullptr));
+    }
+    // registration.hpp:122-124 — identical signature
+    Eigen::Matrix4d RunRegister(const std::vector<PointStruct>& source_local, const VoxelHashMap& voxel_map,
+                                const Eigen::Matrix4d& initial_guess, RegistrationConfig m_config, bool& is_success,
+                                double& fitness_score, Eigen::Matrix6d& local_cov) {
+        elm_reg_config c{};
+        c.icp_method = static_cast<int32_t>(m_config.icp_method);
+        c.max_iteration = m_config.max_iteration;
+        c.max_thread = m_config.i_max_thread;
+        c.use_radar_cov = m_config.use_radar_cov ? 1 : 0;
+        c.debug_print = m_config.b_debug_print ? 1 : 0;
+        c.max_search_dist = m_config.max_search_dist;
+        c.lm_lambda = m_config.lm_lambda;
+        c.icp_termination_threshold_m = m_config.icp_termination_threshold_m;
+        c.min_overlap_ratio = m_config.min_overlap_ratio;
+        c.max_fitness_score = m_config.max_fitness_score;
+        c.range_variance_m = m_config.range_variance_m;
+        c.azimuth_variance_deg = m_config.azimuth_variance_deg;
+        c.elevation_variance_deg = m_config.elevation_variance_deg;
+        const std::vector<float> xyz = elm_shim::flatten(source_local);
+        const Eigen::Matrix<double, 4, 4, Eigen::RowMajor> T0 = initial_guess;  // the ABI is row-major
+        Eigen::Matrix<double, 4, 4, Eigen::RowMajor> T;
+        Eigen::Matrix<double, 6, 6, Eigen::RowMajor> cov;
+        int32_t ok = 0;
+        const int st = elm_run_register(h_, voxel_map.h_, xyz.data(), source_local.size(), T0.data(), &c, T.data(), &ok,
+                                        &fitness_score, cov.data());
+        if (st != ELM_OK) {  // CUDA / NCCL trouble degrades to the reference's soft failure (never throw)
+            elm_shim::check(st);
+            is_success = false;
+            local_cov = Eigen::Matrix6d::Identity();
+            return initial_guess;
+        }
+        is_success = ok != 0;
+        local_cov = cov;
+        return T;
+    }
+    RegistrationConfig config_;
+    elm_registration* h_ = nullptr;
+};
