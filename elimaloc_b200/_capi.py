@@ -23,6 +23,14 @@ class RegConfig(C.Structure):
                 ("azimuth_variance_deg", C.c_double), ("elevation_variance_deg", C.c_double)]
 
 
+class DeskewTables(C.Structure):
+    """elm_deskew_tables — the member tables ImuDeskewInfo / OdomDeskewInfo fill (pcm_matching.cpp:533-729)."""
+    _fields_ = [("imu_time", C.POINTER(C.c_double)), ("imu_rot_x", C.POINTER(C.c_double)), ("imu_rot_y", C.POINTER(C.c_double)),
+                ("imu_rot_z", C.POINTER(C.c_double)), ("imu_pointer_cur", C.c_int32), ("imu_available", C.c_int32),
+                ("odom_available", C.c_int32), ("reserved0", C.c_int32), ("odom_incre_x", C.c_float), ("odom_incre_y", C.c_float),
+                ("odom_incre_z", C.c_float), ("reserved1", C.c_float), ("time_scan_cur", C.c_double), ("time_scan_end", C.c_double)]
+
+
 class ElmError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"elimaloc_b200 status {status}: {message}")
@@ -60,6 +68,8 @@ SIGNATURES = {
     "elm_registration_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "elm_registration_set_binning": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_set_exhaustive": (C.c_int, [C.c_void_p, C.c_int]),
+    "elm_deskew_points": (C.c_int, [C.c_void_p, _fp, _fp, C.c_size_t, C.POINTER(DeskewTables), _fp]),
+    "elm_deskew_points_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(DeskewTables), C.c_void_p]),
     "elm_comm_unique_id": (C.c_int, [_u8p]),
     "elm_registration_set_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
 }

@@ -13,6 +13,7 @@
 
 #include "../../include/elimaloc_b200.h"
 #include "host_map.hpp"
+#include "deskew.cuh"
 #include "icp_kernels.cuh"
 
 namespace {
@@ -175,6 +176,13 @@ struct elm_registration {
     bool pending = false, trivial = false;  // trivial: empty map or n == 0 -> no kernels ran
     elm_reg_config cfg{};
     double T_init[16];
+    // deskew scratch
+    double* d_dtable = nullptr;
+    double* h_dtable = nullptr;  // pinned staging of the four table rows
+    int dtable_cap = 0;
+    float* d_dsk_in = nullptr;   // xyz | rel_time
+    float* d_dsk_out = nullptr;
+    size_t dsk_cap = 0;
     // NCCL
     void* comm = nullptr;
     int rank = 0, world = 1;
@@ -184,6 +192,7 @@ struct elm_registration {
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_ticket); cudaFree(d_stats);
+        cudaFree(d_dtable); cudaFreeHost(h_dtable); cudaFree(d_dsk_in); cudaFree(d_dsk_out);
         cudaFree(d_sorted); cudaFree(d_orig); cudaFree(d_bin); cudaFree(d_hist); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -631,6 +640,63 @@ int elm_registration_set_binning(elm_registration* reg, int enable) {
 int elm_registration_set_exhaustive(elm_registration* reg, int exhaustive) {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     reg->prune = exhaustive ? 0 : 1;
+    return ELM_OK;
+}
+
+int elm_deskew_points_device(elm_registration* reg, const float* d_xyz, const float* d_rel_time, size_t n, const elm_deskew_tables* t,
+                             float* d_xyz_out) {
+    if (!reg || !t || (n && (!d_xyz || !d_rel_time || !d_xyz_out))) return fail(ELM_ERR_INVALID, "elm_deskew_points: bad argument");
+    if (n > 0x7fffffffull / 4) return fail(ELM_ERR_INVALID, "scan too large");
+    if (t->imu_available && (t->imu_pointer_cur < 0 || !t->imu_time || !t->imu_rot_x || !t->imu_rot_y || !t->imu_rot_z))
+        return fail(ELM_ERR_INVALID, "elm_deskew_points: IMU table missing");
+    if (n == 0) return ELM_OK;
+    ELM_CUDA(cudaSetDevice(reg->device));
+    const int entries = t->imu_available ? t->imu_pointer_cur + 1 : 1;
+    if (entries > reg->dtable_cap) {
+        cudaFree(reg->d_dtable); cudaFreeHost(reg->h_dtable);
+        reg->d_dtable = nullptr; reg->h_dtable = nullptr;
+        const int cap = (entries + 255) / 256 * 256;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_dtable), static_cast<size_t>(cap) * 4 * sizeof(double)));
+        ELM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&reg->h_dtable), static_cast<size_t>(cap) * 4 * sizeof(double)));
+        reg->dtable_cap = cap;
+    }
+    elm::DeskewParams p{};
+    p.imu_pointer_cur = t->imu_available ? t->imu_pointer_cur : 0;
+    p.imu_available = t->imu_available;
+    p.odom_available = t->odom_available;
+    p.table_stride = reg->dtable_cap;
+    p.odom_incre_x = t->odom_incre_x; p.odom_incre_y = t->odom_incre_y; p.odom_incre_z = t->odom_incre_z;
+    p.time_scan_cur = t->time_scan_cur; p.time_scan_end = t->time_scan_end;
+    if (t->imu_available) {
+        ELM_CUDA(cudaStreamSynchronize(reg->stream));  // the pinned staging buffer may still feed the previous call
+        const double* rows[4] = {t->imu_time, t->imu_rot_x, t->imu_rot_y, t->imu_rot_z};
+        for (int r = 0; r < 4; ++r) std::memcpy(reg->h_dtable + static_cast<size_t>(r) * reg->dtable_cap, rows[r], entries * sizeof(double));
+        ELM_CUDA(cudaMemcpyAsync(reg->d_dtable, reg->h_dtable, static_cast<size_t>(reg->dtable_cap) * 4 * sizeof(double), cudaMemcpyHostToDevice, reg->stream));
+    }
+    ELM_CUDA(elm::launch_deskew_points(d_xyz, d_rel_time, static_cast<int>(n), p, reg->d_dtable, d_xyz_out, reg->num_sms, reg->stream));
+    return ELM_OK;
+}
+
+int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_time, size_t n, const elm_deskew_tables* t, float* xyz_out) {
+    if (!reg || !t || (n && (!xyz || !rel_time || !xyz_out))) return fail(ELM_ERR_INVALID, "elm_deskew_points: bad argument");
+    if (n == 0) return ELM_OK;
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (n > reg->dsk_cap) {
+        cudaFree(reg->d_dsk_in); cudaFree(reg->d_dsk_out);
+        reg->d_dsk_in = nullptr; reg->d_dsk_out = nullptr;
+        const size_t cap = (n + 1023) / 1024 * 1024;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_dsk_in), cap * 4 * sizeof(float)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_dsk_out), cap * 3 * sizeof(float)));
+        reg->dsk_cap = cap;
+    }
+    float* d_xyz = reg->d_dsk_in;
+    float* d_t = reg->d_dsk_in + 3 * reg->dsk_cap;
+    ELM_CUDA(cudaMemcpyAsync(d_xyz, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    ELM_CUDA(cudaMemcpyAsync(d_t, rel_time, n * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    const int rc = elm_deskew_points_device(reg, d_xyz, d_t, n, t, reg->d_dsk_out);
+    if (rc) return rc;
+    ELM_CUDA(cudaMemcpyAsync(xyz_out, reg->d_dsk_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
     return ELM_OK;
 }
 

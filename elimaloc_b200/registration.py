@@ -205,6 +205,31 @@ class Registration:
                                         _i(cnt), _d(tgt)))
         return cnt, tgt
 
+    # ---- deskew (PcmMatching::DeskewPointCloud's per-point loop, pcm_matching.cpp:499-511, 780-824) ----
+    @staticmethod
+    def _deskew_tables(t):
+        keep = [np.ascontiguousarray(t[k], dtype=np.float64) for k in ("imu_time", "imu_rot_x", "imu_rot_y", "imu_rot_z")]
+        inc = np.asarray(t["odom_incre"], dtype=np.float32)
+        st = _capi.DeskewTables(_d(keep[0]), _d(keep[1]), _d(keep[2]), _d(keep[3]), int(t["imu_pointer_cur"]), int(t["imu_available"]),
+                                int(t["odom_available"]), 0, float(inc[0]), float(inc[1]), float(inc[2]), 0.0,
+                                float(t["time_scan_cur"]), float(t["time_scan_end"]))
+        return st, keep
+
+    def DeskewPoints(self, xyz, rel_time, tables):
+        """tables: dict with imu_time, imu_rot_{x,y,z}, imu_pointer_cur, imu_available, odom_available, odom_incre[3],
+        time_scan_cur, time_scan_end (the node's member variables of the same meaning)."""
+        xyz = _xyz(xyz)
+        rt = np.ascontiguousarray(rel_time, dtype=np.float32)
+        out = np.zeros_like(xyz)
+        st, keep = self._deskew_tables(tables)
+        check(lib().elm_deskew_points(self._h, _f(xyz), _f(rt), xyz.shape[0], C.byref(st), _f(out)))
+        return out
+
+    def deskew_device(self, d_xyz_ptr, d_time_ptr, n, tables, d_out_ptr):
+        st, keep = self._deskew_tables(tables)
+        check(lib().elm_deskew_points_device(self._h, C.c_void_p(d_xyz_ptr), C.c_void_p(d_time_ptr), int(n), C.byref(st),
+                                             C.c_void_p(d_out_ptr)))
+
     # ---- multi-GPU ----
     @staticmethod
     def comm_unique_id():

@@ -153,6 +153,32 @@ int elm_registration_set_binning(elm_registration* reg, int enable);
  * voxels exactly like GetCorrespondencePoints (voxel_hash_map.cpp:40-51) — same answers, more bytes. */
 int elm_registration_set_exhaustive(elm_registration* reg, int exhaustive);
 
+/* ---- deskew --------------------------------------------------------------------------------------------------- */
+/* Inputs of the per-point deskew = the member tables PcmMatching::ImuDeskewInfo / OdomDeskewInfo fill on the host
+ * (pcm_matching.cpp:533-729; vec_d_imu_time_, vec_d_imu_rot_{x,y,z}_, i_imu_pointer_cur_, f_odom_incre_{x,y,z}_,
+ * d_time_scan_cur_, d_time_scan_end_, b_is_imu_available_, b_is_odom_available_). */
+typedef struct elm_deskew_tables {
+    const double* imu_time;  /* host arrays, imu_pointer_cur + 1 valid entries each */
+    const double* imu_rot_x;
+    const double* imu_rot_y;
+    const double* imu_rot_z;
+    int32_t imu_pointer_cur;
+    int32_t imu_available;
+    int32_t odom_available;
+    int32_t reserved0;
+    float odom_incre_x, odom_incre_y, odom_incre_z, reserved1;
+    double time_scan_cur, time_scan_end;
+} elm_deskew_tables;
+
+/* The tbb::parallel_for over DeskewPoint of PcmMatching::DeskewPointCloud (pcm_matching.cpp:499-511, 780-824) with
+ * FindRotation / FindPosition (:731-778): xyz[3n] + rel_time[n] (PointXYZIT::time, seconds after scan start) ->
+ * xyz_out[3n], float32 like the reference.  Host buffers, synchronous; runs on the registration handle's device/stream. */
+int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_time, size_t n, const elm_deskew_tables* tables,
+                      float* xyz_out);
+/* Same with device buffers (d_xyz_out may feed elm_register_enqueue directly); asynchronous on the handle's stream. */
+int elm_deskew_points_device(elm_registration* reg, const float* d_xyz, const float* d_rel_time, size_t n,
+                             const elm_deskew_tables* tables, float* d_xyz_out);
+
 /* ---- multi-GPU (one process per GPU; scan sharded over ranks, map replicated) --------------------------------- */
 /* unique_id: 128 bytes.  Rank 0 fills it with elm_comm_unique_id and hands it to the other ranks (bench.py uses
  * torch.distributed for that); every rank then calls elm_registration_set_comm.  After that each RunRegister sums the

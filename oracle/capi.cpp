@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "registration.hpp"
+#include "deskew.hpp"
 
 using namespace orc;
 
@@ -178,6 +179,38 @@ double orc_time_register(void* reg, void* map, const float* src, size_t n, const
     const auto t1 = std::chrono::steady_clock::now();
     if (iters_done) *iters_done = (int32_t)trace.size();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- deskew (pcm_matching.cpp:467-824) -------------------------------------------------------------------------------
+// tables: out arrays of kImuQueueLength doubles each; meta_i = {imu_pointer_cur, imu_available, odom_available};
+// meta_f = {odom_incre_x, y, z}
+void orc_deskew_tables(const double* imu_stamp, const double* gyro_xyz, int n_imu, const double* start_pose, double start_stamp,
+                       const double* end_pose, double end_stamp, double time_scan_cur, double time_scan_end, double* imu_time,
+                       double* rot_x, double* rot_y, double* rot_z, int32_t* meta_i, float* meta_f) {
+    DeskewTables t;
+    t.time_scan_cur = time_scan_cur;
+    t.time_scan_end = time_scan_end;
+    ImuDeskewInfo(imu_stamp, gyro_xyz, n_imu, t);
+    if (start_pose && end_pose) OdomDeskewInfo(start_pose, start_stamp, end_pose, end_stamp, t);
+    std::memcpy(imu_time, t.imu_time.data(), kImuQueueLength * sizeof(double));
+    std::memcpy(rot_x, t.imu_rot_x.data(), kImuQueueLength * sizeof(double));
+    std::memcpy(rot_y, t.imu_rot_y.data(), kImuQueueLength * sizeof(double));
+    std::memcpy(rot_z, t.imu_rot_z.data(), kImuQueueLength * sizeof(double));
+    meta_i[0] = t.imu_pointer_cur; meta_i[1] = t.imu_available; meta_i[2] = t.odom_available;
+    meta_f[0] = t.odom_incre_x; meta_f[1] = t.odom_incre_y; meta_f[2] = t.odom_incre_z;
+}
+
+void orc_deskew_points(const double* imu_time, const double* rot_x, const double* rot_y, const double* rot_z, const int32_t* meta_i,
+                       const float* meta_f, double time_scan_cur, double time_scan_end, const float* xyz, const float* rel_time, size_t n,
+                       float* out) {
+    DeskewTables t;
+    const int e = meta_i[0] + 1;
+    t.imu_time.assign(imu_time, imu_time + e); t.imu_rot_x.assign(rot_x, rot_x + e);
+    t.imu_rot_y.assign(rot_y, rot_y + e); t.imu_rot_z.assign(rot_z, rot_z + e);
+    t.imu_pointer_cur = meta_i[0]; t.imu_available = meta_i[1] != 0; t.odom_available = meta_i[2] != 0;
+    t.odom_incre_x = meta_f[0]; t.odom_incre_y = meta_f[1]; t.odom_incre_z = meta_f[2];
+    t.time_scan_cur = time_scan_cur; t.time_scan_end = time_scan_end;
+    DeskewPoints(t, xyz, rel_time, n, out);
 }
 
 }  // extern "C"

@@ -69,6 +69,8 @@ def lib():
         L.orc_correspondences.argtypes = [C.c_void_p, fp, C.c_size_t, dp, C.c_int, C.c_double, ip, dp]
         L.orc_time_register.restype = C.c_double
         L.orc_time_register.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_size_t, dp, C.POINTER(RegConfig), ip]
+        L.orc_deskew_tables.argtypes = [dp, dp, C.c_int, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp, ip, fp]
+        L.orc_deskew_points.argtypes = [dp, dp, dp, dp, ip, fp, C.c_double, C.c_double, fp, fp, C.c_size_t, fp]
         _LIB = L
     return _LIB
 
@@ -185,3 +187,35 @@ def correspondences(voxel_map, source_local, pose, method, max_dist):
     lib().orc_correspondences(voxel_map._h, _f(src), src.shape[0], _d(T0), int(method), float(max_dist), _i(cnt),
                               _d(tgt))
     return cnt, tgt
+
+
+IMU_QUEUE_LENGTH = 2000
+
+
+def deskew_tables(imu_stamp, gyro_xyz, time_scan_cur, time_scan_end, start_pose=None, start_stamp=0.0, end_pose=None, end_stamp=0.0):
+    """ImuDeskewInfo + OdomDeskewInfo (pcm_matching.cpp:533-729) on plain arrays -> dict of the member tables."""
+    st = np.ascontiguousarray(imu_stamp, dtype=np.float64)
+    gy = np.ascontiguousarray(gyro_xyz, dtype=np.float64).reshape(-1, 3)
+    t = dict(imu_time=np.zeros(IMU_QUEUE_LENGTH), imu_rot_x=np.zeros(IMU_QUEUE_LENGTH), imu_rot_y=np.zeros(IMU_QUEUE_LENGTH),
+             imu_rot_z=np.zeros(IMU_QUEUE_LENGTH))
+    mi, mf = np.zeros(3, np.int32), np.zeros(3, np.float32)
+    sp = np.ascontiguousarray(start_pose, dtype=np.float64) if start_pose is not None else None
+    ep = np.ascontiguousarray(end_pose, dtype=np.float64) if end_pose is not None else None
+    lib().orc_deskew_tables(_d(st), _d(gy), len(st), _d(sp) if sp is not None else None, float(start_stamp),
+                            _d(ep) if ep is not None else None, float(end_stamp), float(time_scan_cur), float(time_scan_end),
+                            _d(t["imu_time"]), _d(t["imu_rot_x"]), _d(t["imu_rot_y"]), _d(t["imu_rot_z"]), _i(mi), _f(mf))
+    t.update(imu_pointer_cur=int(mi[0]), imu_available=bool(mi[1]), odom_available=bool(mi[2]), odom_incre=mf.copy(),
+             time_scan_cur=float(time_scan_cur), time_scan_end=float(time_scan_end))
+    return t
+
+
+def deskew_points(t, xyz, rel_time):
+    """DeskewPoint over a scan (pcm_matching.cpp:499-511, 780-824), float32."""
+    xyz = _xyz(xyz)
+    rt = np.ascontiguousarray(rel_time, dtype=np.float32)
+    out = np.zeros_like(xyz)
+    mi = np.array([t["imu_pointer_cur"], int(t["imu_available"]), int(t["odom_available"])], np.int32)
+    mf = np.ascontiguousarray(t["odom_incre"], dtype=np.float32)
+    lib().orc_deskew_points(_d(t["imu_time"]), _d(t["imu_rot_x"]), _d(t["imu_rot_y"]), _d(t["imu_rot_z"]), _i(mi), _f(mf),
+                            t["time_scan_cur"], t["time_scan_end"], _f(xyz), _f(rt), xyz.shape[0], _f(out))
+    return out
