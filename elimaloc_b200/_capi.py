@@ -31,6 +31,33 @@ class DeskewTables(C.Structure):
                 ("odom_incre_z", C.c_float), ("reserved1", C.c_float), ("time_scan_cur", C.c_double), ("time_scan_end", C.c_double)]
 
 
+class EkfConfig(C.Structure):
+    """elm_ekf_config (EkfLocalizationConfig subset); defaults of config/localization.ini in ekf.make_ekf_config"""
+    _fields_ = [(n, C.c_double) for n in ("imu_gravity", "ekf_init_x_m", "ekf_init_y_m", "ekf_init_z_m", "ekf_init_roll_deg",
+                                          "ekf_init_pitch_deg", "ekf_init_yaw_deg", "state_std_pos_m", "state_std_rot_deg",
+                                          "state_std_vel_mps", "imu_std_gyro_dps", "imu_std_acc_mps", "imu_bias_cov_gyro",
+                                          "imu_bias_cov_acc")] + [("imu_estimate_gravity", C.c_int32),
+                                                                  ("use_complementary_filter", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
+class EkfState(C.Structure):
+    """elm_ekf_state"""
+    _fields_ = [("pos", C.c_double * 3), ("rot", C.c_double * 4), ("vel", C.c_double * 3), ("gyro", C.c_double * 3),
+                ("acc", C.c_double * 3), ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("grav", C.c_double * 3),
+                ("imu_rot", C.c_double * 4), ("P", C.c_double * (27 * 27)), ("prev_timestamp", C.c_double),
+                ("prev_gnss_timestamp", C.c_double), ("ckf_prev_vel_local_x", C.c_double), ("ckf_prev_time", C.c_double),
+                ("ego", C.c_double * 26), ("ego_prev_timestamp", C.c_double)] + \
+               [(n, C.c_int32) for n in ("reset_for_init_prediction", "state_initialized", "yaw_initialized", "rotation_stabilized",
+                                         "state_stabilized", "pcm_init_on_going", "pcm_update_count", "ckf_has_prev", "predictions",
+                                         "updates")] + [("reserved", C.c_int32 * 2)]
+
+
+class EkfMeasurement(C.Structure):
+    """elm_ekf_measurement; source 3 = PCM, 4 = PCM_INIT"""
+    _fields_ = [("timestamp", C.c_double), ("pos", C.c_double * 3), ("rot", C.c_double * 4), ("pos_cov", C.c_double * 9),
+                ("rot_cov", C.c_double * 9), ("source", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ElmError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"elimaloc_b200 status {status}: {message}")
@@ -70,6 +97,13 @@ SIGNATURES = {
     "elm_registration_set_exhaustive": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_deskew_points": (C.c_int, [C.c_void_p, _fp, _fp, C.c_size_t, C.POINTER(DeskewTables), _fp]),
     "elm_deskew_points_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(DeskewTables), C.c_void_p]),
+    "elm_ekf_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(EkfConfig), C.c_int, C.c_void_p]),
+    "elm_ekf_destroy": (None, [C.c_void_p]),
+    "elm_ekf_predict_imu": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),
+    "elm_ekf_update_pose": (C.c_int, [C.c_void_p, C.POINTER(EkfMeasurement)]),
+    "elm_ekf_get_state": (C.c_int, [C.c_void_p, C.POINTER(EkfState)]),
+    "elm_ekf_set_state": (C.c_int, [C.c_void_p, C.POINTER(EkfState)]),
+    "elm_ekf_get_current_state": (C.c_int, [C.c_void_p, _dp]),
     "elm_comm_unique_id": (C.c_int, [_u8p]),
     "elm_registration_set_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
 }

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -14,6 +15,7 @@
 #include "../../include/elimaloc_b200.h"
 #include "host_map.hpp"
 #include "deskew.cuh"
+#include "ekf.cuh"
 #include "icp_kernels.cuh"
 
 namespace {
@@ -194,6 +196,20 @@ struct elm_registration {
         cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_ticket); cudaFree(d_stats);
         cudaFree(d_dtable); cudaFreeHost(h_dtable); cudaFree(d_dsk_in); cudaFree(d_dsk_out);
         cudaFree(d_sorted); cudaFree(d_orig); cudaFree(d_bin); cudaFree(d_hist); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct elm_ekf {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    elm_ekf_config cfg{};
+    elm_ekf_state* d_state = nullptr;
+    elm_ekf_state* h_state = nullptr;  // pinned
+    ~elm_ekf() {
+        cudaSetDevice(device);
+        cudaFree(d_state); cudaFreeHost(h_state);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -697,6 +713,85 @@ int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_
     if (rc) return rc;
     ELM_CUDA(cudaMemcpyAsync(xyz_out, reg->d_dsk_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    return ELM_OK;
+}
+
+int elm_ekf_create(elm_ekf** out, const elm_ekf_config* cfg, int device, void* stream) {
+    if (!out || !cfg) return fail(ELM_ERR_INVALID, "elm_ekf_create: bad argument");
+    if (device < 0 || device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_ekf_create: no such CUDA device");
+    ELM_CUDA(cudaSetDevice(device));
+    elm_ekf* e = new (std::nothrow) elm_ekf();
+    if (!e) return fail(ELM_ERR_INVALID, "out of memory");
+    e->device = device;
+    e->cfg = *cfg;
+    if (stream) e->stream = static_cast<cudaStream_t>(stream);
+    else {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return fail(ELM_ERR_CUDA, "cudaStreamCreate failed"); }
+        e->own_stream = true;
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&e->d_state), sizeof(elm_ekf_state)) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&e->h_state), sizeof(elm_ekf_state)) != cudaSuccess) {
+        delete e;
+        return fail(ELM_ERR_CUDA, "EKF state allocation failed");
+    }
+    elm::ekf_init_state(*cfg, *e->h_state);
+    if (cudaMemcpyAsync(e->d_state, e->h_state, sizeof(elm_ekf_state), cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+        cudaStreamSynchronize(e->stream) != cudaSuccess) {
+        delete e;
+        return fail(ELM_ERR_CUDA, "EKF state upload failed");
+    }
+    *out = e;
+    return ELM_OK;
+}
+
+void elm_ekf_destroy(elm_ekf* ekf) { delete ekf; }
+
+int elm_ekf_predict_imu(elm_ekf* ekf, double timestamp, const double gyro[3], const double acc[3]) {
+    if (!ekf || !gyro || !acc) return fail(ELM_ERR_INVALID, "elm_ekf_predict_imu: bad argument");
+    ELM_CUDA(cudaSetDevice(ekf->device));
+    ELM_CUDA(elm::launch_ekf_predict_imu(ekf->d_state, ekf->cfg, timestamp, gyro, acc, ekf->stream));
+    return ELM_OK;
+}
+
+int elm_ekf_update_pose(elm_ekf* ekf, const elm_ekf_measurement* meas) {
+    if (!ekf || !meas) return fail(ELM_ERR_INVALID, "elm_ekf_update_pose: bad argument");
+    if (meas->source != 3 && meas->source != 4) return fail(ELM_ERR_UNSUPPORTED, "only the PCM (3) and PCM_INIT (4) sources are in scope");
+    ELM_CUDA(cudaSetDevice(ekf->device));
+    ELM_CUDA(elm::launch_ekf_update_pose(ekf->d_state, ekf->cfg, *meas, ekf->stream));
+    return ELM_OK;
+}
+
+int elm_ekf_get_state(elm_ekf* ekf, elm_ekf_state* out) {
+    if (!ekf || !out) return fail(ELM_ERR_INVALID, "elm_ekf_get_state: bad argument");
+    ELM_CUDA(cudaSetDevice(ekf->device));
+    ELM_CUDA(cudaMemcpyAsync(ekf->h_state, ekf->d_state, sizeof(elm_ekf_state), cudaMemcpyDeviceToHost, ekf->stream));
+    ELM_CUDA(cudaStreamSynchronize(ekf->stream));
+    std::memcpy(out, ekf->h_state, sizeof(elm_ekf_state));
+    return ELM_OK;
+}
+
+int elm_ekf_set_state(elm_ekf* ekf, const elm_ekf_state* in) {
+    if (!ekf || !in) return fail(ELM_ERR_INVALID, "elm_ekf_set_state: bad argument");
+    ELM_CUDA(cudaSetDevice(ekf->device));
+    ELM_CUDA(cudaStreamSynchronize(ekf->stream));
+    std::memcpy(ekf->h_state, in, sizeof(elm_ekf_state));
+    ELM_CUDA(cudaMemcpyAsync(ekf->d_state, ekf->h_state, sizeof(elm_ekf_state), cudaMemcpyHostToDevice, ekf->stream));
+    ELM_CUDA(cudaStreamSynchronize(ekf->stream));
+    return ELM_OK;
+}
+
+int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]) {
+    if (!ekf || !ego) return fail(ELM_ERR_INVALID, "elm_ekf_get_current_state: bad argument");
+    ELM_CUDA(cudaSetDevice(ekf->device));
+    ELM_CUDA(cudaMemcpyAsync(ekf->h_state, ekf->d_state, sizeof(elm_ekf_state), cudaMemcpyDeviceToHost, ekf->stream));
+    ELM_CUDA(cudaStreamSynchronize(ekf->stream));
+    if (!elm::ekf_current_state(*ekf->h_state, ego)) {
+        // prev_ego_state_ is part of the filter object: keep the device copy of the cache in step
+        const size_t off = offsetof(elm_ekf_state, ego);
+        ELM_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(ekf->d_state) + off, reinterpret_cast<char*>(ekf->h_state) + off,
+                                 27 * sizeof(double), cudaMemcpyHostToDevice, ekf->stream));
+        ELM_CUDA(cudaStreamSynchronize(ekf->stream));
+    }
     return ELM_OK;
 }
 

@@ -179,6 +179,63 @@ int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_
 int elm_deskew_points_device(elm_registration* reg, const float* d_xyz, const float* d_rel_time, size_t n,
                              const elm_deskew_tables* tables, float* d_xyz_out);
 
+/* ---- EKF (ekf_localization) ------------------------------------------------------------------------------------ */
+/* The 27-state filter of EkfAlgorithm (README: "24-DOF"; STATE_ORDER is 27, ekf_algorithm.hpp:41-69) with its state and
+ * covariance resident in HBM.  In scope: Init, RunPredictionImu, RunGnssUpdate for the PCM / PCM_INIT sources,
+ * UpdateEkfState, ComplementaryKalmanFilter, the Check* flags, GetCurrentState.  CAN / ZUPT / NavSat / IMU-mount
+ * calibration branches are off in config/localization.ini and not provided. */
+#define ELM_EKF_STATE_ORDER 27
+
+/* EkfLocalizationConfig fields those functions read (ekf_localization_config.hpp:20-95; INI names in the comments) */
+typedef struct elm_ekf_config {
+    double imu_gravity;           /* imu_gravity */
+    double ekf_init_x_m, ekf_init_y_m, ekf_init_z_m, ekf_init_roll_deg, ekf_init_pitch_deg, ekf_init_yaw_deg;
+    double state_std_pos_m;       /* ekf_state_uncertainty_pos_m */
+    double state_std_rot_deg;     /* ekf_state_uncertainty_rot_deg */
+    double state_std_vel_mps;     /* ekf_state_uncertainty_vel_mps */
+    double imu_std_gyro_dps;      /* ekf_imu_uncertainty_gyro_dps */
+    double imu_std_acc_mps;       /* ekf_imu_uncertainty_acc_mps */
+    double imu_bias_cov_gyro;     /* ekf_imu_bias_cov_gyro */
+    double imu_bias_cov_acc;      /* ekf_imu_bias_cov_acc */
+    int32_t imu_estimate_gravity; /* imu_estimate_gravity */
+    int32_t use_complementary_filter;
+    int32_t reserved[2];
+} elm_ekf_config;
+
+/* Members of EkfAlgorithm (ekf_algorithm.hpp:269-289: S_, P_, flags, prev_timestamp_, prev_ego_state_) plus the
+ * function-static memory of ComplementaryKalmanFilter (ekf_algorithm.cpp:613-614).  Quaternions are (w, x, y, z);
+ * P is row-major 27 x 27 in the S_X .. S_IMU_YAW order. */
+typedef struct elm_ekf_state {
+    double pos[3], rot[4], vel[3], gyro[3], acc[3], bg[3], ba[3], grav[3], imu_rot[4];
+    double P[ELM_EKF_STATE_ORDER * ELM_EKF_STATE_ORDER];
+    double prev_timestamp, prev_gnss_timestamp;
+    double ckf_prev_vel_local_x, ckf_prev_time;
+    double ego[26], ego_prev_timestamp;
+    int32_t reset_for_init_prediction, state_initialized, yaw_initialized, rotation_stabilized, state_stabilized;
+    int32_t pcm_init_on_going, pcm_update_count, ckf_has_prev, predictions, updates, reserved[2];
+} elm_ekf_state;
+
+/* EkfGnssMeasurement (localization_struct.hpp:146-153); source follows the GnssSource enum: 3 = PCM, 4 = PCM_INIT */
+typedef struct elm_ekf_measurement {
+    double timestamp, pos[3], rot[4], pos_cov[9], rot_cov[9];
+    int32_t source, reserved;
+} elm_ekf_measurement;
+
+typedef struct elm_ekf elm_ekf;
+/* EkfAlgorithm::EkfAlgorithm + Init (ekf_algorithm.cpp:13-66) */
+int elm_ekf_create(elm_ekf** out, const elm_ekf_config* cfg, int device, void* stream);
+void elm_ekf_destroy(elm_ekf* ekf);
+/* RunPredictionImu (ekf_algorithm.cpp:167-316): one single-block kernel, asynchronous on the handle's stream */
+int elm_ekf_predict_imu(elm_ekf* ekf, double timestamp, const double gyro[3], const double acc[3]);
+/* RunGnssUpdate for the PCM / PCM_INIT sources (ekf_algorithm.cpp:318-432): one kernel, asynchronous */
+int elm_ekf_update_pose(elm_ekf* ekf, const elm_ekf_measurement* meas);
+/* raw state down / up (synchronises the stream) */
+int elm_ekf_get_state(elm_ekf* ekf, elm_ekf_state* out);
+int elm_ekf_set_state(elm_ekf* ekf, const elm_ekf_state* in);
+/* GetCurrentState (ekf_algorithm.cpp:778-833): ego[26] = timestamp, x y z, roll pitch yaw, roll/pitch/yaw rate,
+ * vx vy vz (local), ax ay az (local), x/y/z_cov_m (local), latitude/longitude/height std, roll/pitch/yaw cov, 0 */
+int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]);
+
 /* ---- multi-GPU (one process per GPU; scan sharded over ranks, map replicated) --------------------------------- */
 /* unique_id: 128 bytes.  Rank 0 fills it with elm_comm_unique_id and hands it to the other ranks (bench.py uses
  * torch.distributed for that); every rank then calls elm_registration_set_comm.  After that each RunRegister sums the

@@ -9,6 +9,7 @@
 
 #include "registration.hpp"
 #include "deskew.hpp"
+#include "ekf.hpp"
 
 using namespace orc;
 
@@ -212,5 +213,12 @@ void orc_deskew_points(const double* imu_time, const double* rot_x, const double
     t.time_scan_cur = time_scan_cur; t.time_scan_end = time_scan_end;
     DeskewPoints(t, xyz, rel_time, n, out);
 }
+
+// ---- EKF (ekf_algorithm.cpp) -------------------------------------------------------------------------------------------
+size_t orc_ekf_state_size() { return sizeof(EkfStateBlob); }
+void orc_ekf_init(const EkfConfig* c, EkfStateBlob* s) { EkfInit(*c, *s); }
+int orc_ekf_predict_imu(const EkfConfig* c, EkfStateBlob* s, double t, const double* gyro, const double* acc) { return EkfPredictImu(*c, *s, t, gyro, acc) ? 1 : 0; }
+int orc_ekf_update_pose(const EkfConfig* c, EkfStateBlob* s, const EkfMeasurement* m) { return EkfUpdatePose(*c, *s, *m) ? 1 : 0; }
+void orc_ekf_get_current_state(EkfStateBlob* s, double* ego) { EkfGetCurrentState(*s, ego); }
 
 }  // extern "C"

@@ -71,6 +71,11 @@ def lib():
         L.orc_time_register.argtypes = [C.c_void_p, C.c_void_p, fp, C.c_size_t, dp, C.POINTER(RegConfig), ip]
         L.orc_deskew_tables.argtypes = [dp, dp, C.c_int, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp, ip, fp]
         L.orc_deskew_points.argtypes = [dp, dp, dp, dp, ip, fp, C.c_double, C.c_double, fp, fp, C.c_size_t, fp]
+        L.orc_ekf_state_size.restype = C.c_size_t
+        L.orc_ekf_init.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_ekf_predict_imu.argtypes = [C.c_void_p, C.c_void_p, C.c_double, dp, dp]
+        L.orc_ekf_update_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ekf_get_current_state.argtypes = [C.c_void_p, dp]
         _LIB = L
     return _LIB
 
@@ -219,3 +224,27 @@ def deskew_points(t, xyz, rel_time):
     lib().orc_deskew_points(_d(t["imu_time"]), _d(t["imu_rot_x"]), _d(t["imu_rot_y"]), _d(t["imu_rot_z"]), _i(mi), _f(mf),
                             t["time_scan_cur"], t["time_scan_end"], _f(xyz), _f(rt), xyz.shape[0], _f(out))
     return out
+
+
+class EkfAlgorithm:
+    """Oracle EKF (oracle/ekf.cpp).  cfg / state / measurement are ctypes structures with the layout of
+    elm_ekf_config / elm_ekf_state / elm_ekf_measurement (passed in by the tests so that both sides share them)."""
+
+    def __init__(self, cfg, state_type):
+        self.cfg = cfg
+        self.s = state_type()
+        assert C.sizeof(self.s) == lib().orc_ekf_state_size(), "EKF state layout mismatch between oracle and C ABI"
+        lib().orc_ekf_init(C.byref(self.cfg), C.byref(self.s))
+
+    def RunPredictionImu(self, t, gyro, acc):
+        g = np.ascontiguousarray(gyro, dtype=np.float64)
+        a = np.ascontiguousarray(acc, dtype=np.float64)
+        return bool(lib().orc_ekf_predict_imu(C.byref(self.cfg), C.byref(self.s), float(t), _d(g), _d(a)))
+
+    def RunGnssUpdate(self, meas):
+        return bool(lib().orc_ekf_update_pose(C.byref(self.cfg), C.byref(self.s), C.byref(meas)))
+
+    def GetCurrentState(self):
+        ego = np.zeros(26)
+        lib().orc_ekf_get_current_state(C.byref(self.s), _d(ego))
+        return ego
