@@ -34,6 +34,34 @@ def map_u(m_raw, box, seed=SEED_MAP, origin=0.0):
     return out
 
 
+def map_s(m_raw, box, seed=SEED_MAP, ground_z=0.0, n_walls=24, wall_height=6.0):
+    """Map-S: surface-like map (optional): a ground plane z ~ N(ground_z, 0.02^2) plus random
+    vertical walls with 2 cm thickness noise, inside [0, box)^2.  Voxel-Gaussian methods (VGICP / AVGICP) need surfaces;
+    on the uniform Map-U their voxel means carry almost no geometry."""
+    rng = np.random.default_rng(seed)
+    n_ground = m_raw // 2
+    g = np.empty((n_ground, 3))
+    g[:, :2] = rng.random((n_ground, 2)) * box
+    g[:, 2] = ground_z + rng.normal(0.0, 0.02, n_ground)
+    n_wall = m_raw - n_ground
+    per = n_wall // n_walls
+    walls = []
+    for w in range(n_walls):
+        n = per if w < n_walls - 1 else n_wall - per * (n_walls - 1)
+        c = rng.random(2) * box
+        a = rng.random() * np.pi
+        d = np.array([np.cos(a), np.sin(a)])
+        length = box * (0.2 + 0.5 * rng.random())
+        u = (rng.random(n) - 0.5) * length
+        xy = c[None, :] + u[:, None] * d[None, :] + rng.normal(0.0, 0.02, (n, 1)) * np.array([-d[1], d[0]])[None, :]
+        z = ground_z + rng.random(n) * wall_height
+        walls.append(np.column_stack([xy, z]))
+    pts = np.vstack([g] + walls)
+    keep = (pts[:, 0] >= 0) & (pts[:, 0] < box) & (pts[:, 1] >= 0) & (pts[:, 1] < box)
+    pts = pts[keep]
+    return pts[rng.permutation(len(pts))].astype(np.float32)
+
+
 def scan_u(n, half_width, seed=SEED_SCAN):
     """Scan-U (throughput): n float32 points uniform in a cube of the given half width around the sensor."""
     rng = np.random.default_rng(seed)

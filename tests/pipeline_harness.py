@@ -1,0 +1,314 @@
+"""BASELINE config 5 harness: deskew -> AVGICP registration -> covariance shaping -> time compensation -> EKF update, scans
+streamed at 10 Hz with a 100 Hz IMU, closing the loop through the EKF pose like the two ROS nodes do.
+
+The per-point / per-matrix work is done by an ARM (the oracle on the CPU or the product on the GPU); the small host glue
+between those steps is restated ONCE here in numpy and shared by both arms, so it cannot be a source of divergence
+(SURVEY.md section 8 row a22).  Glue restated (reference file:line):
+  GetInterpolatedPose      pcm_matching/src/pcm_matching.cpp:933-1045 (float32 Affine3f, slerp lfun.hpp:216-241)
+  sync_lidar_pose          pcm_matching.cpp:266                        icp_ego_pose  :298
+  PublishPcmOdom shaping   pcm_matching.cpp:1082-1098, pcm_matching.hpp:222-273
+  CallbackPcmOdom          ekf_localization/src/ekf_localization.cpp:147-179
+  GnssTimeCompensation     ekf_localization.cpp:323-394
+  ImuDeskewInfo / OdomDeskewInfo  pcm_matching.cpp:533-729 (through oracle.deskew_tables — table builders are glue)
+Not modelled: ROS transport delays other than one fixed processing latency, VoxelDownsample (disabled: cell 0 keeps
+every point, the default 1.5 m cell would leave a few thousand points), the Ouster index sampling (Q17)."""
+import numpy as np
+
+from elimaloc_b200 import ekf as pekf, synth
+from oracle import oracle as O
+
+F32 = np.float32
+
+
+# ------------------------------------------------------------------------------------------------ small maths (glue)
+def rpy_to_R(r, p, y):
+    return synth.exp_so3([0, 0, y]) @ synth.exp_so3([0, p, 0]) @ synth.exp_so3([r, 0, 0])
+
+
+def R_to_quat_wxyz(R):
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        return np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    i = int(np.argmax(np.diag(R)))
+    j, k = (i + 1) % 3, (i + 2) % 3
+    s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+    q = np.zeros(4)
+    q[0] = (R[k, j] - R[j, k]) / s
+    q[1 + i] = 0.25 * s
+    q[1 + j] = (R[j, i] + R[i, j]) / s
+    q[1 + k] = (R[k, i] + R[i, k]) / s
+    return q
+
+
+def quat_to_R(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def rot_to_vec(R):  # lfun.hpp RotToVec
+    if abs(R[2, 0]) > 0.998:
+        a = [0.0, np.pi / 2 * (1 if R[2, 0] >= 0 else -1), np.arctan2(-R[1, 2], R[1, 1])]
+    else:
+        p = np.arcsin(-R[2, 0])
+        a = [np.arctan2(R[2, 1] / np.cos(p), R[2, 2] / np.cos(p)), p, np.arctan2(R[1, 0] / np.cos(p), R[0, 0] / np.cos(p))]
+    return np.array([np.fmod(v + np.pi, 2 * np.pi) - np.pi for v in a])
+
+
+def angle_diff(ref, rel):  # lfun.hpp AngleDiffRad
+    d = rel - ref
+    while d > np.pi:
+        d -= 2 * np.pi
+    while d < -np.pi:
+        d += 2 * np.pi
+    return d
+
+
+def interpolate_tf_with_time(M, dt_scan, dt_trans):
+    """InterpolateTfWithTime in float32 (lfun.hpp:216-241)"""
+    if dt_trans == 0.0:
+        return np.eye(4, dtype=F32)
+    ratio = F32(dt_scan / dt_trans)
+    trans = (M[:3, 3] * ratio).astype(F32)
+    q = R_to_quat_wxyz(M[:3, :3].astype(np.float64)).astype(F32)
+    ident = np.array([1, 0, 0, 0], F32)
+    d = F32(np.dot(ident, q))
+    ad = abs(d)
+    if ad >= F32(1.0) - np.finfo(F32).eps:
+        s0, s1 = F32(1) - ratio, ratio
+    else:
+        th = np.arccos(ad)
+        st = np.sin(th)
+        s0, s1 = F32(np.sin((F32(1) - ratio) * th) / st), F32(np.sin(ratio * th) / st)
+    if d < 0:
+        s1 = -s1
+    qi = (s0 * ident + s1 * q).astype(F32)
+    out = np.eye(4, dtype=F32)
+    out[:3, :3] = quat_to_R(qi.astype(np.float64)).astype(F32)
+    out[:3, 3] = trans
+    return out
+
+
+def odom_to_affine(o):
+    M = np.eye(4, dtype=F32)
+    M[:3, :3] = quat_to_R(o["quat"]).astype(F32)
+    M[:3, 3] = o["pos"].astype(F32)
+    return M
+
+
+def get_interpolated_pose(deq, t):
+    """pcm_matching.cpp:933-1045 (the extrapolation branch integrates the last twist)"""
+    before = after = None
+    for o in deq:
+        if o["t"] <= t:
+            before = o
+        if o["t"] > t:
+            after = o
+            break
+    if before is None:
+        return None
+    if after is None:
+        last = deq[-1]
+        dt = t - last["t"]
+        r, p, y = rot_to_vec(quat_to_R(last["quat"]))
+        Rg = rpy_to_R(r, p, y)
+        pos = last["pos"] + Rg @ last["vel_local"] * dt
+        r, p, y = r + last["rate"][0] * dt, p + last["rate"][1] * dt, y + last["rate"][2] * dt
+        after = dict(t=last["t"], pos=pos, quat=R_to_quat_wxyz(rpy_to_R(r, p, y)))  # header stamp stays default -> d_time_after
+    A, B = odom_to_affine(before), odom_to_affine(after)
+    between = (np.linalg.inv(A.astype(np.float64)) @ B.astype(np.float64)).astype(F32)
+    interp = interpolate_tf_with_time(between, t - before["t"], after["t"] - before["t"])
+    return (A @ interp).astype(F32)
+
+
+def normalize_covariance(c):  # pcm_matching.hpp:247-273
+    c = c.copy()
+    m = min(c[0, 0], c[1, 1], c[2, 2])
+    if m <= 1e-9:
+        c *= 1e9
+        m = min(c[0, 0], c[1, 1], c[2, 2])
+        if m < 1e-9:
+            m = 1e-9
+    return np.minimum(c / m, 5.0)
+
+
+def shape_pcm_covariance(R_ego, local_cov, fitness):
+    """PublishPcmOdom (pcm_matching.cpp:1082-1098): 6x6 row-major pose covariance"""
+    std = max(fitness, 0.25)
+    tc = R_ego @ local_cov[:3, :3] @ R_ego.T
+    rc = local_cov[3:, 3:]
+    ang = std * np.pi / 180.0
+    return normalize_covariance(tc) * std * std, normalize_covariance(rc) * ang * ang
+
+
+def gnss_time_compensation(meas, deq_state):
+    """ekf_localization.cpp:323-394; meas = dict(t, pos, quat); deq_state = list of EgoState arrays (26)"""
+    if not deq_state:
+        return None
+    cur = deq_state[-1]
+    if deq_state[0][0] > meas["t"]:
+        return None
+    closest = None
+    for s in deq_state:
+        if s[0] > meas["t"]:
+            closest = s
+            break
+        closest = s
+    gap = cur[0] - meas["t"]
+    if gap <= 0.0:
+        return dict(meas)
+    d = np.zeros(6)
+    if abs(cur[0] - closest[0]) > 1e-5:
+        ratio = gap / (cur[0] - closest[0])
+        d[:3] = (cur[1:4] - closest[1:4]) * ratio
+        d[3:] = [angle_diff(closest[4 + i], cur[4 + i]) * ratio for i in range(3)]
+    dq = R_to_quat_wxyz(rpy_to_R(d[3], d[4], d[5]))
+    w1, x1, y1, z1 = meas["quat"]
+    w2, x2, y2, z2 = dq
+    q = np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
+                  w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2])
+    return dict(t=cur[0], pos=meas["pos"] + d[:3], quat=q / np.linalg.norm(q))
+
+
+# ------------------------------------------------------------------------------------------------ arms
+class OracleArm:
+    name = "oracle"
+
+    def __init__(self, raw_map, ekf_cfg_kwargs):
+        from elimaloc_b200 import _capi
+        self.map = O.VoxelHashMap(1.0, 30)
+        self.map.AddPoints(raw_map)
+        self.map.CalVoxelCovAll()
+        self.reg = O.Registration()
+        self.ekf = O.EkfAlgorithm(pekf.make_ekf_config(**ekf_cfg_kwargs), _capi.EkfState)
+        self.cfg = O.make_config(icp_method=O.AVGICP, max_iteration=10, max_thread=8, max_fitness_score=2.0)
+
+    def stored(self):
+        return self.map.export()["pxyz"]
+
+    def deskew(self, xyz, rel, tab):
+        return O.deskew_points(tab, xyz, rel)
+
+    def register(self, scan, T0):
+        r = self.reg.RunRegister(scan, self.map, T0, self.cfg)
+        return r["pose"], r["is_success"], r["fitness_score"], r["local_cov"]
+
+    def ekf_pose(self):
+        return np.concatenate([np.array(self.ekf.s.pos[:]), np.array(self.ekf.s.rot[:])])
+
+
+class GpuArm:
+    name = "gpu"
+
+    def __init__(self, raw_map, ekf_cfg_kwargs, device=0):
+        import elimaloc_b200 as E
+        self.map = E.VoxelHashMap(1.0, 30, device=device)
+        self.map.AddPoints(raw_map)
+        self.map.CalVoxelCovAll()
+        self.reg = E.Registration(device=device)
+        self.ekf = E.EkfAlgorithm(pekf.make_ekf_config(**ekf_cfg_kwargs), device=device)
+        self.cfg = E.RegistrationConfig(icp_method=E.AVGICP, max_iteration=10, max_fitness_score=2.0)
+
+    def stored(self):
+        return self.map.Pointcloud()
+
+    def deskew(self, xyz, rel, tab):
+        return self.reg.DeskewPoints(xyz, rel, tab)
+
+    def register(self, scan, T0):
+        return self.reg.RunRegister(scan, self.map, T0, self.cfg)
+
+    def ekf_pose(self):
+        st = self.ekf.state()
+        return np.concatenate([np.array(st.pos[:]), np.array(st.rot[:])])
+
+
+# ------------------------------------------------------------------------------------------------ world + loop
+class World:
+    """constant-twist arc through the map; IMU in the body frame; raw scans with per-point motion distortion"""
+
+    def __init__(self, box, n_points, seed=7, radius=8.0, omega=0.25, t0=100.0, height=1.6):
+        self.c = np.array([box / 2 - 4.0, box / 2 - 6.0, height])  # sensor `height` above the ground plane of Map-S
+        self.r, self.w, self.t0, self.n = radius, omega, t0, n_points
+        self.rng = np.random.default_rng(seed)
+
+    def pose(self, t):
+        a = self.w * (t - self.t0)
+        T = np.eye(4)
+        T[:3, :3] = synth.exp_so3([0, 0, a])
+        T[:3, 3] = self.c + self.r * np.array([np.sin(a), 1 - np.cos(a), 0.0])
+        return T
+
+    def imu(self, t):
+        v = self.r * self.w
+        gyro = np.array([0.0, 0.0, self.w]) + self.rng.normal(0, 5e-4, 3)
+        acc = np.array([0.0, v * self.w, 9.81]) + self.rng.normal(0, 5e-3, 3)
+        return gyro, acc
+
+    def scan(self, stored, t_end, span=0.1):
+        Te = self.pose(t_end)
+        near = stored[np.linalg.norm(stored - Te[:3, 3].astype(F32), axis=1) < 14.0]
+        idx = self.rng.integers(0, len(near), self.n)
+        tt = np.sort(self.rng.random(self.n)) * span
+        pts = near[idx].astype(np.float64) + self.rng.normal(0, 0.01, (self.n, 3))
+        a = self.w * (t_end - span + tt - self.t0)
+        ca, sa = np.cos(a), np.sin(a)
+        pos = self.c[None, :] + self.r * np.stack([sa, 1 - ca, np.zeros_like(a)], axis=1)
+        d = pts - pos
+        local = np.stack([ca * d[:, 0] + sa * d[:, 1], -sa * d[:, 0] + ca * d[:, 1], d[:, 2]], axis=1)  # R(t)^T (p - pos(t))
+        return local.astype(F32), tt.astype(F32)
+
+
+def run(arm, world, n_scans, imu_dt=0.01, latency=0.03):
+    """returns dict of per-scan arrays: icp pose, EKF pose (pos + quaternion) after the update, success flag, fitness"""
+    stored = arm.stored()
+    t0 = world.t0
+    T0 = world.pose(t0)
+    arm.ekf.RunGnssUpdate(pekf.make_measurement(t0, T0[:3, 3], R_to_quat_wxyz(T0[:3, :3]), np.eye(3) * 1e-9, np.eye(3) * 1e-9,
+                                                source=pekf.PCM_INIT))  # CallbackPcmInitOdom (ekf_localization.cpp:181-210)
+    deq_odom, deq_state, imu_log = [], [], []
+    out = dict(icp=[], ego=[], ok=[], fit=[], t=[])
+    k_imu = 0
+    pending = None
+
+    def step_imu(until):
+        nonlocal k_imu
+        while t0 + k_imu * imu_dt <= until + 1e-9:
+            t = t0 + k_imu * imu_dt
+            g, a = world.imu(t)
+            imu_log.append((t, g))
+            arm.ekf.RunPredictionImu(t, g, a)
+            ego = arm.ekf.GetCurrentState()                       # PublishInThread (ekf_localization.cpp:400-...)
+            deq_state.append(ego.copy())
+            R = rpy_to_R(ego[4], ego[5], ego[6])
+            deq_odom.append(dict(t=ego[0], pos=ego[1:4].copy(), quat=R_to_quat_wxyz(R), vel_local=ego[10:13].copy(), rate=ego[7:10].copy()))
+            k_imu += 1
+
+    for s in range(n_scans):
+        t_end = t0 + 0.1 * (s + 1)
+        t_cur = t_end - 0.1
+        step_imu(t_end + latency)                                  # the result is applied `latency` after the scan end
+        xyz, rel = world.scan(stored, t_end)
+        st = np.array([x[0] for x in imu_log])
+        gy = np.array([x[1] for x in imu_log])
+        sel = st >= t_cur - 0.05
+        # start / end odometry of the scan span (OdomDeskewInfo picks the first odom at/after each stamp)
+        od_s = next(o for o in deq_odom if o["t"] >= t_cur - 1e-9)
+        od_e = next((o for o in deq_odom if o["t"] >= t_end - 1e-9), deq_odom[-1])
+        ps = np.concatenate([od_s["pos"], rot_to_vec(quat_to_R(od_s["quat"]))])
+        pe = np.concatenate([od_e["pos"], rot_to_vec(quat_to_R(od_e["quat"]))])
+        tab = O.deskew_tables(st[sel], gy[sel], t_cur, t_end, ps, od_s["t"], pe, od_e["t"])
+        und = arm.deskew(xyz, rel, tab)
+        sync = get_interpolated_pose(deq_odom, t_end)
+        T_init = sync.astype(np.float64)                           # tf_ego_to_lidar = identity (pcm_matching.cpp:266)
+        pose, ok, fit, cov = arm.register(und, T_init)
+        out["icp"].append(np.array(pose)); out["ok"].append(bool(ok)); out["fit"].append(float(fit)); out["t"].append(t_end)
+        if ok:                                                     # pcm_matching.cpp:289-299
+            pc, rc = shape_pcm_covariance(pose[:3, :3], np.array(cov), fit)
+            meas = gnss_time_compensation(dict(t=t_end, pos=pose[:3, 3].copy(), quat=R_to_quat_wxyz(pose[:3, :3])), deq_state)
+            if meas is not None:
+                arm.ekf.RunGnssUpdate(pekf.make_measurement(meas["t"], meas["pos"], meas["quat"], pc, rc, source=pekf.PCM))
+        out["ego"].append(arm.ekf_pose())                          # raw filter pose (pos, quaternion) after the update
+    return {k: np.array(v) for k, v in out.items()}
