@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--iters", type=int, default=ITERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=2, help="ICP iterations per CPU-baseline sample")
+    ap.add_argument("--fused", action="store_true", help="P2P/GICP: one fused search+accumulate+solve kernel per iteration")
     ap.add_argument("--binning", action="store_true", help="search the scan in spatially binned order")
     ap.add_argument("--exhaustive", action="store_true",
                     help="visit all 27 voxels like the reference instead of the exact-pruning search")
@@ -237,6 +238,7 @@ def main():
     reg = E.Registration(device=local_rank, stream=stream.cuda_stream)
     reg.set_exhaustive(args.exhaustive)
     reg.set_binning(args.binning)
+    reg.set_fused(args.fused)
     if world > 1:
         ids = [E.Registration.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

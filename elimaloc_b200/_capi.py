@@ -93,6 +93,7 @@ SIGNATURES = {
     "elm_registration_profile": (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_int64)]),
     "elm_registration_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "elm_registration_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_set_binning": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_set_exhaustive": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_deskew_points": (C.c_int, [C.c_void_p, _fp, _fp, C.c_size_t, C.POINTER(DeskewTables), _fp]),

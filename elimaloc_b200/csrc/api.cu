@@ -156,6 +156,8 @@ struct elm_registration {
     uint32_t* d_bin = nullptr;
     uint32_t* d_hist = nullptr;
     size_t sort_cap = 0;
+    int fuse = 0;             // 1: P2P / GICP linearise + reduce + solve inside the search kernel (measured slower: spills)
+    bool keep_match = false;  // also write match[] in the fused mode (off: nobody reads it)
     int binning = 0;          // 1 = search the scan in spatially binned order (measured: no gain on B200)
     bool use_sorted = false;  // the current enqueue searches d_sorted / d_orig
     unsigned int* d_ticket = nullptr;
@@ -305,7 +307,10 @@ elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg,
 int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm, bool solve) {
     const int sgrid = elm::icp_search_grid(prm, r->num_sms);
     const int agrid = elm::icp_accumulate_grid(prm, r->num_sms);
-    int rc = ensure_partials(r, agrid);
+    // P2P / GICP: search, linearisation, reduction and solve are ONE kernel (unless the search runs on the binned copy,
+    // whose order differs from the caller's: then the accumulation stays a separate launch in the caller's order)
+    const bool fuse = r->fuse && prm.method <= ELM_GICP && !r->use_sorted;
+    int rc = ensure_partials(r, fuse ? sgrid : agrid);
     if (rc) return rc;
     rc = ensure_match(r, prm.n);
     if (rc) return rc;
@@ -317,15 +322,18 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
         }
         ELM_CUDA(cudaEventRecord(r->ev[r->ev_used], r->stream));
     }
+    const int solve_here = (solve && !r->comm) ? 1 : 0;
     if (prm.method != ELM_AVGICP) {
         ELM_CUDA(elm::launch_icp_search(map->view(), r->use_sorted ? r->d_sorted : d_scan, r->use_sorted ? r->d_orig : nullptr, prm, r->d_state,
-                                        r->d_match, sgrid, r->prune, r->stream));
+                                        (fuse && !r->keep_match) ? nullptr : r->d_match, sgrid, r->prune, fuse ? 1 : 0, r->d_partials, r->d_ticket,
+                                        solve_here, r->stream));
         r->launches += 1;
     }
     if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
-    const int solve_here = (solve && !r->comm) ? 1 : 0;
-    ELM_CUDA(elm::launch_icp_accumulate(map->view(), d_scan, r->d_match, prm, r->d_state, r->d_partials, r->d_ticket, solve_here, agrid, r->stream));
-    r->launches += 1;
+    if (!fuse) {
+        ELM_CUDA(elm::launch_icp_accumulate(map->view(), d_scan, r->d_match, prm, r->d_state, r->d_partials, r->d_ticket, solve_here, agrid, r->stream));
+        r->launches += 1;
+    }
     if (r->profiling) {
         ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 2], r->stream));
         r->ev_used += 3;
@@ -594,7 +602,8 @@ int elm_correspondences(elm_registration* reg, const elm_map* map, const float* 
     if (rc) return rc;
     if (method != ELM_AVGICP)
         ELM_CUDA(elm::launch_icp_search(map->view(), reg->use_sorted ? reg->d_sorted : reg->d_scan, reg->use_sorted ? reg->d_orig : nullptr, prm,
-                                        reg->d_state, reg->d_match, elm::icp_search_grid(prm, reg->num_sms), reg->prune, reg->stream));
+                                        reg->d_state, reg->d_match, elm::icp_search_grid(prm, reg->num_sms), reg->prune, 0, nullptr, nullptr, 0,
+                                        reg->stream));
     ELM_CUDA(elm::launch_icp_export(map->view(), reg->d_scan, reg->d_match, static_cast<int>(n), reg->d_state, method,
                                     max_search_dist * max_search_dist, reg->d_count, reg->d_target, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(count, reg->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
@@ -644,6 +653,12 @@ int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, 
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
     *map_points_visited = h[0];
     *queries = h[1];
+    return ELM_OK;
+}
+
+int elm_registration_set_fused(elm_registration* reg, int enable) {
+    if (!reg) return fail(ELM_ERR_INVALID, "null registration");
+    reg->fuse = enable ? 1 : 0;
     return ELM_OK;
 }
 

@@ -109,6 +109,13 @@ struct Best {
 // Stream `n` consecutive stored points and fold them into `b`; ord0/idx0 = visit order / index of the first one.
 __device__ __forceinline__ void visit_points(const float4* __restrict__ p, uint32_t n, uint32_t ord0, uint32_t idx0, double px, double py,
                                              double pz, Best& b) {
+#ifdef ELM_PREFETCH_RUNS
+    {   // pull every 128-B line of the run towards L1 before streaming it
+        const char* pb = reinterpret_cast<const char*>(p);
+        const char* pe = pb + static_cast<size_t>(n) * 16;
+        for (const char* a = pb + 64; a < pe; a += 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    }
+#endif
 #pragma unroll 4
     for (uint32_t o = 0; o < n; ++o) {
         const float4 q = __ldg(p + o);
@@ -188,179 +195,6 @@ __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, do
 }
 
 }  // namespace
-
-// ======================================================================================================================
-// search: P2P / GICP
-// ======================================================================================================================
-// Block = 256 threads = one tile of 256 scan points, pulled into shared memory by the TMA bulk-copy engine (packed xyz,
-// 12 B/point; double-buffered when a block owns several tiles).  TransformPoints is fused (reg.hpp:136-148).
-//
-// COOP = true (default, exact pruning), three phases per tile:
-//   A  thread per QUERY : transform, probe + stream the centre column, derive which other voxels cannot be excluded
-//                         and append one work item per such voxel to a block-wide list in shared memory;
-//   B  thread per ITEM  : probe that voxel and stream its points for the item's query (balanced: every lane busy,
-//                         instead of each query thread walking its own 0..24 voxels while its warp-mates idle);
-//   C  merge            : atomicMin on the fp64 distance bits, then on (visit order, index) among the exact minima,
-//                         which reproduces the reference's first-in-visit-order tie-break (vhm.cpp:45).
-// COOP = false: every thread walks all 9 columns of its own query — the reference's exhaustive visit.
-constexpr int kNoItem = 0xffff;
-constexpr int kItemCap = 1024;  // work items per tile kept in shared memory (typical: ~600); overflow stays with its owner
-
-template <bool COOP>
-__global__ void __launch_bounds__(kIcpThreads, 4)
-icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, const IcpState* __restrict__ st,
-                         int* __restrict__ match) {
-    __shared__ __align__(16) float s_tile[2][kIcpThreads * 3];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ double s_T[12];
-    __shared__ double s_px[COOP ? kIcpThreads : 1], s_py[COOP ? kIcpThreads : 1], s_pz[COOP ? kIcpThreads : 1];
-    __shared__ int s_kx[COOP ? kIcpThreads : 1], s_ky[COOP ? kIcpThreads : 1], s_kz[COOP ? kIcpThreads : 1];
-    __shared__ unsigned long long s_best[COOP ? kIcpThreads : 1], s_win[COOP ? kIcpThreads : 1];
-    __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1], s_item_win[COOP ? kItemCap : 1];
-    __shared__ uint16_t s_items[COOP ? kItemCap : 1];
-    __shared__ int s_nitems;
-
-    if (st->done) return;  // loop already left (termination / overlap failure)
-    const int tid = threadIdx.x;
-    if (tid < 12) s_T[tid] = st->T[tid];
-
-    constexpr int tile_pts = kIcpThreads;
-    const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
-    const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-
-    auto tile_count = [&](int t) { return min(tile_pts, prm.n - t * tile_pts); };
-    auto tile_tma_ok = [&](int t) { return base_aligned && ((tile_count(t) * 12) & 15) == 0; };
-    auto issue = [&](int t, int buf) {
-        const uint32_t bytes = tile_count(t) * 12;
-        mbar_expect_tx(&s_bar[buf], bytes);
-        tma_load_1d(s_tile[buf], scan + static_cast<size_t>(t) * tile_pts * 3, bytes, &s_bar[buf]);
-    };
-    const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
-
-    uint32_t visited = 0, searched = 0;
-    int tile = blockIdx.x, buf = 0;
-    uint32_t phase[2] = {0, 0};
-    if (tile < ntiles && tid == 0 && tile_tma_ok(tile)) issue(tile, 0);
-    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const int next = tile + gridDim.x;
-        if (tid == 0 && next < ntiles && tile_tma_ok(next)) issue(next, buf ^ 1);  // prefetch the next tile
-        if (tid == 0) s_nitems = 0;
-        if (tile_tma_ok(tile)) {
-            mbar_wait(&s_bar[buf], phase[buf]);
-            phase[buf] ^= 1;
-        } else {  // ragged last tile / unaligned base: plain cooperative copy
-            const int nf = tile_count(tile) * 3;
-            for (int i = tid; i < nf; i += kIcpThreads) s_tile[buf][i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
-        }
-        __syncthreads();
-        const int cnt = tile_count(tile);
-        const bool mine = tid < cnt;
-        // ---- phase A: one thread per query
-        Best b;
-        double px = 0, py = 0, pz = 0;
-        int kx = 0, ky = 0, kz = 0;
-        uint32_t own_need = 0;
-        if (mine) {
-            const float* sp = &s_tile[buf][tid * 3];
-            const double sx = sp[0], sy = sp[1], sz = sp[2];
-            px = row_apply_exact(s_T, 0, sx, sy, sz);
-            py = row_apply_exact(s_T, 1, sx, sy, sz);
-            pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            float fx, fy, fz;
-            kx = voxel_floor(px, map.voxel_size, &fx); ky = voxel_floor(py, map.voxel_size, &fy); kz = voxel_floor(pz, map.voxel_size, &fz);
-            const bool interior = neighbourhood_interior(kx, ky, kz);
-            ++searched;
-            if (COOP) {
-                visited += visit_column(map, kx, ky, kz, interior, 12u, px, py, pz, b);
-                own_need = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up);
-                s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
-                s_kx[tid] = kx; s_ky[tid] = ky; s_kz[tid] = kz;
-                s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
-                s_win[tid] = ~0ull;
-                const int k = __popc(own_need);
-                if (k) {
-                    const int pos = atomicAdd(&s_nitems, k);
-                    if (pos + k <= kItemCap) {  // hand the voxels to the block; otherwise they stay with this thread
-                        int w = pos;
-                        for (uint32_t m = own_need; m; m &= m - 1) s_items[w++] = static_cast<uint16_t>((tid << 5) | (__ffs(m) - 1));
-                        own_need = 0;
-                    } else {
-                        for (int w = pos; w < kItemCap; ++w) s_items[w] = kNoItem;  // the tail of the list this claim straddles
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < 9; ++c)
-                    visited += visit_column(map, kx + c / 3 - 1, ky + c % 3 - 1, kz, interior, static_cast<uint32_t>(3 * c), px, py, pz, b);
-                const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
-                match[orig ? orig[gi] : gi] = (b.ord == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
-            }
-        }
-        if (COOP) {
-            __syncthreads();
-            // ---- phase B: one thread per (query, voxel) item
-            const int nitems = min(s_nitems, kItemCap);  // (items beyond the cap were never written: their owners kept them)
-            for (int j = tid; j < nitems; j += kIcpThreads) {
-                const int it = s_items[j], q = it >> 5, L = it & 31;
-                if (it == kNoItem) continue;
-                Best ib;
-                visited += visit_voxel(map, s_kx[q], s_ky[q], s_kz[q], L, s_px[q], s_py[q], s_pz[q], ib);
-                const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
-                s_item_d2[j] = bits;
-                s_item_win[j] = (static_cast<unsigned long long>(ib.ord) << 32) | ib.idx;
-                if (ib.ord != 0xffffffffu) atomicMin(&s_best[q], bits);
-            }
-            if (mine) {
-                for (uint32_t m = own_need; m; m &= m - 1) visited += visit_voxel(map, kx, ky, kz, __ffs(m) - 1, px, py, pz, b);
-                if (b.ord != 0xffffffffu) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(b.d2)));
-            }
-            __syncthreads();
-            // ---- phase C: among the exact minima the smallest visit order wins
-            for (int j = tid; j < nitems; j += kIcpThreads) {
-                const int q = s_items[j] >> 5;
-                if (s_items[j] == kNoItem) continue;
-                if (s_item_d2[j] == s_best[q] && (s_item_win[j] >> 32) != 0xffffffffull) atomicMin(&s_win[q], s_item_win[j]);
-            }
-            if (mine && b.ord != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
-                atomicMin(&s_win[tid], (static_cast<unsigned long long>(b.ord) << 32) | b.idx);
-            __syncthreads();
-            if (mine) {
-                const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
-                match[orig ? orig[gi] : gi] = (s_win[tid] == ~0ull) ? -1 : static_cast<int>(s_win[tid] & 0xffffffffu);
-            }
-        }
-        if (next < ntiles) __syncthreads();  // everyone is done with the tile's shared state before it is refilled (block-uniform)
-    }
-    if (prm.stats) {
-        // warp-aggregate, one atomic pair per warp
-        for (int o = 16; o > 0; o >>= 1) { visited += __shfl_xor_sync(kFull, visited, o); searched += __shfl_xor_sync(kFull, searched, o); }
-        if ((tid & 31) == 0 && searched) {
-            atomicAdd(prm.stats, static_cast<unsigned long long>(visited));
-            atomicAdd(prm.stats + 1, static_cast<unsigned long long>(searched));
-        }
-    }
-}
-
-// ======================================================================================================================
-// search: VGICP
-// ======================================================================================================================
-__global__ void __launch_bounds__(kIcpThreads, 4)
-icp_search_means_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, const IcpState* __restrict__ st,
-                        int* __restrict__ match) {
-    __shared__ double s_T[12];
-    if (st->done) return;
-    const int tid = threadIdx.x;
-    if (tid < 12) s_T[tid] = st->T[tid];
-    __syncthreads();
-    for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
-        const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
-        const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-        const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
-        match[orig ? orig[i] : i] = nearest_mean_27(map, px, py, pz, kx, ky, kz);
-    }
-}
 
 // ======================================================================================================================
 // accumulation + reduction (+ solve)
@@ -671,7 +505,325 @@ __device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc,
     for (int i = 0; i < 9; ++i) st->Rinv[i] = Ri[i];
 }
 
+// One P2P / GICP correspondence -> accumulators (reg.cpp:28-51 / 85-132).  m = index of the matched map point or -1
+// (then the reference's default-constructed neighbour at the origin applies, Q2); p = T * s exactly as the search saw it.
+template <int METHOD>
+__device__ __forceinline__ void linearize_point_pair(const MapView& map, int m, double sx, double sy, double sz, double px, double py, double pz,
+                                                     const double* s_Tinv, const double* s_Rinv, double th, double max_dist2, double* acc) {
+    double tx = 0.0, ty = 0.0, tz = 0.0;  // default-constructed neighbour at the origin (Q2, vhm.cpp:37)
+    if (m >= 0) { const float4 t = __ldg(map.pts + m); tx = t.x; ty = t.y; tz = t.z; }
+    if (!(sq3_exact(tx - px, ty - py, tz - pz) < max_dist2)) return;  // vhm.cpp:66
+    if (METHOD == 0) {
+        const double lx = s_Tinv[0] * tx + s_Tinv[1] * ty + s_Tinv[2] * tz + s_Tinv[3];
+        const double ly = s_Tinv[4] * tx + s_Tinv[5] * ty + s_Tinv[6] * tz + s_Tinv[7];
+        const double lz = s_Tinv[8] * tx + s_Tinv[9] * ty + s_Tinv[10] * tz + s_Tinv[11];
+        acc_p2p(acc, sx, sy, sz, lx - sx, ly - sy, lz - sz, th);
+    } else {
+        double mean[3] = {0.0, 0.0, 0.0}, C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, nrm[3] = {1.0, 0.0, 0.0};
+        if (m >= 0) {
+            const double2* r = reinterpret_cast<const double2*>(map.prec + static_cast<size_t>(m) * 16);
+            const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5),
+                          r6 = __ldg(r + 6), r7 = __ldg(r + 7);
+            mean[0] = r0.x; mean[1] = r0.y; mean[2] = r1.x;
+            C[0] = r1.y; C[1] = r2.x; C[2] = r2.y; C[3] = r3.x; C[4] = r3.y; C[5] = r4.x; C[6] = r4.y; C[7] = r5.x; C[8] = r5.y;
+            nrm[0] = r6.x; nrm[1] = r6.y; nrm[2] = r7.x;
+        }
+        // residual to the neighbourhood MEAN, not the matched point (Q4, reg.cpp:97-101)
+        const double lx = s_Tinv[0] * mean[0] + s_Tinv[1] * mean[1] + s_Tinv[2] * mean[2] + s_Tinv[3];
+        const double ly = s_Tinv[4] * mean[0] + s_Tinv[5] * mean[1] + s_Tinv[6] * mean[2] + s_Tinv[7];
+        const double lz = s_Tinv[8] * mean[0] + s_Tinv[9] * mean[1] + s_Tinv[10] * mean[2] + s_Tinv[11];
+        const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
+        double M[9];
+        mahalanobis_local(s_Rinv, C, M);
+        const double r2 = rx * rx + ry * ry + rz * rz;
+        const double den = th + r2;
+        const double w = (th * th) / (den * den) * 0.8 + 0.2;  // reg.cpp:121
+        acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
+        // point-to-plane fitness term (reg.cpp:94-95,128-131)
+        double nx = s_Rinv[0] * nrm[0] + s_Rinv[1] * nrm[1] + s_Rinv[2] * nrm[2];
+        double ny = s_Rinv[3] * nrm[0] + s_Rinv[4] * nrm[1] + s_Rinv[5] * nrm[2];
+        double nz = s_Rinv[6] * nrm[0] + s_Rinv[7] * nrm[1] + s_Rinv[8] * nrm[2];
+        const double nn = nx * nx + ny * ny + nz * nz;
+        if (nn > 0.0) { const double il = 1.0 / sqrt(nn); nx *= il; ny *= il; nz *= il; }
+        acc[27] += fabs(rx * nx + ry * ny + rz * nz);
+        acc[28] += 1.0;
+    }
+}
+
+// Block tree over per-lane accumulators: warp shuffles, then the 8 warps in fixed order; thread k < 29 ADDS the block's
+// sum of canonical slot k to s_sum[k].  Every thread of the block must call it.
+template <int NACC, bool IS_P2P>
+__device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc], double* s_sum) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        acc[k] = v;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 29; ++k) s_red[warp][k] = IS_P2P ? expand_p2p(acc, k) : acc[k < NACC ? k : 0];
+    }
+    __syncthreads();
+    if (tid < 29) {
+        double v = 0.0;
+        for (int w = 0; w < kIcpWarps; ++w) v += s_red[w][tid];
+        s_sum[tid] += v;
+    }
+    __syncthreads();
+}
+
+// Publish this block's sums and let the LAST block to arrive reduce all partials in a fixed order (bit-reproducible
+// whichever block is last) into st->acc and, when `solve_here`, run the solve/update step.
+__device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)[kAcc], double* s_acc, bool* s_last, SolveScratch* s_solve,
+                                            const double* s_T, IcpState* st, const IcpParams& prm, double* __restrict__ partials,
+                                            unsigned int* __restrict__ ticket, int solve_here) {
+    const int tid = threadIdx.x;
+    if (tid < kAcc) {
+        double v = 0.0;
+        if (tid < 29) v = s_sum[tid];
+        else if (tid == kIdxNtotal) v = (blockIdx.x == 0) ? static_cast<double>(prm.n) : 0.0;
+        partials[blockIdx.x * kAcc + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        *s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    {
+        const int k = tid & 31, g = tid >> 5;
+        double v = 0.0;
+        const int nb = static_cast<int>(gridDim.x);
+        int b = g;
+        for (; b + 7 * kIcpWarps < nb; b += 8 * kIcpWarps) {  // 8 independent loads in flight, summed in index order
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(partials + (b + u * kIcpWarps) * kAcc + k);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += t[u];
+        }
+        for (; b < nb; b += kIcpWarps) v += __ldcg(partials + b * kAcc + k);
+        s_red[g][k] = v;
+    }
+    __syncthreads();
+    if (tid < kAcc) {
+        double t = 0.0;
+        for (int i = 0; i < kIcpWarps; ++i) t += s_red[i][tid];
+        st->acc[tid] = t;
+        s_acc[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *ticket = 0;
+        if (solve_here) solve_step(st, prm, s_solve, s_acc, s_T);
+    }
+}
+
 }  // namespace
+
+// ======================================================================================================================
+// search: P2P / GICP
+// ======================================================================================================================
+// Block = 256 threads = one tile of 256 scan points, pulled into shared memory by the TMA bulk-copy engine (packed xyz,
+// 12 B/point; double-buffered when a block owns several tiles).  TransformPoints is fused (reg.hpp:136-148).
+//
+// COOP = true (default, exact pruning), three phases per tile:
+//   A  thread per QUERY : transform, probe + stream the centre column, derive which other voxels cannot be excluded
+//                         and append one work item per such voxel to a block-wide list in shared memory;
+//   B  thread per ITEM  : probe that voxel and stream its points for the item's query (balanced: every lane busy,
+//                         instead of each query thread walking its own 0..24 voxels while its warp-mates idle);
+//   C  merge            : atomicMin on the fp64 distance bits, then on (visit order, index) among the exact minima,
+//                         which reproduces the reference's first-in-visit-order tie-break (vhm.cpp:45).
+// COOP = false: every thread walks all 9 columns of its own query — the reference's exhaustive visit.
+constexpr int kNoItem = 0xffff;
+constexpr int kItemCap = 1024;  // work items per tile kept in shared memory (typical: ~600); overflow stays with its owner
+
+// FUSE = 0 (P2P) / 1 (GICP): the tile's threads go straight on to linearise their correspondence (AlignCloudsLocal /
+// AlignCloudsLocalPointCov accumulation), the block tree-reduces, and the last block of the grid reduces all partials and
+// solves — ONE launch per ICP iteration, the matched point still hot in L1/L2.  FUSE = -1: search only (match[] out).
+template <bool COOP, int FUSE>
+__global__ void __launch_bounds__(kIcpThreads, FUSE == 1 ? 3 : 4)
+icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, IcpState* __restrict__ st,
+                         int* __restrict__ match, double* __restrict__ partials, unsigned int* __restrict__ ticket, int solve_here) {
+    constexpr bool kFuse = FUSE >= 0;
+    constexpr int NACC = AccSize<FUSE == 0 ? 0 : 1>::value;
+    __shared__ double s_Tinv[kFuse ? 12 : 1], s_Rinv[kFuse ? 9 : 1];
+    __shared__ double s_red[kFuse ? kIcpWarps : 1][kAcc], s_sum[kAcc], s_acc[kAcc];
+    __shared__ SolveScratch s_solve;
+    __shared__ bool s_last;
+    __shared__ __align__(16) float s_tile[2][kIcpThreads * 3];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ double s_T[12];
+    __shared__ double s_px[COOP ? kIcpThreads : 1], s_py[COOP ? kIcpThreads : 1], s_pz[COOP ? kIcpThreads : 1];
+    __shared__ int s_kx[COOP ? kIcpThreads : 1], s_ky[COOP ? kIcpThreads : 1], s_kz[COOP ? kIcpThreads : 1];
+    __shared__ unsigned long long s_best[COOP ? kIcpThreads : 1], s_win[COOP ? kIcpThreads : 1];
+    __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1], s_item_win[COOP ? kItemCap : 1];
+    __shared__ uint16_t s_items[COOP ? kItemCap : 1];
+    __shared__ int s_nitems;
+
+    if (st->done) return;  // loop already left (termination / overlap failure)
+    const int tid = threadIdx.x;
+    if (tid < 12) s_T[tid] = st->T[tid];
+    if (kFuse) {
+        if (tid < 12) s_Tinv[tid] = st->Tinv[tid];
+        if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+        if (tid < kAcc) s_sum[tid] = 0.0;
+    }
+
+    constexpr int tile_pts = kIcpThreads;
+    const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+
+    auto tile_count = [&](int t) { return min(tile_pts, prm.n - t * tile_pts); };
+    auto tile_tma_ok = [&](int t) { return base_aligned && ((tile_count(t) * 12) & 15) == 0; };
+    auto issue = [&](int t, int buf) {
+        const uint32_t bytes = tile_count(t) * 12;
+        mbar_expect_tx(&s_bar[buf], bytes);
+        tma_load_1d(s_tile[buf], scan + static_cast<size_t>(t) * tile_pts * 3, bytes, &s_bar[buf]);
+    };
+    const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
+
+    uint32_t visited = 0, searched = 0;
+    int tile = blockIdx.x, buf = 0;
+    uint32_t phase[2] = {0, 0};
+    if (tile < ntiles && tid == 0 && tile_tma_ok(tile)) issue(tile, 0);
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles && tile_tma_ok(next)) issue(next, buf ^ 1);  // prefetch the next tile
+        if (tid == 0) s_nitems = 0;
+        if (tile_tma_ok(tile)) {
+            mbar_wait(&s_bar[buf], phase[buf]);
+            phase[buf] ^= 1;
+        } else {  // ragged last tile / unaligned base: plain cooperative copy
+            const int nf = tile_count(tile) * 3;
+            for (int i = tid; i < nf; i += kIcpThreads) s_tile[buf][i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
+        }
+        __syncthreads();
+        const int cnt = tile_count(tile);
+        const bool mine = tid < cnt;
+        // ---- phase A: one thread per query
+        Best b;
+        double px = 0, py = 0, pz = 0, sx = 0, sy = 0, sz = 0;
+        int kx = 0, ky = 0, kz = 0;
+        uint32_t own_need = 0;
+        int my_match = -1;
+        if (mine) {
+            const float* sp = &s_tile[buf][tid * 3];
+            sx = sp[0]; sy = sp[1]; sz = sp[2];
+            px = row_apply_exact(s_T, 0, sx, sy, sz);
+            py = row_apply_exact(s_T, 1, sx, sy, sz);
+            pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            float fx, fy, fz;
+            kx = voxel_floor(px, map.voxel_size, &fx); ky = voxel_floor(py, map.voxel_size, &fy); kz = voxel_floor(pz, map.voxel_size, &fz);
+            const bool interior = neighbourhood_interior(kx, ky, kz);
+            ++searched;
+            if (COOP) {
+                visited += visit_column(map, kx, ky, kz, interior, 12u, px, py, pz, b);
+                own_need = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up);
+                s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
+                s_kx[tid] = kx; s_ky[tid] = ky; s_kz[tid] = kz;
+                s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
+                s_win[tid] = ~0ull;
+                const int k = __popc(own_need);
+                if (k) {
+                    const int pos = atomicAdd(&s_nitems, k);
+                    if (pos + k <= kItemCap) {  // hand the voxels to the block; otherwise they stay with this thread
+                        int w = pos;
+                        for (uint32_t m = own_need; m; m &= m - 1) s_items[w++] = static_cast<uint16_t>((tid << 5) | (__ffs(m) - 1));
+                        own_need = 0;
+                    } else {
+                        for (int w = pos; w < kItemCap; ++w) s_items[w] = kNoItem;  // the tail of the list this claim straddles
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 9; ++c)
+                    visited += visit_column(map, kx + c / 3 - 1, ky + c % 3 - 1, kz, interior, static_cast<uint32_t>(3 * c), px, py, pz, b);
+                my_match = (b.ord == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
+            }
+        }
+        if (COOP) {
+            __syncthreads();
+            // ---- phase B: one thread per (query, voxel) item
+            const int nitems = min(s_nitems, kItemCap);  // (items beyond the cap were never written: their owners kept them)
+            for (int j = tid; j < nitems; j += kIcpThreads) {
+                const int it = s_items[j], q = it >> 5, L = it & 31;
+                if (it == kNoItem) continue;
+                Best ib;
+                visited += visit_voxel(map, s_kx[q], s_ky[q], s_kz[q], L, s_px[q], s_py[q], s_pz[q], ib);
+                const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
+                s_item_d2[j] = bits;
+                s_item_win[j] = (static_cast<unsigned long long>(ib.ord) << 32) | ib.idx;
+                if (ib.ord != 0xffffffffu) atomicMin(&s_best[q], bits);
+            }
+            if (mine) {
+                for (uint32_t m = own_need; m; m &= m - 1) visited += visit_voxel(map, kx, ky, kz, __ffs(m) - 1, px, py, pz, b);
+                if (b.ord != 0xffffffffu) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(b.d2)));
+            }
+            __syncthreads();
+            // ---- phase C: among the exact minima the smallest visit order wins
+            for (int j = tid; j < nitems; j += kIcpThreads) {
+                const int q = s_items[j] >> 5;
+                if (s_items[j] == kNoItem) continue;
+                if (s_item_d2[j] == s_best[q] && (s_item_win[j] >> 32) != 0xffffffffull) atomicMin(&s_win[q], s_item_win[j]);
+            }
+            if (mine && b.ord != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
+                atomicMin(&s_win[tid], (static_cast<unsigned long long>(b.ord) << 32) | b.idx);
+            __syncthreads();
+            if (mine) my_match = (s_win[tid] == ~0ull) ? -1 : static_cast<int>(s_win[tid] & 0xffffffffu);
+        }
+        if (mine && match) {
+            const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
+            match[orig ? orig[gi] : gi] = my_match;
+        }
+        if (kFuse) {  // linearise this tile's correspondences and fold them into the block's running sums
+            double acc[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+            if (mine) linearize_point_pair<FUSE == 1 ? 1 : 0>(map, my_match, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+            block_sum_into<NACC, FUSE == 0>(acc, s_red, s_sum);
+        } else if (next < ntiles) {
+            __syncthreads();  // everyone is done with the tile's shared state before it is refilled (block-uniform)
+        }
+    }
+    if (prm.stats) {
+        // warp-aggregate, one atomic pair per warp
+        for (int o = 16; o > 0; o >>= 1) { visited += __shfl_xor_sync(kFull, visited, o); searched += __shfl_xor_sync(kFull, searched, o); }
+        if ((tid & 31) == 0 && searched) {
+            atomicAdd(prm.stats, static_cast<unsigned long long>(visited));
+            atomicAdd(prm.stats + 1, static_cast<unsigned long long>(searched));
+        }
+    }
+    if (kFuse) finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, partials, ticket, solve_here);
+}
+
+// ======================================================================================================================
+// search: VGICP
+// ======================================================================================================================
+__global__ void __launch_bounds__(kIcpThreads, 4)
+icp_search_means_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, const IcpState* __restrict__ st,
+                        int* __restrict__ match) {
+    __shared__ double s_T[12];
+    if (st->done) return;
+    const int tid = threadIdx.x;
+    if (tid < 12) s_T[tid] = st->T[tid];
+    __syncthreads();
+    for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
+        const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
+        const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+        const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+        match[orig ? orig[i] : i] = nearest_mean_27(map, px, py, pz, kx, ky, kz);
+    }
+}
+
 
 // One thread per scan point (8 threads per point for AVGICP).  partials[gridDim.x][kAcc]; the last block to finish
 // sums them in a fixed order into st->acc and, when `solve_here`, runs the solve/update step.
@@ -685,7 +837,7 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
     __shared__ SolveScratch s_solve;
     __shared__ bool s_last;
     if (st->done) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
     if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
     __syncthreads();
@@ -748,96 +900,16 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
                 }
                 if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_voxel_pair(sx, sy, sz, m, mx, my, mz);  // vhm.cpp:129
             } else {
-                double tx = 0.0, ty = 0.0, tz = 0.0;  // default-constructed neighbour at the origin (Q2, vhm.cpp:37)
-                if (m >= 0) { const float4 t = __ldg(map.pts + m); tx = t.x; ty = t.y; tz = t.z; }
-                if (!(sq3_exact(tx - px, ty - py, tz - pz) < prm.max_dist2)) continue;  // vhm.cpp:66
-                if (METHOD == 0) {
-                    const double lx = s_Tinv[0] * tx + s_Tinv[1] * ty + s_Tinv[2] * tz + s_Tinv[3];
-                    const double ly = s_Tinv[4] * tx + s_Tinv[5] * ty + s_Tinv[6] * tz + s_Tinv[7];
-                    const double lz = s_Tinv[8] * tx + s_Tinv[9] * ty + s_Tinv[10] * tz + s_Tinv[11];
-                    acc_p2p(acc, sx, sy, sz, lx - sx, ly - sy, lz - sz, prm.th);
-                } else {
-                    double mean[3] = {0.0, 0.0, 0.0}, C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, nrm[3] = {1.0, 0.0, 0.0};
-                    if (m >= 0) {
-                        const double2* r = reinterpret_cast<const double2*>(map.prec + static_cast<size_t>(m) * 16);
-                        const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4),
-                                      r5 = __ldg(r + 5), r6 = __ldg(r + 6), r7 = __ldg(r + 7);
-                        mean[0] = r0.x; mean[1] = r0.y; mean[2] = r1.x;
-                        C[0] = r1.y; C[1] = r2.x; C[2] = r2.y; C[3] = r3.x; C[4] = r3.y; C[5] = r4.x; C[6] = r4.y; C[7] = r5.x; C[8] = r5.y;
-                        nrm[0] = r6.x; nrm[1] = r6.y; nrm[2] = r7.x;
-                    }
-                    // residual to the neighbourhood MEAN, not the matched point (Q4, reg.cpp:97-101)
-                    const double lx = s_Tinv[0] * mean[0] + s_Tinv[1] * mean[1] + s_Tinv[2] * mean[2] + s_Tinv[3];
-                    const double ly = s_Tinv[4] * mean[0] + s_Tinv[5] * mean[1] + s_Tinv[6] * mean[2] + s_Tinv[7];
-                    const double lz = s_Tinv[8] * mean[0] + s_Tinv[9] * mean[1] + s_Tinv[10] * mean[2] + s_Tinv[11];
-                    const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
-                    double M[9];
-                    mahalanobis_local(s_Rinv, C, M);
-                    const double r2 = rx * rx + ry * ry + rz * rz;
-                    const double den = prm.th + r2;
-                    const double w = (prm.th * prm.th) / (den * den) * 0.8 + 0.2;  // reg.cpp:121
-                    acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
-                    // point-to-plane fitness term (reg.cpp:94-95,128-131)
-                    double nx = s_Rinv[0] * nrm[0] + s_Rinv[1] * nrm[1] + s_Rinv[2] * nrm[2];
-                    double ny = s_Rinv[3] * nrm[0] + s_Rinv[4] * nrm[1] + s_Rinv[5] * nrm[2];
-                    double nz = s_Rinv[6] * nrm[0] + s_Rinv[7] * nrm[1] + s_Rinv[8] * nrm[2];
-                    const double nn = nx * nx + ny * ny + nz * nz;
-                    if (nn > 0.0) { const double il = 1.0 / sqrt(nn); nx *= il; ny *= il; nz *= il; }
-                    acc[27] += fabs(rx * nx + ry * ny + rz * nz);
-                    acc[28] += 1.0;
-                }
+                linearize_point_pair<METHOD == 1 ? 1 : 0>(map, m, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
             }
         }
     }
 
-    // block tree: warp shuffles, then the 8 warps in fixed order
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        acc[k] = v;
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 29; ++k) s_red[warp][k] = (METHOD == 0) ? expand_p2p(acc, k) : acc[k < NACC ? k : 0];
-    }
+    __shared__ double s_sum[kAcc], s_acc[kAcc];
+    if (tid < kAcc) s_sum[tid] = 0.0;
     __syncthreads();
-    if (tid < kAcc) {
-        double v = 0.0;
-        if (tid < 29) { for (int w = 0; w < kIcpWarps; ++w) v += s_red[w][tid]; }
-        else if (tid == kIdxNtotal) v = (blockIdx.x == 0) ? static_cast<double>(prm.n) : 0.0;
-        partials[blockIdx.x * kAcc + tid] = v;
-    }
-    // last block to arrive finishes the job (fixed-order sum => bit-reproducible whichever block is last)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    {
-        const int k = tid & 31, g = tid >> 5;
-        double v = 0.0;
-        for (int b = g; b < static_cast<int>(gridDim.x); b += kIcpWarps) v += __ldcg(partials + b * kAcc + k);
-        s_red[g][k] = v;
-    }
-    __syncthreads();
-    __shared__ double s_acc[kAcc];
-    if (tid < kAcc) {
-        double t = 0.0;
-        for (int i = 0; i < kIcpWarps; ++i) t += s_red[i][tid];
-        st->acc[tid] = t;
-        s_acc[tid] = t;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        *ticket = 0;
-        if (solve_here) solve_step(st, prm, &s_solve, s_acc, s_T);
-    }
+    block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);
+    finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, partials, ticket, solve_here);
 }
 
 // ======================================================================================================================
@@ -933,12 +1005,15 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
     return cudaGetLastError();
 }
 
-cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, const IcpState* st, int* match,
-                              int grid, int prune, cudaStream_t s) {
+// fuse: linearise + reduce (+ solve when solve_here) inside the search kernel (P2P / GICP only); then `match` may be NULL
+cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, int* match,
+                              int grid, int prune, int fuse, double* partials, unsigned int* ticket, int solve_here, cudaStream_t s) {
     if (prm.method <= 1) {
-if (prune) icp_search_points_kernel<true><<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match);
-        else icp_search_points_kernel<false><<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match);
-
+#define ELM_LAUNCH(C, F) icp_search_points_kernel<C, F><<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match, partials, ticket, solve_here)
+        if (!fuse) { if (prune) ELM_LAUNCH(true, -1); else ELM_LAUNCH(false, -1); }
+        else if (prm.method == 0) { if (prune) ELM_LAUNCH(true, 0); else ELM_LAUNCH(false, 0); }
+        else { if (prune) ELM_LAUNCH(true, 1); else ELM_LAUNCH(false, 1); }
+#undef ELM_LAUNCH
     } else if (prm.method == 2) {
         icp_search_means_kernel<<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match);
     }

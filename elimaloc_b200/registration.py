@@ -177,6 +177,10 @@ class Registration:
         check(lib().elm_registration_stats(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def set_fused(self, enable):
+        """P2P / GICP: one fused kernel per iteration (default) or search + accumulate as two launches."""
+        check(lib().elm_registration_set_fused(self._h, int(bool(enable))))
+
     def set_binning(self, enable):
         """Search the scan in spatially binned order (default) or in the caller's order; results are identical."""
         check(lib().elm_registration_set_binning(self._h, int(bool(enable))))

@@ -143,6 +143,11 @@ int elm_registration_profile(const elm_registration* reg, double* search_ms, dou
 int elm_registration_set_stats(elm_registration* reg, int enable);
 int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, uint64_t* queries);
 
+/* P2P / GICP kernel structure.  Default (0): a search kernel (match[] out) followed by an accumulate+reduce+solve kernel.
+ * 1: search, linearisation, block/grid reduction and the 6x6 solve in ONE kernel per ICP iteration — same results to
+ * rounding (the per-block summation order differs); measured slower on B200 (register pressure), kept as an option. */
+int elm_registration_set_fused(elm_registration* reg, int enable);
+
 /* Spatial binning of the scan (default OFF — measured slower on B200 for the pruned search): once per call the scan is counting-sorted on the device by the voxel each
  * point falls into under the initial guess, and the SEARCH walks it in that order so that neighbouring queries share
  * cache lines of the map.  The accumulation keeps the caller's order, so results do not depend on this switch. */

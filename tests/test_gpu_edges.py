@@ -128,6 +128,20 @@ def test_comm_path_world_size_one_equals_fused_path(small):
     assert oka == okb and np.array_equal(Ta, Tb) and fa == fb and np.array_equal(ca, cb)
 
 
+@pytest.mark.parametrize("method", [E.P2P, E.GICP])
+def test_fused_kernel_matches_two_kernel_path(small, method):
+    """elm_registration_set_fused(1): one kernel per iteration; sums equal the default path to rounding"""
+    scan = synth.scan_m(small["stored"], 3000, small["T_true"])
+    cfg = E.RegistrationConfig(icp_method=method, max_iteration=6, **synth.timing_knobs())
+    a, b = E.Registration(device=0), E.Registration(device=0)
+    b.set_fused(True)
+    la, lb = a.linearize(scan, small["gm"], small["T0"], cfg), b.linearize(scan, small["gm"], small["T0"], cfg)
+    assert la["n_corr"] == lb["n_corr"] and rel_err(la["JTJ"], lb["JTJ"]) < 1e-12 and rel_err(la["JTr"], lb["JTr"]) < 1e-10
+    Ta, oka, fa, ca = a.RunRegister(scan, small["gm"], small["T0"], cfg)
+    Tb, okb, fb, cb = b.RunRegister(scan, small["gm"], small["T0"], cfg)
+    assert oka == okb and rel_err(Tb, Ta) < 1e-10 and abs(fa - fb) < 1e-10 and rel_err(cb, ca) < 1e-8
+
+
 def test_run_to_run_bit_reproducible(small):
     scan = synth.scan_m(small["stored"], 5000, small["T_true"])
     cfg = E.RegistrationConfig(icp_method=E.P2P, max_iteration=8, **synth.timing_knobs())
