@@ -51,6 +51,9 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
     bool load() {
         if (h) return true;
+        // single-node path: keep NCCL's bootstrap on the loopback interface unless the user chose otherwise (interface
+        // probing / reverse DNS in containers can take minutes)
+        setenv("NCCL_SOCKET_IFNAME", "lo", 0);
         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!h) return false;

@@ -151,9 +151,10 @@ __device__ __forceinline__ float axis_gap2(int kq, int o, float f) {
     const float g = fmaxf(fmaxf(fmaxf(lo - f, f - hi), 0.0f) - 1e-5f, 0.0f);
     return g * g;
 }
-// Bit L set <=> voxel L (outside the centre column 12..14) may still hold a point at least as close as `best_d2`:
-// a voxel is dropped only when its box is PROVABLY farther, so dropping can never change the result.
-__device__ __forceinline__ uint32_t voxels_to_visit(int kx, int ky, int kz, float fx, float fy, float fz, double best_d2, float inv_vs2_up) {
+// Bit L set <=> voxel L (outside the mask `skip` of already visited ones) may still hold a point at least as close as
+// `best_d2`: a voxel is dropped only when its box is PROVABLY farther, so dropping can never change the result.
+__device__ __forceinline__ uint32_t voxels_to_visit(int kx, int ky, int kz, float fx, float fy, float fz, double best_d2, float inv_vs2_up,
+                                                    uint32_t skip) {
     const float bound = __double2float_ru(best_d2) * inv_vs2_up;  // best distance so far, voxel units, rounded up
     const float gx[3] = {axis_gap2(kx, -1, fx), axis_gap2(kx, 0, fx), axis_gap2(kx, 1, fx)};
     const float gy[3] = {axis_gap2(ky, -1, fy), axis_gap2(ky, 0, fy), axis_gap2(ky, 1, fy)};
@@ -161,11 +162,10 @@ __device__ __forceinline__ uint32_t voxels_to_visit(int kx, int ky, int kz, floa
     uint32_t need = 0;
 #pragma unroll
     for (int L = 0; L < 27; ++L) {
-        if (L >= 12 && L <= 14) continue;
         const float lb = (gx[L / 9] + gy[(L / 3) % 3] + gz[L % 3]) * 0.9999f;
         if (!(lb > bound)) need |= 1u << L;
     }
-    return need;
+    return need & ~skip;
 }
 // Visit ONE voxel L of the neighbourhood of (kx, ky, kz); returns the number of points streamed.
 __device__ __forceinline__ uint32_t visit_voxel(const MapView& map, int kx, int ky, int kz, int L, double px, double py, double pz, Best& b) {
@@ -634,8 +634,8 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
 // 12 B/point; double-buffered when a block owns several tiles).  TransformPoints is fused (reg.hpp:136-148).
 //
 // COOP = true (default, exact pruning), three phases per tile:
-//   A  thread per QUERY : transform, probe + stream the centre column, derive which other voxels cannot be excluded
-//                         and append one work item per such voxel to a block-wide list in shared memory;
+//   A  thread per QUERY : transform, probe + stream the z-column of the voxel the query falls into, derive which of the
+//                         other 24 voxels cannot be excluded and append one work item per such voxel to a block-wide list;
 //   B  thread per ITEM  : probe that voxel and stream its points for the item's query (balanced: every lane busy,
 //                         instead of each query thread walking its own 0..24 voxels while its warp-mates idle);
 //   C  merge            : atomicMin on the fp64 distance bits, then on (visit order, index) among the exact minima,
@@ -726,8 +726,13 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             const bool interior = neighbourhood_interior(kx, ky, kz);
             ++searched;
             if (COOP) {
-                visited += visit_column(map, kx, ky, kz, interior, 12u, px, py, pz, b);
-                own_need = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up);
+                // the z-column holding the voxel whose STORED-key cell contains the query: insert keys truncate toward zero
+                // (vhm.cpp:275), so on a negative axis that cell is the floor key + 1.  (Visiting only the one voxel instead
+                // of its column was measured: fewer points, 36 vs 46 per query, but more items and random probes: 55 vs 51 us.)
+                const int hx = (kx < 0) ? 1 : 0, hy = (ky < 0) ? 1 : 0;
+                const uint32_t L0 = static_cast<uint32_t>(9 * (hx + 1) + 3 * (hy + 1));
+                visited += visit_column(map, kx + hx, ky + hy, kz, interior, L0, px, py, pz, b);
+                own_need = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up, 7u << L0);
                 s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
                 s_kx[tid] = kx; s_ky[tid] = ky; s_kz[tid] = kz;
                 s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
