@@ -47,6 +47,9 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
+        # shared hosts: never let idle OpenMP workers spin (an oversubscribed box turns every barrier into seconds)
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+        os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 16)))
         L = C.CDLL(build())
         dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
         L.orc_map_create.restype = C.c_void_p
