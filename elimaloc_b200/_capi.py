@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libelimaloc_b200.so")
+# ELIMALOC_B200_LIB: developer override to A/B-test another build of the same library (profiles/quick_bench.sh)
+LIB_PATH = os.environ.get("ELIMALOC_B200_LIB") or os.path.join(_HERE, "libelimaloc_b200.so")
 
 ELM_OK, ELM_ERR_INVALID, ELM_ERR_CUDA, ELM_ERR_NCCL, ELM_ERR_UNSUPPORTED, ELM_ERR_RANGE, ELM_ERR_STATE = range(7)
 P2P, GICP, VGICP, AVGICP = 0, 1, 2, 3
@@ -80,6 +81,7 @@ SIGNATURES = {
     "elm_map_num_voxels": (C.c_size_t, [C.c_void_p]),
     "elm_map_num_points": (C.c_size_t, [C.c_void_p]),
     "elm_map_export": (C.c_int, [C.c_void_p, _ip, _ip, _dp, _dp, _fp, _dp, _dp]),
+    "elm_map_directory_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "elm_registration_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "elm_registration_destroy": (None, [C.c_void_p]),
     "elm_run_register": (C.c_int, [C.c_void_p, C.c_void_p, _fp, C.c_size_t, _dp, C.POINTER(RegConfig), _dp, _ip, _dp, _dp]),

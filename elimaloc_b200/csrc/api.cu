@@ -75,7 +75,8 @@ constexpr int kNcclSum = 0;      // ncclSum
 struct elm_map {
     elm::HostMap host;
     int device = -1;  // -1: host-only map (builder tests without a GPU)
-    uint4* d_slots = nullptr;
+    uint4* d_dslots = nullptr;
+    uint2* d_drows = nullptr;
     float4* d_pts = nullptr;
     double* d_prec = nullptr;
     double4* d_vslots = nullptr;
@@ -83,7 +84,7 @@ struct elm_map {
 
     elm::MapView view() const {
         elm::MapView v;
-        v.slots = d_slots; v.pts = d_pts; v.prec = d_prec; v.vslots = d_vslots; v.vcov = d_vcov;
+        v.dslots = d_dslots; v.drows = d_drows; v.bmask = host.dir_bmask; v.pts = d_pts; v.prec = d_prec; v.vslots = d_vslots; v.vcov = d_vcov;
         v.mask = host.mask; v.voxel_size = host.voxel_size;
         return v;
     }
@@ -97,7 +98,9 @@ struct elm_map {
             p4[i].w = __int_as_float_host(host.porig[i]);
         }
         ELM_CUDA(upload(&d_pts, p4.data(), P));
-        ELM_CUDA(upload(&d_slots, host.slots.data(), host.slots.size()));
+        static_assert(sizeof(elm::DirSlot) == sizeof(uint4) && sizeof(elm::DirDesc) == sizeof(uint2), "directory layout");
+        ELM_CUDA(upload(&d_dslots, reinterpret_cast<const uint4*>(host.dir_slots.data()), host.dir_slots.size()));
+        ELM_CUDA(upload(&d_drows, reinterpret_cast<const uint2*>(host.dir_rows.data()), host.dir_rows.size()));
         if (d_prec) { cudaFree(d_prec); d_prec = nullptr; }
         if (d_vslots) { cudaFree(d_vslots); d_vslots = nullptr; }
         if (d_vcov) { cudaFree(d_vcov); d_vcov = nullptr; }
@@ -137,7 +140,7 @@ struct elm_map {
     ~elm_map() {
         if (device >= 0) {
             cudaSetDevice(device);
-            cudaFree(d_slots); cudaFree(d_pts); cudaFree(d_prec); cudaFree(d_vslots); cudaFree(d_vcov);
+            cudaFree(d_dslots); cudaFree(d_drows); cudaFree(d_pts); cudaFree(d_prec); cudaFree(d_vslots); cudaFree(d_vcov);
         }
     }
 };
@@ -432,6 +435,62 @@ int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* v
     if (pxyz) std::memcpy(pxyz, h.pxyz.data(), h.pxyz.size() * sizeof(float));
     if (pmean) std::memcpy(pmean, h.pmean.data(), h.pmean.size() * sizeof(double));
     if (pcov) std::memcpy(pcov, h.pcov.data(), h.pcov.size() * sizeof(double));
+    return ELM_OK;
+}
+
+int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slots, uint64_t* mismatches) {
+    if (!map || !entries || !slots || !mismatches) return fail(ELM_ERR_INVALID, "elm_map_directory_check: bad argument");
+    const elm::HostMap& h = map->host;
+    *entries = h.dir_entries;
+    *slots = h.dir_slots.size();
+    uint64_t bad = 0, found = 0;
+    // every stored slot: descriptors against the canonical arrays
+    for (size_t s = 0; s < h.dir_slots.size(); ++s) {
+        const elm::DirSlot& sl = h.dir_slots[s];
+        if ((sl.key_lo & sl.key_hi) == 0xffffffffu) continue;
+        ++found;
+        const uint64_t key = (static_cast<uint64_t>(sl.key_hi) << 32) | sl.key_lo;
+        if (h.dir_find(key) != static_cast<int64_t>(s)) ++bad;
+        int32_t x, y, z;
+        elm::unpack_key(key, x, y, z);
+        bool any = false;
+        for (int c = 0; c < 9; ++c) {
+            const elm::DirDesc d = h.dir_rows[s * elm::kDirRowDescs + c];
+            uint32_t first = 0, counts = 0;
+            bool have = false;
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int32_t vx = x + c / 3 - 1, vy = y + c % 3 - 1, vz = z + dz;
+                if (!elm::key_in_range(vx) || !elm::key_in_range(vy) || !elm::key_in_range(vz)) continue;
+                const int64_t v = h.find(elm::pack_key(vx, vy, vz));
+                if (v < 0) continue;
+                if (!have) { first = h.vstart[v]; have = true; }
+                else if (h.vstart[v] != first + (counts & elm::kDirCountMask) + ((counts >> elm::kDirCountBits) & elm::kDirCountMask)) ++bad;  // contiguity
+                counts |= (h.vstart[v + 1] - h.vstart[v]) << (elm::kDirCountBits * static_cast<uint32_t>(dz + 1));
+            }
+            any = any || have;
+            if (d.counts != counts || (have && d.first != first)) ++bad;
+            if (c == 4 && (sl.counts != counts || (have && sl.first != first))) ++bad;
+        }
+        if (!any) ++bad;  // an entry whose neighbourhood is empty should not exist
+    }
+    if (found != h.dir_entries) ++bad;
+    // every occupied voxel makes its 27 surrounding centres findable; two voxels further out along x there is a miss
+    // unless that centre has its own occupied neighbour
+    for (size_t v = 0; v < h.V(); ++v) {
+        int32_t x, y, z;
+        elm::unpack_key(h.vkey[v], x, y, z);
+        for (int dx = -1; dx <= 1; ++dx) for (int dy = -1; dy <= 1; ++dy) for (int dz = -1; dz <= 1; ++dz)
+            if (h.dir_find(elm::pack_key(x + dx, y + dy, z + dz)) < 0) ++bad;
+        for (int dx : {-2, 2}) {
+            const int32_t cx = x + dx;
+            if (!elm::key_in_range(cx)) continue;
+            bool occupied_near = false;
+            for (int ex = -1; ex <= 1 && !occupied_near; ++ex) for (int ey = -1; ey <= 1 && !occupied_near; ++ey) for (int ez = -1; ez <= 1; ++ez)
+                if (elm::key_in_range(cx + ex) && h.find(elm::pack_key(cx + ex, y + ey, z + ez)) >= 0) { occupied_near = true; break; }
+            if ((h.dir_find(elm::pack_key(cx, y, z)) >= 0) != occupied_near) ++bad;
+        }
+    }
+    *mismatches = bad;
     return ELM_OK;
 }
 

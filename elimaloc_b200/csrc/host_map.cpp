@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <initializer_list>
 #include <atomic>
 #include <thread>
 
@@ -123,6 +124,7 @@ void plane_regularize(const double cov[9], double out[9], double normal[3]) {
 
 std::string HostMap::add_points(const float* xyz, size_t n) {
     if (n == 0) return "";
+    if (cap > static_cast<int>(kDirCountMask)) return "max_points_per_voxel above 1023 does not fit the column descriptors";
     const size_t P0 = P();
     const size_t total = P0 + n;
     if (total >= (1ull << 32)) return "more than 2^32 points";
@@ -137,7 +139,9 @@ std::string HostMap::add_points(const float* xyz, size_t n) {
         for (size_t i = b; i < e; ++i) {
             const double qx = static_cast<double>(xyz[3 * i]) / vs, qy = static_cast<double>(xyz[3 * i + 1]) / vs,
                          qz = static_cast<double>(xyz[3 * i + 2]) / vs;
-            if (!(std::fabs(qx) < kKeyBias && std::fabs(qy) < kKeyBias && std::fabs(qz) < kKeyBias)) { bad = true; continue; }
+            // (two voxels of margin so that every centre key whose neighbourhood reaches a stored voxel is itself packable)
+            const double lim = static_cast<double>(kKeyBias - 2);
+            if (!(std::fabs(qx) < lim && std::fabs(qy) < lim && std::fabs(qz) < lim)) { bad = true; continue; }
             recs[P0 + i] = Rec{pack_key(static_cast<int32_t>(qx), static_cast<int32_t>(qy), static_cast<int32_t>(qz)),
                                static_cast<uint32_t>(P0 + i)};
         }
@@ -199,7 +203,115 @@ std::string HostMap::add_points(const float* xyz, size_t n) {
     has_vcov = has_pcov = false;
     vmean.clear(); vcov.clear(); pmean.clear(); pcov.clear(); pnormal.clear();
     build_table();
+    return build_directory();
+}
+
+// ---- neighbourhood directory ------------------------------------------------------------------------------------
+namespace {
+
+// keys (sorted, unique) dilated by one voxel along one axis: {k - unit, k, k + unit}, still sorted and unique
+std::vector<uint64_t> dilate_axis(const std::vector<uint64_t>& in, int axis) {
+    const int shift = kKeyBits * (2 - axis);
+    const uint64_t unit = 1ull << shift, fmask = (1ull << kKeyBits) - 1;
+    std::vector<uint64_t> lo, hi;
+    lo.reserve(in.size()); hi.reserve(in.size());
+    for (uint64_t k : in) {
+        const uint64_t f = (k >> shift) & fmask;
+        if (f > 0) lo.push_back(k - unit);
+        if (f < fmask) hi.push_back(k + unit);
+    }
+    std::vector<uint64_t> t(lo.size() + in.size()), out(lo.size() + in.size() + hi.size());
+    std::merge(lo.begin(), lo.end(), in.begin(), in.end(), t.begin());
+    std::merge(t.begin(), t.end(), hi.begin(), hi.end(), out.begin());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    return out;
+}
+
+}  // namespace
+
+std::string HostMap::build_directory() {
+    dir_slots.clear(); dir_rows.clear(); dir_bmask = 0; dir_entries = 0;
+    if (vkey.empty()) return "";
+    // 1. centre keys: occupied voxels and their one-voxel halo (separable dilation z, y, x of the sorted key list)
+    std::vector<uint64_t> E = dilate_axis(dilate_axis(dilate_axis(vkey, 2), 1), 0);
+    dir_entries = E.size();
+    if (E.size() >= (1ull << 31)) return "map too large for the neighbourhood directory";
+    // 2. 2-choice cuckoo placement, 2 slots per bucket, load <= 0.75; deterministic random walk, table doubled on failure
+    size_t nb = 2;
+    while (nb * 2 * 3 < E.size() * 4) nb <<= 1;
+    std::vector<int64_t> owner;  // slot -> entry index or -1
+    for (;; nb <<= 1) {
+        if (nb * 2 >= (1ull << 32)) return "map too large for the neighbourhood directory";
+        const uint32_t bm = static_cast<uint32_t>(nb - 1);
+        owner.assign(nb * 2, -1);
+        uint64_t rng = 0x9E3779B97F4A7C15ull;
+        bool ok = true;
+        for (size_t e0 = 0; e0 < E.size() && ok; ++e0) {
+            int64_t cur = static_cast<int64_t>(e0);
+            uint32_t avoid = 0xffffffffu;  // bucket the current key was just evicted from
+            for (int kick = 0;; ++kick) {
+                uint32_t b1, b2;
+                dir_buckets(E[cur], bm, b1, b2);
+                int64_t* s1 = &owner[2 * static_cast<size_t>(b1)];
+                int64_t* s2 = &owner[2 * static_cast<size_t>(b2)];
+                if (s1[0] < 0) { s1[0] = cur; break; }
+                if (s1[1] < 0) { s1[1] = cur; break; }
+                if (s2[0] < 0) { s2[0] = cur; break; }
+                if (s2[1] < 0) { s2[1] = cur; break; }
+                if (kick >= 2000) { ok = false; break; }
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                const uint32_t b = (b1 == avoid) ? b2 : ((b2 == avoid) ? b1 : ((rng & 2) ? b1 : b2));
+                int64_t* victim = &owner[2 * static_cast<size_t>(b) + (rng & 1)];
+                std::swap(cur, *victim);
+                avoid = b;
+            }
+        }
+        if (ok) { dir_bmask = bm; break; }
+    }
+    // 3. slots + rows (row r belongs to slot r)
+    const size_t S = owner.size();
+    dir_slots.assign(S, DirSlot{0xffffffffu, 0xffffffffu, 0, 0});
+    dir_rows.assign(S * kDirRowDescs, DirDesc{0, 0});
+    parallel_for(S, 1 << 14, [&](size_t sb, size_t se) {
+        for (size_t s = sb; s < se; ++s) {
+            if (owner[s] < 0) continue;
+            const uint64_t key = E[owner[s]];
+            int32_t x, y, z;
+            unpack_key(key, x, y, z);
+            DirDesc* row = &dir_rows[s * kDirRowDescs];
+            for (int c = 0; c < 9; ++c) {
+                const int32_t cx = x + c / 3 - 1, cy = y + c % 3 - 1;
+                if (!key_in_range(cx) || !key_in_range(cy)) continue;
+                const int32_t zlo = std::max(z - 1, -kKeyBias), zhi = std::min(z + 1, kKeyBias - 1);
+                const uint64_t klo = pack_key(cx, cy, zlo), khi = pack_key(cx, cy, zhi);
+                size_t v = static_cast<size_t>(std::lower_bound(vkey.begin(), vkey.end(), klo) - vkey.begin());
+                uint32_t first = 0, counts = 0;
+                bool any = false;
+                for (; v < vkey.size() && vkey[v] <= khi; ++v) {
+                    int32_t vx, vy, vz;
+                    unpack_key(vkey[v], vx, vy, vz);
+                    if (!any) { first = vstart[v]; any = true; }
+                    counts |= (vstart[v + 1] - vstart[v]) << (kDirCountBits * static_cast<uint32_t>(vz - (z - 1)));
+                }
+                row[c] = DirDesc{first, counts};
+            }
+            dir_slots[s] = DirSlot{static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), row[4].first, row[4].counts};
+        }
+    });
     return "";
+}
+
+int64_t HostMap::dir_find(uint64_t key) const {
+    if (dir_slots.empty()) return -1;
+    uint32_t b1, b2;
+    dir_buckets(key, dir_bmask, b1, b2);
+    const uint32_t lo = static_cast<uint32_t>(key), hi = static_cast<uint32_t>(key >> 32);
+    for (uint32_t b : {b1, b2})
+        for (uint32_t j = 0; j < 2; ++j) {
+            const DirSlot& s = dir_slots[2 * static_cast<size_t>(b) + j];
+            if (s.key_lo == lo && s.key_hi == hi) return static_cast<int64_t>(2 * static_cast<size_t>(b) + j);
+        }
+    return -1;
 }
 
 void HostMap::build_table() {

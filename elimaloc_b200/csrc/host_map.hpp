@@ -20,6 +20,15 @@ namespace elm {
 // One open-addressed slot, 16 bytes: {key lo, key hi, first stored point, stored count}.
 struct Slot { uint32_t key_lo, key_hi, start, count; };
 
+// Neighbourhood directory (what the P2P/GICP search reads): one entry per voxel key whose 27-neighbourhood holds at
+// least one stored point (occupied voxels + their one-voxel halo).  Entry = a 16-byte slot in a 2-choice cuckoo table
+// with 2-slot buckets {key, first point and counts of the centre z-column} + a 96-byte row, indexed by the SLOT position,
+// of nine column descriptors {first point, n(z-1) | n(z) << 10 | n(z+1) << 20} for the columns (x+dx, y+dy), dx outer.
+// A lookup is two independent 32-byte loads (no probe chains); a miss means "no candidate at all".
+struct DirSlot { uint32_t key_lo, key_hi, first, counts; };
+struct DirDesc { uint32_t first, counts; };
+constexpr int kDirRowDescs = 12;  // 9 used, padded to 96 bytes = three 32-byte sectors
+
 struct HostMap {
     double voxel_size = 1.0;
     int cap = 30;
@@ -41,6 +50,12 @@ struct HostMap {
     std::vector<int32_t> slot_voxel;
     uint32_t mask = 0;
 
+    // neighbourhood directory (see above); dir_slots.size() == 2 * (dir_bmask + 1), dir_rows.size() == 12 * dir_slots.size()
+    std::vector<DirSlot> dir_slots;
+    std::vector<DirDesc> dir_rows;
+    uint32_t dir_bmask = 0;
+    size_t dir_entries = 0;
+
     size_t V() const { return vkey.size(); }
     size_t P() const { return pxyz.size() / 3; }
 
@@ -49,6 +64,10 @@ struct HostMap {
     void cal_voxel_cov();
     void cal_point_cov(double search_dist);
     void build_table();
+    // returns "" on success
+    std::string build_directory();
+    // slot index of a centre key in the directory or -1 (host mirror of the device lookup; tests)
+    int64_t dir_find(uint64_t key) const;
     // voxel index of a packed key or -1
     int64_t find(uint64_t key) const;
 };

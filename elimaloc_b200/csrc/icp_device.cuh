@@ -1,12 +1,16 @@
 // Device-side data layout of the registration hot path (sm_100a).
 //
 // HBM layout of the map (built by host_map.cpp, uploaded by device_map.cu):
-//   slots   uint4[capacity]      open-addressed table, 16 B/slot {key_lo, key_hi, first point, count}; capacity = 2^k
-//                                >= 2 V; key = 3 x 21-bit biased voxel coordinates; empty = all ones; linear probing
+//   dslots  uint4[2 B]           neighbourhood directory: 2-choice cuckoo table, B = 2^k buckets of two 16-B slots
+//                                {key_lo, key_hi, first point, counts} of every voxel key whose 27-neighbourhood holds a
+//                                stored point; first/counts describe the centre z-column (x, y, z-1..z+1);
+//                                counts = n(z-1) | n(z) << 10 | n(z+1) << 20; key = 3 x 21-bit biased coordinates
+//   drows   uint2[12 * 2 B]      one 96-B row per SLOT: {first point, counts} of the nine z-columns (x+dx, y+dy), dx outer
 //   pts     float4[P]            stored points in canonical order (voxels sorted by (x,y,z), insertion order inside):
 //                                the voxels (x,y,z-1..z+1) of one column are ONE contiguous run; w = raw-index bits
 //   prec    double[16 P]         GICP record per stored point: mean[3] cov[9] normal[3] pad  (128 B, one line)
-//   vslots  double4[capacity]    VGICP/AVGICP: 32 B/slot {key bits, mean[3]} parallel to `slots` (same slot index)
+//   vslots  double4[capacity]    VGICP/AVGICP: 32 B/slot {key bits, mean[3]}, open-addressed with linear probing, capacity = 2^k
+//                                >= 2 V (mask = capacity - 1); empty = all ones
 //   vcov    double[12 capacity]  VGICP/AVGICP: 96 B/slot {cov[9], pad[3]}
 #pragma once
 #include <cuda_runtime.h>
@@ -15,12 +19,14 @@
 namespace elm {
 
 struct MapView {
-    const uint4* slots;
+    const uint4* dslots;
+    const uint2* drows;
     const float4* pts;
     const double* prec;
     const double4* vslots;
     const double* vcov;
-    uint32_t mask;
+    uint32_t mask;   // vslots
+    uint32_t bmask;  // directory buckets - 1
     double voxel_size;
 };
 

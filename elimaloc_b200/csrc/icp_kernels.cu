@@ -67,18 +67,6 @@ __device__ __forceinline__ int voxel_floor(double p, double vs, float* frac = nu
     // saturate far outside the table's key range instead of the reference's undefined int overflow
     return (f >= 2.0e9) ? 2000000000 : ((f <= -2.0e9) ? -2000000000 : static_cast<int>(f));
 }
-// Same probe when the home slot has already been fetched (lets the first loads of several probes overlap).
-__device__ __forceinline__ void probe_resume(const uint4* __restrict__ slots, uint32_t mask, uint64_t key, uint32_t h, uint4 s,
-                                             uint32_t& start, uint32_t& count) {
-    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
-    count = 0;
-    for (uint32_t i = 0; i <= mask; ++i) {
-        if (s.x == klo && s.y == khi) { start = s.z; count = s.w; return; }
-        if ((s.x & s.y) == 0xffffffffu) return;
-        h = (h + 1) & mask;
-        s = __ldg(slots + h);
-    }
-}
 // Linear probe of the 32-B VGICP table {key, mean}; returns the slot or -1 and the mean.
 __device__ __forceinline__ int probe_mean(const double4* __restrict__ vslots, uint32_t mask, uint64_t key, double& mx, double& my, double& mz) {
     uint32_t h = home_slot(key) & mask;
@@ -93,52 +81,59 @@ __device__ __forceinline__ int probe_mean(const double4* __restrict__ vslots, ui
     return -1;
 }
 
-// Linear probe of the 16-B table.  count = 0 on a miss.
-__device__ __forceinline__ void probe(const uint4* __restrict__ slots, uint32_t mask, uint64_t key, uint32_t& start, uint32_t& count) {
-    const uint32_t h = home_slot(key) & mask;
-    probe_resume(slots, mask, key, h, __ldg(slots + h), start, count);
+// Neighbourhood-directory lookup of the centre key: two independent 32-byte bucket loads (2-choice cuckoo, 2 slots per
+// bucket) — one round trip, no probe chain, lanes of a warp never wait for each other's collisions.  Returns the slot
+// index (== row index) or -1 when no voxel of the 27-neighbourhood holds a point; `centre` = descriptor of the centre
+// z-column {first point, n(z-1) | n(z) << 10 | n(z+1) << 20}.
+__device__ __forceinline__ int dir_lookup(const MapView& map, int kx, int ky, int kz, uint2& centre) {
+    if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) return -1;
+    const uint64_t key = pack_key(kx, ky, kz);
+    uint32_t b1, b2;
+    dir_buckets(key, map.bmask, b1, b2);
+    const uint4 s0 = __ldg(map.dslots + 2 * static_cast<size_t>(b1)), s1 = __ldg(map.dslots + 2 * static_cast<size_t>(b1) + 1);
+    const uint4 s2 = __ldg(map.dslots + 2 * static_cast<size_t>(b2)), s3 = __ldg(map.dslots + 2 * static_cast<size_t>(b2) + 1);
+    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
+    if (s0.x == klo && s0.y == khi) { centre = make_uint2(s0.z, s0.w); return static_cast<int>(2 * b1); }
+    if (s1.x == klo && s1.y == khi) { centre = make_uint2(s1.z, s1.w); return static_cast<int>(2 * b1 + 1); }
+    if (s2.x == klo && s2.y == khi) { centre = make_uint2(s2.z, s2.w); return static_cast<int>(2 * b2); }
+    if (s3.x == klo && s3.y == khi) { centre = make_uint2(s3.z, s3.w); return static_cast<int>(2 * b2 + 1); }
+    return -1;
+}
+// descriptor of column c (= 3 (dx + 1) + (dy + 1)) of the row that belongs to directory slot `si`
+__device__ __forceinline__ uint2 dir_column(const MapView& map, int si, int c) {
+    return __ldg(map.drows + static_cast<size_t>(si) * 12 + c);
+}
+// The contiguous run of `pts` that covers the voxels of `zmask` (bit 0: z-1, bit 1: z, bit 2: z+1; != 0) of a column.
+// (A mask with a gap also covers the voxel in between: visiting more candidates never changes the exact result.)
+__device__ __forceinline__ void column_run(uint2 d, uint32_t zmask, uint32_t& start, uint32_t& len) {
+    const uint32_t n0 = d.y & kDirCountMask, n1 = (d.y >> kDirCountBits) & kDirCountMask, n2 = (d.y >> (2 * kDirCountBits)) & kDirCountMask;
+    const uint32_t lo = (zmask & 1u) ? 0u : ((zmask & 2u) ? n0 : n0 + n1);
+    const uint32_t hi = (zmask & 4u) ? n0 + n1 + n2 : ((zmask & 2u) ? n0 + n1 : n0);
+    start = d.x + lo;
+    len = hi - lo;
 }
 
-// Running best of one search: smallest (d2, ord); ord encodes the reference's visit order so that any visiting order
-// yields the reference's winner (voxels x-outer / y / z-inner, vhm.cpp:234-240; insertion order inside a voxel; strict <,
-// vhm.cpp:45).
+// Running best of one search: smallest (d2, idx).  `pts` is in canonical order — voxels sorted by (x, y, z), insertion
+// order inside — which IS the reference's visit order (voxels x-outer / y / z-inner, vhm.cpp:234-240; strict <,
+// vhm.cpp:45): among equal distances the reference keeps the candidate with the smallest canonical index.
 struct Best {
     double d2 = kDblMax;
-    uint32_t ord = 0xffffffffu, idx = 0;
+    uint32_t idx = 0xffffffffu;
 };
-// Stream `n` consecutive stored points and fold them into `b`; ord0/idx0 = visit order / index of the first one.
-__device__ __forceinline__ void visit_points(const float4* __restrict__ p, uint32_t n, uint32_t ord0, uint32_t idx0, double px, double py,
-                                             double pz, Best& b) {
-#ifdef ELM_PREFETCH_RUNS
-    {   // pull every 128-B line of the run towards L1 before streaming it
-        const char* pb = reinterpret_cast<const char*>(p);
-        const char* pe = pb + static_cast<size_t>(n) * 16;
-        for (const char* a = pb + 64; a < pe; a += 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-    }
-#endif
+// Stream `n` consecutive stored points starting at index idx0 and fold them into `b` (ascending index + strict <
+// keeps the first of equals).
+__device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, double px, double py, double pz, Best& b) {
+    const float4* __restrict__ p = pts + idx0;
 #pragma unroll 4
     for (uint32_t o = 0; o < n; ++o) {
         const float4 q = __ldg(p + o);
         const double d2 = sq3_exact(static_cast<double>(q.x) - px, static_cast<double>(q.y) - py, static_cast<double>(q.z) - pz);
-        if (d2 < b.d2 || (d2 == b.d2 && ord0 + o < b.ord)) { b.d2 = d2; b.ord = ord0 + o; b.idx = idx0 + o; }
+        if (d2 < b.d2) { b.d2 = d2; b.idx = idx0 + o; }
     }
 }
-// One column (x, y, kz-1..kz+1) of the neighbourhood = one contiguous run of `pts`; L0 = visit index of its first voxel.
-__device__ __forceinline__ uint32_t visit_column(const MapView& map, int x, int y, int kz, bool interior, uint32_t L0, double px, double py,
-                                                 double pz, Best& b) {
-    uint32_t s0 = 0, c0 = 0, s1 = 0, c1 = 0, s2 = 0, c2 = 0;
-    const bool xy_ok = interior || (key_in_range(x) && key_in_range(y));
-    if (xy_ok && (interior || key_in_range(kz - 1))) probe(map.slots, map.mask, pack_key(x, y, kz - 1), s0, c0);
-    if (xy_ok && (interior || key_in_range(kz))) probe(map.slots, map.mask, pack_key(x, y, kz), s1, c1);
-    if (xy_ok && (interior || key_in_range(kz + 1))) probe(map.slots, map.mask, pack_key(x, y, kz + 1), s2, c2);
-    const uint32_t rl = c0 + c1 + c2;
-    const uint32_t rs = c0 ? s0 : (c1 ? s1 : s2);
-    visit_points(map.pts + rs, rl, L0 << 16, rs, px, py, pz, b);
-    return rl;
-}
-// the whole neighbourhood is inside the key range unless the centre sits on its border
-__device__ __forceinline__ bool neighbourhood_interior(int kx, int ky, int kz) {
-    return kx > -kKeyBias && kx < kKeyBias - 1 && ky > -kKeyBias && ky < kKeyBias - 1 && kz > -kKeyBias && kz < kKeyBias - 1;
+// folds a candidate found elsewhere (smaller distance wins, then smaller index)
+__device__ __forceinline__ void fold_best(Best& b, const Best& o) {
+    if (o.d2 < b.d2 || (o.d2 == b.d2 && o.idx < b.idx)) b = o;
 }
 
 // Squared-distance lower bound helper (fp32, units of voxel_size, deliberately under-estimated): gap along one axis
@@ -167,16 +162,6 @@ __device__ __forceinline__ uint32_t voxels_to_visit(int kx, int ky, int kz, floa
     }
     return need & ~skip;
 }
-// Visit ONE voxel L of the neighbourhood of (kx, ky, kz); returns the number of points streamed.
-__device__ __forceinline__ uint32_t visit_voxel(const MapView& map, int kx, int ky, int kz, int L, double px, double py, double pz, Best& b) {
-    const int x = kx + L / 9 - 1, y = ky + (L / 3) % 3 - 1, z = kz + L % 3 - 1;
-    if (!(key_in_range(x) && key_in_range(y) && key_in_range(z))) return 0;
-    uint32_t vs0 = 0, vc = 0;
-    probe(map.slots, map.mask, pack_key(x, y, z), vs0, vc);
-    visit_points(map.pts + vs0, vc, static_cast<uint32_t>(L) << 16, vs0, px, py, pz, b);
-    return vc;
-}
-
 // Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115), one thread per query.  Returns the winning slot or -1.
 __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, double py, double pz, int kx, int ky, int kz) {
     double best = kDblMax;
@@ -633,16 +618,20 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
 // Block = 256 threads = one tile of 256 scan points, pulled into shared memory by the TMA bulk-copy engine (packed xyz,
 // 12 B/point; double-buffered when a block owns several tiles).  TransformPoints is fused (reg.hpp:136-148).
 //
+// Every query starts with ONE directory lookup of its centre key (two independent 32-byte loads): a miss means the
+// 27-neighbourhood is empty; a hit yields the centre z-column's run and the row of the other eight column runs.
+//
 // COOP = true (default, exact pruning), three phases per tile:
-//   A  thread per QUERY : transform, probe + stream the z-column of the voxel the query falls into, derive which of the
-//                         other 24 voxels cannot be excluded and append one work item per such voxel to a block-wide list;
-//   B  thread per ITEM  : probe that voxel and stream its points for the item's query (balanced: every lane busy,
-//                         instead of each query thread walking its own 0..24 voxels while its warp-mates idle);
-//   C  merge            : atomicMin on the fp64 distance bits, then on (visit order, index) among the exact minima,
+//   A  thread per QUERY : transform, lookup, stream the z-column of the voxel the query falls into, derive which of the
+//                         other 24 voxels cannot be excluded and append one work item per COLUMN that still has such
+//                         voxels (with their z-mask) to a block-wide list;
+//   B  thread per ITEM  : fetch the column's descriptor from the query's row and stream that run (balanced: every lane
+//                         busy, instead of each query thread walking its own 0..8 columns while its warp-mates idle);
+//   C  merge            : atomicMin on the fp64 distance bits, then on the canonical index among the exact minima,
 //                         which reproduces the reference's first-in-visit-order tie-break (vhm.cpp:45).
-// COOP = false: every thread walks all 9 columns of its own query — the reference's exhaustive visit.
+// COOP = false: every thread streams all 9 columns of its own query — the reference's exhaustive visit.
 constexpr int kNoItem = 0xffff;
-constexpr int kItemCap = 1024;  // work items per tile kept in shared memory (typical: ~600); overflow stays with its owner
+constexpr int kItemCap = 1024;  // work items per tile kept in shared memory; overflow stays with its owner
 
 // FUSE = 0 (P2P) / 1 (GICP): the tile's threads go straight on to linearise their correspondence (AlignCloudsLocal /
 // AlignCloudsLocalPointCov accumulation), the block tree-reduces, and the last block of the grid reduces all partials and
@@ -661,9 +650,11 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_T[12];
     __shared__ double s_px[COOP ? kIcpThreads : 1], s_py[COOP ? kIcpThreads : 1], s_pz[COOP ? kIcpThreads : 1];
-    __shared__ int s_kx[COOP ? kIcpThreads : 1], s_ky[COOP ? kIcpThreads : 1], s_kz[COOP ? kIcpThreads : 1];
-    __shared__ unsigned long long s_best[COOP ? kIcpThreads : 1], s_win[COOP ? kIcpThreads : 1];
-    __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1], s_item_win[COOP ? kItemCap : 1];
+    __shared__ int s_row[COOP ? kIcpThreads : 1];
+    __shared__ unsigned long long s_best[COOP ? kIcpThreads : 1];
+    __shared__ unsigned int s_win[COOP ? kIcpThreads : 1];
+    __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1];
+    __shared__ unsigned int s_item_idx[COOP ? kItemCap : 1];
     __shared__ uint16_t s_items[COOP ? kItemCap : 1];
     __shared__ int s_nitems;
 
@@ -712,8 +703,8 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
         // ---- phase A: one thread per query
         Best b;
         double px = 0, py = 0, pz = 0, sx = 0, sy = 0, sz = 0;
-        int kx = 0, ky = 0, kz = 0;
-        uint32_t own_need = 0;
+        uint32_t own_cols = 0;  // voxel mask (bit 3 c + iz) of the columns this thread has to walk itself
+        int row = -1;
         int my_match = -1;
         if (mine) {
             const float* sp = &s_tile[buf][tid * 3];
@@ -722,68 +713,101 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             py = row_apply_exact(s_T, 1, sx, sy, sz);
             pz = row_apply_exact(s_T, 2, sx, sy, sz);
             float fx, fy, fz;
-            kx = voxel_floor(px, map.voxel_size, &fx); ky = voxel_floor(py, map.voxel_size, &fy); kz = voxel_floor(pz, map.voxel_size, &fz);
-            const bool interior = neighbourhood_interior(kx, ky, kz);
+            const int kx = voxel_floor(px, map.voxel_size, &fx), ky = voxel_floor(py, map.voxel_size, &fy), kz = voxel_floor(pz, map.voxel_size, &fz);
             ++searched;
+            uint2 centre;
+            row = dir_lookup(map, kx, ky, kz, centre);
             if (COOP) {
-                // the z-column holding the voxel whose STORED-key cell contains the query: insert keys truncate toward zero
-                // (vhm.cpp:275), so on a negative axis that cell is the floor key + 1.  (Visiting only the one voxel instead
-                // of its column was measured: fewer points, 36 vs 46 per query, but more items and random probes: 55 vs 51 us.)
-                const int hx = (kx < 0) ? 1 : 0, hy = (ky < 0) ? 1 : 0;
-                const uint32_t L0 = static_cast<uint32_t>(9 * (hx + 1) + 3 * (hy + 1));
-                visited += visit_column(map, kx + hx, ky + hy, kz, interior, L0, px, py, pz, b);
-                own_need = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up, 7u << L0);
-                s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
-                s_kx[tid] = kx; s_ky[tid] = ky; s_kz[tid] = kz;
                 s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
-                s_win[tid] = ~0ull;
-                const int k = __popc(own_need);
-                if (k) {
-                    const int pos = atomicAdd(&s_nitems, k);
-                    if (pos + k <= kItemCap) {  // hand the voxels to the block; otherwise they stay with this thread
-                        int w = pos;
-                        for (uint32_t m = own_need; m; m &= m - 1) s_items[w++] = static_cast<uint16_t>((tid << 5) | (__ffs(m) - 1));
-                        own_need = 0;
-                    } else {
-                        for (int w = pos; w < kItemCap; ++w) s_items[w] = kNoItem;  // the tail of the list this claim straddles
+                s_win[tid] = 0xffffffffu;
+                if (row >= 0) {
+                    // the z-column holding the voxel whose STORED-key cell contains the query: insert keys truncate toward
+                    // zero (vhm.cpp:275), so on a negative axis that cell is the floor key + 1
+                    const int hx = (kx < 0) ? 1 : 0, hy = (ky < 0) ? 1 : 0;
+                    const int ch = 3 * (hx + 1) + (hy + 1);
+                    const uint2 hd = (ch == 4) ? centre : dir_column(map, row, ch);
+                    uint32_t rs, rl;
+                    column_run(hd, 7u, rs, rl);
+                    visit_points(map.pts, rs, rl, px, py, pz, b);
+                    visited += rl;
+                    own_cols = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up, 7u << (3 * ch));
+                    s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
+                    s_row[tid] = row;
+                    int k = 0;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) k += ((own_cols >> (3 * c)) & 7u) ? 1 : 0;
+                    if (k) {
+                        const int pos = atomicAdd(&s_nitems, k);
+                        if (pos + k <= kItemCap) {  // hand the columns to the block; otherwise they stay with this thread
+                            int w = pos;
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) {
+                                const uint32_t zm = (own_cols >> (3 * c)) & 7u;
+                                if (zm) s_items[w++] = static_cast<uint16_t>((tid << 7) | (c << 3) | zm);
+                            }
+                            own_cols = 0;
+                        } else {
+                            for (int w = pos; w < kItemCap; ++w) s_items[w] = kNoItem;  // the tail of the list this claim straddles
+                        }
                     }
                 }
-            } else {
+            } else if (row >= 0) {
 #pragma unroll 1
-                for (int c = 0; c < 9; ++c)
-                    visited += visit_column(map, kx + c / 3 - 1, ky + c % 3 - 1, kz, interior, static_cast<uint32_t>(3 * c), px, py, pz, b);
-                my_match = (b.ord == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
+                for (int c = 0; c < 9; ++c) {  // ascending column = ascending canonical index = the reference's visit order
+                    const uint2 d = (c == 4) ? centre : dir_column(map, row, c);
+                    uint32_t rs, rl;
+                    column_run(d, 7u, rs, rl);
+                    visit_points(map.pts, rs, rl, px, py, pz, b);
+                    visited += rl;
+                }
+                my_match = (b.idx == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
             }
         }
         if (COOP) {
             __syncthreads();
-            // ---- phase B: one thread per (query, voxel) item
+            // ---- phase B: one thread per (query, column) item
             const int nitems = min(s_nitems, kItemCap);  // (items beyond the cap were never written: their owners kept them)
             for (int j = tid; j < nitems; j += kIcpThreads) {
-                const int it = s_items[j], q = it >> 5, L = it & 31;
+                const int it = s_items[j];
                 if (it == kNoItem) continue;
+                const int q = it >> 7;
+                uint32_t rs, rl;
+                column_run(dir_column(map, s_row[q], (it >> 3) & 15), static_cast<uint32_t>(it & 7), rs, rl);
                 Best ib;
-                visited += visit_voxel(map, s_kx[q], s_ky[q], s_kz[q], L, s_px[q], s_py[q], s_pz[q], ib);
-                const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
-                s_item_d2[j] = bits;
-                s_item_win[j] = (static_cast<unsigned long long>(ib.ord) << 32) | ib.idx;
-                if (ib.ord != 0xffffffffu) atomicMin(&s_best[q], bits);
+                visit_points(map.pts, rs, rl, s_px[q], s_py[q], s_pz[q], ib);
+                visited += rl;
+                s_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
+                s_item_idx[j] = ib.idx;
+                if (ib.idx != 0xffffffffu) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
             }
             if (mine) {
-                for (uint32_t m = own_need; m; m &= m - 1) visited += visit_voxel(map, kx, ky, kz, __ffs(m) - 1, px, py, pz, b);
-                if (b.ord != 0xffffffffu) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(b.d2)));
+                if (own_cols) {
+#pragma unroll 1
+                    for (int c = 0; c < 9; ++c) {
+                        const uint32_t zm = (own_cols >> (3 * c)) & 7u;
+                        if (!zm) continue;
+                        uint32_t rs, rl;
+                        column_run(dir_column(map, row, c), zm, rs, rl);
+                        Best ob;
+                        visit_points(map.pts, rs, rl, px, py, pz, ob);
+                        visited += rl;
+                        fold_best(b, ob);
+                    }
+                }
+                if (b.idx != 0xffffffffu) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(b.d2)));
             }
             __syncthreads();
-            // ---- phase C: among the exact minima the smallest visit order wins
+            // ---- phase C: among the exact minima the smallest canonical index wins
             for (int j = tid; j < nitems; j += kIcpThreads) {
-                const int q = s_items[j] >> 5;
-                if (s_items[j] == kNoItem) continue;
-                if (s_item_d2[j] == s_best[q] && (s_item_win[j] >> 32) != 0xffffffffull) atomicMin(&s_win[q], s_item_win[j]);
+                const int it = s_items[j];
+                if (it == kNoItem) continue;
+                const int q = it >> 7;
+                if (s_item_idx[j] != 0xffffffffu && s_item_d2[j] == s_best[q]) atomicMin(&s_win[q], s_item_idx[j]);
             }
-            if (mine && b.ord != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
-                atomicMin(&s_win[tid], (static_cast<unsigned long long>(b.ord) << 32) | b.idx);
+            if (mine && b.idx != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
+                atomicMin(&s_win[tid], b.idx);
             __syncthreads();
-            if (mine) my_match = (s_win[tid] == ~0ull) ? -1 : static_cast<int>(s_win[tid] & 0xffffffffu);
+            if (mine) my_match = (s_win[tid] == 0xffffffffu) ? -1 : static_cast<int>(s_win[tid]);
         }
         if (mine && match) {
             const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;

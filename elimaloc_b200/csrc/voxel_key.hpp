@@ -39,4 +39,19 @@ ELM_HD uint32_t home_slot(uint64_t key) {
     return h;
 }
 
+// second, independent mix: the alternative bucket of the 2-choice (cuckoo) neighbourhood directory
+ELM_HD uint32_t home_slot2(uint64_t key) {
+    uint32_t h = (static_cast<uint32_t>(key) * 0xC2B2AE3Du) + (static_cast<uint32_t>(key >> 32) * 0x27D4EB2Fu) + 0x165667B1u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+// the two candidate buckets of a key (bucket = 2 slots = one 32-byte sector); always distinct
+ELM_HD void dir_buckets(uint64_t key, uint32_t bmask, uint32_t& b1, uint32_t& b2) {
+    b1 = home_slot(key) & bmask;
+    b2 = home_slot2(key) & bmask;
+    if (b2 == b1) b2 = b1 ^ 1u;
+}
+constexpr uint32_t kDirCountBits = 10;                       // per-voxel count field of a column descriptor
+constexpr uint32_t kDirCountMask = (1u << kDirCountBits) - 1;
+
 }  // namespace elm

@@ -84,6 +84,12 @@ class VoxelHashMap:
     def num_points(self):
         return lib().elm_map_num_points(self._h)
 
+    def directory_check(self):
+        """(centre keys stored, table slots, mismatches) of the neighbourhood directory; mismatches must be 0."""
+        e, s, m = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().elm_map_directory_check(self._h, C.byref(e), C.byref(s), C.byref(m)))
+        return int(e.value), int(s.value), int(m.value)
+
     def export(self, voxel_cov=False, point_cov=False):
         V, P = self.num_voxels(), self.num_points()
         out = dict(keys=np.zeros((V, 3), np.int32), counts=np.zeros(V, np.int32), pxyz=np.zeros((P, 3), np.float32))

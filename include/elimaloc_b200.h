@@ -93,6 +93,12 @@ size_t elm_map_num_points(const elm_map* map);
 int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* vmean, double* vcov, float* pxyz,
                    double* pmean, double* pcov);
 
+/* Self-check of the neighbourhood directory the P2P/GICP search reads (test hook, host only): every centre key whose
+ * 27 voxels (GetAdjacentVoxels range 2, voxel_hash_map.cpp:232-241) hold a stored point must be found by the 2-bucket
+ * lookup, its nine column descriptors must equal the canonical arrays, and keys outside that set must miss.
+ * entries = centre keys stored, slots = table slots, mismatches = violations found (0 = consistent). */
+int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slots, uint64_t* mismatches);
+
 /* ---- Registration ------------------------------------------------------------------------------------------- */
 /* stream: a cudaStream_t (as void*) every kernel of this handle is launched on; NULL = a private stream. */
 int elm_registration_create(elm_registration** out, int device, void* stream);

@@ -113,3 +113,25 @@ def test_product_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
                 assert "oracle" not in open(os.path.join(dirpath, f), errors="replace").read().lower(), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("kind", ["dense_negative", "sparse_surface", "single_point", "incremental"])
+def test_neighbourhood_directory_is_consistent(kind):
+    """The 2-choice directory the P2P/GICP search reads: every centre key whose 27 voxels (GetAdjacentVoxels range 2,
+    voxel_hash_map.cpp:232-241) hold a point is found, column descriptors equal the canonical arrays, others miss."""
+    pm = E.VoxelHashMap(1.0, 30, device=-1)
+    if kind == "dense_negative":
+        pm.AddPoints(synth.map_u(80_000, 16.0, origin=-7.0))
+    elif kind == "sparse_surface":
+        pm.AddPoints(synth.map_s(40_000, 60.0))
+    elif kind == "single_point":
+        pm.AddPoints(np.array([[-0.5, 0.25, 3.5]], np.float32))
+    else:
+        raw = synth.map_u(30_000, 12.0, origin=-2.0)
+        pm.AddPoints(raw[:10_000])
+        pm.AddPoints(raw[10_000:])
+    entries, slots, bad = pm.directory_check()
+    assert bad == 0
+    assert entries >= pm.num_voxels() and slots >= entries and slots <= 8 * max(entries, 2)
+    if kind == "single_point":
+        assert entries == 27
