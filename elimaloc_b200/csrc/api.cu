@@ -86,18 +86,21 @@ struct elm_map {
         elm::MapView v;
         v.dslots = d_dslots; v.drows = d_drows; v.bmask = host.dir_bmask; v.pts = d_pts; v.prec = d_prec; v.vslots = d_vslots; v.vcov = d_vcov;
         v.mask = host.mask; v.voxel_size = host.voxel_size;
+        int e2 = 0;
+        v.inv_voxel_size = (std::frexp(host.voxel_size, &e2) == 0.5) ? 1.0 / host.voxel_size : 0.0;
         return v;
     }
     int publish_points() {
         if (device < 0) return ELM_OK;
         ELM_CUDA(cudaSetDevice(device));
         const size_t P = host.P();
-        std::vector<float4> p4(P);
+        std::vector<float4> p4(P + 1);  // one element of padding: the search reads aligned 32-byte pairs
+        p4[P] = float4{0.f, 0.f, 0.f, 0.f};
         for (size_t i = 0; i < P; ++i) {
             p4[i].x = host.pxyz[3 * i]; p4[i].y = host.pxyz[3 * i + 1]; p4[i].z = host.pxyz[3 * i + 2];
             p4[i].w = __int_as_float_host(host.porig[i]);
         }
-        ELM_CUDA(upload(&d_pts, p4.data(), P));
+        ELM_CUDA(upload(&d_pts, p4.data(), P + 1));
         static_assert(sizeof(elm::DirSlot) == sizeof(uint4) && sizeof(elm::DirDesc) == sizeof(uint2), "directory layout");
         ELM_CUDA(upload(&d_dslots, reinterpret_cast<const uint4*>(host.dir_slots.data()), host.dir_slots.size()));
         ELM_CUDA(upload(&d_drows, reinterpret_cast<const uint2*>(host.dir_rows.data()), host.dir_rows.size()));
@@ -700,8 +703,8 @@ int elm_registration_profile(const elm_registration* reg, double* search_ms, dou
 int elm_registration_set_stats(elm_registration* reg, int enable) {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     ELM_CUDA(cudaSetDevice(reg->device));
-    if (!reg->d_stats) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_stats), 2 * sizeof(unsigned long long)));
-    ELM_CUDA(cudaMemsetAsync(reg->d_stats, 0, 2 * sizeof(unsigned long long), reg->stream));
+    if (!reg->d_stats) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_stats), 32 * sizeof(unsigned long long)));
+    ELM_CUDA(cudaMemsetAsync(reg->d_stats, 0, 32 * sizeof(unsigned long long), reg->stream));
     reg->stats_on = enable != 0;
     return ELM_OK;
 }
@@ -710,9 +713,16 @@ int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, 
     if (!reg || !map_points_visited || !queries) return fail(ELM_ERR_INVALID, "bad argument");
     if (!reg->d_stats) return fail(ELM_ERR_STATE, "stats were never enabled");
     ELM_CUDA(cudaSetDevice(reg->device));
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[32] = {0};
     ELM_CUDA(cudaMemcpyAsync(h, reg->d_stats, sizeof h, cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    if (getenv("ELM_PHASE_TIMING"))  // developer aid: per-warp cycle sums of the search phases (-DELM_PHASE_TIMING builds)
+        std::fprintf(stderr, "[phase cycles] warps %llu | tile %llu lookup %llu home %llu prune+items %llu B %llu C %llu\n", h[8], h[2], h[3], h[4], h[5], h[6], h[7]);
+    if (getenv("ELM_PHASE_TIMING"))
+        std::fprintf(stderr, "[fine cycles] warps %llu | transform+keys %llu lookup-loads %llu home-desc %llu\n", h[8], h[16], h[17], h[18]);
+    if (getenv("ELM_PHASE_TIMING"))
+        std::fprintf(stderr, "[accumulate cycles] blocks %llu | state %llu gather+linearise %llu block-reduce %llu publish+ticket %llu | last block: final-reduce %llu solve %llu\n",
+                     h[15], h[9], h[10], h[11], h[12], h[13], h[14]);
     *map_points_visited = h[0];
     *queries = h[1];
     return ELM_OK;

@@ -28,6 +28,7 @@ struct MapView {
     uint32_t mask;   // vslots
     uint32_t bmask;  // directory buckets - 1
     double voxel_size;
+    double inv_voxel_size;  // 1 / voxel_size when that is exact (voxel_size a power of two: p * inv == p / vs bit for bit), else 0
 };
 
 constexpr int kAcc = 32;       // accumulator vector: 21 JtJ (upper, row-major) + 6 Jtr + residual + n_corr + n_total + pad

@@ -60,8 +60,9 @@ __device__ __forceinline__ double row_apply_exact(const double* T, int r, double
     return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4 * r], x), __dmul_rn(T[4 * r + 1], y)), __dmul_rn(T[4 * r + 2], z)), T[4 * r + 3]);
 }
 // PointToVoxel (vhm.hpp:176-180): floor(p / vs); also returns the in-cell fraction (for the pruning bound)
-__device__ __forceinline__ int voxel_floor(double p, double vs, float* frac = nullptr) {
-    const double q = __ddiv_rn(p, vs);
+__device__ __forceinline__ int voxel_floor(double p, const MapView& map, float* frac = nullptr) {
+    // a power-of-two voxel size (the default 1.0) divides exactly by multiplication: skips the software DDIV sequence
+    const double q = (map.inv_voxel_size != 0.0) ? __dmul_rn(p, map.inv_voxel_size) : __ddiv_rn(p, map.voxel_size);
     const double f = floor(q);
     if (frac) *frac = static_cast<float>(q - f);
     // saturate far outside the table's key range instead of the reference's undefined int overflow
@@ -90,8 +91,12 @@ __device__ __forceinline__ int dir_lookup(const MapView& map, int kx, int ky, in
     const uint64_t key = pack_key(kx, ky, kz);
     uint32_t b1, b2;
     dir_buckets(key, map.bmask, b1, b2);
-    const uint4 s0 = __ldg(map.dslots + 2 * static_cast<size_t>(b1)), s1 = __ldg(map.dslots + 2 * static_cast<size_t>(b1) + 1);
-    const uint4 s2 = __ldg(map.dslots + 2 * static_cast<size_t>(b2)), s3 = __ldg(map.dslots + 2 * static_cast<size_t>(b2) + 1);
+    // one 32-byte load per bucket (sm_100 LDG.E.256): half the L1TEX requests of four 16-byte loads
+    uint4 s0, s1, s2, s3;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(s0.x), "=r"(s0.y), "=r"(s0.z), "=r"(s0.w), "=r"(s1.x), "=r"(s1.y), "=r"(s1.z), "=r"(s1.w) : "l"(map.dslots + 2 * static_cast<size_t>(b1)));
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(s2.x), "=r"(s2.y), "=r"(s2.z), "=r"(s2.w), "=r"(s3.x), "=r"(s3.y), "=r"(s3.z), "=r"(s3.w) : "l"(map.dslots + 2 * static_cast<size_t>(b2)));
     const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
     if (s0.x == klo && s0.y == khi) { centre = make_uint2(s0.z, s0.w); return static_cast<int>(2 * b1); }
     if (s1.x == klo && s1.y == khi) { centre = make_uint2(s1.z, s1.w); return static_cast<int>(2 * b1 + 1); }
@@ -120,16 +125,107 @@ struct Best {
     double d2 = kDblMax;
     uint32_t idx = 0xffffffffu;
 };
-// Stream `n` consecutive stored points starting at index idx0 and fold them into `b` (ascending index + strict <
-// keeps the first of equals).
-__device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, double px, double py, double pz, Best& b) {
-    const float4* __restrict__ p = pts + idx0;
-#pragma unroll 4
-    for (uint32_t o = 0; o < n; ++o) {
-        const float4 q = __ldg(p + o);
-        const double d2 = sq3_exact(static_cast<double>(q.x) - px, static_cast<double>(q.y) - py, static_cast<double>(q.z) - pz);
-        if (d2 < b.d2) { b.d2 = d2; b.idx = idx0 + o; }
+// One candidate: exact fp64 squared distance in the reference's association order, strict < (vhm.cpp:44-45).
+__device__ __forceinline__ void fold_point(float x, float y, float z, uint32_t idx, double px, double py, double pz, Best& b) {
+    const double d2 = sq3_exact(static_cast<double>(x) - px, static_cast<double>(y) - py, static_cast<double>(z) - pz);
+    if (d2 < b.d2) { b.d2 = d2; b.idx = idx; }
+}
+// 32-byte (two stored points) read-only load: sm_100 LDG.E.256.  With one lane per query every lane touches a different
+// 128-byte line, so the L1TEX tag stage — one line per cycle — bounds the search (measured: ~14.5 B/cycle/SM with 16-byte
+// loads, profiles/r01b_*); a 32-byte load moves twice the points per tag lookup.
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+// Stream `n` consecutive stored points starting at index idx0 and fold them into `b`, exactly (ascending index + strict <
+// keeps the first of equals).  The loads of one batch are issued TOGETHER, before any of them is consumed: addresses
+// past the run are clamped to its last element instead of being guarded by the loop condition, which would make every
+// load wait for the previous iteration's exit test (one load in flight per thread — what the compiler produced from the
+// plain `for (o < n)` loop whatever the unroll factor).  `pts` is padded by one element so that an aligned pair that
+// straddles the end of the array can be read.
+#ifndef ELM_BATCH
+#define ELM_BATCH 3
+#endif
+__device__ __forceinline__ void visit_points_exact(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, double px, double py, double pz, Best& b) {
+    if (n == 0) return;
+    const uint32_t end = idx0 + n;
+    constexpr uint32_t K = ELM_BATCH;  // 32-byte pairs per batch
+    const uint32_t last_pair = (end - 1) & ~1u;
+    for (uint32_t i = idx0 & ~1u; i < end; i += 2 * K) {
+        float4 q0[K], q1[K];
+#pragma unroll
+        for (uint32_t u = 0; u < K; ++u) ldg256(pts + min(i + 2 * u, last_pair), q0[u], q1[u]);
+#pragma unroll
+        for (uint32_t u = 0; u < K; ++u) {
+            const uint32_t pi = i + 2 * u;
+            if (pi >= idx0 && pi < end) fold_point(q0[u].x, q0[u].y, q0[u].z, pi, px, py, pz, b);
+            if (pi + 1 < end) fold_point(q1[u].x, q1[u].y, q1[u].z, pi + 1, px, py, pz, b);  // (pi + 1 >= idx0 always)
+        }
     }
+}
+
+// The query as the streaming loop needs it: exact fp64 position, its fp32 rounding and the width of the fp32 error band.
+struct Query {
+    double px, py, pz;
+    float fx, fy, fz;
+    float band;  // 2^-20 (|x| + |y| + |z|): bounds twice the error the fp32 rounding of the query adds to a distance
+    __device__ __forceinline__ Query(double x, double y, double z)
+        : px(x), py(y), pz(z), fx(static_cast<float>(x)), fy(static_cast<float>(y)), fz(static_cast<float>(z)) {
+        band = (fabsf(fx) + fabsf(fy) + fabsf(fz)) * 9.5367431640625e-07f;
+    }
+};
+
+// Same result as visit_points_exact — bit for bit — at about half the instructions: the run is scanned with fp32
+// distances (no F2F/DADD/DMUL per candidate), keeping the fp32 minimum m, its index and the SECOND smallest value s.
+// With r the true distance, u the fp32 difference vector and d the fp32 sum of squares:
+//   | |u| - r | <= 2^-24 (1 + 2^-24) |p| + 2^-24 r      (rounding of the query to fp32 + of the three subtractions)
+//   sqrt(d) in |u| [1 - 2^-23, 1 + 2^-23]               (FMUL + 2 FFMA, all terms >= 0)
+// hence a candidate j can only be at least as close as the fp32 argmin if sqrt(d_j) <= sqrt(m) (1 + 2^-21) + 2^-22 |p|.
+// If s lies outside that band (widened 2-4x below to absorb the float evaluation of the bound itself) the fp32 argmin is
+// the unique exact nearest point of the run and ONE exact fp64 distance is computed for it; otherwise (a near tie,
+// ~1e-3 of the runs on a 100 m map) the run is re-scanned exactly.
+__device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, const Query& Q, Best& b) {
+#ifdef ELM_EXACT_SCAN
+    visit_points_exact(pts, idx0, n, Q.px, Q.py, Q.pz, b);
+#else
+    if (n == 0) return;
+    const uint32_t end = idx0 + n;
+    constexpr uint32_t K = ELM_BATCH;
+    const uint32_t last_pair = (end - 1) & ~1u;
+    const float kInf = __int_as_float(0x7f800000);
+    float m = kInf, s2 = kInf;
+    uint32_t mi = idx0;
+    auto fold32 = [&](const float4& q, uint32_t pi, bool valid) {
+        const float dx = q.x - Q.fx, dy = q.y - Q.fy, dz = q.z - Q.fz;
+        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        d = valid ? d : kInf;
+        s2 = fminf(s2, fmaxf(d, m));
+        mi = (d < m) ? pi : mi;
+        m = fminf(m, d);
+    };
+    for (uint32_t i = idx0 & ~1u; i < end; i += 2 * K) {
+        float4 q0[K], q1[K];
+#pragma unroll
+        for (uint32_t u = 0; u < K; ++u) ldg256(pts + min(i + 2 * u, last_pair), q0[u], q1[u]);
+#pragma unroll
+        for (uint32_t u = 0; u < K; ++u) {
+            const uint32_t pi = i + 2 * u;
+            fold32(q0[u], pi, pi >= idx0 && pi < end);
+            fold32(q1[u], pi + 1, pi + 1 < end);
+        }
+    }
+    const float sm = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);            // sqrt(m) (1 + 2^-20) + band
+    const float T = fmaf(sm * sm, 1.000003814697265625f, 1e-30f);                  // (1 + 2^-18), + underflow slack
+    if (s2 > T) {  // (false for NaN / inf: those take the exact path)
+        const float4 q = __ldg(pts + mi);
+        const double d2 = sq3_exact(static_cast<double>(q.x) - Q.px, static_cast<double>(q.y) - Q.py, static_cast<double>(q.z) - Q.pz);
+        if (d2 < b.d2 || (d2 == b.d2 && mi < b.idx)) { b.d2 = d2; b.idx = mi; }
+    } else {
+        Best e;
+        visit_points_exact(pts, idx0, n, Q.px, Q.py, Q.pz, e);
+        if (e.idx != 0xffffffffu && (e.d2 < b.d2 || (e.d2 == b.d2 && e.idx < b.idx))) b = e;
+    }
+#endif
 }
 // folds a candidate found elsewhere (smaller distance wins, then smaller index)
 __device__ __forceinline__ void fold_best(Best& b, const Best& o) {
@@ -560,12 +656,20 @@ __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc
     __syncthreads();
 }
 
+#ifdef ELM_PHASE_TIMING
+#define ELM_ATICK(k) do { const long long t__ = clock64(); if (prm.stats && threadIdx.x == 0) atomicAdd(prm.stats + (k), static_cast<unsigned long long>(t__ - atick)); atick = t__; } while (0)
+#else
+#define ELM_ATICK(k) do { } while (0)
+#endif
 // Publish this block's sums and let the LAST block to arrive reduce all partials in a fixed order (bit-reproducible
 // whichever block is last) into st->acc and, when `solve_here`, run the solve/update step.
 __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)[kAcc], double* s_acc, bool* s_last, SolveScratch* s_solve,
                                             const double* s_T, IcpState* st, const IcpParams& prm, double* __restrict__ partials,
                                             unsigned int* __restrict__ ticket, int solve_here) {
     const int tid = threadIdx.x;
+#ifdef ELM_PHASE_TIMING
+    long long atick = clock64();
+#endif
     if (tid < kAcc) {
         double v = 0.0;
         if (tid < 29) v = s_sum[tid];
@@ -579,6 +683,7 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
         *s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
+    ELM_ATICK(12);
     if (!*s_last) return;
     __threadfence();
     {
@@ -604,10 +709,12 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
         s_acc[tid] = t;
     }
     __syncthreads();
+    ELM_ATICK(13);
     if (tid == 0) {
         *ticket = 0;
         if (solve_here) solve_step(st, prm, s_solve, s_acc, s_T);
     }
+    ELM_ATICK(14);
 }
 
 }  // namespace
@@ -630,14 +737,35 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
 //   C  merge            : atomicMin on the fp64 distance bits, then on the canonical index among the exact minima,
 //                         which reproduces the reference's first-in-visit-order tie-break (vhm.cpp:45).
 // COOP = false: every thread streams all 9 columns of its own query — the reference's exhaustive visit.
+#ifdef ELM_PHASE_TIMING
+#define ELM_USE(cond) do { if (__any_sync(__activemask(), (cond))) asm volatile(""); } while (0)
+#define ELM_TICK(k) do { const long long t__ = clock64(); if (prm.stats && (threadIdx.x & 31) == 0) atomicAdd(prm.stats + (k), static_cast<unsigned long long>(t__ - tick)); tick = t__; } while (0)
+#else
+#define ELM_TICK(k) do { } while (0)
+#define ELM_USE(cond) do { } while (0)
+#endif
 constexpr int kNoItem = 0xffff;
 constexpr int kItemCap = 1024;  // work items per tile kept in shared memory; overflow stays with its owner
+// Scope of the work-item list.  Warp scope (default): every warp shares out the items of ITS 32 queries among its own
+// lanes and only ever waits for itself (__syncwarp) — the warps of a block drift through the phases independently and hide
+// each other's load latency.  Block scope (-DELM_BLOCK_SCOPE): one list per tile and __syncthreads between the phases
+// (better balance, but every warp waits for the slowest one: 19 % of the stall samples were barrier waits).
+#ifdef ELM_BLOCK_SCOPE
+constexpr int kItemGroups = 1;
+#else
+constexpr int kItemGroups = kIcpWarps;
+#endif
+constexpr int kGroupCap = kItemCap / kItemGroups;
+constexpr int kGroupThreads = kIcpThreads / kItemGroups;
 
 // FUSE = 0 (P2P) / 1 (GICP): the tile's threads go straight on to linearise their correspondence (AlignCloudsLocal /
 // AlignCloudsLocalPointCov accumulation), the block tree-reduces, and the last block of the grid reduces all partials and
 // solves — ONE launch per ICP iteration, the matched point still hot in L1/L2.  FUSE = -1: search only (match[] out).
 template <bool COOP, int FUSE>
-__global__ void __launch_bounds__(kIcpThreads, FUSE == 1 ? 3 : 4)
+#ifndef ELM_MINBLOCKS
+#define ELM_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kIcpThreads, FUSE == 1 ? 3 : (FUSE == 0 ? 4 : ELM_MINBLOCKS))
 icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, IcpState* __restrict__ st,
                          int* __restrict__ match, double* __restrict__ partials, unsigned int* __restrict__ ticket, int solve_here) {
     constexpr bool kFuse = FUSE >= 0;
@@ -656,10 +784,15 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1];
     __shared__ unsigned int s_item_idx[COOP ? kItemCap : 1];
     __shared__ uint16_t s_items[COOP ? kItemCap : 1];
-    __shared__ int s_nitems;
+    __shared__ int s_nitems[kItemGroups];
 
     if (st->done) return;  // loop already left (termination / overlap failure)
     const int tid = threadIdx.x;
+    const int grp = tid / kGroupThreads, gtid = tid % kGroupThreads;  // item-list group of this thread and its rank in it
+    uint16_t* const g_items = s_items + (COOP ? grp * kGroupCap : 0);
+    unsigned long long* const g_item_d2 = s_item_d2 + (COOP ? grp * kGroupCap : 0);
+    unsigned int* const g_item_idx = s_item_idx + (COOP ? grp * kGroupCap : 0);
+    auto group_sync = [&]() { if (kItemGroups == 1) __syncthreads(); else __syncwarp(); };
     if (tid < 12) s_T[tid] = st->T[tid];
     if (kFuse) {
         if (tid < 12) s_Tinv[tid] = st->Tinv[tid];
@@ -689,7 +822,11 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int next = tile + gridDim.x;
         if (tid == 0 && next < ntiles && tile_tma_ok(next)) issue(next, buf ^ 1);  // prefetch the next tile
-        if (tid == 0) s_nitems = 0;
+#ifdef ELM_PHASE_TIMING
+        long long tick = clock64();
+        if (prm.stats && (tid & 31) == 0) atomicAdd(prm.stats + 8, 1ull);
+#endif
+        if (gtid == 0) s_nitems[grp] = 0;
         if (tile_tma_ok(tile)) {
             mbar_wait(&s_bar[buf], phase[buf]);
             phase[buf] ^= 1;
@@ -700,6 +837,7 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
         __syncthreads();
         const int cnt = tile_count(tile);
         const bool mine = tid < cnt;
+        ELM_TICK(2);
         // ---- phase A: one thread per query
         Best b;
         double px = 0, py = 0, pz = 0, sx = 0, sy = 0, sz = 0;
@@ -713,10 +851,22 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             py = row_apply_exact(s_T, 1, sx, sy, sz);
             pz = row_apply_exact(s_T, 2, sx, sy, sz);
             float fx, fy, fz;
-            const int kx = voxel_floor(px, map.voxel_size, &fx), ky = voxel_floor(py, map.voxel_size, &fy), kz = voxel_floor(pz, map.voxel_size, &fz);
+            const int kx = voxel_floor(px, map, &fx), ky = voxel_floor(py, map, &fy), kz = voxel_floor(pz, map, &fz);
             ++searched;
+#ifdef ELM_PHASE_TIMING
+            long long ftick = clock64();
+            ELM_USE(kx + ky + kz == 0x7fffffff);
+            { const long long t__ = clock64(); if (prm.stats && (tid & 31) == 0) atomicAdd(prm.stats + 16, static_cast<unsigned long long>(t__ - tick)); ftick = t__; }
+#endif
             uint2 centre;
             row = dir_lookup(map, kx, ky, kz, centre);
+#ifdef ELM_PHASE_TIMING
+            ELM_USE(row == 0x7fffffff);
+            { const long long t__ = clock64(); if (prm.stats && (tid & 31) == 0) atomicAdd(prm.stats + 17, static_cast<unsigned long long>(t__ - ftick)); ftick = t__; }
+#endif
+            const Query Q(px, py, pz);
+            ELM_USE(row == 0x7fffffff);
+            ELM_TICK(3);
             if (COOP) {
                 s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
                 s_win[tid] = 0xffffffffu;
@@ -727,27 +877,36 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                     const int ch = 3 * (hx + 1) + (hy + 1);
                     const uint2 hd = (ch == 4) ? centre : dir_column(map, row, ch);
                     uint32_t rs, rl;
-                    column_run(hd, 7u, rs, rl);
-                    visit_points(map.pts, rs, rl, px, py, pz, b);
+                    // phase A streams that voxel only (-DELM_HOME_COLUMN: its whole z-column — more candidates, fewer items;
+                    // measured 36.7 vs 35.1 us)
+#ifdef ELM_HOME_COLUMN
+                    const uint32_t hz = 7u;
+#else
+                    const uint32_t hz = (kz < 0) ? 4u : 2u;
+#endif
+                    column_run(hd, hz, rs, rl);
+                    visit_points(map.pts, rs, rl, Q, b);
                     visited += rl;
-                    own_cols = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up, 7u << (3 * ch));
+                    ELM_USE(b.d2 < 0.0);
+                    ELM_TICK(4);
+                    own_cols = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up, hz << (3 * ch));
                     s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
                     s_row[tid] = row;
                     int k = 0;
 #pragma unroll
                     for (int c = 0; c < 9; ++c) k += ((own_cols >> (3 * c)) & 7u) ? 1 : 0;
                     if (k) {
-                        const int pos = atomicAdd(&s_nitems, k);
-                        if (pos + k <= kItemCap) {  // hand the columns to the block; otherwise they stay with this thread
+                        const int pos = atomicAdd(&s_nitems[grp], k);
+                        if (pos + k <= kGroupCap) {  // hand the columns to the group; otherwise they stay with this thread
                             int w = pos;
 #pragma unroll
                             for (int c = 0; c < 9; ++c) {
                                 const uint32_t zm = (own_cols >> (3 * c)) & 7u;
-                                if (zm) s_items[w++] = static_cast<uint16_t>((tid << 7) | (c << 3) | zm);
+                                if (zm) g_items[w++] = static_cast<uint16_t>((tid << 7) | (c << 3) | zm);
                             }
                             own_cols = 0;
                         } else {
-                            for (int w = pos; w < kItemCap; ++w) s_items[w] = kNoItem;  // the tail of the list this claim straddles
+                            for (int w = pos; w < kGroupCap; ++w) g_items[w] = kNoItem;  // the tail of the list this claim straddles
                         }
                     }
                 }
@@ -757,27 +916,28 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                     const uint2 d = (c == 4) ? centre : dir_column(map, row, c);
                     uint32_t rs, rl;
                     column_run(d, 7u, rs, rl);
-                    visit_points(map.pts, rs, rl, px, py, pz, b);
+                    visit_points(map.pts, rs, rl, Q, b);
                     visited += rl;
                 }
                 my_match = (b.idx == 0xffffffffu) ? -1 : static_cast<int>(b.idx);
             }
         }
         if (COOP) {
-            __syncthreads();
+            group_sync();
+            ELM_TICK(5);
             // ---- phase B: one thread per (query, column) item
-            const int nitems = min(s_nitems, kItemCap);  // (items beyond the cap were never written: their owners kept them)
-            for (int j = tid; j < nitems; j += kIcpThreads) {
-                const int it = s_items[j];
+            const int nitems = min(s_nitems[grp], kGroupCap);  // (items beyond the cap were never written: their owners kept them)
+            for (int j = gtid; j < nitems; j += kGroupThreads) {
+                const int it = g_items[j];
                 if (it == kNoItem) continue;
                 const int q = it >> 7;
                 uint32_t rs, rl;
                 column_run(dir_column(map, s_row[q], (it >> 3) & 15), static_cast<uint32_t>(it & 7), rs, rl);
                 Best ib;
-                visit_points(map.pts, rs, rl, s_px[q], s_py[q], s_pz[q], ib);
+                visit_points(map.pts, rs, rl, Query(s_px[q], s_py[q], s_pz[q]), ib);
                 visited += rl;
-                s_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
-                s_item_idx[j] = ib.idx;
+                g_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
+                g_item_idx[j] = ib.idx;
                 if (ib.idx != 0xffffffffu) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
             }
             if (mine) {
@@ -789,24 +949,26 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                         uint32_t rs, rl;
                         column_run(dir_column(map, row, c), zm, rs, rl);
                         Best ob;
-                        visit_points(map.pts, rs, rl, px, py, pz, ob);
+                        visit_points(map.pts, rs, rl, Query(px, py, pz), ob);
                         visited += rl;
                         fold_best(b, ob);
                     }
                 }
                 if (b.idx != 0xffffffffu) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(b.d2)));
             }
-            __syncthreads();
+            group_sync();
+            ELM_TICK(6);
             // ---- phase C: among the exact minima the smallest canonical index wins
-            for (int j = tid; j < nitems; j += kIcpThreads) {
-                const int it = s_items[j];
+            for (int j = gtid; j < nitems; j += kGroupThreads) {
+                const int it = g_items[j];
                 if (it == kNoItem) continue;
                 const int q = it >> 7;
-                if (s_item_idx[j] != 0xffffffffu && s_item_d2[j] == s_best[q]) atomicMin(&s_win[q], s_item_idx[j]);
+                if (g_item_idx[j] != 0xffffffffu && g_item_d2[j] == s_best[q]) atomicMin(&s_win[q], g_item_idx[j]);
             }
             if (mine && b.idx != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
                 atomicMin(&s_win[tid], b.idx);
-            __syncthreads();
+            group_sync();
+            ELM_TICK(7);
             if (mine) my_match = (s_win[tid] == 0xffffffffu) ? -1 : static_cast<int>(s_win[tid]);
         }
         if (mine && match) {
@@ -848,7 +1010,7 @@ icp_search_means_kernel(MapView map, const float* __restrict__ scan, const int* 
     for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
         const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
         const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-        const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+        const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
         match[orig ? orig[i] : i] = nearest_mean_27(map, px, py, pz, kx, ky, kz);
     }
 }
@@ -867,9 +1029,14 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
     __shared__ bool s_last;
     if (st->done) return;
     const int tid = threadIdx.x;
+#ifdef ELM_PHASE_TIMING
+    long long atick = clock64();
+    if (prm.stats && tid == 0) atomicAdd(prm.stats + 15, 1ull);
+#endif
     if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
     if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
     __syncthreads();
+    ELM_ATICK(9);
 
     double acc[NACC];
 #pragma unroll
@@ -907,7 +1074,7 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
             if (j == 7) continue;
             const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
             const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+            int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
             kx += (j == 1) - (j == 2); ky += (j == 3) - (j == 4); kz += (j == 5) - (j == 6);
             if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) continue;
             double mx, my, mz;
@@ -937,7 +1104,9 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
     __shared__ double s_sum[kAcc], s_acc[kAcc];
     if (tid < kAcc) s_sum[tid] = 0.0;
     __syncthreads();
+    ELM_ATICK(10);
     block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);
+    ELM_ATICK(11);
     finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, partials, ticket, solve_here);
 }
 
@@ -975,7 +1144,7 @@ icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __rest
         if (i >= n) return;
         const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
         const double px = row_apply_exact(T, 0, sx, sy, sz), py = row_apply_exact(T, 1, sx, sy, sz), pz = row_apply_exact(T, 2, sx, sy, sz);
-        const int kx = voxel_floor(px, map.voxel_size), ky = voxel_floor(py, map.voxel_size), kz = voxel_floor(pz, map.voxel_size);
+        const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
         double* t = target + static_cast<size_t>(i) * 21;
         int c = 0;
         for (int j = 0; j < 7; ++j) {

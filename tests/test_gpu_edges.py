@@ -179,3 +179,40 @@ def test_full_size_properties():
     idx = np.random.default_rng(6).choice(len(scan), 4096, replace=False)
     oc, ot = O.correspondences(om, scan[idx], T, O.P2P, 5.0)
     assert np.array_equal(oc, c1[idx]) and np.array_equal(ot, t1[idx])
+
+
+@pytest.mark.parametrize("origin", [0.0, -8.0, 4096.0])
+@pytest.mark.parametrize("exhaustive", [False, True])
+def test_exact_ties_and_near_ties(origin, exhaustive):
+    """Lattice map + queries at cell / face / edge centres: many candidates at EXACTLY equal distance, so the winner is
+    decided by the reference's first-in-visit-order rule (strict <, voxel_hash_map.cpp:45); tiny offsets put further
+    queries inside and just outside the fp32 pre-filter's error band (wide at origin 4096).  Bit-exact vs the oracle."""
+    g = np.arange(16, dtype=np.float64) * 0.5 + 0.25
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(7)
+    raw = (lat[rng.permutation(len(lat))] + origin).astype(np.float32)
+    gm = E.VoxelHashMap(1.0, 30, device=0)
+    gm.AddPoints(raw)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    base = rng.integers(2, 13, size=(600, 3)).astype(np.float64) * 0.5 + 0.25      # a lattice point
+    kind = rng.integers(0, 4, size=600)
+    off = np.zeros((600, 3))
+    off[kind >= 1, 0] = 0.25                                                       # edge midpoint: 2 ties
+    off[kind >= 2, 1] = 0.25                                                       # face centre: 4 ties
+    off[kind >= 3, 2] = 0.25                                                       # cell centre: 8 ties
+    eps = rng.choice([0.0, 1e-7, -1e-7, 1e-6, 3e-5, -2e-4], size=(600, 3))
+    scan = (base + off + eps + origin).astype(np.float32)
+    reg = E.Registration(device=0)
+    reg.set_exhaustive(exhaustive)
+    for T in (I4, synth.se3([0.0, 0.0, 0.0], [0.0, 0.0, 0.0]) @ I4):
+        gc, gt = reg.correspondences(scan, gm, T, E.P2P, 5.0)
+        oc, ot = O.correspondences(om, scan, T, E.P2P, 5.0)
+        assert np.array_equal(gc, oc)
+        assert np.array_equal(gt, ot), np.flatnonzero((gt != ot).any(axis=(1, 2)))[:10]
+    # a pose that is not the identity: the transformed query is no longer an fp32 value
+    T = synth.se3([0.125 + origin * 1e-3, -0.25, 0.0625], [0.0, 0.0, np.pi / 2])
+    local = (np.linalg.inv(T) @ np.c_[scan.astype(np.float64), np.ones(len(scan))].T).T[:, :3].astype(np.float32)
+    gc, gt = reg.correspondences(local, gm, T, E.P2P, 5.0)
+    oc, ot = O.correspondences(om, local, T, E.P2P, 5.0)
+    assert np.array_equal(gc, oc) and np.array_equal(gt, ot)
