@@ -11,8 +11,12 @@ synthetic Scan-U against the 10 M-raw-point Map-U (BASELINE.md section 4, config
   roofline   dominant kernel (fused search+accumulate) : algorithmic bytes / its CUDA-event time vs measured HBM peak
   cpu_baseline   the oracle (structure-faithful CPU port of the reference) on the box's host cores, bounded sample
 
-N > 1 (torchrun): the scan is sharded over ranks, the map replicated, one ncclAllReduce of the 30 accumulators per
-iteration (strong scaling of the fixed 131 072-point scan).
+N > 1 (torchrun): the scan is sharded over ranks, the map replicated, and the 32 accumulators are all-reduced once per
+iteration — by default inside the accumulation kernel through peer-memory mailboxes over NVLink (--comm peer), or with
+ncclAllReduce + a separate solve launch (--comm nccl).  Default --scaling weak: every rank holds a 131 072-point shard of
+an N x 131 072-point scan, `value` = searches+accumulations/s / 131 072 (= ICP iterations/s of the metric's 128k-point
+scan; identical to plain iterations/s at N = 1); the strong-scaling figure of the fixed 131 072-point scan is measured in
+the same run and reported in config.strong_scaling.
 --impl reference: times the oracle port of the reference's CPU path (the reference itself cannot be built here:
 no Eigen/TBB/PCL/ROS), search parallel over host threads + serial accumulate exactly like the reference.
 """
@@ -51,6 +55,9 @@ def parse():
     ap.add_argument("--cpu-iters", type=int, default=2, help="ICP iterations per CPU-baseline sample")
     ap.add_argument("--fused", action="store_true", help="P2P/GICP: one fused search+accumulate+solve kernel per iteration")
     ap.add_argument("--binning", action="store_true", help="search the scan in spatially binned order")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="N > 1: how the accumulators are all-reduced")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = n-scan points PER RANK (default), strong = n-scan points in total")
     ap.add_argument("--exhaustive", action="store_true",
                     help="visit all 27 voxels like the reference instead of the exact-pruning search")
     return ap.parse_args()
@@ -203,7 +210,7 @@ def main():
                   f"{r['threads']} OpenMP threads for the search, serial accumulate as in the reference")
         out = {"impl": "reference", "metric": "icp_iterations_per_sec", "value": r["value"], "unit": "iterations/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+               "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": "port",
                                 "sample": sample},
@@ -240,19 +247,28 @@ def main():
     reg.set_binning(args.binning)
     reg.set_fused(args.fused)
     if world > 1:
-        ids = [E.Registration.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        reg.set_comm(ids[0], rank, world)
+        if args.comm == "peer":
+            reg.peer_setup(dist)
+        else:
+            ids = [E.Registration.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            reg.set_comm(ids[0], rank, world)
 
     # a different scan per step so that no step re-reads what the previous one left in L2; all resident in HBM
     n_variants = 4
     scans_full = [synth.scan_u(args.n_scan, half, seed=synth.SEED_SCAN + i) for i in range(n_variants)]
     lo = args.n_scan * rank // world
     hi = args.n_scan * (rank + 1) // world
-    shards = [np.ascontiguousarray(s[lo:hi]) for s in scans_full]
+    strong_shards = [np.ascontiguousarray(s[lo:hi]) for s in scans_full]
+    weak = world > 1 and args.scaling == "weak"
+    if weak:   # every rank owns a full-size shard of an N-times larger scan
+        shards = [synth.scan_u(args.n_scan, half, seed=synth.SEED_SCAN + i + 1000 * rank) for i in range(n_variants)]
+    else:
+        shards = strong_shards
     d_scans = [torch.from_numpy(s).cuda() for s in shards]
     h_scans = [torch.from_numpy(s).pin_memory() for s in shards]
-    n_local = hi - lo
+    n_local = len(shards[0])
+    n_global = n_local * world if weak else args.n_scan
     cfg = E.RegistrationConfig(icp_method=method, max_iteration=args.iters, **synth.timing_knobs())
 
     def barrier():
@@ -298,7 +314,26 @@ def main():
         reg.set_stats(False)
         visited_per_search = vis / max(nq, 1)
     iters_total = args.steps * args.iters
-    value = iters_total / (ms_total * 1e-3)
+    # ICP iterations/s of the metric's n-scan-point scan: (points searched + accumulated per second) / n-scan
+    units = n_global / args.n_scan
+    value = units * iters_total / (ms_total * 1e-3)
+
+    # N > 1, weak: the strong-scaling figure of the fixed n-scan-point scan, measured the same way
+    strong = None
+    if weak:
+        ds = [torch.from_numpy(s).cuda() for s in strong_shards]
+        for i in range(args.warmup):
+            reg.enqueue(ds[i % n_variants].data_ptr(), hi - lo, gmap, T_init, cfg)
+        reg.fetch()
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            reg.enqueue(ds[i % n_variants].data_ptr(), hi - lo, gmap, T_init, cfg)
+        e1.record(stream)
+        barrier()
+        reg.fetch()
+        strong = {"iterations_per_sec": iters_total / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3), "n_scan_total": args.n_scan,
+                  "points_per_rank": hi - lo}
 
     # ---- end-to-end arm: host buffers through elm_run_register (H2D of the scan + D2H of the result every step)
     import ctypes as C
@@ -323,7 +358,7 @@ def main():
     e1.record(stream)
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = iters_total / (e2e_ms * 1e-3)
+    e2e_value = units * iters_total / (e2e_ms * 1e-3)
     state_bytes = 16 * 8 * 2 + 9 * 8 + 32 * 8 + 36 * 8 + 6 * 8 + 3 * 8 + 36 * 8 + 16  # sizeof(IcpState)
 
     # ---- roofline of the dominant kernel (rank 0's shard)
@@ -375,10 +410,16 @@ def main():
     if rank == 0:
         out = {"metric": "icp_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": dict(config, parallelism=f"scan sharded over {world} GPU(s), map replicated",
+               "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": dict(config, parallelism=f"scan sharded over {world} GPU(s) ({n_local} points per rank, {n_global} in total), "
+                                                  f"map replicated, accumulators all-reduced per iteration via "
+                                                  f"{'peer-memory mailboxes inside the accumulation kernel' if args.comm == 'peer' else 'ncclAllReduce'}"
+                                                  if world > 1 else "1 GPU",
+                              value_definition="ICP iterations/s of the n_scan-point scan = (searches+accumulations per second) / n_scan",
+                              strong_scaling=strong,
                               l2_policy="inputs larger than L2 (map + table > 126 MB) and a different scan every step",
-                              searches_per_sec=value * args.n_scan, map_build_s=build_s,
+                              searches_per_sec=value * args.n_scan, n_scan_global=n_global, map_build_s=build_s,
                               stored_points=int(ex["counts"].sum()), voxels=int(len(ex["counts"])),
                               iterations_run_last_step=res[4], success_last_step=res[1]),
                "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": n_local * 12,

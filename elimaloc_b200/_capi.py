@@ -109,6 +109,9 @@ SIGNATURES = {
     "elm_ekf_get_current_state": (C.c_int, [C.c_void_p, _dp]),
     "elm_comm_unique_id": (C.c_int, [_u8p]),
     "elm_registration_set_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
+    "elm_registration_peer_export": (C.c_int, [C.c_void_p, _u8p]),
+    "elm_registration_peer_attach": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
+    "elm_registration_peer_detach": (C.c_int, [C.c_void_p]),
 }
 
 _LIB = None

@@ -199,10 +199,17 @@ struct elm_registration {
     // NCCL
     void* comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory exchange (CUDA IPC mailboxes, see icp_device.cuh)
+    elm::PeerMailbox* d_mailbox = nullptr;
+    elm::PeerComm peer{};          // peer.world > 0: the accumulate kernel's last block all-reduces over the ranks itself
+    void* peer_opened[elm::kMaxPeers] = {};
+    bool sharded() const { return comm != nullptr || peer.world > 0; }
 
     ~elm_registration() {
         cudaSetDevice(device);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        for (void* p : peer_opened) if (p) cudaIpcCloseMemHandle(p);
+        cudaFree(d_mailbox);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_ticket); cudaFree(d_stats);
         cudaFree(d_dtable); cudaFreeHost(h_dtable); cudaFree(d_dsk_in); cudaFree(d_dsk_out);
@@ -308,6 +315,7 @@ elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg,
     p.term_thr = cfg->icp_termination_threshold_m;
     p.min_overlap = cfg->min_overlap_ratio;
     p.stats = r->stats_on ? r->d_stats : nullptr;
+    p.peer = r->peer;
     return p;
 }
 
@@ -331,7 +339,9 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
         }
         ELM_CUDA(cudaEventRecord(r->ev[r->ev_used], r->stream));
     }
-    const int solve_here = (solve && !r->comm) ? 1 : 0;
+    // peer mode: the exchange happens inside the kernel, then the solve; NCCL mode: allreduce + separate solve launch below
+    const bool use_nccl = r->comm != nullptr && r->peer.world == 0;
+    const int solve_here = (solve && !use_nccl) ? 1 : 0;
     if (prm.method != ELM_AVGICP) {
         ELM_CUDA(elm::launch_icp_search(map->view(), r->use_sorted ? r->d_sorted : d_scan, r->use_sorted ? r->d_orig : nullptr, prm, r->d_state,
                                         (fuse && !r->keep_match) ? nullptr : r->d_match, sgrid, r->prune, fuse ? 1 : 0, r->d_partials, r->d_ticket,
@@ -347,7 +357,7 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
         ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 2], r->stream));
         r->ev_used += 3;
     }
-    if (r->comm) {
+    if (use_nccl) {
         const int e = g_nccl.AllReduce(r->d_state->acc, r->d_state->acc, elm::kAcc, kNcclFloat64, kNcclSum, r->comm, r->stream);
         if (e != 0) return fail(ELM_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(e));
         r->launches += 1;
@@ -540,7 +550,7 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     reg->pending = true;
     // reg.cpp:291-295 (empty map) and the n == 0 guard: nothing to run.  In the sharded mode a rank with an empty shard
     // still has to take part in the allreduces, so only the single-rank case short-circuits on n == 0.
-    reg->trivial = map->host.vkey.empty() || (n == 0 && !reg->comm);
+    reg->trivial = map->host.vkey.empty() || (n == 0 && !reg->sharded());
     if (reg->trivial) return ELM_OK;
     const elm::IcpParams prm = make_params(reg, cfg, n);
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->d_ticket, reg->stream));
@@ -571,6 +581,7 @@ int elm_register_fetch(elm_registration* reg, double T_out[16], int32_t* is_succ
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
     if (reg->profiling) collect_profile(reg);
     const elm::IcpState& st = *reg->h_state;
+    if (st.comm_error) return fail(ELM_ERR_NCCL, "peer-memory exchange timed out: a rank never delivered its accumulators");
     std::memcpy(T_out, st.T, 16 * sizeof(double));
     if (local_cov) std::memcpy(local_cov, st.local_cov, 36 * sizeof(double));
     if (iterations_run) *iterations_run = st.iterations;
@@ -614,7 +625,7 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     std::memset(JTr, 0, 6 * sizeof(double));
     *residual_sum = 0.0;
     *n_corr = 0;
-    if (map->host.vkey.empty() || (n == 0 && !reg->comm)) return ELM_OK;
+    if (map->host.vkey.empty() || (n == 0 && !reg->sharded())) return ELM_OK;
     rc = ensure_scan(reg, n);
     if (rc) return rc;
     if (n) ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
@@ -901,6 +912,61 @@ int elm_registration_set_comm(elm_registration* reg, const uint8_t unique_id[128
     if (e != 0) { reg->comm = nullptr; return fail(ELM_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(e)); }
     reg->rank = rank;
     reg->world = world_size;
+    return ELM_OK;
+}
+
+int elm_registration_peer_export(elm_registration* reg, uint8_t handle[64]) {
+    if (!reg || !handle) return fail(ELM_ERR_INVALID, "elm_registration_peer_export: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (!reg->d_mailbox) {
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_mailbox), sizeof(elm::PeerMailbox)));
+        ELM_CUDA(cudaMemset(reg->d_mailbox, 0, sizeof(elm::PeerMailbox)));
+    }
+    cudaIpcMemHandle_t h;
+    ELM_CUDA(cudaIpcGetMemHandle(&h, reg->d_mailbox));
+    std::memcpy(handle, &h, 64);
+    return ELM_OK;
+}
+
+int elm_registration_peer_attach(elm_registration* reg, const uint8_t* handles, int rank, int world_size) {
+    if (!reg || world_size < 1 || world_size > elm::kMaxPeers || rank < 0 || rank >= world_size || (world_size > 1 && !handles))
+        return fail(ELM_ERR_INVALID, "elm_registration_peer_attach: bad argument (1 <= world_size <= 8)");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (!reg->d_mailbox) {
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_mailbox), sizeof(elm::PeerMailbox)));
+    }
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    ELM_CUDA(cudaMemset(reg->d_mailbox, 0, sizeof(elm::PeerMailbox)));
+    for (void*& p : reg->peer_opened) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
+    elm::PeerComm pc{};
+    pc.rank = rank;
+    pc.world = world_size;
+    for (int r = 0; r < world_size; ++r) {
+        if (r == rank) { pc.box[r] = reg->d_mailbox; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * r, 64);
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ELM_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        }
+        reg->peer_opened[r] = ptr;
+        pc.box[r] = static_cast<elm::PeerMailbox*>(ptr);
+    }
+    reg->peer = pc;
+    reg->rank = rank;
+    reg->world = world_size;
+    return ELM_OK;
+}
+
+int elm_registration_peer_detach(elm_registration* reg) {
+    if (!reg) return fail(ELM_ERR_INVALID, "null registration");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    for (void*& p : reg->peer_opened) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
+    reg->peer = elm::PeerComm{};
     return ELM_OK;
 }
 

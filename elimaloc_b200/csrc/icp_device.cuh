@@ -35,6 +35,22 @@ constexpr int kAcc = 32;       // accumulator vector: 21 JtJ (upper, row-major) 
 constexpr int kAccUsed = 30;
 constexpr int kIdxJtr = 21, kIdxRes = 27, kIdxNcorr = 28, kIdxNtotal = 29;
 
+// Peer-memory exchange of the accumulators (multi-GPU): every rank owns one mailbox in its HBM, mapped into the other
+// ranks' address spaces (CUDA IPC over NVLink).  Rank r writes its 32 sums straight into slot [parity][r] of EVERY
+// mailbox and then raises flag [parity][r] = sequence number; each rank waits for all flags of its own mailbox and sums
+// the slots in rank order — bit-identical on all ranks, no broadcast, no separate collective launch.
+constexpr int kMaxPeers = 8;
+struct PeerMailbox {
+    double acc[2][kMaxPeers][kAcc];
+    unsigned long long flag[2][kMaxPeers];
+    unsigned long long seq;  // exchanges completed by the owner (all ranks advance in lockstep)
+};
+struct PeerComm {
+    PeerMailbox* box[kMaxPeers];  // box[rank] is the local one
+    int rank;
+    int world;                    // 0: no peer exchange
+};
+
 struct IcpParams {
     int method;
     int n;              // scan points of THIS rank
@@ -44,6 +60,7 @@ struct IcpParams {
     double lm_lambda;
     double term_thr;
     double min_overlap;
+    PeerComm peer;
     unsigned long long* stats;  // optional: [0] += map points visited by the search, [1] += queries (NULL = off)
 };
 
@@ -62,7 +79,7 @@ struct IcpState {
     int iterations;     // AlignClouds* calls executed
     int done;           // loop left (termination, overlap failure)
     int overlap_fail;   // reg.cpp:352-356
-    int pad;
+    int comm_error;     // the peer exchange timed out (a rank never arrived)
 };
 
 }  // namespace elm

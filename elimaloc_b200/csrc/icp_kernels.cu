@@ -710,6 +710,46 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
     }
     __syncthreads();
     ELM_ATICK(13);
+    if (prm.peer.world > 0) {
+        // ---- all-reduce over the ranks through peer memory (NVLink stores into every rank's mailbox), fused into this kernel
+        const PeerComm& pc = prm.peer;
+        PeerMailbox* mine = pc.box[pc.rank];
+        __shared__ unsigned long long s_seq;
+        __shared__ int s_timeout;
+        if (tid == 0) { s_seq = *reinterpret_cast<volatile unsigned long long*>(&mine->seq) + 1; s_timeout = 0; }
+        __syncthreads();
+        const unsigned long long seq = s_seq;
+        const int par = static_cast<int>(seq & 1);
+        if (tid < pc.world * kAcc) {
+            const int p = tid / kAcc, k = tid % kAcc;
+            *reinterpret_cast<volatile double*>(&pc.box[p]->acc[par][pc.rank][k]) = s_acc[k];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < pc.world) {
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&pc.box[tid]->flag[par][pc.rank]), "l"(seq) : "memory");
+            const long long t0 = clock64();
+            unsigned long long f;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&mine->flag[par][tid]) : "memory");
+                if (f >= seq) break;
+                if (clock64() - t0 > 6000000000ll) { s_timeout = 1; break; }  // ~3 s: a rank died; give up instead of hanging the GPU
+            }
+        }
+        __syncthreads();
+        if (tid < kAcc) {
+            double t = 0.0;
+            for (int r = 0; r < pc.world; ++r) t += *reinterpret_cast<volatile double*>(&mine->acc[par][r][tid]);  // rank order: identical on every rank
+            st->acc[tid] = t;
+            s_acc[tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(&mine->seq) = seq;
+            if (s_timeout) { st->comm_error = 1; st->done = 1; }
+        }
+        if (s_timeout) { if (tid == 0) *ticket = 0; return; }
+    }
     if (tid == 0) {
         *ticket = 0;
         if (solve_here) solve_step(st, prm, s_solve, s_acc, s_T);
@@ -1118,7 +1158,7 @@ __global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket) 
         for (int i = 0; i < 16; ++i) st->T[i] = T0.m[i];
         refresh_inverses(st);
         for (int i = 0; i < 36; ++i) st->local_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;  // reg.cpp:280
-        st->iterations = 0; st->done = 0; st->overlap_fail = 0;
+        st->iterations = 0; st->done = 0; st->overlap_fail = 0; st->comm_error = 0;
         *ticket = 0;
     }
 }

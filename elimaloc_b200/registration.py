@@ -250,3 +250,27 @@ class Registration:
     def set_comm(self, unique_id, rank, world_size):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(lib().elm_registration_set_comm(self._h, buf, int(rank), int(world_size)))
+
+    def peer_export(self):
+        """64-byte CUDA IPC handle of this rank's accumulator mailbox (elm_registration_peer_export)."""
+        buf = (C.c_uint8 * 64)()
+        check(lib().elm_registration_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_attach(self, handles, rank, world_size):
+        """handles: world_size handles in rank order (this rank's own entry is ignored)."""
+        flat = b"".join(handles)
+        assert len(flat) == 64 * world_size
+        buf = (C.c_uint8 * len(flat)).from_buffer_copy(flat)
+        check(lib().elm_registration_peer_attach(self._h, buf, int(rank), int(world_size)))
+
+    def peer_detach(self):
+        check(lib().elm_registration_peer_detach(self._h))
+
+    def peer_setup(self, dist):
+        """Export / all-gather / attach over an initialised torch.distributed process group, then barrier."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        handles = [None] * world
+        dist.all_gather_object(handles, self.peer_export())
+        self.peer_attach(handles, rank, world)
+        dist.barrier()

@@ -255,6 +255,18 @@ int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]);
 int elm_comm_unique_id(uint8_t unique_id[128]);
 int elm_registration_set_comm(elm_registration* reg, const uint8_t unique_id[128], int rank, int world_size);
 
+/* Peer-memory exchange (preferred on one NVLink/NVSwitch box): instead of ncclAllReduce + a separate solve launch, the
+ * last block of the accumulation kernel writes its 32 sums into a mailbox of EVERY rank (CUDA IPC mapping, NVLink stores),
+ * waits for the other ranks' flags and sums the mailbox slots in rank order, then solves — one kernel, no collective launch.
+ *   1. every rank: elm_registration_peer_export -> 64-byte cudaIpcMemHandle of its mailbox
+ *   2. exchange the handles (any host transport; the tests use torch.distributed all_gather)
+ *   3. every rank: elm_registration_peer_attach(handles[world_size][64], rank, world_size), then a host barrier
+ * world_size <= 8.  A rank that never arrives makes the others time out after ~3 s (ELM_ERR_NCCL) instead of hanging.
+ * Takes precedence over elm_registration_set_comm while attached. */
+int elm_registration_peer_export(elm_registration* reg, uint8_t handle[64]);
+int elm_registration_peer_attach(elm_registration* reg, const uint8_t* handles, int rank, int world_size);
+int elm_registration_peer_detach(elm_registration* reg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,24 @@ def test_comm_path_world_size_one_equals_fused_path(small):
     assert oka == okb and np.array_equal(Ta, Tb) and fa == fb and np.array_equal(ca, cb)
 
 
+@pytest.mark.parametrize("method", [E.P2P, E.AVGICP])
+def test_peer_exchange_world_size_one_equals_fused_path(small, method):
+    """elm_registration_peer_attach with a single rank runs the in-kernel mailbox exchange (write own slot, raise and
+    wait for the flag, sum the slots) before the solve; the results must equal the plain single-GPU path bit for bit."""
+    scan = synth.scan_m(small["stored"], 3000, small["T_true"])
+    cfg = E.RegistrationConfig(icp_method=method, max_iteration=6, **synth.timing_knobs())
+    a = E.Registration(device=0)
+    b = E.Registration(device=0)
+    b.peer_attach([b.peer_export()], 0, 1)
+    for _ in range(2):  # twice: the mailbox sequence number keeps counting across calls
+        Ta, oka, fa, ca = a.RunRegister(scan, small["gm"], small["T0"], cfg)
+        Tb, okb, fb, cb = b.RunRegister(scan, small["gm"], small["T0"], cfg)
+        assert oka == okb and np.array_equal(Ta, Tb) and fa == fb and np.array_equal(ca, cb)
+    b.peer_detach()
+    Tb, okb, fb, cb = b.RunRegister(scan, small["gm"], small["T0"], cfg)
+    assert np.array_equal(Ta, Tb)
+
+
 @pytest.mark.parametrize("method", [E.P2P, E.GICP])
 def test_fused_kernel_matches_two_kernel_path(small, method):
     """elm_registration_set_fused(1): one kernel per iteration; sums equal the default path to rounding"""

@@ -1,0 +1,47 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): the scan sharded over 2 ranks with the accumulators
+all-reduced through peer memory (or NCCL) must give every rank the SAME bits, and the same registration as one GPU over
+the whole scan up to the summation order of the shards (1e-9)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import elimaloc_b200 as E
+from elimaloc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("comm", ["peer", "nccl"])
+@pytest.mark.parametrize("method", [E.P2P, E.VGICP])
+def test_two_ranks_match_one_gpu(tmp_path, comm, method):
+    if E.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = 29500 + (os.getpid() + 7 * method + (3 if comm == "peer" else 0)) % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(tmp_path), comm, str(method)]
+    subprocess.run(cmd, check=True, timeout=600, cwd=ROOT)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for k in ("T", "fit", "cov", "JTJ", "JTr", "n_corr", "residual_sum"):
+        assert np.array_equal(r0[k], r1[k]), k  # bit-identical on every rank: same sums in the same (rank) order
+    assert np.array_equal(r0["T"][0], r0["T"][1]) and np.array_equal(r0["T"][0], r0["T"][2])  # run-to-run reproducible
+    # one GPU, whole scan
+    raw = synth.map_u(60_000, 16.0, origin=-4.0)
+    gm = E.VoxelHashMap(1.0, 30, device=0)
+    gm.AddPoints(raw)
+    gm.CalVoxelCovAll()
+    gm.CalPointCovAll(0.4)
+    T_true = synth.se3([2.0, 3.0, 2.5], [0.01, -0.02, 0.2])
+    scan = synth.scan_m(gm.Pointcloud(), 6001, T_true)
+    T0 = T_true @ synth.canonical_offset()
+    reg = E.Registration(device=0)
+    cfg = E.RegistrationConfig(icp_method=method, max_iteration=8, **synth.timing_knobs())
+    T, ok, fit, cov = reg.RunRegister(scan, gm, T0, cfg)
+    lin = reg.linearize(scan, gm, T0, cfg)
+    assert lin["n_corr"] == int(r0["n_corr"])
+    assert np.abs(lin["JTJ"] - r0["JTJ"]).max() <= 1e-9 * np.abs(lin["JTJ"]).max()
+    assert np.abs(T - r0["T"][0]).max() <= 1e-9 * np.abs(T).max()
+    assert bool(r0["ok"]) == ok and abs(float(r0["fit"]) - fit) <= 1e-9 * max(1.0, abs(fit))
