@@ -20,6 +20,9 @@
 #include "icp_kernels.cuh"
 #include "voxel_key.hpp"
 
+#include <cstdlib>
+#include <utility>
+
 namespace elm {
 
 namespace {
@@ -50,6 +53,15 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Every kernel of the ICP loop is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its blocks may become
+// resident while the previous kernel of the stream is still finishing (for the search: while the last block of the
+// accumulation reduces and solves), run their prologue — barrier init, TMA of the first scan tile — and then block in
+// pdl_wait() until the previous grid has completed and its memory is visible.  NOTHING written by an earlier kernel may
+// be read (and nothing it reads may be written) before pdl_wait().  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- exact helpers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double sq3_exact(double dx, double dy, double dz) {  // (dx^2 + dy^2) + dz^2, no FMA
@@ -826,20 +838,15 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     __shared__ uint16_t s_items[COOP ? kItemCap : 1];
     __shared__ int s_nitems[kItemGroups];
 
-    if (st->done) return;  // loop already left (termination / overlap failure)
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int grp = tid / kGroupThreads, gtid = tid % kGroupThreads;  // item-list group of this thread and its rank in it
     uint16_t* const g_items = s_items + (COOP ? grp * kGroupCap : 0);
     unsigned long long* const g_item_d2 = s_item_d2 + (COOP ? grp * kGroupCap : 0);
     unsigned int* const g_item_idx = s_item_idx + (COOP ? grp * kGroupCap : 0);
     auto group_sync = [&]() { if (kItemGroups == 1) __syncthreads(); else __syncwarp(); };
-    if (tid < 12) s_T[tid] = st->T[tid];
-    if (kFuse) {
-        if (tid < 12) s_Tinv[tid] = st->Tinv[tid];
-        if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
-        if (tid < kAcc) s_sum[tid] = 0.0;
-    }
 
+    // ---- prologue that does not depend on the previous kernel: barriers + the TMA of the first scan tile
     constexpr int tile_pts = kIcpThreads;
     const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
@@ -858,7 +865,20 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     uint32_t visited = 0, searched = 0;
     int tile = blockIdx.x, buf = 0;
     uint32_t phase[2] = {0, 0};
-    if (tile < ntiles && tid == 0 && tile_tma_ok(tile)) issue(tile, 0);
+    const bool first_by_tma = tile < ntiles && tile_tma_ok(tile);
+    if (first_by_tma && tid == 0) issue(tile, 0);
+    // ---- from here on the previous kernel's results (pose, done flag) are read, and match[] is written
+    pdl_wait();
+    if (st->done) {  // loop already left (termination / overlap failure)
+        if (first_by_tma) mbar_wait(&s_bar[0], 0);  // the bulk copy must land before the block's shared memory is released
+        return;
+    }
+    if (tid < 12) s_T[tid] = st->T[tid];
+    if (kFuse) {
+        if (tid < 12) s_Tinv[tid] = st->Tinv[tid];
+        if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+        if (tid < kAcc) s_sum[tid] = 0.0;
+    }
     for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int next = tile + gridDim.x;
         if (tid == 0 && next < ntiles && tile_tma_ok(next)) issue(next, buf ^ 1);  // prefetch the next tile
@@ -1043,6 +1063,8 @@ __global__ void __launch_bounds__(kIcpThreads, 4)
 icp_search_means_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, const IcpState* __restrict__ st,
                         int* __restrict__ match) {
     __shared__ double s_T[12];
+    pdl_launch_dependents();
+    pdl_wait();
     if (st->done) return;
     const int tid = threadIdx.x;
     if (tid < 12) s_T[tid] = st->T[tid];
@@ -1067,6 +1089,8 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
     __shared__ double s_red[kIcpWarps][kAcc];
     __shared__ SolveScratch s_solve;
     __shared__ bool s_last;
+    pdl_launch_dependents();
+    pdl_wait();
     if (st->done) return;
     const int tid = threadIdx.x;
 #ifdef ELM_PHASE_TIMING
@@ -1166,6 +1190,8 @@ __global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket) 
 __global__ void icp_solve_kernel(IcpState* st, IcpParams prm) {
     __shared__ SolveScratch s_solve;
     __shared__ double s_acc[kAcc], s_T[12];
+    pdl_launch_dependents();
+    pdl_wait();
     if (st->done) return;
     if (threadIdx.x < kAcc) s_acc[threadIdx.x] = st->acc[threadIdx.x];
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->T[threadIdx.x];
@@ -1218,6 +1244,9 @@ icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __rest
 // ======================================================================================================================
 // launch wrappers
 // ======================================================================================================================
+// developer switch: ELM_NO_PDL=1 launches every kernel fully serialised
+static const bool g_use_pdl = [] { const char* e = getenv("ELM_NO_PDL"); return !(e && e[0] == '1'); }();
+
 int icp_search_grid(const IcpParams& prm, int num_sms) {
     int blocks;
     if (prm.method <= 1) {
@@ -1236,6 +1265,24 @@ int icp_accumulate_grid(const IcpParams& prm, int num_sms) {
     return blocks < 1 ? 1 : (blocks > cap ? cap : static_cast<int>(blocks));
 }
 
+namespace {
+// launch with programmatic stream serialization (see pdl_wait above)
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+}  // namespace
+
 cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, cudaStream_t s) {
     Pose16 p;
     for (int i = 0; i < 16; ++i) p.m[i] = T0[i];
@@ -1246,32 +1293,34 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
 // fuse: linearise + reduce (+ solve when solve_here) inside the search kernel (P2P / GICP only); then `match` may be NULL
 cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, int* match,
                               int grid, int prune, int fuse, double* partials, unsigned int* ticket, int solve_here, cudaStream_t s) {
+    cudaError_t e = cudaSuccess;
     if (prm.method <= 1) {
-#define ELM_LAUNCH(C, F) icp_search_points_kernel<C, F><<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match, partials, ticket, solve_here)
+#define ELM_LAUNCH(C, F) e = launch_pdl(icp_search_points_kernel<C, F>, grid, kIcpThreads, s, map, scan, orig, prm, st, match, partials, ticket, solve_here)
         if (!fuse) { if (prune) ELM_LAUNCH(true, -1); else ELM_LAUNCH(false, -1); }
         else if (prm.method == 0) { if (prune) ELM_LAUNCH(true, 0); else ELM_LAUNCH(false, 0); }
         else { if (prune) ELM_LAUNCH(true, 1); else ELM_LAUNCH(false, 1); }
 #undef ELM_LAUNCH
     } else if (prm.method == 2) {
-        icp_search_means_kernel<<<grid, kIcpThreads, 0, s>>>(map, scan, orig, prm, st, match);
+        e = launch_pdl(icp_search_means_kernel, grid, kIcpThreads, s, map, scan, orig, prm, static_cast<const IcpState*>(st), match);
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const int* match, const IcpParams& prm, IcpState* st, double* partials,
                                   unsigned int* ticket, int solve_here, int grid, cudaStream_t s) {
+    cudaError_t e = cudaSuccess;
     switch (prm.method) {
-        case 0: icp_accumulate_kernel<0><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
-        case 1: icp_accumulate_kernel<1><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
-        case 2: icp_accumulate_kernel<2><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
-        default: icp_accumulate_kernel<3><<<grid, kIcpThreads, 0, s>>>(map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 0: e = launch_pdl(icp_accumulate_kernel<0>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 1: e = launch_pdl(icp_accumulate_kernel<1>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 2: e = launch_pdl(icp_accumulate_kernel<2>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        default: e = launch_pdl(icp_accumulate_kernel<3>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s) {
-    icp_solve_kernel<<<1, 32, 0, s>>>(st, prm);
-    return cudaGetLastError();
+    const cudaError_t e = launch_pdl(icp_solve_kernel, 1, 32, s, st, prm);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_icp_export(const MapView& map, const float* scan, const int* match, int n, const IcpState* st, int method, double max_dist2,

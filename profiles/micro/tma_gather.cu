@@ -51,6 +51,22 @@ __global__ void __launch_bounds__(kThreads) gather(const float4* __restrict__ pt
             }
             asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
             __syncwarp();
+        } else if (MODE == 3) {  // warp-cooperative coalesced LDG.128 -> STS.128, 8 runs in flight per lane
+            for (int q0 = 0; q0 < 32; q0 += 8) {
+                uint32_t sq[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sq[u] = __shfl_sync(0xffffffffu, s, q0 + u);
+                for (int o = lane; o < run_pts; o += 32) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        v[u] = (warp * 32 + q0 + u < runs_per_round) ? __ldg(pts + sq[u] + o) : make_float4(0, 0, 0, 0);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (warp * 32 + q0 + u < runs_per_round) pool[(warp * 32 + q0 + u) * run_pts + o] = v[u];
+                }
+            }
+            __syncwarp();
         }
         if (active) {
             if (MODE == 2) {
@@ -61,7 +77,8 @@ __global__ void __launch_bounds__(kThreads) gather(const float4* __restrict__ pt
                 for (int o = 0; o < run_pts; ++o) { const float4 q = pool[tid * run_pts + o]; acc += q.x * q.y + q.z; }
             }
         }
-        if (MODE != 2) __syncthreads();
+        if (MODE == 0 || MODE == 1) __syncthreads();
+        if (MODE == 3) __syncwarp();
     }
     out[blockIdx.x * kThreads + tid] = acc;
 }
@@ -71,12 +88,12 @@ int main(int argc, char** argv) {
     std::vector<float4> h(npts);
     for (size_t i = 0; i < npts; ++i) h[i] = make_float4(float(i & 255), 1.f, 2.f, 0.f);
     float4* d_pts; cudaMalloc(&d_pts, npts * sizeof(float4)); cudaMemcpy(d_pts, h.data(), npts * sizeof(float4), cudaMemcpyHostToDevice);
-    const int blocks_per_sm_list[] = {1, 2, 3};
+    const int blocks_per_sm_list[] = {3, 4};
     const int rounds = 16;
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
     const int sms = prop.multiProcessorCount;
     float* d_out; cudaMalloc(&d_out, sizeof(float) * kThreads * sms * 8);
-    for (int run_pts : {9, 27, 64}) {
+    for (int run_pts : {9, 12, 27}) {
         for (int bps : blocks_per_sm_list) {
             const int grid = sms * bps;
             int pool_bytes = 200 * 1024 / bps; if (pool_bytes > 200 * 1024) pool_bytes = 200 * 1024;
@@ -86,11 +103,12 @@ int main(int argc, char** argv) {
             uint64_t rng = 88172645463325252ull;
             for (auto& v : st) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; v = static_cast<uint32_t>(rng % (npts - 128)); }
             uint32_t* d_st; cudaMalloc(&d_st, st.size() * 4); cudaMemcpy(d_st, st.data(), st.size() * 4, cudaMemcpyHostToDevice);
-            for (int mode = 0; mode < 3; ++mode) {
+            for (int mode = 0; mode < 4; ++mode) {
                 auto launch = [&]() {
                     if (mode == 0) { cudaFuncSetAttribute(gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pool_bytes); gather<0><<<grid, kThreads, pool_bytes>>>(d_pts, d_st, run_pts, rounds, runs_per_round, d_out); }
                     if (mode == 1) { cudaFuncSetAttribute(gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pool_bytes); gather<1><<<grid, kThreads, pool_bytes>>>(d_pts, d_st, run_pts, rounds, runs_per_round, d_out); }
                     if (mode == 2) gather<2><<<grid, kThreads, 0>>>(d_pts, d_st, run_pts, rounds, runs_per_round, d_out);
+                    if (mode == 3) { cudaFuncSetAttribute(gather<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pool_bytes); gather<3><<<grid, kThreads, pool_bytes>>>(d_pts, d_st, run_pts, rounds, runs_per_round, d_out); }
                 };
                 launch(); cudaDeviceSynchronize();
                 cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -99,7 +117,7 @@ int main(int argc, char** argv) {
                 const double runs = double(grid) * rounds * runs_per_round;
                 cudaError_t err = cudaGetLastError();
                 printf("run_pts %3d blocks/SM %d runs/round %3d mode %s: %8.1f us  %7.2f runs/us/SM  %7.1f GB/s %s\n", run_pts, bps, runs_per_round,
-                       mode == 0 ? "TMA   " : (mode == 1 ? "LDGSTS" : "LDG   "), ms * 1e3, runs / (ms * 1e3) / sms, runs * run_pts * 16 / (ms * 1e-3) / 1e9,
+                       mode == 0 ? "TMA   " : (mode == 1 ? "LDGSTS" : (mode == 2 ? "LDG   " : "COOP  ")), ms * 1e3, runs / (ms * 1e3) / sms, runs * run_pts * 16 / (ms * 1e-3) / 1e9,
                        err == cudaSuccess ? "" : cudaGetErrorString(err));
             }
             cudaFree(d_st);
