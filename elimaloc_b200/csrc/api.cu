@@ -81,10 +81,12 @@ struct elm_map {
     double* d_prec = nullptr;
     double4* d_vslots = nullptr;
     double* d_vcov = nullptr;
+    float4* d_vcand = nullptr;
+    int* d_dir7 = nullptr;
 
     elm::MapView view() const {
         elm::MapView v;
-        v.dslots = d_dslots; v.drows = d_drows; v.bmask = host.dir_bmask; v.pts = d_pts; v.prec = d_prec; v.vslots = d_vslots; v.vcov = d_vcov;
+        v.dslots = d_dslots; v.drows = d_drows; v.bmask = host.dir_bmask; v.pts = d_pts; v.prec = d_prec; v.vslots = d_vslots; v.vcov = d_vcov; v.vcand = d_vcand; v.dir7 = d_dir7;
         v.mask = host.mask; v.voxel_size = host.voxel_size;
         int e2 = 0;
         v.inv_voxel_size = (std::frexp(host.voxel_size, &e2) == 0.5) ? 1.0 / host.voxel_size : 0.0;
@@ -107,6 +109,8 @@ struct elm_map {
         if (d_prec) { cudaFree(d_prec); d_prec = nullptr; }
         if (d_vslots) { cudaFree(d_vslots); d_vslots = nullptr; }
         if (d_vcov) { cudaFree(d_vcov); d_vcov = nullptr; }
+        if (d_vcand) { cudaFree(d_vcand); d_vcand = nullptr; }
+        if (d_dir7) { cudaFree(d_dir7); d_dir7 = nullptr; }
         return ELM_OK;
     }
     static float __int_as_float_host(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -125,6 +129,10 @@ struct elm_map {
         }
         ELM_CUDA(upload(reinterpret_cast<double**>(&d_vslots), vs.data(), 4 * S));
         ELM_CUDA(upload(&d_vcov, vc.data(), 12 * S));
+        // candidate lists + the row descriptors 9 / 10 that point into them
+        ELM_CUDA(upload(&d_vcand, reinterpret_cast<const float4*>(host.vcand.data()), host.vcand.size() / 4));
+        ELM_CUDA(upload(&d_dir7, host.dir7.data(), host.dir7.size()));
+        ELM_CUDA(upload(&d_drows, reinterpret_cast<const uint2*>(host.dir_rows.data()), host.dir_rows.size()));
         return ELM_OK;
     }
     int publish_point_cov() {
@@ -143,7 +151,7 @@ struct elm_map {
     ~elm_map() {
         if (device >= 0) {
             cudaSetDevice(device);
-            cudaFree(d_dslots); cudaFree(d_drows); cudaFree(d_pts); cudaFree(d_prec); cudaFree(d_vslots); cudaFree(d_vcov);
+            cudaFree(d_dslots); cudaFree(d_drows); cudaFree(d_pts); cudaFree(d_prec); cudaFree(d_vslots); cudaFree(d_vcov); cudaFree(d_vcand); cudaFree(d_dir7);
         }
     }
 };
@@ -485,6 +493,31 @@ int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slo
             if (c == 4 && (sl.counts != counts || (have && sl.first != first))) ++bad;
         }
         if (!any) ++bad;  // an entry whose neighbourhood is empty should not exist
+        if (h.has_vcov) {  // VGICP / AVGICP candidate list of the entry: occupancy mask, order, fp32 means, voxel slots
+            const elm::DirDesc run = h.dir_rows[s * elm::kDirRowDescs + 10], occ = h.dir_rows[s * elm::kDirRowDescs + 11];
+            uint32_t c = 0;
+            for (int L = 0; L < 27; ++L) {
+                const int32_t vx = x + L / 9 - 1, vy = y + (L / 3) % 3 - 1, vz = z + L % 3 - 1;
+                const int64_t v = (elm::key_in_range(vx) && elm::key_in_range(vy) && elm::key_in_range(vz)) ? h.find(elm::pack_key(vx, vy, vz)) : -1;
+                if ((v >= 0) != (((occ.first >> L) & 1u) != 0)) { ++bad; continue; }
+                if (v < 0) continue;
+                const float* cd = &h.vcand[4 * static_cast<size_t>(run.first + c)];
+                uint32_t slot;
+                std::memcpy(&slot, &cd[3], 4);
+                if (slot >= h.slot_voxel.size() || h.slot_voxel[slot] != v) ++bad;
+                for (int k = 0; k < 3; ++k) if (cd[k] != static_cast<float>(h.vmean[3 * v + k])) ++bad;
+                ++c;
+            }
+            if (c != run.counts) ++bad;
+            static const int kL7[7] = {13, 22, 4, 16, 10, 14, 12};
+            for (int j = 0; j < 7; ++j) {
+                const int L = kL7[j];
+                const int32_t vx = x + L / 9 - 1, vy = y + (L / 3) % 3 - 1, vz = z + L % 3 - 1;
+                const int64_t v = (elm::key_in_range(vx) && elm::key_in_range(vy) && elm::key_in_range(vz)) ? h.find(elm::pack_key(vx, vy, vz)) : -1;
+                const int32_t sl7 = h.dir7[8 * s + j];
+                if ((v < 0) != (sl7 < 0) || (v >= 0 && h.slot_voxel[sl7] != v)) ++bad;
+            }
+        }
     }
     if (found != h.dir_entries) ++bad;
     // every occupied voxel makes its 27 surrounding centres findable; two voxels further out along x there is a miss

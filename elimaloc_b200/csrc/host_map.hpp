@@ -55,6 +55,13 @@ struct HostMap {
     std::vector<DirDesc> dir_rows;
     uint32_t dir_bmask = 0;
     size_t dir_entries = 0;
+    // VGICP / AVGICP candidates (built by cal_voxel_cov): for every directory entry the non-empty voxels of its
+    // 27-neighbourhood in the reference's visit order (x outer, y, z inner), one float4 each {mean rounded to fp32, bits of
+    // the voxel's slot in `slots`}.  Row descriptor 10 of the entry = {first candidate, count}, descriptor 11 = {27-bit
+    // occupancy mask (bit 9 (dx+1) + 3 (dy+1) + (dz+1)), 0}.
+    std::vector<float> vcand;  // 4 per candidate
+    // AVGICP: per directory SLOT the voxel-table slots of {centre, +x, -x, +y, -y, +z, -z} (vhm.cpp:224-230) or -1, padded to 8
+    std::vector<int32_t> dir7;
 
     size_t V() const { return vkey.size(); }
     size_t P() const { return pxyz.size() / 3; }
@@ -64,6 +71,7 @@ struct HostMap {
     void cal_voxel_cov();
     void cal_point_cov(double search_dist);
     void build_table();
+    void build_voxel_candidates();
     // returns "" on success
     std::string build_directory();
     // slot index of a centre key in the directory or -1 (host mirror of the device lookup; tests)

@@ -11,6 +11,9 @@
 //   prec    double[16 P]         GICP record per stored point: mean[3] cov[9] normal[3] pad  (128 B, one line)
 //   vslots  double4[capacity]    VGICP/AVGICP: 32 B/slot {key bits, mean[3]}, open-addressed with linear probing, capacity = 2^k
 //                                >= 2 V (mask = capacity - 1); empty = all ones
+//   vcand   float4[C]            VGICP/AVGICP candidates: for every directory entry the non-empty voxels of its 27-neighbourhood
+//                                in visit order, {mean rounded to fp32, bits of the voxel's slot in vslots}; row descriptor 10 of
+//                                the entry = {first candidate, count}, descriptor 11 = {27-bit occupancy mask, 0}
 //   vcov    double[12 capacity]  VGICP/AVGICP: 96 B/slot {cov[9], pad[3]}
 #pragma once
 #include <cuda_runtime.h>
@@ -25,6 +28,8 @@ struct MapView {
     const double* prec;
     const double4* vslots;
     const double* vcov;
+    const float4* vcand;
+    const int* dir7;  // AVGICP: 8 ints per directory slot: voxel-table slots of {c, +x, -x, +y, -y, +z, -z} or -1
     uint32_t mask;   // vslots
     uint32_t bmask;  // directory buckets - 1
     double voxel_size;

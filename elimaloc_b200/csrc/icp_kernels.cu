@@ -80,20 +80,6 @@ __device__ __forceinline__ int voxel_floor(double p, const MapView& map, float* 
     // saturate far outside the table's key range instead of the reference's undefined int overflow
     return (f >= 2.0e9) ? 2000000000 : ((f <= -2.0e9) ? -2000000000 : static_cast<int>(f));
 }
-// Linear probe of the 32-B VGICP table {key, mean}; returns the slot or -1 and the mean.
-__device__ __forceinline__ int probe_mean(const double4* __restrict__ vslots, uint32_t mask, uint64_t key, double& mx, double& my, double& mz) {
-    uint32_t h = home_slot(key) & mask;
-    for (uint32_t i = 0; i <= mask; ++i) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(vslots + h));
-        const double2 b = __ldg(reinterpret_cast<const double2*>(vslots + h) + 1);
-        const uint64_t k = static_cast<uint64_t>(__double_as_longlong(a.x));
-        if (k == key) { mx = a.y; my = b.x; mz = b.y; return static_cast<int>(h); }
-        if (k == kEmptyKey) return -1;
-        h = (h + 1) & mask;
-    }
-    return -1;
-}
-
 // Neighbourhood-directory lookup of the centre key: two independent 32-byte bucket loads (2-choice cuckoo, 2 slots per
 // bucket) — one round trip, no probe chain, lanes of a warp never wait for each other's collisions.  Returns the slot
 // index (== row index) or -1 when no voxel of the 27-neighbourhood holds a point; `centre` = descriptor of the centre
@@ -137,11 +123,6 @@ struct Best {
     double d2 = kDblMax;
     uint32_t idx = 0xffffffffu;
 };
-// One candidate: exact fp64 squared distance in the reference's association order, strict < (vhm.cpp:44-45).
-__device__ __forceinline__ void fold_point(float x, float y, float z, uint32_t idx, double px, double py, double pz, Best& b) {
-    const double d2 = sq3_exact(static_cast<double>(x) - px, static_cast<double>(y) - py, static_cast<double>(z) - pz);
-    if (d2 < b.d2) { b.d2 = d2; b.idx = idx; }
-}
 // 32-byte (two stored points) read-only load: sm_100 LDG.E.256.  With one lane per query every lane touches a different
 // 128-byte line, so the L1TEX tag stage — one line per cycle — bounds the search (measured: ~14.5 B/cycle/SM with 16-byte
 // loads, profiles/r01b_*); a 32-byte load moves twice the points per tag lookup.
@@ -158,7 +139,30 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
 #ifndef ELM_BATCH
 #define ELM_BATCH 3
 #endif
-__device__ __forceinline__ void visit_points_exact(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, double px, double py, double pz, Best& b) {
+// Exact position of a candidate record.  Stored map points: the fp32 coordinates ARE the exact position (note A of the
+// survey: map points are float32 values).  Voxel means (VGICP): the record holds the mean rounded to fp32 for the
+// pre-filter plus the voxel's slot; the exact fp64 mean is read from the voxel table.
+struct ExactPoint {
+    __device__ __forceinline__ void operator()(const float4& q, double& x, double& y, double& z) const { x = q.x; y = q.y; z = q.z; }
+};
+struct ExactMean {
+    const double4* vslots;
+    __device__ __forceinline__ void operator()(const float4& q, double& x, double& y, double& z) const {
+        const double2* r = reinterpret_cast<const double2*>(vslots + __float_as_uint(q.w));
+        const double2 a = __ldg(r), b = __ldg(r + 1);
+        x = a.y; y = b.x; z = b.y;
+    }
+};
+template <class Fetch>
+__device__ __forceinline__ void fold_exact(const Fetch& fetch, const float4& q, uint32_t idx, double px, double py, double pz, Best& b) {
+    double x, y, z;
+    fetch(q, x, y, z);
+    const double d2 = sq3_exact(x - px, y - py, z - pz);
+    if (d2 < b.d2) { b.d2 = d2; b.idx = idx; }
+}
+template <class Fetch>
+__device__ __forceinline__ void visit_points_exact(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, double px, double py, double pz, Best& b,
+                                                   const Fetch& fetch) {
     if (n == 0) return;
     const uint32_t end = idx0 + n;
     constexpr uint32_t K = ELM_BATCH;  // 32-byte pairs per batch
@@ -170,8 +174,8 @@ __device__ __forceinline__ void visit_points_exact(const float4* __restrict__ pt
 #pragma unroll
         for (uint32_t u = 0; u < K; ++u) {
             const uint32_t pi = i + 2 * u;
-            if (pi >= idx0 && pi < end) fold_point(q0[u].x, q0[u].y, q0[u].z, pi, px, py, pz, b);
-            if (pi + 1 < end) fold_point(q1[u].x, q1[u].y, q1[u].z, pi + 1, px, py, pz, b);  // (pi + 1 >= idx0 always)
+            if (pi >= idx0 && pi < end) fold_exact(fetch, q0[u], pi, px, py, pz, b);
+            if (pi + 1 < end) fold_exact(fetch, q1[u], pi + 1, px, py, pz, b);  // (pi + 1 >= idx0 always)
         }
     }
 }
@@ -196,9 +200,13 @@ struct Query {
 // If s lies outside that band (widened 2-4x below to absorb the float evaluation of the bound itself) the fp32 argmin is
 // the unique exact nearest point of the run and ONE exact fp64 distance is computed for it; otherwise (a near tie,
 // ~1e-3 of the runs on a 100 m map) the run is re-scanned exactly.
-__device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, const Query& Q, Best& b) {
+// (Voxel means: the candidate's fp32 rounding adds 2^-24 |mean| <= 2^-24 (|p| + r) per candidate; the band needed
+// becomes sqrt(m) (1 + 2^-21.2) + 2^-22 |p|, still inside the one used.)
+template <class Fetch = ExactPoint>
+__device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, const Query& Q, Best& b,
+                                             const Fetch& fetch = Fetch()) {
 #ifdef ELM_EXACT_SCAN
-    visit_points_exact(pts, idx0, n, Q.px, Q.py, Q.pz, b);
+    visit_points_exact(pts, idx0, n, Q.px, Q.py, Q.pz, b, fetch);
 #else
     if (n == 0) return;
     const uint32_t end = idx0 + n;
@@ -230,11 +238,13 @@ __device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uin
     const float T = fmaf(sm * sm, 1.000003814697265625f, 1e-30f);                  // (1 + 2^-18), + underflow slack
     if (s2 > T) {  // (false for NaN / inf: those take the exact path)
         const float4 q = __ldg(pts + mi);
-        const double d2 = sq3_exact(static_cast<double>(q.x) - Q.px, static_cast<double>(q.y) - Q.py, static_cast<double>(q.z) - Q.pz);
+        double x, y, z;
+        fetch(q, x, y, z);
+        const double d2 = sq3_exact(x - Q.px, y - Q.py, z - Q.pz);
         if (d2 < b.d2 || (d2 == b.d2 && mi < b.idx)) { b.d2 = d2; b.idx = mi; }
     } else {
         Best e;
-        visit_points_exact(pts, idx0, n, Q.px, Q.py, Q.pz, e);
+        visit_points_exact(pts, idx0, n, Q.px, Q.py, Q.pz, e, fetch);
         if (e.idx != 0xffffffffu && (e.d2 < b.d2 || (e.d2 == b.d2 && e.idx < b.idx))) b = e;
     }
 #endif
@@ -270,21 +280,31 @@ __device__ __forceinline__ uint32_t voxels_to_visit(int kx, int ky, int kz, floa
     }
     return need & ~skip;
 }
-// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115), one thread per query.  Returns the winning slot or -1.
+// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115), one thread per query: ONE directory lookup, then the
+// entry's candidate list (the non-empty voxels of the neighbourhood in the reference's visit order, means rounded to fp32)
+// is scanned like a run of points; the winner's exact fp64 mean decides (strict < keeps the first of equals).
+// Returns the winning voxel's slot or -1.
 __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, double py, double pz, int kx, int ky, int kz) {
-    double best = kDblMax;
-    int slot = -1;
-#pragma unroll 1
-    for (int L = 0; L < 27; ++L) {  // reference visit order; strict < keeps the first of equals
-        const int x = kx + L / 9 - 1, y = ky + (L / 3) % 3 - 1, z = kz + L % 3 - 1;
-        if (!(key_in_range(x) && key_in_range(y) && key_in_range(z))) continue;
-        double mx, my, mz;
-        const int s = probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz);
-        if (s < 0) continue;
-        const double d2 = sq3_exact(mx - px, my - py, mz - pz);
-        if (d2 < best) { best = d2; slot = s; }
-    }
-    return slot;
+    uint2 centre;
+    const int row = dir_lookup(map, kx, ky, kz, centre);
+    if (row < 0) return -1;
+    const uint2 d = dir_column(map, row, 10);  // {first candidate, count}
+    Best b;
+    visit_points(map.vcand, d.x, d.y, Query(px, py, pz), b, ExactMean{map.vslots});
+    return (b.idx == 0xffffffffu) ? -1 : static_cast<int>(__float_as_uint(__ldg(map.vcand + b.idx).w));
+}
+
+// AVGICP (vhm.cpp:153-206, GetAdjacentVoxels range 1): voxel j of {centre, +x, -x, +y, -y, +z, -z} around the query's
+// directory entry: its slot in the voxel table or -1 when it holds no points.  No probing: one 32-byte row per entry,
+// shared by the 8 lanes of a point.
+__device__ __forceinline__ int neighbour7_slot(const MapView& map, int row, int j) {
+    return __ldg(map.dir7 + static_cast<size_t>(row) * 8 + j);
+}
+// exact fp64 mean of a voxel slot
+__device__ __forceinline__ void slot_mean(const MapView& map, int slot, double& mx, double& my, double& mz) {
+    const double2* r = reinterpret_cast<const double2*>(map.vslots + slot);
+    const double2 a = __ldg(r), b = __ldg(r + 1);
+    mx = a.y; my = b.x; mz = b.y;
 }
 
 }  // namespace
@@ -1138,12 +1158,14 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
             if (j == 7) continue;
             const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
             const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
-            kx += (j == 1) - (j == 2); ky += (j == 3) - (j == 4); kz += (j == 5) - (j == 6);
-            if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) continue;
-            double mx, my, mz;
-            const int slot = probe_mean(map.vslots, map.mask, pack_key(kx, ky, kz), mx, my, mz);
+            const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
+            uint2 centre;
+            const int row = dir_lookup(map, kx, ky, kz, centre);  // (the 8 lanes of a point read the same two sectors)
+            if (row < 0) continue;
+            const int slot = neighbour7_slot(map, row, j);
             if (slot < 0) continue;
+            double mx, my, mz;
+            slot_mean(map, slot, mx, my, mz);
             if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_voxel_pair(sx, sy, sz, slot, mx, my, mz);  // vhm.cpp:183
         }
     } else {
@@ -1213,11 +1235,13 @@ icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __rest
         const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
         double* t = target + static_cast<size_t>(i) * 21;
         int c = 0;
-        for (int j = 0; j < 7; ++j) {
-            const int x = kx + (j == 1) - (j == 2), y = ky + (j == 3) - (j == 4), z = kz + (j == 5) - (j == 6);
-            if (!(key_in_range(x) && key_in_range(y) && key_in_range(z))) continue;
+        uint2 centre;
+        const int row = dir_lookup(map, kx, ky, kz, centre);
+        for (int j = 0; j < 7 && row >= 0; ++j) {
+            const int slot = neighbour7_slot(map, row, j);
+            if (slot < 0) continue;
             double mx, my, mz;
-            if (probe_mean(map.vslots, map.mask, pack_key(x, y, z), mx, my, mz) < 0) continue;
+            slot_mean(map, slot, mx, my, mz);
             if (sq3_exact(mx - px, my - py, mz - pz) < max_dist2) { t[3 * c] = mx; t[3 * c + 1] = my; t[3 * c + 2] = mz; ++c; }
         }
         count[i] = c;

@@ -132,6 +132,8 @@ def test_neighbourhood_directory_is_consistent(kind):
         pm.AddPoints(raw[10_000:])
     entries, slots, bad = pm.directory_check()
     assert bad == 0
+    pm.CalVoxelCovAll()  # adds the VGICP / AVGICP candidate lists: checked as well from now on
+    assert pm.directory_check()[2] == 0
     assert entries >= pm.num_voxels() and slots >= entries and slots <= 8 * max(entries, 2)
     if kind == "single_point":
         assert entries == 27
