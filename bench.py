@@ -399,6 +399,7 @@ def main():
                     "algorithmic_bytes_per_search": bps, "searches_per_launch": n_local,
                     "search_mode": "exhaustive-27" if args.exhaustive else "exact-pruning",
                     "map_points_visited_per_search": visited_per_search,
+                    "requested_bytes_per_search": (12 + 64 + 16 * visited_per_search) if visited_per_search is not None else None,
                     "exhaustive_bytes_per_search": bps_exh,
                     "exhaustive_equivalent_gbs": bps_exh * n_local / (dom_ms * 1e-3) / 1e9,
                     "mean_stored_points_in_27_voxels": st["sum27"], "mean_nonempty_voxels_27": st["v27"],
