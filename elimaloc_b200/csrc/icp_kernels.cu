@@ -234,8 +234,11 @@ __device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uin
             fold32(q1[u], pi + 1, pi + 1 < end);
         }
     }
-    const float sm = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);            // sqrt(m) (1 + 2^-20) + band
-    const float T = fmaf(sm * sm, 1.000003814697265625f, 1e-30f);                  // (1 + 2^-18), + underflow slack
+    auto band_around = [&](float d) {
+        const float sd = fmaf(sqrtf(d), 1.00000095367431640625f, Q.band);          // sqrt(d) (1 + 2^-20) + band
+        return fmaf(sd * sd, 1.000003814697265625f, 1e-30f);                        // (1 + 2^-18), + underflow slack
+    };
+    const float T = band_around(m);
     if (s2 > T) {  // (false for NaN / inf: those take the exact path)
         const float4 q = __ldg(pts + mi);
         double x, y, z;
@@ -817,7 +820,10 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
 #define ELM_USE(cond) do { } while (0)
 #endif
 constexpr int kNoItem = 0xffff;
-constexpr int kItemCap = 1024;  // work items per tile kept in shared memory; overflow stays with its owner
+#ifndef ELM_ITEM_CAP
+#define ELM_ITEM_CAP 1024
+#endif
+constexpr int kItemCap = ELM_ITEM_CAP;  // work items per tile kept in shared memory; overflow stays with its owner
 // Scope of the work-item list.  Warp scope (default): every warp shares out the items of ITS 32 queries among its own
 // lanes and only ever waits for itself (__syncwarp) — the warps of a block drift through the phases independently and hide
 // each other's load latency.  Block scope (-DELM_BLOCK_SCOPE): one list per tile and __syncthreads between the phases
@@ -850,7 +856,6 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_T[12];
     __shared__ double s_px[COOP ? kIcpThreads : 1], s_py[COOP ? kIcpThreads : 1], s_pz[COOP ? kIcpThreads : 1];
-    __shared__ int s_row[COOP ? kIcpThreads : 1];
     __shared__ unsigned long long s_best[COOP ? kIcpThreads : 1];
     __shared__ unsigned int s_win[COOP ? kIcpThreads : 1];
     __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1];
@@ -948,7 +953,6 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             ELM_USE(row == 0x7fffffff);
             ELM_TICK(3);
             if (COOP) {
-                s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
                 s_win[tid] = 0xffffffffu;
                 if (row >= 0) {
                     // the z-column holding the voxel whose STORED-key cell contains the query: insert keys truncate toward
@@ -971,7 +975,6 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                     ELM_TICK(4);
                     own_cols = voxels_to_visit(kx, ky, kz, fx, fy, fz, b.d2, inv_vs2_up, hz << (3 * ch));
                     s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
-                    s_row[tid] = row;
                     int k = 0;
 #pragma unroll
                     for (int c = 0; c < 9; ++c) k += ((own_cols >> (3 * c)) & 7u) ? 1 : 0;
@@ -982,14 +985,22 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
 #pragma unroll
                             for (int c = 0; c < 9; ++c) {
                                 const uint32_t zm = (own_cols >> (3 * c)) & 7u;
-                                if (zm) g_items[w++] = static_cast<uint16_t>((tid << 7) | (c << 3) | zm);
+                                if (zm) {
+                                    // the item's column descriptor travels with it: cp.async (8 bytes, no registers) into the slot
+                                    // that later receives the item's result, so phase B starts streaming at once
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(g_item_d2 + w)),
+                                                 "l"(map.drows + static_cast<size_t>(row) * 12 + c) : "memory");
+                                    g_items[w++] = static_cast<uint16_t>((tid << 7) | (c << 3) | zm);
+                                }
                             }
                             own_cols = 0;
                         } else {
                             for (int w = pos; w < kGroupCap; ++w) g_items[w] = kNoItem;  // the tail of the list this claim straddles
                         }
                     }
+                    asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
                 }
+                s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(b.d2));  // what phase A found (DBL_MAX: nothing)
             } else if (row >= 0) {
 #pragma unroll 1
                 for (int c = 0; c < 9; ++c) {  // ascending column = ascending canonical index = the reference's visit order
@@ -1012,7 +1023,8 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                 if (it == kNoItem) continue;
                 const int q = it >> 7;
                 uint32_t rs, rl;
-                column_run(dir_column(map, s_row[q], (it >> 3) & 15), static_cast<uint32_t>(it & 7), rs, rl);
+                const unsigned long long dbits = g_item_d2[j];
+                column_run(make_uint2(static_cast<uint32_t>(dbits), static_cast<uint32_t>(dbits >> 32)), static_cast<uint32_t>(it & 7), rs, rl);
                 Best ib;
                 visit_points(map.pts, rs, rl, Query(s_px[q], s_py[q], s_pz[q]), ib);
                 visited += rl;
@@ -1292,11 +1304,11 @@ int icp_accumulate_grid(const IcpParams& prm, int num_sms) {
 namespace {
 // launch with programmatic stream serialization (see pdl_wait above)
 template <class... KArgs, class... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args&&... args) {
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int dyn_smem, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(static_cast<unsigned>(block));
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = static_cast<size_t>(dyn_smem);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1319,13 +1331,13 @@ cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* 
                               int grid, int prune, int fuse, double* partials, unsigned int* ticket, int solve_here, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
     if (prm.method <= 1) {
-#define ELM_LAUNCH(C, F) e = launch_pdl(icp_search_points_kernel<C, F>, grid, kIcpThreads, s, map, scan, orig, prm, st, match, partials, ticket, solve_here)
+#define ELM_LAUNCH(C, F) e = launch_pdl(icp_search_points_kernel<C, F>, grid, kIcpThreads, 0, s, map, scan, orig, prm, st, match, partials, ticket, solve_here)
         if (!fuse) { if (prune) ELM_LAUNCH(true, -1); else ELM_LAUNCH(false, -1); }
         else if (prm.method == 0) { if (prune) ELM_LAUNCH(true, 0); else ELM_LAUNCH(false, 0); }
         else { if (prune) ELM_LAUNCH(true, 1); else ELM_LAUNCH(false, 1); }
 #undef ELM_LAUNCH
     } else if (prm.method == 2) {
-        e = launch_pdl(icp_search_means_kernel, grid, kIcpThreads, s, map, scan, orig, prm, static_cast<const IcpState*>(st), match);
+        e = launch_pdl(icp_search_means_kernel, grid, kIcpThreads, 0, s, map, scan, orig, prm, static_cast<const IcpState*>(st), match);
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -1334,16 +1346,16 @@ cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const i
                                   unsigned int* ticket, int solve_here, int grid, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
     switch (prm.method) {
-        case 0: e = launch_pdl(icp_accumulate_kernel<0>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
-        case 1: e = launch_pdl(icp_accumulate_kernel<1>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
-        case 2: e = launch_pdl(icp_accumulate_kernel<2>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
-        default: e = launch_pdl(icp_accumulate_kernel<3>, grid, kIcpThreads, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 0: e = launch_pdl(icp_accumulate_kernel<0>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 1: e = launch_pdl(icp_accumulate_kernel<1>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 2: e = launch_pdl(icp_accumulate_kernel<2>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        default: e = launch_pdl(icp_accumulate_kernel<3>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s) {
-    const cudaError_t e = launch_pdl(icp_solve_kernel, 1, 32, s, st, prm);
+    const cudaError_t e = launch_pdl(icp_solve_kernel, 1, 32, 0, s, st, prm);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
