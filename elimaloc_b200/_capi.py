@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ELIMALOC_B200_LIB: developer override to A/B-test another build of the same library (profiles/quick_bench.sh)
 LIB_PATH = os.environ.get("ELIMALOC_B200_LIB") or os.path.join(_HERE, "libelimaloc_b200.so")
 
-ELM_OK, ELM_ERR_INVALID, ELM_ERR_CUDA, ELM_ERR_NCCL, ELM_ERR_UNSUPPORTED, ELM_ERR_RANGE, ELM_ERR_STATE = range(7)
+ELM_OK, ELM_ERR_INVALID, ELM_ERR_CUDA, ELM_ERR_NCCL, ELM_ERR_UNSUPPORTED, ELM_ERR_RANGE, ELM_ERR_STATE, ELM_ERR_IO = range(8)
 P2P, GICP, VGICP, AVGICP = 0, 1, 2, 3
 
 
@@ -81,6 +81,9 @@ SIGNATURES = {
     "elm_map_num_voxels": (C.c_size_t, [C.c_void_p]),
     "elm_map_num_points": (C.c_size_t, [C.c_void_p]),
     "elm_map_export": (C.c_int, [C.c_void_p, _ip, _ip, _dp, _dp, _fp, _dp, _dp]),
+    "elm_shape_pcm_covariance": (C.c_int, [_dp, _dp, C.c_double, _dp]),
+    "elm_map_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "elm_map_load": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
     "elm_map_directory_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "elm_registration_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "elm_registration_destroy": (None, [C.c_void_p]),

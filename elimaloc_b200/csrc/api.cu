@@ -8,6 +8,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -456,6 +457,62 @@ int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* v
     if (pxyz) std::memcpy(pxyz, h.pxyz.data(), h.pxyz.size() * sizeof(float));
     if (pmean) std::memcpy(pmean, h.pmean.data(), h.pmean.size() * sizeof(double));
     if (pcov) std::memcpy(pcov, h.pcov.data(), h.pcov.size() * sizeof(double));
+    return ELM_OK;
+}
+
+int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], double icp_pose_std_m, double pose_cov[36]) {
+    if (!R_ego || !local_cov || !pose_cov) return fail(ELM_ERR_INVALID, "elm_shape_pcm_covariance: bad argument");
+    auto normalize = [](const double* in, double* out) {
+        double scale = 1.0, m = std::fmin(in[0], std::fmin(in[4], in[8]));
+        if (m <= 1e-9) { scale = 1e9; m = std::fmin(in[0] * scale, std::fmin(in[4] * scale, in[8] * scale)); if (m < 1e-9) m = 1e-9; }
+        for (int i = 0; i < 9; ++i) out[i] = std::fmin(in[i] * scale / m, 5.0);
+    };
+    const double sd = std::fmax(icp_pose_std_m, 0.25), ang = sd * 3.14159265358979323846 / 180.0;
+    double t[9], r[9], tn[9], rn[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                double rc = 0.0;
+                for (int k = 0; k < 3; ++k) rc += R_ego[3 * i + k] * local_cov[6 * k + a];
+                acc += rc * R_ego[3 * j + a];
+            }
+            t[3 * i + j] = acc;
+            r[3 * i + j] = local_cov[6 * (i + 3) + (j + 3)];
+        }
+    normalize(t, tn);
+    normalize(r, rn);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            pose_cov[6 * i + j] = tn[3 * i + j] * sd * sd;
+            pose_cov[6 * (i + 3) + (j + 3)] = rn[3 * i + j] * ang * ang;
+        }
+    return ELM_OK;
+}
+
+int elm_map_save(const elm_map* map, const char* path) {
+    if (!map || !path) return fail(ELM_ERR_INVALID, "elm_map_save: bad argument");
+    const std::string e = map->host.save(path);
+    if (!e.empty()) return fail(ELM_ERR_IO, e);
+    return ELM_OK;
+}
+
+int elm_map_load(elm_map** out, const char* path, int device) {
+    if (!out || !path) return fail(ELM_ERR_INVALID, "elm_map_load: bad argument");
+    if (device >= 0) {
+        if (device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_map_load: no such CUDA device");
+        ELM_CUDA(cudaSetDevice(device));
+    }
+    std::unique_ptr<elm_map> m(new (std::nothrow) elm_map());
+    if (!m) return fail(ELM_ERR_INVALID, "out of memory");
+    const std::string e = m->host.load(path);
+    if (!e.empty()) return fail(ELM_ERR_IO, e);
+    m->device = device;
+    int rc = m->publish_points();
+    if (rc == ELM_OK && m->host.has_vcov) rc = m->publish_voxel_cov();
+    if (rc == ELM_OK && m->host.has_pcov) rc = m->publish_point_cov();
+    if (rc != ELM_OK) return rc;
+    *out = m.release();
     return ELM_OK;
 }
 

@@ -7,8 +7,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <initializer_list>
+#include <memory>
 #include <atomic>
 #include <thread>
 
@@ -298,6 +300,109 @@ std::string HostMap::build_directory() {
             dir_slots[s] = DirSlot{static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), row[4].first, row[4].counts};
         }
     });
+    return "";
+}
+
+// ---- built-map file ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr char kMapMagic[8] = {'E', 'L', 'M', 'B', '2', '0', '0', 'M'};
+constexpr uint32_t kMapVersion = 3;
+
+// checksum of everything written / read so far: 8 interleaved FNV-1a lanes over 64-bit words (tail bytes one by one)
+struct Checksum {
+    uint64_t h[8] = {0xcbf29ce484222325ull, 0x84222325cbf29ce4ull, 0x9ce484222325cbf2ull, 0x2325cbf29ce48422ull,
+                     0xf29ce484222325cbull, 0x222325cbf29ce484ull, 0xe484222325cbf29cull, 0x25cbf29ce4842223ull};
+    void add(const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64)
+            for (int l = 0; l < 8; ++l) { uint64_t w; std::memcpy(&w, b + i + 8 * l, 8); h[l] = (h[l] ^ w) * 0x100000001b3ull; }
+        for (; i < n; ++i) h[i & 7] = (h[i & 7] ^ b[i]) * 0x100000001b3ull;
+    }
+    uint64_t value() const { uint64_t v = 0; for (int l = 0; l < 8; ++l) v = (v ^ h[l]) * 0x100000001b3ull; return v; }
+};
+struct Writer {
+    std::FILE* f; Checksum c; bool ok = true;
+    void put(const void* p, size_t n) { if (ok && n) { ok = std::fwrite(p, 1, n, f) == n; c.add(p, n); } }
+};
+struct Reader {
+    std::FILE* f; Checksum c; bool ok = true;
+    void get(void* p, size_t n) { if (ok && n) { ok = std::fread(p, 1, n, f) == n; if (ok) c.add(p, n); } }
+};
+
+struct FileCloser { void operator()(std::FILE* f) const { if (f) std::fclose(f); } };
+
+template <class T>
+void write_vec(Writer& w, const std::vector<T>& v) {
+    const uint64_t n = v.size();
+    w.put(&n, sizeof n);
+    w.put(v.data(), n * sizeof(T));
+}
+template <class T>
+void read_vec(Reader& r, std::vector<T>& v, uint64_t max_elems) {
+    uint64_t n = 0;
+    r.get(&n, sizeof n);
+    if (!r.ok || n > max_elems) { r.ok = false; return; }
+    v.resize(n);
+    r.get(v.data(), n * sizeof(T));
+}
+
+}  // namespace
+
+std::string HostMap::save(const std::string& path) const {
+    std::unique_ptr<std::FILE, FileCloser> f(std::fopen(path.c_str(), "wb"));
+    if (!f) return "cannot open " + path + " for writing";
+    const uint32_t flags = (has_vcov ? 1u : 0u) | (has_pcov ? 2u : 0u);
+    const uint64_t counts[4] = {V(), P(), dir_entries, n_raw_seen};
+    Writer w{f.get()};
+    w.put(kMapMagic, 8); w.put(&kMapVersion, 4); w.put(&flags, 4); w.put(&voxel_size, 8); w.put(&cap, 4); w.put(&mask, 4);
+    w.put(&dir_bmask, 4); w.put(counts, sizeof counts);
+    write_vec(w, vkey); write_vec(w, vstart); write_vec(w, pxyz); write_vec(w, porig); write_vec(w, vmean); write_vec(w, vcov);
+    write_vec(w, pmean); write_vec(w, pcov); write_vec(w, pnormal); write_vec(w, slots); write_vec(w, slot_voxel);
+    write_vec(w, dir_slots); write_vec(w, dir_rows); write_vec(w, vcand); write_vec(w, dir7);
+    const uint64_t sum = w.c.value();
+    bool ok = w.ok && std::fwrite(&sum, 8, 1, f.get()) == 1;
+    if (!ok || std::fflush(f.get()) != 0) return "short write to " + path;
+    return "";
+}
+
+std::string HostMap::load(const std::string& path) {
+    std::unique_ptr<std::FILE, FileCloser> f(std::fopen(path.c_str(), "rb"));
+    if (!f) return "cannot open " + path;
+    char magic[8];
+    uint32_t version = 0, flags = 0;
+    uint64_t counts[4] = {0, 0, 0, 0};
+    HostMap m;
+    Reader r{f.get()};
+    r.get(magic, 8); r.get(&version, 4);
+    if (!r.ok || std::memcmp(magic, kMapMagic, 8) != 0) return path + " is not an elimaloc_b200 map file";
+    if (version != kMapVersion) return path + ": unsupported map file version " + std::to_string(version);
+    r.get(&flags, 4); r.get(&m.voxel_size, 8); r.get(&m.cap, 4); r.get(&m.mask, 4); r.get(&m.dir_bmask, 4); r.get(counts, sizeof counts);
+    const uint64_t lim = 1ull << 34;
+    read_vec(r, m.vkey, lim); read_vec(r, m.vstart, lim); read_vec(r, m.pxyz, lim); read_vec(r, m.porig, lim); read_vec(r, m.vmean, lim);
+    read_vec(r, m.vcov, lim); read_vec(r, m.pmean, lim); read_vec(r, m.pcov, lim); read_vec(r, m.pnormal, lim); read_vec(r, m.slots, lim);
+    read_vec(r, m.slot_voxel, lim); read_vec(r, m.dir_slots, lim); read_vec(r, m.dir_rows, lim); read_vec(r, m.vcand, lim);
+    read_vec(r, m.dir7, lim);
+    uint64_t sum = 0;
+    bool ok = r.ok && std::fread(&sum, 8, 1, f.get()) == 1 && sum == r.c.value();
+    if (!ok) return path + ": truncated or corrupt map file";
+    m.has_vcov = (flags & 1u) != 0;
+    m.has_pcov = (flags & 2u) != 0;
+    m.dir_entries = counts[2];
+    m.n_raw_seen = counts[3];
+    // structural consistency (a file from another build / a damaged file must not reach the kernels)
+    const size_t nv = m.vkey.size(), np = m.pxyz.size() / 3;
+    ok = counts[0] == nv && counts[1] == np && m.pxyz.size() == 3 * np && m.vstart.size() == nv + 1 && m.porig.size() == np &&
+         (nv == 0 || (m.vstart.front() == 0 && m.vstart.back() == np)) && m.slots.size() == m.slot_voxel.size() &&
+         (m.slots.empty() || m.slots.size() == static_cast<size_t>(m.mask) + 1) &&
+         (m.dir_slots.empty() || m.dir_slots.size() == 2 * (static_cast<size_t>(m.dir_bmask) + 1)) &&
+         m.dir_rows.size() == m.dir_slots.size() * kDirRowDescs && m.voxel_size > 0.0 && m.cap >= 1 &&
+         (!m.has_vcov || (m.vmean.size() == 3 * nv && m.vcov.size() == 9 * nv && m.dir7.size() == 8 * m.dir_slots.size())) &&
+         (!m.has_pcov || (m.pmean.size() == 3 * np && m.pcov.size() == 9 * np && m.pnormal.size() == 3 * np));
+    for (size_t v = 0; ok && v + 1 < nv; ++v) ok = m.vkey[v] < m.vkey[v + 1] && m.vstart[v] < m.vstart[v + 1];
+    if (!ok) return path + ": inconsistent map file";
+    *this = std::move(m);
     return "";
 }
 

@@ -78,6 +78,11 @@ struct HostMap {
     int64_t dir_find(uint64_t key) const;
     // voxel index of a packed key or -1
     int64_t find(uint64_t key) const;
+    // Built-map file (the reference reloads the .pcd and rebuilds the whole map at every start,
+    // pcm_matching.cpp:69-101): every array above, little-endian, behind a header with magic / version / sizes.
+    // Both return "" on success, else an error message.
+    std::string save(const std::string& path) const;
+    std::string load(const std::string& path);
 };
 
 // Symmetric 3x3 "plane regularisation" used by both covariance passes (voxel_hash_map.hpp:141-144, 241-244):

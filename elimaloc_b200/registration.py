@@ -84,6 +84,20 @@ class VoxelHashMap:
     def num_points(self):
         return lib().elm_map_num_points(self._h)
 
+    def Save(self, path):
+        """Write the built map (points, voxel table, directory, covariances) to `path` (elm_map_save)."""
+        check(lib().elm_map_save(self._h, str(path).encode()))
+
+    @classmethod
+    def Load(cls, path, device=0):
+        """A map restored from a file written by Save, uploaded to `device` (elm_map_load)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.device = device
+        check(lib().elm_map_load(C.byref(self._h), str(path).encode(), int(device)))
+        self.voxel_size_ = self.max_points_per_voxel_ = None
+        return self
+
     def directory_check(self):
         """(centre keys stored, table slots, mismatches) of the neighbourhood directory; mismatches must be 0."""
         e, s, m = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
@@ -112,6 +126,15 @@ class VoxelHashMap:
         e = self.export(voxel_cov=True)
         keep = e["counts"] > 2
         return e["vmean"][keep], e["vcov"][keep]
+
+
+def shape_pcm_covariance(R_ego, local_cov, icp_pose_std_m, cov36=None):
+    """PcmMatching::PublishPcmOdom's covariance shaping (pcm_matching.cpp:1082-1098) -> 6x6 row-major pose covariance."""
+    R = np.ascontiguousarray(R_ego, dtype=np.float64).reshape(3, 3)
+    lc = np.ascontiguousarray(local_cov, dtype=np.float64).reshape(6, 6)
+    out = np.zeros((6, 6)) if cov36 is None else np.ascontiguousarray(cov36, dtype=np.float64).reshape(6, 6).copy()
+    check(lib().elm_shape_pcm_covariance(_d(R), _d(lc), float(icp_pose_std_m), _d(out)))
+    return out
 
 
 class Registration:

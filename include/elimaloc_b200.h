@@ -35,8 +35,9 @@ typedef enum elm_status {
     ELM_ERR_CUDA = 2,        /* CUDA runtime error or no device */
     ELM_ERR_NCCL = 3,        /* NCCL error or NCCL library not loadable */
     ELM_ERR_UNSUPPORTED = 4, /* valid in the reference but out of scope here (use_radar_cov = 1) */
-    ELM_ERR_RANGE = 5,       /* map extent beyond +-2^20 voxels per axis */
-    ELM_ERR_STATE = 6        /* call order (e.g. GICP without elm_map_cal_point_cov) */
+    ELM_ERR_RANGE = 5,       /* map extent beyond +-(2^20 - 2) voxels per axis, max_points_per_voxel > 1023 */
+    ELM_ERR_STATE = 6,       /* call order (e.g. GICP without elm_map_cal_point_cov) */
+    ELM_ERR_IO = 7           /* map file cannot be opened / is not a map file / is truncated or inconsistent */
 } elm_status;
 
 /* IcpMethod, pcm_matching/include/registration.hpp:60 */
@@ -92,6 +93,20 @@ size_t elm_map_num_points(const elm_map* map);
  * keys[3V] counts[V] vmean[3V] vcov[9V] pxyz[3P] pmean[3P] pcov[9P] */
 int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* vmean, double* vcov, float* pxyz,
                    double* pmean, double* pcov);
+
+/* Result shaping: PcmMatching::PublishPcmOdom's pose covariance (pcm_matching.cpp:1082-1098 with
+ * NormalizeCovariance / UpdateCovarianceField, pcm_matching.hpp:247-290).  R_ego: rotation of the published ego pose
+ * (row-major 3x3); local_cov: RunRegister's 6x6 output; icp_pose_std_m: cfg_.d_icp_pose_std_m (= the fitness score,
+ * pcm_matching.cpp:295).  Writes the translation block [0..2][0..2] and the rotation block [3..5][3..5] of the row-major
+ * 6x6 `pose_cov`; the other 18 entries are left as they are, as the reference does.  Host arithmetic (a dozen flops). */
+int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], double icp_pose_std_m, double pose_cov[36]);
+
+/* Built-map file.  The reference reloads its .pcd and rebuilds the whole voxel map at every start of the
+ * node (pcm_matching.cpp:69-101); elm_map_save writes everything AddPoints / CalVoxelCovAll / CalPointCovAll produced
+ * (canonical points, voxel table, neighbourhood directory, covariances) and elm_map_load brings it back — host arrays
+ * validated, then uploaded to `device` (-1: host only) — without touching the raw cloud again. */
+int elm_map_save(const elm_map* map, const char* path);
+int elm_map_load(elm_map** out, const char* path, int device);
 
 /* Self-check of the neighbourhood directory the P2P/GICP search reads (test hook, host only): every centre key whose
  * 27 voxels (GetAdjacentVoxels range 2, voxel_hash_map.cpp:232-241) hold a stored point must be found by the 2-bucket

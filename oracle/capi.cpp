@@ -221,4 +221,39 @@ int orc_ekf_predict_imu(const EkfConfig* c, EkfStateBlob* s, double t, const dou
 int orc_ekf_update_pose(const EkfConfig* c, EkfStateBlob* s, const EkfMeasurement* m) { return EkfUpdatePose(*c, *s, *m) ? 1 : 0; }
 void orc_ekf_get_current_state(EkfStateBlob* s, double* ego) { EkfGetCurrentState(*s, ego); }
 
+// ---- result shaping (PcmMatching::PublishPcmOdom, pcm_matching.cpp:1082-1098; NormalizeCovariance, pcm_matching.hpp:247-273)
+// Test infrastructure like everything in oracle/: restates the reference line by line in plain loops.
+static void orc_normalize_cov(const double in[9], double out[9]) {
+    double c[9];
+    for (int i = 0; i < 9; ++i) c[i] = in[i];
+    double min_diag = std::min(c[0], std::min(c[4], c[8]));                 // hpp:252
+    const double min_threshold = 1e-9;
+    if (min_diag <= min_threshold) {                                        // hpp:256
+        for (int i = 0; i < 9; ++i) c[i] *= 1e9;                            // hpp:257
+        min_diag = std::min(c[0], std::min(c[4], c[8]));
+        if (min_diag < min_threshold) min_diag = min_threshold;             // hpp:260
+    }
+    for (int i = 0; i < 9; ++i) out[i] = std::min(c[i] / min_diag, 5.0);    // hpp:264-268
+}
+void orc_shape_pcm_covariance(const double* R, const double* local_cov, double icp_pose_std_m, double* cov36) {
+    const double std_m = std::max(icp_pose_std_m, 0.25);                    // cpp:1082
+    double RC[9], tc[9], rc[9], tn[9], rn[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        RC[3 * i + j] = 0.0;
+        for (int k = 0; k < 3; ++k) RC[3 * i + j] += R[3 * i + k] * local_cov[6 * k + j];
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {                // cpp:1085-1086: R C R^T
+        tc[3 * i + j] = 0.0;
+        for (int k = 0; k < 3; ++k) tc[3 * i + j] += RC[3 * i + k] * R[3 * j + k];
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) rc[3 * i + j] = local_cov[6 * (i + 3) + (j + 3)];  // cpp:1090
+    const double angle_std = std_m * M_PI / 180.0;                          // cpp:1093
+    orc_normalize_cov(tc, tn);
+    orc_normalize_cov(rc, rn);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {                // UpdateCovarianceField, hpp:275-290
+        cov36[6 * i + j] = tn[3 * i + j] * std_m * std_m;
+        cov36[6 * (i + 3) + (j + 3)] = rn[3 * i + j] * angle_std * angle_std;
+    }
+}
+
 }  // extern "C"

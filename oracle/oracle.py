@@ -79,6 +79,7 @@ def lib():
         L.orc_ekf_predict_imu.argtypes = [C.c_void_p, C.c_void_p, C.c_double, dp, dp]
         L.orc_ekf_update_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ekf_get_current_state.argtypes = [C.c_void_p, dp]
+        L.orc_shape_pcm_covariance.argtypes = [dp, dp, C.c_double, dp]
         _LIB = L
     return _LIB
 
@@ -251,3 +252,13 @@ class EkfAlgorithm:
         ego = np.zeros(26)
         lib().orc_ekf_get_current_state(C.byref(self.s), _d(ego))
         return ego
+
+
+def shape_pcm_covariance(R_ego, local_cov, icp_pose_std_m, cov36=None):
+    """PublishPcmOdom's covariance shaping (pcm_matching.cpp:1082-1098): fills the two 3x3 blocks of a 6x6 row-major pose
+    covariance (other entries keep the values of `cov36`, zeros by default)."""
+    R = np.ascontiguousarray(R_ego, dtype=np.float64).reshape(3, 3)
+    lc = np.ascontiguousarray(local_cov, dtype=np.float64).reshape(6, 6)
+    out = np.zeros((6, 6)) if cov36 is None else np.ascontiguousarray(cov36, dtype=np.float64).reshape(6, 6).copy()
+    lib().orc_shape_pcm_covariance(_d(R), _d(lc), float(icp_pose_std_m), _d(out))
+    return out

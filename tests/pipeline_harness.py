@@ -175,6 +175,7 @@ def gnss_time_compensation(meas, deq_state):
 # ------------------------------------------------------------------------------------------------ arms
 class OracleArm:
     name = "oracle"
+    shape_covariance = staticmethod(lambda R, cov, fit: O.shape_pcm_covariance(R, cov, fit))
 
     def __init__(self, raw_map, ekf_cfg_kwargs):
         from elimaloc_b200 import _capi
@@ -201,6 +202,11 @@ class OracleArm:
 
 class GpuArm:
     name = "gpu"
+
+    @staticmethod
+    def shape_covariance(R, cov, fit):
+        import elimaloc_b200 as E
+        return E.shape_pcm_covariance(R, cov, fit)
 
     def __init__(self, raw_map, ekf_cfg_kwargs, device=0):
         import elimaloc_b200 as E
@@ -306,7 +312,8 @@ def run(arm, world, n_scans, imu_dt=0.01, latency=0.03):
         pose, ok, fit, cov = arm.register(und, T_init)
         out["icp"].append(np.array(pose)); out["ok"].append(bool(ok)); out["fit"].append(float(fit)); out["t"].append(t_end)
         if ok:                                                     # pcm_matching.cpp:289-299
-            pc, rc = shape_pcm_covariance(pose[:3, :3], np.array(cov), fit)
+            c66 = arm.shape_covariance(pose[:3, :3], np.array(cov), fit)   # product / oracle implementation of the arm
+            pc, rc = c66[:3, :3].copy(), c66[3:, 3:].copy()
             meas = gnss_time_compensation(dict(t=t_end, pos=pose[:3, 3].copy(), quat=R_to_quat_wxyz(pose[:3, :3])), deq_state)
             if meas is not None:
                 arm.ekf.RunGnssUpdate(pekf.make_measurement(meas["t"], meas["pos"], meas["quat"], pc, rc, source=pekf.PCM))

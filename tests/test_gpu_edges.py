@@ -234,3 +234,17 @@ def test_exact_ties_and_near_ties(origin, exhaustive):
     gc, gt = reg.correspondences(local, gm, T, E.P2P, 5.0)
     oc, ot = O.correspondences(om, local, T, E.P2P, 5.0)
     assert np.array_equal(gc, oc) and np.array_equal(gt, ot)
+
+
+def test_registration_on_a_restored_map_is_bit_identical(small, tmp_path):
+    """elm_map_save -> elm_map_load -> RunRegister: the restored device map (points, directory, covariances) gives the same
+    bits as the map it was saved from, for every method."""
+    path = tmp_path / "small.elm"
+    small["gm"].Save(path)
+    lm = E.VoxelHashMap.Load(path, device=0)
+    scan = synth.scan_m(small["stored"], 2500, small["T_true"], seed=5)
+    for method in (E.P2P, E.GICP, E.VGICP, E.AVGICP):
+        cfg = E.RegistrationConfig(icp_method=method, max_iteration=5, **synth.timing_knobs())
+        a = small["greg"].RunRegister(scan, small["gm"], small["T0"], cfg)
+        b = small["greg"].RunRegister(scan, lm, small["T0"], cfg)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3]), method

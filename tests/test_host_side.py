@@ -137,3 +137,59 @@ def test_neighbourhood_directory_is_consistent(kind):
     assert entries >= pm.num_voxels() and slots >= entries and slots <= 8 * max(entries, 2)
     if kind == "single_point":
         assert entries == 27
+
+
+def test_map_file_round_trip(tmp_path):
+    """elm_map_save / elm_map_load: the restored map is identical (canonical arrays, covariances, directory) and corrupt
+    or foreign files are refused with ELM_ERR_IO."""
+    pm = E.VoxelHashMap(1.0, 30, device=-1)
+    pm.AddPoints(synth.map_u(40_000, 14.0, origin=-5.0))
+    pm.CalVoxelCovAll()
+    pm.CalPointCovAll(0.4)
+    path = tmp_path / "map.elm"
+    pm.Save(path)
+    lm = E.VoxelHashMap.Load(path, device=-1)
+    a, b = pm.export(True, True), lm.export(True, True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert lm.directory_check() == pm.directory_check() and lm.directory_check()[2] == 0
+    assert not lm.Empty() and lm.num_points() == pm.num_points()
+    # AddPoints keeps working on a restored map (incremental build, voxel_hash_map.cpp:268-285)
+    extra = synth.map_u(5_000, 14.0, origin=-5.0, seed=99)
+    pm.AddPoints(extra)
+    lm.AddPoints(extra)
+    assert np.array_equal(pm.export()["pxyz"], lm.export()["pxyz"])
+    raw = open(path, "rb").read()
+    for bad in (raw[: len(raw) // 2], b"not a map" + raw[9:], raw[:12] + bytes([raw[12] ^ 0xFF]) + raw[13:]):
+        p2 = tmp_path / "bad.elm"
+        p2.write_bytes(bad)
+        with pytest.raises(E.ElmError) as ei:
+            E.VoxelHashMap.Load(p2, device=-1)
+        assert ei.value.status == _capi.ELM_ERR_IO
+    with pytest.raises(E.ElmError):
+        E.VoxelHashMap.Load(tmp_path / "missing.elm", device=-1)
+
+
+def test_result_shaping_matches_oracle_and_closed_forms():
+    """elm_shape_pcm_covariance vs the oracle restatement of PublishPcmOdom (pcm_matching.cpp:1082-1098) on random SPD
+    inputs, plus the branches of NormalizeCovariance (pcm_matching.hpp:247-273): cap at 5, the 1e9 rescue of tiny diagonals,
+    the 0.25 m floor of the std, untouched off-diagonal blocks."""
+    rng = np.random.default_rng(3)
+    for k in range(50):
+        A = rng.normal(size=(6, 6))
+        cov = A @ A.T * 10.0 ** rng.integers(-14, 2)
+        Rz = synth.se3([0, 0, 0], rng.normal(size=3))[:3, :3]
+        std = float(rng.choice([0.01, 0.25, 0.4, 3.0]))
+        seed36 = rng.normal(size=(6, 6))
+        g = E.shape_pcm_covariance(Rz, cov, std, seed36)
+        o = O.shape_pcm_covariance(Rz, cov, std, seed36)
+        assert np.allclose(g, o, rtol=1e-12, atol=1e-300), k
+        assert np.array_equal(g[:3, 3:], seed36[:3, 3:]) and np.array_equal(g[3:, :3], seed36[3:, :3])
+    # closed forms: identity local_cov (every method but GICP, registration.cpp:280) -> std^2 I and (std pi/180)^2 I
+    g = E.shape_pcm_covariance(np.eye(3), np.eye(6), 0.1)
+    assert np.allclose(g[:3, :3], 0.25 ** 2 * np.eye(3)) and np.allclose(g[3:, 3:], (0.25 * np.pi / 180) ** 2 * np.eye(3))
+    g = E.shape_pcm_covariance(np.eye(3), np.diag([1.0, 2.0, 100.0, 1e-12, 2e-12, 1.0]), 1.0)
+    assert np.allclose(np.diag(g)[:3], [1.0, 2.0, 5.0])                                   # normalised by the minimum, capped at 5
+    assert np.allclose(np.diag(g)[3:], np.array([1.0, 2.0, 5.0]) * (np.pi / 180) ** 2)     # x1e9 rescue: (1e-3, 2e-3, 1e9) / 1e-3, capped
+    g = E.shape_pcm_covariance(np.eye(3), np.diag([0.0, 1e-30, 1e-20, 1.0, 1.0, 1.0]), 1.0)
+    assert np.allclose(np.diag(g)[:3], [0.0, 1e-12, 0.01])                                # still below the threshold: divided by 1e-9
