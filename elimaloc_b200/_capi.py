@@ -103,6 +103,9 @@ SIGNATURES = {
     "elm_registration_set_exhaustive": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_deskew_points": (C.c_int, [C.c_void_p, _fp, _fp, C.c_size_t, C.POINTER(DeskewTables), _fp]),
     "elm_deskew_points_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(DeskewTables), C.c_void_p]),
+    "elm_scan_preprocess": (C.c_int, [C.c_void_p, _fp, _fp, C.c_size_t, C.c_double, C.c_double, _fp, _fp, _ip, C.POINTER(C.c_size_t)]),
+    "elm_scan_preprocess_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "elm_ekf_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(EkfConfig), C.c_int, C.c_void_p]),
     "elm_ekf_destroy": (None, [C.c_void_p]),
     "elm_ekf_predict_imu": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),

@@ -18,6 +18,7 @@
 #include "deskew.cuh"
 #include "ekf.cuh"
 #include "icp_kernels.cuh"
+#include "scan_prep.cuh"
 
 namespace {
 
@@ -205,6 +206,14 @@ struct elm_registration {
     float* d_dsk_in = nullptr;   // xyz | rel_time
     float* d_dsk_out = nullptr;
     size_t dsk_cap = 0;
+    // scan pre-processing scratch (scan_prep.cu)
+    elm::ScanPrepScratch prep{};
+    size_t prep_cap = 0;
+    int* d_prep_n = nullptr;
+    float* d_prep_in = nullptr;    // host-buffer entry point: xyz | aux in, xyz | aux | index out
+    float* d_prep_out = nullptr;
+    int* d_prep_idx = nullptr;
+    size_t prep_io_cap = 0;
     // NCCL
     void* comm = nullptr;
     int rank = 0, world = 1;
@@ -217,6 +226,8 @@ struct elm_registration {
     ~elm_registration() {
         cudaSetDevice(device);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        cudaFree(prep.tkeys); cudaFree(prep.tmin); cudaFree(prep.keep); cudaFree(prep.block_count); cudaFree(prep.block_offset);
+        cudaFree(prep.error); cudaFree(d_prep_n); cudaFree(d_prep_in); cudaFree(d_prep_out); cudaFree(d_prep_idx);
         for (void* p : peer_opened) if (p) cudaIpcCloseMemHandle(p);
         cudaFree(d_mailbox);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
@@ -901,6 +912,71 @@ int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_
     if (rc) return rc;
     ELM_CUDA(cudaMemcpyAsync(xyz_out, reg->d_dsk_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    return ELM_OK;
+}
+
+int elm_scan_preprocess_device(elm_registration* reg, const float* d_xyz, const float* d_aux, size_t n, double max_dist, double voxel_size,
+                               float* d_xyz_out, float* d_aux_out, int32_t* d_index_out, size_t* n_out) {
+    if (!reg || !n_out || (n && (!d_xyz || !d_xyz_out)) || (d_aux_out && !d_aux)) return fail(ELM_ERR_INVALID, "elm_scan_preprocess: bad argument");
+    if (n > 0x7fffffffull / 4) return fail(ELM_ERR_INVALID, "scan too large");
+    *n_out = 0;
+    if (n == 0) return ELM_OK;
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (n > reg->prep_cap) {
+        cudaFree(reg->prep.tkeys); cudaFree(reg->prep.tmin); cudaFree(reg->prep.keep); cudaFree(reg->prep.block_count); cudaFree(reg->prep.block_offset);
+        reg->prep = elm::ScanPrepScratch{};
+        reg->prep_cap = 0;
+        const size_t cap = (n + 4095) / 4096 * 4096, slots = elm::scan_prep_table_slots(cap), blocks = (cap + 255) / 256;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.tkeys), slots * sizeof(unsigned long long)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.tmin), slots * sizeof(uint32_t)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.keep), cap));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.block_count), blocks * sizeof(uint32_t)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.block_offset), blocks * sizeof(uint32_t)));
+        reg->prep.table_slots = slots;
+        reg->prep_cap = cap;
+    }
+    if (!reg->prep.error) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.error), sizeof(int)));
+    if (!reg->d_prep_n) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_prep_n), sizeof(int)));
+    ELM_CUDA(elm::launch_scan_prep(d_xyz, d_aux, static_cast<int>(n), max_dist, voxel_size, reg->prep, d_xyz_out, d_aux_out, d_index_out,
+                                   reg->d_prep_n, reg->stream));
+    int h[2] = {0, 0};
+    ELM_CUDA(cudaMemcpyAsync(&h[0], reg->d_prep_n, sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaMemcpyAsync(&h[1], reg->prep.error, sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    if (h[1]) return fail(ELM_ERR_RANGE, "scan point not finite or beyond +-2^20 voxels of the down-sampling grid");
+    *n_out = static_cast<size_t>(h[0]);
+    return ELM_OK;
+}
+
+int elm_scan_preprocess(elm_registration* reg, const float* xyz, const float* aux, size_t n, double max_dist, double voxel_size, float* xyz_out,
+                        float* aux_out, int32_t* index_out, size_t* n_out) {
+    if (!reg || !n_out || (n && (!xyz || !xyz_out)) || (aux_out && !aux)) return fail(ELM_ERR_INVALID, "elm_scan_preprocess: bad argument");
+    *n_out = 0;
+    if (n == 0) return ELM_OK;
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (n > reg->prep_io_cap) {
+        cudaFree(reg->d_prep_in); cudaFree(reg->d_prep_out); cudaFree(reg->d_prep_idx);
+        reg->d_prep_in = reg->d_prep_out = nullptr; reg->d_prep_idx = nullptr;
+        reg->prep_io_cap = 0;
+        const size_t cap = (n + 4095) / 4096 * 4096;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_prep_in), cap * 4 * sizeof(float)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_prep_out), cap * 4 * sizeof(float)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_prep_idx), cap * sizeof(int)));
+        reg->prep_io_cap = cap;
+    }
+    float* d_aux = aux ? reg->d_prep_in + 3 * reg->prep_io_cap : nullptr;
+    float* d_aux_out = aux_out ? reg->d_prep_out + 3 * reg->prep_io_cap : nullptr;
+    ELM_CUDA(cudaMemcpyAsync(reg->d_prep_in, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    if (aux) ELM_CUDA(cudaMemcpyAsync(d_aux, aux, n * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    const int rc = elm_scan_preprocess_device(reg, reg->d_prep_in, d_aux, n, max_dist, voxel_size, reg->d_prep_out, d_aux_out,
+                                              index_out ? reg->d_prep_idx : nullptr, n_out);
+    if (rc) return rc;
+    if (*n_out) {
+        ELM_CUDA(cudaMemcpyAsync(xyz_out, reg->d_prep_out, *n_out * 3 * sizeof(float), cudaMemcpyDeviceToHost, reg->stream));
+        if (aux_out) ELM_CUDA(cudaMemcpyAsync(aux_out, d_aux_out, *n_out * sizeof(float), cudaMemcpyDeviceToHost, reg->stream));
+        if (index_out) ELM_CUDA(cudaMemcpyAsync(index_out, reg->d_prep_idx, *n_out * sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
+        ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    }
     return ELM_OK;
 }
 

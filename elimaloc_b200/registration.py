@@ -263,6 +263,21 @@ class Registration:
         check(lib().elm_deskew_points_device(self._h, C.c_void_p(d_xyz_ptr), C.c_void_p(d_time_ptr), int(n), C.byref(st),
                                              C.c_void_p(d_out_ptr)))
 
+    # ---- scan pre-processing (FilterPointsByDistance + VoxelDownsample, pcm_matching.cpp:451-465, voxel_hash_map.hpp:260-283) ----
+    def PreprocessScan(self, xyz, max_dist=0.0, voxel_size=0.0, aux=None):
+        """Returns (xyz of the survivors in input order, their aux values or None, their input indices)."""
+        xyz = _xyz(xyz)
+        n = xyz.shape[0]
+        out = np.zeros_like(xyz)
+        idx = np.zeros(n, np.int32)
+        a = np.ascontiguousarray(aux, dtype=np.float32) if aux is not None else None
+        ao = np.zeros(n, np.float32) if aux is not None else None
+        m = C.c_size_t(0)
+        check(lib().elm_scan_preprocess(self._h, _f(xyz), _f(a) if a is not None else None, n, float(max_dist), float(voxel_size), _f(out),
+                                        _f(ao) if ao is not None else None, _i(idx), C.byref(m)))
+        k = int(m.value)
+        return out[:k], (ao[:k] if ao is not None else None), idx[:k]
+
     # ---- multi-GPU ----
     @staticmethod
     def comm_unique_id():

@@ -205,6 +205,19 @@ int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_
 int elm_deskew_points_device(elm_registration* reg, const float* d_xyz, const float* d_rel_time, size_t n,
                              const elm_deskew_tables* tables, float* d_xyz_out);
 
+/* Scan pre-processing — the two serial steps the node runs on every scan before RunRegister, as one stable
+ * compaction on the GPU:
+ *   FilterPointsByDistance (pcm_matching.cpp:451-465): keep iff sqrt(x^2 + y^2 + z^2) <= max_dist (float32 arithmetic);
+ *   VoxelDownsample (voxel_hash_map.hpp:260-283): keep the first point (input order) of every voxel floor(p / voxel_size).
+ * max_dist <= 0 / voxel_size <= 0 switch a step off (the node filters the raw scan, deskews, then down-samples: call it
+ * twice around elm_deskew_points_device).  Survivors keep their input order (the reference emits them in unordered_map
+ * order, which is implementation-defined).  aux / aux_out: one float per point carried along (the relative time stamp);
+ * index_out: input index of every survivor; both optional.  n_out: survivors. */
+int elm_scan_preprocess(elm_registration* reg, const float* xyz, const float* aux, size_t n, double max_dist, double voxel_size,
+                        float* xyz_out, float* aux_out, int32_t* index_out, size_t* n_out);
+int elm_scan_preprocess_device(elm_registration* reg, const float* d_xyz, const float* d_aux, size_t n, double max_dist,
+                               double voxel_size, float* d_xyz_out, float* d_aux_out, int32_t* d_index_out, size_t* n_out);
+
 /* ---- EKF (ekf_localization) ------------------------------------------------------------------------------------ */
 /* The 27-state filter of EkfAlgorithm (README: "24-DOF"; STATE_ORDER is 27, ekf_algorithm.hpp:41-69) with its state and
  * covariance resident in HBM.  In scope: Init, RunPredictionImu, RunGnssUpdate for the PCM / PCM_INIT sources,

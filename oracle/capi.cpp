@@ -221,6 +221,36 @@ int orc_ekf_predict_imu(const EkfConfig* c, EkfStateBlob* s, double t, const dou
 int orc_ekf_update_pose(const EkfConfig* c, EkfStateBlob* s, const EkfMeasurement* m) { return EkfUpdatePose(*c, *s, *m) ? 1 : 0; }
 void orc_ekf_get_current_state(EkfStateBlob* s, double* ego) { EkfGetCurrentState(*s, ego); }
 
+// ---- scan pre-processing: FilterPointsByDistance (pcm_matching.cpp:451-465) then VoxelDownsample (vhm.hpp:260-283) ----
+// Writes the INPUT INDEX of every survivor (input order); returns their number.  max_dist <= 0 / voxel_size <= 0 skip a step.
+size_t orc_scan_preprocess(const float* xyz, size_t n, double max_dist, double voxel_size, int32_t* index_out) {
+    std::vector<size_t> kept;
+    kept.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (max_dist > 0.0) {
+            const double distance = std::sqrt(x * x + y * y + z * z);   // float expression, float sqrt, widened (cpp:456)
+            if (distance > max_dist) continue;                          // cpp:457
+        }
+        kept.push_back(i);
+    }
+    size_t m = 0;
+    if (voxel_size > 0.0) {
+        std::vector<PointStruct> pts(kept.size());
+        for (size_t k = 0; k < kept.size(); ++k) {
+            pts[k].pose = V3(xyz[3 * kept[k]], xyz[3 * kept[k] + 1], xyz[3 * kept[k] + 2]);
+            pts[k].local = pts[k].pose;
+            pts[k].intensity = static_cast<double>(k);                  // carries the position through VoxelDownsample
+        }
+        VoxelHashMap grid_owner;
+        grid_owner.Init(1.0, 1);
+        for (const PointStruct& p : grid_owner.VoxelDownsample(pts, voxel_size)) index_out[m++] = static_cast<int32_t>(kept[static_cast<size_t>(p.intensity)]);
+    } else {
+        for (size_t k : kept) index_out[m++] = static_cast<int32_t>(k);
+    }
+    return m;
+}
+
 // ---- result shaping (PcmMatching::PublishPcmOdom, pcm_matching.cpp:1082-1098; NormalizeCovariance, pcm_matching.hpp:247-273)
 // Test infrastructure like everything in oracle/: restates the reference line by line in plain loops.
 static void orc_normalize_cov(const double in[9], double out[9]) {

@@ -80,6 +80,8 @@ def lib():
         L.orc_ekf_update_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ekf_get_current_state.argtypes = [C.c_void_p, dp]
         L.orc_shape_pcm_covariance.argtypes = [dp, dp, C.c_double, dp]
+        L.orc_scan_preprocess.restype = C.c_size_t
+        L.orc_scan_preprocess.argtypes = [fp, C.c_size_t, C.c_double, C.c_double, ip]
         _LIB = L
     return _LIB
 
@@ -262,3 +264,12 @@ def shape_pcm_covariance(R_ego, local_cov, icp_pose_std_m, cov36=None):
     out = np.zeros((6, 6)) if cov36 is None else np.ascontiguousarray(cov36, dtype=np.float64).reshape(6, 6).copy()
     lib().orc_shape_pcm_covariance(_d(R), _d(lc), float(icp_pose_std_m), _d(out))
     return out
+
+
+def scan_preprocess(xyz, max_dist=0.0, voxel_size=0.0):
+    """FilterPointsByDistance + VoxelDownsample (pcm_matching.cpp:451-465, voxel_hash_map.hpp:260-283): input indices of the
+    survivors, in input order."""
+    src = _xyz(xyz)
+    idx = np.zeros(src.shape[0], np.int32)
+    m = lib().orc_scan_preprocess(_f(src), src.shape[0], float(max_dist), float(voxel_size), _i(idx))
+    return idx[:m]

@@ -248,3 +248,23 @@ def test_registration_on_a_restored_map_is_bit_identical(small, tmp_path):
         a = small["greg"].RunRegister(scan, small["gm"], small["T0"], cfg)
         b = small["greg"].RunRegister(scan, lm, small["T0"], cfg)
         assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3]), method
+
+
+@pytest.mark.parametrize("n", [1, 255, 5000, 200_000])
+def test_scan_preprocess_matches_oracle(n):
+    """FilterPointsByDistance + VoxelDownsample on the GPU (pcm_matching.cpp:451-465, voxel_hash_map.hpp:260-283) vs the
+    oracle: same survivors, same (input) order, bit-identical coordinates; the relative time stamps travel with them."""
+    rng = np.random.default_rng(n)
+    xyz = ((rng.random((n, 3), dtype=np.float32) * 2 - 1) * np.float32(60.0)).astype(np.float32)
+    xyz[::7] = np.round(xyz[::7] * 2) / 2            # points exactly on voxel faces of the 0.5 m / 1.5 m grids
+    xyz[::11, 0] = np.float32(50.0)                  # ... and exactly at the distance limit along x
+    xyz[::11, 1:] = 0
+    rel = rng.random(n).astype(np.float32)
+    reg = E.Registration(device=0)
+    for max_dist, vs in [(50.0, 0.0), (0.0, 1.5), (50.0, 1.5), (45.5, 0.5), (0.0, 0.0)]:
+        want = O.scan_preprocess(xyz, max_dist, vs)
+        got_xyz, got_rel, got_idx = reg.PreprocessScan(xyz, max_dist, vs, aux=rel)
+        assert np.array_equal(got_idx, want), (max_dist, vs)
+        assert np.array_equal(got_xyz, xyz[want]) and np.array_equal(got_rel, rel[want])
+    with pytest.raises(E.ElmError):                  # a voxel key that cannot be packed is reported, not silently dropped
+        reg.PreprocessScan(np.array([[1e9, 0, 0]], np.float32), 0.0, 0.5)
