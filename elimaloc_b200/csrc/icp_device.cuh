@@ -42,12 +42,13 @@ constexpr int kIdxJtr = 21, kIdxRes = 27, kIdxNcorr = 28, kIdxNtotal = 29;
 
 // Peer-memory exchange of the accumulators (multi-GPU): every rank owns one mailbox in its HBM, mapped into the other
 // ranks' address spaces (CUDA IPC over NVLink).  Rank r writes its 32 sums straight into slot [parity][r] of EVERY
-// mailbox and then raises flag [parity][r] = sequence number; each rank waits for all flags of its own mailbox and sums
-// the slots in rank order — bit-identical on all ranks, no broadcast, no separate collective launch.
+// mailbox; each rank waits until all slots of its own mailbox carry the current sequence number and sums them in rank
+// order — bit-identical on all ranks, no broadcast, no separate collective launch.  The slots are self-validating
+// ("LL" style): every fp64 value travels as two 8-byte words {32 data bits, 32-bit sequence tag}; an 8-byte store is
+// atomic, so a word whose tag matches carries valid data — no fence, no separate flag write, ONE NVLink hop.
 constexpr int kMaxPeers = 8;
 struct PeerMailbox {
-    double acc[2][kMaxPeers][kAcc];
-    unsigned long long flag[2][kMaxPeers];
+    unsigned long long word[2][kMaxPeers][kAcc][2];  // [parity][source rank][accumulator][low / high half]: data | tag << 32
     unsigned long long seq;  // exchanges completed by the owner (all ranks advance in lockstep)
 };
 struct PeerComm {

@@ -755,26 +755,28 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
         __syncthreads();
         const unsigned long long seq = s_seq;
         const int par = static_cast<int>(seq & 1);
-        if (tid < pc.world * kAcc) {
+        const unsigned long long tag = (seq & 0xffffffffull) << 32;
+        if (tid < pc.world * kAcc) {  // one thread per (destination rank, accumulator): two self-validating 8-byte stores
             const int p = tid / kAcc, k = tid % kAcc;
-            *reinterpret_cast<volatile double*>(&pc.box[p]->acc[par][pc.rank][k]) = s_acc[k];
+            const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(s_acc[k]));
+            volatile unsigned long long* w = pc.box[p]->word[par][pc.rank][k];
+            w[0] = (bits & 0xffffffffull) | tag;
+            w[1] = (bits >> 32) | tag;
         }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < pc.world) {
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&pc.box[tid]->flag[par][pc.rank]), "l"(seq) : "memory");
-            const long long t0 = clock64();
-            unsigned long long f;
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&mine->flag[par][tid]) : "memory");
-                if (f >= seq) break;
-                if (clock64() - t0 > 6000000000ll) { s_timeout = 1; break; }  // ~3 s: a rank died; give up instead of hanging the GPU
-            }
-        }
-        __syncthreads();
+        __syncthreads();  // (s_acc is overwritten below)
         if (tid < kAcc) {
             double t = 0.0;
-            for (int r = 0; r < pc.world; ++r) t += *reinterpret_cast<volatile double*>(&mine->acc[par][r][tid]);  // rank order: identical on every rank
+            const long long t0 = clock64();
+            for (int r = 0; r < pc.world; ++r) {  // rank order: identical on every rank
+                const volatile unsigned long long* w = mine->word[par][r][tid];
+                unsigned long long lo, hi;
+                for (;;) {
+                    lo = w[0]; hi = w[1];
+                    if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+                    if (clock64() - t0 > 6000000000ll) { s_timeout = 1; lo = hi = 0; break; }  // ~3 s: a rank died; do not hang the GPU
+                }
+                t += __longlong_as_double(static_cast<long long>((lo & 0xffffffffull) | (hi << 32)));
+            }
             st->acc[tid] = t;
             s_acc[tid] = t;
         }
