@@ -91,9 +91,12 @@ __device__ __forceinline__ int dir_lookup(const MapView& map, int kx, int ky, in
     dir_buckets(key, map.bmask, b1, b2);
     // one 32-byte load per bucket (sm_100 LDG.E.256): half the L1TEX requests of four 16-byte loads
     uint4 s0, s1, s2, s3;
-    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef ELM_DIR_LD
+#define ELM_DIR_LD "ld.global.nc.v8.u32"
+#endif
+    asm(ELM_DIR_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(s0.x), "=r"(s0.y), "=r"(s0.z), "=r"(s0.w), "=r"(s1.x), "=r"(s1.y), "=r"(s1.z), "=r"(s1.w) : "l"(map.dslots + 2 * static_cast<size_t>(b1)));
-    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm(ELM_DIR_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(s2.x), "=r"(s2.y), "=r"(s2.z), "=r"(s2.w), "=r"(s3.x), "=r"(s3.y), "=r"(s3.z), "=r"(s3.w) : "l"(map.dslots + 2 * static_cast<size_t>(b2)));
     const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
     if (s0.x == klo && s0.y == khi) { centre = make_uint2(s0.z, s0.w); return static_cast<int>(2 * b1); }
@@ -127,7 +130,10 @@ struct Best {
 // 128-byte line, so the L1TEX tag stage — one line per cycle — bounds the search (measured: ~14.5 B/cycle/SM with 16-byte
 // loads, profiles/r01b_*); a 32-byte load moves twice the points per tag lookup.
 __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef ELM_PTS_LD
+#define ELM_PTS_LD "ld.global.nc.v8.f32"
+#endif
+    asm(ELM_PTS_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 // Stream `n` consecutive stored points starting at index idx0 and fold them into `b`, exactly (ascending index + strict <
@@ -608,9 +614,11 @@ __device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc,
 #pragma unroll
     for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
     st->iterations += 1;
-    const double R[9] = {D0, D1, D2, D4, D5, D6, D8, D9, D10};
-    const double tn = rotation_angle(R) + sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);  // reg.cpp:381-384
-    if (tn < prm.term_thr) { st->done = 1; return; }                                      // reg.cpp:385-387
+    if (prm.term_thr > 0.0) {  // (the metric is >= 0: with a threshold <= 0 the test of reg.cpp:385 can never fire)
+        const double R[9] = {D0, D1, D2, D4, D5, D6, D8, D9, D10};
+        const double tn = rotation_angle(R) + sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);  // reg.cpp:381-384
+        if (tn < prm.term_thr) { st->done = 1; return; }                                      // reg.cpp:385-387
+    }
     double Ti[16], Ri[9];
     inverse4(Tn, Ti);
     const double Rn[9] = {Tn[0], Tn[1], Tn[2], Tn[4], Tn[5], Tn[6], Tn[8], Tn[9], Tn[10]};
@@ -725,15 +733,19 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
         const int k = tid & 31, g = tid >> 5;
         double v = 0.0;
         const int nb = static_cast<int>(gridDim.x);
-        int b = g;
-        for (; b + 7 * kIcpWarps < nb; b += 8 * kIcpWarps) {  // 8 independent loads in flight, summed in index order
-            double t[8];
+        // 16 loads in flight per thread, summed in index order; rows past the end contribute +0.0 (the tail used to be one
+        // dependent load per row: 9 round trips for 296 rows instead of 3)
+        constexpr int kDepth = 16;
+        for (int b = g; b < nb; b += kDepth * kIcpWarps) {
+            double t[kDepth];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = __ldcg(partials + (b + u * kIcpWarps) * kAcc + k);
+            for (int u = 0; u < kDepth; ++u) {
+                const int row = b + u * kIcpWarps;
+                t[u] = (row < nb) ? __ldcg(partials + static_cast<size_t>(row) * kAcc + k) : 0.0;
+            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v += t[u];
+            for (int u = 0; u < kDepth; ++u) v += t[u];
         }
-        for (; b < nb; b += kIcpWarps) v += __ldcg(partials + b * kAcc + k);
         s_red[g][k] = v;
     }
     __syncthreads();
