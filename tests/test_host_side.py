@@ -193,3 +193,28 @@ def test_result_shaping_matches_oracle_and_closed_forms():
     assert np.allclose(np.diag(g)[3:], np.array([1.0, 2.0, 5.0]) * (np.pi / 180) ** 2)     # x1e9 rescue: (1e-3, 2e-3, 1e9) / 1e-3, capped
     g = E.shape_pcm_covariance(np.eye(3), np.diag([0.0, 1e-30, 1e-20, 1.0, 1.0, 1.0]), 1.0)
     assert np.allclose(np.diag(g)[:3], [0.0, 1e-12, 0.01])                                # still below the threshold: divided by 1e-9
+
+
+def test_new_entry_points_validate_their_arguments():
+    """argument checks of the entry points added for SURVEY 8f and the peer exchange (no GPU needed: they fail before any CUDA call)"""
+    L = _capi.lib()
+    cov, R = np.eye(6), np.eye(3)
+    dp = C.POINTER(C.c_double)
+    assert L.elm_shape_pcm_covariance(None, cov.ctypes.data_as(dp), 1.0, cov.ctypes.data_as(dp)) == _capi.ELM_ERR_INVALID
+    assert L.elm_shape_pcm_covariance(R.ctypes.data_as(dp), cov.ctypes.data_as(dp), 1.0, None) == _capi.ELM_ERR_INVALID
+    assert L.elm_map_save(None, b"/tmp/x") == _capi.ELM_ERR_INVALID
+    h = C.c_void_p()
+    assert L.elm_map_load(C.byref(h), None, -1) == _capi.ELM_ERR_INVALID
+    assert L.elm_map_load(C.byref(h), b"/nonexistent/dir/map.elm", -1) == _capi.ELM_ERR_IO
+    assert b"cannot open" in L.elm_last_error()
+    n = C.c_size_t(7)
+    assert L.elm_scan_preprocess(None, None, None, 0, 0.0, 0.0, None, None, None, C.byref(n)) == _capi.ELM_ERR_INVALID
+    assert L.elm_registration_peer_export(None, None) == _capi.ELM_ERR_INVALID
+    assert L.elm_registration_peer_attach(None, None, 0, 1) == _capi.ELM_ERR_INVALID
+    u = C.c_uint64(0)
+    assert L.elm_map_directory_check(None, C.byref(u), C.byref(u), C.byref(u)) == _capi.ELM_ERR_INVALID
+    pm = E.VoxelHashMap(1.0, 30, device=-1)
+    with pytest.raises(E.ElmError) as ei:   # more points per voxel than a column descriptor can count
+        E.VoxelHashMap(1.0, 2000, device=-1).AddPoints(np.zeros((1, 3), np.float32))
+    assert ei.value.status == _capi.ELM_ERR_RANGE
+    assert pm.directory_check() == (0, 0, 0)   # empty map: empty directory
