@@ -1,8 +1,8 @@
 // registration_shim.hpp — drop-in for pcm_matching's registration.hpp / voxel_hash_map.hpp on top of the C ABI of
 // libelimaloc_b200.so, so that pcm_matching.cpp compiles UNCHANGED (it keeps calling local_map_.Init / AddPoints /
 // CalVoxelCovAll / CalPointCovAll and registration_.RunRegister exactly as at pcm_matching.cpp:82-101, 280-282,
-// 412-414).  Header-only; needs Eigen (the node already has it).  It is NOT compiled in this repository's CI because
-// the build image has no Eigen/ROS — the C ABI underneath is what the tests exercise.
+// 412-414).  Header-only; needs Eigen (the node already has it).  The build image has no Eigen/ROS: tests/test_shim.py
+// compiles it against a minimal stand-in (tests/mock_eigen) and runs the node's call sequence through it.
 //
 // Reference interface replaced:
 //   struct PointStruct / CovStruct          pcm_matching/include/voxel_hash_map.hpp:41-87   (layout kept)
@@ -16,6 +16,10 @@
 #include <vector>
 
 #include "elimaloc_b200.h"
+
+#ifndef ELM_SHIM_DEVICE
+#define ELM_SHIM_DEVICE 0  // CUDA device ordinal the node's map and registration live on
+#endif
 
 namespace Eigen {
 using Matrix6d = Eigen::Matrix<double, 6, 6>;
@@ -76,7 +80,7 @@ struct VoxelHashMap {
     void Init(double voxel_size, int max_points_per_voxel) {
         if (h_) elm_map_destroy(h_);
         h_ = nullptr;
-        elm_shim::check(elm_map_create(&h_, voxel_size, max_points_per_voxel, /*device=*/0));
+        elm_shim::check(elm_map_create(&h_, voxel_size, max_points_per_voxel, ELM_SHIM_DEVICE));
         voxel_size_ = voxel_size;
         max_points_per_voxel_ = max_points_per_voxel;
     }
@@ -104,7 +108,7 @@ struct Registration {
     ~Registration() { if (h_) elm_registration_destroy(h_); }
     void Init(RegistrationConfig config) {
         config_ = config;
-        if (!h_) elm_shim::check(elm_registration_create(&h_, /*device=*/0, /*stream=*/nullptr));
+        if (!h_) elm_shim::check(elm_registration_create(&h_, ELM_SHIM_DEVICE, /*stream=*/nullptr));
     }
     // registration.hpp:122-124 — identical signature
     Eigen::Matrix4d RunRegister(const std::vector<PointStruct>& source_local, const VoxelHashMap& voxel_map,
