@@ -13,6 +13,8 @@
 #include <memory>
 #include <atomic>
 #include <thread>
+#include <chrono>
+#include <cstdlib>
 
 namespace elm {
 
@@ -124,88 +126,228 @@ void plane_regularize(const double cov[9], double out[9], double normal[3]) {
     if (normal) { normal[0] = n[0]; normal[1] = n[1]; normal[2] = n[2]; }
 }
 
+namespace {
+// ELM_BUILD_TIMING=1: stage times of the host builder on stderr (developer aid)
+struct StageTimer {
+    bool on = std::getenv("ELM_BUILD_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[host map] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
+// Parallel, bit-identical restatement of the sequential insert: points are partitioned into x-slabs of voxels (the packed
+// key's most significant field, so slab order is key order), every slab is sorted by (voxel, arrival) and filtered
+// independently — voxels never interact (AddPointWithSpacing looks only at the points already kept in the SAME voxel), and
+// inside a voxel the arrival order is preserved — and the kept points of the slabs are concatenated.  Records carry their
+// coordinates, so after the partition pass every stage streams through memory.
 std::string HostMap::add_points(const float* xyz, size_t n) {
     if (n == 0) return "";
+    StageTimer timer;
     if (cap > static_cast<int>(kDirCountMask)) return "max_points_per_voxel above 1023 does not fit the column descriptors";
     const size_t P0 = P();
     const size_t total = P0 + n;
     if (total >= (1ull << 32)) return "more than 2^32 points";
-    // 1. keys: stored points keep their voxel; new points: static_cast<int>(p / voxel_size) — truncation toward zero.
-    struct Rec { uint64_t key; uint32_t idx; };
-    std::vector<Rec> recs(total);
-    for (size_t v = 0; v < V(); ++v)
-        for (uint32_t p = vstart[v]; p < vstart[v + 1]; ++p) recs[p] = Rec{vkey[v], p};
+    struct Rec { uint64_t key; uint32_t idx; float x, y, z; };  // idx = arrival rank: stored points first (they arrived earlier)
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    const size_t T = std::max<size_t>(1, std::min<size_t>(hw, (total + (1u << 16) - 1) >> 16));
+
+    // 1. keys.  Stored points keep their voxel; new points: static_cast<int>(p / voxel_size) — truncation toward zero (vhm.cpp:275).
+    std::vector<uint64_t> keys(total);
     std::atomic<bool> bad{false};
     const double vs = voxel_size;
-    parallel_for(n, 1 << 16, [&](size_t b, size_t e) {
-        for (size_t i = b; i < e; ++i) {
+    parallel_for(V(), 1 << 12, [&](size_t vb, size_t ve) {
+        for (size_t v = vb; v < ve; ++v) for (uint32_t p = vstart[v]; p < vstart[v + 1]; ++p) keys[p] = vkey[v];
+    });
+    parallel_for(n, 1 << 16, [&](size_t b0, size_t e0) {
+        for (size_t i = b0; i < e0; ++i) {
             const double qx = static_cast<double>(xyz[3 * i]) / vs, qy = static_cast<double>(xyz[3 * i + 1]) / vs,
                          qz = static_cast<double>(xyz[3 * i + 2]) / vs;
             // (two voxels of margin so that every centre key whose neighbourhood reaches a stored voxel is itself packable)
             const double lim = static_cast<double>(kKeyBias - 2);
-            if (!(std::fabs(qx) < lim && std::fabs(qy) < lim && std::fabs(qz) < lim)) { bad = true; continue; }
-            recs[P0 + i] = Rec{pack_key(static_cast<int32_t>(qx), static_cast<int32_t>(qy), static_cast<int32_t>(qz)),
-                               static_cast<uint32_t>(P0 + i)};
+            if (!(std::fabs(qx) < lim && std::fabs(qy) < lim && std::fabs(qz) < lim)) { bad = true; keys[P0 + i] = 0; continue; }
+            keys[P0 + i] = pack_key(static_cast<int32_t>(qx), static_cast<int32_t>(qy), static_cast<int32_t>(qz));
         }
     });
     if (bad) return "map point outside +-2^20 voxels per axis (or not finite)";
-    // 2. stable order: (key, arrival index).  Stored points precede new ones inside their voxel.
-    std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.key != b.key ? a.key < b.key : a.idx < b.idx; });
-    // 3. voxel groups
-    std::vector<size_t> gstart;
-    for (size_t i = 0; i < total; ++i) if (i == 0 || recs[i].key != recs[i - 1].key) gstart.push_back(i);
-    const size_t G = gstart.size();
-    gstart.push_back(total);
-    auto coord = [&](uint32_t idx, int c) -> float { return idx < P0 ? pxyz[3 * idx + c] : xyz[3 * (idx - P0) + c]; };
-    // 4. per-voxel sequential spacing filter (AddPointWithSpacing), voxels in parallel
+    timer.lap("keys");
+
+    // 2. slabs: bucket = (biased x field - min) >> shift, at most 2^14 buckets
+    uint64_t xmin = ~0ull, xmax = 0;
+    {
+        std::vector<uint64_t> lo(T, ~0ull), hi(T, 0);
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+                uint64_t a = ~0ull, c = 0;
+                for (size_t i = total * t / T; i < total * (t + 1) / T; ++i) { const uint64_t x = keys[i] >> (2 * kKeyBits); a = std::min(a, x); c = std::max(c, x); }
+                lo[t] = a; hi[t] = c;
+            });
+        for (auto& x : th) x.join();
+        for (size_t t = 0; t < T; ++t) { xmin = std::min(xmin, lo[t]); xmax = std::max(xmax, hi[t]); }
+    }
+    int shift = 0;
+    while (((xmax - xmin) >> shift) >= (1u << 14)) ++shift;
+    const size_t B = static_cast<size_t>((xmax - xmin) >> shift) + 1;
+    auto bucket_of = [&](uint64_t key) { return static_cast<size_t>(((key >> (2 * kKeyBits)) - xmin) >> shift); };
+    // per-thread histograms over contiguous arrival chunks; offsets bucket-major then thread-major keep arrival order inside a bucket
+    std::vector<uint32_t> hist(T * B, 0);
+    {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+                uint32_t* h = &hist[t * B];
+                for (size_t i = total * t / T; i < total * (t + 1) / T; ++i) ++h[bucket_of(keys[i])];
+            });
+        for (auto& x : th) x.join();
+    }
+    std::vector<uint32_t> bstart(B + 1, 0);
+    {
+        uint32_t run = 0;
+        for (size_t b0 = 0; b0 < B; ++b0) {
+            bstart[b0] = run;
+            for (size_t t = 0; t < T; ++t) { const uint32_t c = hist[t * B + b0]; hist[t * B + b0] = run; run += c; }
+        }
+        bstart[B] = run;
+    }
+    std::vector<Rec> recs(total);
+    {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+                uint32_t* h = &hist[t * B];
+                for (size_t i = total * t / T; i < total * (t + 1) / T; ++i) {
+                    const float* c = i < P0 ? &pxyz[3 * i] : &xyz[3 * (i - P0)];
+                    recs[h[bucket_of(keys[i])]++] = Rec{keys[i], static_cast<uint32_t>(i), c[0], c[1], c[2]};
+                }
+            });
+        for (auto& x : th) x.join();
+    }
+    std::vector<uint64_t>().swap(keys);
+    timer.lap("partition into x-slabs");
+
+    // 3. per slab: sort by (voxel, arrival), sequential spacing filter per voxel (AddPointWithSpacing, vhm.hpp:106-113), kept
+    //    points compacted in place at the front of the slab; voxel keys / counts collected per slab
     const double map_resolution = std::sqrt(voxel_size * voxel_size / cap);
-    std::vector<uint8_t> keep(total, 0);
-    std::vector<uint32_t> gcount(G, 0);
-    parallel_for(G, 4096, [&](size_t gb, size_t ge) {
-        std::vector<double> kept;
-        for (size_t g = gb; g < ge; ++g) {
-            kept.clear();
-            for (size_t i = gstart[g]; i < gstart[g + 1]; ++i) {
-                const uint32_t idx = recs[i].idx;
-                const double x = coord(idx, 0), y = coord(idx, 1), z = coord(idx, 2);
-                bool ok = true;
-                if (idx >= P0 && !kept.empty()) {          // first point of a voxel is always kept (vhm.cpp:281-283)
-                    if (kept.size() / 3 >= static_cast<size_t>(cap)) break;  // full: nothing later can enter
-                    for (size_t k = 0; k < kept.size(); k += 3) {
-                        const double dx = kept[k] - x, dy = kept[k + 1] - y, dz = kept[k + 2] - z;
-                        if (std::sqrt((dx * dx + dy * dy) + dz * dz) < map_resolution) { ok = false; break; }
+    // sqrt(d2) < map_resolution  <=>  d2 < d2_limit with d2_limit = the smallest double whose correctly rounded square root
+    // is >= map_resolution (sqrt is monotone): the same decisions as the reference's test, without a square root per pair
+    double d2_limit = map_resolution * map_resolution;
+    while (std::sqrt(d2_limit) >= map_resolution) d2_limit = std::nextafter(d2_limit, 0.0);
+    while (std::sqrt(d2_limit) < map_resolution) d2_limit = std::nextafter(d2_limit, HUGE_VAL);
+    std::vector<std::vector<uint64_t>> slab_keys(B);
+    std::vector<std::vector<uint32_t>> slab_counts(B);
+    std::atomic<size_t> next{0};
+    {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; ++t)
+            th.emplace_back([&]() {
+                std::vector<double> kept;
+                std::vector<Rec> tmp;
+                std::vector<uint32_t> cnt;
+                for (;;) {
+                    const size_t b0 = next.fetch_add(1);
+                    if (b0 >= B) break;
+                    Rec* r = recs.data() + bstart[b0];
+                    const size_t m = bstart[b0 + 1] - bstart[b0];
+                    // stable LSD counting sort by key, one pass per 21-bit coordinate field (z, then y, then x) with as many bins as
+                    // the field's range inside the slab (fields wider than 2^12 values take two passes; constant fields none).
+                    // The slab is in arrival order and every pass is stable, so the result is ordered by (voxel, arrival).
+                    if (tmp.size() < m) tmp.resize(m);
+                    {
+                        Rec* src = r;
+                        Rec* dst = tmp.data();
+                        const uint64_t fmask = (1ull << kKeyBits) - 1;
+                        for (int f = 0; f < 3 && m > 1; ++f) {
+                            const int fsh = kKeyBits * f;  // 0: z, 21: y, 42: x
+                            uint64_t lo = ~0ull, hi = 0;
+                            for (size_t i = 0; i < m; ++i) { const uint64_t v = (src[i].key >> fsh) & fmask; lo = std::min(lo, v); hi = std::max(hi, v); }
+                            const uint64_t range = hi - lo + 1;
+                            const int passes = range == 1 ? 0 : (range <= 4096 ? 1 : 2);
+                            for (int ps = 0; ps < passes; ++ps) {
+                                const int dsh = (passes == 2 && ps == 1) ? 11 : 0;
+                                const uint64_t dmask = passes == 2 ? 2047u : ~0ull;
+                                const size_t bins = passes == 2 ? 2048 : static_cast<size_t>(range);
+                                cnt.assign(bins + 1, 0);
+                                for (size_t i = 0; i < m; ++i) ++cnt[static_cast<size_t>(((((src[i].key >> fsh) & fmask) - lo) >> dsh) & dmask) + 1];
+                                for (size_t k = 0; k < bins; ++k) cnt[k + 1] += cnt[k];
+                                for (size_t i = 0; i < m; ++i) dst[cnt[static_cast<size_t>(((((src[i].key >> fsh) & fmask) - lo) >> dsh) & dmask)]++] = src[i];
+                                std::swap(src, dst);
+                            }
+                        }
+                        if (src != r) std::memcpy(r, src, m * sizeof(Rec));
+                    }
+                    size_t out = 0;
+                    for (size_t i = 0; i < m;) {
+                        const uint64_t key = r[i].key;
+                        kept.clear();
+                        size_t j = i;
+                        for (; j < m && r[j].key == key; ++j) {
+                            const double x = r[j].x, y = r[j].y, z = r[j].z;
+                            bool ok = true;
+                            if (r[j].idx >= P0 && !kept.empty()) {      // first point of a voxel is always kept (vhm.cpp:281-283)
+                                if (kept.size() / 3 >= static_cast<size_t>(cap)) ok = false;  // full: nothing later can enter
+                                for (size_t k = 0; ok && k < kept.size(); k += 3) {
+                                    const double dx = kept[k] - x, dy = kept[k + 1] - y, dz = kept[k + 2] - z;
+                                    if ((dx * dx + dy * dy) + dz * dz < d2_limit) ok = false;
+                                }
+                            }
+                            if (ok) { kept.push_back(x); kept.push_back(y); kept.push_back(z); r[out++] = r[j]; }
+                        }
+                        slab_keys[b0].push_back(key);
+                        slab_counts[b0].push_back(static_cast<uint32_t>(kept.size() / 3));
+                        i = j;
                     }
                 }
-                if (ok) { keep[i] = 1; kept.push_back(x); kept.push_back(y); kept.push_back(z); }
-            }
-            gcount[g] = static_cast<uint32_t>(kept.size() / 3);
-        }
-    });
-    // 5. compact into the canonical arrays
+            });
+        for (auto& x : th) x.join();
+    }
+    timer.lap("sort + spacing filter per slab");
+
+    // 4. concatenate the slabs (slab order == key order) into the canonical arrays
+    std::vector<size_t> vbase(B + 1, 0), pbase(B + 1, 0);
+    for (size_t b0 = 0; b0 < B; ++b0) {
+        vbase[b0 + 1] = vbase[b0] + slab_keys[b0].size();
+        size_t c = 0;
+        for (uint32_t k : slab_counts[b0]) c += k;
+        pbase[b0 + 1] = pbase[b0] + c;
+    }
+    const size_t G = vbase[B], P1 = pbase[B];
     std::vector<uint64_t> nkey(G);
     std::vector<uint32_t> nstart(G + 1, 0);
-    for (size_t g = 0; g < G; ++g) { nkey[g] = recs[gstart[g]].key; nstart[g + 1] = nstart[g] + gcount[g]; }
-    const size_t P1 = nstart[G];
     std::vector<float> nxyz(3 * P1);
     std::vector<uint32_t> norig(P1);
-    parallel_for(G, 4096, [&](size_t gb, size_t ge) {
-        for (size_t g = gb; g < ge; ++g) {
-            uint32_t o = nstart[g];
-            for (size_t i = gstart[g]; i < gstart[g + 1]; ++i) {
-                if (!keep[i]) continue;
-                const uint32_t idx = recs[i].idx;
-                nxyz[3 * o] = coord(idx, 0); nxyz[3 * o + 1] = coord(idx, 1); nxyz[3 * o + 2] = coord(idx, 2);
-                norig[o] = idx < P0 ? porig[idx] : static_cast<uint32_t>(n_raw_seen + (idx - P0));
-                ++o;
+    parallel_for(B, 1, [&](size_t bb, size_t be) {
+        for (size_t b0 = bb; b0 < be; ++b0) {
+            size_t p = pbase[b0];
+            for (size_t g = 0; g < slab_keys[b0].size(); ++g) {
+                nkey[vbase[b0] + g] = slab_keys[b0][g];
+                nstart[vbase[b0] + g] = static_cast<uint32_t>(p);
+                p += slab_counts[b0][g];
+            }
+            const Rec* r = recs.data() + bstart[b0];
+            for (size_t i = 0, o = pbase[b0]; o < pbase[b0 + 1]; ++i, ++o) {
+                nxyz[3 * o] = r[i].x; nxyz[3 * o + 1] = r[i].y; nxyz[3 * o + 2] = r[i].z;
+                norig[o] = r[i].idx < P0 ? porig[r[i].idx] : static_cast<uint32_t>(n_raw_seen + (r[i].idx - P0));
             }
         }
     });
+    nstart[G] = static_cast<uint32_t>(P1);
     vkey.swap(nkey); vstart.swap(nstart); pxyz.swap(nxyz); porig.swap(norig);
     n_raw_seen += n;
     has_vcov = has_pcov = false;
     vmean.clear(); vcov.clear(); pmean.clear(); pcov.clear(); pnormal.clear();
+    vcand.clear(); dir7.clear();
+    timer.lap("compaction");
     build_table();
-    return build_directory();
+    timer.lap("voxel table");
+    const std::string e = build_directory();
+    timer.lap("neighbourhood directory");
+    return e;
 }
 
 // ---- neighbourhood directory ------------------------------------------------------------------------------------
@@ -234,10 +376,12 @@ std::vector<uint64_t> dilate_axis(const std::vector<uint64_t>& in, int axis) {
 std::string HostMap::build_directory() {
     dir_slots.clear(); dir_rows.clear(); dir_bmask = 0; dir_entries = 0;
     if (vkey.empty()) return "";
+    StageTimer timer;
     // 1. centre keys: occupied voxels and their one-voxel halo (separable dilation z, y, x of the sorted key list)
     std::vector<uint64_t> E = dilate_axis(dilate_axis(dilate_axis(vkey, 2), 1), 0);
     dir_entries = E.size();
     if (E.size() >= (1ull << 31)) return "map too large for the neighbourhood directory";
+    timer.lap("  dilation");
     // 2. 2-choice cuckoo placement, 2 slots per bucket, load <= 0.75; deterministic random walk, table doubled on failure
     size_t nb = 2;
     while (nb * 2 * 3 < E.size() * 4) nb <<= 1;
@@ -270,26 +414,44 @@ std::string HostMap::build_directory() {
         }
         if (ok) { dir_bmask = bm; break; }
     }
-    // 3. slots + rows (row r belongs to slot r)
+    timer.lap("  cuckoo placement");
+    // 3. slots + rows (row r belongs to slot r).  Entries are walked in KEY order with one forward cursor per column into the
+    //    sorted voxel list (shifting a key by (dx, dy) keeps the order), so the nine runs of an entry cost O(1) amortised
+    //    instead of a binary search each; the rows are written to the entry's slot.
     const size_t S = owner.size();
     dir_slots.assign(S, DirSlot{0xffffffffu, 0xffffffffu, 0, 0});
     dir_rows.assign(S * kDirRowDescs, DirDesc{0, 0});
-    parallel_for(S, 1 << 14, [&](size_t sb, size_t se) {
-        for (size_t s = sb; s < se; ++s) {
-            if (owner[s] < 0) continue;
-            const uint64_t key = E[owner[s]];
+    std::vector<uint32_t> slot_of(E.size());
+    for (size_t s = 0; s < S; ++s) if (owner[s] >= 0) slot_of[static_cast<size_t>(owner[s])] = static_cast<uint32_t>(s);
+    const size_t nV = vkey.size();
+    parallel_for(E.size(), 1 << 14, [&](size_t eb, size_t ee) {
+        size_t cur[9];
+        uint64_t last[9];
+        bool primed[9] = {false, false, false, false, false, false, false, false, false};
+        for (size_t e = eb; e < ee; ++e) {
+            const uint64_t key = E[e];
             int32_t x, y, z;
             unpack_key(key, x, y, z);
+            const size_t s = slot_of[e];
             DirDesc* row = &dir_rows[s * kDirRowDescs];
             for (int c = 0; c < 9; ++c) {
                 const int32_t cx = x + c / 3 - 1, cy = y + c % 3 - 1;
                 if (!key_in_range(cx) || !key_in_range(cy)) continue;
                 const int32_t zlo = std::max(z - 1, -kKeyBias), zhi = std::min(z + 1, kKeyBias - 1);
                 const uint64_t klo = pack_key(cx, cy, zlo), khi = pack_key(cx, cy, zhi);
-                size_t v = static_cast<size_t>(std::lower_bound(vkey.begin(), vkey.end(), klo) - vkey.begin());
+                if (!primed[c] || klo < last[c]) {  // first use in this chunk (or a non-monotone step at the range border)
+                    cur[c] = static_cast<size_t>(std::lower_bound(vkey.begin(), vkey.end(), klo) - vkey.begin());
+                    primed[c] = true;
+                } else {
+                    size_t v = cur[c], step = 0;
+                    while (v < nV && vkey[v] < klo && step < 64) { ++v; ++step; }
+                    if (v < nV && vkey[v] < klo) v = static_cast<size_t>(std::lower_bound(vkey.begin() + v, vkey.end(), klo) - vkey.begin());
+                    cur[c] = v;
+                }
+                last[c] = klo;
                 uint32_t first = 0, counts = 0;
                 bool any = false;
-                for (; v < vkey.size() && vkey[v] <= khi; ++v) {
+                for (size_t v = cur[c]; v < nV && vkey[v] <= khi; ++v) {
                     int32_t vx, vy, vz;
                     unpack_key(vkey[v], vx, vy, vz);
                     if (!any) { first = vstart[v]; any = true; }
@@ -300,6 +462,7 @@ std::string HostMap::build_directory() {
             dir_slots[s] = DirSlot{static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), row[4].first, row[4].counts};
         }
     });
+    timer.lap("  slots + rows");
     return "";
 }
 
