@@ -707,10 +707,22 @@ void HostMap::cal_point_cov(double search_dist) {
             nb.push_back(x); nb.push_back(y); nb.push_back(z);
             const int32_t kx = static_cast<int32_t>(std::floor(x / vs)), ky = static_cast<int32_t>(std::floor(y / vs)),
                           kz = static_cast<int32_t>(std::floor(z / vs));
+            // Squared gap (metres, under-estimated) between the point and anything STORED under key c along one axis: insert
+            // keys truncate toward zero, so key c holds p / vs in [c, c+1) for c > 0, (c-1, c] for c < 0 and (-1, 1) for c == 0.
+            // A voxel whose box is farther than the search radius cannot contribute a neighbour: skipping it leaves the
+            // neighbour list — and its order, hence every rounding of the sums — exactly as the full 27-voxel visit builds it.
+            auto gap2 = [vs](double p, int32_t c) {
+                const double q = p / vs;
+                const double lo = static_cast<double>(c <= 0 ? c - 1 : c), hi = static_cast<double>(c >= 0 ? c + 1 : c);
+                const double g = std::max(std::max(lo - q, q - hi), 0.0) * vs * (1.0 - 1e-9);
+                return g * g;
+            };
+            const double r2_skip = r2 * (1.0 + 1e-9);
             for (int i = kx - 1; i <= kx + 1; ++i)
                 for (int j = ky - 1; j <= ky + 1; ++j)
                     for (int k = kz - 1; k <= kz + 1; ++k) {
                         if (!key_in_range(i) || !key_in_range(j) || !key_in_range(k)) continue;
+                        if (gap2(x, i) + gap2(y, j) + gap2(z, k) > r2_skip) continue;
                         const int64_t v = find(pack_key(i, j, k));
                         if (v < 0) continue;
                         for (uint32_t q = vstart[v]; q < vstart[v + 1]; ++q) {
