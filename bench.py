@@ -246,10 +246,26 @@ def main():
     reg.set_exhaustive(args.exhaustive)
     reg.set_binning(args.binning)
     reg.set_fused(args.fused)
+    comm_used = args.comm
     if world > 1:
         if args.comm == "peer":
-            reg.peer_setup(dist)
-        else:
+            # CUDA IPC peer mapping needs P2P access between the GPUs of the box; if ANY rank cannot attach, every rank
+            # falls back to the NCCL all-reduce so that the run still measures the sharded path
+            ok = 1
+            try:
+                reg.peer_setup(dist)
+            except Exception as exc:  # noqa: BLE001
+                ok = 0
+                print(f"[bench] rank {rank}: peer-memory attach failed ({exc}); falling back to NCCL", file=sys.stderr)
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                try:
+                    reg.peer_detach()
+                except Exception:  # noqa: BLE001
+                    pass
+                comm_used = "nccl"
+        if comm_used == "nccl":
             ids = [E.Registration.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
             reg.set_comm(ids[0], rank, world)
@@ -421,7 +437,7 @@ def main():
                "dtype": "f64", "data": "synthetic",
                "config": dict(config, parallelism=f"scan sharded over {world} GPU(s) ({n_local} points per rank, {n_global} in total), "
                                                   f"map replicated, accumulators all-reduced per iteration via "
-                                                  f"{'peer-memory mailboxes inside the accumulation kernel' if args.comm == 'peer' else 'ncclAllReduce'}"
+                                                  f"{'peer-memory mailboxes inside the accumulation kernel' if comm_used == 'peer' else 'ncclAllReduce'}"
                                                   if world > 1 else "1 GPU",
                               value_definition="ICP iterations/s of the n_scan-point scan = (searches+accumulations per second) / n_scan",
                               strong_scaling=strong,

@@ -310,5 +310,11 @@ class Registration:
         rank, world = dist.get_rank(), dist.get_world_size()
         handles = [None] * world
         dist.all_gather_object(handles, self.peer_export())
-        self.peer_attach(handles, rank, world)
+        err = None
+        try:
+            self.peer_attach(handles, rank, world)
+        except _capi.ElmError as exc:  # keep the collective call sequence identical on every rank, then report
+            err = exc
         dist.barrier()
+        if err is not None:
+            raise err
