@@ -1,0 +1,188 @@
+"""An INDEPENDENT restatement of the three correspondence searches — numpy + a plain dict, none of the oracle's code — checked
+against the oracle (oracle/ is "parity unpinned": the reference ships no vectors and cannot be built here, so the C++
+restatement is cross-examined by a second, differently structured one).  Follows voxel_hash_map.cpp:31-243 directly:
+floor query key (voxel_hash_map.hpp:176-180), GetAdjacentVoxels order (x outer, y, z inner / c,+x,-x,+y,-y,+z,-z), strict <
+(first of equals wins), the default-constructed neighbour at the origin when nothing is found, the max-distance gate."""
+import numpy as np
+import pytest
+
+from elimaloc_b200 import synth
+from oracle import oracle as O
+
+P2P, GICP, VGICP, AVGICP = 0, 1, 2, 3
+
+
+def transform_exact(T, s):
+    """(T [s; 1]).head3 in the association order of a 4x4 * 4x1 product: ((T0 x + T1 y) + T2 z) + T3, one rounding per op."""
+    x, y, z = (s[:, k].astype(np.float64) for k in range(3))
+    return np.stack([((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3] for r in range(3)], axis=1)
+
+
+def brute_force(export, scan, T, method, max_dist, vs):
+    keys, counts, pxyz = export["keys"], export["counts"], export["pxyz"].astype(np.float64)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    voxel = {tuple(int(c) for c in k): v for v, k in enumerate(keys)}
+    p = transform_exact(np.asarray(T, np.float64), scan)
+    K = 7 if method == AVGICP else 1
+    cnt = np.zeros(len(scan), np.int32)
+    tgt = np.zeros((len(scan), K, 3))
+    for i, q in enumerate(p):
+        k = np.floor(q / vs).astype(np.int64)
+        if method == AVGICP:
+            c = 0
+            for d in ((0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+                v = voxel.get((k[0] + d[0], k[1] + d[1], k[2] + d[2]))
+                if v is None:
+                    continue
+                m = export["vmean"][v]
+                e = m - q
+                if (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2] < max_dist * max_dist:
+                    tgt[i, c] = m
+                    c += 1
+            cnt[i] = c
+            continue
+        cand = []
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    v = voxel.get((k[0] + dx, k[1] + dy, k[2] + dz))
+                    if v is None:
+                        continue
+                    cand.append(export["vmean"][v][None, :] if method == VGICP else pxyz[starts[v]:starts[v + 1]])
+        best = np.zeros(3)  # the default-constructed neighbour sits at the origin
+        if cand:
+            c = np.concatenate(cand)
+            e = c - q[None, :]
+            d2 = (e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1]) + e[:, 2] * e[:, 2]
+            best = c[int(np.argmin(d2))]  # argmin returns the FIRST minimum: the strict < of the reference
+        e = best - q
+        if (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2] < max_dist * max_dist:
+            cnt[i] = 1
+            tgt[i, 0] = best
+    return cnt, tgt
+
+
+@pytest.mark.parametrize("origin", [0.0, -6.5])
+@pytest.mark.parametrize("method", [P2P, VGICP, AVGICP])
+def test_oracle_searches_equal_an_independent_restatement(origin, method):
+    raw = synth.map_u(25_000, 13.0, origin=origin)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    ex = om.export()
+    T = synth.se3([origin + 6.0, origin + 7.0, origin + 6.5], [0.02, -0.03, 0.4])
+    rng = np.random.default_rng(11)
+    scan = ((rng.random((500, 3)) * 2 - 1) * 9.0).astype(np.float32)       # inside, at the border of and outside the map
+    scan[:40] = (np.linalg.inv(T) @ np.c_[ex["pxyz"][:40].astype(np.float64), np.ones(40)].T).T[:, :3].astype(np.float32)  # near-zero distances
+    for max_dist in (5.0, 0.6):
+        oc, ot = O.correspondences(om, scan, T, method, max_dist)
+        bc, bt = brute_force(ex, scan, T, method, max_dist, 1.0)
+        assert np.array_equal(oc, bc), (method, max_dist, np.flatnonzero(oc != bc)[:5])
+        assert np.array_equal(ot, bt), (method, max_dist)
+
+
+def test_oracle_origin_default_is_reproduced_by_the_restatement():
+    """Q2: a query whose 27 voxels are empty is matched to the origin when it lies within max_dist of it."""
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(np.array([[40.0, 40.0, 40.0]], np.float32))
+    om.CalVoxelCovAll()
+    scan = np.array([[1.0, 2.0, 2.0], [4.0, 4.0, 4.0]], np.float32)
+    for method in (P2P, VGICP):
+        oc, ot = O.correspondences(om, scan, np.eye(4), method, 5.0)
+        bc, bt = brute_force(om.export(), scan, np.eye(4), method, 5.0, 1.0)
+        assert np.array_equal(oc, bc) and np.array_equal(ot, bt) and list(oc) == [1, 0]
+
+
+def skew(v):
+    return np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+
+
+def linearize_numpy(scan, cnt, tgt, T, method, th, covs=None):
+    """AlignCloudsLocal (registration.cpp:15-66) / AlignCloudsLocalVoxelCov (:154-225) written with numpy.linalg — a
+    restatement that shares nothing with the oracle's hand-written small-matrix code."""
+    Tinv = np.linalg.inv(T)
+    Rinv = np.linalg.inv(T[:3, :3])
+    JTJ, JTr, res, n = np.zeros((6, 6)), np.zeros(6), 0.0, 0
+    for i in range(len(scan)):
+        s = scan[i].astype(np.float64)
+        for c in range(cnt[i]):
+            t = tgt[i, c]
+            r = (Tinv @ np.r_[t, 1.0])[:3] - s
+            J = np.hstack([np.eye(3), -skew(s)])
+            w = th * th / (th + r @ r) ** 2
+            n += 1
+            if method == P2P:
+                JTJ += w * J.T @ J
+                JTr += w * J.T @ r
+                res += np.linalg.norm(r)
+            else:
+                if w < 0.01:
+                    continue
+                M = np.linalg.inv(Rinv @ covs[i][c] @ Rinv.T)
+                JTJ += w * J.T @ M @ J
+                JTr += w * J.T @ M @ r
+                res += np.linalg.norm(r)
+    return JTJ, JTr, res, n
+
+
+@pytest.mark.parametrize("method", [P2P, VGICP, AVGICP])
+def test_oracle_linearisation_equals_a_numpy_restatement(method):
+    raw = synth.map_s(40_000, 30.0) if method != P2P else synth.map_u(25_000, 13.0, origin=-2.0)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    ex = om.export()
+    T_true = synth.se3([6.0, 7.0, 2.0], [0.02, -0.03, 0.4])
+    scan = synth.scan_m(ex["pxyz"], 400, T_true)
+    T = T_true @ synth.canonical_offset()
+    th = 5.0
+    cnt, tgt = brute_force(ex, scan, T, method, th, 1.0)
+    covs = None
+    if method != P2P:  # the covariance that belongs to each emitted voxel mean (means are unique per voxel)
+        by_mean = {tuple(m): c for m, c in zip(ex["vmean"], ex["vcov"])}
+        covs = [[by_mean.get(tuple(tgt[i, c]), np.eye(3)) for c in range(cnt[i])] for i in range(len(scan))]
+    JTJ, JTr, res, n = linearize_numpy(scan, cnt, tgt, T, method, th, covs)
+    lin = O.Registration().linearize(scan, om, T, O.make_config(icp_method=method, max_search_dist=th))
+    assert lin["n_corr"] == n and n > 300
+    assert np.abs(lin["JTJ"] - JTJ).max() <= 1e-10 * np.abs(JTJ).max()
+    assert np.abs(lin["JTr"] - JTr).max() <= 1e-10 * max(np.abs(JTr).max(), 1e-300) + 1e-9
+    assert abs(lin["residual_sum"] - res) <= 1e-10 * res
+
+
+def test_oracle_gicp_linearisation_equals_a_numpy_restatement():
+    """AlignCloudsLocalPointCov (registration.cpp:68-152): the nearest neighbour is chosen by POSITION, the residual goes to
+    that point's neighbourhood MEAN (Q4), weight 0.8 w + 0.2 (Q8), M from the point's covariance, fitness = |r . n| with n the
+    eigenvector of the smallest eigenvalue (numpy.linalg.eigh here; the sign of n does not matter)."""
+    raw = synth.map_s(40_000, 30.0)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    om.CalPointCovAll(0.4)
+    ex = om.export()
+    T_true = synth.se3([6.0, 7.0, 2.0], [0.02, -0.03, 0.4])
+    scan = synth.scan_m(ex["pxyz"], 400, T_true)
+    T = T_true @ synth.canonical_offset()
+    th = 5.0
+    cnt, tgt = brute_force(ex, scan, T, P2P, th, 1.0)
+    index = {tuple(p): i for i, p in enumerate(ex["pxyz"].astype(np.float64))}   # stored positions are unique (spacing filter)
+    Tinv, Rinv = np.linalg.inv(T), np.linalg.inv(T[:3, :3])
+    JTJ, JTr, res, n = np.zeros((6, 6)), np.zeros(6), 0.0, 0
+    for i in range(len(scan)):
+        if not cnt[i]:
+            continue
+        m = index[tuple(tgt[i, 0])]
+        s = scan[i].astype(np.float64)
+        r = (Tinv @ np.r_[ex["pmean"][m], 1.0])[:3] - s
+        J = np.hstack([np.eye(3), -skew(s)])
+        w = th * th / (th + r @ r) ** 2 * 0.8 + 0.2
+        M = np.linalg.inv(Rinv @ ex["pcov"][m] @ Rinv.T)
+        JTJ += w * J.T @ M @ J
+        JTr += w * J.T @ M @ r
+        nl = Rinv @ np.linalg.eigh(ex["pcov"][m])[1][:, 0]
+        res += abs(r @ (nl / np.linalg.norm(nl)))
+        n += 1
+    lin = O.Registration().linearize(scan, om, T, O.make_config(icp_method=GICP, max_search_dist=th))
+    assert lin["n_corr"] == n and n > 300
+    assert np.abs(lin["JTJ"] - JTJ).max() <= 1e-10 * np.abs(JTJ).max()
+    assert np.abs(lin["JTr"] - JTr).max() <= 1e-10 * np.abs(JTr).max() + 1e-9
+    assert abs(lin["residual_sum"] - res) <= 1e-8 * res
