@@ -186,3 +186,127 @@ def test_oracle_gicp_linearisation_equals_a_numpy_restatement():
     assert np.abs(lin["JTJ"] - JTJ).max() <= 1e-10 * np.abs(JTJ).max()
     assert np.abs(lin["JTr"] - JTr).max() <= 1e-10 * np.abs(JTr).max() + 1e-9
     assert abs(lin["residual_sum"] - res) <= 1e-8 * res
+
+
+def regularize_svd(cov):
+    """U diag(1, 1, 1e-3) V^T with numpy's SVD (voxel_hash_map.hpp:141-144); well defined for full-rank covariances"""
+    U, s, Vt = np.linalg.svd(cov)
+    return U @ np.diag([1.0, 1.0, 1e-3]) @ Vt, s
+
+
+@pytest.mark.parametrize("origin", [0.0, -5.5])
+def test_oracle_map_build_and_covariances_equal_a_python_restatement(origin):
+    """AddPoints / AddPointWithSpacing (voxel_hash_map.cpp:270-285, .hpp:106-113) as a dict of lists filled one point at a time;
+    CalVoxelCov (.hpp:114-148) and ProcessVoxelBlock (.hpp:195-250, self counted twice) with numpy SVD.  Covariances whose
+    sample covariance is (numerically) rank deficient are excluded: their null-space basis is implementation-defined."""
+    vs, cap = 1.0, 30
+    raw = synth.map_u(12_000, 9.0, origin=origin)
+    om = O.VoxelHashMap(vs, cap)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    om.CalPointCovAll(0.4)
+    ex = om.export()
+    # ---- sequential insert
+    res = np.sqrt(vs * vs / cap)
+    vox = {}
+    for p in raw.astype(np.float64):
+        key = tuple(int(c) for c in (p / vs))                       # static_cast<int>: truncation toward zero
+        pts = vox.setdefault(key, [])
+        if not pts:
+            pts.append(p)                                           # the first point of a voxel is always kept
+        elif len(pts) < cap and all(np.sqrt(((q - p) ** 2)[0] + ((q - p) ** 2)[1] + ((q - p) ** 2)[2]) >= res for q in pts):
+            pts.append(p)
+    keys = sorted(vox)
+    assert np.array_equal(ex["keys"], np.array(keys, np.int32))
+    assert np.array_equal(ex["counts"], np.array([len(vox[k]) for k in keys], np.int32))
+    assert np.array_equal(ex["pxyz"].astype(np.float64), np.concatenate([np.array(vox[k]) for k in keys]))
+    # ---- voxel covariances
+    checked = 0
+    for v, k in enumerate(keys):
+        P = np.array(vox[k])
+        if len(P) == 1:
+            assert np.array_equal(ex["vmean"][v], P[0]) and np.array_equal(ex["vcov"][v], np.eye(3))
+            continue
+        mean = P.mean(axis=0)
+        cov, s = regularize_svd((P - mean).T @ (P - mean) / (len(P) - 1))
+        assert np.allclose(ex["vmean"][v], mean, rtol=0, atol=1e-12)
+        if s[2] > 1e-6 * s[0] and s[1] - s[2] > 1e-6 * s[0]:
+            assert np.abs(ex["vcov"][v] - cov).max() < 1e-8
+            checked += 1
+    assert checked > 0.5 * len(keys)
+    # ---- point covariances (a sample of points): neighbours = self + every stored point of the 27 FLOOR-keyed voxels within 0.4 m
+    starts = np.concatenate([[0], np.cumsum(ex["counts"])])
+    stored = ex["pxyz"].astype(np.float64)
+    index = {k: v for v, k in enumerate(keys)}
+    checked = 0
+    for p in range(0, len(stored), 37):
+        x = stored[p]
+        kf = np.floor(x / vs).astype(int)
+        nb = [x]
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    v = index.get((kf[0] + dx, kf[1] + dy, kf[2] + dz))
+                    if v is None:
+                        continue
+                    for q in stored[starts[v]:starts[v + 1]]:
+                        e = q - x
+                        if (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2] <= 0.4 * 0.4:
+                            nb.append(q)
+        N = np.array(nb)
+        mean = N.mean(axis=0)
+        cov, s = regularize_svd((N - mean).T @ (N - mean) / (len(N) - 1))
+        assert np.allclose(ex["pmean"][p], mean, rtol=0, atol=1e-12)
+        if s[2] > 1e-6 * s[0] and s[1] - s[2] > 1e-6 * s[0]:
+            assert np.abs(ex["pcov"][p] - cov).max() < 1e-8
+            checked += 1
+    assert checked > 20
+
+
+def rodrigues(w):
+    """AngleAxisd(|w|, w / |w|).toRotationMatrix() (registration.cpp:58-62)"""
+    a = np.linalg.norm(w)
+    if a == 0.0:
+        return np.eye(3)
+    k = skew(w / a)
+    return np.eye(3) + np.sin(a) * k + (1.0 - np.cos(a)) * (k @ k)
+
+
+@pytest.mark.parametrize("method", [P2P, VGICP])
+def test_oracle_run_register_equals_an_independent_icp_loop(method):
+    """RunRegister (registration.cpp:274-418) end to end, rebuilt from the independent pieces above: search, linearise,
+    x = (JtJ + lambda diag(JtJ))^-1 Jtr (numpy.linalg.solve instead of LDLT), right-multiplied update T <- T dT with
+    x = [t; w], termination test AFTER the update, fitness = residual sum / pairs.  Six iterations from the canonical offset."""
+    raw = synth.map_s(30_000, 24.0) if method == VGICP else synth.map_u(25_000, 13.0, origin=-2.0)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    ex = om.export()
+    T_true = synth.se3([6.0, 7.0, 2.0], [0.02, -0.03, 0.4])
+    scan = synth.scan_m(ex["pxyz"], 300, T_true)
+    T = T_true @ synth.canonical_offset()
+    th, lam, thr, iters = 5.0, 0.5, 1e-4, 6
+    by_mean = {tuple(m): c for m, c in zip(ex["vmean"], ex["vcov"])}
+    fitness, done_at = None, iters
+    Tk = T.copy()
+    for it in range(iters):
+        cnt, tgt = brute_force(ex, scan, Tk, method, th, 1.0)
+        covs = [[by_mean.get(tuple(tgt[i, c]), np.eye(3)) for c in range(cnt[i])] for i in range(len(scan))] if method == VGICP else None
+        JTJ, JTr, res, n = linearize_numpy(scan, cnt, tgt, Tk, method, th, covs)
+        fitness = res / n
+        x = np.linalg.solve(JTJ + lam * np.diag(np.diag(JTJ)), JTr)
+        dT = np.eye(4)
+        dT[:3, :3] = rodrigues(x[3:])
+        dT[:3, 3] = x[:3]
+        Tk = Tk @ dT
+        if np.linalg.norm(x[3:]) + np.linalg.norm(x[:3]) < thr:   # angle of dR == |w| for |w| < pi
+            done_at = it + 1
+            break
+    cfg = O.make_config(icp_method=method, max_iteration=iters, max_search_dist=th, lm_lambda=lam, icp_termination_threshold_m=thr,
+                        min_overlap_ratio=0.0, max_fitness_score=1e30)
+    o = O.Registration().RunRegister(scan, om, T, cfg)
+    assert o["is_success"]
+    assert np.abs(o["pose"] - Tk).max() <= 1e-9 * np.abs(Tk).max()
+    assert abs(o["fitness_score"] - fitness) <= 1e-9 * fitness
+    # ... and the loop really moves towards the truth (LM damping 0.5: about a third of the error is removed per iteration)
+    assert np.linalg.norm(Tk[:3, 3] - T_true[:3, 3]) < 0.5 * np.linalg.norm(T[:3, 3] - T_true[:3, 3])
