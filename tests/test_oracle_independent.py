@@ -310,3 +310,44 @@ def test_oracle_run_register_equals_an_independent_icp_loop(method):
     assert abs(o["fitness_score"] - fitness) <= 1e-9 * fitness
     # ... and the loop really moves towards the truth (LM damping 0.5: about a third of the error is removed per iteration)
     assert np.linalg.norm(Tk[:3, 3] - T_true[:3, 3]) < 0.5 * np.linalg.norm(T[:3, 3] - T_true[:3, 3])
+
+
+def test_oracle_deskew_equals_a_numpy_restatement():
+    """DeskewPoint / FindRotation / FindPosition (pcm_matching.cpp:731-824) in float64 numpy: table lookup with linear
+    interpolation, odometry ratio, the Q3 quirk (z translation takes the interpolated yaw integral), Rz Ry Rx.  The oracle
+    works in float32 like the reference, so the comparison allows float32 rounding of 80 m coordinates."""
+    rng = np.random.default_rng(5)
+    t_end, span = 500.0, 0.1
+    t_cur = t_end - span
+    stamps = np.arange(t_cur - 0.04, t_end + 0.04, 0.005)
+    gyro = np.tile([0.08, -0.05, 0.7], (len(stamps), 1)) + rng.normal(0, 0.01, (len(stamps), 3))
+    start = np.array([3.0, -2.0, 0.5, 0.02, -0.01, 0.3])
+    end = start + np.array([0.9, 0.05, 0.02, 0.008, -0.005, 0.07])
+    tab = O.deskew_tables(stamps, gyro, t_cur, t_end, start, t_cur, end, t_end)
+    xyz = ((rng.random((3000, 3), dtype=np.float32) * 2 - 1) * np.float32(80.0)).astype(np.float32)
+    rel = np.sort(rng.random(3000).astype(np.float32) * np.float32(span))
+    got = O.deskew_points(tab, xyz, rel)
+
+    cur = tab["imu_pointer_cur"]
+    tt, rx, ry, rz = (np.asarray(tab[k], np.float64) for k in ("imu_time", "imu_rot_x", "imu_rot_y", "imu_rot_z"))
+    inc = np.asarray(tab["odom_incre"], np.float64)
+    want = np.zeros((len(xyz), 3))
+    for i, (p, dt) in enumerate(zip(xyz.astype(np.float64), rel.astype(np.float64))):
+        t = tab["time_scan_cur"] + dt
+        front = 0
+        while front < cur and not t < tt[front]:
+            front += 1
+        if t > tt[front] or front == 0:
+            rot = np.array([rx[front], ry[front], rz[front]])
+        else:
+            back = front - 1
+            a = (t - tt[back]) / (tt[front] - tt[back])
+            b = (tt[front] - t) / (tt[front] - tt[back])
+            rot = np.array([rx[front] * a + rx[back] * b, ry[front] * a + ry[back] * b, rz[front] * a + rz[back] * b])
+        pos = dt / (tab["time_scan_end"] - tab["time_scan_cur"]) * inc if tab["odom_available"] else np.zeros(3)
+        d_rot = rot - np.array([rx[cur], ry[cur], rz[cur]])
+        d_pos = np.array([pos[0] - inc[0], pos[1] - inc[1], rot[2] - inc[2]])   # Q3: rot z, not pos z (pcm_matching.cpp:804)
+        R = synth.exp_so3([0, 0, d_rot[2]]) @ synth.exp_so3([0, d_rot[1], 0]) @ synth.exp_so3([d_rot[0], 0, 0])
+        want[i] = R @ p + d_pos
+    assert np.abs(got - want).max() < 1e-4          # float32 arithmetic on |x| <= 80 m
+    assert np.abs(got - xyz).max() > 0.05           # the correction is not a no-op
