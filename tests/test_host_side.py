@@ -220,13 +220,15 @@ def test_new_entry_points_validate_their_arguments():
     assert pm.directory_check() == (0, 0, 0)   # empty map: empty directory
 
 
-@pytest.mark.parametrize("kind", ["surface_half_metre", "forty_km_wide"])
+@pytest.mark.parametrize("kind", ["surface_half_metre", "forty_km_wide", "every_host_thread"])
 def test_parallel_builder_equals_sequential_insert_on_awkward_maps(kind):
     """The slab-partitioned parallel AddPoints (x-slabs, stable counting sort, per-voxel sequential spacing filter) must equal
     the oracle's one-point-at-a-time insert bit for bit: sparse surface map with 0.5 m voxels; an extent of 40 000 voxels
     along x (more slabs than buckets: several voxel columns per slab) straddling the origin; both fed in three calls."""
     if kind == "surface_half_metre":
         raw, vs = synth.map_s(120_000, 150.0), 0.5
+    elif kind == "every_host_thread":   # enough points for one partition chunk per hardware thread
+        raw, vs = synth.map_u(600_000, 38.0, origin=-9.0), 1.0
     else:
         rng = np.random.default_rng(1)
         raw, vs = (rng.random((80_000, 3)) * np.array([40000.0, 30.0, 10.0]) - np.array([20000.0, 15.0, 5.0])).astype(np.float32), 1.0
