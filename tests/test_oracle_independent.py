@@ -351,3 +351,69 @@ def test_oracle_deskew_equals_a_numpy_restatement():
         want[i] = R @ p + d_pos
     assert np.abs(got - want).max() < 1e-4          # float32 arithmetic on |x| <= 80 m
     assert np.abs(got - xyz).max() > 0.05           # the correction is not a no-op
+
+
+def test_oracle_imu_prediction_equals_a_numpy_restatement():
+    """EkfAlgorithm::RunPredictionImu (ekf_algorithm.cpp:167-316) for one step from a random state, complementary filter off:
+    strap-down propagation with bias and gravity, Q (diagonal blocks x dt^2), F (identity + sparse blocks incl. the gravity
+    column and -dExp/dgyro), P <- F P F^T + Q — written with numpy, compared with the oracle's hand-rolled 27x27 code."""
+    from elimaloc_b200 import _capi, ekf as pekf
+    rng = np.random.default_rng(42)
+    cfg = pekf.make_ekf_config(use_complementary_filter=0)
+    f = O.EkfAlgorithm(cfg, _capi.EkfState)
+    N = 27
+    A = rng.normal(size=(N, N))
+    P0 = A @ A.T / N + np.eye(N) * 0.05
+    R0 = synth.exp_so3([0.1, -0.2, 0.7])
+    w = np.sqrt(1 + np.trace(R0)) / 2
+    q0 = np.array([w, (R0[2, 1] - R0[1, 2]) / (4 * w), (R0[0, 2] - R0[2, 0]) / (4 * w), (R0[1, 0] - R0[0, 1]) / (4 * w)])
+    st = dict(pos=[1.0, -2.0, 0.5], vel=[7.0, 0.3, -0.1], bg=[0.002, -0.001, 0.003], ba=[0.05, -0.02, 0.01], grav=[0.0, 0.0, 9.79])
+    for k, v in st.items():
+        getattr(f.s, k)[:] = v
+    f.s.rot[:] = list(q0)
+    f.s.P[:] = list(P0.reshape(-1))
+    f.s.state_initialized = 1
+    f.s.reset_for_init_prediction = 0
+    f.s.pcm_init_on_going = 0
+    t0, dt = 50.0, 0.01
+    f.s.prev_timestamp = t0
+    gyro, acc = np.array([0.02, -0.01, 0.3]), np.array([0.4, 2.1, 9.9])
+    assert f.RunPredictionImu(t0 + dt, gyro, acc)
+
+    bg, ba, grav, pos, vel = (np.array(st[k]) for k in ("bg", "ba", "grav", "pos", "vel"))
+    wg = gyro - bg
+    R1 = R0 @ rodrigues(wg * dt)
+    a_g = R0 @ (acc - ba) - grav
+    pos1 = pos + vel * dt + 0.5 * a_g * dt * dt
+    vel1 = vel + a_g * dt
+    Q = np.zeros((N, N))
+    d2r = np.pi / 180.0
+    for idx, sd in ((0, cfg.state_std_pos_m), (3, cfg.state_std_rot_deg * d2r), (6, cfg.state_std_vel_mps), (9, cfg.imu_std_gyro_dps * d2r),
+                    (12, cfg.imu_std_acc_mps), (15, cfg.imu_bias_cov_gyro), (18, cfg.imu_bias_cov_acc), (21, cfg.imu_bias_cov_acc),
+                    (24, cfg.state_std_rot_deg * d2r)):
+        Q[idx:idx + 3, idx:idx + 3] = np.eye(3) * sd ** 2 * dt * dt
+    F = np.eye(N)
+    F[0:3, 6:9] = np.eye(3) * dt
+    F[0:3, 18:21] = -0.5 * R0 * dt * dt
+    om = wg * dt
+    th = np.linalg.norm(om)
+    K = skew(om / th)
+    F[3:6, 15:18] = -dt * (np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (th - np.sin(th)) / th ** 3 * K @ K)
+    F[6:9, 18:21] = -R0 * dt
+    F[9:12, 15:18] = -np.eye(3)
+    F[12:15, 18:21] = -R0
+    F[2, 23], F[8, 23], F[14, 23] = -0.5 * dt * dt, -dt, -1.0      # imu_estimate_gravity: z column only
+    P1 = F @ P0 @ F.T + Q
+
+    s = pekf.state_to_dict(f.s)
+    qw, qx, qy, qz = s["rot"]
+    Rq = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                   [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                   [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+    np.testing.assert_allclose(Rq, R1, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s["pos"], pos1, rtol=1e-13)
+    np.testing.assert_allclose(s["vel"], vel1, rtol=1e-13)
+    np.testing.assert_allclose(s["gyro"], wg, rtol=1e-13)
+    np.testing.assert_allclose(s["acc"], a_g, rtol=1e-12)
+    np.testing.assert_allclose(np.array(s["P"]).reshape(N, N), P1, rtol=1e-11, atol=1e-14)
+    assert s["prev_timestamp"] == t0 + dt and s["predictions"] == 1
