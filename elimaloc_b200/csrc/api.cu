@@ -18,6 +18,7 @@
 #include "deskew.cuh"
 #include "ekf.cuh"
 #include "icp_kernels.cuh"
+#include "pcd_reader.hpp"
 #include "scan_prep.cuh"
 
 namespace {
@@ -499,6 +500,30 @@ int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], 
             pose_cov[6 * (i + 3) + (j + 3)] = rn[3 * i + j] * ang * ang;
         }
     return ELM_OK;
+}
+
+int elm_pcd_read_xyz(const char* path, float* xyz, size_t capacity_points, size_t* n_points, size_t* n_dropped) {
+    if (!path || !n_points) return fail(ELM_ERR_INVALID, "elm_pcd_read_xyz: bad argument");
+    std::vector<float> v;
+    size_t dropped = 0;
+    const std::string e = elm::read_pcd_xyz(path, v, &dropped);
+    if (!e.empty()) return fail(ELM_ERR_IO, e);
+    *n_points = v.size() / 3;
+    if (n_dropped) *n_dropped = dropped;
+    if (xyz) {
+        if (capacity_points < v.size() / 3) return fail(ELM_ERR_INVALID, "elm_pcd_read_xyz: buffer too small");
+        std::memcpy(xyz, v.data(), v.size() * sizeof(float));
+    }
+    return ELM_OK;
+}
+
+int elm_map_add_points_pcd(elm_map* map, const char* path, size_t* n_points) {
+    if (!map || !path) return fail(ELM_ERR_INVALID, "elm_map_add_points_pcd: bad argument");
+    std::vector<float> v;
+    const std::string e = elm::read_pcd_xyz(path, v, nullptr);
+    if (!e.empty()) return fail(ELM_ERR_IO, e);
+    if (n_points) *n_points = v.size() / 3;
+    return elm_map_add_points(map, v.data(), v.size() / 3);
 }
 
 int elm_map_save(const elm_map* map, const char* path) {

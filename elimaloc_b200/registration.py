@@ -69,6 +69,12 @@ class VoxelHashMap:
         xyz = _xyz(xyz)
         check(lib().elm_map_add_points(self._h, _f(xyz), xyz.shape[0]))
 
+    def AddPointsFromPcd(self, path):
+        """loadPCDFile + AddPoints (pcm_matching.cpp:69-88); returns the number of points read"""
+        n = C.c_size_t(0)
+        check(lib().elm_map_add_points_pcd(self._h, str(path).encode(), C.byref(n)))
+        return int(n.value)
+
     def CalVoxelCovAll(self):
         check(lib().elm_map_cal_voxel_cov(self._h))
 
@@ -126,6 +132,15 @@ class VoxelHashMap:
         e = self.export(voxel_cov=True)
         keep = e["counts"] > 2
         return e["vmean"][keep], e["vcov"][keep]
+
+
+def read_pcd_xyz(path):
+    """x, y, z of a PCD v0.7 file (ascii / binary / binary_compressed) as float32 (n, 3); returns (xyz, dropped non-finite)."""
+    n, dropped = C.c_size_t(0), C.c_size_t(0)
+    check(lib().elm_pcd_read_xyz(str(path).encode(), None, 0, C.byref(n), C.byref(dropped)))
+    xyz = np.zeros((int(n.value), 3), np.float32)
+    check(lib().elm_pcd_read_xyz(str(path).encode(), _f(xyz), int(n.value), C.byref(n), C.byref(dropped)))
+    return xyz, int(dropped.value)
 
 
 def shape_pcm_covariance(R_ego, local_cov, icp_pose_std_m, cov36=None):

@@ -101,6 +101,14 @@ int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* v
  * 6x6 `pose_cov`; the other 18 entries are left as they are, as the reference does.  Host arithmetic (a dozen flops). */
 int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], double icp_pose_std_m, double pose_cov[36]);
 
+/* PCD input: the node fills its map from a .pcd through pcl::io::loadPCDFile<PointType>
+ * (pcm_matching.cpp:69-79) and uses x, y, z only (Pcl2PointStruct, pcm_matching.hpp:205-220).  Dependency-free reader of PCD
+ * v0.7 (DATA ascii / binary / binary_compressed; x, y, z of TYPE F/I/U, any SIZE).  Points with a non-finite coordinate are
+ * dropped (counted in n_dropped).  elm_pcd_read_xyz: xyz may be NULL to query n_points first.
+ * elm_map_add_points_pcd = read + elm_map_add_points. */
+int elm_pcd_read_xyz(const char* path, float* xyz, size_t capacity_points, size_t* n_points, size_t* n_dropped);
+int elm_map_add_points_pcd(elm_map* map, const char* path, size_t* n_points);
+
 /* Built-map file.  The reference reloads its .pcd and rebuilds the whole voxel map at every start of the
  * node (pcm_matching.cpp:69-101); elm_map_save writes everything AddPoints / CalVoxelCovAll / CalPointCovAll produced
  * (canonical points, voxel table, neighbourhood directory, covariances) and elm_map_load brings it back — host arrays
