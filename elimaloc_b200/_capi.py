@@ -82,6 +82,7 @@ SIGNATURES = {
     "elm_map_num_points": (C.c_size_t, [C.c_void_p]),
     "elm_map_export": (C.c_int, [C.c_void_p, _ip, _ip, _dp, _dp, _fp, _dp, _dp]),
     "elm_shape_pcm_covariance": (C.c_int, [_dp, _dp, C.c_double, _dp]),
+    "elm_map_find_ground_height": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _dp, _ip]),
     "elm_pcd_read_xyz": (C.c_int, [C.c_char_p, _fp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "elm_map_add_points_pcd": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t)]),
     "elm_map_save": (C.c_int, [C.c_void_p, C.c_char_p]),

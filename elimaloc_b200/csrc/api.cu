@@ -502,6 +502,14 @@ int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], 
     return ELM_OK;
 }
 
+int elm_map_find_ground_height(const elm_map* map, double x, double y, double* ground_z, int32_t* found) {
+    if (!map || !ground_z || !found) return fail(ELM_ERR_INVALID, "elm_map_find_ground_height: bad argument");
+    double z = 0.0;
+    *found = map->host.find_ground_height(x, y, z) ? 1 : 0;
+    if (*found) *ground_z = z;  // untouched otherwise, like the reference's out-parameter
+    return ELM_OK;
+}
+
 int elm_pcd_read_xyz(const char* path, float* xyz, size_t capacity_points, size_t* n_points, size_t* n_dropped) {
     if (!path || !n_points) return fail(ELM_ERR_INVALID, "elm_pcd_read_xyz: bad argument");
     std::vector<float> v;

@@ -607,6 +607,35 @@ int64_t HostMap::find(uint64_t key) const {
     }
 }
 
+bool HostMap::find_ground_height(double x, double y, double& ground_z) const {
+    const double range = 5.0, range2 = range * range;                     // vhm.hpp:286-287
+    if (vkey.empty()) return false;
+    // stored keys truncate toward zero: a point with p / vs in (c - 1, c + 1) may sit under key c, so widen by one voxel
+    const double vs = voxel_size;
+    const int32_t x0 = static_cast<int32_t>(std::max(std::floor((x - range) / vs) - 1.0, static_cast<double>(-kKeyBias))),
+                  x1 = static_cast<int32_t>(std::min(std::floor((x + range) / vs) + 1.0, static_cast<double>(kKeyBias - 1)));
+    const int32_t y0 = static_cast<int32_t>(std::max(std::floor((y - range) / vs) - 1.0, static_cast<double>(-kKeyBias))),
+                  y1 = static_cast<int32_t>(std::min(std::floor((y + range) / vs) + 1.0, static_cast<double>(kKeyBias - 1)));
+    std::vector<double> zs;
+    for (int32_t kx = x0; kx <= x1; ++kx)
+        for (int32_t ky = y0; ky <= y1; ++ky) {
+            // all voxels of the column (kx, ky, *) are one contiguous run of the sorted key list
+            const uint64_t lo = pack_key(kx, ky, -kKeyBias), hi = pack_key(kx, ky, kKeyBias - 1);
+            for (size_t v = static_cast<size_t>(std::lower_bound(vkey.begin(), vkey.end(), lo) - vkey.begin()); v < vkey.size() && vkey[v] <= hi; ++v)
+                for (uint32_t p = vstart[v]; p < vstart[v + 1]; ++p) {
+                    const double dx = static_cast<double>(pxyz[3 * p]) - x, dy = static_cast<double>(pxyz[3 * p + 1]) - y;
+                    if (dx * dx + dy * dy <= range2) zs.push_back(pxyz[3 * p + 2]);   // vhm.hpp:292-296
+                }
+        }
+    if (zs.size() <= 3) return false;                                       // vhm.hpp:298-300
+    const size_t n = std::min<size_t>(5, zs.size());                        // vhm.hpp:302-306
+    std::partial_sort(zs.begin(), zs.begin() + static_cast<std::ptrdiff_t>(n), zs.end());
+    double sum = 0.0;
+    for (size_t i = 0; i < n; ++i) sum += zs[i];
+    ground_z = sum / static_cast<double>(n);                                // vhm.hpp:318-319
+    return true;
+}
+
 // CalVoxelCovAll: n == 0 -> (I, 0) [cannot occur: a voxel exists only with >= 1 point]; n == 1 -> (I, p);
 // n >= 2 -> sample covariance /(n-1), regularised, with the mean.
 void HostMap::cal_voxel_cov() {

@@ -78,6 +78,10 @@ struct HostMap {
     int64_t dir_find(uint64_t key) const;
     // voxel index of a packed key or -1
     int64_t find(uint64_t key) const;
+    // VoxelHashMap::FindGroundHeight (voxel_hash_map.hpp:285-322): mean z of the (up to) five lowest stored points within 5 m
+    // of (x, y) in the plane; false when three or fewer points are in range.  Walks only the voxel columns that can reach
+    // the disc instead of copying the whole map as the reference does.
+    bool find_ground_height(double x, double y, double& ground_z) const;
     // Built-map file (the reference reloads the .pcd and rebuilds the whole map at every start,
     // pcm_matching.cpp:69-101): every array above, little-endian, behind a header with magic / version / sizes.
     // Both return "" on success, else an error message.

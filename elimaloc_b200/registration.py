@@ -75,6 +75,12 @@ class VoxelHashMap:
         check(lib().elm_map_add_points_pcd(self._h, str(path).encode(), C.byref(n)))
         return int(n.value)
 
+    def FindGroundHeight(self, position_xy):
+        """voxel_hash_map.hpp:285-322: (found, ground_z)"""
+        z, found = C.c_double(0.0), C.c_int32(0)
+        check(lib().elm_map_find_ground_height(self._h, float(position_xy[0]), float(position_xy[1]), C.byref(z), C.byref(found)))
+        return bool(found.value), float(z.value)
+
     def CalVoxelCovAll(self):
         check(lib().elm_map_cal_voxel_cov(self._h))
 

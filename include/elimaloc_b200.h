@@ -101,6 +101,12 @@ int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* v
  * 6x6 `pose_cov`; the other 18 entries are left as they are, as the reference does.  Host arithmetic (a dozen flops). */
 int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], double icp_pose_std_m, double pose_cov[36]);
 
+/* VoxelHashMap::FindGroundHeight (voxel_hash_map.hpp:285-322; used by the RViz initial-pose click, pcm_matching.cpp:387):
+ * mean z of the up to five lowest stored points within 5 m of (x, y) in the plane; found = 0 (ground_z untouched) when three
+ * or fewer points are in range.  Host arithmetic on the sorted map (only the voxel columns that reach the disc are visited;
+ * the reference copies the whole map per click). */
+int elm_map_find_ground_height(const elm_map* map, double x, double y, double* ground_z, int32_t* found);
+
 /* PCD input: the node fills its map from a .pcd through pcl::io::loadPCDFile<PointType>
  * (pcm_matching.cpp:69-79) and uses x, y, z only (Pcl2PointStruct, pcm_matching.hpp:205-220).  Dependency-free reader of PCD
  * v0.7 (DATA ascii / binary / binary_compressed; x, y, z of TYPE F/I/U, any SIZE).  Points with a non-finite coordinate are

@@ -221,6 +221,25 @@ int orc_ekf_predict_imu(const EkfConfig* c, EkfStateBlob* s, double t, const dou
 int orc_ekf_update_pose(const EkfConfig* c, EkfStateBlob* s, const EkfMeasurement* m) { return EkfUpdatePose(*c, *s, *m) ? 1 : 0; }
 void orc_ekf_get_current_state(EkfStateBlob* s, double* ego) { EkfGetCurrentState(*s, ego); }
 
+// ---- FindGroundHeight (vhm.hpp:285-322): the reference's full scan over Pointcloud() ------------------------------------
+int orc_find_ground_height(void* mp, double x, double y, double* ground_z) {
+    auto* M = static_cast<VoxelHashMap*>(mp);
+    const double range2 = 5.0 * 5.0;                                           // :286-287
+    std::vector<double> zs;
+    for (const auto& kv : M->map_)                                             // Pointcloud(), :288
+        for (const PointStruct& p : kv.second.points) {
+            const double dx = p.pose.x - x, dy = p.pose.y - y;
+            if (dx * dx + dy * dy <= range2) zs.push_back(p.pose.z);           // :291-296
+        }
+    if (zs.size() <= 3) return 0;                                              // :298-300
+    const size_t n = std::min<size_t>(5, zs.size());
+    std::partial_sort(zs.begin(), zs.begin() + static_cast<std::ptrdiff_t>(n), zs.end());   // :303-306 (by z)
+    double sum = 0.0;
+    for (size_t i = 0; i < n; ++i) sum += zs[i];
+    *ground_z = sum / static_cast<double>(n);                                  // :318-319
+    return 1;
+}
+
 // ---- scan pre-processing: FilterPointsByDistance (pcm_matching.cpp:451-465) then VoxelDownsample (vhm.hpp:260-283) ----
 // Writes the INPUT INDEX of every survivor (input order); returns their number.  max_dist <= 0 / voxel_size <= 0 skip a step.
 size_t orc_scan_preprocess(const float* xyz, size_t n, double max_dist, double voxel_size, int32_t* index_out) {

@@ -80,6 +80,7 @@ def lib():
         L.orc_ekf_update_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ekf_get_current_state.argtypes = [C.c_void_p, dp]
         L.orc_shape_pcm_covariance.argtypes = [dp, dp, C.c_double, dp]
+        L.orc_find_ground_height.argtypes = [C.c_void_p, C.c_double, C.c_double, dp]
         L.orc_scan_preprocess.restype = C.c_size_t
         L.orc_scan_preprocess.argtypes = [fp, C.c_size_t, C.c_double, C.c_double, ip]
         _LIB = L
@@ -133,6 +134,12 @@ class VoxelHashMap:
 
     def Empty(self):
         return self.num_voxels() == 0
+
+    def FindGroundHeight(self, position_xy):
+        """vhm.hpp:285-322: (found, ground_z)"""
+        z = C.c_double(0.0)
+        found = lib().orc_find_ground_height(self._h, float(position_xy[0]), float(position_xy[1]), C.byref(z))
+        return bool(found), float(z.value)
 
     def export(self):
         V, P = self.num_voxels(), self.num_points()

@@ -91,6 +91,11 @@ struct VoxelHashMap {
     void CalVoxelCovAll() { elm_shim::check(elm_map_cal_voxel_cov(h_)); }
     void CalPointCovAll(double d_search_dist) { elm_shim::check(elm_map_cal_point_cov(h_, d_search_dist)); }
     bool Empty() const { return !h_ || elm_map_empty(h_); }
+    bool FindGroundHeight(const Eigen::Matrix<double, 2, 1>& position, double& ground_z) const {  // voxel_hash_map.hpp:285-322
+        int32_t found = 0;
+        elm_shim::check(elm_map_find_ground_height(h_, position(0), position(1), &ground_z, &found));
+        return found != 0;
+    }
     std::vector<PointStruct> Pointcloud() const {  // visualisation only (pcm_matching.cpp:104)
         std::vector<float> xyz(3 * elm_map_num_points(h_));
         elm_map_export(h_, nullptr, nullptr, nullptr, nullptr, xyz.data(), nullptr, nullptr);

@@ -240,3 +240,27 @@ def test_parallel_builder_equals_sequential_insert_on_awkward_maps(kind):
     for k in ("keys", "counts", "pxyz"):
         assert np.array_equal(pe[k], oe[k]), k
     assert pm.directory_check()[2] == 0
+
+
+def test_find_ground_height_matches_oracle_and_numpy():
+    """VoxelHashMap::FindGroundHeight (voxel_hash_map.hpp:285-322): product (column walk over the sorted map), oracle (full scan
+    like the reference) and a numpy one-liner agree; three or fewer points in range -> not found, output untouched."""
+    raw = synth.map_s(60_000, 60.0)
+    raw[:, 2] += np.float32(-3.0)                       # ground below zero, walls across it
+    raw[:, :2] -= np.float32(25.0)                      # positive and negative x / y
+    pm, om = E.VoxelHashMap(1.0, 30, device=-1), O.VoxelHashMap(1.0, 30)
+    pm.AddPoints(raw)
+    om.AddPoints(raw)
+    stored = pm.export()["pxyz"].astype(np.float64)
+    rng = np.random.default_rng(0)
+    for q in np.vstack([rng.uniform(-30, 40, (40, 2)), [[-25.0, -25.0], [1000.0, 0.0], [34.99, 34.99]]]):
+        d2 = (stored[:, 0] - q[0]) ** 2 + (stored[:, 1] - q[1]) ** 2
+        zs = np.sort(stored[d2 <= 25.0, 2])
+        gf, gz = pm.FindGroundHeight(q)
+        of, oz = om.FindGroundHeight(q)
+        assert gf == of == (len(zs) > 3)
+        if gf:
+            want = zs[:5].sum() / min(5, len(zs))
+            assert abs(gz - want) < 1e-12 and abs(oz - want) < 1e-12
+        else:
+            assert gz == 0.0
