@@ -184,7 +184,16 @@ def cpu_arm(args, raw, scan, T_init, method, steps, warmup, iters_per_sample):
         s, it = reg.time_register(scan, om, T_init, cfg)
         tot_s += s
         tot_it += it
-    return dict(value=tot_it / tot_s, seconds=tot_s, iterations=tot_it, threads=threads, build_s=build_s)
+    # second line: the same port with AlignClouds* and TransformPoints parallel too (not the reference's structure),
+    # so that the GPU/CPU ratio is not inflated by the reference's serial accumulation
+    cfg_be = O.make_config(icp_method=method, max_iteration=iters_per_sample, max_thread=threads, reserved0=1, **synth.timing_knobs())
+    reg.time_register(scan, om, T_init, cfg_be)
+    be_s, be_it = 0.0, 0
+    for _ in range(max(1, steps)):
+        s, it = reg.time_register(scan, om, T_init, cfg_be)
+        be_s += s
+        be_it += it
+    return dict(value=tot_it / tot_s, seconds=tot_s, iterations=tot_it, threads=threads, build_s=build_s, best_effort=be_it / be_s)
 
 
 def main():
@@ -213,7 +222,7 @@ def main():
                "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": "port",
-                                "sample": sample},
+                                "sample": sample, "best_effort_all_parallel_value": r["best_effort"]},
                "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
         print(json.dumps(out))
@@ -428,7 +437,8 @@ def main():
         cpu = {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": "port",
                "sample": f"2 RunRegister calls x {args.cpu_iters} forced iterations of the same workload "
                          f"(oracle port; search on {r['threads']} OpenMP threads, accumulate serial as in the reference); "
-                         f"oracle map build {r['build_s']:.1f} s not timed"}
+                         f"oracle map build {r['build_s']:.1f} s not timed",
+               "best_effort_all_parallel_value": r["best_effort"]}
 
     if rank == 0:
         out = {"metric": "icp_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,

@@ -29,6 +29,7 @@ static RegistrationConfig to_cfg(const orc_reg_config* c) {
     r.i_max_thread = c->max_thread > 0 ? c->max_thread : 1;
     r.use_radar_cov = c->use_radar_cov != 0;
     r.b_debug_print = c->debug_print != 0;
+    r.parallel_accumulate = (c->reserved0 & 1) != 0;
     r.max_search_dist = c->max_search_dist;
     r.lm_lambda = c->lm_lambda;
     r.icp_termination_threshold_m = c->icp_termination_threshold_m;

@@ -35,6 +35,30 @@ inline void accumulate(const double J[3][6], const M3& M, const V3& r, double w,
     }
 }
 
+// The accumulation loop of the three AlignClouds*.  threads <= 1: one serial loop, as in the reference.  Otherwise (the
+// best-effort timing variant, not in the reference): static chunks, per-chunk sums joined in chunk order.
+struct PairSums { M6 JTJ; V6 JTr; double res = 0.0; };
+template <class Body>
+inline PairSums accumulate_pairs(size_t n, int threads, Body body) {
+    if (threads <= 1) {
+        PairSums s;
+        for (size_t i = 0; i < n; ++i) body(i, s);
+        return s;
+    }
+    std::vector<PairSums> parts(static_cast<size_t>(threads));
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; ++t) {
+        PairSums& s = parts[static_cast<size_t>(t)];
+        for (size_t i = n * static_cast<size_t>(t) / threads; i < n * static_cast<size_t>(t + 1) / threads; ++i) body(i, s);
+    }
+    PairSums tot = parts[0];
+    for (int t = 1; t < threads; ++t) {
+        for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) tot.JTJ(a, b) += parts[t].JTJ(a, b); tot.JTr.v[a] += parts[t].JTr.v[a]; }
+        tot.res += parts[t].res;
+    }
+    return tot;
+}
+
 // Tail shared by the three AlignClouds*: LM damping on diag(JTJ), LDLT solve, AngleAxis -> 4x4
 // (reg.cpp:55-65, 136-151, 213-224).  x = [translation ; rotation vector]  (Q9, Q10).
 inline M4 solve_update(const M6& JTJ, const V6& JTr, double lm_lambda, M6* regularized_out) {
@@ -51,11 +75,16 @@ inline M4 solve_update(const M6& JTJ, const V6& JTr, double lm_lambda, M6* regul
 }
 }  // namespace
 
+// threads of TransformPoints: 1 (serial, as in the reference) unless the best-effort timing variant is on
+static int g_transform_threads = 1;
+
 // reg.hpp:136-148 — pose <- T * pose, every other field (incl. `local`) copied.
 void Registration::TransformPoints(const M4& T, const std::vector<PointStruct>& points,
                                    std::vector<PointStruct>& o_points) {
     o_points.resize(points.size());
-    for (size_t i = 0; i < points.size(); ++i) {
+    const long long n = static_cast<long long>(points.size());
+#pragma omp parallel for num_threads(g_transform_threads) schedule(static) if (g_transform_threads > 1)
+    for (long long i = 0; i < n; ++i) {
         PointStruct p = points[i];
         p.pose = apply(T, points[i].pose);
         o_points[i] = p;
@@ -66,20 +95,20 @@ void Registration::TransformPoints(const M4& T, const std::vector<PointStruct>& 
 M4 Registration::AlignCloudsLocal(const std::vector<PointStruct>& source_global,
                                   const std::vector<PointStruct>& target_global, const M4& last_icp_pose,
                                   double trans_th, const RegistrationConfig& cfg, Linearization* lin) {
-    M6 JTJ;
-    V6 JTr;
     const M4 last_icp_pose_inv = inverse(last_icp_pose);  // reg.cpp:24
     const M3 I3 = M3::Identity();
-    double d_residual_sum = 0.0;
-    for (size_t i = 0; i < source_global.size(); ++i) {
+    const PairSums sums = accumulate_pairs(source_global.size(), cfg.parallel_accumulate ? cfg.i_max_thread : 1, [&](size_t i, PairSums& s) {
         const V3 target_local = apply(last_icp_pose_inv, target_global[i].pose);  // reg.cpp:29-33
         const V3 residual_local = target_local - source_global[i].local;          // reg.cpp:34
         double J[3][6];
         jacobian(source_global[i].local, J);
         const double weight_g = square(trans_th) / square(trans_th + sqnorm(residual_local));  // reg.cpp:44
-        accumulate(J, I3, residual_local, weight_g, JTJ, JTr);                                 // reg.cpp:47-48
-        d_residual_sum += norm(residual_local);                                                // reg.cpp:50
-    }
+        accumulate(J, I3, residual_local, weight_g, s.JTJ, s.JTr);                             // reg.cpp:47-48
+        s.res += norm(residual_local);                                                         // reg.cpp:50
+    });
+    const M6& JTJ = sums.JTJ;
+    const V6& JTr = sums.JTr;
+    const double d_residual_sum = sums.res;
     d_fitness_score_ = d_residual_sum / source_global.size();  // reg.cpp:53
     if (lin) { lin->JTJ = JTJ; lin->JTr = JTr; lin->residual_sum = d_residual_sum; lin->n_corr = (long long)source_global.size(); }
     return solve_update(JTJ, JTr, cfg.lm_lambda, nullptr);
@@ -90,14 +119,11 @@ M4 Registration::AlignCloudsLocalPointCov(const std::vector<PointStruct>& source
                                           const std::vector<PointStruct>& target_global, M6& local_cov,
                                           const M4& last_icp_pose, double trans_th, const RegistrationConfig& cfg,
                                           Linearization* lin) {
-    M6 JTJ;
-    V6 JTr;
     const M3 sensor_rot = rot_of(last_icp_pose);
     const M3 sensor_rot_inv = inverse(sensor_rot);         // reg.cpp:79
     const M3 sensor_rot_inv_t = transpose(sensor_rot_inv);
     const M4 last_icp_pose_inv = inverse(last_icp_pose);   // reg.cpp:81
-    double d_residual_sum = 0.0;
-    for (size_t i = 0; i < source_global.size(); ++i) {
+    const PairSums sums = accumulate_pairs(source_global.size(), cfg.parallel_accumulate ? cfg.i_max_thread : 1, [&](size_t i, PairSums& s) {
         const CovStruct& target_cov = target_global[i].covariance;
         double w[3];
         M3 V;
@@ -111,9 +137,12 @@ M4 Registration::AlignCloudsLocalPointCov(const std::vector<PointStruct>& source
         double J[3][6];
         jacobian(source_global[i].local, J);
         const double weight_g = square(trans_th) / square(trans_th + sqnorm(residual_local)) * 0.8 + 0.2;  // reg.cpp:121
-        accumulate(J, mahalanobis_local, residual_local, weight_g, JTJ, JTr);                            // reg.cpp:124-125
-        d_residual_sum += std::fabs(dot(residual_local, vec_normal_local));                              // reg.cpp:128-131
-    }
+        accumulate(J, mahalanobis_local, residual_local, weight_g, s.JTJ, s.JTr);                        // reg.cpp:124-125
+        s.res += std::fabs(dot(residual_local, vec_normal_local));                                       // reg.cpp:128-131
+    });
+    const M6& JTJ = sums.JTJ;
+    const V6& JTr = sums.JTr;
+    const double d_residual_sum = sums.res;
     d_fitness_score_ = d_residual_sum / source_global.size();  // reg.cpp:134
     if (lin) { lin->JTJ = JTJ; lin->JTr = JTr; lin->residual_sum = d_residual_sum; lin->n_corr = (long long)source_global.size(); }
     M6 regularized;
@@ -126,14 +155,11 @@ M4 Registration::AlignCloudsLocalPointCov(const std::vector<PointStruct>& source
 M4 Registration::AlignCloudsLocalVoxelCov(const std::vector<PointStruct>& source_global,
                                           const std::vector<CovStruct>& target_cov_global, const M4& last_icp_pose,
                                           double trans_th, const RegistrationConfig& cfg, Linearization* lin) {
-    M6 JTJ;
-    V6 JTr;
     const M3 sensor_rot = rot_of(last_icp_pose);
     const M3 sensor_rot_inv = inverse(sensor_rot);        // reg.cpp:165
     const M3 sensor_rot_inv_t = transpose(sensor_rot_inv);
     const M4 last_icp_pose_inv = inverse(last_icp_pose);  // reg.cpp:167
-    double d_residual_sum = 0.0;
-    for (size_t i = 0; i < source_global.size(); ++i) {
+    const PairSums sums = accumulate_pairs(source_global.size(), cfg.parallel_accumulate ? cfg.i_max_thread : 1, [&](size_t i, PairSums& s) {
         const CovStruct& target_cov = target_cov_global[i];
         const V3 target_local = apply(last_icp_pose_inv, target_cov.mean);          // reg.cpp:176-180
         const V3 residual_local = target_local - source_global[i].local;            // reg.cpp:181
@@ -142,10 +168,13 @@ M4 Registration::AlignCloudsLocalVoxelCov(const std::vector<PointStruct>& source
         double J[3][6];
         jacobian(source_global[i].local, J);
         const double weight_g = square(trans_th) / square(trans_th + sqnorm(residual_local));  // reg.cpp:199
-        if (weight_g < 0.01) continue;                                                         // reg.cpp:201
-        accumulate(J, mahalanobis_local, residual_local, weight_g, JTJ, JTr);                  // reg.cpp:204-205
-        d_residual_sum += norm(residual_local);                                                // reg.cpp:207
-    }
+        if (weight_g < 0.01) return;                                                           // reg.cpp:201 (continue)
+        accumulate(J, mahalanobis_local, residual_local, weight_g, s.JTJ, s.JTr);              // reg.cpp:204-205
+        s.res += norm(residual_local);                                                         // reg.cpp:207
+    });
+    const M6& JTJ = sums.JTJ;
+    const V6& JTr = sums.JTr;
+    const double d_residual_sum = sums.res;
     d_fitness_score_ = d_residual_sum / source_global.size();  // reg.cpp:210
     if (lin) { lin->JTJ = JTJ; lin->JTr = JTr; lin->residual_sum = d_residual_sum; lin->n_corr = (long long)source_global.size(); }
     return solve_update(JTJ, JTr, cfg.lm_lambda, nullptr);
@@ -155,6 +184,7 @@ Linearization Registration::LinearizeOnce(const std::vector<PointStruct>& source
                                           const M4& pose, const RegistrationConfig& cfg) {
     std::vector<PointStruct> source_global, sc, tc;
     std::vector<CovStruct> tcc;
+    g_transform_threads = cfg.parallel_accumulate ? cfg.i_max_thread : 1;
     TransformPoints(pose, source_local, source_global);
     Linearization lin;
     M6 cov_unused;
@@ -194,6 +224,7 @@ M4 Registration::RunRegister(const std::vector<PointStruct>& source_local, const
     double corres_ratio = 0.0;
 
     std::vector<PointStruct> source_global;
+    g_transform_threads = cfg.parallel_accumulate ? cfg.i_max_thread : 1;
     TransformPoints(initial_guess, source_local, source_global);  // reg.cpp:289
 
     if (voxel_map.Empty()) {  // reg.cpp:291-295

@@ -26,6 +26,9 @@ struct RegistrationConfig {
     double azimuth_variance_deg = 0.4;
     double elevation_variance_deg = 0.4;
     bool b_debug_print = false;
+    // NOT in the reference: "best-effort CPU" timing variant — AlignClouds* and TransformPoints run over
+    // i_max_thread static chunks whose partial sums are joined in chunk order.  Off: serial loops exactly as reg.cpp has them.
+    bool parallel_accumulate = false;
 };
 
 // One linearisation (what a single AlignClouds* call accumulates before its solve).

@@ -211,3 +211,26 @@ def test_golden_config1(name, method):
         assert om.num_voxels() == int(d["n_voxels"]) and om.num_points() == int(d["n_points"])
         assert np.array_equal(e["keys"][:64], d["keys_head"]) and np.array_equal(e["pxyz"][:64], d["pxyz_head"])
         np.testing.assert_allclose(e["pcov"][:16], d["pcov_head"], atol=1e-12)
+
+
+def test_best_effort_parallel_variant_equals_the_serial_structure():
+    """reserved0 = 1 switches the oracle's AlignClouds* / TransformPoints to chunked parallel loops (the "best-effort CPU"
+    timing line of SURVEY 8d; not in the reference): same numbers up to the summation order of the chunks."""
+    raw = synth.map_s(40_000, 30.0)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw)
+    om.CalVoxelCovAll()
+    om.CalPointCovAll(0.4)
+    T_true = synth.se3([6.0, 7.0, 2.0], [0.02, -0.03, 0.4])
+    scan = synth.scan_m(om.export()["pxyz"], 3000, T_true)
+    T0 = T_true @ synth.canonical_offset()
+    for method in (O.P2P, O.GICP, O.VGICP, O.AVGICP):
+        kw = dict(icp_method=method, max_iteration=5, **synth.timing_knobs())
+        a = O.Registration().linearize(scan, om, T0, O.make_config(max_thread=1, **kw))
+        b = O.Registration().linearize(scan, om, T0, O.make_config(max_thread=5, reserved0=1, **kw))
+        assert a["n_corr"] == b["n_corr"]
+        assert np.abs(a["JTJ"] - b["JTJ"]).max() <= 1e-12 * np.abs(a["JTJ"]).max()
+        assert abs(a["residual_sum"] - b["residual_sum"]) <= 1e-12 * a["residual_sum"]
+        ra = O.Registration().RunRegister(scan, om, T0, O.make_config(max_thread=3, **kw))
+        rb = O.Registration().RunRegister(scan, om, T0, O.make_config(max_thread=3, reserved0=1, **kw))
+        assert np.abs(ra["pose"] - rb["pose"]).max() <= 1e-10 * np.abs(ra["pose"]).max()
