@@ -668,30 +668,23 @@ void HostMap::build_voxel_candidates() {
     if (S == 0) return;
     std::vector<int32_t> voxel_slot(V(), -1);
     for (size_t s = 0; s < slot_voxel.size(); ++s) if (slot_voxel[s] >= 0) voxel_slot[slot_voxel[s]] = static_cast<int32_t>(s);
+    // The nine column descriptors of the entry's row already say which of the 27 voxels exist (count > 0) and where their
+    // points start; the voxels of one column are consecutive in the sorted voxel list, so one search per non-empty column
+    // (first point -> voxel index) replaces 27 table look-ups.
     // pass 1: occupancy mask + count per entry; pass 2: fill (two passes so that the candidate array is laid out in slot order)
     std::vector<uint32_t> first(S + 1, 0);
-    auto neighbours = [&](size_t s, int64_t* v27) -> uint32_t {
-        const DirSlot& sl = dir_slots[s];
-        if ((sl.key_lo & sl.key_hi) == 0xffffffffu) return 0;
-        const uint64_t key = (static_cast<uint64_t>(sl.key_hi) << 32) | sl.key_lo;
-        int32_t x, y, z;
-        unpack_key(key, x, y, z);
-        uint32_t mask = 0;
-        for (int L = 0; L < 27; ++L) {
-            const int32_t vx = x + L / 9 - 1, vy = y + (L / 3) % 3 - 1, vz = z + L % 3 - 1;
-            v27[L] = -1;
-            if (!key_in_range(vx) || !key_in_range(vy) || !key_in_range(vz)) continue;
-            const int64_t v = find(pack_key(vx, vy, vz));
-            if (v < 0) continue;
-            v27[L] = v;
-            mask |= 1u << L;
-        }
-        return mask;
-    };
     std::vector<uint32_t> masks(S, 0);
-    parallel_for(S, 1 << 13, [&](size_t sb, size_t se) {
-        int64_t v27[27];
-        for (size_t s = sb; s < se; ++s) masks[s] = neighbours(s, v27);
+    parallel_for(S, 1 << 14, [&](size_t sb, size_t se) {
+        for (size_t s = sb; s < se; ++s) {
+            const DirSlot& sl = dir_slots[s];
+            if ((sl.key_lo & sl.key_hi) == 0xffffffffu) continue;
+            uint32_t mask = 0;
+            for (int c = 0; c < 9; ++c) {
+                const uint32_t counts = dir_rows[s * kDirRowDescs + c].counts;
+                for (int dz = 0; dz < 3; ++dz) if ((counts >> (kDirCountBits * dz)) & kDirCountMask) mask |= 1u << (3 * c + dz);
+            }
+            masks[s] = mask;
+        }
     });
     for (size_t s = 0; s < S; ++s) first[s + 1] = first[s] + static_cast<uint32_t>(__builtin_popcount(masks[s]));
     vcand.assign(4 * static_cast<size_t>(first[S]) + 4, 0.0f);  // (+1 element of padding: aligned 32-byte pair loads)
@@ -703,7 +696,13 @@ void HostMap::build_voxel_candidates() {
             row[10] = DirDesc{first[s], first[s + 1] - first[s]};
             row[11] = DirDesc{masks[s], 0};
             if (!masks[s]) continue;
-            neighbours(s, v27);
+            for (int c = 0; c < 9; ++c) {
+                v27[3 * c] = v27[3 * c + 1] = v27[3 * c + 2] = -1;
+                if (!((masks[s] >> (3 * c)) & 7u)) continue;
+                // voxel that owns the column's first point: vstart[v] <= first < vstart[v + 1]
+                int64_t v = static_cast<int64_t>(std::upper_bound(vstart.begin(), vstart.end(), row[c].first) - vstart.begin()) - 1;
+                for (int dz = 0; dz < 3; ++dz) if ((masks[s] >> (3 * c + dz)) & 1u) v27[3 * c + dz] = v++;
+            }
             static const int kL7[7] = {13, 22, 4, 16, 10, 14, 12};  // centre, +x, -x, +y, -y, +z, -z
             for (int j = 0; j < 7; ++j) if (v27[kL7[j]] >= 0) dir7[8 * s + j] = voxel_slot[v27[kL7[j]]];
             float* out = &vcand[4 * static_cast<size_t>(first[s])];
