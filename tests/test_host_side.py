@@ -115,7 +115,7 @@ def test_product_does_not_import_the_oracle():
                 assert "oracle" not in open(os.path.join(dirpath, f), errors="replace").read().lower(), os.path.join(dirpath, f)
 
 
-@pytest.mark.parametrize("kind", ["dense_negative", "sparse_surface", "single_point", "incremental"])
+@pytest.mark.parametrize("kind", ["dense_negative", "sparse_surface", "single_point", "incremental", "long_line", "two_far_clusters"])
 def test_neighbourhood_directory_is_consistent(kind):
     """The 2-choice directory the P2P/GICP search reads: every centre key whose 27 voxels (GetAdjacentVoxels range 2,
     voxel_hash_map.cpp:232-241) hold a point is found, column descriptors equal the canonical arrays, others miss."""
@@ -126,6 +126,13 @@ def test_neighbourhood_directory_is_consistent(kind):
         pm.AddPoints(synth.map_s(40_000, 60.0))
     elif kind == "single_point":
         pm.AddPoints(np.array([[-0.5, 0.25, 3.5]], np.float32))
+    elif kind == "long_line":          # 60 000 voxels in a row: keys differ in one field only (a bad case for a weak hash)
+        x = np.arange(-30_000, 30_000, dtype=np.float64) + 0.5
+        pm.AddPoints(np.stack([x, np.full_like(x, 0.5), np.full_like(x, -0.5)], 1).astype(np.float32))
+    elif kind == "two_far_clusters":   # near the ends of the key range, 2 million voxels apart
+        a = synth.map_u(3_000, 6.0, origin=-1_000_000.0)
+        b = synth.map_u(3_000, 6.0, origin=999_990.0, seed=5)
+        pm.AddPoints(np.vstack([a, b]))
     else:
         raw = synth.map_u(30_000, 12.0, origin=-2.0)
         pm.AddPoints(raw[:10_000])
