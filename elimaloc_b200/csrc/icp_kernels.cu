@@ -6,16 +6,19 @@
 //   icp_accumulate_kernel<M>   AlignCloudsLocal{,PointCov,VoxelCov} accumulation        reg.cpp:28-51 / 85-132 / 171-208
 //        (AVGICP searches its 7 voxels inside this kernel, vhm.cpp:153-206), block tree reduction, and in the LAST
 //        block to finish: fixed-order reduction of all partials + the solve/update step below
+//        (multi-GPU: before the solve the last block all-reduces the 32 sums over the ranks through peer-memory mailboxes)
 //   icp_solve_kernel           overlap gate, LM-damped LDLT solve, exp map, pose update, termination test
-//        (reg.cpp:349-356, 53-65, 136-151, 378-387) — separate launch only in multi-GPU mode, after the ncclAllReduce
+//        (reg.cpp:349-356, 53-65, 136-151, 378-387) — separate launch only in the NCCL mode, after the ncclAllReduce
 //   icp_begin_kernel           state <- initial guess (+ inverses)                      reg.cpp:298,24,79
 //   icp_export_kernel          match[] -> (count, target) dump for the parity tests
+// All searches start from ONE lookup in the neighbourhood directory (icp_device.cuh) instead of 27 / 7 probes of a voxel table.
 //
-// Exactness: the transformed scan point, its voxel key and every candidate distance are computed in fp64 with explicit
-// round-to-nearest mul/add (never contracted into FMA) in the same association order as the CPU reference, so the
-// nearest-neighbour choice — including its first-in-visit-order tie-break — is bit-identical to the reference.
-// The search may skip voxels whose bounding box is provably farther than the best candidate found so far (exact
-// pruning: identical result, fewer bytes); `prune = 0` visits all 27 voxels like the reference does.
+// Exactness: the transformed scan point, its voxel key and every DECIDING candidate distance are computed in fp64 with
+// explicit round-to-nearest mul/add (never contracted into FMA) in the same association order as the CPU reference, so the
+// nearest-neighbour choice — including its first-in-visit-order tie-break — is bit-identical to the reference.  Two
+// shortcuts never change that choice: voxels whose bounding box is provably farther than the best candidate found so far are
+// skipped (exact pruning; `prune = 0` visits all 27 voxels like the reference does), and candidates are pre-filtered with fp32
+// distances inside a proved error band (visit_points) — anything that could win or tie is still decided in fp64.
 // The accumulation that follows is plain fp64 (FMA allowed) and is compared with a tolerance.
 #include "icp_kernels.cuh"
 #include "voxel_key.hpp"
