@@ -417,3 +417,163 @@ def test_oracle_imu_prediction_equals_a_numpy_restatement():
     np.testing.assert_allclose(s["acc"], a_g, rtol=1e-12)
     np.testing.assert_allclose(np.array(s["P"]).reshape(N, N), P1, rtol=1e-11, atol=1e-14)
     assert s["prev_timestamp"] == t0 + dt and s["predictions"] == 1
+
+
+def quat_to_R(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def R_to_quat(R):
+    w = np.sqrt(1 + np.trace(R)) / 2
+    return np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
+
+
+def rot_to_vec(R):
+    """RotToVec (localization_functions.hpp:312-333), non-gimbal branch: roll, pitch, yaw"""
+    pitch = np.arcsin(-R[2, 0])
+    return np.array([np.arctan2(R[2, 1] / np.cos(pitch), R[2, 2] / np.cos(pitch)), pitch, np.arctan2(R[1, 0] / np.cos(pitch), R[0, 0] / np.cos(pitch))])
+
+
+def test_oracle_pcm_update_equals_a_numpy_restatement():
+    """EkfAlgorithm::RunGnssUpdate for a PCM measurement (ekf_algorithm.cpp:366-428) + UpdateEkfState (ekf_algorithm.hpp:116-145):
+    Y = [dpos; Euler(meas) - Euler(state)] (CalEulerResidualFromQuat), K = P H^T (H P H^T + R)^-1, EVERY state block updated from
+    K Y, rot and imu_rot right-multiplied by the angle-axis quaternions of their slices, P <- P - K H P."""
+    from elimaloc_b200 import _capi, ekf as pekf
+    rng = np.random.default_rng(9)
+    N = 27
+    f = O.EkfAlgorithm(pekf.make_ekf_config(use_complementary_filter=0), _capi.EkfState)
+    A = rng.normal(size=(N, N))
+    P0 = A @ A.T / N + np.eye(N) * 0.05
+    R0 = synth.exp_so3([0.03, -0.05, 0.8])
+    Ri = synth.exp_so3([0.01, 0.02, -0.03])
+    st = dict(pos=[4.0, -1.0, 0.2], vel=[6.0, 0.5, 0.0], gyro=[0.0, 0.01, 0.2], acc=[0.1, 0.2, 0.0], bg=[1e-3, 2e-3, -1e-3],
+              ba=[0.02, 0.0, -0.01], grav=[0.0, 0.0, 9.8])
+    for k, v in st.items():
+        getattr(f.s, k)[:] = v
+    f.s.rot[:] = list(R_to_quat(R0))
+    f.s.imu_rot[:] = list(R_to_quat(Ri))
+    f.s.P[:] = list(P0.reshape(-1))
+    f.s.state_initialized = 1
+    Rm = synth.exp_so3([0.0, 0.0, 0.83]) @ synth.exp_so3([0.0, -0.04, 0.0]) @ synth.exp_so3([0.02, 0.0, 0.0])
+    zpos = np.array([4.2, -1.1, 0.25])
+    R6 = np.diag([0.04, 0.05, 0.09, 2e-4, 1e-4, 4e-4])
+    assert f.RunGnssUpdate(pekf.make_measurement(7.0, zpos, R_to_quat(Rm), R6[:3, :3], R6[3:, 3:], source=pekf.PCM))
+
+    H = np.zeros((6, N))
+    H[:6, :6] = np.eye(6)
+    K = P0 @ H.T @ np.linalg.inv(H @ P0 @ H.T + R6)
+    res = rot_to_vec(Rm) - rot_to_vec(R0)
+    res = (res + np.pi) % (2 * np.pi) - np.pi
+    Y = np.r_[zpos - np.array(st["pos"]), res]
+    du = K @ Y
+    s = pekf.state_to_dict(f.s)
+    for name, lo in (("pos", 0), ("vel", 6), ("gyro", 9), ("acc", 12), ("bg", 15), ("ba", 18), ("grav", 21)):
+        np.testing.assert_allclose(s[name], np.array(st[name]) + du[lo:lo + 3], rtol=1e-10, atol=1e-13, err_msg=name)
+    np.testing.assert_allclose(quat_to_R(s["rot"]), R0 @ rodrigues(du[3:6]), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(quat_to_R(s["imu_rot"]), Ri @ rodrigues(du[24:27]), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.array(s["P"]).reshape(N, N), P0 - K @ H @ P0, rtol=1e-10, atol=1e-13)
+
+
+def predict_numpy(st, P0, gyro, acc, dt, cfg, N=27):
+    """the strap-down step + F / Q of test_oracle_imu_prediction..., as a function: returns (new state dict, P1)"""
+    d2r = np.pi / 180.0
+    R0 = st["R"]
+    wg = gyro - st["bg"]
+    a_g = R0 @ (acc - st["ba"]) - st["grav"]
+    new = dict(st, R=R0 @ rodrigues(wg * dt), pos=st["pos"] + st["vel"] * dt + 0.5 * a_g * dt * dt, vel=st["vel"] + a_g * dt, gyro=wg, acc=a_g)
+    Q = np.zeros((N, N))
+    for idx, sd in ((0, cfg.state_std_pos_m), (3, cfg.state_std_rot_deg * d2r), (6, cfg.state_std_vel_mps), (9, cfg.imu_std_gyro_dps * d2r),
+                    (12, cfg.imu_std_acc_mps), (15, cfg.imu_bias_cov_gyro), (18, cfg.imu_bias_cov_acc), (21, cfg.imu_bias_cov_acc),
+                    (24, cfg.state_std_rot_deg * d2r)):
+        Q[idx:idx + 3, idx:idx + 3] = np.eye(3) * sd ** 2 * dt * dt
+    F = np.eye(N)
+    F[0:3, 6:9] = np.eye(3) * dt
+    F[0:3, 18:21] = -0.5 * R0 * dt * dt
+    om = wg * dt
+    th = np.linalg.norm(om)
+    if th >= 1e-5:
+        K = skew(om / th)
+        F[3:6, 15:18] = -dt * (np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (th - np.sin(th)) / th ** 3 * K @ K)
+    F[6:9, 18:21] = -R0 * dt
+    F[9:12, 15:18] = -np.eye(3)
+    F[12:15, 18:21] = -R0
+    F[2, 23], F[8, 23], F[14, 23] = -0.5 * dt * dt, -dt, -1.0
+    return new, F @ P0 @ F.T + Q
+
+
+def apply_update(st, P, K, Y, H):
+    """UpdateEkfState (ekf_algorithm.hpp:116-145)"""
+    du = K @ Y
+    out = dict(st)
+    for name, lo in (("pos", 0), ("vel", 6), ("gyro", 9), ("acc", 12), ("bg", 15), ("ba", 18), ("grav", 21)):
+        out[name] = st[name] + du[lo:lo + 3]
+    out["R"] = st["R"] @ rodrigues(du[3:6])
+    out["Ri"] = st["Ri"] @ rodrigues(du[24:27])
+    return out, P - K @ H @ P
+
+
+@pytest.mark.parametrize("p_scale", [1.0, 1e-7])
+def test_oracle_complementary_filter_equals_a_numpy_restatement(p_scale):
+    """ComplementaryKalmanFilter (ekf_algorithm.cpp:597-701) inside RunPredictionImu: roll / pitch pseudo-measurement from the
+    bias-corrected accelerometer with the centripetal (v_x * yaw rate) and — once the rotation is stabilised (P small) — the
+    longitudinal (d v_x / dt, function-static memory) accelerations removed, noise scaled by the dynamics, 2-row update.
+    Two predictions: the first only latches the statics (dt = 0), the second applies the update."""
+    from elimaloc_b200 import _capi, ekf as pekf
+    rng = np.random.default_rng(4)
+    N = 27
+    cfg = pekf.make_ekf_config(use_complementary_filter=1)
+    f = O.EkfAlgorithm(cfg, _capi.EkfState)
+    A = rng.normal(size=(N, N))
+    P = (A @ A.T / N + np.eye(N) * 0.05) * p_scale
+    st = dict(R=synth.exp_so3([0.02, -0.03, 0.5]), Ri=np.eye(3), pos=np.array([1.0, 2.0, 0.3]), vel=np.array([7.0, 1.0, 0.05]),
+              gyro=np.zeros(3), acc=np.zeros(3), bg=np.array([1e-3, -2e-3, 5e-4]), ba=np.array([0.03, -0.01, 0.02]),
+              grav=np.array([0.0, 0.0, 9.80]))
+    for k in ("pos", "vel", "bg", "ba", "grav"):
+        getattr(f.s, k)[:] = list(st[k])
+    f.s.rot[:] = list(R_to_quat(st["R"]))
+    f.s.P[:] = list(P.reshape(-1))
+    f.s.state_initialized = 1
+    f.s.reset_for_init_prediction = 0
+    f.s.pcm_init_on_going = 0
+    t0, dt = 20.0, 0.01
+    f.s.prev_timestamp = t0
+    imu = [(np.array([0.01, -0.02, 0.25]), np.array([0.9, 1.9, 9.7])), (np.array([0.012, -0.018, 0.26]), np.array([1.1, 2.0, 9.75]))]
+    prev = None
+    for k, (gyro, acc) in enumerate(imu):
+        t = t0 + (k + 1) * dt
+        stabilised = all(np.sqrt(P[i, i]) < 0.2 * np.pi / 180 for i in (3, 4, 5))     # CheckRotationStabilized, before the step
+        assert f.RunPredictionImu(t, gyro, acc)
+        st, P = predict_numpy(st, P, gyro, acc, dt, cfg)
+        # ---- ComplementaryKalmanFilter
+        a_meas = acc - st["ba"]
+        v_local = st["R"].T @ st["vel"]
+        centrip = v_local[0] * st["gyro"][2]
+        if prev is None:
+            prev = (v_local[0], t)
+            continue                                                                   # first call: dt == 0 -> return
+        est_ax = (v_local[0] - prev[0]) / (t - prev[1])
+        prev = (v_local[0], t)
+        comp = a_meas - np.array([0.0, centrip, 0.0])
+        if stabilised:
+            comp = comp - np.array([est_ax, 0.0, 0.0])
+        gdir = comp / np.linalg.norm(comp)
+        z = np.array([np.arctan2(gdir[1], gdir[2]), -np.arcsin(gdir[0])])
+        innov = z - rot_to_vec(st["R"])[:2]
+        innov = (innov + np.pi) % (2 * np.pi) - np.pi
+        H = np.zeros((2, N))
+        H[0, 3] = H[1, 4] = 1.0
+        base = 1.0 * np.pi / 180
+        diff = abs(np.linalg.norm(a_meas) - np.linalg.norm(st["grav"])) / 9.81 * 10
+        lat, lon = 1 + diff + abs(centrip) / 9.81 * 10, 1 + diff + abs(est_ax) / 9.81 * 10
+        Rm = np.diag([max((base * lat) ** 2, base ** 2), max((base * lon) ** 2, base ** 2)])
+        K = P @ H.T @ np.linalg.inv(H @ P @ H.T + Rm)
+        st, P = apply_update(st, P, K, innov, H)
+    s = pekf.state_to_dict(f.s)
+    np.testing.assert_allclose(quat_to_R(s["rot"]), st["R"], rtol=0, atol=1e-11)
+    for name in ("pos", "vel", "gyro", "acc", "bg", "ba", "grav"):
+        np.testing.assert_allclose(s[name], st[name], rtol=1e-9, atol=1e-12, err_msg=name)
+    np.testing.assert_allclose(np.array(s["P"]).reshape(N, N), P, rtol=1e-9, atol=1e-16 * p_scale + 1e-20)
+    assert s["ckf_has_prev"] == 1 and s["predictions"] == 2
