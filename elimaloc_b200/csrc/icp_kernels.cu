@@ -879,6 +879,9 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     __shared__ unsigned int s_item_idx[COOP ? kItemCap : 1];
     __shared__ uint16_t s_items[COOP ? kItemCap : 1];
     __shared__ int s_nitems[kItemGroups];
+#if defined(ELM_GREEDY_ITEMS) && !defined(ELM_BLOCK_SCOPE)
+    __shared__ int s_cursor[kItemGroups];
+#endif
 
     pdl_launch_dependents();
     const int tid = threadIdx.x;
@@ -1035,6 +1038,90 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             ELM_TICK(5);
             // ---- phase B: one thread per (query, column) item
             const int nitems = min(s_nitems[grp], kGroupCap);  // (items beyond the cap were never written: their owners kept them)
+#if defined(ELM_GREEDY_ITEMS) && !defined(ELM_BLOCK_SCOPE)
+            // EXPERIMENTAL, NOT MEASURED YET (-DELM_GREEDY_ITEMS; see DESIGN.md "What comes next" and profiles/sim/item_balance.py):
+            // greedy list scheduling at batch granularity.  One item per lane and round costs the longest run of every round
+            // (44 % lane efficiency in the simulation); here every lane advances ITS item by one batch of loads per warp step and
+            // pulls the next item of the warp's list from a shared cursor as soon as it runs out (11.1 -> 7.7 warp steps per tile
+            // in the simulation).  Same arithmetic and the same merge as the loop below.
+            {
+                if (gtid == 0) s_cursor[grp] = 32;
+                __syncwarp();
+                constexpr uint32_t K = ELM_BATCH;
+                const float kInf = __int_as_float(0x7f800000);
+                int j = gtid < nitems ? gtid : -1;
+                uint32_t i = 0, rs = 0, end = 0, last_pair = 0, mi = 0;
+                float m = kInf, s2 = kInf, qfx = 0.f, qfy = 0.f, qfz = 0.f;
+                int q = 0;
+                auto begin_item = [&]() {   // -> false when the item is a hole or its run is empty (nothing to scan)
+                    const int it = g_items[j];
+                    if (it == kNoItem) return false;
+                    q = it >> 7;
+                    uint32_t rl;
+                    const unsigned long long dbits = g_item_d2[j];
+                    column_run(make_uint2(static_cast<uint32_t>(dbits), static_cast<uint32_t>(dbits >> 32)), static_cast<uint32_t>(it & 7), rs, rl);
+                    g_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
+                    g_item_idx[j] = 0xffffffffu;
+                    if (rl == 0) return false;
+                    visited += rl;
+                    end = rs + rl;
+                    i = rs & ~1u;
+                    last_pair = (end - 1) & ~1u;
+                    m = kInf; s2 = kInf; mi = rs;
+                    qfx = static_cast<float>(s_px[q]); qfy = static_cast<float>(s_py[q]); qfz = static_cast<float>(s_pz[q]);
+                    return true;
+                };
+                auto next_item = [&]() {    // pull items until one has something to scan, or the list is exhausted
+                    for (;;) {
+                        j = atomicAdd(&s_cursor[grp], 1);
+                        if (j >= nitems) { j = -1; return; }
+                        if (begin_item()) return;
+                    }
+                };
+                if (j >= 0 && !begin_item()) next_item();
+                while (__any_sync(kFull, j >= 0)) {
+                    if (j >= 0) {
+                        float4 q0[K], q1[K];
+#pragma unroll
+                        for (uint32_t u = 0; u < K; ++u) ldg256(map.pts + min(i + 2 * u, last_pair), q0[u], q1[u]);
+#pragma unroll
+                        for (uint32_t u = 0; u < K; ++u) {
+                            const uint32_t pi = i + 2 * u;
+                            {
+                                const float dx = q0[u].x - qfx, dy = q0[u].y - qfy, dz = q0[u].z - qfz;
+                                float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                                d = (pi >= rs && pi < end) ? d : kInf;
+                                s2 = fminf(s2, fmaxf(d, m)); mi = (d < m) ? pi : mi; m = fminf(m, d);
+                            }
+                            {
+                                const float dx = q1[u].x - qfx, dy = q1[u].y - qfy, dz = q1[u].z - qfz;
+                                float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                                d = (pi + 1 < end) ? d : kInf;
+                                s2 = fminf(s2, fmaxf(d, m)); mi = (d < m) ? pi + 1 : mi; m = fminf(m, d);
+                            }
+                        }
+                        i += 2 * K;
+                        if (i >= end) {     // run finished: decide exactly (same rule as visit_points), publish, pull the next item
+                            const Query Qj(s_px[q], s_py[q], s_pz[q]);
+                            const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Qj.band);
+                            const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
+                            Best ib;
+                            if (s2 > T) {
+                                const float4 c = __ldg(map.pts + mi);
+                                ib.d2 = sq3_exact(static_cast<double>(c.x) - Qj.px, static_cast<double>(c.y) - Qj.py, static_cast<double>(c.z) - Qj.pz);
+                                ib.idx = mi;
+                            } else {
+                                visit_points_exact(map.pts, rs, end - rs, Qj.px, Qj.py, Qj.pz, ib, ExactPoint());
+                            }
+                            g_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
+                            g_item_idx[j] = ib.idx;
+                            if (ib.idx != 0xffffffffu) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
+                            next_item();
+                        }
+                    }
+                }
+            }
+#else
             for (int j = gtid; j < nitems; j += kGroupThreads) {
                 const int it = g_items[j];
                 if (it == kNoItem) continue;
@@ -1049,6 +1136,7 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                 g_item_idx[j] = ib.idx;
                 if (ib.idx != 0xffffffffu) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
             }
+#endif
             if (mine) {
                 if (own_cols) {
 #pragma unroll 1
