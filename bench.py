@@ -17,8 +17,10 @@ ncclAllReduce + a separate solve launch (--comm nccl).  Default --scaling weak: 
 an N x 131 072-point scan, `value` = searches+accumulations/s / 131 072 (= ICP iterations/s of the metric's 128k-point
 scan; identical to plain iterations/s at N = 1); the strong-scaling figure of the fixed 131 072-point scan is measured in
 the same run and reported in config.strong_scaling.
---impl reference: times the oracle port of the reference's CPU path (the reference itself cannot be built here:
-no Eigen/TBB/PCL/ROS), search parallel over host threads + serial accumulate exactly like the reference.
+--impl reference: times the reference's CPU path on the host cores — the oracle port AND, when oracle/_ref/libref.so is built,
+the reference's own registration.cpp + voxel_hash_map.cpp (compiled unmodified against stand-in Eigen / oneTBB headers; the
+real third-party libraries are absent here) — search parallel over host threads + serial accumulate exactly like the
+reference; `value` is the faster of the two.
 """
 import argparse
 import json
@@ -193,7 +195,46 @@ def cpu_arm(args, raw, scan, T_init, method, steps, warmup, iters_per_sample):
         s, it = reg.time_register(scan, om, T_init, cfg_be)
         be_s += s
         be_it += it
-    return dict(value=tot_it / tot_s, seconds=tot_s, iterations=tot_it, threads=threads, build_s=build_s, best_effort=be_it / be_s)
+    out = dict(value=tot_it / tot_s, seconds=tot_s, iterations=tot_it, threads=threads, build_s=build_s, best_effort=be_it / be_s,
+               kind="port", port_value=tot_it / tot_s, reference_build_value=None)
+    # third line: the reference's OWN registration.cpp + voxel_hash_map.cpp (oracle/_ref/libref.so: compiled unmodified against
+    # stand-in Eigen / oneTBB headers), same workload, same thread count.  The faster of the two CPU
+    # figures becomes `value`, so the GPU/CPU ratio is never flattered by the choice.
+    del reg, om
+    try:
+        from oracle import reference_build as RB
+        if RB.available():
+            RB.set_threads(threads)
+            rm = RB.VoxelHashMap(1.0, 30)
+            t0 = time.time()
+            rm.AddPoints(raw)
+            if method in (2, 3):
+                rm.CalVoxelCovAll()
+            if method == 1:
+                rm.CalPointCovAll(0.4)
+            out["reference_build_map_s"] = time.time() - t0
+            rreg = RB.Registration()
+            for _ in range(warmup):
+                rreg.time_register(scan, rm, T_init, cfg)
+            r_s, r_it = 0.0, 0
+            for _ in range(steps):
+                s_, it_ = rreg.time_register(scan, rm, T_init, cfg)
+                r_s += s_
+                r_it += it_
+            out["reference_build_value"] = r_it / r_s
+            if out["reference_build_value"] > out["value"]:
+                out.update(value=r_it / r_s, seconds=r_s, iterations=r_it, kind="reference")
+    except Exception as e:  # the checker's extra arm must never take the bench down
+        out["reference_build_error"] = repr(e)
+    return out
+
+
+def cpu_baseline_dict(r, sample):
+    return {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": r["kind"], "sample": sample,
+            "port_value": r["port_value"], "reference_build_value": r["reference_build_value"],
+            "best_effort_all_parallel_value": r["best_effort"],
+            "note": "value = the faster of port_value (oracle port, OpenMP) and reference_build_value (the reference's own "
+                    "registration.cpp / voxel_hash_map.cpp compiled against stand-in Eigen + oneTBB headers, std::thread chunks)"}
 
 
 def main():
@@ -214,15 +255,15 @@ def main():
         from elimaloc_b200 import synth
         scan = synth.scan_u(args.n_scan, half)
         r = cpu_arm(args, raw, scan, T_init, method, max(1, args.steps), args.warmup, args.cpu_iters)
-        sample = (f"oracle port of the reference CPU path (reference not buildable here: no Eigen/TBB/PCL/ROS); "
+        sample = (f"reference CPU path, two builds timed (oracle port; and the reference's own sources against stand-in "
+                  f"Eigen/oneTBB headers when oracle/_ref is built); "
                   f"each step = RunRegister with {args.cpu_iters} forced iterations on the full workload, "
-                  f"{r['threads']} OpenMP threads for the search, serial accumulate as in the reference")
+                  f"{r['threads']} threads for the search, serial accumulate as in the reference")
         out = {"impl": "reference", "metric": "icp_iterations_per_sec", "value": r["value"], "unit": "iterations/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-               "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": "port",
-                                "sample": sample, "best_effort_all_parallel_value": r["best_effort"]},
+               "cpu_baseline": cpu_baseline_dict(r, sample),
                "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
         print(json.dumps(out))
@@ -434,11 +475,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_arm(args, raw, scans_full[0], T_init, method, 2, 1, args.cpu_iters)
-        cpu = {"value": r["value"], "unit": "iterations/s", "cores": r["threads"], "kind": "port",
-               "sample": f"2 RunRegister calls x {args.cpu_iters} forced iterations of the same workload "
-                         f"(oracle port; search on {r['threads']} OpenMP threads, accumulate serial as in the reference); "
-                         f"oracle map build {r['build_s']:.1f} s not timed",
-               "best_effort_all_parallel_value": r["best_effort"]}
+        cpu = cpu_baseline_dict(r, f"2 RunRegister calls x {args.cpu_iters} forced iterations of the same workload "
+                                   f"(search on {r['threads']} threads, accumulate serial as in the reference); "
+                                   f"oracle map build {r['build_s']:.1f} s not timed")
 
     if rank == 0:
         out = {"metric": "icp_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,

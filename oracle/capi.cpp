@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).  Parity status: UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).
+// Parity status: PINNED on oracle/_ref — the reference's own sources compiled against stand-in Eigen/oneTBB headers
+// (tests/test_reference_build.py); Eigen's arithmetic kernels themselves stay restated (smallmat.hpp).
 // Plain-C entry points so that tests/, smoke() and bench.py's cpu_baseline / --impl reference legs can
 // drive the CPU restatement through ctypes (oracle/oracle.py).  Never linked into the product.
 #include <algorithm>

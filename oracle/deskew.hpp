@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).  Parity status: UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).
+// Parity status: UNPINNED for this part (its reference sources need ROS / full Eigen and are not compiled here; anchored on
+// the cited lines and on the independent numpy restatement in tests/test_oracle_independent.py).
 // CPU restatement of the per-point deskew of pcm_matching (float32 arithmetic like the reference):
 //   /root/reference/src/app/localization/pcm_matching/src/pcm_matching.cpp
 //     DeskewPointCloud :467-531   ImuDeskewInfo :533-585   OdomDeskewInfo :587-729

@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).  Parity status: UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).
+// Parity status: UNPINNED for this part (its reference sources need ROS / full Eigen and are not compiled here; anchored on
+// the cited lines and on the independent numpy restatement in tests/test_oracle_independent.py).
 // CPU restatement of the 27-state EKF of ekf_localization (README says "24-DOF"; STATE_ORDER is 27):
 //   /root/reference/src/app/localization/ekf_localization/include/ekf_algorithm.hpp   (ekf_alg.hpp)
 //   /root/reference/src/app/localization/ekf_localization/src/ekf_algorithm.cpp       (ekf_alg.cpp)

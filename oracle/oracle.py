@@ -1,4 +1,5 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: UNPINNED (the reference ships no golden vectors).
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: registration + voxel map PINNED on oracle/_ref (the reference's own
+sources compiled against stand-in Eigen/oneTBB headers, oracle/reference_build.py); deskew and EKF unpinned.
 
 ctypes front-end of oracle/liboracle.so, the CPU restatement of the reference's
 pcm_matching hot path (registration.cpp / voxel_hash_map.{hpp,cpp}).  Only tests/,

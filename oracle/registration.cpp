@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).  Parity status: UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).
+// Parity status: PINNED on oracle/_ref — the reference's own sources compiled against stand-in Eigen/oneTBB headers
+// (tests/test_reference_build.py); Eigen's arithmetic kernels themselves stay restated (smallmat.hpp).
 // Restates /root/reference/src/app/localization/pcm_matching/src/registration.cpp; every function
 // cites the lines it follows.  The radar-covariance branch (use_radar_cov, reg.cpp:109-111,188-190,
 // 302-305; quirk Q14) is out of scope and not restated.

@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).  Parity status: UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).
+// Parity status: PINNED on oracle/_ref — the reference's own sources compiled against stand-in Eigen/oneTBB headers
+// (tests/test_reference_build.py); Eigen's arithmetic kernels themselves stay restated (smallmat.hpp).
 // Restates /root/reference/src/app/localization/pcm_matching/src/voxel_hash_map.cpp and the inline
 // bodies of .../include/voxel_hash_map.hpp; each function cites the lines it follows.
 #include "voxel_map.hpp"

@@ -121,6 +121,26 @@ def test_full_registration_config1(world, method):
 
 
 @pytest.mark.parametrize("method", METHODS)
+def test_reference_golden_config1(world, method):
+    """The CUDA path against tests/golden/config1_*.npz — outputs of the REFERENCE's own registration.cpp / voxel_hash_map.cpp
+    (oracle/_ref, generated in the build container by tests/golden/make_golden.py; same seeded inputs as this module's world):
+    correspondences of the first 256 scan points bit-equal, first-iteration pair count equal, pose 1e-4, JTJ 1e-5."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"config1_{NAMES[method].lower()}.npz"))
+    gcfg, _ = both_cfg(icp_method=method, max_iteration=10, **synth.timing_knobs())
+    T, ok, fit, cov = world["greg"].RunRegister(world["scan"], world["gm"], world["T0"], gcfg)
+    assert ok == bool(g["is_success"])
+    assert rel_err(T, g["pose"]) < 1e-4
+    assert abs(fit - float(g["fitness"])) <= 1e-6 * max(1.0, abs(float(g["fitness"])))
+    assert rel_err(cov, g["local_cov"]) < 1e-5
+    gc, gt = world["greg"].correspondences(world["scan"][:256], world["gm"], world["T0"], method, 5.0)
+    assert np.array_equal(gc, g["corr_count"]) and np.array_equal(gt, g["corr_target"])
+    lin = world["greg"].linearize(world["scan"], world["gm"], world["T0"], gcfg)
+    assert lin["n_corr"] == int(g["ncorr"][0])
+    assert rel_err(lin["JTJ"], g["JTJ"][0]) < 1e-5 and rel_err(lin["JTr"], g["JTr"][0]) < 1e-5
+
+
+@pytest.mark.parametrize("method", METHODS)
 def test_default_ini_config(world, method):
     """The reference's own knobs (localization.ini): early termination + overlap + fitness gates."""
     gcfg, ocfg = both_cfg(icp_method=method)

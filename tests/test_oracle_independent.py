@@ -1,6 +1,6 @@
 """An INDEPENDENT restatement of the three correspondence searches — numpy + a plain dict, none of the oracle's code — checked
-against the oracle (oracle/ is "parity unpinned": the reference ships no vectors and cannot be built here, so the C++
-restatement is cross-examined by a second, differently structured one).  Follows voxel_hash_map.cpp:31-243 directly:
+against the oracle (the reference ships no vectors; besides the pin on the reference's own sources, tests/test_reference_build.py,
+the C++ restatement is cross-examined by a second, differently structured one that shares none of its linear algebra).  Follows voxel_hash_map.cpp:31-243 directly:
 floor query key (voxel_hash_map.hpp:176-180), GetAdjacentVoxels order (x outer, y, z inner / c,+x,-x,+y,-y,+z,-z), strict <
 (first of equals wins), the default-constructed neighbour at the origin when nothing is found, the max-distance gate."""
 import numpy as np

@@ -1,8 +1,8 @@
 """Known-answer tests of the CPU oracle (runs without a GPU).
 
 The reference ships no tests; each case below pins a behaviour read off the cited reference lines (SURVEY.md section 4 /
-quirk checklist Q1..Q13), by hand-computed closed forms where possible, and the committed golden vectors pin the
-oracle itself against regressions."""
+quirk checklist Q1..Q13), by hand-computed closed forms where possible; the committed golden vectors are outputs of the
+reference's own sources (oracle/_ref, see tests/golden/make_golden.py and tests/test_reference_build.py)."""
 import os
 
 import numpy as np
@@ -191,7 +191,7 @@ def test_update_is_right_multiplied_and_lm_damps_the_diagonal():
 
 @pytest.mark.parametrize("name,method", [("p2p", O.P2P), ("gicp", O.GICP), ("vgicp", O.VGICP), ("avgicp", O.AVGICP)])
 def test_golden_config1(name, method):
-    """oracle vs the committed vectors of tests/golden/make_golden.py (regression pin; reference parity is unpinned)"""
+    """oracle vs the committed vectors of tests/golden/make_golden.py — outputs of the reference's own sources (oracle/_ref)"""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
     mg = importlib.util.module_from_spec(spec)
