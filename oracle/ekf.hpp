@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).
-// Parity status: UNPINNED for this part (its reference sources need ROS / full Eigen and are not compiled here; anchored on
-// the cited lines and on the independent numpy restatement in tests/test_oracle_independent.py).
+// Parity status: PINNED on oracle/_ref/libref_ekf.so — the reference's own ekf_algorithm.cpp (+ ekf_algorithm.hpp,
+// localization_functions.hpp, localization_struct.hpp) compiled unmodified against stand-in Eigen / ROS headers
+// (tests/test_reference_build_ekf.py compares every member after every call); Eigen's arithmetic kernels stay restated.
 // CPU restatement of the 27-state EKF of ekf_localization (README says "24-DOF"; STATE_ORDER is 27):
 //   /root/reference/src/app/localization/ekf_localization/include/ekf_algorithm.hpp   (ekf_alg.hpp)
 //   /root/reference/src/app/localization/ekf_localization/src/ekf_algorithm.cpp       (ekf_alg.cpp)

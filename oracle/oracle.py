@@ -1,5 +1,5 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: registration + voxel map PINNED on oracle/_ref (the reference's own
-sources compiled against stand-in Eigen/oneTBB headers, oracle/reference_build.py); deskew and EKF unpinned.
+sources compiled against stand-in Eigen/oneTBB/ROS headers, oracle/reference_build.py) and so is the EKF; deskew unpinned.
 
 ctypes front-end of oracle/liboracle.so, the CPU restatement of the reference's
 pcm_matching hot path (registration.cpp / voxel_hash_map.{hpp,cpp}).  Only tests/,

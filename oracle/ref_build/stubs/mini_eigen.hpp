@@ -16,6 +16,8 @@
 #pragma once
 #include <cmath>
 #include <cstddef>
+#include <limits>
+#include <ostream>
 #include <type_traits>
 #include <vector>
 
@@ -30,6 +32,8 @@ template <typename T, int R, int C> class Matrix;
 template <typename T, int N> struct DiagonalWrapper { Matrix<T, N, 1> d; };
 template <typename T, int BR, int BC, int R, int C> class BlockRef;
 template <typename T, int N> class LDLT;
+template <typename T> class Quaternion;
+struct ScaledIdentityXd { int n; double s; };  // MatrixXd::Identity(n, n) * s  (ekf_algorithm.cpp:41)
 
 // Records every ldlt().solve(A, b) when enabled: lets the test driver read the normal equations (JTJ + lambda diag, JTr)
 // that the reference's AlignClouds* functions keep in locals.
@@ -70,6 +74,13 @@ public:
         for (int i = 0; i < R; ++i) (*this)(i, i) = w.d(i);
     }
 
+    Matrix(const Quaternion<T>& q);  // 3x3 only: rotation matrix of a quaternion (Eigen: RotationBase assignment)
+    Matrix(const ScaledIdentityXd& w) {
+        static_assert(R == C, "square");
+        for (int i = 0; i < Size; ++i) m_[i] = T(0);
+        for (int i = 0; i < R; ++i) (*this)(i, i) = static_cast<T>(w.s);
+    }
+
     static Matrix Zero() { return Matrix(); }
     static Matrix Identity() { Matrix r; for (int i = 0; i < (R < C ? R : C); ++i) r(i, i) = T(1); return r; }
     static Matrix UnitX() { Matrix r; r.m_[0] = T(1); return r; }
@@ -94,6 +105,12 @@ public:
     const T* data() const { return m_; }
 
     void setZero() { for (int i = 0; i < Size; ++i) m_[i] = T(0); }
+    void setIdentity() { *this = Identity(); }
+    T trace() const { T s = (*this)(0, 0); for (int i = 1; i < (R < C ? R : C); ++i) s = s + (*this)(i, i); return s; }
+    Matrix cross(const Matrix& o) const {
+        static_assert(Size == 3, "3-vector");
+        return Matrix(m_[1] * o.m_[2] - m_[2] * o.m_[1], m_[2] * o.m_[0] - m_[0] * o.m_[2], m_[0] * o.m_[1] - m_[1] * o.m_[0]);
+    }
     Matrix& noalias() { return *this; }
     const Matrix& matrix() const { return *this; }
 
@@ -129,6 +146,10 @@ public:
 
     template <int N> Matrix<T, N, 1> head() const { static_assert(C == 1, "column vector"); Matrix<T, N, 1> r; for (int i = 0; i < N; ++i) r(i) = m_[i]; return r; }
     template <int N> Matrix<T, N, 1> tail() const { static_assert(C == 1, "column vector"); Matrix<T, N, 1> r; for (int i = 0; i < N; ++i) r(i) = m_[R - N + i]; return r; }
+    template <int N> Matrix<T, N, 1> segment(int i) const { static_assert(C == 1, "column vector"); Matrix<T, N, 1> r; for (int k = 0; k < N; ++k) r(k) = m_[i + k]; return r; }
+    template <int N> BlockRef<T, N, 1, R, C> head() { static_assert(C == 1, "column vector"); return BlockRef<T, N, 1, R, C>(*this, 0, 0); }
+    template <int N> BlockRef<T, N, 1, R, C> tail() { static_assert(C == 1, "column vector"); return BlockRef<T, N, 1, R, C>(*this, R - N, 0); }
+    template <int N> BlockRef<T, N, 1, R, C> segment(int i) { static_assert(C == 1, "column vector"); return BlockRef<T, N, 1, R, C>(*this, i, 0); }
     Matrix<T, R, 1> col(int j) const { Matrix<T, R, 1> r; for (int i = 0; i < R; ++i) r(i) = (*this)(i, j); return r; }
 
     template <int BR, int BC> BlockRef<T, BR, BC, R, C> block(int i, int j) { return BlockRef<T, BR, BC, R, C>(*this, i, j); }
@@ -178,6 +199,12 @@ Matrix<T, R, N> operator*(const Matrix<T, R, N>& a, const DiagonalWrapper<T, N>&
     return r;
 }
 
+template <typename T, int R, int C>
+std::ostream& operator<<(std::ostream& os, const Matrix<T, R, C>& m) {  // debug prints only
+    for (int i = 0; i < R; ++i) { for (int j = 0; j < C; ++j) os << (j ? " " : "") << m(i, j); if (i + 1 < R) os << "\n"; }
+    return os;
+}
+
 // Writable view of a fixed block of a fixed matrix; reads convert to a Matrix value.
 template <typename T, int BR, int BC, int R, int C>
 class BlockRef {
@@ -204,6 +231,16 @@ public:
     T norm() const { return eval().norm(); }
     T squaredNorm() const { return eval().squaredNorm(); }
     Matrix<T, BC, BR> transpose() const { return eval().transpose(); }
+    BlockRef& operator=(const BlockRef& o) { return *this = o.eval(); }
+    template <int R2, int C2> BlockRef& operator=(const BlockRef<T, BR, BC, R2, C2>& o) { return *this = o.eval(); }
+    BlockRef& operator+=(const Matrix<T, BR, BC>& v) { return *this = eval() + v; }
+    BlockRef& operator-=(const Matrix<T, BR, BC>& v) { return *this = eval() - v; }
+    friend Matrix<T, BR, BC> operator+(const BlockRef& a, const Matrix<T, BR, BC>& b) { return a.eval() + b; }
+    friend Matrix<T, BR, BC> operator+(const Matrix<T, BR, BC>& a, const BlockRef& b) { return a + b.eval(); }
+    friend Matrix<T, BR, BC> operator-(const BlockRef& a, const Matrix<T, BR, BC>& b) { return a.eval() - b; }
+    friend Matrix<T, BR, BC> operator-(const Matrix<T, BR, BC>& a, const BlockRef& b) { return a - b.eval(); }
+    template <int R2, int C2> Matrix<T, BR, BC> operator+(const BlockRef<T, BR, BC, R2, C2>& b) const { return eval() + b.eval(); }
+    template <int R2, int C2> Matrix<T, BR, BC> operator-(const BlockRef<T, BR, BC, R2, C2>& b) const { return eval() - b.eval(); }
 private:
     Matrix<T, R, C>& m_;
     int i_, j_;
@@ -269,8 +306,17 @@ inline orc::V3 to_orc(const Matrix<double, 3, 1>& v) { return orc::V3(v(0), v(1)
 
 template <typename T, int R, int C>
 Matrix<T, R, C> Matrix<T, R, C>::inverse() const {
-    static_assert(std::is_same<T, double>::value && R == C && (R == 3 || R == 4 || R == 6), "inverse(): double 3x3 / 4x4 / 6x6 only");
-    return stub::from_orc(orc::inverse(stub::to_orc(*this)));
+    static_assert(std::is_same<T, double>::value && R == C, "inverse(): square double matrices only");
+    if constexpr (R == 3) {
+        return stub::from_orc(orc::inverse(stub::to_orc(*this)));  // cofactor formula
+    } else {  // Gauss-Jordan with partial pivoting (oracle/smallmat.hpp inverse_n)
+        double a[R * R], out[R * R];
+        for (int i = 0; i < R; ++i) for (int j = 0; j < R; ++j) a[i * R + j] = (*this)(i, j);
+        orc::inverse_n<R>(a, out);
+        Matrix r;
+        for (int i = 0; i < R; ++i) for (int j = 0; j < R; ++j) r(i, j) = out[i * R + j];
+        return r;
+    }
 }
 
 template <typename T, int N>
@@ -357,13 +403,112 @@ public:
     T angle() const { return angle_; }
     const Matrix<T, 3, 1>& axis() const { return axis_; }
     Matrix<T, 3, 3> toRotationMatrix() const { return stub::from_orc(orc::angle_axis_to_rot(angle_, stub::to_orc(axis_))); }
-    // Eigen returns a quaternion here; only CalPointCov (use_radar_cov, out of scope) uses it, assigned to a Matrix3d.
-    friend Matrix<T, 3, 3> operator*(const AngleAxis& a, const AngleAxis& b) { return a.toRotationMatrix() * b.toRotationMatrix(); }
+    // AngleAxis * AngleAxis is a quaternion product in Eigen (defined after Quaternion below)
+    friend Quaternion<T> operator*(const AngleAxis& a, const AngleAxis& b) { return Quaternion<T>(a) * Quaternion<T>(b); }
 private:
     T angle_;
     Matrix<T, 3, 1> axis_;
 };
 
+// Eigen::Quaternion restated from its published formulas (coefficient order w, x, y, z in the constructor).
+template <typename T>
+class Quaternion {
+public:
+    Quaternion() : w_(1), x_(0), y_(0), z_(0) {}
+    Quaternion(T w, T x, T y, T z) : w_(w), x_(x), y_(y), z_(z) {}
+    Quaternion(const AngleAxis<T>& aa) {  // w = cos(a/2), vec = sin(a/2) * axis
+        const T h = T(0.5) * aa.angle(), sn = std::sin(h);
+        w_ = std::cos(h); x_ = sn * aa.axis()(0); y_ = sn * aa.axis()(1); z_ = sn * aa.axis()(2);
+    }
+    explicit Quaternion(const Matrix<T, 3, 3>& m) {  // Shepperd's method, as Eigen's quaternionbase_assign_impl
+        T t = m(0, 0) + m(1, 1) + m(2, 2);
+        if (t > T(0)) {
+            t = std::sqrt(t + T(1));
+            w_ = T(0.5) * t; t = T(0.5) / t;
+            x_ = (m(2, 1) - m(1, 2)) * t; y_ = (m(0, 2) - m(2, 0)) * t; z_ = (m(1, 0) - m(0, 1)) * t;
+        } else {
+            int i = 0;
+            if (m(1, 1) > m(0, 0)) i = 1;
+            if (m(2, 2) > m(i, i)) i = 2;
+            const int j = (i + 1) % 3, k = (j + 1) % 3;
+            t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + T(1));
+            T v[3];
+            v[i] = T(0.5) * t; t = T(0.5) / t;
+            w_ = (m(k, j) - m(j, k)) * t;
+            v[j] = (m(j, i) + m(i, j)) * t;
+            v[k] = (m(k, i) + m(i, k)) * t;
+            x_ = v[0]; y_ = v[1]; z_ = v[2];
+        }
+    }
+    static Quaternion Identity() { return Quaternion(T(1), T(0), T(0), T(0)); }
+    T& w() { return w_; } T& x() { return x_; } T& y() { return y_; } T& z() { return z_; }
+    const T& w() const { return w_; } const T& x() const { return x_; } const T& y() const { return y_; } const T& z() const { return z_; }
+    Matrix<T, 3, 1> vec() const { return Matrix<T, 3, 1>(x_, y_, z_); }
+    T squaredNorm() const { return w_ * w_ + x_ * x_ + y_ * y_ + z_ * z_; }
+    T norm() const { return std::sqrt(squaredNorm()); }
+    Quaternion normalized() const { const T n = norm(); return Quaternion(w_ / n, x_ / n, y_ / n, z_ / n); }
+    void normalize() { *this = normalized(); }
+    Quaternion conjugate() const { return Quaternion(w_, -x_, -y_, -z_); }
+    Quaternion inverse() const { const T n2 = squaredNorm(); return Quaternion(w_ / n2, -x_ / n2, -y_ / n2, -z_ / n2); }
+    Quaternion operator*(const Quaternion& b) const {
+        const Quaternion& a = *this;
+        return Quaternion(a.w_ * b.w_ - a.x_ * b.x_ - a.y_ * b.y_ - a.z_ * b.z_, a.w_ * b.x_ + a.x_ * b.w_ + a.y_ * b.z_ - a.z_ * b.y_,
+                          a.w_ * b.y_ + a.y_ * b.w_ + a.z_ * b.x_ - a.x_ * b.z_, a.w_ * b.z_ + a.z_ * b.w_ + a.x_ * b.y_ - a.y_ * b.x_);
+    }
+    Quaternion operator*(const AngleAxis<T>& b) const { return *this * Quaternion(b); }
+    Matrix<T, 3, 1> operator*(const Matrix<T, 3, 1>& v) const {  // _transformVector: v + w * uv + vec x uv, uv = 2 vec x v
+        const Matrix<T, 3, 1> u = vec();
+        Matrix<T, 3, 1> uv = u.cross(v);
+        uv += uv;
+        return v + w_ * uv + u.cross(uv);
+    }
+    Matrix<T, 3, 3> toRotationMatrix() const {
+        const T tx = T(2) * x_, ty = T(2) * y_, tz = T(2) * z_;
+        const T twx = tx * w_, twy = ty * w_, twz = tz * w_, txx = tx * x_, txy = ty * x_, txz = tz * x_, tyy = ty * y_, tyz = tz * y_, tzz = tz * z_;
+        Matrix<T, 3, 3> r;
+        r(0, 0) = T(1) - (tyy + tzz); r(0, 1) = txy - twz; r(0, 2) = txz + twy;
+        r(1, 0) = txy + twz; r(1, 1) = T(1) - (txx + tzz); r(1, 2) = tyz - twx;
+        r(2, 0) = txz - twy; r(2, 1) = tyz + twx; r(2, 2) = T(1) - (txx + tyy);
+        return r;
+    }
+    Quaternion slerp(T t, const Quaternion& o) const {  // Eigen's slerp
+        const T one = T(1) - std::numeric_limits<T>::epsilon();
+        const T d = w_ * o.w_ + x_ * o.x_ + y_ * o.y_ + z_ * o.z_, ad = std::fabs(d);
+        T s0, s1;
+        if (ad >= one) { s0 = T(1) - t; s1 = t; }
+        else { const T th = std::acos(ad), st = std::sin(th); s0 = std::sin((T(1) - t) * th) / st; s1 = std::sin(t * th) / st; }
+        if (d < T(0)) s1 = -s1;
+        return Quaternion(s0 * w_ + s1 * o.w_, s0 * x_ + s1 * o.x_, s0 * y_ + s1 * o.y_, s0 * z_ + s1 * o.z_);
+    }
+private:
+    T w_, x_, y_, z_;
+};
+template <typename T, int R, int C>
+Matrix<T, R, C>::Matrix(const Quaternion<T>& q) { static_assert(R == 3 && C == 3, "rotation matrix"); *this = q.toRotationMatrix(); }
+
+struct MatrixXd { static ScaledIdentityXd Identity(int rows, int cols) { (void)cols; return ScaledIdentityXd{rows, 1.0}; } };
+inline ScaledIdentityXd operator*(const ScaledIdentityXd& a, double s) { return ScaledIdentityXd{a.n, a.s * s}; }
+
+// Just enough of Transform<float, 3, Affine> for InterpolateTfWithTime (localization_functions.hpp:219-242) to compile;
+// nothing on the compiled paths calls it.
+template <typename T>
+class AffineStub {
+public:
+    static AffineStub Identity() { return AffineStub(); }
+    Matrix<T, 3, 1> translation() const { return t_; }
+    Matrix<T, 3, 3> rotation() const { return r_; }
+    AffineStub& translate(const Matrix<T, 3, 1>& v) { t_ += r_ * v; return *this; }
+    AffineStub& rotate(const Quaternion<T>& q) { r_ = r_ * q.toRotationMatrix(); return *this; }
+private:
+    Matrix<T, 3, 3> r_ = Matrix<T, 3, 3>::Identity();
+    Matrix<T, 3, 1> t_;
+};
+
+using Matrix2d = Matrix<double, 2, 2>;
+using Matrix3f = Matrix<float, 3, 3>;
+using Quaterniond = Quaternion<double>;
+using Quaternionf = Quaternion<float>;
+using Affine3f = AffineStub<float>;
 using Matrix3d = Matrix<double, 3, 3>;
 using Matrix4d = Matrix<double, 4, 4>;
 using Vector2d = Matrix<double, 2, 1>;

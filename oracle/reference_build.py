@@ -2,8 +2,10 @@
 
 ctypes front-end of oracle/_ref/libref.so: the REFERENCE's own registration.cpp + voxel_hash_map.{hpp,cpp}, compiled
 unmodified from /root/reference against the stand-in third-party headers in oracle/ref_build/stubs (Eigen3, oneTBB and PCL are
-absent from this image; see stubs/mini_eigen.hpp for what the stand-in does and does not preserve).  It is the pin of the
-oracle: tests/test_reference_build.py runs the oracle and this library on the same seeded inputs.
+absent from this image; see stubs/mini_eigen.hpp for what the stand-in does and does not preserve), and of
+oracle/_ref/libref_ekf.so: the reference's own ekf_algorithm.cpp built the same way (plus ref_build/ros_stubs).  They are the
+pin of the oracle: tests/test_reference_build.py and tests/test_reference_build_ekf.py run the oracle and these libraries on
+the same seeded inputs.
 
 /root/reference exists only in the build container; `build()` compiles there, the GPU box uses the prebuilt file (git-ignored,
 not gpurun-ignored).  Same call surface as oracle/oracle.py so one test body drives both.
@@ -20,6 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libref.so")
 REFERENCE_ROOT = os.environ.get("ELM_REFERENCE_ROOT", "/root/reference")
 _PCM = os.path.join(REFERENCE_ROOT, "src", "app", "localization", "pcm_matching")
+_SO_EKF = os.path.join(_HERE, "_ref", "libref_ekf.so")
 _LIB = None
 
 
@@ -31,10 +34,15 @@ def available():
     return os.path.isfile(_SO) or sources_present()
 
 
+def ekf_available():
+    return os.path.isfile(_SO_EKF) or sources_present()
+
+
 def build(force=False):
     """Compile the reference's two translation units where they lie (never copied) + ref_build/ref_capi.cpp."""
     if sources_present():  # make decides whether anything is stale
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref_ekf.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
     if not os.path.isfile(_SO):
         raise FileNotFoundError("oracle/_ref/libref.so is not built and the reference sources are not here")
     return _SO
@@ -196,3 +204,68 @@ def voxel_downsample(xyz, voxel_size):
     idx = np.zeros(max(xyz.shape[0], 1), np.int32)
     n = lib().ref_voxel_downsample(_f(xyz), xyz.shape[0], float(voxel_size), _i(idx))
     return idx[:n]
+
+
+# ---------------------------------------------------------------------------------------------------------------- EKF
+def ekf_lib(fresh_statics=False):
+    """oracle/_ref/libref_ekf.so.  ComplementaryKalmanFilter keeps its previous sample in function-static variables
+    (ekf_algorithm.cpp:613-614), shared by every filter of the process: fresh_statics loads a private copy of the library."""
+    import shutil
+    import tempfile
+    build()
+    if not os.path.isfile(_SO_EKF):
+        raise FileNotFoundError("oracle/_ref/libref_ekf.so is not built and the reference sources are not here")
+    path = _SO_EKF
+    if fresh_statics:
+        fd, path = tempfile.mkstemp(suffix=".so", prefix="libref_ekf_")
+        os.close(fd)
+        shutil.copyfile(_SO_EKF, path)
+    L = C.CDLL(path)
+    if fresh_statics:
+        os.unlink(path)  # stays mapped
+    dp = C.POINTER(C.c_double)
+    L.ref_ekf_create.restype = C.c_void_p
+    L.ref_ekf_create.argtypes = [C.c_void_p]
+    L.ref_ekf_destroy.argtypes = [C.c_void_p]
+    L.ref_ekf_predict_imu.argtypes = [C.c_void_p, C.c_double, dp, dp]
+    L.ref_ekf_update_pose.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_ekf_get_current_state.argtypes = [C.c_void_p, dp]
+    L.ref_ekf_dump.argtypes = [C.c_void_p, C.c_void_p]
+    return L
+
+
+class EkfAlgorithm:
+    """The reference's EkfAlgorithm (ekf_algorithm.hpp:79-290), itself; same call surface as oracle.EkfAlgorithm.
+    `s` is refreshed from the filter's members after every call (the ComplementaryKalmanFilter statics are not reachable)."""
+
+    def __init__(self, cfg, state_type, fresh_statics=True):
+        self._L = ekf_lib(fresh_statics)
+        self.cfg = cfg
+        self.s = state_type()
+        self._h = self._L.ref_ekf_create(C.byref(cfg))
+        self._sync()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ref_ekf_destroy(self._h)
+            self._h = None
+
+    def _sync(self):
+        self._L.ref_ekf_dump(self._h, C.byref(self.s))
+
+    def RunPredictionImu(self, t, gyro, acc):
+        g = np.ascontiguousarray(gyro, dtype=np.float64)
+        a = np.ascontiguousarray(acc, dtype=np.float64)
+        r = bool(self._L.ref_ekf_predict_imu(self._h, float(t), _d(g), _d(a)))
+        self._sync()
+        return r
+
+    def RunGnssUpdate(self, meas):
+        r = bool(self._L.ref_ekf_update_pose(self._h, C.byref(meas)))
+        self._sync()
+        return r
+
+    def GetCurrentState(self):
+        ego = np.zeros(26)
+        self._L.ref_ekf_get_current_state(self._h, _d(ego))
+        return ego
