@@ -289,3 +289,54 @@ def test_threads_of_the_tbb_stand_in_do_not_change_results(world):
     e1, e4 = r1.export(), r4.export()
     assert all(np.array_equal(e1[k], e4[k]) for k in e1)
     assert np.array_equal(a["pose"], b["pose"]) and a["n_iter"] == b["n_iter"]
+
+
+@pytest.mark.parametrize("voxel_size,cap,n,box,radius", [(1.0, 30, 60_000, 18.0, 0.4), (0.5, 12, 30_000, 8.0, 0.3), (2.0, 5, 40_000, 16.0, 0.8)])
+def test_product_host_map_builder_against_the_reference_sources(voxel_size, cap, n, box, radius):
+    """the PRODUCT's map builder (elimaloc_b200/csrc/host_map.cpp: slab-parallel counting sort, no hash map; device = -1 keeps it
+    on the host, no GPU needed) directly against the reference's AddPoints / CalVoxelCovAll / CalPointCovAll: same voxels, same
+    stored points in the same per-voxel order, covariances to 1e-9 — without the oracle in between"""
+    import elimaloc_b200 as E
+    raw = synth.map_u(n, box, seed=21, origin=-0.4 * box)
+    pm, rm = E.VoxelHashMap(voxel_size, cap, device=-1), R.VoxelHashMap(voxel_size, cap)
+    for m in (pm, rm):
+        m.AddPoints(raw[: n // 3])
+        m.AddPoints(raw[n // 3:])
+        m.CalVoxelCovAll()
+        m.CalPointCovAll(radius)
+    pe, re_ = pm.export(True, True), rm.export()
+    for k in ("keys", "counts", "pxyz"):
+        assert np.array_equal(pe[k], re_[k]), k
+    for k in ("vmean", "vcov", "pmean", "pcov"):
+        assert np.abs(pe[k] - re_[k]).max() < 1e-9, k
+    rng = np.random.default_rng(2)
+    for q in rng.uniform(-0.5 * box, 0.7 * box, (20, 2)):
+        pf, pz = pm.FindGroundHeight(q)
+        rf, rz = rm.FindGroundHeight(q)
+        assert pf == rf and (not rf or abs(pz - rz) < 1e-12)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_worlds(seed):
+    """small random worlds: random voxel size, cap, covariance radius, map extent (straddling the origin or far from it), pose and
+    max_dist; all four methods; oracle and reference sources must agree on everything"""
+    rng = np.random.default_rng(1000 + seed)
+    vs = float(rng.choice([0.4, 0.75, 1.0, 1.6]))
+    cap = int(rng.choice([3, 10, 30]))
+    box = float(rng.uniform(6, 14)) * vs
+    origin = float(rng.choice([-0.5 * box, -3.0, 120.0, -250.0]))
+    raw = synth.map_u(int(rng.integers(5_000, 25_000)), box, seed=seed, origin=origin)
+    om, rm = build_both(raw, vs, cap, radius=0.4 * vs)
+    assert_same_map(om, rm)
+    c = origin + 0.5 * box
+    T_true = synth.se3([c + rng.uniform(-1, 1), c + rng.uniform(-1, 1), c + rng.uniform(-0.5, 0.5)], rng.normal(0, 0.2, 3))
+    scan = synth.scan_m(om.export()["pxyz"], 600, T_true, noise=0.03 * vs, seed=seed)
+    T0 = T_true @ synth.se3(rng.normal(0, 0.15 * vs, 3), rng.normal(0, 0.01, 3))
+    md = float(rng.choice([0.8, 2.0, 5.0])) * vs
+    for method in METHODS:
+        co, to = O.correspondences(om, scan, T0, method, md)
+        cr, tr = R.correspondences(rm, scan, T0, method, md)
+        assert np.array_equal(co, cr) and np.array_equal(to, tr)
+        cfg = O.make_config(icp_method=method, max_search_dist=md, max_iteration=int(rng.integers(1, 12)), lm_lambda=float(rng.choice([0.0, 0.1, 0.5])))
+        compare_runs(O.Registration().RunRegister(scan, om, T0, cfg, fitness_in=-3.0), R.Registration().RunRegister(scan, rm, T0, cfg, fitness_in=-3.0),
+                     lm_lambda=cfg.lm_lambda, pose_tol=1e-9)
