@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see smallmat.hpp header).
-// Parity status: UNPINNED for this part (its reference sources need ROS / full Eigen and are not compiled here; anchored on
-// the cited lines and on the independent numpy restatement in tests/test_oracle_independent.py).
+// Parity status: PINNED on oracle/_ref/libref_node.so — the reference's own ROS node class (pcm_matching.cpp) compiled
+// unmodified against stand-in ROS / tf / PCL / Eigen headers (tests/test_reference_build_node.py: tables 1e-15, the per-point
+// transform bit-equal); pcl::getTransformation and tf's RPY conversions stay restated from their published definitions.
 // CPU restatement of the per-point deskew of pcm_matching (float32 arithmetic like the reference):
 //   /root/reference/src/app/localization/pcm_matching/src/pcm_matching.cpp
 //     DeskewPointCloud :467-531   ImuDeskewInfo :533-585   OdomDeskewInfo :587-729

@@ -1,5 +1,6 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: registration + voxel map PINNED on oracle/_ref (the reference's own
-sources compiled against stand-in Eigen/oneTBB/ROS headers, oracle/reference_build.py) and so is the EKF; deskew unpinned.
+sources compiled against stand-in Eigen/oneTBB/ROS/PCL headers, oracle/reference_build.py), and so are the EKF and the
+node-side stages (deskew, distance filter, pose interpolation, covariance shaping).
 
 ctypes front-end of oracle/liboracle.so, the CPU restatement of the reference's
 pcm_matching hot path (registration.cpp / voxel_hash_map.{hpp,cpp}).  Only tests/,

@@ -106,6 +106,18 @@ public:
 
     void setZero() { for (int i = 0; i < Size; ++i) m_[i] = T(0); }
     void setIdentity() { *this = Identity(); }
+    T determinant() const {
+        static_assert(R == 3 && C == 3, "3x3");
+        const Matrix& a = *this;
+        return a(0, 0) * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) - a(0, 1) * (a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0)) + a(0, 2) * (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0));
+    }
+    T minCoeff() const { T v = m_[0]; for (int i = 1; i < Size; ++i) if (m_[i] < v) v = m_[i]; return v; }
+    Matrix cwiseMin(T s) const { Matrix r; for (int i = 0; i < Size; ++i) r.m_[i] = m_[i] < s ? m_[i] : s; return r; }
+    Matrix cwiseMax(T s) const { Matrix r; for (int i = 0; i < Size; ++i) r.m_[i] = m_[i] > s ? m_[i] : s; return r; }
+    template <typename F> Matrix unaryExpr(F f) const { Matrix r; for (int i = 0; i < Size; ++i) r.m_[i] = f(m_[i]); return r; }
+    template <typename S, typename = std::enable_if_t<std::is_arithmetic<S>::value>> Matrix& operator*=(S s) { for (int i = 0; i < Size; ++i) m_[i] = m_[i] * static_cast<T>(s); return *this; }
+    template <typename S, typename = std::enable_if_t<std::is_arithmetic<S>::value>> Matrix& operator/=(S s) { for (int i = 0; i < Size; ++i) m_[i] = m_[i] / static_cast<T>(s); return *this; }
+    BlockRef<T, R, 1, R, C> col(int j) { return BlockRef<T, R, 1, R, C>(*this, 0, j); }
     T trace() const { T s = (*this)(0, 0); for (int i = 1; i < (R < C ? R : C); ++i) s = s + (*this)(i, i); return s; }
     Matrix cross(const Matrix& o) const {
         static_assert(Size == 3, "3-vector");
@@ -209,7 +221,13 @@ std::ostream& operator<<(std::ostream& os, const Matrix<T, R, C>& m) {  // debug
 template <typename T, int BR, int BC, int R, int C>
 class BlockRef {
 public:
+    using Scalar = T;
+    static constexpr int Rows = BR, Cols = BC;
     BlockRef(Matrix<T, R, C>& m, int i, int j) : m_(m), i_(i), j_(j) {}
+    T& operator()(int a, int b) { return m_(i_ + a, j_ + b); }
+    CommaInit<BlockRef> operator<<(T v) { return CommaInit<BlockRef>(*this, v); }
+    template <int N> Matrix<T, N, 1> head() const { static_assert(BC == 1, "column vector"); Matrix<T, N, 1> r; for (int k = 0; k < N; ++k) r(k) = m_(i_ + k, j_); return r; }
+    Matrix<T, BR, BC> operator-() const { return -eval(); }
     // same shape, or — as Eigen allows for vectors — a column vector into a row-vector block (reg.cpp:252 assigns a
     // Vector3d to a 1x3 block)
     template <int VR, int VC>
@@ -235,6 +253,8 @@ public:
     template <int R2, int C2> BlockRef& operator=(const BlockRef<T, BR, BC, R2, C2>& o) { return *this = o.eval(); }
     BlockRef& operator+=(const Matrix<T, BR, BC>& v) { return *this = eval() + v; }
     BlockRef& operator-=(const Matrix<T, BR, BC>& v) { return *this = eval() - v; }
+    template <int K> friend Matrix<T, K, BC> operator*(const Matrix<T, K, BR>& a, const BlockRef& b) { return a * b.eval(); }
+    template <int K> friend Matrix<T, BR, K> operator*(const BlockRef& a, const Matrix<T, BC, K>& b) { return a.eval() * b; }
     friend Matrix<T, BR, BC> operator+(const BlockRef& a, const Matrix<T, BR, BC>& b) { return a.eval() + b; }
     friend Matrix<T, BR, BC> operator+(const Matrix<T, BR, BC>& a, const BlockRef& b) { return a + b.eval(); }
     friend Matrix<T, BR, BC> operator-(const BlockRef& a, const Matrix<T, BR, BC>& b) { return a.eval() - b; }
@@ -306,10 +326,19 @@ inline orc::V3 to_orc(const Matrix<double, 3, 1>& v) { return orc::V3(v(0), v(1)
 
 template <typename T, int R, int C>
 Matrix<T, R, C> Matrix<T, R, C>::inverse() const {
-    static_assert(std::is_same<T, double>::value && R == C, "inverse(): square double matrices only");
-    if constexpr (R == 3) {
+    static_assert(R == C, "inverse(): square matrices only");
+    if constexpr (R == 3 && std::is_same<T, double>::value) {
         return stub::from_orc(orc::inverse(stub::to_orc(*this)));  // cofactor formula
-    } else {  // Gauss-Jordan with partial pivoting (oracle/smallmat.hpp inverse_n)
+    } else if constexpr (R == 3) {  // float: the same cofactor formula
+        const Matrix& a = *this;
+        Matrix c;
+        c(0, 0) = a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1); c(0, 1) = a(0, 2) * a(2, 1) - a(0, 1) * a(2, 2); c(0, 2) = a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1);
+        c(1, 0) = a(1, 2) * a(2, 0) - a(1, 0) * a(2, 2); c(1, 1) = a(0, 0) * a(2, 2) - a(0, 2) * a(2, 0); c(1, 2) = a(0, 2) * a(1, 0) - a(0, 0) * a(1, 2);
+        c(2, 0) = a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0); c(2, 1) = a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1); c(2, 2) = a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0);
+        const T det = (a(0, 0) * c(0, 0) + a(0, 1) * c(1, 0)) + a(0, 2) * c(2, 0);
+        return c * (T(1) / det);
+    } else {
+        static_assert(std::is_same<T, double>::value, "N x N inverse: double only");  // Gauss-Jordan with partial pivoting (oracle/smallmat.hpp inverse_n)
         double a[R * R], out[R * R];
         for (int i = 0; i < R; ++i) for (int j = 0; j < R; ++j) a[i * R + j] = (*this)(i, j);
         orc::inverse_n<R>(a, out);
@@ -489,19 +518,44 @@ Matrix<T, R, C>::Matrix(const Quaternion<T>& q) { static_assert(R == 3 && C == 3
 struct MatrixXd { static ScaledIdentityXd Identity(int rows, int cols) { (void)cols; return ScaledIdentityXd{rows, 1.0}; } };
 inline ScaledIdentityXd operator*(const ScaledIdentityXd& a, double s) { return ScaledIdentityXd{a.n, a.s * s}; }
 
-// Just enough of Transform<float, 3, Affine> for InterpolateTfWithTime (localization_functions.hpp:219-242) to compile;
-// nothing on the compiled paths calls it.
+// Transform<T, 3, Affine> as far as the node and InterpolateTfWithTime use it: a 4 x 4 matrix whose last row stays (0 0 0 1).
 template <typename T>
 class AffineStub {
 public:
+    AffineStub() : m_(Matrix<T, 4, 4>::Identity()) {}
     static AffineStub Identity() { return AffineStub(); }
-    Matrix<T, 3, 1> translation() const { return t_; }
-    Matrix<T, 3, 3> rotation() const { return r_; }
-    AffineStub& translate(const Matrix<T, 3, 1>& v) { t_ += r_ * v; return *this; }
-    AffineStub& rotate(const Quaternion<T>& q) { r_ = r_ * q.toRotationMatrix(); return *this; }
+    T& operator()(int i, int j) { return m_(i, j); }
+    const T& operator()(int i, int j) const { return m_(i, j); }
+    const Matrix<T, 4, 4>& matrix() const { return m_; }
+    BlockRef<T, 3, 1, 4, 4> translation() { return BlockRef<T, 3, 1, 4, 4>(m_, 0, 3); }
+    Matrix<T, 3, 1> translation() const { return m_.template block<3, 1>(0, 3); }
+    Matrix<T, 3, 3> linear() const { return m_.template block<3, 3>(0, 0); }
+    Matrix<T, 3, 3> rotation() const { return linear(); }  // the node only stores rigid transforms
+    AffineStub& translate(const Matrix<T, 3, 1>& v) { m_.template block<3, 1>(0, 3) = translation_value() + linear() * v; return *this; }
+    AffineStub& rotate(const Quaternion<T>& q) { m_.template block<3, 3>(0, 0) = linear() * q.toRotationMatrix(); return *this; }
+    AffineStub inverse() const {  // Affine mode: linear^-1 and -linear^-1 * translation
+        AffineStub r;
+        const Matrix<T, 3, 3> li = linear().inverse();
+        r.m_.template block<3, 3>(0, 0) = li;
+        r.m_.template block<3, 1>(0, 3) = -(li * translation_value());
+        return r;
+    }
+    AffineStub operator*(const AffineStub& o) const {
+        AffineStub r;
+        r.m_.template block<3, 3>(0, 0) = linear() * o.linear();
+        r.m_.template block<3, 1>(0, 3) = linear() * o.translation_value() + translation_value();
+        return r;
+    }
 private:
-    Matrix<T, 3, 3> r_ = Matrix<T, 3, 3>::Identity();
-    Matrix<T, 3, 1> t_;
+    Matrix<T, 3, 1> translation_value() const { return m_.template block<3, 1>(0, 3); }
+    Matrix<T, 4, 4> m_;
+};
+
+template <typename M> class Map;
+template <typename T, int R, int C>
+class Map<const Matrix<T, R, C>> : public Matrix<T, R, C> {
+public:
+    explicit Map(const T* p) { for (int i = 0; i < R * C; ++i) this->data()[i] = p[i]; }
 };
 
 using Matrix2d = Matrix<double, 2, 2>;

@@ -3,9 +3,10 @@
 ctypes front-end of oracle/_ref/libref.so: the REFERENCE's own registration.cpp + voxel_hash_map.{hpp,cpp}, compiled
 unmodified from /root/reference against the stand-in third-party headers in oracle/ref_build/stubs (Eigen3, oneTBB and PCL are
 absent from this image; see stubs/mini_eigen.hpp for what the stand-in does and does not preserve), and of
-oracle/_ref/libref_ekf.so: the reference's own ekf_algorithm.cpp built the same way (plus ref_build/ros_stubs).  They are the
-pin of the oracle: tests/test_reference_build.py and tests/test_reference_build_ekf.py run the oracle and these libraries on
-the same seeded inputs.
+oracle/_ref/libref_ekf.so: the reference's own ekf_algorithm.cpp built the same way (plus ref_build/ros_stubs), and of
+oracle/_ref/libref_node.so: the ROS node class of pcm_matching.cpp itself (plus ref_build/node_stubs: ROS, tf, PCL, boost).
+They are the pin of the oracle: tests/test_reference_build.py, test_reference_build_ekf.py and test_reference_build_node.py
+run the oracle and these libraries on the same seeded inputs.
 
 /root/reference exists only in the build container; `build()` compiles there, the GPU box uses the prebuilt file (git-ignored,
 not gpurun-ignored).  Same call surface as oracle/oracle.py so one test body drives both.
@@ -23,6 +24,7 @@ _SO = os.path.join(_HERE, "_ref", "libref.so")
 REFERENCE_ROOT = os.environ.get("ELM_REFERENCE_ROOT", "/root/reference")
 _PCM = os.path.join(REFERENCE_ROOT, "src", "app", "localization", "pcm_matching")
 _SO_EKF = os.path.join(_HERE, "_ref", "libref_ekf.so")
+_SO_NODE = os.path.join(_HERE, "_ref", "libref_node.so")
 _LIB = None
 
 
@@ -34,6 +36,10 @@ def available():
     return os.path.isfile(_SO) or sources_present()
 
 
+def node_available():
+    return os.path.isfile(_SO_NODE) or sources_present()
+
+
 def ekf_available():
     return os.path.isfile(_SO_EKF) or sources_present()
 
@@ -43,6 +49,7 @@ def build(force=False):
     if sources_present():  # make decides whether anything is stale
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref_ekf.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref_node.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
     if not os.path.isfile(_SO):
         raise FileNotFoundError("oracle/_ref/libref.so is not built and the reference sources are not here")
     return _SO
@@ -269,3 +276,155 @@ class EkfAlgorithm:
         ego = np.zeros(26)
         self._L.ref_ekf_get_current_state(self._h, _d(ego))
         return ego
+
+
+# --------------------------------------------------------------------------------------------------------------- the node
+LOCALIZATION_INI = """[common_variable]
+lidar_type = velodyne
+lidar_scan_time_end = {scan_time_end}
+lidar_time_delay = {time_delay}
+lidar_topic_name = /velodyne_points
+imu_topic_name = /imu/data
+
+[pcm_matching]
+debug_print = 0
+pcm_voxel_size = {voxel_size}
+pcm_voxel_max_point = {voxel_max_point}
+run_deskew = {run_deskew}
+input_max_dist = {input_max_dist}
+input_index_sampling = 1
+input_voxel_ds_m = {input_voxel_ds_m}
+icp_method = {icp_method}
+voxel_search_method = 2
+gicp_cov_search_dist = 0.4
+max_thread = {max_thread}
+max_iteration = {max_iteration}
+max_search_dist = {max_search_dist}
+lm_lambda = {lm_lambda}
+icp_termination_threshold_m = {icp_termination_threshold_m}
+min_overlap_ratio = {min_overlap_ratio}
+max_fitness_score = {max_fitness_score}
+use_radar_cov = 0
+doppler_trans_lambda = 0.5
+range_variance_m = 1.0
+azimuth_variance_deg = 0.4
+elevation_variance_deg = 0.4
+"""
+CALIBRATION_INI = """[Rear To Imu]
+transform_xyz_m = 0.0 0.0 0.0
+rotation_rpy_deg = {imu_rpy}
+
+[Rear To Main LiDAR]
+transform_xyz_m = {lidar_xyz}
+rotation_rpy_deg = {lidar_rpy}
+"""
+
+
+class PcmMatchingNode:
+    """The reference's ROS node class PcmMatching (pcm_matching.hpp:112-380), itself, with this wrapper as the middleware.
+    Configuration goes through the node's own ini parser: the two files are written into a temporary $PWD/config."""
+
+    def __init__(self, map_xyz, lidar_xyz=(0.0, 0.0, 0.0), lidar_rpy_deg=(0.0, 0.0, 0.0), imu_rpy_deg=(0.0, 0.0, 0.0), **kw):
+        import tempfile
+        build()
+        if not os.path.isfile(_SO_NODE):
+            raise FileNotFoundError("oracle/_ref/libref_node.so is not built and the reference sources are not here")
+        d = dict(scan_time_end=0, time_delay=0.0, voxel_size=1.0, voxel_max_point=30, run_deskew=1, input_max_dist=100.0, input_voxel_ds_m=1.5,
+                 icp_method=1, max_thread=1, max_iteration=10, max_search_dist=5.0, lm_lambda=0.5, icp_termination_threshold_m=0.02,
+                 min_overlap_ratio=0.4, max_fitness_score=0.5)
+        d.update(kw)
+        self.cfg = d
+        self._dir = tempfile.TemporaryDirectory(prefix="pcm_node_")
+        os.makedirs(os.path.join(self._dir.name, "config"))
+        with open(os.path.join(self._dir.name, "config", "localization.ini"), "w") as f:
+            f.write(LOCALIZATION_INI.format(**d))
+        with open(os.path.join(self._dir.name, "config", "calibration.ini"), "w") as f:
+            f.write(CALIBRATION_INI.format(imu_rpy=" ".join(map(str, imu_rpy_deg)), lidar_xyz=" ".join(map(str, lidar_xyz)),
+                                           lidar_rpy=" ".join(map(str, lidar_rpy_deg))))
+        L = C.CDLL(_SO_NODE)
+        dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.ref_node_create.restype = C.c_void_p
+        L.ref_node_create.argtypes = [C.c_char_p, fp, C.c_size_t]
+        L.ref_node_destroy.argtypes = [C.c_void_p]
+        L.ref_node_map_points.restype = C.c_size_t
+        L.ref_node_map_points.argtypes = [C.c_void_p]
+        L.ref_node_imu.argtypes = [C.c_void_p, C.c_double, dp, dp]
+        L.ref_node_odom.argtypes = [C.c_void_p, C.c_double, dp, dp, dp, dp]
+        L.ref_node_cloud.restype = C.c_size_t
+        L.ref_node_cloud.argtypes = [C.c_void_p, C.c_double, fp, fp, C.c_size_t]
+        L.ref_node_last_pcm_odom.argtypes = [dp, dp, dp, dp]
+        L.ref_node_last_registered_cloud.restype = C.c_size_t
+        L.ref_node_last_registered_cloud.argtypes = [fp, C.c_size_t]
+        L.ref_node_filter_by_distance.restype = C.c_size_t
+        L.ref_node_filter_by_distance.argtypes = [C.c_void_p, fp, C.c_size_t, ip]
+        L.ref_node_deskew.argtypes = [C.c_void_p, C.c_double, fp, fp, C.c_size_t]
+        L.ref_node_undistorted.restype = C.c_size_t
+        L.ref_node_undistorted.argtypes = [C.c_void_p, fp, C.c_size_t]
+        L.ref_node_deskew_tables.argtypes = [C.c_void_p, dp, dp, dp, dp, ip, fp, dp]
+        L.ref_node_interpolated_pose.argtypes = [C.c_void_p, C.c_double, fp]
+        L.ref_node_shape_covariance.argtypes = [C.c_void_p, dp, dp, C.c_double, dp]
+        self._L = L
+        m = _xyz(map_xyz)
+        self._h = L.ref_node_create(self._dir.name.encode(), _f(m), m.shape[0])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ref_node_destroy(self._h)
+            self._h = None
+
+    def map_points(self):
+        return self._L.ref_node_map_points(self._h)
+
+    def imu(self, t, gyro, acc):
+        g, a = np.ascontiguousarray(gyro, dtype=np.float64), np.ascontiguousarray(acc, dtype=np.float64)
+        self._L.ref_node_imu(self._h, float(t), _d(g), _d(a))
+
+    def odom(self, t, pos, quat_wxyz, lin=(0, 0, 0), ang=(0, 0, 0)):
+        q = np.asarray(quat_wxyz, dtype=np.float64)
+        p, qx = np.ascontiguousarray(pos, dtype=np.float64), np.ascontiguousarray([q[1], q[2], q[3], q[0]], dtype=np.float64)
+        li, an = np.ascontiguousarray(lin, dtype=np.float64), np.ascontiguousarray(ang, dtype=np.float64)
+        self._L.ref_node_odom(self._h, float(t), _d(p), _d(qx), _d(li), _d(an))
+
+    def cloud(self, stamp, xyz, rel_time):
+        """CallbackPointCloud; returns the published pcm odometry of THIS call (dict) or None"""
+        x, rt = _xyz(xyz), np.ascontiguousarray(rel_time, dtype=np.float32)
+        before = getattr(self, "_n_odom", 0)
+        self._n_odom = self._L.ref_node_cloud(self._h, float(stamp), _f(x), _f(rt), x.shape[0])
+        if self._n_odom == before:
+            return None
+        st, pos, q, cov = np.zeros(1), np.zeros(3), np.zeros(4), np.zeros((6, 6))
+        self._L.ref_node_last_pcm_odom(_d(st), _d(pos), _d(q), _d(cov))
+        reg = np.zeros((x.shape[0], 3), np.float32)
+        n = self._L.ref_node_last_registered_cloud(_f(reg), x.shape[0])
+        return dict(stamp=float(st[0]), pos=pos, quat_wxyz=np.array([q[3], q[0], q[1], q[2]]), cov=cov, registered_world=reg[:n])
+
+    def filter_by_distance(self, xyz):
+        x = _xyz(xyz)
+        idx = np.zeros(max(1, x.shape[0]), np.int32)
+        n = self._L.ref_node_filter_by_distance(self._h, _f(x), x.shape[0], _i(idx))
+        return idx[:n]
+
+    def deskew(self, stamp, xyz, rel_time):
+        """DeskewPointCloud; returns (ok, undistorted cloud, tables in the layout of oracle.deskew_tables)"""
+        x, rt = _xyz(xyz), np.ascontiguousarray(rel_time, dtype=np.float32)
+        ok = bool(self._L.ref_node_deskew(self._h, float(stamp), _f(x), _f(rt), x.shape[0]))
+        out = np.zeros_like(x)
+        n = self._L.ref_node_undistorted(self._h, _f(out), x.shape[0])
+        t = dict(imu_time=np.zeros(2000), imu_rot_x=np.zeros(2000), imu_rot_y=np.zeros(2000), imu_rot_z=np.zeros(2000))
+        mi, mf, tm = np.zeros(3, np.int32), np.zeros(3, np.float32), np.zeros(2)
+        self._L.ref_node_deskew_tables(self._h, _d(t["imu_time"]), _d(t["imu_rot_x"]), _d(t["imu_rot_y"]), _d(t["imu_rot_z"]), _i(mi), _f(mf), _d(tm))
+        t.update(imu_pointer_cur=int(mi[0]), imu_available=bool(mi[1]), odom_available=bool(mi[2]), odom_incre=mf.copy(),
+                 time_scan_cur=float(tm[0]), time_scan_end=float(tm[1]))
+        return ok, out[:n], t
+
+    def interpolated_pose(self, t):
+        T = np.zeros((4, 4), np.float32)
+        ok = bool(self._L.ref_node_interpolated_pose(self._h, float(t), _f(T)))
+        return ok, T
+
+    def shape_covariance(self, pose, local_cov, icp_pose_std_m):
+        T = np.ascontiguousarray(pose, dtype=np.float64).reshape(4, 4)
+        lc = np.ascontiguousarray(local_cov, dtype=np.float64).reshape(6, 6)
+        out = np.zeros((6, 6))
+        self._L.ref_node_shape_covariance(self._h, _d(T), _d(lc), float(icp_pose_std_m), _d(out))
+        return out

@@ -9,8 +9,9 @@
 // library (index-level results identical, floating point to rounding) and tests/golden/*.npz are its outputs.
 // What stays restated and unpinned: Eigen's own arithmetic kernels — the routines of THIS file, which the stand-in Eigen
 // reuses — and, for a rank-deficient covariance, Eigen's implementation-defined null-space basis (plane_regularize below).
-// The EKF (ekf.hpp) is pinned the same way on oracle/_ref/libref_ekf.so (the reference's ekf_algorithm.cpp).  The deskew
-// (deskew.hpp) lives inside the ROS node pcm_matching.cpp, has no buildable reference here and remains unpinned.
+// The EKF (ekf.hpp) is pinned the same way on oracle/_ref/libref_ekf.so (the reference's ekf_algorithm.cpp), and the deskew,
+// distance filter, pose interpolation and covariance shaping on oracle/_ref/libref_node.so (the ROS node pcm_matching.cpp
+// itself, against stand-in ROS / tf / PCL headers).
 //
 // Tiny fixed-size fp64 linear algebra that stands in for the Eigen3 calls the reference makes
 // (Eigen is a third-party dependency that is absent from /root/reference; apt libeigen3-dev,

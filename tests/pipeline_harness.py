@@ -116,7 +116,10 @@ def get_interpolated_pose(deq, t):
         Rg = rpy_to_R(r, p, y)
         pos = last["pos"] + Rg @ last["vel_local"] * dt
         r, p, y = r + last["rate"][0] * dt, p + last["rate"][1] * dt, y + last["rate"][2] * dt
-        after = dict(t=last["t"], pos=pos, quat=R_to_quat_wxyz(rpy_to_R(r, p, y)))  # header stamp stays default -> d_time_after
+        # odom_after is default-constructed in the reference and only its pose is filled: header.stamp stays 0, so
+        # d_time_after = 0 and the ratio dt_scan / (0 - d_time_before) is a tiny NEGATIVE number — the extrapolated pose is in
+        # effect discarded (verified against the node itself, tests/test_reference_build_node.py)
+        after = dict(t=0.0, pos=pos, quat=R_to_quat_wxyz(rpy_to_R(r, p, y)))
     A, B = odom_to_affine(before), odom_to_affine(after)
     between = (np.linalg.inv(A.astype(np.float64)) @ B.astype(np.float64)).astype(F32)
     interp = interpolate_tf_with_time(between, t - before["t"], after["t"] - before["t"])

@@ -1,0 +1,212 @@
+"""The pin of the stages around RunRegister: the REFERENCE's own ROS node class PcmMatching (pcm_matching.cpp, compiled unmodified
+from /root/reference against stand-in ROS / tf / PCL / boost / Eigen headers into oracle/_ref/libref_node.so) with the test as
+the middleware, against the oracle's restatements and the numpy glue of tests/pipeline_harness.py.  Runs without a GPU.
+
+  FilterPointsByDistance   pcm_matching.cpp:451-465     vs oracle.scan_preprocess                      identical indices
+  ImuDeskewInfo / OdomDeskewInfo  :533-729              vs oracle.deskew_tables                        tables 1e-15 / float increments
+  DeskewPoint over a scan  :499-511, 780-824            vs oracle.deskew_points                        bit-equal on the same tables
+  GetInterpolatedPose      :933-1045                    vs pipeline_harness.get_interpolated_pose      float32 rounding
+  PublishPcmOdom covariance :1047-1101                  vs oracle.shape_pcm_covariance + the product's host function   1e-12
+  CallbackPointCloud end to end :198-324                vs the same chain composed from the oracle's pieces             1e-6
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import pipeline_harness as H  # noqa: E402
+from elimaloc_b200 import synth  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from oracle import reference_build as R  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not R.node_available(), reason="neither /root/reference nor a prebuilt oracle/_ref/libref_node.so is here")
+
+T0 = 100.0
+LIDAR_XYZ, LIDAR_RPY_DEG = (0.0961, -0.1338, 0.3032), (-1.26, -0.876, 0.287)  # the reference's config/calibration.ini
+
+
+def tf_quat_from_rpy(r, p, y):
+    """tf::Quaternion::setRPY -> (w, x, y, z)"""
+    cy, sy, cp, sp, cr, sr = np.cos(y / 2), np.sin(y / 2), np.cos(p / 2), np.sin(p / 2), np.cos(r / 2), np.sin(r / 2)
+    return np.array([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy])
+
+
+def tf_rpy_from_quat(q):
+    """tf::Matrix3x3(q).getRPY (non-degenerate branch)"""
+    Rm = H.quat_to_R(np.asarray(q, dtype=np.float64))
+    pitch = -np.arcsin(Rm[2, 0])
+    return np.arctan2(Rm[2, 1] / np.cos(pitch), Rm[2, 2] / np.cos(pitch)), pitch, np.arctan2(Rm[1, 0] / np.cos(pitch), Rm[0, 0] / np.cos(pitch))
+
+
+def ego_pose(t, centre):
+    yaw = 0.3 * (t - T0)
+    return np.array([centre[0] + 3 * np.sin(yaw), centre[1] + 3 * (1 - np.cos(yaw)), centre[2]]), (0.01, -0.02, yaw)
+
+
+def feed(node, centre, k0=-5, k1=30, imu=True, odom=True):
+    """100 Hz odometry and IMU; returns the odometry queue in the harness' format and the IMU arrays"""
+    deq, stamps, gyro = [], [], []
+    for k in range(k0, k1):
+        t = T0 + 0.01 * k
+        p, rpy = ego_pose(t, centre)
+        q = tf_quat_from_rpy(*rpy)
+        if odom:
+            node.odom(t, p, q, lin=(0.9, 0.0, 0.0), ang=(0.0, 0.0, 0.3))
+            deq.append(dict(t=t, pos=p, quat=q, vel_local=np.array([0.9, 0.0, 0.0]), rate=np.array([0.0, 0.0, 0.3])))
+        if imu:
+            g = [0.01 + 1e-3 * np.sin(k), -0.02, 0.3 + 1e-3 * np.cos(k)]
+            node.imu(t + 0.003, g, [0.0, 0.0, 9.81])
+            stamps.append(t + 0.003)
+            gyro.append(g)
+    return deq, np.array(stamps), np.array(gyro)
+
+
+def oracle_tables(deq, stamps, gyro, t_cur, t_end):
+    """the odometry selection of OdomDeskewInfo (first message not older than scan start / scan end) + the oracle's tables"""
+    s = next(o for o in deq if not o["t"] < t_cur)
+    e = next(o for o in deq if not o["t"] < t_end)
+    return O.deskew_tables(stamps, gyro, t_cur, t_end, list(s["pos"]) + list(tf_rpy_from_quat(s["quat"])), s["t"],
+                           list(e["pos"]) + list(tf_rpy_from_quat(e["quat"])), e["t"])
+
+
+@pytest.fixture(scope="module")
+def raw_map():
+    return synth.map_u(40_000, 16.0, origin=-3.0)
+
+
+def test_node_builds_the_same_map(raw_map):
+    node = R.PcmMatchingNode(raw_map, icp_method=1)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw_map)
+    assert node.map_points() == om.num_points()
+
+
+def test_distance_filter(raw_map):
+    node = R.PcmMatchingNode(raw_map[:100], input_max_dist=37.5)
+    xyz = synth.scan_u(20_000, 40.0, seed=3)
+    xyz[:5] = [[37.5, 0, 0], [0, -37.5, 0], [22.5, 30.0, 0], [37.500004, 0, 0], [0, 0, 0]]  # on and just beyond the sphere
+    got = node.filter_by_distance(xyz)
+    assert np.array_equal(got, O.scan_preprocess(xyz, 37.5, 0.0))
+    assert 0 in got and 1 in got and 3 not in got and 0 < len(got) < len(xyz)
+
+
+@pytest.mark.parametrize("scan_time_end", [0, 1])
+def test_deskew_tables_and_points(raw_map, scan_time_end):
+    node = R.PcmMatchingNode(raw_map[:100], scan_time_end=scan_time_end)
+    deq, stamps, gyro = feed(node, (2.0, 1.0, 0.5))
+    n = 4000
+    rng = np.random.default_rng(0)
+    xyz = synth.scan_u(n, 30.0, seed=1)
+    rel = np.sort(rng.random(n).astype(np.float32) * np.float32(0.1))
+    stamp = T0 + 0.05
+    if scan_time_end:  # "last point is time 0": negative per-point times, stamp = scan end
+        rel_in, stamp_in = (rel - rel[-1]).astype(np.float32), stamp + float(rel[-1])
+        t_end = stamp_in
+        t_cur = t_end + float(rel_in[0])
+        rel_eff = (rel_in - rel_in[0]).astype(np.float32)
+    else:
+        rel_in, stamp_in, t_cur, t_end, rel_eff = rel, stamp, stamp, stamp + float(rel[-1]), rel
+    ok, und, tab = node.deskew(stamp_in, xyz, rel_in)
+    assert ok and tab["imu_available"] and tab["odom_available"]
+    assert tab["time_scan_cur"] == t_cur and tab["time_scan_end"] == t_end
+    # the per-point transform on the node's own tables: bit-equal
+    assert np.array_equal(und, O.deskew_points(tab, xyz, rel_eff))
+    # the tables themselves
+    ot = oracle_tables(deq, stamps, gyro, t_cur, t_end)
+    k = tab["imu_pointer_cur"]
+    assert ot["imu_pointer_cur"] == k > 3
+    for name in ("imu_time", "imu_rot_x", "imu_rot_y", "imu_rot_z"):
+        assert np.abs(ot[name][:k + 1] - tab[name][:k + 1]).max() < 1e-15, name
+    assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 2e-7  # float32; rpy goes through a quaternion on the node's side
+    assert np.abs(und - O.deskew_points(ot, xyz, rel_eff)).max() < 2e-5
+
+
+def test_deskew_needs_imu_and_odometry(raw_map):
+    xyz = synth.scan_u(100, 10.0, seed=2)
+    rel = np.linspace(0, 0.1, 100).astype(np.float32)
+    node = R.PcmMatchingNode(raw_map[:100])
+    feed(node, (2.0, 1.0, 0.5), imu=False)
+    assert not node.deskew(T0 + 0.05, xyz, rel)[0]
+    node = R.PcmMatchingNode(raw_map[:100])
+    feed(node, (2.0, 1.0, 0.5), odom=False)
+    assert not node.deskew(T0 + 0.05, xyz, rel)[0]
+    node = R.PcmMatchingNode(raw_map[:100])
+    feed(node, (2.0, 1.0, 0.5), k0=10)  # the first odometry message is newer than the scan start: no synced pose
+    assert not node.deskew(T0 + 0.05, xyz, rel)[0]
+
+
+def test_interpolated_pose(raw_map):
+    node = R.PcmMatchingNode(raw_map[:100])
+    deq, _, _ = feed(node, (2.0, 1.0, 0.5))
+    for t in (T0 + 0.1234, T0 + 0.05, deq[-1]["t"], deq[-1]["t"] + 0.02, deq[-1]["t"] + 0.5):  # between, on, last, beyond the queue
+        ok, T = node.interpolated_pose(t)
+        want = H.get_interpolated_pose(deq, t)
+        assert ok and np.abs(T - want).max() < 1e-6, t
+    assert not node.interpolated_pose(deq[0]["t"] - 1.0)[0] and H.get_interpolated_pose(deq, deq[0]["t"] - 1.0) is None
+
+
+def test_covariance_shaping(raw_map):
+    import elimaloc_b200 as E
+    node = R.PcmMatchingNode(raw_map[:100])
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        A = rng.normal(size=(6, 6)) * (1e-6 if trial % 3 == 0 else 1e-2)
+        local_cov = A @ A.T + np.diag(rng.random(6) * (1e-12 if trial % 4 == 0 else 1e-4))
+        pose = synth.se3(rng.normal(0, 5, 3), rng.normal(0, 0.5, 3))
+        std = [0.1, 0.25, 0.4, 1.3][trial % 4]
+        got = node.shape_covariance(pose, local_cov, std)
+        want = O.shape_pcm_covariance(pose[:3, :3], local_cov, std)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+        assert np.abs(E.shape_pcm_covariance(pose[:3, :3], local_cov, std) - got).max() <= 1e-12 * max(1.0, np.abs(got).max())
+
+
+@pytest.mark.parametrize("method", [O.P2P, O.GICP, O.VGICP])
+def test_lidar_callback_end_to_end(raw_map, method):
+    """one lidar message through the node's CallbackPointCloud against the same chain composed from the oracle's pieces:
+    filter -> deskew -> pose interpolation -> first-in-voxel down-sampling -> RunRegister -> ego pose -> covariance"""
+    node = R.PcmMatchingNode(raw_map, lidar_xyz=LIDAR_XYZ, lidar_rpy_deg=LIDAR_RPY_DEG, icp_method=method, input_max_dist=60.0)
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw_map)
+    om.CalVoxelCovAll()
+    om.CalPointCovAll(0.4)
+    centre = (5.0, 4.0, 5.0)
+    deq, stamps, gyro = feed(node, centre)
+    tf = np.eye(4)
+    tf[:3, :3] = H.rpy_to_R(*np.deg2rad(LIDAR_RPY_DEG))
+    tf[:3, 3] = LIDAR_XYZ
+    # a scan of map points seen from the lidar at scan end, with per-point times
+    stamp, n = T0 + 0.05, 3000
+    rng = np.random.default_rng(7)
+    rel = np.sort(rng.random(n).astype(np.float32) * np.float32(0.1))
+    p_end, rpy_end = ego_pose(stamp + float(rel[-1]), centre)
+    T_lidar = np.eye(4)
+    T_lidar[:3, :3] = H.rpy_to_R(*rpy_end)
+    T_lidar[:3, 3] = p_end
+    T_lidar = T_lidar @ tf
+    scan = synth.scan_m(om.export()["pxyz"], n, T_lidar, noise=0.02, seed=11)
+    scan[:3] *= np.float32(40.0)  # three points beyond input_max_dist
+    out = node.cloud(stamp, scan, rel)
+    assert out is not None, "the node did not publish a pose"
+    # --- the same chain from the oracle's pieces
+    keep = O.scan_preprocess(scan, 60.0, 0.0)
+    assert len(keep) == n - 3
+    xyz, rt = scan[keep], rel[keep]
+    t_cur, t_end = stamp, stamp + float(rt[-1])
+    und = O.deskew_points(oracle_tables(deq, stamps, gyro, t_cur, t_end), xyz, rt)
+    sync = H.get_interpolated_pose(deq, t_end).astype(np.float64) @ tf
+    ds = und[O.scan_preprocess(und, 0.0, 1.5)]
+    r = O.Registration().RunRegister(ds, om, sync, O.make_config(icp_method=method))
+    assert r["is_success"]
+    ego = r["pose"] @ np.linalg.inv(tf)
+    assert out["stamp"] == t_end
+    assert len(out["registered_world"]) == len(ds)
+    assert np.abs(out["pos"] - ego[:3, 3]).max() < 2e-6
+    q = H.R_to_quat_wxyz(ego[:3, :3])
+    assert min(np.abs(out["quat_wxyz"] - q).max(), np.abs(out["quat_wxyz"] + q).max()) < 1e-7
+    want_cov = O.shape_pcm_covariance(ego[:3, :3], r["local_cov"], r["fitness_score"])
+    assert np.abs(out["cov"] - want_cov).max() <= 1e-5 * np.abs(want_cov).max()
+    # and the pose is sensible: the node localised the scan (the synthetic scan is not motion-distorted, so the deskew itself
+    # moves points by up to the 9 cm the vehicle travels during the sweep)
+    assert np.linalg.norm(out["pos"] - p_end) < 0.15
