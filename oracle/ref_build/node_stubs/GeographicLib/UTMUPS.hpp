@@ -1,0 +1,3 @@
+// Forwarding stand-in: see node_world.hpp.
+#pragma once
+#include "../node_world.hpp"

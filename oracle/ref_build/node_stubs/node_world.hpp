@@ -84,14 +84,24 @@ struct NodeHandle {
         out = it->second;
         return true;
     }
+    bool getParam(const std::string& key, double& out) const {
+        auto it = Capture::get().params.find(key);
+        if (it == Capture::get().params.end()) return false;
+        out = std::atof(it->second.c_str());
+        return true;
+    }
 };
 }  // namespace ros
 #define ROS_WARN_STREAM(x) do { std::ostringstream ros_stub_oss; ros_stub_oss << x; } while (0)
 #define ROS_INFO_STREAM(x) ROS_WARN_STREAM(x)
 #define ROS_ERROR_STREAM(x) ROS_WARN_STREAM(x)
+#define ROS_INFO(...) do { } while (0)
+#define ROS_WARN(...) do { } while (0)
+#define ROS_ERROR(...) do { } while (0)
 
 // ------------------------------------------------------------------------------------------------------------- messages
 namespace std_msgs {
+struct Float32 { float data = 0; };
 struct Header { uint32_t seq = 0; ros::Time stamp; std::string frame_id; };
 struct ColorRGBA { float r = 0, g = 0, b = 0, a = 0; };
 }  // namespace std_msgs
@@ -108,6 +118,8 @@ struct PoseWithCovarianceStamped {
     PoseWithCovariance pose;
     using ConstPtr = boost::shared_ptr<const PoseWithCovarianceStamped>;
 };
+struct TwistStamped { std_msgs::Header header; Twist twist; };
+using TwistStampedConstPtr = boost::shared_ptr<const TwistStamped>;
 struct Transform { Vector3 translation; Quaternion rotation; };
 struct TransformStamped { std_msgs::Header header; std::string child_frame_id; Transform transform; };
 }  // namespace geometry_msgs
@@ -127,6 +139,15 @@ struct Imu {
     geometry_msgs::Vector3 angular_velocity, linear_acceleration;
     using ConstPtr = boost::shared_ptr<const Imu>;
 };
+struct NavSatStatus { int8_t status = 0; uint16_t service = 0; };
+struct NavSatFix {
+    std_msgs::Header header;
+    NavSatStatus status;
+    double latitude = 0, longitude = 0, altitude = 0;
+    boost::array<double, 9> position_covariance{};
+    uint8_t position_covariance_type = 0;
+    using ConstPtr = boost::shared_ptr<const NavSatFix>;
+};
 // The wire format is not modelled: a cloud message carries typed records (x, y, z, intensity, per-point time and the Ouster
 // fields); pcl::fromROSMsg below copies the fields the target point type has.
 struct PointRecord { float x = 0, y = 0, z = 0, intensity = 0, time = 0; uint32_t t = 0; uint16_t reflectivity = 0, ring = 0, ambient = 0; uint32_t range = 0; };
@@ -139,7 +160,7 @@ struct PointCloud2 {
 }  // namespace sensor_msgs
 namespace visualization_msgs {
 struct Marker {
-    enum { CYLINDER = 3, ADD = 0 };
+    enum { CUBE = 1, CYLINDER = 3, ADD = 0 };
     std_msgs::Header header;
     std::string ns;
     int id = 0, type = 0, action = 0;
@@ -196,8 +217,44 @@ struct Matrix3x3 {  // tf/LinearMath/Matrix3x3.h: setRotation + getEulerYPR (sol
         }
     }
 };
-struct TransformBroadcaster {};
+struct Vector3 { double x, y, z; Vector3(double a = 0, double b = 0, double c = 0) : x(a), y(b), z(c) {} };
+struct Transform {
+    Vector3 origin;
+    Quaternion rotation;
+    void setOrigin(const Vector3& v) { origin = v; }
+    void setRotation(const Quaternion& q) { rotation = q; }
+};
+struct StampedTransform {
+    Transform transform;
+    ros::Time stamp;
+    std::string frame_id, child_frame_id;
+    StampedTransform(const Transform& t, const ros::Time& s, const std::string& f, const std::string& c) : transform(t), stamp(s), frame_id(f), child_frame_id(c) {}
+};
+struct TransformBroadcaster { void sendTransform(const StampedTransform&) {} };
 }  // namespace tf
+namespace jsk_rviz_plugins {
+struct OverlayText {
+    int action = 0, width = 0, height = 0, left = 0, top = 0, text_size = 0, line_width = 0;
+    std_msgs::ColorRGBA bg_color, fg_color;
+    std::string font, text;
+};
+}  // namespace jsk_rviz_plugins
+// GeographicLib::LocalCartesian is only used to fill the latitude / longitude / height fields of the published state
+// (ekf_localization.cpp:412-418, 643-648); geodesy is not restated: a flat-earth stand-in keeps the calls well defined.
+namespace GeographicLib {
+class LocalCartesian {
+public:
+    LocalCartesian(double lat0, double lon0, double h0) : lat0_(lat0), lon0_(lon0), h0_(h0) {}
+    void Reverse(double x, double y, double z, double& lat, double& lon, double& h) const {
+        lat = lat0_ + y / 111320.0; lon = lon0_ + x / (111320.0 * std::cos(lat0_ * M_PI / 180.0)); h = h0_ + z;
+    }
+    void Forward(double lat, double lon, double h, double& x, double& y, double& z) const {
+        y = (lat - lat0_) * 111320.0; x = (lon - lon0_) * 111320.0 * std::cos(lat0_ * M_PI / 180.0); z = h - h0_;
+    }
+private:
+    double lat0_, lon0_, h0_;
+};
+}  // namespace GeographicLib
 namespace tf2_ros {
 struct StaticTransformBroadcaster { void sendTransform(const geometry_msgs::TransformStamped&) {} };
 }  // namespace tf2_ros

@@ -25,6 +25,7 @@ REFERENCE_ROOT = os.environ.get("ELM_REFERENCE_ROOT", "/root/reference")
 _PCM = os.path.join(REFERENCE_ROOT, "src", "app", "localization", "pcm_matching")
 _SO_EKF = os.path.join(_HERE, "_ref", "libref_ekf.so")
 _SO_NODE = os.path.join(_HERE, "_ref", "libref_node.so")
+_SO_EKFNODE = os.path.join(_HERE, "_ref", "libref_ekfnode.so")
 _LIB = None
 
 
@@ -37,7 +38,7 @@ def available():
 
 
 def node_available():
-    return os.path.isfile(_SO_NODE) or sources_present()
+    return (os.path.isfile(_SO_NODE) and os.path.isfile(_SO_EKFNODE)) or sources_present()
 
 
 def ekf_available():
@@ -50,6 +51,7 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref_ekf.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref_node.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["_ref/libref_ekfnode.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
     if not os.path.isfile(_SO):
         raise FileNotFoundError("oracle/_ref/libref.so is not built and the reference sources are not here")
     return _SO
@@ -310,7 +312,52 @@ range_variance_m = 1.0
 azimuth_variance_deg = 0.4
 elevation_variance_deg = 0.4
 """
-CALIBRATION_INI = """[Rear To Imu]
+EKF_INI = """
+[ekf_localization]
+debug_print = 0
+debug_imu_print = 0
+imu_gravity = {imu_gravity}
+imu_estimate_gravity = {imu_estimate_gravity}
+imu_estimate_calibration = 0
+use_zupt = 0
+use_complementary_filter = {use_complementary_filter}
+gps_type = 2
+gnss_uncertainy_max_m = 1.0
+use_gps = 0
+use_imu = 1
+use_can = 0
+use_pcm_matching = 1
+can_vel_scale_factor = 1.0
+ekf_init_x_m = {ekf_init_x_m}
+ekf_init_y_m = {ekf_init_y_m}
+ekf_init_z_m = {ekf_init_z_m}
+ekf_init_roll_deg = {ekf_init_roll_deg}
+ekf_init_pitch_deg = {ekf_init_pitch_deg}
+ekf_init_yaw_deg = {ekf_init_yaw_deg}
+ekf_state_uncertainty_pos_m = {state_std_pos_m}
+ekf_state_uncertainty_rot_deg = {state_std_rot_deg}
+ekf_state_uncertainty_vel_mps = {state_std_vel_mps}
+ekf_state_uncertainty_gyro_dps = 5.0
+ekf_state_uncertainty_acc_mps = 100.0
+ekf_imu_uncertainty_gyro_dps = {imu_std_gyro_dps}
+ekf_imu_uncertainty_acc_mps = {imu_std_acc_mps}
+ekf_imu_bias_cov_gyro = {imu_bias_cov_gyro}
+ekf_imu_bias_cov_acc = {imu_bias_cov_acc}
+ekf_gnss_min_cov_x_m = 0.2
+ekf_gnss_min_cov_y_m = 0.2
+ekf_gnss_min_cov_z_m = 0.7
+ekf_gnss_min_cov_roll_deg = 0.0
+ekf_gnss_min_cov_pitch_deg = 0.0
+ekf_gnss_min_cov_yaw_deg = 0.0
+ekf_can_meas_uncertainty_vel_mps = 2.0
+ekf_can_meas_uncertainty_yaw_rate_deg = 10.0
+ekf_bestvel_meas_uncertainty_vel_mps = 1.0
+"""
+CALIBRATION_INI = """[Rear To Gps]
+transform_xyz_m = 0.0 0.0 0.0
+rotation_rpy_deg = 0.0 0.0 0.0
+
+[Rear To Imu]
 transform_xyz_m = 0.0 0.0 0.0
 rotation_rpy_deg = {imu_rpy}
 
@@ -428,3 +475,92 @@ class PcmMatchingNode:
         out = np.zeros((6, 6))
         self._L.ref_node_shape_covariance(self._h, _d(T), _d(lc), float(icp_pose_std_m), _d(out))
         return out
+
+
+def _fresh_cdll(path):
+    """a private copy of a library: its function-static variables start from scratch"""
+    import shutil
+    import tempfile
+    fd, tmp = tempfile.mkstemp(suffix=".so", prefix="libref_")
+    os.close(fd)
+    shutil.copyfile(path, tmp)
+    L = C.CDLL(tmp)
+    os.unlink(tmp)
+    return L
+
+
+class EkfLocalizationNode:
+    """The reference's EKF ROS node class EkfLocalization (ekf_localization.hpp), itself; configured through its own ini
+    parser from the field names of elimaloc_b200.ekf.make_ekf_config (`ekf_cfg` is that ctypes structure)."""
+
+    def __init__(self, ekf_cfg):
+        import tempfile
+        build()
+        if not os.path.isfile(_SO_EKFNODE):
+            raise FileNotFoundError("oracle/_ref/libref_ekfnode.so is not built and the reference sources are not here")
+        d = {name: getattr(ekf_cfg, name) for name, _ in ekf_cfg._fields_ if name != "reserved"}
+        self._dir = tempfile.TemporaryDirectory(prefix="ekf_node_")
+        os.makedirs(os.path.join(self._dir.name, "config"))
+        with open(os.path.join(self._dir.name, "config", "localization.ini"), "w") as f:
+            f.write("[common_variable]\ncan_topic_name = /can\nimu_topic_name = /imu/data\nnavsatfix_topic_name = /gps/fix\nprojection_mode = Cartesian\n")
+            f.write(EKF_INI.format(**{k: repr(v) if isinstance(v, float) else v for k, v in d.items()}))
+        with open(os.path.join(self._dir.name, "config", "calibration.ini"), "w") as f:
+            f.write(CALIBRATION_INI.format(imu_rpy="0.0 0.0 0.0", lidar_xyz="0.0 0.0 0.0", lidar_rpy="0.0 0.0 0.0").replace(
+                "[Rear To Imu]", "[Rear To Imu]\ntransform_xyz_m = 0.0 0.0 0.0", 1).replace("transform_xyz_m = 0.0 0.0 0.0\ntransform_xyz_m", "transform_xyz_m", 1))
+        L = _fresh_cdll(_SO_EKFNODE)
+        dp = C.POINTER(C.c_double)
+        L.ref_ekfnode_create.restype = C.c_void_p
+        L.ref_ekfnode_create.argtypes = [C.c_char_p]
+        L.ref_ekfnode_destroy.argtypes = [C.c_void_p]
+        L.ref_ekfnode_imu.argtypes = [C.c_void_p, C.c_double, dp, dp]
+        L.ref_ekfnode_pcm_odom.argtypes = [C.c_void_p, C.c_double, dp, dp, dp]
+        L.ref_ekfnode_pcm_init_odom.argtypes = [C.c_void_p, C.c_double, dp, dp]
+        L.ref_ekfnode_last_odom.argtypes = [dp, dp, dp, dp, dp]
+        L.ref_ekfnode_filter_pose.argtypes = [C.c_void_p, dp, dp]
+        L.ref_ekfnode_time_compensate.argtypes = [C.c_void_p, C.c_double, dp, dp, dp, dp, dp]
+        L.ref_ekfnode_state_queue.restype = C.c_size_t
+        L.ref_ekfnode_state_queue.argtypes = [C.c_void_p, dp, C.c_size_t]
+        self._L = L
+        self._h = L.ref_ekfnode_create(self._dir.name.encode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ref_ekfnode_destroy(self._h)
+            self._h = None
+
+    def imu(self, t, gyro, acc):
+        """CallbackImu; returns the /app/loc/ekf_pose_odom it published: dict(t, pos, quat wxyz, vel_local, rate)"""
+        g, a = np.ascontiguousarray(gyro, dtype=np.float64), np.ascontiguousarray(acc, dtype=np.float64)
+        self._L.ref_ekfnode_imu(self._h, float(t), _d(g), _d(a))
+        st, pos, q, lin, ang = np.zeros(1), np.zeros(3), np.zeros(4), np.zeros(3), np.zeros(3)
+        if not self._L.ref_ekfnode_last_odom(_d(st), _d(pos), _d(q), _d(lin), _d(ang)):
+            return None
+        return dict(t=float(st[0]), pos=pos, quat=np.array([q[3], q[0], q[1], q[2]]), vel_local=lin, rate=ang)
+
+    def pcm_odom(self, t, pos, quat_wxyz, cov66):
+        q = np.asarray(quat_wxyz, dtype=np.float64)
+        p, qx = np.ascontiguousarray(pos, dtype=np.float64), np.ascontiguousarray([q[1], q[2], q[3], q[0]], dtype=np.float64)
+        c = np.ascontiguousarray(cov66, dtype=np.float64).reshape(36)
+        self._L.ref_ekfnode_pcm_odom(self._h, float(t), _d(p), _d(qx), _d(c))
+
+    def pcm_init_odom(self, t, pos, quat_wxyz):
+        q = np.asarray(quat_wxyz, dtype=np.float64)
+        p, qx = np.ascontiguousarray(pos, dtype=np.float64), np.ascontiguousarray([q[1], q[2], q[3], q[0]], dtype=np.float64)
+        self._L.ref_ekfnode_pcm_init_odom(self._h, float(t), _d(p), _d(qx))
+
+    def filter_pose(self):
+        pos, q = np.zeros(3), np.zeros(4)
+        self._L.ref_ekfnode_filter_pose(self._h, _d(pos), _d(q))
+        return np.concatenate([pos, q])
+
+    def time_compensate(self, t, pos, quat_wxyz):
+        p, q = np.ascontiguousarray(pos, dtype=np.float64), np.ascontiguousarray(quat_wxyz, dtype=np.float64)
+        to, po, qo = np.zeros(1), np.zeros(3), np.zeros(4)
+        if not self._L.ref_ekfnode_time_compensate(self._h, float(t), _d(p), _d(q), _d(to), _d(po), _d(qo)):
+            return None
+        return dict(t=float(to[0]), pos=po, quat=qo)
+
+    def state_queue(self):
+        rows = np.zeros((1000, 7))
+        n = self._L.ref_ekfnode_state_queue(self._h, _d(rows), 1000)
+        return rows[:n]

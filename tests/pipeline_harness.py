@@ -270,8 +270,9 @@ class World:
         return local.astype(F32), tt.astype(F32)
 
 
-def run(arm, world, n_scans, imu_dt=0.01, latency=0.03):
-    """returns dict of per-scan arrays: icp pose, EKF pose (pos + quaternion) after the update, success flag, fitness"""
+def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0):
+    """returns dict of per-scan arrays: icp pose, EKF pose (pos + quaternion) after the update, success flag, fitness.
+    scan_offset shifts the scan stamps off the IMU grid (the reference selects odometry with exact `<` on the stamps)."""
     stored = arm.stored()
     t0 = world.t0
     T0 = world.pose(t0)
@@ -296,28 +297,31 @@ def run(arm, world, n_scans, imu_dt=0.01, latency=0.03):
             k_imu += 1
 
     for s in range(n_scans):
-        t_end = t0 + 0.1 * (s + 1)
+        t_end = t0 + 0.1 * (s + 1) + scan_offset
         t_cur = t_end - 0.1
         step_imu(t_end + latency)                                  # the result is applied `latency` after the scan end
         xyz, rel = world.scan(stored, t_end)
+        t_scan_end = t_cur + float(rel[-1])                        # d_time_scan_end_ = stamp + time of the last point (pcm.cpp:474)
         st = np.array([x[0] for x in imu_log])
         gy = np.array([x[1] for x in imu_log])
         sel = st >= t_cur - 0.05
-        # start / end odometry of the scan span (OdomDeskewInfo picks the first odom at/after each stamp)
-        od_s = next(o for o in deq_odom if o["t"] >= t_cur - 1e-9)
-        od_e = next((o for o in deq_odom if o["t"] >= t_end - 1e-9), deq_odom[-1])
+        # start / end odometry of the scan span: OdomDeskewInfo skips messages with stamp < scan start / scan end — exact
+        # comparisons on the doubles, no tolerance (pcm_matching.cpp:611-617, 640-647; checked against the node itself in
+        # tests/test_reference_build_node.py, where a tolerance here showed up as centimetres on stamps that coincide)
+        od_s = next(o for o in deq_odom if not o["t"] < t_cur)
+        od_e = next((o for o in deq_odom if not o["t"] < t_scan_end), deq_odom[-1])
         ps = np.concatenate([od_s["pos"], rot_to_vec(quat_to_R(od_s["quat"]))])
         pe = np.concatenate([od_e["pos"], rot_to_vec(quat_to_R(od_e["quat"]))])
-        tab = O.deskew_tables(st[sel], gy[sel], t_cur, t_end, ps, od_s["t"], pe, od_e["t"])
+        tab = O.deskew_tables(st[sel], gy[sel], t_cur, t_scan_end, ps, od_s["t"], pe, od_e["t"])
         und = arm.deskew(xyz, rel, tab)
-        sync = get_interpolated_pose(deq_odom, t_end)
+        sync = get_interpolated_pose(deq_odom, t_scan_end)
         T_init = sync.astype(np.float64)                           # tf_ego_to_lidar = identity (pcm_matching.cpp:266)
         pose, ok, fit, cov = arm.register(und, T_init)
         out["icp"].append(np.array(pose)); out["ok"].append(bool(ok)); out["fit"].append(float(fit)); out["t"].append(t_end)
         if ok:                                                     # pcm_matching.cpp:289-299
             c66 = arm.shape_covariance(pose[:3, :3], np.array(cov), fit)   # product / oracle implementation of the arm
             pc, rc = c66[:3, :3].copy(), c66[3:, 3:].copy()
-            meas = gnss_time_compensation(dict(t=t_end, pos=pose[:3, 3].copy(), quat=R_to_quat_wxyz(pose[:3, :3])), deq_state)
+            meas = gnss_time_compensation(dict(t=t_scan_end, pos=pose[:3, 3].copy(), quat=R_to_quat_wxyz(pose[:3, :3])), deq_state)
             if meas is not None:
                 arm.ekf.RunGnssUpdate(pekf.make_measurement(meas["t"], meas["pos"], meas["quat"], pc, rc, source=pekf.PCM))
         out["ego"].append(arm.ekf_pose())                          # raw filter pose (pos, quaternion) after the update

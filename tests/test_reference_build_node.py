@@ -210,3 +210,102 @@ def test_lidar_callback_end_to_end(raw_map, method):
     # and the pose is sensible: the node localised the scan (the synthetic scan is not motion-distorted, so the deskew itself
     # moves points by up to the 9 cm the vehicle travels during the sweep)
     assert np.linalg.norm(out["pos"] - p_end) < 0.15
+
+
+# ------------------------------------------------------------------------------------------------ the closed loop
+class PinnedSpanWorld(H.World):
+    """scans whose first / last per-point times are exactly 0 and float32(0.1): the node derives the scan end from the last
+    point's time, the harness takes it as given"""
+
+    def scan(self, stored, t_end, span=0.1):
+        xyz, tt = super().scan(stored, t_end, span)
+        tt[0], tt[-1] = np.float32(0.0), np.float32(span)
+        return xyz, tt
+
+
+def run_reference_nodes(raw_map, world, n_scans, ekf_cfg, imu_dt=0.01, latency=0.03, scan_offset=0.0):
+    """the same sensor stream as pipeline_harness.run, through the reference's own two ROS nodes with this function as the
+    middleware: IMU -> both nodes, EKF odometry -> PCM node, lidar -> PCM node, PCM odometry -> EKF node"""
+    pcm = R.PcmMatchingNode(raw_map, icp_method=O.AVGICP, max_fitness_score=2.0, max_thread=4, input_voxel_ds_m=0.001, input_max_dist=1000.0)
+    ekf = R.EkfLocalizationNode(ekf_cfg)
+    stored = None
+    t0 = world.t0
+    T0 = world.pose(t0)
+    ekf.pcm_init_odom(t0, T0[:3, 3], H.R_to_quat_wxyz(T0[:3, :3]))
+    out = dict(icp=[], ego=[], ok=[], t=[])
+    k_imu = 0
+
+    def step_imu(until):
+        nonlocal k_imu
+        while t0 + k_imu * imu_dt <= until + 1e-9:
+            t = t0 + k_imu * imu_dt
+            g, a = world.imu(t)
+            od = ekf.imu(t, g, a)
+            pcm.imu(t, g, a)
+            if od is not None:
+                pcm.odom(od["t"], od["pos"], od["quat"], od["vel_local"], od["rate"])
+            k_imu += 1
+
+    om = O.VoxelHashMap(1.0, 30)
+    om.AddPoints(raw_map)
+    stored = om.export()["pxyz"]
+    for s in range(n_scans):
+        t_end = t0 + 0.1 * (s + 1) + scan_offset
+        step_imu(t_end + latency)
+        xyz, rel = world.scan(stored, t_end)
+        res = pcm.cloud(t_end - 0.1, xyz, rel)
+        out["ok"].append(res is not None)
+        out["t"].append(t_end)
+        if res is not None:
+            T = np.eye(4)
+            T[:3, :3] = H.quat_to_R(res["quat_wxyz"])
+            T[:3, 3] = res["pos"]
+            out["icp"].append(T)
+            ekf.pcm_odom(res["stamp"], res["pos"], res["quat_wxyz"], res["cov"])
+        else:
+            out["icp"].append(np.full((4, 4), np.nan))
+        out["ego"].append(ekf.filter_pose())
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def test_gnss_time_compensation(raw_map):
+    from elimaloc_b200 import ekf as pekf
+    ekf = R.EkfLocalizationNode(pekf.make_ekf_config())
+    assert ekf.time_compensate(100.0, [0, 0, 0], [1, 0, 0, 0]) is None            # empty state queue
+    ekf.pcm_init_odom(100.0, [1.0, 2.0, 0.5], [1, 0, 0, 0])
+    for k in range(12):                                                            # leave the PCM-init phase
+        ekf.imu(100.0 + 0.01 * k, [0, 0, 0.2], [0.1, 0.3, 9.81])
+        ekf.pcm_odom(100.0 + 0.01 * k, [1.0, 2.0, 0.5], [1, 0, 0, 0], np.diag([0.01] * 3 + [1e-4] * 3))
+    for k in range(12, 80):
+        ekf.imu(100.0 + 0.01 * k, [0.01, -0.02, 0.2], [0.4, 0.3, 9.81])
+    rows = ekf.state_queue()
+    deq = [np.concatenate([r, np.zeros(19)]) for r in rows]
+    assert len(rows) > 50 and np.ptp(rows[:, 1]) > 1e-3 and np.ptp(rows[:, 6]) > 1e-3  # the filter moved and turned
+    q_in = H.R_to_quat_wxyz(synth.exp_so3([0.02, -0.01, 0.7]))
+    for t in (rows[0, 0] - 0.5, rows[10, 0], rows[30, 0] + 0.004, rows[-1, 0] - 0.0301, rows[-1, 0], rows[-1, 0] + 0.2):
+        got = ekf.time_compensate(t, [3.0, -1.0, 0.2], q_in)
+        want = H.gnss_time_compensation(dict(t=t, pos=np.array([3.0, -1.0, 0.2]), quat=q_in), deq)
+        assert (got is None) == (want is None), t
+        if got is not None:
+            assert got["t"] == want["t"] and np.abs(got["pos"] - want["pos"]).max() < 1e-12 and np.abs(got["quat"] - want["quat"]).max() < 1e-12, t
+
+
+@pytest.mark.parametrize("world_cls,offset", [(H.World, 0.0), (PinnedSpanWorld, 0.0037)])
+def test_closed_loop_on_the_reference_nodes_matches_the_harness(world_cls, offset):
+    """BASELINE config 5: deskew -> AVGICP -> time compensation -> EKF update at 10 Hz with a 100 Hz IMU, 16 scans, on the
+    reference's own two nodes (PcmMatching + EkfLocalization) against tests/pipeline_harness.run with the oracle arm — the
+    harness whose GPU arm tests/test_pipeline.py checks on the B200.  offset 0: scan stamps coincide with IMU / odometry
+    stamps, where the node's exact `<` comparisons decide which odometry sample is used."""
+    from elimaloc_b200 import ekf as pekf
+    box, n_scans = 30.0, 16  # the world of tests/test_pipeline.py::test_oracle_pipeline_tracks_the_truth
+    raw = synth.map_s(250_000, box)
+    ref = run_reference_nodes(raw, world_cls(box, 4096, seed=7), n_scans, pekf.make_ekf_config(), scan_offset=offset)
+    har = H.run(H.OracleArm(raw, {}), world_cls(box, 4096, seed=7), n_scans, scan_offset=offset)
+    assert ref["ok"].all() and har["ok"].all()
+    d_icp, d_ego = np.abs(ref["icp"] - har["icp"]).max(), np.abs(ref["ego"] - har["ego"]).max()
+    print("closed loop, reference nodes vs harness: max |d icp pose| %.3g, max |d filter pose| %.3g" % (d_icp, d_ego))
+    assert d_icp < 2e-5 and d_ego < 2e-5
+    # and both follow the true trajectory (AVGICP with 1 m voxels is a coarse estimator: decimetres)
+    w = world_cls(box, 4096, seed=7)
+    err = max(np.linalg.norm(ref["icp"][i][:3, 3] - w.pose(ref["t"][i])[:3, 3]) for i in range(n_scans))
+    assert err < 0.6
