@@ -2,7 +2,7 @@
 //
 // C entry points over the REFERENCE's own EkfAlgorithm (ekf_localization/src/ekf_algorithm.cpp + include/ekf_algorithm.hpp +
 // localization_interface/localization_functions.hpp / localization_struct.hpp, all compiled unmodified from /root/reference
-// against the stand-in headers of stubs/ and ros_stubs/), with the state / config / measurement layouts of oracle/ekf.hpp so
+// against the stand-in headers of stubs/ and node_stubs/), with the state / config / measurement layouts of oracle/ekf.hpp so
 // that tests/test_reference_build_ekf.py can compare the oracle's EKF member for member.
 // Built by oracle/Makefile into oracle/_ref/libref_ekf.so (git-ignored).
 #include <deque>

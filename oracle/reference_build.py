@@ -3,7 +3,7 @@
 ctypes front-end of oracle/_ref/libref.so: the REFERENCE's own registration.cpp + voxel_hash_map.{hpp,cpp}, compiled
 unmodified from /root/reference against the stand-in third-party headers in oracle/ref_build/stubs (Eigen3, oneTBB and PCL are
 absent from this image; see stubs/mini_eigen.hpp for what the stand-in does and does not preserve), and of
-oracle/_ref/libref_ekf.so: the reference's own ekf_algorithm.cpp built the same way (plus ref_build/ros_stubs), and of
+oracle/_ref/libref_ekf.so: the reference's own ekf_algorithm.cpp built the same way (plus ref_build/node_stubs), and of
 oracle/_ref/libref_node.so: the ROS node class of pcm_matching.cpp itself (plus ref_build/node_stubs: ROS, tf, PCL, boost).
 They are the pin of the oracle: tests/test_reference_build.py, test_reference_build_ekf.py and test_reference_build_node.py
 run the oracle and these libraries on the same seeded inputs.

@@ -1,6 +1,6 @@
 """The pin of the oracle's EKF: oracle/ekf.cpp against oracle/_ref/libref_ekf.so — the REFERENCE's own ekf_algorithm.cpp with
 ekf_algorithm.hpp, localization_functions.hpp and localization_struct.hpp, compiled unmodified from /root/reference against
-stand-in Eigen / ROS headers (oracle/ref_build/stubs, ros_stubs).  Runs without a GPU.
+stand-in Eigen / ROS headers (oracle/ref_build/stubs, node_stubs).  Runs without a GPU.
 
 The filter's members are read after every call and compared member for member: state vector, both quaternions, the whole
 27 x 27 covariance, timestamps, the initialised / stabilised flags, the PCM-init counter, return values, GetCurrentState.
