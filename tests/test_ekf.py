@@ -119,3 +119,35 @@ def test_gpu_ekf_guards_and_uninitialised_path():
     assert gs["predictions"] == os_["predictions"] and gs["updates"] == os_["updates"] == 6
     np.testing.assert_allclose(gs["P"], os_["P"], rtol=1e-9, atol=1e-13)
     np.testing.assert_allclose(gs["pos"], os_["pos"], rtol=1e-9, atol=1e-12)
+
+
+# ---- golden vectors generated by the REFERENCE's own EkfAlgorithm (tests/golden/make_golden_stages.py) ------------------------
+def load_reference_ekf(ckf):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_ekf_drive_ckf{ckf}.npz"))
+
+
+def check_against_reference_golden(f, state, ckf, slack=1.0):
+    g = load_reference_ekf(ckf)
+    snaps = np.array(drive(f))
+    np.testing.assert_allclose(snaps, g["snaps"], rtol=1e-9 * slack, atol=1e-10 * slack)
+    s = pekf.state_to_dict(state())
+    for k in ("pos", "rot", "vel", "gyro", "acc", "bg", "ba", "grav", "imu_rot"):
+        np.testing.assert_allclose(s[k], g[k], rtol=1e-9 * slack, atol=1e-11 * slack, err_msg=k)
+    np.testing.assert_allclose(s["P"], g["P"], rtol=1e-8 * slack, atol=1e-13 * slack)
+    for k in ("state_initialized", "yaw_initialized", "rotation_stabilized", "state_stabilized", "pcm_init_on_going", "pcm_update_count"):
+        assert s[k] == g[k], k
+
+
+@pytest.mark.parametrize("ckf", [1, 0])
+def test_oracle_ekf_matches_the_reference_golden(ckf):
+    o = O.EkfAlgorithm(pekf.make_ekf_config(use_complementary_filter=ckf), _capi.EkfState)
+    check_against_reference_golden(o, lambda: o.s, ckf)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ckf", [1, 0])
+def test_gpu_ekf_matches_the_reference_golden(ckf):
+    import elimaloc_b200 as E
+    g = E.EkfAlgorithm(pekf.make_ekf_config(use_complementary_filter=ckf), device=0)
+    check_against_reference_golden(g, g.state, ckf, slack=3.0)  # GPU-vs-oracle and oracle-vs-reference rounding add up
