@@ -30,14 +30,30 @@ def test_oracle_pipeline_tracks_the_truth():
     assert ekf_err < 1.5  # the filter free-runs on PCM updates only until 10 updates have passed (ekf_algorithm.cpp:189-194)
 
 
+GPU_WORLD = dict(m_raw=400_000, box=40.0, n_points=8192, seed=7, n_scans=30)
+
+
+def test_the_world_of_the_gpu_comparison_is_a_stable_one():
+    """The closed loop (AVGICP on 1 m voxels feeding an EKF that starts with zero velocity) is not stable in every synthetic
+    world: in some the reference algorithm itself loses track after ~20 scans (the reference's own two ROS nodes do exactly the
+    same, tests/test_reference_build_node.py), and a comparison of two arms inside a diverging loop measures chaos, not
+    parity.  The world of the GPU test below is one where the loop tracks with a comfortable margin for all 30 scans."""
+    raw = synth.map_s(GPU_WORLD["m_raw"], GPU_WORLD["box"])
+    world = H.World(GPU_WORLD["box"], GPU_WORLD["n_points"], seed=GPU_WORLD["seed"])
+    res = H.run(H.OracleArm(raw, EKF_KW), world, GPU_WORLD["n_scans"])
+    assert res["ok"].all()
+    e = truth_errors(world, res)
+    assert e.max() < 0.6 and e[-10:].max() < 0.35, e
+
+
 @pytest.mark.gpu
 def test_gpu_pipeline_matches_oracle_pipeline():
     """pose-trajectory diff GPU vs CPU reference port over 30 scans (3 s at 10 Hz, 100 Hz IMU).  Tolerance: 1e-4 relative
     on the pose (north star) — the translation is O(20 m), so 2e-3 m absolute; rotation entries 1e-4."""
-    raw = synth.map_s(400_000, 34.0)
+    raw = synth.map_s(GPU_WORLD["m_raw"], GPU_WORLD["box"])
     ga, oa = H.GpuArm(raw, EKF_KW), H.OracleArm(raw, EKF_KW)
-    rg = H.run(ga, H.World(34.0, 8192, seed=7), 30)
-    ro = H.run(oa, H.World(34.0, 8192, seed=7), 30)
+    rg = H.run(ga, H.World(GPU_WORLD["box"], GPU_WORLD["n_points"], seed=GPU_WORLD["seed"]), GPU_WORLD["n_scans"])
+    ro = H.run(oa, H.World(GPU_WORLD["box"], GPU_WORLD["n_points"], seed=GPU_WORLD["seed"]), GPU_WORLD["n_scans"])
     assert np.array_equal(rg["ok"], ro["ok"]) and ro["ok"].all()
     scale = np.abs(ro["icp"][:, :3, 3]).max()
     assert np.abs(rg["icp"][:, :3, 3] - ro["icp"][:, :3, 3]).max() <= 1e-4 * scale

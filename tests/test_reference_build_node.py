@@ -290,22 +290,22 @@ def test_gnss_time_compensation(raw_map):
             assert got["t"] == want["t"] and np.abs(got["pos"] - want["pos"]).max() < 1e-12 and np.abs(got["quat"] - want["quat"]).max() < 1e-12, t
 
 
-@pytest.mark.parametrize("world_cls,offset", [(H.World, 0.0), (PinnedSpanWorld, 0.0037)])
-def test_closed_loop_on_the_reference_nodes_matches_the_harness(world_cls, offset):
+@pytest.mark.parametrize("world_cls,offset,m_raw,box,n_points,n_scans", [(H.World, 0.0, 250_000, 30.0, 4096, 16), (PinnedSpanWorld, 0.0037, 250_000, 30.0, 4096, 16),
+                                                                         (H.World, 0.0, 400_000, 40.0, 8192, 30)])  # the last: the world of the GPU test
+def test_closed_loop_on_the_reference_nodes_matches_the_harness(world_cls, offset, m_raw, box, n_points, n_scans):
     """BASELINE config 5: deskew -> AVGICP -> time compensation -> EKF update at 10 Hz with a 100 Hz IMU, 16 scans, on the
     reference's own two nodes (PcmMatching + EkfLocalization) against tests/pipeline_harness.run with the oracle arm — the
     harness whose GPU arm tests/test_pipeline.py checks on the B200.  offset 0: scan stamps coincide with IMU / odometry
     stamps, where the node's exact `<` comparisons decide which odometry sample is used."""
     from elimaloc_b200 import ekf as pekf
-    box, n_scans = 30.0, 16  # the world of tests/test_pipeline.py::test_oracle_pipeline_tracks_the_truth
-    raw = synth.map_s(250_000, box)
-    ref = run_reference_nodes(raw, world_cls(box, 4096, seed=7), n_scans, pekf.make_ekf_config(), scan_offset=offset)
-    har = H.run(H.OracleArm(raw, {}), world_cls(box, 4096, seed=7), n_scans, scan_offset=offset)
+    raw = synth.map_s(m_raw, box)  # the worlds of tests/test_pipeline.py
+    ref = run_reference_nodes(raw, world_cls(box, n_points, seed=7), n_scans, pekf.make_ekf_config(), scan_offset=offset)
+    har = H.run(H.OracleArm(raw, {}), world_cls(box, n_points, seed=7), n_scans, scan_offset=offset)
     assert ref["ok"].all() and har["ok"].all()
     d_icp, d_ego = np.abs(ref["icp"] - har["icp"]).max(), np.abs(ref["ego"] - har["ego"]).max()
     print("closed loop, reference nodes vs harness: max |d icp pose| %.3g, max |d filter pose| %.3g" % (d_icp, d_ego))
     assert d_icp < 2e-5 and d_ego < 2e-5
     # and both follow the true trajectory (AVGICP with 1 m voxels is a coarse estimator: decimetres)
-    w = world_cls(box, 4096, seed=7)
+    w = world_cls(box, n_points, seed=7)
     err = max(np.linalg.norm(ref["icp"][i][:3, 3] - w.pose(ref["t"][i])[:3, 3]) for i in range(n_scans))
     assert err < 0.6
