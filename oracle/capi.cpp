@@ -308,4 +308,42 @@ void orc_shape_pcm_covariance(const double* R, const double* local_cov, double i
     }
 }
 
+// ---- the restated third-party kernels of smallmat.hpp on their own, for tests/test_oracle_kernels.py (checked against LAPACK
+// through numpy): everything row-major.
+void orc_k_inverse(int n, const double* a, double* out) {
+    if (n == 3) { M3 m; std::memcpy(m.m, a, sizeof m.m); const M3 r = inverse(m); std::memcpy(out, r.m, sizeof r.m); }
+    else if (n == 4) { M4 m; std::memcpy(m.m, a, sizeof m.m); const M4 r = inverse(m); std::memcpy(out, r.m, sizeof r.m); }
+    else if (n == 6) { M6 m; std::memcpy(m.m, a, sizeof m.m); const M6 r = inverse(m); std::memcpy(out, r.m, sizeof r.m); }
+}
+void orc_k_ldlt_solve(const double* a36, const double* b6, double* x6) {
+    M6 A; V6 b;
+    std::memcpy(A.m, a36, sizeof A.m);
+    std::memcpy(b.v, b6, sizeof b.v);
+    const V6 x = ldlt_solve(A, b);
+    std::memcpy(x6, x.v, sizeof x.v);
+}
+void orc_k_sym_eig3(const double* a9, double* w3, double* v9) {
+    M3 A, V;
+    std::memcpy(A.m, a9, sizeof A.m);
+    sym_eig3(A, w3, V);
+    std::memcpy(v9, V.m, sizeof V.m);
+}
+void orc_k_plane_regularize(const double* a9, double* out9, double* normal3) {
+    M3 A;
+    std::memcpy(A.m, a9, sizeof A.m);
+    V3 n;
+    const M3 r = plane_regularize(A, &n);
+    std::memcpy(out9, r.m, sizeof r.m);
+    normal3[0] = n.x; normal3[1] = n.y; normal3[2] = n.z;
+}
+void orc_k_angle_axis_to_rot(double angle, const double* axis3, double* r9) {
+    const M3 r = angle_axis_to_rot(angle, V3(axis3[0], axis3[1], axis3[2]));
+    std::memcpy(r9, r.m, sizeof r.m);
+}
+double orc_k_rot_angle(const double* r9) {
+    M3 R;
+    std::memcpy(R.m, r9, sizeof R.m);
+    return rot_angle(R);
+}
+
 }  // extern "C"
