@@ -149,3 +149,31 @@ def test_default_ini_config(world, method):
     assert ok == o["is_success"]
     assert rel_err(T, o["pose"]) < 1e-4
     assert abs(fit - o["fitness_score"]) <= 1e-6 * max(1.0, abs(o["fitness_score"]))
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_gpu_against_the_reference_sources_directly(world, method):
+    """no oracle in between: the CUDA path against oracle/_ref/libref.so — the reference's own registration.cpp /
+    voxel_hash_map.cpp compiled against stand-in third-party headers (built in the build container; the prebuilt file travels
+    to the GPU box).  Correspondences bit-equal, RunRegister with the reference's .ini knobs within the north-star tolerances."""
+    from oracle import reference_build as RB
+    if not RB.available():
+        pytest.skip("oracle/_ref/libref.so is not here")
+    if "rm" not in world:
+        rm = RB.VoxelHashMap(1.0, 30)
+        rm.AddPoints(synth.map_u(100_000, 21.5, origin=-6.0))
+        rm.CalVoxelCovAll()
+        rm.CalPointCovAll(0.4)
+        world["rm"] = rm
+    rm = world["rm"]
+    for T in (world["T0"], world["T_true"]):
+        gc, gt = world["greg"].correspondences(world["scan"], world["gm"], T, method, 5.0)
+        rc, rt = RB.correspondences(rm, world["scan"], T, method, 5.0)
+        assert np.array_equal(gc, rc) and np.array_equal(gt, rt), NAMES[method]
+    gcfg, rcfg = both_cfg(icp_method=method)
+    T, ok, fit, cov = world["greg"].RunRegister(world["scan"], world["gm"], world["T0"], gcfg, fitness_score=-1.0)
+    r = RB.Registration().RunRegister(world["scan"], rm, world["T0"], rcfg, fitness_in=-1.0)
+    assert ok == r["is_success"]
+    assert rel_err(T, r["pose"]) < 1e-4
+    assert abs(fit - r["fitness_score"]) <= 1e-6 * max(1.0, abs(r["fitness_score"]))
+    assert rel_err(cov, r["local_cov"]) < 1e-5
