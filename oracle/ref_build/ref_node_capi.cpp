@@ -55,6 +55,43 @@ pcl::PointCloud<PointXYZIT>::Ptr make_cloud(const float* xyz, const float* rel_t
 
 extern "C" {
 
+// what Init() published about the map: the voxel-map cloud (visualisation) and, for VGICP / AVGICP, one marker per voxel
+// covariance with more than 2 points (position = voxel mean, scale = 3 sqrt(eigenvalue + 0.01) by descending eigenvalue)
+size_t ref_node_init_map_cloud(float* xyz, size_t capacity) {
+    const auto* m = last_on<sensor_msgs::PointCloud2>("/app/loc/voxel_map_pc");
+    if (!m) return 0;
+    for (size_t i = 0; i < m->records.size() && i < capacity; ++i) { xyz[3 * i] = m->records[i].x; xyz[3 * i + 1] = m->records[i].y; xyz[3 * i + 2] = m->records[i].z; }
+    return m->records.size();
+}
+size_t ref_node_init_markers(double* pos_scale6, size_t capacity) {
+    const auto* m = last_on<visualization_msgs::MarkerArray>("/app/loc/voxel_map_cov");
+    if (!m) return 0;
+    for (size_t i = 0; i < m->markers.size() && i < capacity; ++i) {
+        const auto& k = m->markers[i];
+        const double v[6] = {k.pose.position.x, k.pose.position.y, k.pose.position.z, k.scale.x, k.scale.y, k.scale.z};
+        std::memcpy(pos_scale6 + 6 * i, v, sizeof v);
+    }
+    return m->markers.size();
+}
+
+// CallbackInitialPose (pcm_matching.cpp:356-447): an rviz pose (x, y, yaw) -> ground height from the map -> RunRegister on
+// the last lidar cloud -> /app/loc/pcm_init_odom.  Returns 1 and the published pose when the node published one.
+int ref_node_initial_pose(void* h, double x, double y, double z, double yaw, double* pos, double* quat_xyzw) {
+    Quiet q;
+    auto m = std::make_shared<geometry_msgs::PoseWithCovarianceStamped>();
+    m->pose.pose.position.x = x; m->pose.pose.position.y = y; m->pose.pose.position.z = z;
+    m->pose.pose.orientation.w = std::cos(0.5 * yaw); m->pose.pose.orientation.z = std::sin(0.5 * yaw);
+    m->pose.pose.orientation.x = 0.0; m->pose.pose.orientation.y = 0.0;
+    const size_t before = ros::Capture::get().by_topic["/app/loc/pcm_init_odom"].size();
+    static_cast<PcmMatching*>(h)->CallbackInitialPose(m);
+    if (ros::Capture::get().by_topic["/app/loc/pcm_init_odom"].size() == before) return 0;
+    const auto* o = last_on<nav_msgs::Odometry>("/app/loc/pcm_init_odom");
+    pos[0] = o->pose.pose.position.x; pos[1] = o->pose.pose.position.y; pos[2] = o->pose.pose.position.z;
+    quat_xyzw[0] = o->pose.pose.orientation.x; quat_xyzw[1] = o->pose.pose.orientation.y;
+    quat_xyzw[2] = o->pose.pose.orientation.z; quat_xyzw[3] = o->pose.pose.orientation.w;
+    return 1;
+}
+
 // config_dir must hold config/localization.ini and config/calibration.ini (the node reads $PWD/config/...); the map is what
 // the node would have loaded from its .pcd file.
 void* ref_node_create(const char* config_dir, const float* map_xyz, size_t n_map) {

@@ -26,6 +26,7 @@ _PCM = os.path.join(REFERENCE_ROOT, "src", "app", "localization", "pcm_matching"
 _SO_EKF = os.path.join(_HERE, "_ref", "libref_ekf.so")
 _SO_NODE = os.path.join(_HERE, "_ref", "libref_node.so")
 _SO_EKFNODE = os.path.join(_HERE, "_ref", "libref_ekfnode.so")
+_SO_NODE_ON_CUDA = os.path.join(_HERE, "_ref", "libref_node_on_cuda.so")
 _LIB = None
 
 
@@ -39,6 +40,20 @@ def available():
 
 def node_available():
     return (os.path.isfile(_SO_NODE) and os.path.isfile(_SO_EKFNODE)) or sources_present()
+
+
+def node_on_cuda_available():
+    return os.path.isfile(_SO_NODE_ON_CUDA) or sources_present()
+
+
+def build_node_on_cuda():
+    """The unmodified reference node compiled against shim/registration_shim.hpp and linked with the product library
+    (needs elimaloc_b200/libelimaloc_b200.so to be built first)."""
+    if sources_present():
+        subprocess.check_call(["make", "-C", _HERE, "-s", "_ref/libref_node_on_cuda.so", "_ref/libref_node_on_shim_host.so", "REFERENCE_ROOT=" + REFERENCE_ROOT])
+    if not os.path.isfile(_SO_NODE_ON_CUDA):
+        raise FileNotFoundError("oracle/_ref/libref_node_on_cuda.so is not built and the reference sources are not here")
+    return _SO_NODE_ON_CUDA
 
 
 def ekf_available():
@@ -371,11 +386,19 @@ class PcmMatchingNode:
     """The reference's ROS node class PcmMatching (pcm_matching.hpp:112-380), itself, with this wrapper as the middleware.
     Configuration goes through the node's own ini parser: the two files are written into a temporary $PWD/config."""
 
-    def __init__(self, map_xyz, lidar_xyz=(0.0, 0.0, 0.0), lidar_rpy_deg=(0.0, 0.0, 0.0), imu_rpy_deg=(0.0, 0.0, 0.0), **kw):
+    def __init__(self, map_xyz, lidar_xyz=(0.0, 0.0, 0.0), lidar_rpy_deg=(0.0, 0.0, 0.0), imu_rpy_deg=(0.0, 0.0, 0.0), on_cuda=False, **kw):
+        """on_cuda: the same unmodified node, but compiled against shim/registration_shim.hpp and linked with the product
+        library — its VoxelHashMap / Registration are then the CUDA drop-in (needs a GPU to do anything but fail softly)."""
         import tempfile
-        build()
-        if not os.path.isfile(_SO_NODE):
-            raise FileNotFoundError("oracle/_ref/libref_node.so is not built and the reference sources are not here")
+        if on_cuda:
+            so = build_node_on_cuda()
+            if on_cuda == "host":  # the shim with ELM_SHIM_DEVICE = -1: host-only map, registration fails softly
+                so = so.replace("libref_node_on_cuda.so", "libref_node_on_shim_host.so")
+        else:
+            build()
+            so = _SO_NODE
+        if not os.path.isfile(so):
+            raise FileNotFoundError(so + " is not built and the reference sources are not here")
         d = dict(scan_time_end=0, time_delay=0.0, voxel_size=1.0, voxel_max_point=30, run_deskew=1, input_max_dist=100.0, input_voxel_ds_m=1.5,
                  icp_method=1, max_thread=1, max_iteration=10, max_search_dist=5.0, lm_lambda=0.5, icp_termination_threshold_m=0.02,
                  min_overlap_ratio=0.4, max_fitness_score=0.5)
@@ -388,7 +411,7 @@ class PcmMatchingNode:
         with open(os.path.join(self._dir.name, "config", "calibration.ini"), "w") as f:
             f.write(CALIBRATION_INI.format(imu_rpy=" ".join(map(str, imu_rpy_deg)), lidar_xyz=" ".join(map(str, lidar_xyz)),
                                            lidar_rpy=" ".join(map(str, lidar_rpy_deg))))
-        L = C.CDLL(_SO_NODE)
+        L = C.CDLL(so)
         dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
         L.ref_node_create.restype = C.c_void_p
         L.ref_node_create.argtypes = [C.c_char_p, fp, C.c_size_t]
@@ -410,6 +433,11 @@ class PcmMatchingNode:
         L.ref_node_deskew_tables.argtypes = [C.c_void_p, dp, dp, dp, dp, ip, fp, dp]
         L.ref_node_interpolated_pose.argtypes = [C.c_void_p, C.c_double, fp]
         L.ref_node_shape_covariance.argtypes = [C.c_void_p, dp, dp, C.c_double, dp]
+        L.ref_node_init_map_cloud.restype = C.c_size_t
+        L.ref_node_init_map_cloud.argtypes = [fp, C.c_size_t]
+        L.ref_node_init_markers.restype = C.c_size_t
+        L.ref_node_init_markers.argtypes = [dp, C.c_size_t]
+        L.ref_node_initial_pose.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
         self._L = L
         m = _xyz(map_xyz)
         self._h = L.ref_node_create(self._dir.name.encode(), _f(m), m.shape[0])
@@ -421,6 +449,23 @@ class PcmMatchingNode:
 
     def map_points(self):
         return self._L.ref_node_map_points(self._h)
+
+    def init_publications(self):
+        """what Init() published: (voxel-map cloud [P, 3], covariance markers [V, 6] = position + scale); call before any
+        other node of the same library is created"""
+        n = self.map_points()
+        cloud = np.zeros((max(n, 1), 3), np.float32)
+        nc = self._L.ref_node_init_map_cloud(_f(cloud), cloud.shape[0])
+        mk = np.zeros((max(n, 1), 6))
+        nm = self._L.ref_node_init_markers(_d(mk), mk.shape[0])
+        return cloud[:nc], mk[:nm]
+
+    def initial_pose(self, x, y, yaw, z=0.0):
+        """CallbackInitialPose; returns dict(pos, quat_wxyz) of the published /app/loc/pcm_init_odom or None"""
+        pos, q = np.zeros(3), np.zeros(4)
+        if not self._L.ref_node_initial_pose(self._h, float(x), float(y), float(z), float(yaw), _d(pos), _d(q)):
+            return None
+        return dict(pos=pos, quat_wxyz=np.array([q[3], q[0], q[1], q[2]]))
 
     def imu(self, t, gyro, acc):
         g, a = np.ascontiguousarray(gyro, dtype=np.float64), np.ascontiguousarray(acc, dtype=np.float64)

@@ -1,8 +1,11 @@
 // registration_shim.hpp — drop-in for pcm_matching's registration.hpp / voxel_hash_map.hpp on top of the C ABI of
 // libelimaloc_b200.so, so that pcm_matching.cpp compiles UNCHANGED (it keeps calling local_map_.Init / AddPoints /
-// CalVoxelCovAll / CalPointCovAll and registration_.RunRegister exactly as at pcm_matching.cpp:82-101, 280-282,
-// 412-414).  Header-only; needs Eigen (the node already has it).  The build image has no Eigen/ROS: tests/test_shim.py
-// compiles it against a minimal stand-in (tests/mock_eigen) and runs the node's call sequence through it.
+// CalVoxelCovAll / CalPointCovAll / Pointcloud / Covariances / VoxelDownsample / FindGroundHeight and
+// registration_.Init / RunRegister / TransformPoints exactly as at pcm_matching.cpp:82-105, 258, 280-282, 308-312, 387,
+// 408-414).  Header-only; needs Eigen (the node already has it) and only its coefficient access, so it is independent of
+// Eigen's storage order.  The build image has no Eigen/ROS: tests/test_shim.py compiles it against a minimal stand-in
+// (tests/mock_eigen) and runs the node's call sequence through it, and tests/test_node_on_shim.py compiles the reference's
+// own, unmodified pcm_matching.cpp against it.
 //
 // Reference interface replaced:
 //   struct PointStruct / CovStruct          pcm_matching/include/voxel_hash_map.hpp:41-87   (layout kept)
@@ -11,8 +14,11 @@
 #pragma once
 #include <Eigen/Core>
 #include <Eigen/Dense>
+#include <cmath>
+#include <cstdint>
 #include <iostream>
 #include <stdexcept>
+#include <unordered_map>
 #include <vector>
 
 #include "elimaloc_b200.h"
@@ -97,10 +103,41 @@ struct VoxelHashMap {
         return found != 0;
     }
     std::vector<PointStruct> Pointcloud() const {  // visualisation only (pcm_matching.cpp:104)
+        if (!h_) return {};
         std::vector<float> xyz(3 * elm_map_num_points(h_));
         elm_map_export(h_, nullptr, nullptr, nullptr, nullptr, xyz.data(), nullptr, nullptr);
         std::vector<PointStruct> out(xyz.size() / 3);
         for (size_t i = 0; i < out.size(); ++i) out[i].pose = out[i].local = Eigen::Vector3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        return out;
+    }
+    std::vector<CovStruct> Covariances() const {  // visualisation only (pcm_matching.cpp:105): voxels with more than 2 points
+        std::vector<CovStruct> out;
+        if (!h_) return out;
+        const size_t nv = elm_map_num_voxels(h_);
+        std::vector<int32_t> counts(nv);
+        std::vector<double> vmean(3 * nv), vcov(9 * nv);
+        if (elm_map_export(h_, nullptr, counts.data(), vmean.data(), vcov.data(), nullptr, nullptr, nullptr) != ELM_OK) return out;
+        for (size_t v = 0; v < nv; ++v) {
+            if (counts[v] <= 2) continue;
+            CovStruct c;
+            for (int i = 0; i < 3; ++i) { c.mean(i) = vmean[3 * v + i]; for (int j = 0; j < 3; ++j) c.cov(i, j) = vcov[9 * v + 3 * i + j]; }
+            out.push_back(c);
+        }
+        return out;
+    }
+    // first point of every floor-keyed voxel (voxel_hash_map.hpp:260-283); survivors in input order (the reference emits
+    // them in hash-table order, which nothing downstream depends on beyond rounding).  Host work on a few thousand points.
+    std::vector<PointStruct> VoxelDownsample(const std::vector<PointStruct>& points, const double voxel_size) const {
+        struct Key { int64_t x, y, z; bool operator==(const Key& o) const { return x == o.x && y == o.y && z == o.z; } };
+        struct Hash { size_t operator()(const Key& k) const { return static_cast<size_t>(k.x * 73856093LL ^ k.y * 19349669LL ^ k.z * 83492791LL); } };
+        std::unordered_map<Key, bool, Hash> seen;
+        seen.reserve(points.size());
+        std::vector<PointStruct> out;
+        for (const PointStruct& p : points) {
+            const Key k{static_cast<int64_t>(std::floor(p.pose.x() / voxel_size)), static_cast<int64_t>(std::floor(p.pose.y() / voxel_size)),
+                        static_cast<int64_t>(std::floor(p.pose.z() / voxel_size))};
+            if (seen.emplace(k, true).second) out.push_back(p);
+        }
         return out;
     }
     elm_map* h_ = nullptr;
@@ -134,12 +171,10 @@ struct Registration {
         c.azimuth_variance_deg = m_config.azimuth_variance_deg;
         c.elevation_variance_deg = m_config.elevation_variance_deg;
         const std::vector<float> xyz = elm_shim::flatten(source_local);
-        const Eigen::Matrix<double, 4, 4, Eigen::RowMajor> T0 = initial_guess;  // the ABI is row-major
-        Eigen::Matrix<double, 4, 4, Eigen::RowMajor> T;
-        Eigen::Matrix<double, 6, 6, Eigen::RowMajor> cov;
+        double T0[16], T[16], cov[36];  // the ABI is row-major; coefficient access keeps this independent of Eigen's storage order
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T0[4 * i + j] = initial_guess(i, j);
         int32_t ok = 0;
-        const int st = elm_run_register(h_, voxel_map.h_, xyz.data(), source_local.size(), T0.data(), &c, T.data(), &ok,
-                                        &fitness_score, cov.data());
+        const int st = elm_run_register(h_, voxel_map.h_, xyz.data(), source_local.size(), T0, &c, T, &ok, &fitness_score, cov);
         if (st != ELM_OK) {  // CUDA / NCCL trouble degrades to the reference's soft failure (never throw)
             elm_shim::check(st);
             is_success = false;
@@ -147,8 +182,22 @@ struct Registration {
             return initial_guess;
         }
         is_success = ok != 0;
-        local_cov = cov;
-        return T;
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) local_cov(i, j) = cov[6 * i + j];
+        Eigen::Matrix4d out;
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out(i, j) = T[4 * i + j];
+        return out;
+    }
+    // registration.hpp:126-148 — host helpers of the node's visualisation clouds (pcm_matching.cpp:308, 312)
+    void TransformPoints(const Eigen::Matrix4d& T, std::vector<PointStruct>& points) const {
+        for (PointStruct& p : points) {
+            const double x = p.pose.x(), y = p.pose.y(), z = p.pose.z();
+            p.pose = Eigen::Vector3d(((T(0, 0) * x + T(0, 1) * y) + T(0, 2) * z) + T(0, 3), ((T(1, 0) * x + T(1, 1) * y) + T(1, 2) * z) + T(1, 3),
+                                     ((T(2, 0) * x + T(2, 1) * y) + T(2, 2) * z) + T(2, 3));
+        }
+    }
+    void TransformPoints(const Eigen::Matrix4d& T, const std::vector<PointStruct>& points, std::vector<PointStruct>& o_points) const {
+        o_points = points;
+        TransformPoints(T, o_points);
     }
     RegistrationConfig config_;
     elm_registration* h_ = nullptr;
