@@ -39,3 +39,15 @@ for m, name in enumerate(["P2P", "GICP", "VGICP", "AVGICP"]):
     lo, lr = O.Registration().linearize(scan, om, T, cfg), R.Registration().linearize(scan, rm, T, cfg)
     print(f"{name}: {len(idx)} pairs, emission order and targets identical = {same}; JTJ rel diff = "
           f"{np.abs(lo['JTJ'] - lr['JTJ']).max() / np.abs(lr['JTJ']).max():.3g}, JTr rel diff = {np.abs(lo['JTr'] - lr['JTr']).max() / np.abs(lr['JTr']).max():.3g}", flush=True)
+
+# ---- and the PRODUCT's host map builder (no GPU needed: device = -1) directly against the reference-sources build
+import elimaloc_b200 as E  # noqa: E402
+
+t = time.time()
+pm = E.VoxelHashMap(1.0, 30, device=-1); pm.AddPoints(raw); pm.CalVoxelCovAll(); pm.CalPointCovAll(0.4)
+print(f"product host builder (elimaloc_b200/csrc/host_map.cpp, device = -1): {time.time() - t:.1f} s", flush=True)
+pe, re_ = pm.export(True, True), rm.export()
+for k in ("keys", "counts", "pxyz"):
+    print(f"  {k}: identical = {np.array_equal(pe[k], re_[k])}")
+for k in ("vmean", "vcov", "pmean", "pcov"):
+    print(f"  {k}: max |diff| = {np.abs(pe[k] - re_[k]).max():.3g}")
