@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 from elimaloc_b200 import synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 from oracle import reference_build as R  # noqa: E402
