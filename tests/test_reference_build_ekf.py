@@ -123,3 +123,45 @@ def test_uninitialised_filter_runs_the_complementary_filter_once_yaw_is_known():
             assert fo.RunGnssUpdate(m) == fr.RunGnssUpdate(m)
         assert_same_state(fo, fr, where=f"step {k}")
     assert fr.s.yaw_initialized
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_event_streams(seed):
+    """irregular and repeated IMU stamps, a backwards stamp, measurements at random times with random covariances, large attitude
+    changes (yaw wrapping through +-pi, pitch pushed towards the gimbal-lock branch of RotToVec), re-initialisation by a second
+    PCM_INIT in the middle of the stream — every member compared after every event"""
+    rng = np.random.default_rng(500 + seed)
+    ckf, grav = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+    fo, fr = pair(use_complementary_filter=ckf, imu_estimate_gravity=grav, ekf_init_yaw_deg=float(rng.uniform(-180, 180)),
+                  ekf_init_pitch_deg=float(rng.uniform(-20, 20)))
+    t = 10.0
+    att = np.array([0.0, rng.uniform(-1.2, 1.2), rng.uniform(-3.1, 3.1)])   # roll, pitch, yaw of the "truth"
+    pos = rng.normal(0, 5, 3)
+    m0 = pekf.make_measurement(t, pos, quat_wxyz(synth.exp_so3([0, 0, att[2]]) @ synth.exp_so3([0, att[1], 0])), np.eye(3) * 1e-9, np.eye(3) * 1e-9,
+                               source=pekf.PCM_INIT)
+    assert fo.RunGnssUpdate(m0) == fr.RunGnssUpdate(m0)
+    for k in range(260):
+        ev = rng.random()
+        if ev < 0.70:                                            # IMU sample
+            dt = float(rng.choice([0.0, 1e-7, 0.005, 0.01, 0.01, 0.01, 0.05, -0.02]))
+            t += dt
+            gyro = rng.normal(0, 0.5, 3) * (3.0 if k % 40 < 5 else 1.0)
+            acc = np.array([0.0, 0.0, 9.81]) + rng.normal(0, 1.0, 3)
+            assert fo.RunPredictionImu(t, gyro, acc) == fr.RunPredictionImu(t, gyro, acc), k
+            att += gyro * max(dt, 0.0)
+        elif ev < 0.97:                                          # PCM pose
+            att[2] = (att[2] + np.pi) % (2 * np.pi) - np.pi
+            Rm = synth.exp_so3([0, 0, att[2]]) @ synth.exp_so3([0, np.clip(att[1], -1.5, 1.5), 0]) @ synth.exp_so3([att[0], 0, 0])
+            pc = np.diag(rng.uniform(1e-4, 0.5, 3))
+            rc = np.diag(rng.uniform(1e-6, 1e-2, 3))
+            m = pekf.make_measurement(t - float(rng.uniform(0, 0.05)), pos + rng.normal(0, 0.1, 3), quat_wxyz(Rm), pc, rc, source=pekf.PCM)
+            assert fo.RunGnssUpdate(m) == fr.RunGnssUpdate(m), k
+        else:                                                    # forced re-initialisation
+            m = pekf.make_measurement(t, pos, quat_wxyz(synth.exp_so3([0, 0, att[2]])), np.eye(3) * 1e-9, np.eye(3) * 1e-9, source=pekf.PCM_INIT)
+            assert fo.RunGnssUpdate(m) == fr.RunGnssUpdate(m), k
+        assert_same_state(fo, fr, tol=1e-8, where=f"seed {seed} event {k}")
+        if k % 20 == 19:
+            eo, er = fo.GetCurrentState(), fr.GetCurrentState()
+            assert np.abs(eo[:25] - er[:25]).max() <= 1e-8 * max(1.0, np.abs(er[:25]).max()), k
+    so = pekf.state_to_dict(fo.s)
+    assert np.isfinite(so["P"]).all() and np.isfinite(so["pos"]).all() and so["predictions"] > 40 and so["updates"] > 30
