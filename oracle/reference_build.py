@@ -368,11 +368,15 @@ ekf_can_meas_uncertainty_vel_mps = 2.0
 ekf_can_meas_uncertainty_yaw_rate_deg = 10.0
 ekf_bestvel_meas_uncertainty_vel_mps = 1.0
 """
-CALIBRATION_INI = """[Rear To Gps]
+EKF_CALIBRATION_INI = """[Rear To Imu]
 transform_xyz_m = 0.0 0.0 0.0
 rotation_rpy_deg = 0.0 0.0 0.0
 
-[Rear To Imu]
+[Rear To Gps]
+transform_xyz_m = 0.0 0.0 0.0
+rotation_rpy_deg = 0.0 0.0 0.0
+"""
+CALIBRATION_INI = """[Rear To Imu]
 transform_xyz_m = 0.0 0.0 0.0
 rotation_rpy_deg = {imu_rpy}
 
@@ -550,8 +554,7 @@ class EkfLocalizationNode:
             f.write("[common_variable]\ncan_topic_name = /can\nimu_topic_name = /imu/data\nnavsatfix_topic_name = /gps/fix\nprojection_mode = Cartesian\n")
             f.write(EKF_INI.format(**{k: repr(v) if isinstance(v, float) else v for k, v in d.items()}))
         with open(os.path.join(self._dir.name, "config", "calibration.ini"), "w") as f:
-            f.write(CALIBRATION_INI.format(imu_rpy="0.0 0.0 0.0", lidar_xyz="0.0 0.0 0.0", lidar_rpy="0.0 0.0 0.0").replace(
-                "[Rear To Imu]", "[Rear To Imu]\ntransform_xyz_m = 0.0 0.0 0.0", 1).replace("transform_xyz_m = 0.0 0.0 0.0\ntransform_xyz_m", "transform_xyz_m", 1))
+            f.write(EKF_CALIBRATION_INI)
         L = _fresh_cdll(_SO_EKFNODE)
         dp = C.POINTER(C.c_double)
         L.ref_ekfnode_create.restype = C.c_void_p
