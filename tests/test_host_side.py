@@ -108,11 +108,11 @@ def test_error_statuses_without_fallback():
 
 def test_product_does_not_import_the_oracle():
     """only tests/, smoke() and bench.py's CPU legs may touch oracle/"""
-    pkg = os.path.join(ROOT, "elimaloc_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
-                assert "oracle" not in open(os.path.join(dirpath, f), errors="replace").read().lower(), os.path.join(dirpath, f)
+    for pkg in (os.path.join(ROOT, "elimaloc_b200"), os.path.join(ROOT, "shim"), os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(pkg):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                    assert "oracle" not in open(os.path.join(dirpath, f), errors="replace").read().lower(), os.path.join(dirpath, f)
 
 
 @pytest.mark.parametrize("kind", ["dense_negative", "sparse_surface", "single_point", "incremental", "long_line", "two_far_clusters"])
