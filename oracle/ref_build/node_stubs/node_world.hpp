@@ -47,7 +47,7 @@ struct Duration {
     explicit Duration(double s) : sec(s) {}
     double toSec() const { return sec; }
 };
-struct Time {
+struct Time {  // real ROS stores integer sec / nsec, i.e. quantises a double stamp to 1 ns; the stand-in keeps the double
     double sec = 0.0;
     Time() {}
     explicit Time(double s) : sec(s) {}
