@@ -94,6 +94,8 @@ struct VoxelHashMap {
         const std::vector<float> xyz = elm_shim::flatten(points);
         elm_shim::check(elm_map_add_points(h_, xyz.data(), points.size()));
     }
+    void Update(const std::vector<PointStruct>& points, const Eigen::Vector3d& /*origin*/) { AddPoints(points); }  // voxel_hash_map.cpp:268
+    void Clear() { Init(voxel_size_, max_points_per_voxel_); }                                                       // voxel_hash_map.hpp:324
     void CalVoxelCovAll() { elm_shim::check(elm_map_cal_voxel_cov(h_)); }
     void CalPointCovAll(double d_search_dist) { elm_shim::check(elm_map_cal_point_cov(h_, d_search_dist)); }
     bool Empty() const { return !h_ || elm_map_empty(h_); }
