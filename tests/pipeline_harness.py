@@ -175,6 +175,36 @@ def gnss_time_compensation(meas, deq_state):
     return dict(t=cur[0], pos=meas["pos"] + d[:3], quat=q / np.linalg.norm(q))
 
 
+def deskew_odometry_span(deq, t_cur, t_scan_end):
+    """OdomDeskewInfo's choice of the two poses the sweep is interpolated between (pcm_matching.cpp:587-729), as
+    (pose6 start, stamp start, pose6 end, stamp end) with pose6 = x, y, z, roll, pitch, yaw; None when the node refuses
+    (empty queue, or its first message is newer than the scan start).  Start: the first message not older than the scan
+    start.  End: the first message not older than the scan end if the queue reaches beyond it, otherwise the LATEST message
+    integrated forward with its own twist (local linear velocity rotated by its attitude, Euler rates added to the angles)."""
+    if not deq or deq[0]["t"] > t_cur:
+        return None
+    s = deq[-1]
+    for o in deq:
+        s = o
+        if not o["t"] < t_cur:
+            break
+    ps = np.concatenate([s["pos"], rot_to_vec(quat_to_R(s["quat"]))])
+    if deq[-1]["t"] > t_scan_end:
+        e = deq[-1]
+        for o in deq:
+            e = o
+            if not o["t"] < t_scan_end:
+                break
+        return ps, s["t"], np.concatenate([e["pos"], rot_to_vec(quat_to_R(e["quat"]))]), e["t"]
+    last = deq[-1]
+    dt = t_scan_end - last["t"]
+    r, p, y = rot_to_vec(quat_to_R(last["quat"]))
+    pos = last["pos"] + rpy_to_R(r, p, y) @ last["vel_local"] * dt
+    rpy = np.array([r, p, y]) + last["rate"] * dt
+    rpy = np.array(rot_to_vec(rpy_to_R(*rpy)))  # the node goes through a quaternion (setRPY) and back (getRPY)
+    return ps, s["t"], np.concatenate([pos, rpy]), t_scan_end
+
+
 # ------------------------------------------------------------------------------------------------ arms
 class OracleArm:
     name = "oracle"
@@ -308,11 +338,8 @@ def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0):
         # start / end odometry of the scan span: OdomDeskewInfo skips messages with stamp < scan start / scan end — exact
         # comparisons on the doubles, no tolerance (pcm_matching.cpp:611-617, 640-647; checked against the node itself in
         # tests/test_reference_build_node.py, where a tolerance here showed up as centimetres on stamps that coincide)
-        od_s = next(o for o in deq_odom if not o["t"] < t_cur)
-        od_e = next((o for o in deq_odom if not o["t"] < t_scan_end), deq_odom[-1])
-        ps = np.concatenate([od_s["pos"], rot_to_vec(quat_to_R(od_s["quat"]))])
-        pe = np.concatenate([od_e["pos"], rot_to_vec(quat_to_R(od_e["quat"]))])
-        tab = O.deskew_tables(st[sel], gy[sel], t_cur, t_scan_end, ps, od_s["t"], pe, od_e["t"])
+        ps, ts, pe, te = deskew_odometry_span(deq_odom, t_cur, t_scan_end)
+        tab = O.deskew_tables(st[sel], gy[sel], t_cur, t_scan_end, ps, ts, pe, te)
         und = arm.deskew(xyz, rel, tab)
         sync = get_interpolated_pose(deq_odom, t_scan_end)
         T_init = sync.astype(np.float64)                           # tf_ego_to_lidar = identity (pcm_matching.cpp:266)

@@ -309,3 +309,36 @@ def test_closed_loop_on_the_reference_nodes_matches_the_harness(world_cls, offse
     w = world_cls(box, n_points, seed=7)
     err = max(np.linalg.norm(ref["icp"][i][:3, 3] - w.pose(ref["t"][i])[:3, 3]) for i in range(n_scans))
     assert err < 0.6
+
+
+@pytest.mark.parametrize("last_odom_k", [7, 12, 30])
+def test_deskew_odometry_span_incl_the_integrate_branch(raw_map, last_odom_k):
+    """OdomDeskewInfo's two poses: when the odometry queue ends BEFORE the scan end the node integrates the latest message forward
+    with its own twist (pcm_matching.cpp:648-706) — the harness' deskew_odometry_span against the node's resulting increments"""
+    node = R.PcmMatchingNode(raw_map[:100])
+    deq, stamps, gyro = [], [], []
+    for k in range(-5, 30):
+        t = T0 + 0.01 * k
+        p, rpy = ego_pose(t, (2.0, 1.0, 0.5))
+        q = tf_quat_from_rpy(*rpy)
+        if k <= last_odom_k:
+            node.odom(t, p, q, lin=(0.9, 0.05, -0.02), ang=(0.01, -0.02, 0.3))
+            deq.append(dict(t=t, pos=p, quat=q, vel_local=np.array([0.9, 0.05, -0.02]), rate=np.array([0.01, -0.02, 0.3])))
+        g = [0.01, -0.02, 0.3]
+        node.imu(t + 0.003, g, [0.0, 0.0, 9.81])
+        stamps.append(t + 0.003)
+        gyro.append(g)
+    n = 500
+    xyz = synth.scan_u(n, 30.0, seed=1)
+    rel = np.linspace(0.0, 0.1, n).astype(np.float32)
+    t_cur = T0 + 0.05
+    t_end = t_cur + float(rel[-1])
+    ok, und, tab = node.deskew(t_cur, xyz, rel)
+    span = H.deskew_odometry_span(deq, t_cur, t_end)
+    assert ok == (span is not None)
+    if span is None:
+        return
+    assert (deq[-1]["t"] > t_end) == (last_odom_k == 30)                     # 7, 12: the integrate branch; 30: interpolation
+    ot = O.deskew_tables(np.array(stamps), np.array(gyro), t_cur, t_end, *span)
+    assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 2e-7
+    assert np.abs(und - O.deskew_points(ot, xyz, rel)).max() < 2e-5
