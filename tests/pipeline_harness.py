@@ -225,6 +225,9 @@ class OracleArm:
     def deskew(self, xyz, rel, tab):
         return O.deskew_points(tab, xyz, rel)
 
+    def downsample(self, xyz, voxel_size):
+        return xyz[O.scan_preprocess(xyz, 0.0, voxel_size)]
+
     def register(self, scan, T0):
         r = self.reg.RunRegister(scan, self.map, T0, self.cfg)
         return r["pose"], r["is_success"], r["fitness_score"], r["local_cov"]
@@ -255,6 +258,9 @@ class GpuArm:
 
     def deskew(self, xyz, rel, tab):
         return self.reg.DeskewPoints(xyz, rel, tab)
+
+    def downsample(self, xyz, voxel_size):
+        return self.reg.PreprocessScan(xyz, 0.0, voxel_size)[0]
 
     def register(self, scan, T0):
         return self.reg.RunRegister(scan, self.map, T0, self.cfg)
@@ -300,9 +306,11 @@ class World:
         return local.astype(F32), tt.astype(F32)
 
 
-def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0):
+def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0, input_voxel_ds_m=0.0):
     """returns dict of per-scan arrays: icp pose, EKF pose (pos + quaternion) after the update, success flag, fitness.
-    scan_offset shifts the scan stamps off the IMU grid (the reference selects odometry with exact `<` on the stamps)."""
+    scan_offset shifts the scan stamps off the IMU grid (the reference selects odometry with exact `<` on the stamps);
+    input_voxel_ds_m > 0 keeps the first point of every voxel of that size before the registration, as the node does
+    (VoxelDownsample, pcm_matching.cpp:257-258; localization.ini: 1.5 m) — off by default."""
     stored = arm.stored()
     t0 = world.t0
     T0 = world.pose(t0)
@@ -341,6 +349,8 @@ def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0):
         ps, ts, pe, te = deskew_odometry_span(deq_odom, t_cur, t_scan_end)
         tab = O.deskew_tables(st[sel], gy[sel], t_cur, t_scan_end, ps, ts, pe, te)
         und = arm.deskew(xyz, rel, tab)
+        if input_voxel_ds_m > 0.0:
+            und = arm.downsample(und, input_voxel_ds_m)
         sync = get_interpolated_pose(deq_odom, t_scan_end)
         T_init = sync.astype(np.float64)                           # tf_ego_to_lidar = identity (pcm_matching.cpp:266)
         pose, ok, fit, cov = arm.register(und, T_init)

@@ -223,10 +223,10 @@ class PinnedSpanWorld(H.World):
         return xyz, tt
 
 
-def run_reference_nodes(raw_map, world, n_scans, ekf_cfg, imu_dt=0.01, latency=0.03, scan_offset=0.0):
+def run_reference_nodes(raw_map, world, n_scans, ekf_cfg, imu_dt=0.01, latency=0.03, scan_offset=0.0, input_voxel_ds_m=0.001):
     """the same sensor stream as pipeline_harness.run, through the reference's own two ROS nodes with this function as the
     middleware: IMU -> both nodes, EKF odometry -> PCM node, lidar -> PCM node, PCM odometry -> EKF node"""
-    pcm = R.PcmMatchingNode(raw_map, icp_method=O.AVGICP, max_fitness_score=2.0, max_thread=4, input_voxel_ds_m=0.001, input_max_dist=1000.0)
+    pcm = R.PcmMatchingNode(raw_map, icp_method=O.AVGICP, max_fitness_score=2.0, max_thread=4, input_voxel_ds_m=input_voxel_ds_m, input_max_dist=1000.0)
     ekf = R.EkfLocalizationNode(ekf_cfg)
     stored = None
     t0 = world.t0
@@ -290,21 +290,23 @@ def test_gnss_time_compensation(raw_map):
             assert got["t"] == want["t"] and np.abs(got["pos"] - want["pos"]).max() < 1e-12 and np.abs(got["quat"] - want["quat"]).max() < 1e-12, t
 
 
-@pytest.mark.parametrize("world_cls,offset,m_raw,box,n_points,n_scans", [(H.World, 0.0, 250_000, 30.0, 4096, 16), (PinnedSpanWorld, 0.0037, 250_000, 30.0, 4096, 16),
-                                                                         (H.World, 0.0, 400_000, 40.0, 8192, 30)])  # the last: the world of the GPU test
-def test_closed_loop_on_the_reference_nodes_matches_the_harness(world_cls, offset, m_raw, box, n_points, n_scans):
+@pytest.mark.parametrize("world_cls,offset,m_raw,box,n_points,n_scans,ds", [(H.World, 0.0, 250_000, 30.0, 4096, 16, 0.0), (PinnedSpanWorld, 0.0037, 250_000, 30.0, 4096, 16, 0.0),
+                                                                            (H.World, 0.0, 400_000, 40.0, 8192, 30, 0.0),   # the world of the GPU test
+                                                                            (H.World, 0.0, 400_000, 40.0, 8192, 30, 1.5)])  # with the node's default down-sampling
+def test_closed_loop_on_the_reference_nodes_matches_the_harness(world_cls, offset, m_raw, box, n_points, n_scans, ds):
     """BASELINE config 5: deskew -> AVGICP -> time compensation -> EKF update at 10 Hz with a 100 Hz IMU, 16 scans, on the
     reference's own two nodes (PcmMatching + EkfLocalization) against tests/pipeline_harness.run with the oracle arm — the
     harness whose GPU arm tests/test_pipeline.py checks on the B200.  offset 0: scan stamps coincide with IMU / odometry
     stamps, where the node's exact `<` comparisons decide which odometry sample is used."""
     from elimaloc_b200 import ekf as pekf
     raw = synth.map_s(m_raw, box)  # the worlds of tests/test_pipeline.py
-    ref = run_reference_nodes(raw, world_cls(box, n_points, seed=7), n_scans, pekf.make_ekf_config(), scan_offset=offset)
-    har = H.run(H.OracleArm(raw, {}), world_cls(box, n_points, seed=7), n_scans, scan_offset=offset)
+    ref = run_reference_nodes(raw, world_cls(box, n_points, seed=7), n_scans, pekf.make_ekf_config(), scan_offset=offset, input_voxel_ds_m=ds or 0.001)
+    har = H.run(H.OracleArm(raw, {}), world_cls(box, n_points, seed=7), n_scans, scan_offset=offset, input_voxel_ds_m=ds)
     assert ref["ok"].all() and har["ok"].all()
     d_icp, d_ego = np.abs(ref["icp"] - har["icp"]).max(), np.abs(ref["ego"] - har["ego"]).max()
     print("closed loop, reference nodes vs harness: max |d icp pose| %.3g, max |d filter pose| %.3g" % (d_icp, d_ego))
-    assert d_icp < 2e-5 and d_ego < 2e-5
+    tol = 2e-5 if ds == 0.0 else 1e-4  # down-sampled: the node feeds the survivors in hash-table order, the harness in input order
+    assert d_icp < tol and d_ego < tol
     # and both follow the true trajectory (AVGICP with 1 m voxels is a coarse estimator: decimetres)
     w = world_cls(box, n_points, seed=7)
     err = max(np.linalg.norm(ref["icp"][i][:3, 3] - w.pose(ref["t"][i])[:3, 3]) for i in range(n_scans))
