@@ -347,3 +347,56 @@ def test_deskew_odometry_span_incl_the_integrate_branch(raw_map, last_odom_k):
     ot = O.deskew_tables(np.array(stamps), np.array(gyro), t_cur, t_end, *span)
     assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 2e-7
     assert np.abs(und - O.deskew_points(ot, xyz, rel)).max() < 2e-5
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_randomised_deskew_streams(raw_map, seed):
+    """irregular IMU and odometry rates, gaps, scan spans of different length, both stamp conventions, queues that start late or
+    end early: the node's decision (deskew or refuse), its tables and its undistorted cloud against the oracle + the harness'
+    odometry selection"""
+    rng = np.random.default_rng(900 + seed)
+    mode = int(rng.integers(0, 2))
+    node = R.PcmMatchingNode(raw_map[:100], scan_time_end=mode)
+    span = float(rng.uniform(0.03, 0.12))
+    t_cur = T0 + float(rng.uniform(0.02, 0.08))
+    deq, stamps, gyro = [], [], []
+    t = T0 - 0.1 + float(rng.uniform(0.0, 0.2))                        # sometimes the odometry starts after the scan start
+    t_stop = t_cur + span + float(rng.uniform(-0.03, 0.06))           # sometimes it ends before the scan end
+    while t < t_stop:
+        p, rpy = ego_pose(t, (2.0, 1.0, 0.5))
+        q = tf_quat_from_rpy(*rpy)
+        lin, ang = rng.normal(0, 1.0, 3), rng.normal(0, 0.2, 3)
+        node.odom(t, p, q, lin=lin, ang=ang)
+        deq.append(dict(t=t, pos=p, quat=q, vel_local=lin, rate=ang))
+        t += float(rng.choice([0.005, 0.01, 0.02, 0.035]))
+    t = T0 - 0.05
+    while t < t_cur + span + 0.05:
+        g = rng.normal(0, 0.3, 3)
+        node.imu(t, g, [0.0, 0.0, 9.81])
+        stamps.append(t)
+        gyro.append(g)
+        t += float(rng.choice([0.002, 0.005, 0.01, 0.025]))
+    n = 800
+    xyz = synth.scan_u(n, 40.0, seed=seed)
+    rel = np.sort(rng.random(n).astype(np.float32) * np.float32(span))
+    if mode:  # stamp = scan end, per-point times <= 0
+        rel_in, stamp_in = (rel - rel[-1]).astype(np.float32), t_cur + float(rel[-1])
+        t_end = stamp_in
+        t_start = t_end + float(rel_in[0])
+        rel_eff = (rel_in - rel_in[0]).astype(np.float32)
+    else:
+        rel_in, stamp_in, t_start, t_end, rel_eff = rel, t_cur, t_cur, t_cur + float(rel[-1]), rel
+    ok, und, tab = node.deskew(stamp_in, xyz, rel_in)
+    sp = H.deskew_odometry_span(deq, t_start, t_end)
+    ot = O.deskew_tables(np.array(stamps), np.array(gyro), t_start, t_end, *(sp if sp is not None else (None, 0.0, None, 0.0)))
+    if sp is None:
+        assert not ok and not tab["odom_available"]
+        return
+    assert ok == (ot["imu_available"] and ot["odom_available"])
+    assert tab["imu_pointer_cur"] == ot["imu_pointer_cur"]
+    if ok:
+        k = tab["imu_pointer_cur"]
+        for name in ("imu_time", "imu_rot_x", "imu_rot_y", "imu_rot_z"):
+            assert np.abs(ot[name][:k + 1] - tab[name][:k + 1]).max() < 1e-14, name
+        assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 5e-7
+        assert np.array_equal(und, O.deskew_points(tab, xyz, rel_eff))
