@@ -123,3 +123,29 @@ def test_unmodified_node_on_cuda_publishes_what_the_reference_node_publishes(raw
     assert (ia is None) == (ib is None)
     if ia is not None:
         assert np.abs(ia["pos"] - ib["pos"]).max() <= 1e-4 * np.abs(ia["pos"]).max()
+
+
+def test_shim_host_helpers(tmp_path):
+    """VoxelDownsample and TransformPoints of the shim (host code the node calls around RunRegister) against the oracle:
+    the first point of every floor-keyed voxel in input order; the transform moves `pose` and leaves `local` alone"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "shim_helpers_check")
+    lib_dir = os.path.join(root, "elimaloc_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(root, "oracle", "ref_build", "stubs"), "-I" + os.path.join(root, "shim"),
+                    "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "shim_helpers_check.cpp"), "-o", exe,
+                    os.path.join(lib_dir, "libelimaloc_b200.so"), "-Wl,-rpath," + lib_dir], check=True, capture_output=True, text=True)
+    rng = np.random.default_rng(12)
+    xyz = ((rng.random((20_000, 3)) - 0.5) * 40).astype(np.float32)
+    xyz.tofile(str(tmp_path / "pts.f32"))
+    for voxel in (1.5, 0.5):
+        out = subprocess.run([exe, str(tmp_path / "pts.f32"), str(len(xyz)), repr(voxel)], check=True, capture_output=True, text=True).stdout.split("\n")
+        k = int(out[0])
+        idx = np.array([int(v) for v in out[1:1 + k]])
+        want = O.scan_preprocess(xyz, 0.0, voxel)
+        assert np.array_equal(idx, want)
+        for line, i in zip(out[1 + k:1 + k + 5], want[:5]):
+            v = [float(t) for t in line.split()]
+            p = xyz[i].astype(np.float64)
+            assert np.allclose(v[:3], [-p[1] + 1.5, p[0] - 2.5, p[2] + 0.25], rtol=0, atol=1e-12)   # pose moved
+            assert v[3] == v[0] and v[4] == p[0] and v[5] == p[0] and int(v[6]) == i              # in-place variant; local, input untouched
