@@ -169,7 +169,8 @@ def compare_runs(ro, rr, lm_lambda=0.5, pose_tol=1e-10):
     for k in range(rr["n_iter"]):  # per iteration: the reference's regularised system vs the oracle's raw sums
         A = ro["trace"]["JTJ"][k] + lm_lambda * np.diag(np.diag(ro["trace"]["JTJ"][k]))
         assert np.abs(A - rr["trace"]["A"][k]).max() <= 1e-9 * np.abs(A).max(), k
-        assert np.abs(ro["trace"]["JTr"][k] - rr["trace"]["b"][k]).max() <= 1e-9 * max(1.0, np.abs(rr["trace"]["b"][k]).max()), k
+        # Jtr cancels to ~0 at convergence while its terms stay as large as the entries of JtJ: the rounding scale is |A|, not |b|
+        assert np.abs(ro["trace"]["JTr"][k] - rr["trace"]["b"][k]).max() <= 1e-9 * max(1.0, np.abs(rr["trace"]["b"][k]).max()) + 1e-12 * np.abs(A).max(), k
 
 
 @pytest.mark.parametrize("method", METHODS)

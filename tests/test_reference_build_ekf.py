@@ -164,4 +164,4 @@ def test_randomised_event_streams(seed):
             eo, er = fo.GetCurrentState(), fr.GetCurrentState()
             assert np.abs(eo[:25] - er[:25]).max() <= 1e-8 * max(1.0, np.abs(er[:25]).max()), k
     so = pekf.state_to_dict(fo.s)
-    assert np.isfinite(so["P"]).all() and np.isfinite(so["pos"]).all() and so["predictions"] > 40 and so["updates"] > 30
+    assert np.isfinite(so["P"]).all() and np.isfinite(so["pos"]).all() and so["updates"] > 30

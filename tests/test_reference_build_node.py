@@ -398,5 +398,9 @@ def test_randomised_deskew_streams(raw_map, seed):
         k = tab["imu_pointer_cur"]
         for name in ("imu_time", "imu_rot_x", "imu_rot_y", "imu_rot_z"):
             assert np.abs(ot[name][:k + 1] - tab[name][:k + 1]).max() < 1e-14, name
-        assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 5e-7
+        # float32 increments: when the two odometry samples are closer in time than the sweep is long the interpolation ratio
+        # exceeds 1 and amplifies the float32 rounding of their difference (the node and the oracle round differently: the node's
+        # angles go through a quaternion and back)
+        ratio = (t_end - t_start) / max(sp[3] - sp[1], 1e-9)
+        assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 5e-7 * max(1.0, ratio)
         assert np.array_equal(und, O.deskew_points(tab, xyz, rel_eff))
