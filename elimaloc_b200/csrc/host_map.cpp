@@ -107,10 +107,13 @@ void plane_regularize(const double cov[9], double out[9], double normal[3]) {
         n[0] = 0; n[1] = 0; n[2] = 1;
     } else if (std::fabs(w[1] - w[0]) <= tol) {  // rank-1-like: null space is a plane -> fixed completion
         const double u[3] = {v[0][2], v[1][2], v[2][2]};
+        // axis least aligned with u; components within 1e-9 of each other count as tied (lowest axis wins), so that the choice
+        // does not hinge on the last bits of u when the dominant direction is a lattice diagonal
+        constexpr double kAxisTie = 1e-9;
         int k = 0;
         double best = std::fabs(u[0]);
-        if (std::fabs(u[1]) < best) { best = std::fabs(u[1]); k = 1; }
-        if (std::fabs(u[2]) < best) { best = std::fabs(u[2]); k = 2; }
+        if (std::fabs(u[1]) < best - kAxisTie) { best = std::fabs(u[1]); k = 1; }
+        if (std::fabs(u[2]) < best - kAxisTie) { best = std::fabs(u[2]); k = 2; }
         double e[3] = {0, 0, 0};
         e[k] = 1.0;
         const double d = u[k];

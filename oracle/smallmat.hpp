@@ -235,7 +235,7 @@ inline void sym_eig3(const M3& A_in, double w[3], M3& V) {
 // implementation-defined; ORACLE CONVENTION (shared with the product, documented in DESIGN.md):
 //   * all three equal within tol (incl. the zero matrix)      -> n = e_z     (Eigen gives U = I here)
 //   * two smallest equal within tol, dominant direction u1    -> n = normalise(e_k - (e_k.u1) u1),
-//     k = axis with the smallest |u1_k| (lowest k on ties)
+//     k = axis with the smallest |u1_k| (lowest k on ties; components within 1e-9 of each other are tied)
 // tol = 1e-9 * max(lambda_max, 1e-300).
 inline M3 plane_regularize(const M3& cov, V3* normal_out = nullptr) {
     double w[3];
@@ -248,10 +248,11 @@ inline M3 plane_regularize(const M3& cov, V3* normal_out = nullptr) {
         n = V3(0, 0, 1);
     } else if (std::fabs(w[1] - w[0]) <= tol) {
         const V3 u1(V(0, 2), V(1, 2), V(2, 2));
+        const double kAxisTie = 1e-9;  // |u1_k| within 1e-9 of each other are tied: the lowest axis wins (robust to the last bits of u1)
         int k = 0;
         double best = std::fabs(u1.x);
-        if (std::fabs(u1.y) < best) { best = std::fabs(u1.y); k = 1; }
-        if (std::fabs(u1.z) < best) { best = std::fabs(u1.z); k = 2; }
+        if (std::fabs(u1.y) < best - kAxisTie) { best = std::fabs(u1.y); k = 1; }
+        if (std::fabs(u1.z) < best - kAxisTie) { best = std::fabs(u1.z); k = 2; }
         V3 e(k == 0, k == 1, k == 2);
         const double d = dot(e, u1);
         V3 v = e - d * u1;
