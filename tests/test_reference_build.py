@@ -375,3 +375,29 @@ def test_product_host_map_builder_on_lattices_and_duplicates(seed):
             assert np.array_equal(pe[key], other[key]), key
         for key in ("vmean", "vcov", "pmean", "pcov"):
             assert np.abs(pe[key] - other[key]).max() < 1e-9, key
+
+
+def test_searches_on_lattice_maps_and_lattice_queries():
+    """exact ties everywhere: maps and queries on half- / quarter-voxel lattices (random insertion order, caps that fill up,
+    boxes on both sides of the origin, lattice-preserving poses), all four methods, two gate distances"""
+    total = 0
+    for seed in range(24):
+        rng = np.random.default_rng(3000 + seed)
+        vs = float(rng.choice([0.5, 1.0, 2.0]))
+        cap = int(rng.choice([2, 8, 30]))
+        step = vs / float(rng.choice([2, 4]))
+        n = int(rng.integers(500, 6000))
+        box = float(rng.uniform(3, 9)) * vs
+        origin = float(rng.choice([-0.5 * box, -box - 0.25, 0.0]))
+        raw = np.round(synth.map_u(n, box, seed=seed, origin=origin) / step).astype(np.float32) * np.float32(step)
+        raw = raw[rng.permutation(len(raw))]
+        om, rm = build_both(raw, vs, cap, radius=0.6 * vs)
+        q = np.round(synth.scan_u(400, 0.7 * box, seed=seed) / (step / 2)).astype(np.float32) * np.float32(step / 2) + np.float32(origin + 0.5 * box)
+        pose = synth.se3([step, -step, 0.0], [0, 0, np.pi / 2]) if seed % 3 == 0 else np.eye(4)
+        for method in METHODS:
+            for md in (0.7 * vs, 5.0):
+                co, to = O.correspondences(om, q, pose, method, md)
+                cr, tr = R.correspondences(rm, q, pose, method, md)
+                assert np.array_equal(co, cr) and np.array_equal(to, tr), (seed, method, md)
+                total += 1
+    assert total == 24 * 4 * 2
