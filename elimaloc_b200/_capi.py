@@ -96,6 +96,8 @@ SIGNATURES = {
     "elm_linearize": (C.c_int, [C.c_void_p, C.c_void_p, _fp, C.c_size_t, _dp, C.POINTER(RegConfig), _dp, _dp, _dp,
                                 C.POINTER(C.c_int64)]),
     "elm_correspondences": (C.c_int, [C.c_void_p, C.c_void_p, _fp, C.c_size_t, _dp, C.c_int, C.c_double, _ip, _dp]),
+    "elm_correspondences_sequence": (C.c_int, [C.c_void_p, C.c_void_p, _fp, C.c_size_t, _dp, C.c_int, C.c_int, C.c_double, _ip, _dp]),
+    "elm_registration_set_warm_start": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "elm_registration_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_profile": (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_int64)]),

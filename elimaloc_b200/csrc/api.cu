@@ -79,7 +79,7 @@ struct elm_map {
     elm::HostMap host;
     int device = -1;  // -1: host-only map (builder tests without a GPU)
     uint4* d_dslots = nullptr;
-    uint2* d_drows = nullptr;
+    uint32_t* d_drows = nullptr;
     float4* d_pts = nullptr;
     double* d_prec = nullptr;
     double4* d_vslots = nullptr;
@@ -101,14 +101,17 @@ struct elm_map {
         const size_t P = host.P();
         std::vector<float4> p4(P + 1);  // one element of padding: the search reads aligned 32-byte pairs
         p4[P] = float4{0.f, 0.f, 0.f, 0.f};
-        for (size_t i = 0; i < P; ++i) {
-            p4[i].x = host.pxyz[3 * i]; p4[i].y = host.pxyz[3 * i + 1]; p4[i].z = host.pxyz[3 * i + 2];
-            p4[i].w = __int_as_float_host(host.porig[i]);
+        // device order = octant order inside every voxel (host_map.hpp); w = bits of the CANONICAL index, the rank that
+        // breaks exact distance ties the way the reference's visit order does (vhm.cpp:45)
+        for (size_t d = 0; d < P; ++d) {
+            const size_t i = host.dev_order[d];
+            p4[d].x = host.pxyz[3 * i]; p4[d].y = host.pxyz[3 * i + 1]; p4[d].z = host.pxyz[3 * i + 2];
+            p4[d].w = __int_as_float_host(static_cast<uint32_t>(i));
         }
         ELM_CUDA(upload(&d_pts, p4.data(), P + 1));
-        static_assert(sizeof(elm::DirSlot) == sizeof(uint4) && sizeof(elm::DirDesc) == sizeof(uint2), "directory layout");
+        static_assert(sizeof(elm::DirSlot) == sizeof(uint4), "directory layout");
         ELM_CUDA(upload(&d_dslots, reinterpret_cast<const uint4*>(host.dir_slots.data()), host.dir_slots.size()));
-        ELM_CUDA(upload(&d_drows, reinterpret_cast<const uint2*>(host.dir_rows.data()), host.dir_rows.size()));
+        ELM_CUDA(upload(&d_drows, host.dir_rows.data(), host.dir_rows.size()));
         if (d_prec) { cudaFree(d_prec); d_prec = nullptr; }
         if (d_vslots) { cudaFree(d_vslots); d_vslots = nullptr; }
         if (d_vcov) { cudaFree(d_vcov); d_vcov = nullptr; }
@@ -135,7 +138,7 @@ struct elm_map {
         // candidate lists + the row descriptors 9 / 10 that point into them
         ELM_CUDA(upload(&d_vcand, reinterpret_cast<const float4*>(host.vcand.data()), host.vcand.size() / 4));
         ELM_CUDA(upload(&d_dir7, host.dir7.data(), host.dir7.size()));
-        ELM_CUDA(upload(&d_drows, reinterpret_cast<const uint2*>(host.dir_rows.data()), host.dir_rows.size()));
+        ELM_CUDA(upload(&d_drows, host.dir_rows.data(), host.dir_rows.size()));
         return ELM_OK;
     }
     int publish_point_cov() {
@@ -143,10 +146,11 @@ struct elm_map {
         ELM_CUDA(cudaSetDevice(device));
         const size_t P = host.P();
         std::vector<double> rec(16 * P, 0.0);
-        for (size_t p = 0; p < P; ++p) {
-            for (int k = 0; k < 3; ++k) rec[16 * p + k] = host.pmean[3 * p + k];
-            for (int k = 0; k < 9; ++k) rec[16 * p + 3 + k] = host.pcov[9 * p + k];
-            for (int k = 0; k < 3; ++k) rec[16 * p + 12 + k] = host.pnormal[3 * p + k];
+        for (size_t d = 0; d < P; ++d) {  // same device order as the points
+            const size_t p = host.dev_order[d];
+            for (int k = 0; k < 3; ++k) rec[16 * d + k] = host.pmean[3 * p + k];
+            for (int k = 0; k < 9; ++k) rec[16 * d + 3 + k] = host.pcov[9 * p + k];
+            for (int k = 0; k < 3; ++k) rec[16 * d + 12 + k] = host.pnormal[3 * p + k];
         }
         ELM_CUDA(upload(&d_prec, rec.data(), 16 * P));
         return ELM_OK;
@@ -169,7 +173,10 @@ struct elm_registration {
     double* d_partials = nullptr;
     int partial_rows = 0;
     int* d_match = nullptr;
+    float4* d_win = nullptr;   // matched map point per scan point (streamed by the accumulation)
+    uint4* d_memo = nullptr;   // warm start of the next iteration's search
     size_t match_cap = 0;
+    int warm = 1;              // P2P / GICP: iterations after the first start their search from the previous match (same result)
     // spatially binned copy of the scan for the search kernels (scan_sort.cu)
     float* d_sorted = nullptr;
     int* d_orig = nullptr;
@@ -223,6 +230,7 @@ struct elm_registration {
     elm::PeerComm peer{};          // peer.world > 0: the accumulate kernel's last block all-reduces over the ranks itself
     void* peer_opened[elm::kMaxPeers] = {};
     bool sharded() const { return comm != nullptr || peer.world > 0; }
+    elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, d_partials, d_ticket}; }
 
     ~elm_registration() {
         cudaSetDevice(device);
@@ -232,7 +240,8 @@ struct elm_registration {
         for (void* p : peer_opened) if (p) cudaIpcCloseMemHandle(p);
         cudaFree(d_mailbox);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_ticket); cudaFree(d_stats);
+        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_win); cudaFree(d_memo); cudaFree(d_ticket);
+        cudaFree(d_stats);
         cudaFree(d_dtable); cudaFreeHost(h_dtable); cudaFree(d_dsk_in); cudaFree(d_dsk_out);
         cudaFree(d_sorted); cudaFree(d_orig); cudaFree(d_bin); cudaFree(d_hist); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -278,10 +287,13 @@ int ensure_partials(elm_registration* r, int rows) {
 
 int ensure_match(elm_registration* r, size_t n) {
     if (n > r->match_cap) {
-        if (r->d_match) cudaFree(r->d_match);
-        r->d_match = nullptr;
+        cudaFree(r->d_match); cudaFree(r->d_win); cudaFree(r->d_memo);
+        r->d_match = nullptr; r->d_win = nullptr; r->d_memo = nullptr;
+        r->match_cap = 0;
         const size_t cap = (n + 1023) / 1024 * 1024;
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_match), cap * sizeof(int)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_win), cap * sizeof(float4)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_memo), cap * sizeof(uint4)));
         r->match_cap = cap;
     }
     return ELM_OK;
@@ -342,7 +354,8 @@ elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg,
 
 // one linearisation: search kernel -> accumulate kernel (its last block reduces in a fixed order and, on a single
 // GPU, also solves) -> multi-GPU: allreduce of the 30 sums over ranks, then the solve kernel
-int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm, bool solve) {
+// `warm`: the work buffers hold the previous iteration's matches of the SAME scan (P2P / GICP: warm-started search)
+int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm, bool solve, bool warm = false) {
     const int sgrid = elm::icp_search_grid(prm, r->num_sms);
     const int agrid = elm::icp_accumulate_grid(prm, r->num_sms);
     // P2P / GICP: search, linearisation, reduction and solve are ONE kernel (unless the search runs on the binned copy,
@@ -363,15 +376,17 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // peer mode: the exchange happens inside the kernel, then the solve; NCCL mode: allreduce + separate solve launch below
     const bool use_nccl = r->comm != nullptr && r->peer.world == 0;
     const int solve_here = (solve && !use_nccl) ? 1 : 0;
+    elm::IcpWork wk = r->work();
+    if (fuse && !r->keep_match && prm.method == ELM_P2P) wk.match = nullptr;  // (GICP's accumulation reads the covariance record by index)
     if (prm.method != ELM_AVGICP) {
+        const bool use_warm = warm && r->warm && r->prune && !r->use_sorted && prm.method <= ELM_GICP;
         ELM_CUDA(elm::launch_icp_search(map->view(), r->use_sorted ? r->d_sorted : d_scan, r->use_sorted ? r->d_orig : nullptr, prm, r->d_state,
-                                        (fuse && !r->keep_match) ? nullptr : r->d_match, sgrid, r->prune, fuse ? 1 : 0, r->d_partials, r->d_ticket,
-                                        solve_here, r->stream));
+                                        wk, sgrid, r->prune, fuse ? 1 : 0, use_warm ? 1 : 0, solve_here, r->stream));
         r->launches += 1;
     }
     if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
     if (!fuse) {
-        ELM_CUDA(elm::launch_icp_accumulate(map->view(), d_scan, r->d_match, prm, r->d_state, r->d_partials, r->d_ticket, solve_here, agrid, r->stream));
+        ELM_CUDA(elm::launch_icp_accumulate(map->view(), d_scan, prm, r->d_state, wk, solve_here, agrid, r->stream));
         r->launches += 1;
     }
     if (r->profiling) {
@@ -577,7 +592,7 @@ int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slo
         elm::unpack_key(key, x, y, z);
         bool any = false;
         for (int c = 0; c < 9; ++c) {
-            const elm::DirDesc d = h.dir_rows[s * elm::kDirRowDescs + c];
+            const elm::DirDesc d = h.row_column(s, c);
             uint32_t first = 0, counts = 0;
             bool have = false;
             for (int dz = -1; dz <= 1; ++dz) {
@@ -585,6 +600,23 @@ int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slo
                 if (!elm::key_in_range(vx) || !elm::key_in_range(vy) || !elm::key_in_range(vz)) continue;
                 const int64_t v = h.find(elm::pack_key(vx, vy, vz));
                 if (v < 0) continue;
+                // octant word of the voxel: cumulative counts of its points by octant, recomputed from the device order
+                if (h.octants) {
+                    uint8_t want[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    int prev = 0;
+                    for (uint32_t p = h.vstart[v]; p < h.vstart[v + 1]; ++p) {
+                        const float* q = &h.pxyz[3 * static_cast<size_t>(h.dev_order[p])];
+                        const int o = (elm::axis_half(static_cast<double>(q[2]) / h.voxel_size, vz) << 2) |
+                                      (elm::axis_half(static_cast<double>(q[1]) / h.voxel_size, vy) << 1) |
+                                      elm::axis_half(static_cast<double>(q[0]) / h.voxel_size, vx);
+                        if (o < prev) ++bad;  // device order sorted by octant
+                        if (p > h.vstart[v] && o == prev && h.dev_order[p] < h.dev_order[p - 1]) ++bad;  // stable inside an octant
+                        prev = o;
+                        for (int k = o + 1; k <= 7; ++k) ++want[k - 1];
+                    }
+                    want[7] = static_cast<uint8_t>(h.vstart[v + 1] - h.vstart[v]);
+                    if (std::memcmp(want, &h.dir_rows[elm::row_col_word(s, c) + 2 + 2 * static_cast<size_t>(dz + 1)], 8) != 0) ++bad;
+                }
                 if (!have) { first = h.vstart[v]; have = true; }
                 else if (h.vstart[v] != first + (counts & elm::kDirCountMask) + ((counts >> elm::kDirCountBits) & elm::kDirCountMask)) ++bad;  // contiguity
                 counts |= (h.vstart[v + 1] - h.vstart[v]) << (elm::kDirCountBits * static_cast<uint32_t>(dz + 1));
@@ -595,7 +627,9 @@ int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slo
         }
         if (!any) ++bad;  // an entry whose neighbourhood is empty should not exist
         if (h.has_vcov) {  // VGICP / AVGICP candidate list of the entry: occupancy mask, order, fp32 means, voxel slots
-            const elm::DirDesc run = h.dir_rows[s * elm::kDirRowDescs + 10], occ = h.dir_rows[s * elm::kDirRowDescs + 11];
+            const elm::DirDesc run{h.dir_rows[elm::row_word(s, elm::kRowCandFirst)], h.dir_rows[elm::row_word(s, elm::kRowCandCount)]};
+            const elm::DirDesc occ{h.dir_rows[elm::row_word(s, elm::kRowOccMask)], 0};
+            if (h.dir_rows[elm::row_word(s, elm::kRowKeyLo)] != sl.key_lo || h.dir_rows[elm::row_word(s, elm::kRowKeyHi)] != sl.key_hi) ++bad;
             uint32_t c = 0;
             for (int L = 0; L < 27; ++L) {
                 const int32_t vx = x + L / 9 - 1, vy = y + (L / 3) % 3 - 1, vz = z + L % 3 - 1;
@@ -692,7 +726,7 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     rc = enqueue_binning(reg, map, d_src_xyz, n, T_init, cfg->icp_method);
     if (rc) return rc;
     for (int j = 0; j < cfg->max_iteration; ++j) {  // reg.cpp:310
-        rc = enqueue_linearize(reg, map, d_src_xyz, prm, true);
+        rc = enqueue_linearize(reg, map, d_src_xyz, prm, true, j > 0);
         if (rc) return rc;
     }
     ELM_CUDA(cudaMemcpyAsync(reg->h_state, reg->d_state, sizeof(elm::IcpState), cudaMemcpyDeviceToHost, reg->stream));
@@ -780,9 +814,9 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     return ELM_OK;
 }
 
-int elm_correspondences(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
-                        int method, double max_search_dist, int32_t* count, double* target) {
-    if (!reg || !map || !T || !count || !target || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_correspondences: bad argument");
+int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double* T_seq, int n_poses,
+                                 int method, double max_search_dist, int32_t* count, double* target) {
+    if (!reg || !map || !T_seq || n_poses < 1 || !count || !target || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_correspondences: bad argument");
     elm_reg_config c{};
     c.icp_method = method;
     int rc = check_method(map, &c);
@@ -802,23 +836,42 @@ int elm_correspondences(elm_registration* reg, const elm_map* map, const float* 
         reg->hook_cap = n * 7;
     }
     ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
-    // the hook runs the PRODUCTION search kernel and only converts its match[] into positions
+    // the hook runs the PRODUCTION search kernels — cold at the first pose, warm-started at the following ones exactly as
+    // the ICP loop runs them — and only converts the last match[] into positions
     c.max_search_dist = max_search_dist;
     const elm::IcpParams prm = make_params(reg, &c, n);
     rc = ensure_match(reg, n);
     if (rc) return rc;
-    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
-    rc = enqueue_binning(reg, map, reg->d_scan, n, T, method);
-    if (rc) return rc;
-    if (method != ELM_AVGICP)
-        ELM_CUDA(elm::launch_icp_search(map->view(), reg->use_sorted ? reg->d_sorted : reg->d_scan, reg->use_sorted ? reg->d_orig : nullptr, prm,
-                                        reg->d_state, reg->d_match, elm::icp_search_grid(prm, reg->num_sms), reg->prune, 0, nullptr, nullptr, 0,
-                                        reg->stream));
+    for (int k = 0; k < n_poses; ++k) {
+        const double* T = T_seq + 16 * static_cast<size_t>(k);
+        ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
+        if (k == 0) {
+            rc = enqueue_binning(reg, map, reg->d_scan, n, T, method);
+            if (rc) return rc;
+        }
+        if (method != ELM_AVGICP) {
+            const bool warm = k > 0 && reg->warm && reg->prune && !reg->use_sorted && method <= ELM_GICP;
+            ELM_CUDA(elm::launch_icp_search(map->view(), reg->use_sorted ? reg->d_sorted : reg->d_scan, reg->use_sorted ? reg->d_orig : nullptr, prm,
+                                            reg->d_state, reg->work(), elm::icp_search_grid(prm, reg->num_sms), reg->prune, 0, warm ? 1 : 0, 0,
+                                            reg->stream));
+        }
+    }
     ELM_CUDA(elm::launch_icp_export(map->view(), reg->d_scan, reg->d_match, static_cast<int>(n), reg->d_state, method,
                                     max_search_dist * max_search_dist, reg->d_count, reg->d_target, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(count, reg->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaMemcpyAsync(target, reg->d_target, n * K * 3 * sizeof(double), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    return ELM_OK;
+}
+
+int elm_correspondences(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
+                        int method, double max_search_dist, int32_t* count, double* target) {
+    return elm_correspondences_sequence(reg, map, src_xyz, n, T, 1, method, max_search_dist, count, target);
+}
+
+int elm_registration_set_warm_start(elm_registration* reg, int enable) {
+    if (!reg) return fail(ELM_ERR_INVALID, "null registration");
+    reg->warm = enable ? 1 : 0;
     return ELM_OK;
 }
 

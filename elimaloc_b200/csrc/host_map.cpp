@@ -376,10 +376,49 @@ std::vector<uint64_t> dilate_axis(const std::vector<uint64_t>& in, int axis) {
 
 }  // namespace
 
+// Octant order of the stored points for the device (voxel_key.hpp): per voxel a stable counting sort by octant code.
+void HostMap::build_octants() {
+    const size_t nv = V(), np = P();
+    octants = cap <= kOctantCapMax;
+    dev_order.resize(np);
+    voct.assign(8 * nv, 0);
+    const double vs = voxel_size;
+    parallel_for(nv, 1 << 12, [&](size_t vb, size_t ve) {
+        uint8_t code[kOctantCapMax + 1];
+        for (size_t v = vb; v < ve; ++v) {
+            const uint32_t s = vstart[v], n = vstart[v + 1] - s;
+            if (!octants) {  // whole voxels only: identity order, no octant words
+                for (uint32_t i = 0; i < n; ++i) dev_order[s + i] = s + i;
+                continue;
+            }
+            int32_t cx, cy, cz;
+            unpack_key(vkey[v], cx, cy, cz);
+            uint32_t cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (uint32_t i = 0; i < n; ++i) {
+                const float* p = &pxyz[3 * static_cast<size_t>(s + i)];
+                const int o = (axis_half(static_cast<double>(p[2]) / vs, cz) << 2) | (axis_half(static_cast<double>(p[1]) / vs, cy) << 1) |
+                              axis_half(static_cast<double>(p[0]) / vs, cx);
+                code[i] = static_cast<uint8_t>(o);
+                ++cnt[o + 1];
+            }
+            for (int k = 0; k < 8; ++k) cnt[k + 1] += cnt[k];  // cnt[k] = points in octants < k
+            uint8_t* w = &voct[8 * v];
+            for (int k = 1; k <= 7; ++k) w[k - 1] = static_cast<uint8_t>(cnt[k]);
+            w[7] = static_cast<uint8_t>(n);
+            uint32_t at[8];
+            for (int k = 0; k < 8; ++k) at[k] = cnt[k];
+            for (uint32_t i = 0; i < n; ++i) dev_order[s + at[code[i]]++] = s + i;
+        }
+    });
+}
+
 std::string HostMap::build_directory() {
     dir_slots.clear(); dir_rows.clear(); dir_bmask = 0; dir_entries = 0;
+    dev_order.clear(); voct.clear();
     if (vkey.empty()) return "";
     StageTimer timer;
+    build_octants();
+    timer.lap("  octant order");
     // 1. centre keys: occupied voxels and their one-voxel halo (separable dilation z, y, x of the sorted key list)
     std::vector<uint64_t> E = dilate_axis(dilate_axis(dilate_axis(vkey, 2), 1), 0);
     dir_entries = E.size();
@@ -423,7 +462,7 @@ std::string HostMap::build_directory() {
     //    instead of a binary search each; the rows are written to the entry's slot.
     const size_t S = owner.size();
     dir_slots.assign(S, DirSlot{0xffffffffu, 0xffffffffu, 0, 0});
-    dir_rows.assign(S * kDirRowDescs, DirDesc{0, 0});
+    dir_rows.assign(S * kRowWords, 0u);
     std::vector<uint32_t> slot_of(E.size());
     for (size_t s = 0; s < S; ++s) if (owner[s] >= 0) slot_of[static_cast<size_t>(owner[s])] = static_cast<uint32_t>(s);
     const size_t nV = vkey.size();
@@ -436,7 +475,9 @@ std::string HostMap::build_directory() {
             int32_t x, y, z;
             unpack_key(key, x, y, z);
             const size_t s = slot_of[e];
-            DirDesc* row = &dir_rows[s * kDirRowDescs];
+            uint32_t* hdr = &dir_rows[row_word(s, 0)];
+            hdr[kRowKeyLo] = static_cast<uint32_t>(key); hdr[kRowKeyHi] = static_cast<uint32_t>(key >> 32);
+            hdr[kRowFlags] = octants ? kRowFlagOctants : 0u;
             for (int c = 0; c < 9; ++c) {
                 const int32_t cx = x + c / 3 - 1, cy = y + c % 3 - 1;
                 if (!key_in_range(cx) || !key_in_range(cy)) continue;
@@ -454,15 +495,19 @@ std::string HostMap::build_directory() {
                 last[c] = klo;
                 uint32_t first = 0, counts = 0;
                 bool any = false;
+                uint32_t* col = &dir_rows[row_col_word(s, c)];
                 for (size_t v = cur[c]; v < nV && vkey[v] <= khi; ++v) {
                     int32_t vx, vy, vz;
                     unpack_key(vkey[v], vx, vy, vz);
                     if (!any) { first = vstart[v]; any = true; }
-                    counts |= (vstart[v + 1] - vstart[v]) << (kDirCountBits * static_cast<uint32_t>(vz - (z - 1)));
+                    const uint32_t dz = static_cast<uint32_t>(vz - (z - 1));
+                    counts |= (vstart[v + 1] - vstart[v]) << (kDirCountBits * dz);
+                    std::memcpy(&col[2 + 2 * dz], &voct[8 * v], 8);
                 }
-                row[c] = DirDesc{first, counts};
+                col[0] = first; col[1] = counts;
             }
-            dir_slots[s] = DirSlot{static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), row[4].first, row[4].counts};
+            const DirDesc centre = row_column(s, 4);
+            dir_slots[s] = DirSlot{static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), centre.first, centre.counts};
         }
     });
     timer.lap("  slots + rows");
@@ -473,7 +518,7 @@ std::string HostMap::build_directory() {
 namespace {
 
 constexpr char kMapMagic[8] = {'E', 'L', 'M', 'B', '2', '0', '0', 'M'};
-constexpr uint32_t kMapVersion = 3;
+constexpr uint32_t kMapVersion = 4;
 
 // checksum of everything written / read so far: 8 interleaved FNV-1a lanes over 64-bit words (tail bytes one by one)
 struct Checksum {
@@ -516,6 +561,9 @@ void read_vec(Reader& r, std::vector<T>& v, uint64_t max_elems) {
 
 }  // namespace
 
+// The file holds the CANONICAL arrays only (sorted voxel keys, point prefix, stored points, insertion indices, covariances).
+// Everything the kernels dereference — voxel table, neighbourhood directory, octant order, candidate lists — is rebuilt from
+// them on load, so an internally inconsistent (or crafted) file cannot make the device read out of bounds.
 std::string HostMap::save(const std::string& path) const {
     std::unique_ptr<std::FILE, FileCloser> f(std::fopen(path.c_str(), "wb"));
     if (!f) return "cannot open " + path + " for writing";
@@ -525,8 +573,7 @@ std::string HostMap::save(const std::string& path) const {
     w.put(kMapMagic, 8); w.put(&kMapVersion, 4); w.put(&flags, 4); w.put(&voxel_size, 8); w.put(&cap, 4); w.put(&mask, 4);
     w.put(&dir_bmask, 4); w.put(counts, sizeof counts);
     write_vec(w, vkey); write_vec(w, vstart); write_vec(w, pxyz); write_vec(w, porig); write_vec(w, vmean); write_vec(w, vcov);
-    write_vec(w, pmean); write_vec(w, pcov); write_vec(w, pnormal); write_vec(w, slots); write_vec(w, slot_voxel);
-    write_vec(w, dir_slots); write_vec(w, dir_rows); write_vec(w, vcand); write_vec(w, dir7);
+    write_vec(w, pmean); write_vec(w, pcov); write_vec(w, pnormal);
     const uint64_t sum = w.c.value();
     bool ok = w.ok && std::fwrite(&sum, 8, 1, f.get()) == 1;
     if (!ok || std::fflush(f.get()) != 0) return "short write to " + path;
@@ -537,37 +584,44 @@ std::string HostMap::load(const std::string& path) {
     std::unique_ptr<std::FILE, FileCloser> f(std::fopen(path.c_str(), "rb"));
     if (!f) return "cannot open " + path;
     char magic[8];
-    uint32_t version = 0, flags = 0;
+    uint32_t version = 0, flags = 0, file_mask = 0, file_bmask = 0;
     uint64_t counts[4] = {0, 0, 0, 0};
     HostMap m;
     Reader r{f.get()};
     r.get(magic, 8); r.get(&version, 4);
     if (!r.ok || std::memcmp(magic, kMapMagic, 8) != 0) return path + " is not an elimaloc_b200 map file";
     if (version != kMapVersion) return path + ": unsupported map file version " + std::to_string(version);
-    r.get(&flags, 4); r.get(&m.voxel_size, 8); r.get(&m.cap, 4); r.get(&m.mask, 4); r.get(&m.dir_bmask, 4); r.get(counts, sizeof counts);
+    r.get(&flags, 4); r.get(&m.voxel_size, 8); r.get(&m.cap, 4); r.get(&file_mask, 4); r.get(&file_bmask, 4); r.get(counts, sizeof counts);
     const uint64_t lim = 1ull << 34;
     read_vec(r, m.vkey, lim); read_vec(r, m.vstart, lim); read_vec(r, m.pxyz, lim); read_vec(r, m.porig, lim); read_vec(r, m.vmean, lim);
-    read_vec(r, m.vcov, lim); read_vec(r, m.pmean, lim); read_vec(r, m.pcov, lim); read_vec(r, m.pnormal, lim); read_vec(r, m.slots, lim);
-    read_vec(r, m.slot_voxel, lim); read_vec(r, m.dir_slots, lim); read_vec(r, m.dir_rows, lim); read_vec(r, m.vcand, lim);
-    read_vec(r, m.dir7, lim);
+    read_vec(r, m.vcov, lim); read_vec(r, m.pmean, lim); read_vec(r, m.pcov, lim); read_vec(r, m.pnormal, lim);
     uint64_t sum = 0;
     bool ok = r.ok && std::fread(&sum, 8, 1, f.get()) == 1 && sum == r.c.value();
     if (!ok) return path + ": truncated or corrupt map file";
     m.has_vcov = (flags & 1u) != 0;
     m.has_pcov = (flags & 2u) != 0;
-    m.dir_entries = counts[2];
     m.n_raw_seen = counts[3];
-    // structural consistency (a file from another build / a damaged file must not reach the kernels)
+    // structural consistency of the canonical arrays (a file from another build / a damaged file must not reach the kernels)
     const size_t nv = m.vkey.size(), np = m.pxyz.size() / 3;
     ok = counts[0] == nv && counts[1] == np && m.pxyz.size() == 3 * np && m.vstart.size() == nv + 1 && m.porig.size() == np &&
-         (nv == 0 || (m.vstart.front() == 0 && m.vstart.back() == np)) && m.slots.size() == m.slot_voxel.size() &&
-         (m.slots.empty() || m.slots.size() == static_cast<size_t>(m.mask) + 1) &&
-         (m.dir_slots.empty() || m.dir_slots.size() == 2 * (static_cast<size_t>(m.dir_bmask) + 1)) &&
-         m.dir_rows.size() == m.dir_slots.size() * kDirRowDescs && m.voxel_size > 0.0 && m.cap >= 1 &&
-         (!m.has_vcov || (m.vmean.size() == 3 * nv && m.vcov.size() == 9 * nv && m.dir7.size() == 8 * m.dir_slots.size())) &&
+         np < (1ull << 32) && (nv == 0 || (m.vstart.front() == 0 && m.vstart.back() == np)) && (nv != 0 || np == 0) &&
+         m.voxel_size > 0.0 && m.cap >= 1 && m.cap <= static_cast<int>(kDirCountMask) &&
+         (!m.has_vcov || (m.vmean.size() == 3 * nv && m.vcov.size() == 9 * nv)) &&
          (!m.has_pcov || (m.pmean.size() == 3 * np && m.pcov.size() == 9 * np && m.pnormal.size() == 3 * np));
-    for (size_t v = 0; ok && v + 1 < nv; ++v) ok = m.vkey[v] < m.vkey[v + 1] && m.vstart[v] < m.vstart[v + 1];
+    for (size_t v = 0; ok && v < nv; ++v) {
+        int32_t x, y, z;
+        unpack_key(m.vkey[v], x, y, z);
+        const int32_t lim_k = kKeyBias - 2;
+        ok = (m.vkey[v] >> (3 * kKeyBits)) == 0 && std::abs(x) < lim_k && std::abs(y) < lim_k && std::abs(z) < lim_k &&
+             m.vstart[v] < m.vstart[v + 1] && m.vstart[v + 1] - m.vstart[v] <= static_cast<uint32_t>(m.cap) &&
+             (v + 1 == nv || m.vkey[v] < m.vkey[v + 1]);
+    }
     if (!ok) return path + ": inconsistent map file";
+    m.build_table();
+    const std::string e = m.build_directory();
+    if (!e.empty()) return path + ": " + e;
+    if (m.has_vcov) m.build_voxel_candidates();
+    if (m.dir_entries != counts[2] || m.mask != file_mask || m.dir_bmask != file_bmask) return path + ": inconsistent map file";
     *this = std::move(m);
     return "";
 }
@@ -683,7 +737,7 @@ void HostMap::build_voxel_candidates() {
             if ((sl.key_lo & sl.key_hi) == 0xffffffffu) continue;
             uint32_t mask = 0;
             for (int c = 0; c < 9; ++c) {
-                const uint32_t counts = dir_rows[s * kDirRowDescs + c].counts;
+                const uint32_t counts = row_column(s, c).counts;
                 for (int dz = 0; dz < 3; ++dz) if ((counts >> (kDirCountBits * dz)) & kDirCountMask) mask |= 1u << (3 * c + dz);
             }
             masks[s] = mask;
@@ -695,15 +749,14 @@ void HostMap::build_voxel_candidates() {
     parallel_for(S, 1 << 13, [&](size_t sb, size_t se) {
         int64_t v27[27];
         for (size_t s = sb; s < se; ++s) {
-            DirDesc* row = &dir_rows[s * kDirRowDescs];
-            row[10] = DirDesc{first[s], first[s + 1] - first[s]};
-            row[11] = DirDesc{masks[s], 0};
+            uint32_t* hdr = &dir_rows[row_word(s, 0)];
+            hdr[kRowCandFirst] = first[s]; hdr[kRowCandCount] = first[s + 1] - first[s]; hdr[kRowOccMask] = masks[s];
             if (!masks[s]) continue;
             for (int c = 0; c < 9; ++c) {
                 v27[3 * c] = v27[3 * c + 1] = v27[3 * c + 2] = -1;
                 if (!((masks[s] >> (3 * c)) & 7u)) continue;
                 // voxel that owns the column's first point: vstart[v] <= first < vstart[v + 1]
-                int64_t v = static_cast<int64_t>(std::upper_bound(vstart.begin(), vstart.end(), row[c].first) - vstart.begin()) - 1;
+                int64_t v = static_cast<int64_t>(std::upper_bound(vstart.begin(), vstart.end(), row_column(s, c).first) - vstart.begin()) - 1;
                 for (int dz = 0; dz < 3; ++dz) if ((masks[s] >> (3 * c + dz)) & 1u) v27[3 * c + dz] = v++;
             }
             static const int kL7[7] = {13, 22, 4, 16, 10, 14, 12};  // centre, +x, -x, +y, -y, +z, -z

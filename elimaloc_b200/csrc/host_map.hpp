@@ -22,12 +22,12 @@ struct Slot { uint32_t key_lo, key_hi, start, count; };
 
 // Neighbourhood directory (what the P2P/GICP search reads): one entry per voxel key whose 27-neighbourhood holds at
 // least one stored point (occupied voxels + their one-voxel halo).  Entry = a 16-byte slot in a 2-choice cuckoo table
-// with 2-slot buckets {key, first point and counts of the centre z-column} + a 96-byte row, indexed by the SLOT position,
-// of nine column descriptors {first point, n(z-1) | n(z) << 10 | n(z+1) << 20} for the columns (x+dx, y+dy), dx outer.
+// with 2-slot buckets {key, first point and counts of the centre z-column} + a 320-byte row, indexed by the SLOT position,
+// of nine column records {first point, n(z-1) | n(z) << 10 | n(z+1) << 20, octant words} for the columns (x+dx, y+dy), dx
+// outer (layout: voxel_key.hpp).
 // A lookup is two independent 32-byte loads (no probe chains); a miss means "no candidate at all".
 struct DirSlot { uint32_t key_lo, key_hi, first, counts; };
 struct DirDesc { uint32_t first, counts; };
-constexpr int kDirRowDescs = 12;  // 9 used, padded to 96 bytes = three 32-byte sectors
 
 struct HostMap {
     double voxel_size = 1.0;
@@ -50,9 +50,17 @@ struct HostMap {
     std::vector<int32_t> slot_voxel;
     uint32_t mask = 0;
 
-    // neighbourhood directory (see above); dir_slots.size() == 2 * (dir_bmask + 1), dir_rows.size() == 12 * dir_slots.size()
+    // neighbourhood directory (see above); dir_slots.size() == 2 * (dir_bmask + 1), dir_rows.size() == kRowWords * dir_slots.size()
     std::vector<DirSlot> dir_slots;
-    std::vector<DirDesc> dir_rows;
+    std::vector<uint32_t> dir_rows;
+    DirDesc row_column(size_t slot, int c) const { const size_t w = row_col_word(slot, c); return DirDesc{dir_rows[w], dir_rows[w + 1]}; }
+    // Device order of the stored points: inside every voxel sorted by octant (voxel_key.hpp), stable in the canonical order.
+    // dev_order[d] = canonical index of the point at device position d (a permutation inside each voxel's range);
+    // voct = the 8 octant-word bytes of every voxel.  The canonical arrays above (what export / save / the covariance passes
+    // see) never change order; only the upload is permuted.
+    std::vector<uint32_t> dev_order;
+    std::vector<uint8_t> voct;
+    bool octants = false;  // octant words valid (cap <= 255)
     uint32_t dir_bmask = 0;
     size_t dir_entries = 0;
     // VGICP / AVGICP candidates (built by cal_voxel_cov): for every directory entry the non-empty voxels of its
@@ -72,6 +80,7 @@ struct HostMap {
     void cal_point_cov(double search_dist);
     void build_table();
     void build_voxel_candidates();
+    void build_octants();
     // returns "" on success
     std::string build_directory();
     // slot index of a centre key in the directory or -1 (host mirror of the device lookup; tests)

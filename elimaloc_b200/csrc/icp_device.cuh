@@ -5,15 +5,19 @@
 //                                {key_lo, key_hi, first point, counts} of every voxel key whose 27-neighbourhood holds a
 //                                stored point; first/counts describe the centre z-column (x, y, z-1..z+1);
 //                                counts = n(z-1) | n(z) << 10 | n(z+1) << 20; key = 3 x 21-bit biased coordinates
-//   drows   uint2[12 * 2 B]      one 96-B row per SLOT: {first point, counts} of the nine z-columns (x+dx, y+dy), dx outer
-//   pts     float4[P]            stored points in canonical order (voxels sorted by (x,y,z), insertion order inside):
-//                                the voxels (x,y,z-1..z+1) of one column are ONE contiguous run; w = raw-index bits
-//   prec    double[16 P]         GICP record per stored point: mean[3] cov[9] normal[3] pad  (128 B, one line)
+//   drows   uint32[80 * 2 B]     one 320-B row per SLOT (layout: voxel_key.hpp): header {key, VGICP candidate run, occupancy
+//                                mask, flags} + nine 32-B column records {first point, counts, three octant words} of the
+//                                z-columns (x+dx, y+dy), dx outer
+//   pts     float4[P]            stored points, voxels in canonical order (sorted by (x,y,z)): the voxels (x,y,z-1..z+1) of one
+//                                column are ONE contiguous run; inside a voxel sorted by OCTANT (z-half major), insertion order
+//                                inside an octant; w = bits of the point's canonical index (voxel order, then insertion order)
+//                                = its rank in the reference's visit order, which decides exact distance ties
+//   prec    double[16 P]         GICP record per stored point (same order as pts): mean[3] cov[9] normal[3] pad  (128 B, one line)
 //   vslots  double4[capacity]    VGICP/AVGICP: 32 B/slot {key bits, mean[3]}, open-addressed with linear probing, capacity = 2^k
 //                                >= 2 V (mask = capacity - 1); empty = all ones
 //   vcand   float4[C]            VGICP/AVGICP candidates: for every directory entry the non-empty voxels of its 27-neighbourhood
-//                                in visit order, {mean rounded to fp32, bits of the voxel's slot in vslots}; row descriptor 10 of
-//                                the entry = {first candidate, count}, descriptor 11 = {27-bit occupancy mask, 0}
+//                                in visit order, {mean rounded to fp32, bits of the voxel's slot in vslots}; the row header holds
+//                                {first candidate, count} and the 27-bit occupancy mask
 //   vcov    double[12 capacity]  VGICP/AVGICP: 96 B/slot {cov[9], pad[3]}
 #pragma once
 #include <cuda_runtime.h>
@@ -23,7 +27,7 @@ namespace elm {
 
 struct MapView {
     const uint4* dslots;
-    const uint2* drows;
+    const uint32_t* drows;
     const float4* pts;
     const double* prec;
     const double4* vslots;
@@ -68,6 +72,17 @@ struct IcpParams {
     double min_overlap;
     PeerComm peer;
     unsigned long long* stats;  // optional: [0] += map points visited by the search, [1] += queries (NULL = off)
+};
+
+// Per-registration device scratch of the ICP loop (owned by elm_registration, sized for the largest scan seen).
+struct IcpWork {
+    int* match;             // [n] device index of the matched map point (P2P/GICP) / voxel slot (VGICP); -1 = none
+    float4* win;            // [n] P2P/GICP: the matched map point itself {x, y, z, bits of its canonical rank}; none ->
+                            //     {0, 0, 0, 0xffffffff} = the reference's default-constructed neighbour at the origin (Q2), so the
+                            //     accumulation STREAMS its targets instead of gathering pts[match[i]]
+    uint4* memo;            // [n] warm start of the next iteration's search: {directory row, key_lo, key_hi, device index of the match}
+    double* partials;       // [blocks][kAcc] per-block sums of one linearisation
+    unsigned int* ticket;   // blocks finished
 };
 
 // Lives in HBM for the whole ICP loop; the host reads it back once at the end.

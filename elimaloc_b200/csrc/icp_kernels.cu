@@ -1,8 +1,12 @@
 // Hand-written sm_100a kernels of the ICP hot loop.  One ICP iteration = two launches:
 //
 //   icp_search_points_kernel   P2P/GICP  TransformPoints + GetCorrespondencePoints     reg.hpp:136-148, vhm.cpp:31-88
+//        first iteration of a call ("cold"): directory lookup, home voxel, then the voxels that cannot be excluded
+//   icp_search_warm_kernel     P2P/GICP  the same search from the second iteration on ("warm"): the previous iteration's
+//        match bounds the distance, so only the OCTANTS (half-voxel cells) within that bound are read — same result
 //   icp_search_means_kernel    VGICP     TransformPoints + GetCorrespondencesCov       vhm.cpp:90-151
-//        -> match[n]: index of the winning map point / voxel slot (4 B per scan point, never the 168-B structs)
+//        -> match[n] (index of the winning map point / voxel slot), win[n] (the matched point itself, streamed by the
+//           accumulation), memo[n] (warm start of the next search) — never the 168-B structs
 //   icp_accumulate_kernel<M>   AlignCloudsLocal{,PointCov,VoxelCov} accumulation        reg.cpp:28-51 / 85-132 / 171-208
 //        (AVGICP searches its 7 voxels inside this kernel, vhm.cpp:153-206), block tree reduction, and in the LAST
 //        block to finish: fixed-order reduction of all partials + the solve/update step below
@@ -110,7 +114,7 @@ __device__ __forceinline__ int dir_lookup(const MapView& map, int kx, int ky, in
 }
 // descriptor of column c (= 3 (dx + 1) + (dy + 1)) of the row that belongs to directory slot `si`
 __device__ __forceinline__ uint2 dir_column(const MapView& map, int si, int c) {
-    return __ldg(map.drows + static_cast<size_t>(si) * 12 + c);
+    return __ldg(reinterpret_cast<const uint2*>(map.drows + row_col_word(static_cast<size_t>(si), c)));
 }
 // The contiguous run of `pts` that covers the voxels of `zmask` (bit 0: z-1, bit 1: z, bit 2: z+1; != 0) of a column.
 // (A mask with a gap also covers the voxel in between: visiting more candidates never changes the exact result.)
@@ -122,13 +126,18 @@ __device__ __forceinline__ void column_run(uint2 d, uint32_t zmask, uint32_t& st
     len = hi - lo;
 }
 
-// Running best of one search: smallest (d2, idx).  `pts` is in canonical order — voxels sorted by (x, y, z), insertion
-// order inside — which IS the reference's visit order (voxels x-outer / y / z-inner, vhm.cpp:234-240; strict <,
-// vhm.cpp:45): among equal distances the reference keeps the candidate with the smallest canonical index.
+// Running best of one search: smallest (d2, rank).  The canonical order — voxels sorted by (x, y, z), insertion order
+// inside — IS the reference's visit order (voxels x-outer / y / z-inner, vhm.cpp:234-240; strict <, vhm.cpp:45): among
+// equal distances the reference keeps the candidate with the smallest canonical index.  On the device the points of a
+// voxel are stored sorted by octant, so that index travels with the point (pts[i].w) as its rank.
 struct Best {
     double d2 = kDblMax;
     uint32_t idx = 0xffffffffu;
+    uint32_t rank = 0xffffffffu;  // canonical index of the candidate: the tie-break among equal distances
 };
+constexpr uint32_t kNone = 0xffffffffu;
+__device__ __forceinline__ bool closer(double d2, uint32_t rank, const Best& b) { return d2 < b.d2 || (d2 == b.d2 && rank < b.rank); }
+__device__ __forceinline__ unsigned long long rank_idx(uint32_t rank, uint32_t idx) { return (static_cast<unsigned long long>(rank) << 32) | idx; }
 // 32-byte (two stored points) read-only load: sm_100 LDG.E.256.  With one lane per query every lane touches a different
 // 128-byte line, so the L1TEX tag stage — one line per cycle — bounds the search (measured: ~14.5 B/cycle/SM with 16-byte
 // loads, profiles/r01b_*); a 32-byte load moves twice the points per tag lookup.
@@ -139,8 +148,8 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
     asm(ELM_PTS_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
-// Stream `n` consecutive stored points starting at index idx0 and fold them into `b`, exactly (ascending index + strict <
-// keeps the first of equals).  The loads of one batch are issued TOGETHER, before any of them is consumed: addresses
+// Stream `n` consecutive stored points starting at index idx0 and fold them into `b`, exactly (smaller distance, then
+// smaller rank).  The loads of one batch are issued TOGETHER, before any of them is consumed: addresses
 // past the run are clamped to its last element instead of being guarded by the loop condition, which would make every
 // load wait for the previous iteration's exit test (one load in flight per thread — what the compiler produced from the
 // plain `for (o < n)` loop whatever the unroll factor).  `pts` is padded by one element so that an aligned pair that
@@ -153,6 +162,7 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
 // pre-filter plus the voxel's slot; the exact fp64 mean is read from the voxel table.
 struct ExactPoint {
     __device__ __forceinline__ void operator()(const float4& q, double& x, double& y, double& z) const { x = q.x; y = q.y; z = q.z; }
+    __device__ __forceinline__ uint32_t rank(const float4& q, uint32_t) const { return __float_as_uint(q.w); }
 };
 struct ExactMean {
     const double4* vslots;
@@ -161,13 +171,15 @@ struct ExactMean {
         const double2 a = __ldg(r), b = __ldg(r + 1);
         x = a.y; y = b.x; z = b.y;
     }
+    __device__ __forceinline__ uint32_t rank(const float4&, uint32_t idx) const { return idx; }  // candidate lists are in visit order
 };
 template <class Fetch>
 __device__ __forceinline__ void fold_exact(const Fetch& fetch, const float4& q, uint32_t idx, double px, double py, double pz, Best& b) {
     double x, y, z;
     fetch(q, x, y, z);
     const double d2 = sq3_exact(x - px, y - py, z - pz);
-    if (d2 < b.d2) { b.d2 = d2; b.idx = idx; }
+    const uint32_t r = fetch.rank(q, idx);
+    if (closer(d2, r, b)) { b.d2 = d2; b.idx = idx; b.rank = r; }
 }
 template <class Fetch>
 __device__ __forceinline__ void visit_points_exact(const float4* __restrict__ pts, uint32_t idx0, uint32_t n, double px, double py, double pz, Best& b,
@@ -253,17 +265,18 @@ __device__ __forceinline__ void visit_points(const float4* __restrict__ pts, uin
         double x, y, z;
         fetch(q, x, y, z);
         const double d2 = sq3_exact(x - Q.px, y - Q.py, z - Q.pz);
-        if (d2 < b.d2 || (d2 == b.d2 && mi < b.idx)) { b.d2 = d2; b.idx = mi; }
+        const uint32_t r = fetch.rank(q, mi);
+        if (closer(d2, r, b)) { b.d2 = d2; b.idx = mi; b.rank = r; }
     } else {
         Best e;
         visit_points_exact(pts, idx0, n, Q.px, Q.py, Q.pz, e, fetch);
-        if (e.idx != 0xffffffffu && (e.d2 < b.d2 || (e.d2 == b.d2 && e.idx < b.idx))) b = e;
+        if (e.idx != kNone && closer(e.d2, e.rank, b)) b = e;
     }
 #endif
 }
-// folds a candidate found elsewhere (smaller distance wins, then smaller index)
+// folds a candidate found elsewhere (smaller distance wins, then smaller rank)
 __device__ __forceinline__ void fold_best(Best& b, const Best& o) {
-    if (o.d2 < b.d2 || (o.d2 == b.d2 && o.idx < b.idx)) b = o;
+    if (o.idx != kNone && closer(o.d2, o.rank, b)) b = o;
 }
 
 // Squared-distance lower bound helper (fp32, units of voxel_size, deliberately under-estimated): gap along one axis
@@ -300,7 +313,7 @@ __device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, do
     uint2 centre;
     const int row = dir_lookup(map, kx, ky, kz, centre);
     if (row < 0) return -1;
-    const uint2 d = dir_column(map, row, 10);  // {first candidate, count}
+    const uint2 d = __ldg(reinterpret_cast<const uint2*>(map.drows + row_word(static_cast<size_t>(row), kRowCandFirst)));  // {first candidate, count}
     Best b;
     visit_points(map.vcand, d.x, d.y, Query(px, py, pz), b, ExactMean{map.vslots});
     return (b.idx == 0xffffffffu) ? -1 : static_cast<int>(__float_as_uint(__ldg(map.vcand + b.idx).w));
@@ -632,13 +645,15 @@ __device__ void solve_step(IcpState* st, const IcpParams& prm, SolveScratch* sc,
     for (int i = 0; i < 9; ++i) st->Rinv[i] = Ri[i];
 }
 
-// One P2P / GICP correspondence -> accumulators (reg.cpp:28-51 / 85-132).  m = index of the matched map point or -1
-// (then the reference's default-constructed neighbour at the origin applies, Q2); p = T * s exactly as the search saw it.
+// One P2P / GICP correspondence -> accumulators (reg.cpp:28-51 / 85-132).  target = the matched map point (win[i]), m =
+// its device index or -1 (GICP reads its covariance record; -1: the reference's default-constructed neighbour at the
+// origin, Q2); p = T * s exactly as the search saw it.
 template <int METHOD>
-__device__ __forceinline__ void linearize_point_pair(const MapView& map, int m, double sx, double sy, double sz, double px, double py, double pz,
-                                                     const double* s_Tinv, const double* s_Rinv, double th, double max_dist2, double* acc) {
-    double tx = 0.0, ty = 0.0, tz = 0.0;  // default-constructed neighbour at the origin (Q2, vhm.cpp:37)
-    if (m >= 0) { const float4 t = __ldg(map.pts + m); tx = t.x; ty = t.y; tz = t.z; }
+__device__ __forceinline__ void linearize_point_pair(const MapView& map, int m, const float4& target, double sx, double sy, double sz, double px,
+                                                     double py, double pz, const double* s_Tinv, const double* s_Rinv, double th, double max_dist2,
+                                                     double* acc) {
+    // target = the matched map point, or the default-constructed neighbour at the origin when nothing was found (Q2, vhm.cpp:37)
+    const double tx = target.x, ty = target.y, tz = target.z;
     if (!(sq3_exact(tx - px, ty - py, tz - pz) < max_dist2)) return;  // vhm.cpp:66
     if (METHOD == 0) {
         const double lx = s_Tinv[0] * tx + s_Tinv[1] * ty + s_Tinv[2] * tz + s_Tinv[3];
@@ -862,7 +877,10 @@ template <bool COOP, int FUSE>
 #endif
 __global__ void __launch_bounds__(kIcpThreads, FUSE == 1 ? 3 : (FUSE == 0 ? 4 : ELM_MINBLOCKS))
 icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ orig, IcpParams prm, IcpState* __restrict__ st,
-                         int* __restrict__ match, double* __restrict__ partials, unsigned int* __restrict__ ticket, int solve_here) {
+                         IcpWork wk, int solve_here) {
+    int* const __restrict__ match = wk.match;
+    double* const __restrict__ partials = wk.partials;
+    unsigned int* const __restrict__ ticket = wk.ticket;
     constexpr bool kFuse = FUSE >= 0;
     constexpr int NACC = AccSize<FUSE == 0 ? 0 : 1>::value;
     __shared__ double s_Tinv[kFuse ? 12 : 1], s_Rinv[kFuse ? 9 : 1];
@@ -874,21 +892,18 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
     __shared__ double s_T[12];
     __shared__ double s_px[COOP ? kIcpThreads : 1], s_py[COOP ? kIcpThreads : 1], s_pz[COOP ? kIcpThreads : 1];
     __shared__ unsigned long long s_best[COOP ? kIcpThreads : 1];
-    __shared__ unsigned int s_win[COOP ? kIcpThreads : 1];
+    __shared__ unsigned long long s_win[COOP ? kIcpThreads : 1];      // rank << 32 | index of the winner among the exact minima
     __shared__ unsigned long long s_item_d2[COOP ? kItemCap : 1];
-    __shared__ unsigned int s_item_idx[COOP ? kItemCap : 1];
+    __shared__ unsigned long long s_item_win[COOP ? kItemCap : 1];
     __shared__ uint16_t s_items[COOP ? kItemCap : 1];
     __shared__ int s_nitems[kItemGroups];
-#if defined(ELM_GREEDY_ITEMS) && !defined(ELM_BLOCK_SCOPE)
-    __shared__ int s_cursor[kItemGroups];
-#endif
 
     pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int grp = tid / kGroupThreads, gtid = tid % kGroupThreads;  // item-list group of this thread and its rank in it
     uint16_t* const g_items = s_items + (COOP ? grp * kGroupCap : 0);
     unsigned long long* const g_item_d2 = s_item_d2 + (COOP ? grp * kGroupCap : 0);
-    unsigned int* const g_item_idx = s_item_idx + (COOP ? grp * kGroupCap : 0);
+    unsigned long long* const g_item_win = s_item_win + (COOP ? grp * kGroupCap : 0);
     auto group_sync = [&]() { if (kItemGroups == 1) __syncthreads(); else __syncwarp(); };
 
     // ---- prologue that does not depend on the previous kernel: barriers + the TMA of the first scan tile
@@ -949,6 +964,7 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
         uint32_t own_cols = 0;  // voxel mask (bit 3 c + iz) of the columns this thread has to walk itself
         int row = -1;
         int my_match = -1;
+        uint32_t qkey_lo = kNone, qkey_hi = kNone;  // packed floor key of the query (all ones: outside the key range)
         if (mine) {
             const float* sp = &s_tile[buf][tid * 3];
             sx = sp[0]; sy = sp[1]; sz = sp[2];
@@ -965,6 +981,10 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
 #endif
             uint2 centre;
             row = dir_lookup(map, kx, ky, kz, centre);
+            if (key_in_range(kx) && key_in_range(ky) && key_in_range(kz)) {
+                const uint64_t qk = pack_key(kx, ky, kz);
+                qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32);
+            }
 #ifdef ELM_PHASE_TIMING
             ELM_USE(row == 0x7fffffff);
             { const long long t__ = clock64(); if (prm.stats && (tid & 31) == 0) atomicAdd(prm.stats + 17, static_cast<unsigned long long>(t__ - ftick)); ftick = t__; }
@@ -973,7 +993,7 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             ELM_USE(row == 0x7fffffff);
             ELM_TICK(3);
             if (COOP) {
-                s_win[tid] = 0xffffffffu;
+                s_win[tid] = ~0ull;
                 if (row >= 0) {
                     // the z-column holding the voxel whose STORED-key cell contains the query: insert keys truncate toward
                     // zero (vhm.cpp:275), so on a negative axis that cell is the floor key + 1
@@ -1009,7 +1029,7 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                                     // the item's column descriptor travels with it: cp.async (8 bytes, no registers) into the slot
                                     // that later receives the item's result, so phase B starts streaming at once
                                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(g_item_d2 + w)),
-                                                 "l"(map.drows + static_cast<size_t>(row) * 12 + c) : "memory");
+                                                 "l"(map.drows + row_col_word(static_cast<size_t>(row), c)) : "memory");
                                     g_items[w++] = static_cast<uint16_t>((tid << 7) | (c << 3) | zm);
                                 }
                             }
@@ -1038,90 +1058,6 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             ELM_TICK(5);
             // ---- phase B: one thread per (query, column) item
             const int nitems = min(s_nitems[grp], kGroupCap);  // (items beyond the cap were never written: their owners kept them)
-#if defined(ELM_GREEDY_ITEMS) && !defined(ELM_BLOCK_SCOPE)
-            // EXPERIMENTAL, NOT MEASURED YET (-DELM_GREEDY_ITEMS; see DESIGN.md "What comes next" and profiles/sim/item_balance.py):
-            // greedy list scheduling at batch granularity.  One item per lane and round costs the longest run of every round
-            // (44 % lane efficiency in the simulation); here every lane advances ITS item by one batch of loads per warp step and
-            // pulls the next item of the warp's list from a shared cursor as soon as it runs out (11.1 -> 7.7 warp steps per tile
-            // in the simulation).  Same arithmetic and the same merge as the loop below.
-            {
-                if (gtid == 0) s_cursor[grp] = 32;
-                __syncwarp();
-                constexpr uint32_t K = ELM_BATCH;
-                const float kInf = __int_as_float(0x7f800000);
-                int j = gtid < nitems ? gtid : -1;
-                uint32_t i = 0, rs = 0, end = 0, last_pair = 0, mi = 0;
-                float m = kInf, s2 = kInf, qfx = 0.f, qfy = 0.f, qfz = 0.f;
-                int q = 0;
-                auto begin_item = [&]() {   // -> false when the item is a hole or its run is empty (nothing to scan)
-                    const int it = g_items[j];
-                    if (it == kNoItem) return false;
-                    q = it >> 7;
-                    uint32_t rl;
-                    const unsigned long long dbits = g_item_d2[j];
-                    column_run(make_uint2(static_cast<uint32_t>(dbits), static_cast<uint32_t>(dbits >> 32)), static_cast<uint32_t>(it & 7), rs, rl);
-                    g_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
-                    g_item_idx[j] = 0xffffffffu;
-                    if (rl == 0) return false;
-                    visited += rl;
-                    end = rs + rl;
-                    i = rs & ~1u;
-                    last_pair = (end - 1) & ~1u;
-                    m = kInf; s2 = kInf; mi = rs;
-                    qfx = static_cast<float>(s_px[q]); qfy = static_cast<float>(s_py[q]); qfz = static_cast<float>(s_pz[q]);
-                    return true;
-                };
-                auto next_item = [&]() {    // pull items until one has something to scan, or the list is exhausted
-                    for (;;) {
-                        j = atomicAdd(&s_cursor[grp], 1);
-                        if (j >= nitems) { j = -1; return; }
-                        if (begin_item()) return;
-                    }
-                };
-                if (j >= 0 && !begin_item()) next_item();
-                while (__any_sync(kFull, j >= 0)) {
-                    if (j >= 0) {
-                        float4 q0[K], q1[K];
-#pragma unroll
-                        for (uint32_t u = 0; u < K; ++u) ldg256(map.pts + min(i + 2 * u, last_pair), q0[u], q1[u]);
-#pragma unroll
-                        for (uint32_t u = 0; u < K; ++u) {
-                            const uint32_t pi = i + 2 * u;
-                            {
-                                const float dx = q0[u].x - qfx, dy = q0[u].y - qfy, dz = q0[u].z - qfz;
-                                float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                                d = (pi >= rs && pi < end) ? d : kInf;
-                                s2 = fminf(s2, fmaxf(d, m)); mi = (d < m) ? pi : mi; m = fminf(m, d);
-                            }
-                            {
-                                const float dx = q1[u].x - qfx, dy = q1[u].y - qfy, dz = q1[u].z - qfz;
-                                float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                                d = (pi + 1 < end) ? d : kInf;
-                                s2 = fminf(s2, fmaxf(d, m)); mi = (d < m) ? pi + 1 : mi; m = fminf(m, d);
-                            }
-                        }
-                        i += 2 * K;
-                        if (i >= end) {     // run finished: decide exactly (same rule as visit_points), publish, pull the next item
-                            const Query Qj(s_px[q], s_py[q], s_pz[q]);
-                            const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Qj.band);
-                            const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
-                            Best ib;
-                            if (s2 > T) {
-                                const float4 c = __ldg(map.pts + mi);
-                                ib.d2 = sq3_exact(static_cast<double>(c.x) - Qj.px, static_cast<double>(c.y) - Qj.py, static_cast<double>(c.z) - Qj.pz);
-                                ib.idx = mi;
-                            } else {
-                                visit_points_exact(map.pts, rs, end - rs, Qj.px, Qj.py, Qj.pz, ib, ExactPoint());
-                            }
-                            g_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
-                            g_item_idx[j] = ib.idx;
-                            if (ib.idx != 0xffffffffu) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
-                            next_item();
-                        }
-                    }
-                }
-            }
-#else
             for (int j = gtid; j < nitems; j += kGroupThreads) {
                 const int it = g_items[j];
                 if (it == kNoItem) continue;
@@ -1133,10 +1069,9 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                 visit_points(map.pts, rs, rl, Query(s_px[q], s_py[q], s_pz[q]), ib);
                 visited += rl;
                 g_item_d2[j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
-                g_item_idx[j] = ib.idx;
+                g_item_win[j] = rank_idx(ib.rank, ib.idx);
                 if (ib.idx != 0xffffffffu) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
             }
-#endif
             if (mine) {
                 if (own_cols) {
 #pragma unroll 1
@@ -1160,23 +1095,30 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
                 const int it = g_items[j];
                 if (it == kNoItem) continue;
                 const int q = it >> 7;
-                if (g_item_idx[j] != 0xffffffffu && g_item_d2[j] == s_best[q]) atomicMin(&s_win[q], g_item_idx[j]);
+                if (g_item_win[j] != ~0ull && g_item_d2[j] == s_best[q]) atomicMin(&s_win[q], g_item_win[j]);
             }
             if (mine && b.idx != 0xffffffffu && static_cast<unsigned long long>(__double_as_longlong(b.d2)) == s_best[tid])
-                atomicMin(&s_win[tid], b.idx);
+                atomicMin(&s_win[tid], rank_idx(b.rank, b.idx));
             group_sync();
             ELM_TICK(7);
-            if (mine) my_match = (s_win[tid] == 0xffffffffu) ? -1 : static_cast<int>(s_win[tid]);
+            if (mine) my_match = (s_win[tid] == ~0ull) ? -1 : static_cast<int>(static_cast<uint32_t>(s_win[tid]));
         }
-        if (mine && match) {
+        // the matched point itself (streamed by the accumulation; {0, 0, 0} = the reference's default neighbour, Q2) and the
+        // warm start of the next iteration's search
+        float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
+        if (mine) {
+            if (my_match >= 0) wpt = __ldg(map.pts + my_match);
             const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
-            match[orig ? orig[gi] : gi] = my_match;
+            const size_t oi = orig ? static_cast<size_t>(orig[gi]) : gi;
+            if (match) match[oi] = my_match;
+            if (wk.win) wk.win[oi] = wpt;
+            if (wk.memo) wk.memo[oi] = make_uint4(static_cast<uint32_t>(row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
         }
         if (kFuse) {  // linearise this tile's correspondences and fold them into the block's running sums
             double acc[NACC];
 #pragma unroll
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-            if (mine) linearize_point_pair<FUSE == 1 ? 1 : 0>(map, my_match, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+            if (mine) linearize_point_pair<FUSE == 1 ? 1 : 0>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
             block_sum_into<NACC, FUSE == 0>(acc, s_red, s_sum);
         } else if (next < ntiles) {
             __syncthreads();  // everyone is done with the tile's shared state before it is refilled (block-uniform)
@@ -1191,6 +1133,298 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
         }
     }
     if (kFuse) finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, partials, ticket, solve_here);
+}
+
+// ======================================================================================================================
+// search: P2P / GICP, warm-started (second iteration of a call onwards)
+// ======================================================================================================================
+// The search of iteration k+1 asks the same question as iteration k from a slightly moved pose.  The point matched last
+// time (win[i], still a member of the query's 27 voxels whenever the query's key did not change — memo[i] says so without a
+// directory lookup) gives an upper bound d on the nearest distance BEFORE anything of the map is read, so the search only
+// has to look at map points that can be at least as close: the OCTANTS (half-voxel cells; the points of a voxel are stored
+// sorted by octant, the row of the directory entry carries every voxel's octant offsets) whose box lies within d.  On the
+// benchmark map that is ~10-15 points in ~3 short runs instead of ~36 points in whole voxels, and there is no dependent
+// chain home voxel -> bound -> neighbours any more: one round trip for the column records, one for the runs.
+// Exactness: every point of the 27 voxels at distance <= d lies in an octant whose box is within d, all of those are
+// visited with exact fp64 distances, the previous match itself competes with its rank — so the result (nearest point,
+// first-in-visit-order among equals, vhm.cpp:45) is the one the full visit finds.  A query whose key changed looks its row
+// up again and keeps the bound only if the old match is still inside its 27 voxels; otherwise it visits everything.
+//
+//   A  thread per QUERY : transform, bound, per axis which half-cells are within the bound (separable test, then the voxel's
+//                         box), one 32-byte record per needed column, one run per needed voxel (octants lowest..highest
+//                         needed; runs of z-neighbours that touch are merged), cut into work items of <= 3 aligned pairs
+//                         in the WARP's list;
+//   B  lane per ITEM    : three 32-byte loads, exact distances, atomicMin of the distance bits per query;
+//   C  lane per ITEM    : among the exact minima the smallest rank wins (atomicMin of rank << 32 | index).
+// Items that do not fit the list stay with their owner thread, which scans those runs itself.
+#ifndef ELM_WARM_CAP
+#define ELM_WARM_CAP 256
+#endif
+constexpr int kWarmCap = ELM_WARM_CAP;  // work items per warp
+
+// squared gap (voxel units, fp32, deliberately under-estimated) between the in-cell coordinate f of the query (relative to
+// its floor key) and the interval [a, b]
+__device__ __forceinline__ float interval_gap2(float f, float a, float b) {
+    const float g = fmaxf(fmaxf(fmaxf(a - f, f - b), 0.0f) - 1e-5f, 0.0f);
+    return g * g;
+}
+// Along one axis: bit 2 (o + 1) + h set <=> half h of the voxel at offset o (stored key kq + o, span per the truncation
+// rule of axis_gap2, halves split at the middle of the span — voxel_key.hpp) is within `bound` of the query on this axis
+// alone.  gv[o + 1] = gap to the whole span of that voxel.
+__device__ __forceinline__ uint32_t axis_halves(int kq, float f, float bound, float gv[3]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int o = -1; o <= 1; ++o) {
+        const int c = kq + o;
+        const float lo = static_cast<float>(o - (c <= 0 ? 1 : 0)), hi = static_cast<float>(o + (c >= 0 ? 1 : 0));
+        const float mid = 0.5f * (lo + hi);
+        const float g0 = interval_gap2(f, lo, mid), g1 = interval_gap2(f, mid, hi);
+        gv[o + 1] = fminf(g0, g1);
+        if (!(g0 * 0.9999f > bound)) m |= 1u << (2 * (o + 1));
+        if (!(g1 * 0.9999f > bound)) m |= 2u << (2 * (o + 1));
+    }
+    return m;
+}
+// stored (insert) key of a map coordinate: static_cast<int>(p / voxel_size), truncation toward zero (vhm.cpp:275)
+__device__ __forceinline__ int stored_key(float p, const MapView& map) {
+    const double q = (map.inv_voxel_size != 0.0) ? __dmul_rn(static_cast<double>(p), map.inv_voxel_size) : __ddiv_rn(static_cast<double>(p), map.voxel_size);
+    return static_cast<int>(q);
+}
+// exact scan of the points [s, e) (a run of at most three aligned pairs starting at s & ~1) for the query (px, py, pz)
+__device__ __forceinline__ void scan_item_exact(const float4* __restrict__ pts, uint32_t s, uint32_t e, double px, double py, double pz, Best& b) {
+    const uint32_t p0 = s & ~1u, last_pair = (e - 1) & ~1u;
+    float4 q0[3], q1[3];
+#pragma unroll
+    for (uint32_t u = 0; u < 3; ++u) ldg256(pts + min(p0 + 2 * u, last_pair), q0[u], q1[u]);
+#pragma unroll
+    for (uint32_t u = 0; u < 3; ++u) {
+        const uint32_t pi = p0 + 2 * u;
+        if (pi >= s && pi < e) fold_exact(ExactPoint(), q0[u], pi, px, py, pz, b);
+        if (pi + 1 >= s && pi + 1 < e) fold_exact(ExactPoint(), q1[u], pi + 1, px, py, pz, b);
+    }
+}
+
+template <int FUSE>
+__global__ void __launch_bounds__(kIcpThreads, FUSE == 1 ? 3 : 4)
+icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int solve_here) {
+    constexpr bool kFuse = FUSE >= 0;
+    constexpr int NACC = AccSize<FUSE == 0 ? 0 : 1>::value;
+    __shared__ double s_Tinv[kFuse ? 12 : 1], s_Rinv[kFuse ? 9 : 1];
+    __shared__ double s_red[kFuse ? kIcpWarps : 1][kAcc], s_sum[kAcc], s_acc[kAcc];
+    __shared__ SolveScratch s_solve;
+    __shared__ bool s_last;
+    __shared__ __align__(16) float s_tile[kIcpThreads * 3];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ double s_T[12];
+    __shared__ double s_px[kIcpThreads], s_py[kIcpThreads], s_pz[kIcpThreads];
+    __shared__ unsigned long long s_best[kIcpThreads];   // bits of the smallest exact squared distance of the query
+    __shared__ unsigned long long s_win[kIcpThreads];    // rank << 32 | index among the candidates at that distance
+    __shared__ unsigned long long s_item[kIcpWarps][kWarmCap];  // item {start, (end - pair start) | lane << 8}; after phase B: distance bits
+    __shared__ unsigned int s_item_idx[kIcpWarps][kWarmCap];    // phase B result: index of the item's nearest point
+    __shared__ unsigned char s_item_q[kIcpWarps][kWarmCap];     // owner lane of the item
+    __shared__ int s_nitems[kIcpWarps];
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int tile_pts = kIcpThreads;
+    const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
+    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    auto tile_count = [&](int t) { return min(tile_pts, prm.n - t * tile_pts); };
+    auto tile_tma_ok = [&](int t) { return base_aligned && ((tile_count(t) * 12) & 15) == 0; };
+    auto issue = [&](int t) {
+        const uint32_t bytes = tile_count(t) * 12;
+        mbar_expect_tx(&s_bar, bytes);
+        tma_load_1d(s_tile, scan + static_cast<size_t>(t) * tile_pts * 3, bytes, &s_bar);
+    };
+    const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
+    const float kInf = __int_as_float(0x7f800000);
+    uint32_t visited = 0, searched = 0;
+    int tile = blockIdx.x;
+    uint32_t phase = 0;
+    const bool first_by_tma = tile < ntiles && tile_tma_ok(tile);
+    if (first_by_tma && tid == 0) issue(tile);  // the scan is never written inside the loop: its first tile may start before the wait
+    pdl_wait();
+    if (st->done) {
+        if (first_by_tma) mbar_wait(&s_bar, 0);
+        return;
+    }
+    if (tid < 12) s_T[tid] = st->T[tid];
+    if (kFuse) {
+        if (tid < 12) s_Tinv[tid] = st->Tinv[tid];
+        if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+        if (tid < kAcc) s_sum[tid] = 0.0;
+    }
+    for (bool first = true; tile < ntiles; tile += gridDim.x, first = false) {
+        const int cnt = tile_count(tile);
+        const bool mine = tid < cnt;
+        const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
+        // the previous iteration's result for this query: coalesced, in flight while the scan tile lands
+        uint4 memo = make_uint4(kNone, kNone, kNone, kNone);
+        float4 prev = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
+        if (mine) { memo = wk.memo[gi]; prev = wk.win[gi]; }
+        if (tile_tma_ok(tile)) {
+            if (!first && tid == 0) issue(tile);
+            mbar_wait(&s_bar, phase);
+            phase ^= 1;
+        } else {
+            const int nf = cnt * 3;
+            for (int i = tid; i < nf; i += kIcpThreads) s_tile[i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
+        }
+        if (lane == 0) s_nitems[warp] = 0;
+        __syncthreads();
+        // ---- phase A
+        double px = 0, py = 0, pz = 0, sx = 0, sy = 0, sz = 0;
+        Best own;  // the previous match + whatever this thread has to scan itself
+        int row = -1;
+        uint32_t qkey_lo = kNone, qkey_hi = kNone;
+        if (mine) {
+            sx = s_tile[tid * 3]; sy = s_tile[tid * 3 + 1]; sz = s_tile[tid * 3 + 2];
+            px = row_apply_exact(s_T, 0, sx, sy, sz);
+            py = row_apply_exact(s_T, 1, sx, sy, sz);
+            pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            float fx, fy, fz;
+            const int kx = voxel_floor(px, map, &fx), ky = voxel_floor(py, map, &fy), kz = voxel_floor(pz, map, &fz);
+            ++searched;
+            const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
+            if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
+            bool prev_ok = memo.w != kNone;
+            if (in_range && memo.y == qkey_lo && memo.z == qkey_hi) {
+                row = static_cast<int>(memo.x);  // same voxel as last time: same row, and the old match is one of its candidates
+            } else {
+                uint2 centre;
+                row = dir_lookup(map, kx, ky, kz, centre);
+                if (prev_ok) {  // still inside the 27 voxels of the new key?
+                    const int cx = stored_key(prev.x, map) - kx, cy = stored_key(prev.y, map) - ky, cz = stored_key(prev.z, map) - kz;
+                    prev_ok = cx >= -1 && cx <= 1 && cy >= -1 && cy <= 1 && cz >= -1 && cz <= 1;
+                }
+            }
+            s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
+            s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
+            s_win[tid] = ~0ull;
+            if (row >= 0) {
+                float bound = kInf;
+                if (prev_ok) {
+                    own.d2 = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
+                    own.idx = memo.w; own.rank = __float_as_uint(prev.w);
+                    bound = __double2float_ru(own.d2) * inv_vs2_up;
+                }
+                float gvx[3], gvy[3], gvz[3];
+                const uint32_t hx = axis_halves(kx, fx, bound, gvx), hy = axis_halves(ky, fy, bound, gvy), hz = axis_halves(kz, fz, bound, gvz);
+                const float gzmin = fminf(fminf(gvz[0], gvz[1]), gvz[2]);
+                uint32_t colmask = 0;
+#pragma unroll
+                for (int c = 0; c < 9; ++c)
+                    if (((hx >> (2 * (c / 3))) & 3u) && ((hy >> (2 * (c % 3))) & 3u) && !((gvx[c / 3] + gvy[c % 3] + gzmin) * 0.9999f > bound)) colmask |= 1u << c;
+                auto emit = [&](uint32_t rs, uint32_t re) {
+                    if (re <= rs) return;
+                    visited += re - rs;
+                    const uint32_t p0 = rs & ~1u;
+                    const uint32_t npairs = ((re - 1) >> 1) - (rs >> 1) + 1;
+                    const int nit = static_cast<int>((npairs + 2) / 3);
+                    const int pos = atomicAdd(&s_nitems[warp], nit);
+                    if (pos + nit <= kWarmCap) {
+                        for (int i = 0; i < nit; ++i) {
+                            const uint32_t is = (i == 0) ? rs : p0 + 6u * i, ie = min(re, p0 + 6u * (i + 1));
+                            s_item[warp][pos + i] = (static_cast<unsigned long long>((ie - (is & ~1u)) | (static_cast<uint32_t>(lane) << 8)) << 32) | is;
+                        }
+                    } else {  // list full: holes for the part of the claim that is inside the list, and this thread scans the run itself
+                        for (int j = pos; j < kWarmCap; ++j) s_item[warp][j] = 0ull;
+                        for (uint32_t is = rs; is < re;) {
+                            const uint32_t ie = min(re, (is & ~1u) + 6u);
+                            scan_item_exact(map.pts, is, ie, px, py, pz, own);
+                            is = ie;
+                        }
+                    }
+                };
+                while (colmask) {
+                    const int c = __ffs(colmask) - 1;
+                    colmask &= colmask - 1;
+                    const int ox = c / 3, oy = c - 3 * ox;
+                    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+                    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(map.drows + row_col_word(static_cast<size_t>(row), c)));
+                    const uint32_t xpat = (((hx >> (2 * ox)) & 1u) ? 0x55u : 0u) | (((hx >> (2 * ox)) & 2u) ? 0xaau : 0u);
+                    const uint32_t ypat = (((hy >> (2 * oy)) & 1u) ? 0x33u : 0u) | (((hy >> (2 * oy)) & 2u) ? 0xccu : 0u);
+                    const float gxy = (ox == 0 ? gvx[0] : (ox == 1 ? gvx[1] : gvx[2])) + (oy == 0 ? gvy[0] : (oy == 1 ? gvy[1] : gvy[2]));
+                    uint32_t run_s = 0, run_e = 0, vfirst = r0;
+#pragma unroll
+                    for (int dz = 0; dz < 3; ++dz) {
+                        const uint32_t n = (r1 >> (kDirCountBits * dz)) & kDirCountMask;
+                        const uint32_t zh = (hz >> (2 * dz)) & 3u;
+                        if (n && zh && !((gxy + gvz[dz]) * 0.9999f > bound)) {
+                            const unsigned long long ow = (static_cast<unsigned long long>(dz == 0 ? r3 : (dz == 1 ? r5 : r7)) << 32) | (dz == 0 ? r2 : (dz == 1 ? r4 : r6));
+                            uint32_t a = 0, e = n;
+                            if (ow >> 56) {  // octant words valid (byte 7 = n for cap <= 255, 0 otherwise)
+                                const uint32_t need = xpat & ypat & (((zh & 1u) ? 0x0fu : 0u) | ((zh & 2u) ? 0xf0u : 0u));
+                                const int lo = __ffs(need) - 1, hi = 32 - __clz(need);  // octants lo .. hi - 1
+                                a = lo ? static_cast<uint32_t>(ow >> (8 * (lo - 1))) & 0xffu : 0u;
+                                e = hi < 8 ? static_cast<uint32_t>(ow >> (8 * (hi - 1))) & 0xffu : n;
+                            }
+                            const uint32_t rs = vfirst + a, re = vfirst + e;
+                            if (re > rs) {
+                                if (run_e > run_s && rs <= run_e + 2) run_e = re;  // touches (or nearly) the run of the voxel below: one run
+                                else { emit(run_s, run_e); run_s = rs; run_e = re; }
+                            }
+                        }
+                        vfirst += n;
+                    }
+                    emit(run_s, run_e);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- phase B
+        const int nitems = min(s_nitems[warp], kWarmCap);
+        for (int j = lane; j < nitems; j += 32) {
+            const unsigned long long it = s_item[warp][j];
+            const uint32_t is = static_cast<uint32_t>(it), info = static_cast<uint32_t>(it >> 32);
+            const int q = (warp << 5) | static_cast<int>(info >> 8);
+            s_item_q[warp][j] = static_cast<unsigned char>(info >> 8);
+            Best ib;
+            if (info & 0xffu) scan_item_exact(map.pts, is, (is & ~1u) + (info & 0xffu), s_px[q], s_py[q], s_pz[q], ib);
+            s_item[warp][j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
+            s_item_idx[warp][j] = ib.idx;
+            if (ib.idx != kNone) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
+        }
+        if (mine && own.idx != kNone) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(own.d2)));
+        __syncwarp();
+        // ---- phase C
+        for (int j = lane; j < nitems; j += 32) {
+            const uint32_t idx = s_item_idx[warp][j];
+            const int q = (warp << 5) | s_item_q[warp][j];
+            if (idx != kNone && s_item[warp][j] == s_best[q]) atomicMin(&s_win[q], rank_idx(__float_as_uint(__ldg(map.pts + idx).w), idx));
+        }
+        if (mine && own.idx != kNone && static_cast<unsigned long long>(__double_as_longlong(own.d2)) == s_best[tid])
+            atomicMin(&s_win[tid], rank_idx(own.rank, own.idx));
+        __syncwarp();
+        int my_match = -1;
+        float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
+        if (mine) {
+            if (s_win[tid] != ~0ull) { my_match = static_cast<int>(static_cast<uint32_t>(s_win[tid])); wpt = __ldg(map.pts + my_match); }
+            if (wk.match) wk.match[gi] = my_match;
+            wk.win[gi] = wpt;
+            wk.memo[gi] = make_uint4(static_cast<uint32_t>(row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+        }
+        if (kFuse) {
+            double acc[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+            if (mine) linearize_point_pair<FUSE == 1 ? 1 : 0>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+            block_sum_into<NACC, FUSE == 0>(acc, s_red, s_sum);
+        } else if (tile + static_cast<int>(gridDim.x) < ntiles) {
+            __syncthreads();  // the tile buffer is refilled next
+        }
+    }
+    if (prm.stats) {
+        for (int o = 16; o > 0; o >>= 1) { visited += __shfl_xor_sync(kFull, visited, o); searched += __shfl_xor_sync(kFull, searched, o); }
+        if (lane == 0 && searched) {
+            atomicAdd(prm.stats, static_cast<unsigned long long>(visited));
+            atomicAdd(prm.stats + 1, static_cast<unsigned long long>(searched));
+        }
+    }
+    if (kFuse) finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here);
 }
 
 // ======================================================================================================================
@@ -1219,9 +1453,12 @@ icp_search_means_kernel(MapView map, const float* __restrict__ scan, const int* 
 // sums them in a fixed order into st->acc and, when `solve_here`, runs the solve/update step.
 template <int METHOD>
 __global__ void __launch_bounds__(kIcpThreads, 2)
-icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __restrict__ match, IcpParams prm, IcpState* __restrict__ st,
-                      double* __restrict__ partials, unsigned int* __restrict__ ticket, int solve_here) {
+icp_accumulate_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int solve_here) {
     constexpr int NACC = AccSize<METHOD>::value;
+    const int* const __restrict__ match = wk.match;
+    const float4* const __restrict__ win = wk.win;
+    double* const __restrict__ partials = wk.partials;
+    unsigned int* const __restrict__ ticket = wk.ticket;
     __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
     __shared__ double s_red[kIcpWarps][kAcc];
     __shared__ SolveScratch s_solve;
@@ -1289,7 +1526,7 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
         for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
             const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
             const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            const int m = match[i];
+            const int m = (METHOD == 0) ? 0 : match[i];  // (P2P needs only the streamed target)
             if (METHOD == 2) {
                 double mx = 0.0, my = 0.0, mz = 0.0;  // default CovStruct (I, 0)  (Q2, vhm.cpp:104)
                 if (m >= 0) {
@@ -1299,7 +1536,8 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, const int* __
                 }
                 if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_voxel_pair(sx, sy, sz, m, mx, my, mz);  // vhm.cpp:129
             } else {
-                linearize_point_pair<METHOD == 1 ? 1 : 0>(map, m, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+                const float4 target = __ldg(win + i);  // coalesced: the search wrote the matched point itself
+                linearize_point_pair<METHOD == 1 ? 1 : 0>(map, m, target, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
             }
         }
     }
@@ -1431,30 +1669,35 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
     return cudaGetLastError();
 }
 
-// fuse: linearise + reduce (+ solve when solve_here) inside the search kernel (P2P / GICP only); then `match` may be NULL
-cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, int* match,
-                              int grid, int prune, int fuse, double* partials, unsigned int* ticket, int solve_here, cudaStream_t s) {
+// fuse: linearise + reduce (+ solve when solve_here) inside the search kernel (P2P / GICP only); then wk.match may be NULL.
+// warm: P2P / GICP — start from the previous iteration's wk.win / wk.memo (icp_search_warm_kernel); needs prune.
+cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, const IcpWork& wk,
+                              int grid, int prune, int fuse, int warm, int solve_here, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
-    if (prm.method <= 1) {
-#define ELM_LAUNCH(C, F) e = launch_pdl(icp_search_points_kernel<C, F>, grid, kIcpThreads, 0, s, map, scan, orig, prm, st, match, partials, ticket, solve_here)
+    if (prm.method <= 1 && warm && prune && !orig) {
+        if (!fuse) e = launch_pdl(icp_search_warm_kernel<-1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
+        else if (prm.method == 0) e = launch_pdl(icp_search_warm_kernel<0>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
+        else e = launch_pdl(icp_search_warm_kernel<1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
+    } else if (prm.method <= 1) {
+#define ELM_LAUNCH(C, F) e = launch_pdl(icp_search_points_kernel<C, F>, grid, kIcpThreads, 0, s, map, scan, orig, prm, st, wk, solve_here)
         if (!fuse) { if (prune) ELM_LAUNCH(true, -1); else ELM_LAUNCH(false, -1); }
         else if (prm.method == 0) { if (prune) ELM_LAUNCH(true, 0); else ELM_LAUNCH(false, 0); }
         else { if (prune) ELM_LAUNCH(true, 1); else ELM_LAUNCH(false, 1); }
 #undef ELM_LAUNCH
     } else if (prm.method == 2) {
-        e = launch_pdl(icp_search_means_kernel, grid, kIcpThreads, 0, s, map, scan, orig, prm, static_cast<const IcpState*>(st), match);
+        e = launch_pdl(icp_search_means_kernel, grid, kIcpThreads, 0, s, map, scan, orig, prm, static_cast<const IcpState*>(st), wk.match);
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const int* match, const IcpParams& prm, IcpState* st, double* partials,
-                                  unsigned int* ticket, int solve_here, int grid, cudaStream_t s) {
+cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int solve_here,
+                                  int grid, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
     switch (prm.method) {
-        case 0: e = launch_pdl(icp_accumulate_kernel<0>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
-        case 1: e = launch_pdl(icp_accumulate_kernel<1>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
-        case 2: e = launch_pdl(icp_accumulate_kernel<2>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
-        default: e = launch_pdl(icp_accumulate_kernel<3>, grid, kIcpThreads, 0, s, map, scan, match, prm, st, partials, ticket, solve_here); break;
+        case 0: e = launch_pdl(icp_accumulate_kernel<0>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
+        case 1: e = launch_pdl(icp_accumulate_kernel<1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
+        case 2: e = launch_pdl(icp_accumulate_kernel<2>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
+        default: e = launch_pdl(icp_accumulate_kernel<3>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -14,13 +14,14 @@ int icp_search_grid(const IcpParams& prm, int num_sms);
 int icp_accumulate_grid(const IcpParams& prm, int num_sms);
 
 cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, cudaStream_t s);
-// P2P / GICP / VGICP correspondence search -> match[n] (no-op for AVGICP, which searches inside the accumulation)
-// `orig` (may be NULL): scan is in binned order and match[] must be written at orig[i].
+// P2P / GICP / VGICP correspondence search -> wk.match[n] (+ wk.win, wk.memo for P2P / GICP); no-op for AVGICP, which searches
+// inside the accumulation.  `orig` (may be NULL): scan is in binned order and the outputs are written at orig[i].
 // fuse (P2P / GICP): the search kernel also linearises, reduces and — when solve_here — solves: one launch per iteration.
-cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, int* match,
-                              int grid, int prune, int fuse, double* partials, unsigned int* ticket, int solve_here, cudaStream_t s);
-cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const int* match, const IcpParams& prm, IcpState* st,
-                                  double* partials, unsigned int* ticket, int solve_here, int grid, cudaStream_t s);
+// warm (P2P / GICP): the search starts from the previous iteration's wk.win / wk.memo of the SAME scan (icp_kernels.cu).
+cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, const IcpWork& wk,
+                              int grid, int prune, int fuse, int warm, int solve_here, cudaStream_t s);
+cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int solve_here,
+                                  int grid, cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);
 // spatial binning of the scan (scan_sort.cu)
 int scan_bin_bits(int n);

@@ -54,4 +54,27 @@ ELM_HD void dir_buckets(uint64_t key, uint32_t bmask, uint32_t& b1, uint32_t& b2
 constexpr uint32_t kDirCountBits = 10;                       // per-voxel count field of a column descriptor
 constexpr uint32_t kDirCountMask = (1u << kDirCountBits) - 1;
 
+// ---- directory row: 80 words (320 bytes = ten 32-byte sectors) per directory SLOT ----------------------------------
+//   words 0..7   header  {key_lo, key_hi, first VGICP candidate, candidate count, 27-bit occupancy mask, flags, 0, 0}
+//   words 8+8c.. column c = 3 (dx + 1) + (dy + 1), one sector:
+//                  [0] first stored point of the z-column (x+dx, y+dy, z-1..z+1)   [1] n(z-1) | n(z) << 10 | n(z+1) << 20
+//                  [2..7] three 64-bit OCTANT words, one per voxel of the column (z-1, z, z+1):
+//                         byte k-1 (k = 1..7) = number of the voxel's points in octants < k, byte 7 = min(n, 255)
+// The stored points of a voxel are laid out on the device sorted by octant (hz << 2 | hy << 1 | hx, stable in the canonical
+// order inside an octant), so "octants a..b of voxel v" is the contiguous run [first(v) + byte(a-1), first(v) + byte(b)) —
+// what the warm-started search reads instead of whole voxels.  Along one axis a voxel with stored key c holds p / vs in
+// [c, c+1) for c > 0, (c-1, c] for c < 0 and (-1, 1) for c == 0 (insert keys truncate toward zero, vhm.cpp:275); its upper
+// half is p / vs >= the middle of that span.
+constexpr int kRowWords = 80, kRowHeaderWords = 8, kRowColWords = 8;
+constexpr int kRowKeyLo = 0, kRowKeyHi = 1, kRowCandFirst = 2, kRowCandCount = 3, kRowOccMask = 4, kRowFlags = 5;
+constexpr uint32_t kRowFlagOctants = 1u;   // octant words valid (max_points_per_voxel <= 255)
+constexpr int kOctantCapMax = 255;
+ELM_HD size_t row_word(size_t row, int w) { return row * kRowWords + static_cast<size_t>(w); }
+ELM_HD size_t row_col_word(size_t row, int c) { return row * kRowWords + kRowHeaderWords + static_cast<size_t>(c) * kRowColWords; }
+// upper (1) or lower (0) half of the span of stored key c along one axis, q = p / voxel_size
+ELM_HD int axis_half(double q, int32_t c) {
+    const double mid = (c > 0) ? static_cast<double>(c) + 0.5 : ((c < 0) ? static_cast<double>(c) - 0.5 : 0.0);
+    return q >= mid ? 1 : 0;
+}
+
 }  // namespace elm

@@ -259,6 +259,22 @@ class Registration:
                                         _i(cnt), _d(tgt)))
         return cnt, tgt
 
+    def correspondences_sequence(self, source_local, voxel_map, poses, method, max_dist):
+        """Correspondences at poses[-1] after searching poses[0], poses[1], ... in turn the way the ICP loop does
+        (cold search first, warm-started searches after it)."""
+        src = _xyz(source_local)
+        Ts = np.ascontiguousarray(np.stack([_pose(T) for T in poses]), dtype=np.float64)
+        K = 7 if method == AVGICP else 1
+        cnt = np.zeros(src.shape[0], np.int32)
+        tgt = np.zeros((src.shape[0], K, 3))
+        check(lib().elm_correspondences_sequence(self._h, voxel_map._h, _f(src), src.shape[0], _d(Ts), len(poses), int(method),
+                                                 float(max_dist), _i(cnt), _d(tgt)))
+        return cnt, tgt
+
+    def set_warm_start(self, enable):
+        """P2P / GICP: iterations after the first start their search from the previous match (default on; same results)."""
+        check(lib().elm_registration_set_warm_start(self._h, int(bool(enable))))
+
     # ---- deskew (PcmMatching::DeskewPointCloud's per-point loop, pcm_matching.cpp:499-511, 780-824) ----
     @staticmethod
     def _deskew_tables(t):

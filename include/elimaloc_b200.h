@@ -163,6 +163,12 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
 int elm_correspondences(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
                         int method, double max_search_dist, int32_t* count, double* target);
 
+/* The same dump after a SEQUENCE of poses T_seq[n_poses][16] searched one after the other exactly as the ICP loop does
+ * (first pose: cold search, following poses: warm-started from the previous pose's matches); returns the correspondences
+ * at the last pose.  Test hook: the warm-started search must return what GetCorrespondencePoints returns at that pose. */
+int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double* T_seq,
+                                 int n_poses, int method, double max_search_dist, int32_t* count, double* target);
+
 /* Counters of the last enqueue (kernel launches issued on the stream; used by bench.py's gpu_launches). */
 int elm_registration_launch_count(const elm_registration* reg, int64_t* launches);
 
@@ -192,6 +198,12 @@ int elm_registration_set_binning(elm_registration* reg, int enable);
  * box is provably farther than the best candidate already found, which cannot change the result.  1: visit all 27
  * voxels exactly like GetCorrespondencePoints (voxel_hash_map.cpp:40-51) — same answers, more bytes. */
 int elm_registration_set_exhaustive(elm_registration* reg, int exhaustive);
+
+/* Warm start of the P2P/GICP search (default 1).  From the second iteration of a call on, the point matched in the
+ * previous iteration bounds the nearest distance before the map is read, and only the octants (half-voxel cells) of the
+ * 27 voxels within that bound are visited — identical correspondences (GetCorrespondencePoints, voxel_hash_map.cpp:31-88),
+ * a fraction of the bytes.  0: every iteration runs the cold search. */
+int elm_registration_set_warm_start(elm_registration* reg, int enable);
 
 /* ---- deskew --------------------------------------------------------------------------------------------------- */
 /* Inputs of the per-point deskew = the member tables PcmMatching::ImuDeskewInfo / OdomDeskewInfo fill on the host
