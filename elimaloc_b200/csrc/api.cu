@@ -10,6 +10,7 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,14 @@ namespace {
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// Exception barrier of the C ABI: every extern "C" entry point is a function-try-block ending in ELM_API_CATCH, so that
+// an allocation failure (std::bad_alloc, std::length_error from a huge or corrupt input) becomes a status code instead of
+// terminating the caller's process — the header promises "never throws".
+#define ELM_API_CATCH                                                                                            \
+    catch (const std::bad_alloc&) { return fail(ELM_ERR_INVALID, "out of host memory"); }                        \
+    catch (const std::exception& e__) { return fail(ELM_ERR_INVALID, std::string("internal error: ") + e__.what()); } \
+    catch (...) { return fail(ELM_ERR_INVALID, "internal error"); }
 
 #define ELM_CUDA(expr)                                                                                   \
     do {                                                                                                 \
@@ -175,6 +184,10 @@ struct elm_registration {
     int* d_match = nullptr;
     float4* d_win = nullptr;   // matched map point per scan point (streamed by the accumulation)
     uint4* d_memo = nullptr;   // warm start of the next iteration's search
+    uint32_t* d_ncand = nullptr;
+    float4* d_cand = nullptr;  // per-query candidate lists of the warm search (icp_device.cuh)
+    uint32_t* d_cidx = nullptr;
+    int cand_cap = 32;
     size_t match_cap = 0;
     int warm = 1;              // P2P / GICP: iterations after the first start their search from the previous match (same result)
     // spatially binned copy of the scan for the search kernels (scan_sort.cu)
@@ -187,6 +200,7 @@ struct elm_registration {
     bool keep_match = false;  // also write match[] in the fused mode (off: nobody reads it)
     int binning = 0;          // 1 = search the scan in spatially binned order (measured: no gain on B200)
     bool use_sorted = false;  // the current enqueue searches d_sorted / d_orig
+    bool sorted_all = false;  // ... and accumulates in that order too (RunRegister: only sums leave the loop, no per-point output)
     unsigned int* d_ticket = nullptr;
     unsigned long long* d_stats = nullptr;  // [visited map points, queries] when stats are on
     bool stats_on = false;
@@ -230,7 +244,8 @@ struct elm_registration {
     elm::PeerComm peer{};          // peer.world > 0: the accumulate kernel's last block all-reduces over the ranks itself
     void* peer_opened[elm::kMaxPeers] = {};
     bool sharded() const { return comm != nullptr || peer.world > 0; }
-    elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, d_partials, d_ticket}; }
+    elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, match_cap, d_ncand, d_cand, d_cidx, cand_cap, d_partials, d_ticket}; }
+    double warm_margin_vox = 0.08;  // refresh margin of the warm search in voxel sizes
 
     ~elm_registration() {
         cudaSetDevice(device);
@@ -240,7 +255,7 @@ struct elm_registration {
         for (void* p : peer_opened) if (p) cudaIpcCloseMemHandle(p);
         cudaFree(d_mailbox);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_win); cudaFree(d_memo); cudaFree(d_ticket);
+        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_win); cudaFree(d_memo); cudaFree(d_ncand); cudaFree(d_cand); cudaFree(d_cidx); cudaFree(d_ticket);
         cudaFree(d_stats);
         cudaFree(d_dtable); cudaFreeHost(h_dtable); cudaFree(d_dsk_in); cudaFree(d_dsk_out);
         cudaFree(d_sorted); cudaFree(d_orig); cudaFree(d_bin); cudaFree(d_hist); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
@@ -287,13 +302,16 @@ int ensure_partials(elm_registration* r, int rows) {
 
 int ensure_match(elm_registration* r, size_t n) {
     if (n > r->match_cap) {
-        cudaFree(r->d_match); cudaFree(r->d_win); cudaFree(r->d_memo);
-        r->d_match = nullptr; r->d_win = nullptr; r->d_memo = nullptr;
+        cudaFree(r->d_match); cudaFree(r->d_win); cudaFree(r->d_memo); cudaFree(r->d_ncand); cudaFree(r->d_cand); cudaFree(r->d_cidx);
+        r->d_match = nullptr; r->d_win = nullptr; r->d_memo = nullptr; r->d_ncand = nullptr; r->d_cand = nullptr; r->d_cidx = nullptr;
         r->match_cap = 0;
         const size_t cap = (n + 1023) / 1024 * 1024;
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_match), cap * sizeof(int)));
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_win), cap * sizeof(float4)));
-        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_memo), cap * sizeof(uint4)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_memo), 2 * cap * sizeof(uint4)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_ncand), cap * sizeof(uint32_t)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_cand), static_cast<size_t>(r->cand_cap) * cap * sizeof(float4)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_cidx), static_cast<size_t>(r->cand_cap) * cap * sizeof(uint32_t)));
         r->match_cap = cap;
     }
     return ELM_OK;
@@ -316,6 +334,7 @@ int ensure_sort(elm_registration* r, size_t n) {
 // Bin the scan under pose T (once per call); afterwards the search kernels read d_sorted / d_orig.
 int enqueue_binning(elm_registration* r, const elm_map* map, const float* d_scan, size_t n, const double T[16], int method) {
     r->use_sorted = false;
+    r->sorted_all = false;
     if (!r->binning || method == ELM_AVGICP || n < 2048) return ELM_OK;
     int rc = ensure_sort(r, n);
     if (rc) return rc;
@@ -347,6 +366,7 @@ elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg,
     p.lm_lambda = cfg->lm_lambda;
     p.term_thr = cfg->icp_termination_threshold_m;
     p.min_overlap = cfg->min_overlap_ratio;
+    p.warm_margin = 0.0;  // (set per map in enqueue_linearize)
     p.stats = r->stats_on ? r->d_stats : nullptr;
     p.peer = r->peer;
     return p;
@@ -355,15 +375,17 @@ elm::IcpParams make_params(const elm_registration* r, const elm_reg_config* cfg,
 // one linearisation: search kernel -> accumulate kernel (its last block reduces in a fixed order and, on a single
 // GPU, also solves) -> multi-GPU: allreduce of the 30 sums over ranks, then the solve kernel
 // `warm`: the work buffers hold the previous iteration's matches of the SAME scan (P2P / GICP: warm-started search)
-int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm, bool solve, bool warm = false) {
-    const int sgrid = elm::icp_search_grid(prm, r->num_sms);
-    const int agrid = elm::icp_accumulate_grid(prm, r->num_sms);
+int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_scan, const elm::IcpParams& prm_in, bool solve, bool warm = false) {
+    const elm::IcpParams& prm0 = prm_in;
+    const int sgrid = elm::icp_search_grid(prm0, r->num_sms);
+    const int agrid = elm::icp_accumulate_grid(prm0, r->num_sms);
     // P2P / GICP: search, linearisation, reduction and solve are ONE kernel (unless the search runs on the binned copy,
     // whose order differs from the caller's: then the accumulation stays a separate launch in the caller's order)
-    const bool fuse = r->fuse && prm.method <= ELM_GICP && !r->use_sorted;
-    int rc = ensure_partials(r, fuse ? sgrid : agrid);
+    const bool fuse = r->fuse && prm0.method <= ELM_GICP && !(r->use_sorted && !r->sorted_all);
+    const int wgrid = elm::icp_warm_grid(prm0, r->num_sms);
+    int rc = ensure_partials(r, fuse ? (sgrid > wgrid ? sgrid : wgrid) : agrid);
     if (rc) return rc;
-    rc = ensure_match(r, prm.n);
+    rc = ensure_match(r, prm0.n);
     if (rc) return rc;
     if (r->profiling) {
         while (static_cast<int>(r->ev.size()) < r->ev_used + 3) {
@@ -376,12 +398,16 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // peer mode: the exchange happens inside the kernel, then the solve; NCCL mode: allreduce + separate solve launch below
     const bool use_nccl = r->comm != nullptr && r->peer.world == 0;
     const int solve_here = (solve && !use_nccl) ? 1 : 0;
+    elm::IcpParams prm = prm_in;
+    prm.warm_margin = r->warm_margin_vox * map->host.voxel_size;
     elm::IcpWork wk = r->work();
     if (fuse && !r->keep_match && prm.method == ELM_P2P) wk.match = nullptr;  // (GICP's accumulation reads the covariance record by index)
+    if (r->use_sorted && r->sorted_all) d_scan = r->d_sorted;  // the whole iteration runs on the binned copy
+    const bool mapped = r->use_sorted && !r->sorted_all;       // search in binned order, outputs under the caller's index
     if (prm.method != ELM_AVGICP) {
-        const bool use_warm = warm && r->warm && r->prune && !r->use_sorted && prm.method <= ELM_GICP;
-        ELM_CUDA(elm::launch_icp_search(map->view(), r->use_sorted ? r->d_sorted : d_scan, r->use_sorted ? r->d_orig : nullptr, prm, r->d_state,
-                                        wk, sgrid, r->prune, fuse ? 1 : 0, use_warm ? 1 : 0, solve_here, r->stream));
+        const bool use_warm = warm && r->warm && r->prune && !mapped && prm.method <= ELM_GICP;
+        ELM_CUDA(elm::launch_icp_search(map->view(), mapped ? r->d_sorted : d_scan, mapped ? r->d_orig : nullptr, prm, r->d_state,
+                                        wk, sgrid, r->prune, fuse ? 1 : 0, use_warm ? elm::icp_warm_grid(prm, r->num_sms) : 0, solve_here, r->stream));
         r->launches += 1;
     }
     if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
@@ -429,7 +455,7 @@ int elm_device_count(void) {
     return n;
 }
 
-int elm_map_create(elm_map** out, double voxel_size, int max_points_per_voxel, int device) {
+int elm_map_create(elm_map** out, double voxel_size, int max_points_per_voxel, int device) try {
     if (!out || !(voxel_size > 0.0) || max_points_per_voxel < 1) return fail(ELM_ERR_INVALID, "elm_map_create: bad argument");
     if (device >= 0) {
         if (device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_map_create: no such CUDA device");
@@ -442,35 +468,35 @@ int elm_map_create(elm_map** out, double voxel_size, int max_points_per_voxel, i
     m->device = device;
     *out = m;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 void elm_map_destroy(elm_map* map) { delete map; }
 
-int elm_map_add_points(elm_map* map, const float* xyz, size_t n) {
+int elm_map_add_points(elm_map* map, const float* xyz, size_t n) try {
     if (!map || (!xyz && n)) return fail(ELM_ERR_INVALID, "elm_map_add_points: bad argument");
     const std::string e = map->host.add_points(xyz, n);
     if (!e.empty()) return fail(ELM_ERR_RANGE, e);
     return map->publish_points();
-}
+} ELM_API_CATCH
 
-int elm_map_cal_voxel_cov(elm_map* map) {
+int elm_map_cal_voxel_cov(elm_map* map) try {
     if (!map) return fail(ELM_ERR_INVALID, "null map");
     map->host.cal_voxel_cov();
     return map->publish_voxel_cov();
-}
+} ELM_API_CATCH
 
-int elm_map_cal_point_cov(elm_map* map, double search_dist) {
+int elm_map_cal_point_cov(elm_map* map, double search_dist) try {
     if (!map) return fail(ELM_ERR_INVALID, "null map");
     map->host.cal_point_cov(search_dist);
     return map->publish_point_cov();
-}
+} ELM_API_CATCH
 
 int elm_map_empty(const elm_map* map) { return (!map || map->host.vkey.empty()) ? 1 : 0; }
 size_t elm_map_num_voxels(const elm_map* map) { return map ? map->host.V() : 0; }
 size_t elm_map_num_points(const elm_map* map) { return map ? map->host.P() : 0; }
 
 int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* vmean, double* vcov, float* pxyz,
-                   double* pmean, double* pcov) {
+                   double* pmean, double* pcov) try {
     if (!map) return fail(ELM_ERR_INVALID, "null map");
     const elm::HostMap& h = map->host;
     if ((vmean || vcov) && !h.has_vcov) return fail(ELM_ERR_STATE, "voxel covariances not computed");
@@ -485,9 +511,9 @@ int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* v
     if (pmean) std::memcpy(pmean, h.pmean.data(), h.pmean.size() * sizeof(double));
     if (pcov) std::memcpy(pcov, h.pcov.data(), h.pcov.size() * sizeof(double));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], double icp_pose_std_m, double pose_cov[36]) {
+int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], double icp_pose_std_m, double pose_cov[36]) try {
     if (!R_ego || !local_cov || !pose_cov) return fail(ELM_ERR_INVALID, "elm_shape_pcm_covariance: bad argument");
     auto normalize = [](const double* in, double* out) {
         double scale = 1.0, m = std::fmin(in[0], std::fmin(in[4], in[8]));
@@ -515,17 +541,17 @@ int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], 
             pose_cov[6 * (i + 3) + (j + 3)] = rn[3 * i + j] * ang * ang;
         }
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_map_find_ground_height(const elm_map* map, double x, double y, double* ground_z, int32_t* found) {
+int elm_map_find_ground_height(const elm_map* map, double x, double y, double* ground_z, int32_t* found) try {
     if (!map || !ground_z || !found) return fail(ELM_ERR_INVALID, "elm_map_find_ground_height: bad argument");
     double z = 0.0;
     *found = map->host.find_ground_height(x, y, z) ? 1 : 0;
     if (*found) *ground_z = z;  // untouched otherwise, like the reference's out-parameter
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_pcd_read_xyz(const char* path, float* xyz, size_t capacity_points, size_t* n_points, size_t* n_dropped) {
+int elm_pcd_read_xyz(const char* path, float* xyz, size_t capacity_points, size_t* n_points, size_t* n_dropped) try {
     if (!path || !n_points) return fail(ELM_ERR_INVALID, "elm_pcd_read_xyz: bad argument");
     std::vector<float> v;
     size_t dropped = 0;
@@ -538,25 +564,25 @@ int elm_pcd_read_xyz(const char* path, float* xyz, size_t capacity_points, size_
         std::memcpy(xyz, v.data(), v.size() * sizeof(float));
     }
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_map_add_points_pcd(elm_map* map, const char* path, size_t* n_points) {
+int elm_map_add_points_pcd(elm_map* map, const char* path, size_t* n_points) try {
     if (!map || !path) return fail(ELM_ERR_INVALID, "elm_map_add_points_pcd: bad argument");
     std::vector<float> v;
     const std::string e = elm::read_pcd_xyz(path, v, nullptr);
     if (!e.empty()) return fail(ELM_ERR_IO, e);
     if (n_points) *n_points = v.size() / 3;
     return elm_map_add_points(map, v.data(), v.size() / 3);
-}
+} ELM_API_CATCH
 
-int elm_map_save(const elm_map* map, const char* path) {
+int elm_map_save(const elm_map* map, const char* path) try {
     if (!map || !path) return fail(ELM_ERR_INVALID, "elm_map_save: bad argument");
     const std::string e = map->host.save(path);
     if (!e.empty()) return fail(ELM_ERR_IO, e);
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_map_load(elm_map** out, const char* path, int device) {
+int elm_map_load(elm_map** out, const char* path, int device) try {
     if (!out || !path) return fail(ELM_ERR_INVALID, "elm_map_load: bad argument");
     if (device >= 0) {
         if (device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_map_load: no such CUDA device");
@@ -573,9 +599,9 @@ int elm_map_load(elm_map** out, const char* path, int device) {
     if (rc != ELM_OK) return rc;
     *out = m.release();
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slots, uint64_t* mismatches) {
+int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slots, uint64_t* mismatches) try {
     if (!map || !entries || !slots || !mismatches) return fail(ELM_ERR_INVALID, "elm_map_directory_check: bad argument");
     const elm::HostMap& h = map->host;
     *entries = h.dir_entries;
@@ -673,9 +699,9 @@ int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slo
     }
     *mismatches = bad;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_create(elm_registration** out, int device, void* stream) {
+int elm_registration_create(elm_registration** out, int device, void* stream) try {
     if (!out) return fail(ELM_ERR_INVALID, "null out");
     if (device < 0 || device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_registration_create: no such CUDA device");
     ELM_CUDA(cudaSetDevice(device));
@@ -700,12 +726,12 @@ int elm_registration_create(elm_registration** out, int device, void* stream) {
     std::memset(r->h_state, 0, sizeof(elm::IcpState));
     *out = r;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 void elm_registration_destroy(elm_registration* reg) { delete reg; }
 
 int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float* d_src_xyz, size_t n, const double T_init[16],
-                         const elm_reg_config* cfg) {
+                         const elm_reg_config* cfg) try {
     if (!reg || !map || !T_init || !cfg || (!d_src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_register_enqueue: bad argument");
     if (n > 0x7fffffffull / 8) return fail(ELM_ERR_INVALID, "scan too large");
     int rc = check_method(map, cfg);
@@ -725,16 +751,17 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     reg->launches += 1;
     rc = enqueue_binning(reg, map, d_src_xyz, n, T_init, cfg->icp_method);
     if (rc) return rc;
+    reg->sorted_all = true;
     for (int j = 0; j < cfg->max_iteration; ++j) {  // reg.cpp:310
         rc = enqueue_linearize(reg, map, d_src_xyz, prm, true, j > 0);
         if (rc) return rc;
     }
     ELM_CUDA(cudaMemcpyAsync(reg->h_state, reg->d_state, sizeof(elm::IcpState), cudaMemcpyDeviceToHost, reg->stream));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 int elm_register_fetch(elm_registration* reg, double T_out[16], int32_t* is_success, double* fitness_score, double local_cov[36],
-                       int32_t* iterations_run) {
+                       int32_t* iterations_run) try {
     if (!reg || !T_out || !is_success) return fail(ELM_ERR_INVALID, "elm_register_fetch: bad argument");
     if (!reg->pending) return fail(ELM_ERR_STATE, "elm_register_fetch without elm_register_enqueue");
     ELM_CUDA(cudaSetDevice(reg->device));
@@ -764,10 +791,10 @@ int elm_register_fetch(elm_registration* reg, double T_out[16], int32_t* is_succ
     if (reg->cfg.debug_print)
         std::printf("[elimaloc_b200] RunRegister: %d iterations, fitness %.6f, success %d\n", st.iterations, st.fitness, *is_success);
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 int elm_run_register(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T_init[16],
-                     const elm_reg_config* cfg, double T_out[16], int32_t* is_success, double* fitness_score, double local_cov[36]) {
+                     const elm_reg_config* cfg, double T_out[16], int32_t* is_success, double* fitness_score, double local_cov[36]) try {
     if (!reg || !map || !T_init || !cfg || !T_out || !is_success || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_run_register: bad argument");
     int rc = check_method(map, cfg);
     if (rc) return rc;
@@ -780,10 +807,10 @@ int elm_run_register(elm_registration* reg, const elm_map* map, const float* src
     rc = elm_register_enqueue(reg, map, reg->d_scan, n, T_init, cfg);
     if (rc) return rc;
     return elm_register_fetch(reg, T_out, is_success, fitness_score, local_cov, nullptr);
-}
+} ELM_API_CATCH
 
 int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
-                  const elm_reg_config* cfg, double JTJ[36], double JTr[6], double* residual_sum, int64_t* n_corr) {
+                  const elm_reg_config* cfg, double JTJ[36], double JTr[6], double* residual_sum, int64_t* n_corr) try {
     if (!reg || !map || !T || !cfg || !JTJ || !JTr || !residual_sum || !n_corr || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_linearize: bad argument");
     int rc = check_method(map, cfg);
     if (rc) return rc;
@@ -812,10 +839,10 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     *residual_sum = a[elm::kIdxRes];
     *n_corr = static_cast<int64_t>(std::llround(a[elm::kIdxNcorr]));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double* T_seq, int n_poses,
-                                 int method, double max_search_dist, int32_t* count, double* target) {
+                                 int method, double max_search_dist, int32_t* count, double* target) try {
     if (!reg || !map || !T_seq || n_poses < 1 || !count || !target || (!src_xyz && n)) return fail(ELM_ERR_INVALID, "elm_correspondences: bad argument");
     elm_reg_config c{};
     c.icp_method = method;
@@ -839,7 +866,8 @@ int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, cons
     // the hook runs the PRODUCTION search kernels — cold at the first pose, warm-started at the following ones exactly as
     // the ICP loop runs them — and only converts the last match[] into positions
     c.max_search_dist = max_search_dist;
-    const elm::IcpParams prm = make_params(reg, &c, n);
+    elm::IcpParams prm = make_params(reg, &c, n);
+    prm.warm_margin = reg->warm_margin_vox * map->host.voxel_size;
     rc = ensure_match(reg, n);
     if (rc) return rc;
     for (int k = 0; k < n_poses; ++k) {
@@ -852,8 +880,8 @@ int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, cons
         if (method != ELM_AVGICP) {
             const bool warm = k > 0 && reg->warm && reg->prune && !reg->use_sorted && method <= ELM_GICP;
             ELM_CUDA(elm::launch_icp_search(map->view(), reg->use_sorted ? reg->d_sorted : reg->d_scan, reg->use_sorted ? reg->d_orig : nullptr, prm,
-                                            reg->d_state, reg->work(), elm::icp_search_grid(prm, reg->num_sms), reg->prune, 0, warm ? 1 : 0, 0,
-                                            reg->stream));
+                                            reg->d_state, reg->work(), elm::icp_search_grid(prm, reg->num_sms), reg->prune, 0,
+                                            warm ? elm::icp_warm_grid(prm, reg->num_sms) : 0, 0, reg->stream));
         }
     }
     ELM_CUDA(elm::launch_icp_export(map->view(), reg->d_scan, reg->d_match, static_cast<int>(n), reg->d_state, method,
@@ -862,52 +890,52 @@ int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, cons
     ELM_CUDA(cudaMemcpyAsync(target, reg->d_target, n * K * 3 * sizeof(double), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 int elm_correspondences(elm_registration* reg, const elm_map* map, const float* src_xyz, size_t n, const double T[16],
-                        int method, double max_search_dist, int32_t* count, double* target) {
+                        int method, double max_search_dist, int32_t* count, double* target) try {
     return elm_correspondences_sequence(reg, map, src_xyz, n, T, 1, method, max_search_dist, count, target);
-}
+} ELM_API_CATCH
 
-int elm_registration_set_warm_start(elm_registration* reg, int enable) {
+int elm_registration_set_warm_start(elm_registration* reg, int enable) try {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     reg->warm = enable ? 1 : 0;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_launch_count(const elm_registration* reg, int64_t* launches) {
+int elm_registration_launch_count(const elm_registration* reg, int64_t* launches) try {
     if (!reg || !launches) return fail(ELM_ERR_INVALID, "bad argument");
     *launches = reg->launches;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_set_profiling(elm_registration* reg, int enable) {
+int elm_registration_set_profiling(elm_registration* reg, int enable) try {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     reg->profiling = enable != 0;
     reg->ev_used = 0;
     reg->prof_search_ms = reg->prof_accum_ms = 0.0;
     reg->prof_launches = 0;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_profile(const elm_registration* reg, double* search_ms, double* accumulate_ms, int64_t* iterations) {
+int elm_registration_profile(const elm_registration* reg, double* search_ms, double* accumulate_ms, int64_t* iterations) try {
     if (!reg || !search_ms || !accumulate_ms || !iterations) return fail(ELM_ERR_INVALID, "bad argument");
     *search_ms = reg->prof_search_ms;
     *accumulate_ms = reg->prof_accum_ms;
     *iterations = reg->prof_launches;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_set_stats(elm_registration* reg, int enable) {
+int elm_registration_set_stats(elm_registration* reg, int enable) try {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     ELM_CUDA(cudaSetDevice(reg->device));
     if (!reg->d_stats) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_stats), 32 * sizeof(unsigned long long)));
     ELM_CUDA(cudaMemsetAsync(reg->d_stats, 0, 32 * sizeof(unsigned long long), reg->stream));
     reg->stats_on = enable != 0;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, uint64_t* queries) {
+int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, uint64_t* queries) try {
     if (!reg || !map_points_visited || !queries) return fail(ELM_ERR_INVALID, "bad argument");
     if (!reg->d_stats) return fail(ELM_ERR_STATE, "stats were never enabled");
     ELM_CUDA(cudaSetDevice(reg->device));
@@ -921,31 +949,34 @@ int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, 
     if (getenv("ELM_PHASE_TIMING"))
         std::fprintf(stderr, "[accumulate cycles] blocks %llu | state %llu gather+linearise %llu block-reduce %llu publish+ticket %llu | last block: final-reduce %llu solve %llu\n",
                      h[15], h[9], h[10], h[11], h[12], h[13], h[14]);
+    if (getenv("ELM_PHASE_TIMING"))
+        std::fprintf(stderr, "[warm cycles] warp-tiles %llu | inputs %llu decide %llu reuse-scan %llu refresh %llu winner-reload %llu | refresh reasons: key changed %llu, no match %llu, no list %llu, margin used up %llu\n", h[22], h[23], h[24], h[25], h[26], h[27], h[30], h[31], h[28], h[29]);
+    if (getenv("ELM_WARM_STATS")) std::fprintf(stderr, "[warm search] %llu of %llu warm searches refreshed their runs\n", h[20], h[21]);
     *map_points_visited = h[0];
     *queries = h[1];
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_set_fused(elm_registration* reg, int enable) {
+int elm_registration_set_fused(elm_registration* reg, int enable) try {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     reg->fuse = enable ? 1 : 0;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_set_binning(elm_registration* reg, int enable) {
+int elm_registration_set_binning(elm_registration* reg, int enable) try {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     reg->binning = enable ? 1 : 0;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_set_exhaustive(elm_registration* reg, int exhaustive) {
+int elm_registration_set_exhaustive(elm_registration* reg, int exhaustive) try {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     reg->prune = exhaustive ? 0 : 1;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 int elm_deskew_points_device(elm_registration* reg, const float* d_xyz, const float* d_rel_time, size_t n, const elm_deskew_tables* t,
-                             float* d_xyz_out) {
+                             float* d_xyz_out) try {
     if (!reg || !t || (n && (!d_xyz || !d_rel_time || !d_xyz_out))) return fail(ELM_ERR_INVALID, "elm_deskew_points: bad argument");
     if (n > 0x7fffffffull / 4) return fail(ELM_ERR_INVALID, "scan too large");
     if (t->imu_available && (t->imu_pointer_cur < 0 || !t->imu_time || !t->imu_rot_x || !t->imu_rot_y || !t->imu_rot_z))
@@ -976,9 +1007,9 @@ int elm_deskew_points_device(elm_registration* reg, const float* d_xyz, const fl
     }
     ELM_CUDA(elm::launch_deskew_points(d_xyz, d_rel_time, static_cast<int>(n), p, reg->d_dtable, d_xyz_out, reg->num_sms, reg->stream));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_time, size_t n, const elm_deskew_tables* t, float* xyz_out) {
+int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_time, size_t n, const elm_deskew_tables* t, float* xyz_out) try {
     if (!reg || !t || (n && (!xyz || !rel_time || !xyz_out))) return fail(ELM_ERR_INVALID, "elm_deskew_points: bad argument");
     if (n == 0) return ELM_OK;
     ELM_CUDA(cudaSetDevice(reg->device));
@@ -999,10 +1030,10 @@ int elm_deskew_points(elm_registration* reg, const float* xyz, const float* rel_
     ELM_CUDA(cudaMemcpyAsync(xyz_out, reg->d_dsk_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, reg->stream));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 int elm_scan_preprocess_device(elm_registration* reg, const float* d_xyz, const float* d_aux, size_t n, double max_dist, double voxel_size,
-                               float* d_xyz_out, float* d_aux_out, int32_t* d_index_out, size_t* n_out) {
+                               float* d_xyz_out, float* d_aux_out, int32_t* d_index_out, size_t* n_out) try {
     if (!reg || !n_out || (n && (!d_xyz || !d_xyz_out)) || (d_aux_out && !d_aux)) return fail(ELM_ERR_INVALID, "elm_scan_preprocess: bad argument");
     if (n > 0x7fffffffull / 4) return fail(ELM_ERR_INVALID, "scan too large");
     *n_out = 0;
@@ -1032,10 +1063,10 @@ int elm_scan_preprocess_device(elm_registration* reg, const float* d_xyz, const 
     if (h[1]) return fail(ELM_ERR_RANGE, "scan point not finite or beyond +-2^20 voxels of the down-sampling grid");
     *n_out = static_cast<size_t>(h[0]);
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 int elm_scan_preprocess(elm_registration* reg, const float* xyz, const float* aux, size_t n, double max_dist, double voxel_size, float* xyz_out,
-                        float* aux_out, int32_t* index_out, size_t* n_out) {
+                        float* aux_out, int32_t* index_out, size_t* n_out) try {
     if (!reg || !n_out || (n && (!xyz || !xyz_out)) || (aux_out && !aux)) return fail(ELM_ERR_INVALID, "elm_scan_preprocess: bad argument");
     *n_out = 0;
     if (n == 0) return ELM_OK;
@@ -1064,9 +1095,9 @@ int elm_scan_preprocess(elm_registration* reg, const float* xyz, const float* au
         ELM_CUDA(cudaStreamSynchronize(reg->stream));
     }
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_ekf_create(elm_ekf** out, const elm_ekf_config* cfg, int device, void* stream) {
+int elm_ekf_create(elm_ekf** out, const elm_ekf_config* cfg, int device, void* stream) try {
     if (!out || !cfg) return fail(ELM_ERR_INVALID, "elm_ekf_create: bad argument");
     if (device < 0 || device >= elm_device_count()) return fail(ELM_ERR_CUDA, "elm_ekf_create: no such CUDA device");
     ELM_CUDA(cudaSetDevice(device));
@@ -1092,35 +1123,35 @@ int elm_ekf_create(elm_ekf** out, const elm_ekf_config* cfg, int device, void* s
     }
     *out = e;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 void elm_ekf_destroy(elm_ekf* ekf) { delete ekf; }
 
-int elm_ekf_predict_imu(elm_ekf* ekf, double timestamp, const double gyro[3], const double acc[3]) {
+int elm_ekf_predict_imu(elm_ekf* ekf, double timestamp, const double gyro[3], const double acc[3]) try {
     if (!ekf || !gyro || !acc) return fail(ELM_ERR_INVALID, "elm_ekf_predict_imu: bad argument");
     ELM_CUDA(cudaSetDevice(ekf->device));
     ELM_CUDA(elm::launch_ekf_predict_imu(ekf->d_state, ekf->cfg, timestamp, gyro, acc, ekf->stream));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_ekf_update_pose(elm_ekf* ekf, const elm_ekf_measurement* meas) {
+int elm_ekf_update_pose(elm_ekf* ekf, const elm_ekf_measurement* meas) try {
     if (!ekf || !meas) return fail(ELM_ERR_INVALID, "elm_ekf_update_pose: bad argument");
     if (meas->source != 3 && meas->source != 4) return fail(ELM_ERR_UNSUPPORTED, "only the PCM (3) and PCM_INIT (4) sources are in scope");
     ELM_CUDA(cudaSetDevice(ekf->device));
     ELM_CUDA(elm::launch_ekf_update_pose(ekf->d_state, ekf->cfg, *meas, ekf->stream));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_ekf_get_state(elm_ekf* ekf, elm_ekf_state* out) {
+int elm_ekf_get_state(elm_ekf* ekf, elm_ekf_state* out) try {
     if (!ekf || !out) return fail(ELM_ERR_INVALID, "elm_ekf_get_state: bad argument");
     ELM_CUDA(cudaSetDevice(ekf->device));
     ELM_CUDA(cudaMemcpyAsync(ekf->h_state, ekf->d_state, sizeof(elm_ekf_state), cudaMemcpyDeviceToHost, ekf->stream));
     ELM_CUDA(cudaStreamSynchronize(ekf->stream));
     std::memcpy(out, ekf->h_state, sizeof(elm_ekf_state));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_ekf_set_state(elm_ekf* ekf, const elm_ekf_state* in) {
+int elm_ekf_set_state(elm_ekf* ekf, const elm_ekf_state* in) try {
     if (!ekf || !in) return fail(ELM_ERR_INVALID, "elm_ekf_set_state: bad argument");
     ELM_CUDA(cudaSetDevice(ekf->device));
     ELM_CUDA(cudaStreamSynchronize(ekf->stream));
@@ -1128,9 +1159,9 @@ int elm_ekf_set_state(elm_ekf* ekf, const elm_ekf_state* in) {
     ELM_CUDA(cudaMemcpyAsync(ekf->d_state, ekf->h_state, sizeof(elm_ekf_state), cudaMemcpyHostToDevice, ekf->stream));
     ELM_CUDA(cudaStreamSynchronize(ekf->stream));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]) {
+int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]) try {
     if (!ekf || !ego) return fail(ELM_ERR_INVALID, "elm_ekf_get_current_state: bad argument");
     ELM_CUDA(cudaSetDevice(ekf->device));
     ELM_CUDA(cudaMemcpyAsync(ekf->h_state, ekf->d_state, sizeof(elm_ekf_state), cudaMemcpyDeviceToHost, ekf->stream));
@@ -1143,17 +1174,17 @@ int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]) {
         ELM_CUDA(cudaStreamSynchronize(ekf->stream));
     }
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_comm_unique_id(uint8_t unique_id[128]) {
+int elm_comm_unique_id(uint8_t unique_id[128]) try {
     if (!unique_id) return fail(ELM_ERR_INVALID, "null id");
     if (!g_nccl.load()) return fail(ELM_ERR_NCCL, "libnccl.so.2 could not be loaded");
     const int e = g_nccl.GetUniqueId(unique_id);
     if (e != 0) return fail(ELM_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(e));
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_set_comm(elm_registration* reg, const uint8_t unique_id[128], int rank, int world_size) {
+int elm_registration_set_comm(elm_registration* reg, const uint8_t unique_id[128], int rank, int world_size) try {
     if (!reg || !unique_id || world_size < 1 || rank < 0 || rank >= world_size) return fail(ELM_ERR_INVALID, "elm_registration_set_comm: bad argument");
     if (!g_nccl.load()) return fail(ELM_ERR_NCCL, "libnccl.so.2 could not be loaded");
     ELM_CUDA(cudaSetDevice(reg->device));
@@ -1165,9 +1196,9 @@ int elm_registration_set_comm(elm_registration* reg, const uint8_t unique_id[128
     reg->rank = rank;
     reg->world = world_size;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_peer_export(elm_registration* reg, uint8_t handle[64]) {
+int elm_registration_peer_export(elm_registration* reg, uint8_t handle[64]) try {
     if (!reg || !handle) return fail(ELM_ERR_INVALID, "elm_registration_peer_export: bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     ELM_CUDA(cudaSetDevice(reg->device));
@@ -1179,9 +1210,9 @@ int elm_registration_peer_export(elm_registration* reg, uint8_t handle[64]) {
     ELM_CUDA(cudaIpcGetMemHandle(&h, reg->d_mailbox));
     std::memcpy(handle, &h, 64);
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_peer_attach(elm_registration* reg, const uint8_t* handles, int rank, int world_size) {
+int elm_registration_peer_attach(elm_registration* reg, const uint8_t* handles, int rank, int world_size) try {
     if (!reg || world_size < 1 || world_size > elm::kMaxPeers || rank < 0 || rank >= world_size || (world_size > 1 && !handles))
         return fail(ELM_ERR_INVALID, "elm_registration_peer_attach: bad argument (1 <= world_size <= 8)");
     ELM_CUDA(cudaSetDevice(reg->device));
@@ -1211,15 +1242,15 @@ int elm_registration_peer_attach(elm_registration* reg, const uint8_t* handles, 
     reg->rank = rank;
     reg->world = world_size;
     return ELM_OK;
-}
+} ELM_API_CATCH
 
-int elm_registration_peer_detach(elm_registration* reg) {
+int elm_registration_peer_detach(elm_registration* reg) try {
     if (!reg) return fail(ELM_ERR_INVALID, "null registration");
     ELM_CUDA(cudaSetDevice(reg->device));
     ELM_CUDA(cudaStreamSynchronize(reg->stream));
     for (void*& p : reg->peer_opened) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
     reg->peer = elm::PeerComm{};
     return ELM_OK;
-}
+} ELM_API_CATCH
 
 }  // extern "C"

@@ -70,6 +70,7 @@ struct IcpParams {
     double lm_lambda;
     double term_thr;
     double min_overlap;
+    double warm_margin;  // metres added to the previous match's distance when a warm search refreshes its remembered runs
     PeerComm peer;
     unsigned long long* stats;  // optional: [0] += map points visited by the search, [1] += queries (NULL = off)
 };
@@ -80,7 +81,15 @@ struct IcpWork {
     float4* win;            // [n] P2P/GICP: the matched map point itself {x, y, z, bits of its canonical rank}; none ->
                             //     {0, 0, 0, 0xffffffff} = the reference's default-constructed neighbour at the origin (Q2), so the
                             //     accumulation STREAMS its targets instead of gathering pts[match[i]]
-    uint4* memo;            // [n] warm start of the next iteration's search: {directory row, key_lo, key_hi, device index of the match}
+    uint4* memo;            // warm start of the next iteration's search, two planes of memo_stride elements:
+                            //   [0] {directory row, key_lo, key_hi, device index of the match}
+                            //   [1] {q0.x, q0.y, q0.z, R} (floats): the candidate list holds every point of the 27 voxels within R of q0
+    size_t memo_stride;     // = elements per plane of memo, cand, cidx
+    uint32_t* ncand;        // [n] length of the query's candidate list; ~0: unusable
+    float4* cand;           // candidate j of query i at cand[(i / 256) * cand_cap * 256 + j * 256 + i % 256] (tile-interleaved: the lists
+                            // of 256 consecutive queries form one block, candidate-major inside): a COPY of the stored point
+    uint32_t* cidx;         // same layout: its device index in the map's point array
+    int cand_cap;
     double* partials;       // [blocks][kAcc] per-block sums of one linearisation
     unsigned int* ticket;   // blocks finished
 };

@@ -1112,7 +1112,10 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
             const size_t oi = orig ? static_cast<size_t>(orig[gi]) : gi;
             if (match) match[oi] = my_match;
             if (wk.win) wk.win[oi] = wpt;
-            if (wk.memo) wk.memo[oi] = make_uint4(static_cast<uint32_t>(row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+            if (wk.memo) {  // (no candidate list yet: the first warm search refreshes)
+                wk.memo[oi] = make_uint4(static_cast<uint32_t>(row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+                wk.ncand[oi] = kNone;
+            }
         }
         if (kFuse) {  // linearise this tile's correspondences and fold them into the block's running sums
             double acc[NACC];
@@ -1139,29 +1142,29 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
 // search: P2P / GICP, warm-started (second iteration of a call onwards)
 // ======================================================================================================================
 // The search of iteration k+1 asks the same question as iteration k from a slightly moved pose.  The point matched last
-// time (win[i], still a member of the query's 27 voxels whenever the query's key did not change — memo[i] says so without a
+// time (win[i], still a member of the query's 27 voxels whenever the query's key did not change — memo says so without a
 // directory lookup) gives an upper bound d on the nearest distance BEFORE anything of the map is read, so the search only
 // has to look at map points that can be at least as close: the OCTANTS (half-voxel cells; the points of a voxel are stored
-// sorted by octant, the row of the directory entry carries every voxel's octant offsets) whose box lies within d.  On the
-// benchmark map that is ~10-15 points in ~3 short runs instead of ~36 points in whole voxels, and there is no dependent
-// chain home voxel -> bound -> neighbours any more: one round trip for the column records, one for the runs.
-// Exactness: every point of the 27 voxels at distance <= d lies in an octant whose box is within d, all of those are
-// visited with exact fp64 distances, the previous match itself competes with its rank — so the result (nearest point,
-// first-in-visit-order among equals, vhm.cpp:45) is the one the full visit finds.  A query whose key changed looks its row
-// up again and keeps the bound only if the old match is still inside its 27 voxels; otherwise it visits everything.
+// sorted by octant, the row of the directory entry carries every voxel's octant offsets) whose box lies within d.
 //
-//   A  thread per QUERY : transform, bound, per axis which half-cells are within the bound (separable test, then the voxel's
-//                         box), one 32-byte record per needed column, one run per needed voxel (octants lowest..highest
-//                         needed; runs of z-neighbours that touch are merged), cut into work items of <= 3 aligned pairs
-//                         in the WARP's list;
-//   B  lane per ITEM    : three 32-byte loads, exact distances, atomicMin of the distance bits per query;
-//   C  lane per ITEM    : among the exact minima the smallest rank wins (atomicMin of rank << 32 | index).
-// Items that do not fit the list stay with their owner thread, which scans those runs itself.
-#ifndef ELM_WARM_CAP
-#define ELM_WARM_CAP 256
-#endif
-constexpr int kWarmCap = ELM_WARM_CAP;  // work items per warp
-
+// Two paths per query, both exact:
+//   REFRESH  the octants within R = d + margin of the query q0 are searched, and every stored point really within R of q0
+//            (a handful) is COPIED into the query's own candidate list in HBM (cand[j][i], query-minor: the lanes of a warp
+//            read consecutive addresses); q0 and R go into the memo;
+//   REUSE    while the query keeps its key and  d' + |q - q0| <= R  (d' = distance from the new position q to the previous
+//            match), every map point of the 27 voxels within d' of q is within R of q0, i.e. in the candidate list: the
+//            thread streams its list and is done — no directory, no column records, no random access to the map at all.
+//            In a converging ICP loop the pose moves by less than the margin, so nearly every query of nearly every
+//            iteration takes this path.
+// Why the copy: B200 reads RANDOM 32-byte sectors from HBM at 1.25 TB/s (measured, profiles/micro/dep_gather.cu: the rate
+// of DRAM row activations, whatever the number of loads in flight) against 6.5 TB/s for streams, and the candidate lists
+// of a 131 072-point scan (~40 MB) stay in the 126 MB L2 from one iteration to the next, which the scattered runs of the
+// map (one 128-byte line per 1-2 useful sectors) do not.
+// Exactness: every point of the 27 voxels at distance <= d' is in the scanned set, the decision is the exact fp64 one of
+// visit_points (fp32 pre-filter inside a proved band, exact re-decision on near ties, smallest rank among equals) — so
+// the result (nearest point, first in visit order among equals, vhm.cpp:45) is the one the full visit finds.  A query
+// whose key changed looks its row up again and keeps the bound only if the old match is still inside its 27 voxels;
+// otherwise it visits everything (and its list stays unusable until the next refresh with a finite bound).
 // squared gap (voxel units, fp32, deliberately under-estimated) between the in-cell coordinate f of the query (relative to
 // its floor key) and the interval [a, b]
 __device__ __forceinline__ float interval_gap2(float f, float a, float b) {
@@ -1190,20 +1193,286 @@ __device__ __forceinline__ int stored_key(float p, const MapView& map) {
     const double q = (map.inv_voxel_size != 0.0) ? __dmul_rn(static_cast<double>(p), map.inv_voxel_size) : __ddiv_rn(static_cast<double>(p), map.voxel_size);
     return static_cast<int>(q);
 }
-// exact scan of the points [s, e) (a run of at most three aligned pairs starting at s & ~1) for the query (px, py, pz)
-__device__ __forceinline__ void scan_item_exact(const float4* __restrict__ pts, uint32_t s, uint32_t e, double px, double py, double pz, Best& b) {
-    const uint32_t p0 = s & ~1u, last_pair = (e - 1) & ~1u;
-    float4 q0[3], q1[3];
+// Octant o = hz << 2 | hy << 1 | hx, so "x half 0" = octants 0x55, "y half 0" = 0x33, "z half 0" = 0x0f.
+__device__ __forceinline__ uint32_t half_pattern(uint32_t h, uint32_t p0, uint32_t p1) { return ((h & 1u) ? p0 : 0u) | ((h & 2u) ? p1 : 0u); }
+// The runs of stored points that hold every point of the query's 27 voxels whose octant box is within `bound` (voxel
+// units, squared) of the query, for the z-columns of `columns` (bit c = 3 (dx + 1) + (dy + 1)): per column with a needed
+// voxel one 32-byte record, per needed voxel its octants lowest..highest needed; runs of z-neighbours that touch (or
+// nearly) are merged.  emit(first, end) per run.
+template <class F>
+__device__ __forceinline__ void octant_runs(const MapView& map, int row, int kx, int ky, int kz, float fx, float fy, float fz, float bound,
+                                            uint32_t columns, F&& emit) {
+    float gvx[3], gvy[3], gvz[3];
+    const uint32_t hx = axis_halves(kx, fx, bound, gvx), hy = axis_halves(ky, fy, bound, gvy), hz = axis_halves(kz, fz, bound, gvz);
+    const float gzmin = fminf(fminf(gvz[0], gvz[1]), gvz[2]);
+    uint32_t colmask = 0;
 #pragma unroll
-    for (uint32_t u = 0; u < 3; ++u) ldg256(pts + min(p0 + 2 * u, last_pair), q0[u], q1[u]);
+    for (int c = 0; c < 9; ++c)
+        if (((hx >> (2 * (c / 3))) & 3u) && ((hy >> (2 * (c % 3))) & 3u) && !((gvx[c / 3] + gvy[c % 3] + gzmin) * 0.9999f > bound)) colmask |= 1u << c;
+    colmask &= columns;
+    while (colmask) {
+        const int c = __ffs(colmask) - 1;
+        colmask &= colmask - 1;
+        const int ox = c / 3, oy = c - 3 * ox;
+        uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(map.drows + row_col_word(static_cast<size_t>(row), c)));
+        const uint32_t xy = half_pattern((hx >> (2 * ox)) & 3u, 0x55u, 0xaau) & half_pattern((hy >> (2 * oy)) & 3u, 0x33u, 0xccu);
+        const float gxy = (ox == 0 ? gvx[0] : (ox == 1 ? gvx[1] : gvx[2])) + (oy == 0 ? gvy[0] : (oy == 1 ? gvy[1] : gvy[2]));
+        uint32_t run_s = 0, run_e = 0, vfirst = r0;
 #pragma unroll
-    for (uint32_t u = 0; u < 3; ++u) {
-        const uint32_t pi = p0 + 2 * u;
-        if (pi >= s && pi < e) fold_exact(ExactPoint(), q0[u], pi, px, py, pz, b);
-        if (pi + 1 >= s && pi + 1 < e) fold_exact(ExactPoint(), q1[u], pi + 1, px, py, pz, b);
+        for (int dz = 0; dz < 3; ++dz) {
+            const uint32_t n = (r1 >> (kDirCountBits * dz)) & kDirCountMask;
+            const uint32_t zh = (hz >> (2 * dz)) & 3u;
+            if (n && zh && !((gxy + gvz[dz]) * 0.9999f > bound)) {
+                const unsigned long long ow = (static_cast<unsigned long long>(dz == 0 ? r3 : (dz == 1 ? r5 : r7)) << 32) | (dz == 0 ? r2 : (dz == 1 ? r4 : r6));
+                uint32_t a = 0, e = n;
+                if (ow >> 56) {  // octant words valid (byte 7 = n for cap <= 255, 0 otherwise)
+                    const uint32_t need = xy & half_pattern(zh, 0x0fu, 0xf0u);
+                    const int lo = __ffs(need) - 1, hi = 32 - __clz(need);  // octants lo .. hi - 1
+                    a = lo ? static_cast<uint32_t>(ow >> (8 * (lo - 1))) & 0xffu : 0u;
+                    e = hi < 8 ? static_cast<uint32_t>(ow >> (8 * (hi - 1))) & 0xffu : n;
+                }
+                const uint32_t rs = vfirst + a, re = vfirst + e;
+                if (re > rs) {
+                    if (run_e > run_s && rs <= run_e + 2) run_e = re;  // touches (or nearly) the run of the voxel below: one run
+                    else { if (run_e > run_s) emit(run_s, run_e); run_s = rs; run_e = re; }
+                }
+            }
+            vfirst += n;
+        }
+        if (run_e > run_s) emit(run_s, run_e);
     }
 }
 
+#ifdef ELM_PHASE_TIMING
+#define ELM_WTICK(k) do { const long long t__ = clock64(); if (prm.stats && lane == 0) atomicAdd(prm.stats + (k), static_cast<unsigned long long>(t__ - wtick)); wtick = t__; } while (0)
+#else
+#define ELM_WTICK(k) do { } while (0)
+#endif
+// REFRESH of one query (a query that changed its voxel, used up its margin, or has no usable list yet): look the row up
+// again if the key changed, search the octants within R = d + margin exactly, and copy every stored point in them into the
+// query's candidate list.  Kept out of line: the REUSE path — nearly every query of nearly every iteration — must not
+// pay for this path's registers (with both inlined the kernel spilled 232 bytes per thread = 58 MB of local-memory
+// stores per launch).
+struct WarmRefresh {
+    Best b;           // the exact nearest neighbour (none: idx == kNone)
+    float4 wpt;       // the matched point itself
+    int row;          // directory row of the query's key or -1
+    uint32_t n_new;   // length of the new candidate list; kNone: unusable
+    float Rf;         // every point of the 27 voxels within Rf of the query's fp32 rounding is in the list
+};
+// (The map and the work buffers arrive as scalars: a reference to a kernel-parameter struct would make the compiler copy
+// the whole struct to local memory in every thread.)
+template <int FUSE>
+__device__ __noinline__ void warm_refresh(const uint4* dslots, const uint32_t* drows, const float4* pts, uint32_t bmask, double voxel_size,
+                                          double inv_voxel_size, float4* out_cand, uint32_t* out_cidx, uint32_t ccap, double warm_margin, uint4 m0,
+                                          float4 prev, bool same_key, double px, double py, double pz, WarmRefresh* out) {
+    MapView map;
+    map.dslots = dslots; map.drows = drows; map.pts = pts; map.bmask = bmask; map.voxel_size = voxel_size; map.inv_voxel_size = inv_voxel_size;
+    map.prec = nullptr; map.vslots = nullptr; map.vcov = nullptr; map.vcand = nullptr; map.dir7 = nullptr; map.mask = 0;
+    const float kInf = __int_as_float(0x7f800000);
+    const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
+    constexpr size_t cstride = kIcpThreads;
+    float fx, fy, fz;
+    const int kx = voxel_floor(px, map, &fx), ky = voxel_floor(py, map, &fy), kz = voxel_floor(pz, map, &fz);
+    Best b;
+    float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
+    int row;
+    bool prev_ok = m0.w != kNone;
+    if (same_key) {
+        row = static_cast<int>(m0.x);  // same voxel as last time: same row, and the old match is one of its candidates
+    } else {
+        uint2 centre;
+        row = dir_lookup(map, kx, ky, kz, centre);
+        if (prev_ok) {  // still inside the 27 voxels of the new key?
+            const int cx = stored_key(prev.x, map) - kx, cy = stored_key(prev.y, map) - ky, cz = stored_key(prev.z, map) - kz;
+            prev_ok = cx >= -1 && cx <= 1 && cy >= -1 && cy <= 1 && cz >= -1 && cz <= 1;
+        }
+    }
+    uint32_t n_new = kNone;
+    double R = 0.0;
+    if (row >= 0) {
+        float bound = kInf;
+        if (prev_ok) {
+            b.d2 = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
+            b.idx = m0.w; b.rank = __float_as_uint(prev.w);
+            R = (sqrt(b.d2) + warm_margin) * (1.0 + 1e-9);
+            bound = __double2float_ru(R * R) * inv_vs2_up;
+            n_new = 0;  // (the points within a finite bound are worth remembering)
+        }
+        const Query Q(px, py, pz);
+        // the octants bound WHICH points have to be looked at; the list keeps only those really within R (a handful)
+        const double R2 = R * R;
+        octant_runs(map, row, kx, ky, kz, fx, fy, fz, bound, 0x1ffu, [&](uint32_t rs, uint32_t re) {
+            visit_points(map.pts, rs, re - rs, Q, b);
+            for (uint32_t p = rs; p < re && n_new != kNone; ++p) {
+                const float4 c = __ldg(map.pts + p);  // (just read by visit_points: L1)
+                if (sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz) <= R2) {
+                    if (n_new >= ccap) { n_new = kNone; break; }  // does not fit: no list
+                    out_cand[static_cast<size_t>(n_new) * cstride] = c;
+                    out_cidx[static_cast<size_t>(n_new) * cstride] = p;
+                    ++n_new;
+                }
+            }
+        });
+        if (b.idx != kNone) wpt = __ldg(map.pts + b.idx);
+    }
+    // what the list is good for: every point of the 27 voxels within R of the query; the memo keeps the query rounded to fp32
+    // (q0), so R shrinks by that rounding
+    const double ex = px - static_cast<double>(static_cast<float>(px)), ey = py - static_cast<double>(static_cast<float>(py)),
+                 ez = pz - static_cast<double>(static_cast<float>(pz));
+    out->b = b; out->wpt = wpt; out->row = row; out->n_new = n_new;
+    out->Rf = __double2float_rd(R - sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9));
+}
+
+// REFRESH of ONE query by the whole warp (a straggler: a query that crossed into another voxel while its 31 warp-mates
+// reuse their lists).  The kernel is a single wave, so it lasts as long as its slowest warp; a lone thread walking
+// lookup -> records -> runs -> points is ~15 dependent memory round trips, the warp does it in three: every lane computes the
+// query's bound and masks (same inputs, same results), lanes 0..8 take one z-column each (record + runs), the points of all
+// runs are then spread over the lanes, and the results meet in shuffles.  Same arithmetic as warm_refresh.
+// q = the owner's lane; every lane passes ITS OWN values, the owner's are broadcast.  s_run: 64 words of the warp.
+struct WarmQuery { double px, py, pz; uint4 m0; float4 prev; bool same_key; size_t cbase; };
+__device__ __forceinline__ double shfl_double(double v, int src) {
+    const long long b = __double_as_longlong(v);
+    const int lo = __shfl_sync(kFull, static_cast<int>(b), src), hi = __shfl_sync(kFull, static_cast<int>(b >> 32), src);
+    return __longlong_as_double((static_cast<long long>(hi) << 32) | static_cast<unsigned int>(lo));
+}
+template <int FUSE>
+__device__ __noinline__ void warm_refresh_warp(const uint4* dslots, const uint32_t* drows, const float4* pts, uint32_t bmask, double voxel_size,
+                                               double inv_voxel_size, float4* cand, uint32_t* cidx, uint32_t ccap, double warm_margin, int q,
+                                               const WarmQuery* mine, unsigned int* s_run, WarmRefresh* out) {
+    MapView map;
+    map.dslots = dslots; map.drows = drows; map.pts = pts; map.bmask = bmask; map.voxel_size = voxel_size; map.inv_voxel_size = inv_voxel_size;
+    map.prec = nullptr; map.vslots = nullptr; map.vcov = nullptr; map.vcand = nullptr; map.dir7 = nullptr; map.mask = 0;
+    const int lane = threadIdx.x & 31;
+    const float kInf = __int_as_float(0x7f800000);
+    const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
+    constexpr size_t cstride = kIcpThreads;
+    // the owner's query, in every lane
+    const double px = shfl_double(mine->px, q), py = shfl_double(mine->py, q), pz = shfl_double(mine->pz, q);
+    uint4 m0; float4 prev;
+    m0.x = __shfl_sync(kFull, mine->m0.x, q); m0.y = __shfl_sync(kFull, mine->m0.y, q); m0.z = __shfl_sync(kFull, mine->m0.z, q); m0.w = __shfl_sync(kFull, mine->m0.w, q);
+    prev.x = __shfl_sync(kFull, mine->prev.x, q); prev.y = __shfl_sync(kFull, mine->prev.y, q); prev.z = __shfl_sync(kFull, mine->prev.z, q);
+    prev.w = __shfl_sync(kFull, mine->prev.w, q);
+    const bool same_key = __shfl_sync(kFull, mine->same_key ? 1 : 0, q) != 0;
+    const size_t cbase = (static_cast<size_t>(__shfl_sync(kFull, static_cast<unsigned int>(mine->cbase >> 32), q)) << 32) |
+                         __shfl_sync(kFull, static_cast<unsigned int>(mine->cbase), q);
+    float fx, fy, fz;
+    const int kx = voxel_floor(px, map, &fx), ky = voxel_floor(py, map, &fy), kz = voxel_floor(pz, map, &fz);
+    int row;
+    bool prev_ok = m0.w != kNone;
+    if (same_key) {
+        row = static_cast<int>(m0.x);
+    } else {
+        uint2 centre;
+        row = dir_lookup(map, kx, ky, kz, centre);  // (all lanes: the same two sectors)
+        if (prev_ok) {
+            const int cx = stored_key(prev.x, map) - kx, cy = stored_key(prev.y, map) - ky, cz = stored_key(prev.z, map) - kz;
+            prev_ok = cx >= -1 && cx <= 1 && cy >= -1 && cy <= 1 && cz >= -1 && cz <= 1;
+        }
+    }
+    Best b;
+    float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
+    uint32_t n_new = kNone;
+    double R = 0.0;
+    if (row >= 0) {
+        float bound = kInf;
+        if (prev_ok) {
+            b.d2 = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
+            b.idx = m0.w; b.rank = __float_as_uint(prev.w);
+            R = (sqrt(b.d2) + warm_margin) * (1.0 + 1e-9);
+            bound = __double2float_ru(R * R) * inv_vs2_up;
+            n_new = 0;
+        }
+        const double R2 = R * R;
+        // lanes 0..8: the runs of one z-column each (at most three per column)
+        uint32_t rs3[3] = {0, 0, 0}, rl3[3] = {0, 0, 0};
+        int nr = 0;
+        if (lane < 9)
+            octant_runs(map, row, kx, ky, kz, fx, fy, fz, bound, 1u << lane, [&](uint32_t rs, uint32_t re) {
+                if (nr == 0) { rs3[0] = rs; rl3[0] = re - rs; } else if (nr == 1) { rs3[1] = rs; rl3[1] = re - rs; } else { rs3[2] = rs; rl3[2] = re - rs; }
+                ++nr;
+            });
+        // all runs of the query in the warp's table {first point, first flattened index}, and the total number of points
+        uint32_t mine_pts = rl3[0] + rl3[1] + rl3[2], off = mine_pts;
+        int slot = nr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFull, off, o);
+            const int w = __shfl_up_sync(kFull, slot, o);
+            if (lane >= o) { off += v; slot += w; }
+        }
+        const uint32_t total = __shfl_sync(kFull, off, 31);
+        const int nruns = __shfl_sync(kFull, slot, 31);
+        off -= mine_pts; slot -= nr;
+        for (int k = 0; k < nr; ++k) {
+            const uint32_t st = k == 0 ? rs3[0] : (k == 1 ? rs3[1] : rs3[2]);
+            s_run[2 * (slot + k)] = st;
+            s_run[2 * (slot + k) + 1] = off;
+            off += k == 0 ? rl3[0] : (k == 1 ? rl3[1] : rl3[2]);
+        }
+        if (lane == 0) { s_run[2 * nruns] = 0; s_run[2 * nruns + 1] = total; }  // sentinel
+        __syncwarp();
+        // the points of all runs spread over the lanes: exact distances, the list of those within R, the nearest
+        Best lb;            // this lane's nearest
+        float4 lpt = wpt;
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t j = base + lane;
+            bool within = false;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t p = 0;
+            if (j < total) {
+                int r = 0;
+                while (j >= s_run[2 * (r + 1) + 1]) ++r;
+                p = s_run[2 * r] + (j - s_run[2 * r + 1]);
+                c = __ldg(map.pts + p);
+                const double d2 = sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz);
+                if (closer(d2, __float_as_uint(c.w), lb)) { lb.d2 = d2; lb.rank = __float_as_uint(c.w); lb.idx = p; lpt = c; }
+                within = d2 <= R2;
+            }
+            const uint32_t wmask = __ballot_sync(kFull, within);
+            if (n_new != kNone) {
+                const uint32_t cnt = __popc(wmask);
+                if (n_new + cnt > ccap) n_new = kNone;  // does not fit: no list
+                else {
+                    if (within) {
+                        const uint32_t pos = n_new + __popc(wmask & ((1u << lane) - 1u));
+                        cand[cbase + static_cast<size_t>(pos) * cstride] = c;
+                        cidx[cbase + static_cast<size_t>(pos) * cstride] = p;
+                    }
+                    n_new += cnt;
+                }
+            }
+        }
+        __syncwarp();
+        // the warp's nearest: smaller distance, then smaller rank; the previous match competes through b
+        if (lb.idx != kNone && closer(lb.d2, lb.rank, b)) b = lb;
+        bool have_pt = lb.idx != kNone && b.idx == lb.idx;  // this lane holds the coordinates of its candidate
+        if (!have_pt) lpt = wpt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Best ob;
+            ob.d2 = shfl_double(b.d2, lane ^ o);
+            ob.idx = __shfl_xor_sync(kFull, b.idx, o);
+            ob.rank = __shfl_xor_sync(kFull, b.rank, o);
+            float4 opt;
+            opt.x = __shfl_xor_sync(kFull, lpt.x, o); opt.y = __shfl_xor_sync(kFull, lpt.y, o); opt.z = __shfl_xor_sync(kFull, lpt.z, o); opt.w = __shfl_xor_sync(kFull, lpt.w, o);
+            const bool ohave = __shfl_xor_sync(kFull, have_pt ? 1 : 0, o) != 0;
+            if (ob.idx != kNone && (closer(ob.d2, ob.rank, b) || (ob.idx == b.idx && ohave && !have_pt))) { b = ob; lpt = opt; have_pt = ohave; }
+        }
+        if (b.idx != kNone) wpt = have_pt ? lpt : __ldg(map.pts + b.idx);  // (the previous match won: its coordinates are not in a lane)
+    }
+    const double ex = px - static_cast<double>(static_cast<float>(px)), ey = py - static_cast<double>(static_cast<float>(py)),
+                 ez = pz - static_cast<double>(static_cast<float>(pz));
+    if (lane == q) {
+        out->b = b; out->wpt = wpt; out->row = row; out->n_new = n_new;
+        out->Rf = __double2float_rd(R - sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9));
+    }
+}
+
+// One thread per query, and as few instructions per query as the arithmetic allows: the kernel is a single wave of warps
+// (131 072 queries = 27.7 warps per SM), so its duration is the length of one warp's instruction stream.
 template <int FUSE>
 __global__ void __launch_bounds__(kIcpThreads, FUSE == 1 ? 3 : 4)
 icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int solve_here) {
@@ -1213,199 +1482,154 @@ icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams pr
     __shared__ double s_red[kFuse ? kIcpWarps : 1][kAcc], s_sum[kAcc], s_acc[kAcc];
     __shared__ SolveScratch s_solve;
     __shared__ bool s_last;
-    __shared__ __align__(16) float s_tile[kIcpThreads * 3];
-    __shared__ __align__(8) uint64_t s_bar;
     __shared__ double s_T[12];
-    __shared__ double s_px[kIcpThreads], s_py[kIcpThreads], s_pz[kIcpThreads];
-    __shared__ unsigned long long s_best[kIcpThreads];   // bits of the smallest exact squared distance of the query
-    __shared__ unsigned long long s_win[kIcpThreads];    // rank << 32 | index among the candidates at that distance
-    __shared__ unsigned long long s_item[kIcpWarps][kWarmCap];  // item {start, (end - pair start) | lane << 8}; after phase B: distance bits
-    __shared__ unsigned int s_item_idx[kIcpWarps][kWarmCap];    // phase B result: index of the item's nearest point
-    __shared__ unsigned char s_item_q[kIcpWarps][kWarmCap];     // owner lane of the item
-    __shared__ int s_nitems[kIcpWarps];
+    __shared__ unsigned int s_run[kIcpWarps][64];  // warm_refresh_warp: the runs of the query the warp refreshes together
 
     pdl_launch_dependents();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int tile_pts = kIcpThreads;
-    const int ntiles = (prm.n + tile_pts - 1) / tile_pts;
-    const bool base_aligned = (reinterpret_cast<uintptr_t>(scan) & 15) == 0;
-    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    auto tile_count = [&](int t) { return min(tile_pts, prm.n - t * tile_pts); };
-    auto tile_tma_ok = [&](int t) { return base_aligned && ((tile_count(t) * 12) & 15) == 0; };
-    auto issue = [&](int t) {
-        const uint32_t bytes = tile_count(t) * 12;
-        mbar_expect_tx(&s_bar, bytes);
-        tma_load_1d(s_tile, scan + static_cast<size_t>(t) * tile_pts * 3, bytes, &s_bar);
-    };
-    const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
+    const int tid = threadIdx.x, lane = tid & 31;
     const float kInf = __int_as_float(0x7f800000);
-    uint32_t visited = 0, searched = 0;
-    int tile = blockIdx.x;
-    uint32_t phase = 0;
-    const bool first_by_tma = tile < ntiles && tile_tma_ok(tile);
-    if (first_by_tma && tid == 0) issue(tile);  // the scan is never written inside the loop: its first tile may start before the wait
+    uint4* const memo0 = wk.memo;                   // {row, key_lo, key_hi, index of the match}
+    uint4* const memo1 = wk.memo + wk.memo_stride;  // {q0.x, q0.y, q0.z, R} as floats: the list holds every point of the 27 voxels within R of q0
+    uint32_t* const ncand = wk.ncand;               // length of the candidate list; kNone: unusable
+    const uint32_t ccap = static_cast<uint32_t>(wk.cand_cap);
+    uint32_t visited = 0, searched = 0, refreshed = 0;
+    // the scan is never written inside the loop: this thread's first point may be read before the previous kernel has finished
+    int gi = blockIdx.x * kIcpThreads + tid;
+    float sxf = 0.f, syf = 0.f, szf = 0.f;
+    if (gi < prm.n) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
     pdl_wait();
-    if (st->done) {
-        if (first_by_tma) mbar_wait(&s_bar, 0);
-        return;
-    }
+    if (st->done) return;
     if (tid < 12) s_T[tid] = st->T[tid];
     if (kFuse) {
         if (tid < 12) s_Tinv[tid] = st->Tinv[tid];
         if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
         if (tid < kAcc) s_sum[tid] = 0.0;
     }
-    for (bool first = true; tile < ntiles; tile += gridDim.x, first = false) {
-        const int cnt = tile_count(tile);
-        const bool mine = tid < cnt;
-        const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
-        // the previous iteration's result for this query: coalesced, in flight while the scan tile lands
-        uint4 memo = make_uint4(kNone, kNone, kNone, kNone);
-        float4 prev = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
-        if (mine) { memo = wk.memo[gi]; prev = wk.win[gi]; }
-        if (tile_tma_ok(tile)) {
-            if (!first && tid == 0) issue(tile);
-            mbar_wait(&s_bar, phase);
-            phase ^= 1;
-        } else {
-            const int nf = cnt * 3;
-            for (int i = tid; i < nf; i += kIcpThreads) s_tile[i] = scan[static_cast<size_t>(tile) * tile_pts * 3 + i];
-        }
-        if (lane == 0) s_nitems[warp] = 0;
-        __syncthreads();
-        // ---- phase A
+    __syncthreads();
+    for (bool first = true; gi - tid < prm.n; gi += gridDim.x * kIcpThreads, first = false) {
+#ifdef ELM_PHASE_TIMING
+        long long wtick = clock64();
+        if (prm.stats && lane == 0) atomicAdd(prm.stats + 22, 1ull);
+#endif
+        const bool mine = gi < prm.n;
         double px = 0, py = 0, pz = 0, sx = 0, sy = 0, sz = 0;
-        Best own;  // the previous match + whatever this thread has to scan itself
+        Best b;
+        float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));  // the matched point itself
         int row = -1;
         uint32_t qkey_lo = kNone, qkey_hi = kNone;
+        bool refresh = false;
+        WarmQuery wq;
+        wq.px = wq.py = wq.pz = 0.0; wq.m0 = make_uint4(kNone, kNone, kNone, kNone); wq.prev = wpt; wq.same_key = false; wq.cbase = 0;
         if (mine) {
-            sx = s_tile[tid * 3]; sy = s_tile[tid * 3 + 1]; sz = s_tile[tid * 3 + 2];
+            // candidate j of this query: tile-interleaved (icp_device.cuh) — the 256 queries of a tile keep their lists in one
+            // contiguous block, candidate-major inside it, so a warp reads 512 consecutive bytes per candidate
+            const size_t cbase = static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
+            const float4* const my_cand = wk.cand + cbase;
+            const uint32_t* const my_cidx = wk.cidx + cbase;
+            constexpr size_t cstride = kIcpThreads;
+            const uint4 m0 = memo0[gi], m1 = memo1[gi];
+            const uint32_t nc = ncand[gi];
+            const float4 prev = wk.win[gi];
+            if (!first) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
+            sx = sxf; sy = syf; sz = szf;
             px = row_apply_exact(s_T, 0, sx, sy, sz);
             py = row_apply_exact(s_T, 1, sx, sy, sz);
             pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            float fx, fy, fz;
-            const int kx = voxel_floor(px, map, &fx), ky = voxel_floor(py, map, &fy), kz = voxel_floor(pz, map, &fz);
+            const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
             ++searched;
             const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
             if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
-            bool prev_ok = memo.w != kNone;
-            if (in_range && memo.y == qkey_lo && memo.z == qkey_hi) {
-                row = static_cast<int>(memo.x);  // same voxel as last time: same row, and the old match is one of its candidates
+            const bool same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
+            ELM_USE(same_key && prev.x == 1e30f);
+            ELM_WTICK(23);
+            // REUSE: same key and  d' + |q - q0| <= R  with d' = distance to the previous match (each side rounded against us)
+            bool reuse = false;
+            if (same_key && m0.w != kNone && nc <= ccap) {
+                const double d2_prev = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
+                const float dx = static_cast<float>(px - static_cast<double>(__uint_as_float(m1.x))), dy = static_cast<float>(py - static_cast<double>(__uint_as_float(m1.y))),
+                            dz = static_cast<float>(pz - static_cast<double>(__uint_as_float(m1.z)));
+                const float delta = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f + 1e-30f;
+                const float room = (__uint_as_float(m1.w) - delta) * 0.999999f;  // what is left of R for d'
+                reuse = room > 0.f && d2_prev <= static_cast<double>(room) * static_cast<double>(room);
+            }
+            if (reuse) {
+                row = static_cast<int>(m0.x);
+                // one fp32 pass over the list (coalesced: candidate j of the warp's queries is 512 consecutive bytes), four loads
+                // in flight, then ONE decision (the band of visit_points): the fp32 argmin is the unique exact winner, or (a near
+                // tie) the list is decided again exactly
+                const Query Q(px, py, pz);
+                float m = kInf, s2 = kInf;
+                uint32_t mj = 0;
+                for (uint32_t j = 0; j < nc; j += 4) {
+                    float4 c[4];  // (addresses past the list are clamped, not predicated: a predicated load sent c[] to local memory)
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) c[u] = my_cand[static_cast<size_t>(min(j + u, nc - 1)) * cstride];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        const float dx = c[u].x - Q.fx, dy = c[u].y - Q.fy, dz = c[u].z - Q.fz;
+                        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        d = (j + u < nc) ? d : kInf;
+                        s2 = fminf(s2, fmaxf(d, m)); mj = (d < m) ? j + u : mj; m = fminf(m, d);
+                    }
+                }
+                visited += nc;
+                ELM_USE(m < 0.f);
+                ELM_WTICK(24);
+                const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);
+                const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
+                if (s2 > T) {
+                    wpt = my_cand[static_cast<size_t>(mj) * cstride];
+                    b.d2 = sq3_exact(static_cast<double>(wpt.x) - px, static_cast<double>(wpt.y) - py, static_cast<double>(wpt.z) - pz);
+                    b.rank = __float_as_uint(wpt.w);
+                } else {  // near tie (or an empty list): every candidate exactly, smallest rank among equals
+                    for (uint32_t j = 0; j < nc; ++j) {
+                        const float4 c = my_cand[static_cast<size_t>(j) * cstride];
+                        const double d2 = sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz);
+                        if (closer(d2, __float_as_uint(c.w), b)) { b.d2 = d2; b.rank = __float_as_uint(c.w); b.idx = j; wpt = c; }
+                    }
+                    mj = b.idx;
+                }
+                b.idx = nc ? my_cidx[static_cast<size_t>(mj) * cstride] : kNone;
+            } else if (same_key && static_cast<int>(m0.x) < 0) {
+                // same voxel as last time and its 27-neighbourhood holds no point: still nothing to find (Q2 applies downstream)
             } else {
-                uint2 centre;
-                row = dir_lookup(map, kx, ky, kz, centre);
-                if (prev_ok) {  // still inside the 27 voxels of the new key?
-                    const int cx = stored_key(prev.x, map) - kx, cy = stored_key(prev.y, map) - ky, cz = stored_key(prev.z, map) - kz;
-                    prev_ok = cx >= -1 && cx <= 1 && cy >= -1 && cy <= 1 && cz >= -1 && cz <= 1;
-                }
+                // REFRESH: a query that changed its voxel, used up its margin, or has no usable list (first warm iteration)
+                refresh = true;
+                ++refreshed;
+#ifdef ELM_PHASE_TIMING
+                if (prm.stats) atomicAdd(prm.stats + (!same_key ? 30 : (m0.w == kNone ? 31 : (nc > ccap ? 28 : 29))), 1ull);
+#endif
+                wq.m0 = m0; wq.prev = prev; wq.same_key = same_key; wq.cbase = cbase;
             }
-            s_px[tid] = px; s_py[tid] = py; s_pz[tid] = pz;
-            s_best[tid] = static_cast<unsigned long long>(__double_as_longlong(kDblMax));
-            s_win[tid] = ~0ull;
-            if (row >= 0) {
-                float bound = kInf;
-                if (prev_ok) {
-                    own.d2 = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
-                    own.idx = memo.w; own.rank = __float_as_uint(prev.w);
-                    bound = __double2float_ru(own.d2) * inv_vs2_up;
-                }
-                float gvx[3], gvy[3], gvz[3];
-                const uint32_t hx = axis_halves(kx, fx, bound, gvx), hy = axis_halves(ky, fy, bound, gvy), hz = axis_halves(kz, fz, bound, gvz);
-                const float gzmin = fminf(fminf(gvz[0], gvz[1]), gvz[2]);
-                uint32_t colmask = 0;
-#pragma unroll
-                for (int c = 0; c < 9; ++c)
-                    if (((hx >> (2 * (c / 3))) & 3u) && ((hy >> (2 * (c % 3))) & 3u) && !((gvx[c / 3] + gvy[c % 3] + gzmin) * 0.9999f > bound)) colmask |= 1u << c;
-                auto emit = [&](uint32_t rs, uint32_t re) {
-                    if (re <= rs) return;
-                    visited += re - rs;
-                    const uint32_t p0 = rs & ~1u;
-                    const uint32_t npairs = ((re - 1) >> 1) - (rs >> 1) + 1;
-                    const int nit = static_cast<int>((npairs + 2) / 3);
-                    const int pos = atomicAdd(&s_nitems[warp], nit);
-                    if (pos + nit <= kWarmCap) {
-                        for (int i = 0; i < nit; ++i) {
-                            const uint32_t is = (i == 0) ? rs : p0 + 6u * i, ie = min(re, p0 + 6u * (i + 1));
-                            s_item[warp][pos + i] = (static_cast<unsigned long long>((ie - (is & ~1u)) | (static_cast<uint32_t>(lane) << 8)) << 32) | is;
-                        }
-                    } else {  // list full: holes for the part of the claim that is inside the list, and this thread scans the run itself
-                        for (int j = pos; j < kWarmCap; ++j) s_item[warp][j] = 0ull;
-                        for (uint32_t is = rs; is < re;) {
-                            const uint32_t ie = min(re, (is & ~1u) + 6u);
-                            scan_item_exact(map.pts, is, ie, px, py, pz, own);
-                            is = ie;
-                        }
-                    }
-                };
-                while (colmask) {
-                    const int c = __ffs(colmask) - 1;
-                    colmask &= colmask - 1;
-                    const int ox = c / 3, oy = c - 3 * ox;
-                    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-                    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(map.drows + row_col_word(static_cast<size_t>(row), c)));
-                    const uint32_t xpat = (((hx >> (2 * ox)) & 1u) ? 0x55u : 0u) | (((hx >> (2 * ox)) & 2u) ? 0xaau : 0u);
-                    const uint32_t ypat = (((hy >> (2 * oy)) & 1u) ? 0x33u : 0u) | (((hy >> (2 * oy)) & 2u) ? 0xccu : 0u);
-                    const float gxy = (ox == 0 ? gvx[0] : (ox == 1 ? gvx[1] : gvx[2])) + (oy == 0 ? gvy[0] : (oy == 1 ? gvy[1] : gvy[2]));
-                    uint32_t run_s = 0, run_e = 0, vfirst = r0;
-#pragma unroll
-                    for (int dz = 0; dz < 3; ++dz) {
-                        const uint32_t n = (r1 >> (kDirCountBits * dz)) & kDirCountMask;
-                        const uint32_t zh = (hz >> (2 * dz)) & 3u;
-                        if (n && zh && !((gxy + gvz[dz]) * 0.9999f > bound)) {
-                            const unsigned long long ow = (static_cast<unsigned long long>(dz == 0 ? r3 : (dz == 1 ? r5 : r7)) << 32) | (dz == 0 ? r2 : (dz == 1 ? r4 : r6));
-                            uint32_t a = 0, e = n;
-                            if (ow >> 56) {  // octant words valid (byte 7 = n for cap <= 255, 0 otherwise)
-                                const uint32_t need = xpat & ypat & (((zh & 1u) ? 0x0fu : 0u) | ((zh & 2u) ? 0xf0u : 0u));
-                                const int lo = __ffs(need) - 1, hi = 32 - __clz(need);  // octants lo .. hi - 1
-                                a = lo ? static_cast<uint32_t>(ow >> (8 * (lo - 1))) & 0xffu : 0u;
-                                e = hi < 8 ? static_cast<uint32_t>(ow >> (8 * (hi - 1))) & 0xffu : n;
-                            }
-                            const uint32_t rs = vfirst + a, re = vfirst + e;
-                            if (re > rs) {
-                                if (run_e > run_s && rs <= run_e + 2) run_e = re;  // touches (or nearly) the run of the voxel below: one run
-                                else { emit(run_s, run_e); run_s = rs; run_e = re; }
-                            }
-                        }
-                        vfirst += n;
-                    }
-                    emit(run_s, run_e);
-                }
+            wq.px = px; wq.py = py; wq.pz = pz;
+        }
+        // a few stragglers: the whole warp refreshes them one after the other; many (the first warm iteration): every thread its own
+        const uint32_t rmask = __ballot_sync(kFull, refresh);
+        if (rmask) {
+            WarmRefresh r;
+            if (__popc(rmask) <= 6) {
+                for (uint32_t left = rmask; left; left &= left - 1)
+                    warm_refresh_warp<FUSE>(map.dslots, map.drows, map.pts, map.bmask, map.voxel_size, map.inv_voxel_size, wk.cand, wk.cidx, ccap,
+                                            prm.warm_margin, __ffs(left) - 1, &wq, s_run[tid >> 5], &r);
+            } else if (refresh) {
+                warm_refresh<FUSE>(map.dslots, map.drows, map.pts, map.bmask, map.voxel_size, map.inv_voxel_size, wk.cand + wq.cbase, wk.cidx + wq.cbase, ccap,
+                                   prm.warm_margin, wq.m0, wq.prev, wq.same_key, px, py, pz, &r);
+            }
+            if (refresh) {
+                b = r.b; wpt = r.wpt; row = r.row;
+                memo1[gi] = make_uint4(__float_as_uint(static_cast<float>(px)), __float_as_uint(static_cast<float>(py)), __float_as_uint(static_cast<float>(pz)),
+                                       __float_as_uint(r.Rf));
+                ncand[gi] = r.n_new;
             }
         }
-        __syncwarp();
-        // ---- phase B
-        const int nitems = min(s_nitems[warp], kWarmCap);
-        for (int j = lane; j < nitems; j += 32) {
-            const unsigned long long it = s_item[warp][j];
-            const uint32_t is = static_cast<uint32_t>(it), info = static_cast<uint32_t>(it >> 32);
-            const int q = (warp << 5) | static_cast<int>(info >> 8);
-            s_item_q[warp][j] = static_cast<unsigned char>(info >> 8);
-            Best ib;
-            if (info & 0xffu) scan_item_exact(map.pts, is, (is & ~1u) + (info & 0xffu), s_px[q], s_py[q], s_pz[q], ib);
-            s_item[warp][j] = static_cast<unsigned long long>(__double_as_longlong(ib.d2));
-            s_item_idx[warp][j] = ib.idx;
-            if (ib.idx != kNone) atomicMin(&s_best[q], static_cast<unsigned long long>(__double_as_longlong(ib.d2)));
-        }
-        if (mine && own.idx != kNone) atomicMin(&s_best[tid], static_cast<unsigned long long>(__double_as_longlong(own.d2)));
-        __syncwarp();
-        // ---- phase C
-        for (int j = lane; j < nitems; j += 32) {
-            const uint32_t idx = s_item_idx[warp][j];
-            const int q = (warp << 5) | s_item_q[warp][j];
-            if (idx != kNone && s_item[warp][j] == s_best[q]) atomicMin(&s_win[q], rank_idx(__float_as_uint(__ldg(map.pts + idx).w), idx));
-        }
-        if (mine && own.idx != kNone && static_cast<unsigned long long>(__double_as_longlong(own.d2)) == s_best[tid])
-            atomicMin(&s_win[tid], rank_idx(own.rank, own.idx));
-        __syncwarp();
+        ELM_USE(b.d2 < 0.0);
+        ELM_WTICK(25);
         int my_match = -1;
-        float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
         if (mine) {
-            if (s_win[tid] != ~0ull) { my_match = static_cast<int>(static_cast<uint32_t>(s_win[tid])); wpt = __ldg(map.pts + my_match); }
+            if (b.idx != kNone) my_match = static_cast<int>(b.idx);
             if (wk.match) wk.match[gi] = my_match;
             wk.win[gi] = wpt;
-            wk.memo[gi] = make_uint4(static_cast<uint32_t>(row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+            memo0[gi] = make_uint4(static_cast<uint32_t>(row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
         }
         if (kFuse) {
             double acc[NACC];
@@ -1413,15 +1637,17 @@ icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams pr
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             if (mine) linearize_point_pair<FUSE == 1 ? 1 : 0>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
             block_sum_into<NACC, FUSE == 0>(acc, s_red, s_sum);
-        } else if (tile + static_cast<int>(gridDim.x) < ntiles) {
-            __syncthreads();  // the tile buffer is refilled next
         }
     }
     if (prm.stats) {
-        for (int o = 16; o > 0; o >>= 1) { visited += __shfl_xor_sync(kFull, visited, o); searched += __shfl_xor_sync(kFull, searched, o); }
+        for (int o = 16; o > 0; o >>= 1) {
+            visited += __shfl_xor_sync(kFull, visited, o); searched += __shfl_xor_sync(kFull, searched, o); refreshed += __shfl_xor_sync(kFull, refreshed, o);
+        }
         if (lane == 0 && searched) {
             atomicAdd(prm.stats, static_cast<unsigned long long>(visited));
             atomicAdd(prm.stats + 1, static_cast<unsigned long long>(searched));
+            atomicAdd(prm.stats + 20, static_cast<unsigned long long>(refreshed));  // warm searches that could not reuse their candidate list
+            atomicAdd(prm.stats + 21, static_cast<unsigned long long>(searched));   // warm searches
         }
     }
     if (kFuse) finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here);
@@ -1626,6 +1852,13 @@ icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __rest
 // developer switch: ELM_NO_PDL=1 launches every kernel fully serialised
 static const bool g_use_pdl = [] { const char* e = getenv("ELM_NO_PDL"); return !(e && e[0] == '1'); }();
 
+// blocks of the warm-started search: one query per thread, grid-stride loop beyond one resident wave
+int icp_warm_grid(const IcpParams& prm, int num_sms) {
+    const int blocks = (prm.n + kIcpThreads - 1) / kIcpThreads;
+    const int cap = 4 * num_sms;
+    return blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+}
+
 int icp_search_grid(const IcpParams& prm, int num_sms) {
     int blocks;
     if (prm.method <= 1) {
@@ -1675,6 +1908,7 @@ cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* 
                               int grid, int prune, int fuse, int warm, int solve_here, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
     if (prm.method <= 1 && warm && prune && !orig) {
+        grid = warm;  // (the caller passes the warm grid in `warm`)
         if (!fuse) e = launch_pdl(icp_search_warm_kernel<-1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
         else if (prm.method == 0) e = launch_pdl(icp_search_warm_kernel<0>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
         else e = launch_pdl(icp_search_warm_kernel<1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);

@@ -10,6 +10,7 @@ constexpr int kIcpThreads = kIcpWarps * 32;
 struct Pose16 { double m[16]; };
 
 int icp_search_grid(const IcpParams& prm, int num_sms);
+int icp_warm_grid(const IcpParams& prm, int num_sms);
 // blocks of the accumulation kernel (== rows of `partials`)
 int icp_accumulate_grid(const IcpParams& prm, int num_sms);
 
@@ -17,7 +18,8 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
 // P2P / GICP / VGICP correspondence search -> wk.match[n] (+ wk.win, wk.memo for P2P / GICP); no-op for AVGICP, which searches
 // inside the accumulation.  `orig` (may be NULL): scan is in binned order and the outputs are written at orig[i].
 // fuse (P2P / GICP): the search kernel also linearises, reduces and — when solve_here — solves: one launch per iteration.
-// warm (P2P / GICP): the search starts from the previous iteration's wk.win / wk.memo of the SAME scan (icp_kernels.cu).
+// warm (P2P / GICP): != 0 = the search starts from the previous iteration's wk.win / wk.memo of the SAME scan (icp_kernels.cu);
+// the value is the grid of the warm kernel (icp_warm_grid).
 cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, const IcpWork& wk,
                               int grid, int prune, int fuse, int warm, int solve_here, cudaStream_t s);
 cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int solve_here,

@@ -73,9 +73,10 @@ std::string parse_header(std::FILE* f, Header& h) {
         Field& fd = h.fields[i];
         if (fd.size != 1 && fd.size != 2 && fd.size != 4 && fd.size != 8) return "PCD header: unsupported SIZE";
         if (fd.type != 'F' && fd.type != 'I' && fd.type != 'U') return "PCD header: unsupported TYPE";
-        if (fd.count < 1) return "PCD header: COUNT < 1";
+        if (fd.count < 1 || fd.count > 65536) return "PCD header: COUNT out of range";
         fd.offset = off;
         off += static_cast<size_t>(fd.size) * static_cast<size_t>(fd.count);
+        if (off > (1u << 16)) return "PCD header: record larger than 64 KiB";  // (keeps POINTS x record far from overflowing size_t)
         if (fd.name == "x") h.ix = static_cast<int>(i);
         if (fd.name == "y") h.iy = static_cast<int>(i);
         if (fd.name == "z") h.iz = static_cast<int>(i);
@@ -146,6 +147,22 @@ std::string read_pcd_xyz(const std::string& path, std::vector<float>& xyz, size_
     const std::string e = parse_header(f.get(), h);
     if (!e.empty()) return path + ": " + e;
     const Field &fx = h.fields[h.ix], &fy = h.fields[h.iy], &fz = h.fields[h.iz];
+    // POINTS comes from an untrusted header: never reserve more than the file can hold (a point needs at least 6 bytes in
+    // ascii — three one-digit values, separators, newline — and `record` bytes in the binary encodings, where LZF expands
+    // at most ~264 x), so a forged count cannot exhaust the host's memory before the data turns out to be missing
+    {
+        const long pos = std::ftell(f.get());
+        size_t remaining = 0;
+        if (pos >= 0 && std::fseek(f.get(), 0, SEEK_END) == 0) {
+            const long end = std::ftell(f.get());
+            if (end >= pos) remaining = static_cast<size_t>(end - pos);
+            std::fseek(f.get(), pos, SEEK_SET);
+        }
+        const size_t per_point = h.data == "ascii" ? 6 : h.record;
+        const size_t expansion = h.data == "binary_compressed" ? 264 : 1;
+        const size_t fit = per_point ? (remaining / per_point + 1) * expansion : 0;
+        if (h.points > fit) return path + ": POINTS (" + std::to_string(h.points) + ") exceeds what the file can hold";
+    }
     xyz.reserve(3 * h.points);
     if (h.data == "ascii") {
         std::string line;
@@ -186,6 +203,8 @@ std::string read_pcd_xyz(const std::string& path, std::vector<float>& xyz, size_
         uint32_t csize = 0, usize = 0;
         if (std::fread(&csize, 4, 1, f.get()) != 1 || std::fread(&usize, 4, 1, f.get()) != 1) return path + ": compressed sizes missing";
         if (static_cast<size_t>(usize) != h.points * h.record) return path + ": uncompressed size does not match POINTS x record size";
+        // (record <= 64 KiB and POINTS <= 2^32: the product above cannot wrap, and every field's plane
+        //  [points * offset, points * (offset + size * count)) lies inside the usize bytes)
         std::vector<unsigned char> cbuf(csize), ubuf(usize);
         if (csize && std::fread(cbuf.data(), 1, csize, f.get()) != csize) return path + ": compressed data truncated";
         if (!lzf_decompress(cbuf.data(), csize, ubuf.data(), usize)) return path + ": corrupt LZF stream";
