@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstddef>
@@ -186,7 +187,7 @@ struct elm_registration {
     uint4* d_memo = nullptr;   // warm start of the next iteration's search
     uint32_t* d_ncand = nullptr;
     float4* d_cand = nullptr;  // per-query candidate lists of the warm search (icp_device.cuh)
-    uint32_t* d_cidx = nullptr;
+    uint32_t* d_refresh = nullptr;  // work list of the warm refresh kernel: match_cap entries (a segment per tile) + match_cap / 256 counts
     int cand_cap = 32;
     size_t match_cap = 0;
     int warm = 1;              // P2P / GICP: iterations after the first start their search from the previous match (same result)
@@ -244,7 +245,7 @@ struct elm_registration {
     elm::PeerComm peer{};          // peer.world > 0: the accumulate kernel's last block all-reduces over the ranks itself
     void* peer_opened[elm::kMaxPeers] = {};
     bool sharded() const { return comm != nullptr || peer.world > 0; }
-    elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, match_cap, d_ncand, d_cand, d_cidx, cand_cap, d_partials, d_ticket}; }
+    elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, match_cap, d_ncand, d_cand, cand_cap, d_refresh, d_refresh ? d_refresh + match_cap : nullptr, d_partials, d_ticket}; }
     double warm_margin_vox = 0.08;  // refresh margin of the warm search in voxel sizes
 
     ~elm_registration() {
@@ -255,7 +256,7 @@ struct elm_registration {
         for (void* p : peer_opened) if (p) cudaIpcCloseMemHandle(p);
         cudaFree(d_mailbox);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_win); cudaFree(d_memo); cudaFree(d_ncand); cudaFree(d_cand); cudaFree(d_cidx); cudaFree(d_ticket);
+        cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_win); cudaFree(d_memo); cudaFree(d_ncand); cudaFree(d_cand); cudaFree(d_refresh); cudaFree(d_ticket);
         cudaFree(d_stats);
         cudaFree(d_dtable); cudaFreeHost(h_dtable); cudaFree(d_dsk_in); cudaFree(d_dsk_out);
         cudaFree(d_sorted); cudaFree(d_orig); cudaFree(d_bin); cudaFree(d_hist); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
@@ -302,8 +303,8 @@ int ensure_partials(elm_registration* r, int rows) {
 
 int ensure_match(elm_registration* r, size_t n) {
     if (n > r->match_cap) {
-        cudaFree(r->d_match); cudaFree(r->d_win); cudaFree(r->d_memo); cudaFree(r->d_ncand); cudaFree(r->d_cand); cudaFree(r->d_cidx);
-        r->d_match = nullptr; r->d_win = nullptr; r->d_memo = nullptr; r->d_ncand = nullptr; r->d_cand = nullptr; r->d_cidx = nullptr;
+        cudaFree(r->d_match); cudaFree(r->d_win); cudaFree(r->d_memo); cudaFree(r->d_ncand); cudaFree(r->d_cand); cudaFree(r->d_refresh);
+        r->d_match = nullptr; r->d_win = nullptr; r->d_memo = nullptr; r->d_ncand = nullptr; r->d_cand = nullptr; r->d_refresh = nullptr;
         r->match_cap = 0;
         const size_t cap = (n + 1023) / 1024 * 1024;
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_match), cap * sizeof(int)));
@@ -311,7 +312,7 @@ int ensure_match(elm_registration* r, size_t n) {
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_memo), 2 * cap * sizeof(uint4)));
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_ncand), cap * sizeof(uint32_t)));
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_cand), static_cast<size_t>(r->cand_cap) * cap * sizeof(float4)));
-        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_cidx), static_cast<size_t>(r->cand_cap) * cap * sizeof(uint32_t)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_refresh), (cap + cap / 256 + 1) * sizeof(uint32_t)));
         r->match_cap = cap;
     }
     return ELM_OK;
@@ -382,8 +383,8 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // P2P / GICP: search, linearisation, reduction and solve are ONE kernel (unless the search runs on the binned copy,
     // whose order differs from the caller's: then the accumulation stays a separate launch in the caller's order)
     const bool fuse = r->fuse && prm0.method <= ELM_GICP && !(r->use_sorted && !r->sorted_all);
-    const int wgrid = elm::icp_warm_grid(prm0, r->num_sms);
-    int rc = ensure_partials(r, fuse ? (sgrid > wgrid ? sgrid : wgrid) : agrid);
+    const int wgrid = elm::icp_warm_grid(prm0, r->num_sms), rgrid = elm::icp_warm_refresh_grid(prm0, r->num_sms);
+    int rc = ensure_partials(r, std::max(std::max(sgrid, agrid), wgrid + rgrid));
     if (rc) return rc;
     rc = ensure_match(r, prm0.n);
     if (rc) return rc;
@@ -404,16 +405,25 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     if (fuse && !r->keep_match && prm.method == ELM_P2P) wk.match = nullptr;  // (GICP's accumulation reads the covariance record by index)
     if (r->use_sorted && r->sorted_all) d_scan = r->d_sorted;  // the whole iteration runs on the binned copy
     const bool mapped = r->use_sorted && !r->sorted_all;       // search in binned order, outputs under the caller's index
-    if (prm.method != ELM_AVGICP) {
-        const bool use_warm = warm && r->warm && r->prune && !mapped && prm.method <= ELM_GICP;
-        ELM_CUDA(elm::launch_icp_search(map->view(), mapped ? r->d_sorted : d_scan, mapped ? r->d_orig : nullptr, prm, r->d_state,
-                                        wk, sgrid, r->prune, fuse ? 1 : 0, use_warm ? elm::icp_warm_grid(prm, r->num_sms) : 0, solve_here, r->stream));
-        r->launches += 1;
-    }
-    if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
-    if (!fuse) {
-        ELM_CUDA(elm::launch_icp_accumulate(map->view(), d_scan, prm, r->d_state, wk, solve_here, agrid, r->stream));
-        r->launches += 1;
+    // P2P / GICP from the second iteration of a call on: the warm pair of kernels (reuse: search + linearisation of the
+    // queries whose candidate lists still hold; refresh: the rest, then reduction and solve)
+    const bool use_warm = warm && r->warm && r->prune && !mapped && !fuse && prm.method <= ELM_GICP;
+    if (use_warm) {
+        ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), d_scan, prm, r->d_state, wk, wgrid, r->stream));
+        if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
+        ELM_CUDA(elm::launch_icp_warm_refresh(map->view(), d_scan, prm, r->d_state, wk, wgrid, rgrid, solve_here, r->stream));
+        r->launches += 2;
+    } else {
+        if (prm.method != ELM_AVGICP) {
+            ELM_CUDA(elm::launch_icp_search(map->view(), mapped ? r->d_sorted : d_scan, mapped ? r->d_orig : nullptr, prm, r->d_state,
+                                            wk, sgrid, r->prune, fuse ? 1 : 0, solve_here, r->stream));
+            r->launches += 1;
+        }
+        if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
+        if (!fuse) {
+            ELM_CUDA(elm::launch_icp_accumulate(map->view(), d_scan, prm, r->d_state, wk, solve_here, agrid, r->stream));
+            r->launches += 1;
+        }
     }
     if (r->profiling) {
         ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 2], r->stream));
@@ -877,11 +887,16 @@ int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, cons
             rc = enqueue_binning(reg, map, reg->d_scan, n, T, method);
             if (rc) return rc;
         }
-        if (method != ELM_AVGICP) {
-            const bool warm = k > 0 && reg->warm && reg->prune && !reg->use_sorted && method <= ELM_GICP;
+        const bool warm = k > 0 && reg->warm && reg->prune && !reg->use_sorted && method <= ELM_GICP;
+        if (warm) {
+            const int wgrid = elm::icp_warm_grid(prm, reg->num_sms), rgrid = elm::icp_warm_refresh_grid(prm, reg->num_sms);
+            rc = ensure_partials(reg, wgrid + rgrid);
+            if (rc) return rc;
+            ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), reg->d_scan, prm, reg->d_state, reg->work(), wgrid, reg->stream));
+            ELM_CUDA(elm::launch_icp_warm_refresh(map->view(), reg->d_scan, prm, reg->d_state, reg->work(), wgrid, rgrid, 0, reg->stream));
+        } else if (method != ELM_AVGICP) {
             ELM_CUDA(elm::launch_icp_search(map->view(), reg->use_sorted ? reg->d_sorted : reg->d_scan, reg->use_sorted ? reg->d_orig : nullptr, prm,
-                                            reg->d_state, reg->work(), elm::icp_search_grid(prm, reg->num_sms), reg->prune, 0,
-                                            warm ? elm::icp_warm_grid(prm, reg->num_sms) : 0, 0, reg->stream));
+                                            reg->d_state, reg->work(), elm::icp_search_grid(prm, reg->num_sms), reg->prune, 0, 0, reg->stream));
         }
     }
     ELM_CUDA(elm::launch_icp_export(map->view(), reg->d_scan, reg->d_match, static_cast<int>(n), reg->d_state, method,

@@ -78,7 +78,7 @@ struct IcpParams {
 // Per-registration device scratch of the ICP loop (owned by elm_registration, sized for the largest scan seen).
 struct IcpWork {
     int* match;             // [n] device index of the matched map point (P2P/GICP) / voxel slot (VGICP); -1 = none
-    float4* win;            // [n] P2P/GICP: the matched map point itself {x, y, z, bits of its canonical rank}; none ->
+    float4* win;            // [n] P2P/GICP: the matched map point itself {x, y, z, bits of its device index}; none ->
                             //     {0, 0, 0, 0xffffffff} = the reference's default-constructed neighbour at the origin (Q2), so the
                             //     accumulation STREAMS its targets instead of gathering pts[match[i]]
     uint4* memo;            // warm start of the next iteration's search, two planes of memo_stride elements:
@@ -88,8 +88,11 @@ struct IcpWork {
     uint32_t* ncand;        // [n] length of the query's candidate list; ~0: unusable
     float4* cand;           // candidate j of query i at cand[(i / 256) * cand_cap * 256 + j * 256 + i % 256] (tile-interleaved: the lists
                             // of 256 consecutive queries form one block, candidate-major inside): a COPY of the stored point
-    uint32_t* cidx;         // same layout: its device index in the map's point array
+                            // {x, y, z, bits of its device index}
     int cand_cap;
+    uint32_t* refresh_list;   // queries the reuse kernel of a warm iteration hands to its refresh kernel: one segment of 256 entries
+                              // per tile of 256 queries, filled in thread order
+    uint32_t* refresh_count;  // [tiles] entries used in each segment
     double* partials;       // [blocks][kAcc] per-block sums of one linearisation
     unsigned int* ticket;   // blocks finished
 };

@@ -724,19 +724,26 @@ __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc
 #endif
 // Publish this block's sums and let the LAST block to arrive reduce all partials in a fixed order (bit-reproducible
 // whichever block is last) into st->acc and, when `solve_here`, run the solve/update step.
-__device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)[kAcc], double* s_acc, bool* s_last, SolveScratch* s_solve,
-                                            const double* s_T, IcpState* st, const IcpParams& prm, double* __restrict__ partials,
-                                            unsigned int* __restrict__ ticket, int solve_here) {
+// row0 / nrows / first_row: this grid's blocks write the rows row0 .. row0 + gridDim.x - 1 of `partials`, and the last block
+// sums the rows first_row .. first_row + nrows - 1 (default: this grid's own rows).
+// (the scan size n_total travels in the row of the grid's first block)
+__device__ __forceinline__ void publish_partials(const double* s_sum, const IcpParams& prm, double* __restrict__ partials, int row) {
     const int tid = threadIdx.x;
-#ifdef ELM_PHASE_TIMING
-    long long atick = clock64();
-#endif
     if (tid < kAcc) {
         double v = 0.0;
         if (tid < 29) v = s_sum[tid];
         else if (tid == kIdxNtotal) v = (blockIdx.x == 0) ? static_cast<double>(prm.n) : 0.0;
-        partials[blockIdx.x * kAcc + tid] = v;
+        partials[static_cast<size_t>(row) * kAcc + tid] = v;
     }
+}
+__device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)[kAcc], double* s_acc, bool* s_last, SolveScratch* s_solve,
+                                            const double* s_T, IcpState* st, const IcpParams& prm, double* __restrict__ partials,
+                                            unsigned int* __restrict__ ticket, int solve_here, int row0 = 0, int nrows = -1, int first_row = 0) {
+    const int tid = threadIdx.x;
+#ifdef ELM_PHASE_TIMING
+    long long atick = clock64();
+#endif
+    publish_partials(s_sum, prm, partials, row0 + static_cast<int>(blockIdx.x));
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -750,7 +757,8 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
     {
         const int k = tid & 31, g = tid >> 5;
         double v = 0.0;
-        const int nb = static_cast<int>(gridDim.x);
+        const int nb = nrows >= 0 ? nrows : static_cast<int>(gridDim.x);
+        const double* const rows = partials + static_cast<size_t>(nrows >= 0 ? first_row : row0) * kAcc;
         // 16 loads in flight per thread, summed in index order; rows past the end contribute +0.0 (the tail used to be one
         // dependent load per row: 9 round trips for 296 rows instead of 3)
         constexpr int kDepth = 16;
@@ -759,7 +767,7 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
 #pragma unroll
             for (int u = 0; u < kDepth; ++u) {
                 const int row = b + u * kIcpWarps;
-                t[u] = (row < nb) ? __ldcg(partials + static_cast<size_t>(row) * kAcc + k) : 0.0;
+                t[u] = (row < nb) ? __ldcg(rows + static_cast<size_t>(row) * kAcc + k) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < kDepth; ++u) v += t[u];
@@ -1107,7 +1115,7 @@ icp_search_points_kernel(MapView map, const float* __restrict__ scan, const int*
         // warm start of the next iteration's search
         float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
         if (mine) {
-            if (my_match >= 0) wpt = __ldg(map.pts + my_match);
+            if (my_match >= 0) { wpt = __ldg(map.pts + my_match); wpt.w = __uint_as_float(static_cast<uint32_t>(my_match)); }
             const size_t gi = static_cast<size_t>(tile) * tile_pts + tid;
             const size_t oi = orig ? static_cast<size_t>(orig[gi]) : gi;
             if (match) match[oi] = my_match;
@@ -1252,9 +1260,9 @@ __device__ __forceinline__ void octant_runs(const MapView& map, int row, int kx,
 #endif
 // REFRESH of one query (a query that changed its voxel, used up its margin, or has no usable list yet): look the row up
 // again if the key changed, search the octants within R = d + margin exactly, and copy every stored point in them into the
-// query's candidate list.  Kept out of line: the REUSE path — nearly every query of nearly every iteration — must not
-// pay for this path's registers (with both inlined the kernel spilled 232 bytes per thread = 58 MB of local-memory
-// stores per launch).
+// query's candidate list.  Lives in the refresh kernel: the REUSE path — nearly every query of nearly every iteration —
+// must not pay for this path's registers (with both in one kernel it spilled 232 bytes per thread = 58 MB of
+// local-memory stores per launch) nor wait for its stragglers.
 struct WarmRefresh {
     Best b;           // the exact nearest neighbour (none: idx == kNone)
     float4 wpt;       // the matched point itself
@@ -1262,15 +1270,8 @@ struct WarmRefresh {
     uint32_t n_new;   // length of the new candidate list; kNone: unusable
     float Rf;         // every point of the 27 voxels within Rf of the query's fp32 rounding is in the list
 };
-// (The map and the work buffers arrive as scalars: a reference to a kernel-parameter struct would make the compiler copy
-// the whole struct to local memory in every thread.)
-template <int FUSE>
-__device__ __noinline__ void warm_refresh(const uint4* dslots, const uint32_t* drows, const float4* pts, uint32_t bmask, double voxel_size,
-                                          double inv_voxel_size, float4* out_cand, uint32_t* out_cidx, uint32_t ccap, double warm_margin, uint4 m0,
-                                          float4 prev, bool same_key, double px, double py, double pz, WarmRefresh* out) {
-    MapView map;
-    map.dslots = dslots; map.drows = drows; map.pts = pts; map.bmask = bmask; map.voxel_size = voxel_size; map.inv_voxel_size = inv_voxel_size;
-    map.prec = nullptr; map.vslots = nullptr; map.vcov = nullptr; map.vcand = nullptr; map.dir7 = nullptr; map.mask = 0;
+__device__ __forceinline__ void warm_refresh(const MapView& map, float4* out_cand, uint32_t ccap, double warm_margin, uint4 m0, float4 prev,
+                                             bool same_key, double px, double py, double pz, WarmRefresh* out) {
     const float kInf = __int_as_float(0x7f800000);
     const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
     constexpr size_t cstride = kIcpThreads;
@@ -1296,7 +1297,7 @@ __device__ __noinline__ void warm_refresh(const uint4* dslots, const uint32_t* d
         float bound = kInf;
         if (prev_ok) {
             b.d2 = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
-            b.idx = m0.w; b.rank = __float_as_uint(prev.w);
+            b.idx = m0.w; b.rank = __float_as_uint(__ldg(map.pts + m0.w).w);
             R = (sqrt(b.d2) + warm_margin) * (1.0 + 1e-9);
             bound = __double2float_ru(R * R) * inv_vs2_up;
             n_new = 0;  // (the points within a finite bound are worth remembering)
@@ -1310,13 +1311,12 @@ __device__ __noinline__ void warm_refresh(const uint4* dslots, const uint32_t* d
                 const float4 c = __ldg(map.pts + p);  // (just read by visit_points: L1)
                 if (sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz) <= R2) {
                     if (n_new >= ccap) { n_new = kNone; break; }  // does not fit: no list
-                    out_cand[static_cast<size_t>(n_new) * cstride] = c;
-                    out_cidx[static_cast<size_t>(n_new) * cstride] = p;
+                    out_cand[static_cast<size_t>(n_new) * cstride] = make_float4(c.x, c.y, c.z, __uint_as_float(p));
                     ++n_new;
                 }
             }
         });
-        if (b.idx != kNone) wpt = __ldg(map.pts + b.idx);
+        if (b.idx != kNone) { wpt = __ldg(map.pts + b.idx); wpt.w = __uint_as_float(b.idx); }
     }
     // what the list is good for: every point of the 27 voxels within R of the query; the memo keeps the query rounded to fp32
     // (q0), so R shrinks by that rounding
@@ -1332,32 +1332,27 @@ __device__ __noinline__ void warm_refresh(const uint4* dslots, const uint32_t* d
 // query's bound and masks (same inputs, same results), lanes 0..8 take one z-column each (record + runs), the points of all
 // runs are then spread over the lanes, and the results meet in shuffles.  Same arithmetic as warm_refresh.
 // q = the owner's lane; every lane passes ITS OWN values, the owner's are broadcast.  s_run: 64 words of the warp.
-struct WarmQuery { double px, py, pz; uint4 m0; float4 prev; bool same_key; size_t cbase; };
 __device__ __forceinline__ double shfl_double(double v, int src) {
     const long long b = __double_as_longlong(v);
     const int lo = __shfl_sync(kFull, static_cast<int>(b), src), hi = __shfl_sync(kFull, static_cast<int>(b >> 32), src);
     return __longlong_as_double((static_cast<long long>(hi) << 32) | static_cast<unsigned int>(lo));
 }
-template <int FUSE>
-__device__ __noinline__ void warm_refresh_warp(const uint4* dslots, const uint32_t* drows, const float4* pts, uint32_t bmask, double voxel_size,
-                                               double inv_voxel_size, float4* cand, uint32_t* cidx, uint32_t ccap, double warm_margin, int q,
-                                               const WarmQuery* mine, unsigned int* s_run, WarmRefresh* out) {
-    MapView map;
-    map.dslots = dslots; map.drows = drows; map.pts = pts; map.bmask = bmask; map.voxel_size = voxel_size; map.inv_voxel_size = inv_voxel_size;
-    map.prec = nullptr; map.vslots = nullptr; map.vcov = nullptr; map.vcand = nullptr; map.dir7 = nullptr; map.mask = 0;
+__device__ __forceinline__ void warm_refresh_warp(const MapView& map, float4* cand, uint32_t ccap, double warm_margin, int q, double my_px, double my_py,
+                                                  double my_pz, uint4 my_m0, float4 my_prev, bool my_same_key, size_t my_cbase, unsigned int* s_run,
+                                                  WarmRefresh* out) {
     const int lane = threadIdx.x & 31;
     const float kInf = __int_as_float(0x7f800000);
     const float inv_vs2_up = static_cast<float>(1.0 / (map.voxel_size * map.voxel_size)) * 1.00001f;
     constexpr size_t cstride = kIcpThreads;
     // the owner's query, in every lane
-    const double px = shfl_double(mine->px, q), py = shfl_double(mine->py, q), pz = shfl_double(mine->pz, q);
+    const double px = shfl_double(my_px, q), py = shfl_double(my_py, q), pz = shfl_double(my_pz, q);
     uint4 m0; float4 prev;
-    m0.x = __shfl_sync(kFull, mine->m0.x, q); m0.y = __shfl_sync(kFull, mine->m0.y, q); m0.z = __shfl_sync(kFull, mine->m0.z, q); m0.w = __shfl_sync(kFull, mine->m0.w, q);
-    prev.x = __shfl_sync(kFull, mine->prev.x, q); prev.y = __shfl_sync(kFull, mine->prev.y, q); prev.z = __shfl_sync(kFull, mine->prev.z, q);
-    prev.w = __shfl_sync(kFull, mine->prev.w, q);
-    const bool same_key = __shfl_sync(kFull, mine->same_key ? 1 : 0, q) != 0;
-    const size_t cbase = (static_cast<size_t>(__shfl_sync(kFull, static_cast<unsigned int>(mine->cbase >> 32), q)) << 32) |
-                         __shfl_sync(kFull, static_cast<unsigned int>(mine->cbase), q);
+    m0.x = __shfl_sync(kFull, my_m0.x, q); m0.y = __shfl_sync(kFull, my_m0.y, q); m0.z = __shfl_sync(kFull, my_m0.z, q); m0.w = __shfl_sync(kFull, my_m0.w, q);
+    prev.x = __shfl_sync(kFull, my_prev.x, q); prev.y = __shfl_sync(kFull, my_prev.y, q); prev.z = __shfl_sync(kFull, my_prev.z, q);
+    prev.w = __shfl_sync(kFull, my_prev.w, q);
+    const bool same_key = __shfl_sync(kFull, my_same_key ? 1 : 0, q) != 0;
+    const size_t cbase = (static_cast<size_t>(__shfl_sync(kFull, static_cast<unsigned int>(my_cbase >> 32), q)) << 32) |
+                         __shfl_sync(kFull, static_cast<unsigned int>(my_cbase), q);
     float fx, fy, fz;
     const int kx = voxel_floor(px, map, &fx), ky = voxel_floor(py, map, &fy), kz = voxel_floor(pz, map, &fz);
     int row;
@@ -1380,7 +1375,7 @@ __device__ __noinline__ void warm_refresh_warp(const uint4* dslots, const uint32
         float bound = kInf;
         if (prev_ok) {
             b.d2 = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
-            b.idx = m0.w; b.rank = __float_as_uint(prev.w);
+            b.idx = m0.w; b.rank = __float_as_uint(__ldg(map.pts + m0.w).w);
             R = (sqrt(b.d2) + warm_margin) * (1.0 + 1e-9);
             bound = __double2float_ru(R * R) * inv_vs2_up;
             n_new = 0;
@@ -1438,8 +1433,7 @@ __device__ __noinline__ void warm_refresh_warp(const uint4* dslots, const uint32
                 else {
                     if (within) {
                         const uint32_t pos = n_new + __popc(wmask & ((1u << lane) - 1u));
-                        cand[cbase + static_cast<size_t>(pos) * cstride] = c;
-                        cidx[cbase + static_cast<size_t>(pos) * cstride] = p;
+                        cand[cbase + static_cast<size_t>(pos) * cstride] = make_float4(c.x, c.y, c.z, __uint_as_float(p));
                     }
                     n_new += cnt;
                 }
@@ -1461,7 +1455,10 @@ __device__ __noinline__ void warm_refresh_warp(const uint4* dslots, const uint32
             const bool ohave = __shfl_xor_sync(kFull, have_pt ? 1 : 0, o) != 0;
             if (ob.idx != kNone && (closer(ob.d2, ob.rank, b) || (ob.idx == b.idx && ohave && !have_pt))) { b = ob; lpt = opt; have_pt = ohave; }
         }
-        if (b.idx != kNone) wpt = have_pt ? lpt : __ldg(map.pts + b.idx);  // (the previous match won: its coordinates are not in a lane)
+        if (b.idx != kNone) {
+            wpt = have_pt ? lpt : __ldg(map.pts + b.idx);  // (the previous match won: its coordinates are not in a lane)
+            wpt.w = __uint_as_float(b.idx);
+        }
     }
     const double ex = px - static_cast<double>(static_cast<float>(px)), ey = py - static_cast<double>(static_cast<float>(py)),
                  ez = pz - static_cast<double>(static_cast<float>(pz));
@@ -1471,26 +1468,30 @@ __device__ __noinline__ void warm_refresh_warp(const uint4* dslots, const uint32
     }
 }
 
-// One thread per query, and as few instructions per query as the arithmetic allows: the kernel is a single wave of warps
-// (131 072 queries = 27.7 warps per SM), so its duration is the length of one warp's instruction stream.
-template <int FUSE>
-__global__ void __launch_bounds__(kIcpThreads, FUSE == 1 ? 3 : 4)
-icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int solve_here) {
-    constexpr bool kFuse = FUSE >= 0;
-    constexpr int NACC = AccSize<FUSE == 0 ? 0 : 1>::value;
-    __shared__ double s_Tinv[kFuse ? 12 : 1], s_Rinv[kFuse ? 9 : 1];
-    __shared__ double s_red[kFuse ? kIcpWarps : 1][kAcc], s_sum[kAcc], s_acc[kAcc];
-    __shared__ SolveScratch s_solve;
-    __shared__ bool s_last;
-    __shared__ double s_T[12];
-    __shared__ unsigned int s_run[kIcpWarps][64];  // warm_refresh_warp: the runs of the query the warp refreshes together
+// A warm iteration is TWO launches:
+//   icp_warm_reuse_kernel    one thread per query, nothing but the REUSE path: memo, transform, test, stream the candidate
+//                            list, decide, linearise the correspondence (AlignCloudsLocal / ...PointCov accumulation fused:
+//                            the matched point is in registers), block tree -> one row of partial sums per block.  A query
+//                            that cannot reuse appends itself to a work list and contributes nothing here.  No call, no
+//                            straggler: the kernel is one wave of warps and lasts as long as one warp's instruction stream.
+//   icp_warm_refresh_kernel  the work list: a handful of queries per iteration in a converging loop (one warp per query,
+//                            warm_refresh_warp), all of them in the first warm iteration of a call (one thread per query,
+//                            warm_refresh); their correspondences are linearised here, and the LAST block sums the rows of
+//                            both kernels in a fixed order, all-reduces over the ranks (multi-GPU) and solves.
+template <int METHOD>
+__global__ void __launch_bounds__(kIcpThreads, 4)
+icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, IcpWork wk) {
+    constexpr int NACC = AccSize<METHOD>::value;
+    __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
+    __shared__ double s_red[kIcpWarps][kAcc], s_sum[kAcc];
+    __shared__ int s_done;
+    __shared__ unsigned int s_wcnt[kIcpWarps];
 
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31;
     const float kInf = __int_as_float(0x7f800000);
     uint4* const memo0 = wk.memo;                   // {row, key_lo, key_hi, index of the match}
     uint4* const memo1 = wk.memo + wk.memo_stride;  // {q0.x, q0.y, q0.z, R} as floats: the list holds every point of the 27 voxels within R of q0
-    uint32_t* const ncand = wk.ncand;               // length of the candidate list; kNone: unusable
     const uint32_t ccap = static_cast<uint32_t>(wk.cand_cap);
     uint32_t visited = 0, searched = 0, refreshed = 0;
     // the scan is never written inside the loop: this thread's first point may be read before the previous kernel has finished
@@ -1498,50 +1499,40 @@ icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams pr
     float sxf = 0.f, syf = 0.f, szf = 0.f;
     if (gi < prm.n) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
     pdl_wait();
-    if (st->done) return;
-    if (tid < 12) s_T[tid] = st->T[tid];
-    if (kFuse) {
-        if (tid < 12) s_Tinv[tid] = st->Tinv[tid];
-        if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
-        if (tid < kAcc) s_sum[tid] = 0.0;
-    }
+    // the first query's memo is requested BEFORE the pose is staged in shared memory: both loads share one round trip
+    uint4 m0 = make_uint4(kNone, kNone, kNone, kNone), m1 = make_uint4(0, 0, 0, 0);
+    uint32_t nc = kNone;
+    float4 prev = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
+    if (gi < prm.n) { m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi]; }
+    if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
+    if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+    if (tid < kAcc) s_sum[tid] = 0.0;
+    if (tid == 0) s_done = st->done;
     __syncthreads();
+    if (s_done) return;  // loop already left (termination / overlap failure)
     for (bool first = true; gi - tid < prm.n; gi += gridDim.x * kIcpThreads, first = false) {
-#ifdef ELM_PHASE_TIMING
-        long long wtick = clock64();
-        if (prm.stats && lane == 0) atomicAdd(prm.stats + 22, 1ull);
-#endif
         const bool mine = gi < prm.n;
-        double px = 0, py = 0, pz = 0, sx = 0, sy = 0, sz = 0;
-        Best b;
-        float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));  // the matched point itself
-        int row = -1;
-        uint32_t qkey_lo = kNone, qkey_hi = kNone;
+        double acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
         bool refresh = false;
-        WarmQuery wq;
-        wq.px = wq.py = wq.pz = 0.0; wq.m0 = make_uint4(kNone, kNone, kNone, kNone); wq.prev = wpt; wq.same_key = false; wq.cbase = 0;
         if (mine) {
+            if (!first) {
+                m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi];
+                sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2];
+            }
             // candidate j of this query: tile-interleaved (icp_device.cuh) — the 256 queries of a tile keep their lists in one
             // contiguous block, candidate-major inside it, so a warp reads 512 consecutive bytes per candidate
-            const size_t cbase = static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
-            const float4* const my_cand = wk.cand + cbase;
-            const uint32_t* const my_cidx = wk.cidx + cbase;
+            const float4* const my_cand = wk.cand + static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
             constexpr size_t cstride = kIcpThreads;
-            const uint4 m0 = memo0[gi], m1 = memo1[gi];
-            const uint32_t nc = ncand[gi];
-            const float4 prev = wk.win[gi];
-            if (!first) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
-            sx = sxf; sy = syf; sz = szf;
-            px = row_apply_exact(s_T, 0, sx, sy, sz);
-            py = row_apply_exact(s_T, 1, sx, sy, sz);
-            pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            const double sx = sxf, sy = syf, sz = szf;
+            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
             const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
             ++searched;
+            uint32_t qkey_lo = kNone, qkey_hi = kNone;
             const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
             if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
             const bool same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
-            ELM_USE(same_key && prev.x == 1e30f);
-            ELM_WTICK(23);
             // REUSE: same key and  d' + |q - q0| <= R  with d' = distance to the previous match (each side rounded against us)
             bool reuse = false;
             if (same_key && m0.w != kNone && nc <= ccap) {
@@ -1552,8 +1543,10 @@ icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams pr
                 const float room = (__uint_as_float(m1.w) - delta) * 0.999999f;  // what is left of R for d'
                 reuse = room > 0.f && d2_prev <= static_cast<double>(room) * static_cast<double>(room);
             }
+            int my_match = -1;
+            float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));  // the matched point {x, y, z, index}
+            bool decided = true;
             if (reuse) {
-                row = static_cast<int>(m0.x);
                 // one fp32 pass over the list (coalesced: candidate j of the warp's queries is 512 consecutive bytes), four loads
                 // in flight, then ONE decision (the band of visit_points): the fp32 argmin is the unique exact winner, or (a near
                 // tie) the list is decided again exactly
@@ -1573,71 +1566,48 @@ icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams pr
                     }
                 }
                 visited += nc;
-                ELM_USE(m < 0.f);
-                ELM_WTICK(24);
                 const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);
                 const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
-                if (s2 > T) {
+                if (s2 > T) {  // (the exact distance of the unique winner is not needed: nothing is left to compare it with)
                     wpt = my_cand[static_cast<size_t>(mj) * cstride];
-                    b.d2 = sq3_exact(static_cast<double>(wpt.x) - px, static_cast<double>(wpt.y) - py, static_cast<double>(wpt.z) - pz);
-                    b.rank = __float_as_uint(wpt.w);
-                } else {  // near tie (or an empty list): every candidate exactly, smallest rank among equals
+                } else {       // near tie (or an empty list): every candidate exactly, smallest rank (read from the map) among equals
+                    Best b;
                     for (uint32_t j = 0; j < nc; ++j) {
                         const float4 c = my_cand[static_cast<size_t>(j) * cstride];
                         const double d2 = sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz);
-                        if (closer(d2, __float_as_uint(c.w), b)) { b.d2 = d2; b.rank = __float_as_uint(c.w); b.idx = j; wpt = c; }
+                        const uint32_t rank = __float_as_uint(__ldg(map.pts + __float_as_uint(c.w)).w);
+                        if (closer(d2, rank, b)) { b.d2 = d2; b.rank = rank; b.idx = __float_as_uint(c.w); wpt = c; }
                     }
-                    mj = b.idx;
                 }
-                b.idx = nc ? my_cidx[static_cast<size_t>(mj) * cstride] : kNone;
+                my_match = static_cast<int>(__float_as_uint(wpt.w));  // (kNone = -1: an empty list)
             } else if (same_key && static_cast<int>(m0.x) < 0) {
-                // same voxel as last time and its 27-neighbourhood holds no point: still nothing to find (Q2 applies downstream)
+                // same voxel as last time and its 27-neighbourhood holds no point: still nothing to find (Q2 applies below)
             } else {
-                // REFRESH: a query that changed its voxel, used up its margin, or has no usable list (first warm iteration)
+                decided = false;  // REFRESH: the next kernel searches this query
                 refresh = true;
                 ++refreshed;
-#ifdef ELM_PHASE_TIMING
-                if (prm.stats) atomicAdd(prm.stats + (!same_key ? 30 : (m0.w == kNone ? 31 : (nc > ccap ? 28 : 29))), 1ull);
-#endif
-                wq.m0 = m0; wq.prev = prev; wq.same_key = same_key; wq.cbase = cbase;
             }
-            wq.px = px; wq.py = py; wq.pz = pz;
+            if (decided) {
+                if (wk.match) wk.match[gi] = my_match;
+                wk.win[gi] = wpt;
+                memo0[gi] = make_uint4(m0.x, qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+                linearize_point_pair<METHOD>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+            }
         }
-        // a few stragglers: the whole warp refreshes them one after the other; many (the first warm iteration): every thread its own
+        // the work list of the refresh kernel: one segment per tile, filled in thread order (no atomics: the refresh kernel's
+        // summation order, hence every bit of the result, is the same from run to run)
         const uint32_t rmask = __ballot_sync(kFull, refresh);
-        if (rmask) {
-            WarmRefresh r;
-            if (__popc(rmask) <= 6) {
-                for (uint32_t left = rmask; left; left &= left - 1)
-                    warm_refresh_warp<FUSE>(map.dslots, map.drows, map.pts, map.bmask, map.voxel_size, map.inv_voxel_size, wk.cand, wk.cidx, ccap,
-                                            prm.warm_margin, __ffs(left) - 1, &wq, s_run[tid >> 5], &r);
-            } else if (refresh) {
-                warm_refresh<FUSE>(map.dslots, map.drows, map.pts, map.bmask, map.voxel_size, map.inv_voxel_size, wk.cand + wq.cbase, wk.cidx + wq.cbase, ccap,
-                                   prm.warm_margin, wq.m0, wq.prev, wq.same_key, px, py, pz, &r);
-            }
-            if (refresh) {
-                b = r.b; wpt = r.wpt; row = r.row;
-                memo1[gi] = make_uint4(__float_as_uint(static_cast<float>(px)), __float_as_uint(static_cast<float>(py)), __float_as_uint(static_cast<float>(pz)),
-                                       __float_as_uint(r.Rf));
-                ncand[gi] = r.n_new;
-            }
-        }
-        ELM_USE(b.d2 < 0.0);
-        ELM_WTICK(25);
-        int my_match = -1;
-        if (mine) {
-            if (b.idx != kNone) my_match = static_cast<int>(b.idx);
-            if (wk.match) wk.match[gi] = my_match;
-            wk.win[gi] = wpt;
-            memo0[gi] = make_uint4(static_cast<uint32_t>(row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
-        }
-        if (kFuse) {
-            double acc[NACC];
+        if (lane == 0) s_wcnt[tid >> 5] = __popc(rmask);
+        block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);  // (two block barriers: s_wcnt is complete afterwards)
+        {
+            const int tile = (gi - tid) / kIcpThreads;
+            uint32_t base = 0, total = 0;
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-            if (mine) linearize_point_pair<FUSE == 1 ? 1 : 0>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
-            block_sum_into<NACC, FUSE == 0>(acc, s_red, s_sum);
+            for (int w = 0; w < kIcpWarps; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; total += s_wcnt[w]; }
+            if (refresh) wk.refresh_list[static_cast<size_t>(tile) * kIcpThreads + base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<uint32_t>(gi);
+            if (tid == 0) wk.refresh_count[tile] = total;
         }
+        __syncthreads();  // (s_wcnt is rewritten by the next tile)
     }
     if (prm.stats) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -1650,7 +1620,89 @@ icp_search_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams pr
             atomicAdd(prm.stats + 21, static_cast<unsigned long long>(searched));   // warm searches
         }
     }
-    if (kFuse) finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here);
+    publish_partials(s_sum, prm, wk.partials, static_cast<int>(blockIdx.x));
+}
+
+// rows_before = rows of `partials` the reuse kernel published (its grid size)
+template <int METHOD>
+__global__ void __launch_bounds__(kIcpThreads, 2)
+icp_warm_refresh_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int rows_before, int solve_here) {
+    constexpr int NACC = AccSize<METHOD>::value;
+    __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
+    __shared__ double s_red[kIcpWarps][kAcc], s_sum[kAcc], s_acc[kAcc];
+    __shared__ SolveScratch s_solve;
+    __shared__ bool s_last;
+    __shared__ unsigned int s_run[kIcpWarps][64];
+    pdl_launch_dependents();
+    pdl_wait();
+    if (st->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
+    if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+    if (tid < kAcc) s_sum[tid] = 0.0;
+    __syncthreads();
+    const uint32_t ccap = static_cast<uint32_t>(wk.cand_cap);
+    uint4* const memo0 = wk.memo;
+    uint4* const memo1 = wk.memo + wk.memo_stride;
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    // what one refreshed query leaves behind (executed by the thread that owns the result)
+    auto commit = [&](uint32_t gi, const WarmRefresh& r, double sx, double sy, double sz, double px, double py, double pz, uint32_t qkey_lo, uint32_t qkey_hi) {
+        const int my_match = r.b.idx != kNone ? static_cast<int>(r.b.idx) : -1;
+        if (wk.match) wk.match[gi] = my_match;
+        wk.win[gi] = r.wpt;
+        memo0[gi] = make_uint4(static_cast<uint32_t>(r.row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+        memo1[gi] = make_uint4(__float_as_uint(static_cast<float>(px)), __float_as_uint(static_cast<float>(py)), __float_as_uint(static_cast<float>(pz)), __float_as_uint(r.Rf));
+        wk.ncand[gi] = r.n_new;
+        linearize_point_pair<METHOD>(map, my_match, r.wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+    };
+    auto load_query = [&](uint32_t gi, double& sx, double& sy, double& sz, double& px, double& py, double& pz, uint4& m0, float4& prev, bool& same_key,
+                          uint32_t& qkey_lo, uint32_t& qkey_hi, size_t& cbase) {
+        sx = scan[3 * static_cast<size_t>(gi)]; sy = scan[3 * static_cast<size_t>(gi) + 1]; sz = scan[3 * static_cast<size_t>(gi) + 2];
+        px = row_apply_exact(s_T, 0, sx, sy, sz); py = row_apply_exact(s_T, 1, sx, sy, sz); pz = row_apply_exact(s_T, 2, sx, sy, sz);
+        m0 = memo0[gi]; prev = wk.win[gi];
+        const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
+        qkey_lo = qkey_hi = kNone;
+        const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
+        if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
+        same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
+        cbase = static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
+    };
+    const int ntiles = (prm.n + kIcpThreads - 1) / kIcpThreads;
+    for (int tile = static_cast<int>(blockIdx.x); tile < ntiles; tile += static_cast<int>(gridDim.x)) {
+        const uint32_t count = wk.refresh_count[tile];
+        const uint32_t* const list = wk.refresh_list + static_cast<size_t>(tile) * kIcpThreads;
+        if (count <= 2 * kIcpWarps) {
+            // a handful (a converging loop): one warp per query
+            for (uint32_t it = warp; it < count; it += kIcpWarps) {
+                const uint32_t gi = list[it];
+                double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
+                load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);  // (every lane the same query)
+                WarmRefresh r;
+                warm_refresh_warp(map, wk.cand, ccap, prm.warm_margin, 0, px, py, pz, m0, prev, same_key, cbase, s_run[warp], &r);
+                if (lane == 0) commit(gi, r, sx, sy, sz, px, py, pz, qkey_lo, qkey_hi);
+            }
+        } else if (static_cast<uint32_t>(tid) < count) {
+            // many (the first warm iteration of a call): one thread per query
+            const uint32_t gi = list[tid];
+            double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
+            load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);
+            WarmRefresh r;
+            warm_refresh(map, wk.cand + cbase, ccap, prm.warm_margin, m0, prev, same_key, px, py, pz, &r);
+            commit(gi, r, sx, sy, sz, px, py, pz, qkey_lo, qkey_hi);
+        }
+    }
+    block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);
+    // the rows of the reuse kernel are folded into this grid's rows in parallel (block b takes the rows b, b + gridDim.x, ...
+    // in that order), so that the last block's serial reduction is over gridDim.x rows, not over both grids
+    if (tid < 29) {
+        double v = s_sum[tid];
+        for (int row = static_cast<int>(blockIdx.x); row < rows_before; row += static_cast<int>(gridDim.x)) v += __ldcg(wk.partials + static_cast<size_t>(row) * kAcc + tid);
+        s_sum[tid] = v;
+    }
+    __syncthreads();
+    finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here, rows_before, -1, rows_before);
 }
 
 // ======================================================================================================================
@@ -1852,10 +1904,17 @@ icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __rest
 // developer switch: ELM_NO_PDL=1 launches every kernel fully serialised
 static const bool g_use_pdl = [] { const char* e = getenv("ELM_NO_PDL"); return !(e && e[0] == '1'); }();
 
-// blocks of the warm-started search: one query per thread, grid-stride loop beyond one resident wave
+// blocks of the warm reuse kernel: one query per thread, grid-stride loop beyond one resident wave
 int icp_warm_grid(const IcpParams& prm, int num_sms) {
     const int blocks = (prm.n + kIcpThreads - 1) / kIcpThreads;
     const int cap = 4 * num_sms;
+    return blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+}
+// blocks of the warm refresh kernel (two resident per SM): enough threads for a bulk refresh of the whole scan, not more than
+// one warp per query otherwise... a handful of queries leaves most of them idle, which costs nothing but their launch
+int icp_warm_refresh_grid(const IcpParams& prm, int num_sms) {
+    const int blocks = (prm.n + kIcpThreads - 1) / kIcpThreads;
+    const int cap = 2 * num_sms;
     return blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
 }
 
@@ -1903,16 +1962,10 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
 }
 
 // fuse: linearise + reduce (+ solve when solve_here) inside the search kernel (P2P / GICP only); then wk.match may be NULL.
-// warm: P2P / GICP — start from the previous iteration's wk.win / wk.memo (icp_search_warm_kernel); needs prune.
 cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, const IcpWork& wk,
-                              int grid, int prune, int fuse, int warm, int solve_here, cudaStream_t s) {
+                              int grid, int prune, int fuse, int solve_here, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
-    if (prm.method <= 1 && warm && prune && !orig) {
-        grid = warm;  // (the caller passes the warm grid in `warm`)
-        if (!fuse) e = launch_pdl(icp_search_warm_kernel<-1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
-        else if (prm.method == 0) e = launch_pdl(icp_search_warm_kernel<0>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
-        else e = launch_pdl(icp_search_warm_kernel<1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
-    } else if (prm.method <= 1) {
+    if (prm.method <= 1) {
 #define ELM_LAUNCH(C, F) e = launch_pdl(icp_search_points_kernel<C, F>, grid, kIcpThreads, 0, s, map, scan, orig, prm, st, wk, solve_here)
         if (!fuse) { if (prune) ELM_LAUNCH(true, -1); else ELM_LAUNCH(false, -1); }
         else if (prm.method == 0) { if (prune) ELM_LAUNCH(true, 0); else ELM_LAUNCH(false, 0); }
@@ -1921,6 +1974,21 @@ cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* 
     } else if (prm.method == 2) {
         e = launch_pdl(icp_search_means_kernel, grid, kIcpThreads, 0, s, map, scan, orig, prm, static_cast<const IcpState*>(st), wk.match);
     }
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// One warm iteration of P2P / GICP (search + linearisation + reduction + solve) = the reuse kernel, then the refresh kernel.
+cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, const IcpWork& wk, int reuse_grid,
+                                  cudaStream_t s) {
+    const cudaError_t e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
+                                          : launch_pdl(icp_warm_reuse_kernel<1>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
+                                    int refresh_grid, int solve_here, cudaStream_t s) {
+    const cudaError_t e = prm.method == 0
+                              ? launch_pdl(icp_warm_refresh_kernel<0>, refresh_grid, kIcpThreads, 0, s, map, scan, prm, st, wk, reuse_grid, solve_here)
+                              : launch_pdl(icp_warm_refresh_kernel<1>, refresh_grid, kIcpThreads, 0, s, map, scan, prm, st, wk, reuse_grid, solve_here);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

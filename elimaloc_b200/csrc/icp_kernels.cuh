@@ -18,12 +18,17 @@ cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ti
 // P2P / GICP / VGICP correspondence search -> wk.match[n] (+ wk.win, wk.memo for P2P / GICP); no-op for AVGICP, which searches
 // inside the accumulation.  `orig` (may be NULL): scan is in binned order and the outputs are written at orig[i].
 // fuse (P2P / GICP): the search kernel also linearises, reduces and — when solve_here — solves: one launch per iteration.
-// warm (P2P / GICP): != 0 = the search starts from the previous iteration's wk.win / wk.memo of the SAME scan (icp_kernels.cu);
-// the value is the grid of the warm kernel (icp_warm_grid).
 cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* orig, const IcpParams& prm, IcpState* st, const IcpWork& wk,
-                              int grid, int prune, int fuse, int warm, int solve_here, cudaStream_t s);
+                              int grid, int prune, int fuse, int solve_here, cudaStream_t s);
 cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int solve_here,
                                   int grid, cudaStream_t s);
+// One WARM iteration of P2P / GICP — search from the previous iteration's wk.win / wk.memo / candidate lists of the SAME scan,
+// linearisation, reduction, solve — as two launches (icp_kernels.cu); wk.partials needs reuse_grid + refresh_grid rows.
+int icp_warm_refresh_grid(const IcpParams& prm, int num_sms);
+cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, const IcpWork& wk, int reuse_grid,
+                                  cudaStream_t s);
+cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
+                                    int refresh_grid, int solve_here, cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);
 // spatial binning of the scan (scan_sort.cu)
 int scan_bin_bits(int n);

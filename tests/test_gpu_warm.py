@@ -112,8 +112,9 @@ def test_warm_search_exact_ties_on_a_lattice():
 
 
 @pytest.mark.parametrize("method", [E.P2P, E.GICP])
-def test_registration_with_and_without_warm_start_is_bit_identical(dense, method):
-    """the warm start changes which bytes are read, not a single correspondence: every output of RunRegister is equal bit for bit"""
+def test_registration_with_and_without_warm_start_agrees_to_rounding(dense, method):
+    """the warm start changes which bytes are read, not a single correspondence; the two paths add the per-point terms in a
+    different order (the warm iteration sums inside its two kernels), so the outputs agree to fp64 rounding, not bit for bit"""
     T_true = synth.se3([3.0, 4.0, 2.5], [0.02, -0.01, 0.3])
     scan = synth.scan_m(dense["stored"], 6000, T_true, seed=21)
     T0 = T_true @ synth.canonical_offset()
@@ -123,8 +124,8 @@ def test_registration_with_and_without_warm_start_is_bit_identical(dense, method
     for warm in (True, False):
         reg.set_warm_start(warm)
         out.append(reg.RunRegister(scan, dense["gm"], T0, cfg))
-    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1] and out[0][2] == out[1][2]
-    assert np.array_equal(out[0][3], out[1][3])
+    assert np.abs(out[0][0] - out[1][0]).max() < 1e-11 and out[0][1] == out[1][1] and abs(out[0][2] - out[1][2]) < 1e-12
+    assert np.abs(out[0][3] - out[1][3]).max() <= 1e-9 * np.abs(out[1][3]).max()
     o = O.Registration().RunRegister(scan, dense["om"], T0, O.make_config(icp_method=method, max_iteration=12, **synth.timing_knobs()))
     assert np.abs(out[0][0] - o["pose"]).max() / np.abs(o["pose"]).max() < 1e-4
 
@@ -140,4 +141,4 @@ def test_warm_state_does_not_leak_between_scans(dense):
     reg.RunRegister(a, dense["gm"], T0, cfg)
     got = reg.RunRegister(b, dense["gm"], T0, cfg)
     fresh = E.Registration(device=0).RunRegister(b, dense["gm"], T0, cfg)
-    assert np.array_equal(got[0], fresh[0]) and got[2] == fresh[2]
+    assert np.array_equal(got[0], fresh[0]) and got[2] == fresh[2]   # (same path, same order: bit for bit)
