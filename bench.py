@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the registration hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--method p2p|gicp|vgicp|avgicp]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
+                    [--method p2p|gicp|vgicp|avgicp] [--n-scan N] [--m-raw M] [--box L] [--scaling weak|strong]
+
+--config selects a BASELINE.json configuration: 2 (default) P2P 131 072 x 10 M; 3 GICP same sizes; 4 VGICP 262 144 x 50 M,
+strong-sharded over the ranks; 5 the streamed pipeline (deskew + AVGICP + EKF on 131 072-point scans, profiles/pipeline_bench.py
+holds that mode: scans/s and latency against the 100 ms budget).  Explicit --method / --n-scan / ... override the preset.
 
 One "step" = one RunRegister call: 20 forced ICP iterations (search + accumulate + solve) of a 131 072-point
 synthetic Scan-U against the 10 M-raw-point Map-U.  Prints ONE JSON line.
@@ -48,21 +53,31 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--method", default="p2p", choices=list(METHOD_IDS))
-    ap.add_argument("--n-scan", type=int, default=N_SCAN)
-    ap.add_argument("--m-raw", type=int, default=M_RAW)
-    ap.add_argument("--box", type=float, default=BOX)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configuration (presets below)")
+    ap.add_argument("--method", default=None, choices=list(METHOD_IDS))
+    ap.add_argument("--n-scan", type=int, default=None)
+    ap.add_argument("--m-raw", type=int, default=None)
+    ap.add_argument("--box", type=float, default=None)
     ap.add_argument("--iters", type=int, default=ITERS)
+    ap.add_argument("--no-warm", action="store_true", help="P2P/GICP: every iteration runs the cold search (no warm start)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=2, help="ICP iterations per CPU-baseline sample")
     ap.add_argument("--fused", action="store_true", help="P2P/GICP: one fused search+accumulate+solve kernel per iteration")
     ap.add_argument("--binning", action="store_true", help="search the scan in spatially binned order")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="N > 1: how the accumulators are all-reduced")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = n-scan points PER RANK (default), strong = n-scan points in total")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = n-scan points PER RANK (default), strong = n-scan points in total (default of --config 4)")
     ap.add_argument("--exhaustive", action="store_true",
                     help="visit all 27 voxels like the reference instead of the exact-pruning search")
-    return ap.parse_args()
+    a = ap.parse_args()
+    preset = {2: ("p2p", N_SCAN, M_RAW, BOX, "weak"), 3: ("gicp", N_SCAN, M_RAW, BOX, "weak"),
+              4: ("vgicp", 262144, 50_000_000, 171.0, "strong"), 5: ("avgicp", N_SCAN, M_RAW, BOX, "weak")}[a.config]
+    a.method = a.method or preset[0]
+    a.n_scan = a.n_scan or preset[1]
+    a.m_raw = a.m_raw or preset[2]
+    a.box = a.box or preset[3]
+    a.scaling = a.scaling or preset[4]
+    return a
 
 
 def load_peaks():
@@ -245,7 +260,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"{args.method.upper()} ICP, {args.n_scan}-pt Scan-U vs {args.m_raw}-raw-pt Map-U "
                           f"({args.box:g} m box, voxel 1.0 m, cap 30), {args.iters} forced iterations per step",
-              "n_scan": args.n_scan, "m_raw": args.m_raw, "iterations_per_step": args.iters, "method": args.method}
+              "n_scan": args.n_scan, "m_raw": args.m_raw, "iterations_per_step": args.iters, "method": args.method,
+              "baseline_config": args.config}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -257,7 +273,8 @@ def main():
         r = cpu_arm(args, raw, scan, T_init, method, max(1, args.steps), args.warmup, args.cpu_iters)
         sample = (f"reference CPU path, two builds timed (oracle port; and the reference's own sources against stand-in "
                   f"Eigen/oneTBB headers when oracle/_ref is built); "
-                  f"each step = RunRegister with {args.cpu_iters} forced iterations on the full workload, "
+                  f"each step = RunRegister with {args.cpu_iters} forced iterations (not the GPU arm's {args.iters}: the metric is per "
+                  f"iteration and every CPU iteration costs the same) on the full workload, "
                   f"{r['threads']} threads for the search, serial accumulate as in the reference")
         out = {"impl": "reference", "metric": "icp_iterations_per_sec", "value": r["value"], "unit": "iterations/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -296,6 +313,7 @@ def main():
     reg.set_exhaustive(args.exhaustive)
     reg.set_binning(args.binning)
     reg.set_fused(args.fused)
+    reg.set_warm_start(not args.no_warm)
     comm_used = args.comm
     if world > 1:
         if args.comm == "peer":

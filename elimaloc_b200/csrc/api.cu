@@ -218,6 +218,11 @@ struct elm_registration {
     int ev_used = 0;
     double prof_search_ms = 0.0, prof_accum_ms = 0.0;
     int64_t prof_launches = 0;
+    // the same split by kind of iteration: 0 cold (search + accumulate), 1 first warm (reuse + bulk refresh), 2 later warm
+    std::vector<int> ev_kind;
+    double prof_kind_ms[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    int64_t prof_kind_n[3] = {0, 0, 0};
+    int warm_iterations_enqueued = 0;  // warm iterations since the last cold one (of the current call)
     // last enqueue
     bool pending = false, trivial = false;  // trivial: empty map or n == 0 -> no kernels ran
     elm_reg_config cfg{};
@@ -427,8 +432,11 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     }
     if (r->profiling) {
         ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 2], r->stream));
+        r->ev_kind.resize(r->ev_used / 3 + 1);
+        r->ev_kind[r->ev_used / 3] = use_warm ? (r->warm_iterations_enqueued == 0 ? 1 : 2) : 0;
         r->ev_used += 3;
     }
+    r->warm_iterations_enqueued = use_warm ? r->warm_iterations_enqueued + 1 : 0;
     if (use_nccl) {
         const int e = g_nccl.AllReduce(r->d_state->acc, r->d_state->acc, elm::kAcc, kNcclFloat64, kNcclSum, r->comm, r->stream);
         if (e != 0) return fail(ELM_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(e));
@@ -447,6 +455,8 @@ void collect_profile(elm_registration* reg) {
         if (cudaEventElapsedTime(&a, reg->ev[i], reg->ev[i + 1]) == cudaSuccess &&
             cudaEventElapsedTime(&b, reg->ev[i + 1], reg->ev[i + 2]) == cudaSuccess) {
             reg->prof_search_ms += a; reg->prof_accum_ms += b; reg->prof_launches += 1;
+            const int kind = reg->ev_kind[i / 3];
+            reg->prof_kind_ms[kind][0] += a; reg->prof_kind_ms[kind][1] += b; reg->prof_kind_n[kind] += 1;
         }
     }
     reg->ev_used = 0;
@@ -930,6 +940,7 @@ int elm_registration_set_profiling(elm_registration* reg, int enable) try {
     reg->ev_used = 0;
     reg->prof_search_ms = reg->prof_accum_ms = 0.0;
     reg->prof_launches = 0;
+    for (int k = 0; k < 3; ++k) { reg->prof_kind_ms[k][0] = reg->prof_kind_ms[k][1] = 0.0; reg->prof_kind_n[k] = 0; }
     return ELM_OK;
 } ELM_API_CATCH
 
@@ -938,6 +949,12 @@ int elm_registration_profile(const elm_registration* reg, double* search_ms, dou
     *search_ms = reg->prof_search_ms;
     *accumulate_ms = reg->prof_accum_ms;
     *iterations = reg->prof_launches;
+    return ELM_OK;
+} ELM_API_CATCH
+
+int elm_registration_profile_by_kind(const elm_registration* reg, double ms[6], int64_t iterations[3]) try {
+    if (!reg || !ms || !iterations) return fail(ELM_ERR_INVALID, "bad argument");
+    for (int k = 0; k < 3; ++k) { ms[2 * k] = reg->prof_kind_ms[k][0]; ms[2 * k + 1] = reg->prof_kind_ms[k][1]; iterations[k] = reg->prof_kind_n[k]; }
     return ELM_OK;
 } ELM_API_CATCH
 

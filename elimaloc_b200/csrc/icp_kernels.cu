@@ -1302,21 +1302,33 @@ __device__ __forceinline__ void warm_refresh(const MapView& map, float4* out_can
             bound = __double2float_ru(R * R) * inv_vs2_up;
             n_new = 0;  // (the points within a finite bound are worth remembering)
         }
-        const Query Q(px, py, pz);
-        // the octants bound WHICH points have to be looked at; the list keeps only those really within R (a handful)
+        // the octants bound WHICH points have to be looked at; the list keeps only those really within R (a handful).  One
+        // pass per run, two sectors in flight, every distance exact (a run is a few points: a pre-filter would not pay)
         const double R2 = R * R;
+        float4 bpt = prev;  // coordinates of the best so far (starts as the previous match)
+        auto fold = [&](const float4& c, uint32_t p) {
+            const double d2 = sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz);
+            if (closer(d2, __float_as_uint(c.w), b)) { b.d2 = d2; b.rank = __float_as_uint(c.w); b.idx = p; bpt = c; }
+            if (d2 <= R2 && n_new != kNone) {
+                if (n_new >= ccap) n_new = kNone;  // does not fit: no list
+                else { out_cand[static_cast<size_t>(n_new) * cstride] = make_float4(c.x, c.y, c.z, __uint_as_float(p)); ++n_new; }
+            }
+        };
         octant_runs(map, row, kx, ky, kz, fx, fy, fz, bound, 0x1ffu, [&](uint32_t rs, uint32_t re) {
-            visit_points(map.pts, rs, re - rs, Q, b);
-            for (uint32_t p = rs; p < re && n_new != kNone; ++p) {
-                const float4 c = __ldg(map.pts + p);  // (just read by visit_points: L1)
-                if (sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz) <= R2) {
-                    if (n_new >= ccap) { n_new = kNone; break; }  // does not fit: no list
-                    out_cand[static_cast<size_t>(n_new) * cstride] = make_float4(c.x, c.y, c.z, __uint_as_float(p));
-                    ++n_new;
+            const uint32_t last_pair = (re - 1) & ~1u;
+            for (uint32_t i = rs & ~1u; i < re; i += 4) {
+                float4 q0[2], q1[2];
+#pragma unroll
+                for (uint32_t u = 0; u < 2; ++u) ldg256(map.pts + min(i + 2 * u, last_pair), q0[u], q1[u]);
+#pragma unroll
+                for (uint32_t u = 0; u < 2; ++u) {
+                    const uint32_t pi = i + 2 * u;
+                    if (pi >= rs && pi < re) fold(q0[u], pi);
+                    if (pi + 1 >= rs && pi + 1 < re) fold(q1[u], pi + 1);
                 }
             }
         });
-        if (b.idx != kNone) { wpt = __ldg(map.pts + b.idx); wpt.w = __uint_as_float(b.idx); }
+        if (b.idx != kNone) wpt = make_float4(bpt.x, bpt.y, bpt.z, __uint_as_float(b.idx));
     }
     // what the list is good for: every point of the 27 voxels within R of the query; the memo keeps the query rounded to fp32
     // (q0), so R shrinks by that rounding
@@ -1479,7 +1491,7 @@ __device__ __forceinline__ void warm_refresh_warp(const MapView& map, float4* ca
 //                            warm_refresh); their correspondences are linearised here, and the LAST block sums the rows of
 //                            both kernels in a fixed order, all-reduces over the ranks (multi-GPU) and solves.
 template <int METHOD>
-__global__ void __launch_bounds__(kIcpThreads, 4)
+__global__ void __launch_bounds__(kIcpThreads, METHOD == 1 ? 3 : 4)
 icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, IcpWork wk) {
     constexpr int NACC = AccSize<METHOD>::value;
     __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
@@ -1669,28 +1681,37 @@ icp_warm_refresh_kernel(MapView map, const float* __restrict__ scan, IcpParams p
         same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
         cbase = static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
     };
+    // this block's tiles: blockIdx.x, blockIdx.x + gridDim.x, ... two at a time, so that their few stragglers (a converging
+    // loop: 0-2 per tile) share the block's eight warps instead of queueing tile after tile
     const int ntiles = (prm.n + kIcpThreads - 1) / kIcpThreads;
-    for (int tile = static_cast<int>(blockIdx.x); tile < ntiles; tile += static_cast<int>(gridDim.x)) {
-        const uint32_t count = wk.refresh_count[tile];
-        const uint32_t* const list = wk.refresh_list + static_cast<size_t>(tile) * kIcpThreads;
-        if (count <= 2 * kIcpWarps) {
-            // a handful (a converging loop): one warp per query
-            for (uint32_t it = warp; it < count; it += kIcpWarps) {
-                const uint32_t gi = list[it];
+    for (int tile0 = static_cast<int>(blockIdx.x); tile0 < ntiles; tile0 += 2 * static_cast<int>(gridDim.x)) {
+        const int tile1 = tile0 + static_cast<int>(gridDim.x);
+        const uint32_t c0 = wk.refresh_count[tile0], c1 = tile1 < ntiles ? wk.refresh_count[tile1] : 0u;
+        const uint32_t* const list0 = wk.refresh_list + static_cast<size_t>(tile0) * kIcpThreads;
+        const uint32_t* const list1 = wk.refresh_list + static_cast<size_t>(tile1 < ntiles ? tile1 : tile0) * kIcpThreads;
+        if (c0 + c1 <= 4 * kIcpWarps) {
+            // a handful: one warp per query
+            for (uint32_t it = warp; it < c0 + c1; it += kIcpWarps) {
+                const uint32_t gi = it < c0 ? list0[it] : list1[it - c0];
                 double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
                 load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);  // (every lane the same query)
                 WarmRefresh r;
                 warm_refresh_warp(map, wk.cand, ccap, prm.warm_margin, 0, px, py, pz, m0, prev, same_key, cbase, s_run[warp], &r);
                 if (lane == 0) commit(gi, r, sx, sy, sz, px, py, pz, qkey_lo, qkey_hi);
             }
-        } else if (static_cast<uint32_t>(tid) < count) {
-            // many (the first warm iteration of a call): one thread per query
-            const uint32_t gi = list[tid];
-            double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
-            load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);
-            WarmRefresh r;
-            warm_refresh(map, wk.cand + cbase, ccap, prm.warm_margin, m0, prev, same_key, px, py, pz, &r);
-            commit(gi, r, sx, sy, sz, px, py, pz, qkey_lo, qkey_hi);
+        } else {
+            // many (the first warm iteration of a call): one thread per query, tile after tile
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t cnt = h ? c1 : c0;
+                if (static_cast<uint32_t>(tid) < cnt) {
+                    const uint32_t gi = (h ? list1 : list0)[tid];
+                    double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
+                    load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);
+                    WarmRefresh r;
+                    warm_refresh(map, wk.cand + cbase, ccap, prm.warm_margin, m0, prev, same_key, px, py, pz, &r);
+                    commit(gi, r, sx, sy, sz, px, py, pz, qkey_lo, qkey_hi);
+                }
+            }
         }
     }
     block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);

@@ -218,6 +218,13 @@ class Registration:
         check(lib().elm_registration_profile(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return float(a.value), float(b.value), int(n.value)
 
+    def profile_by_kind(self):
+        """{kind: (ms in the first kernel, ms in the second kernel, iterations)} for kind in cold / first_warm / warm."""
+        ms = np.zeros(6)
+        n = (C.c_int64 * 3)()
+        check(lib().elm_registration_profile_by_kind(self._h, _d(ms), n))
+        return {k: (float(ms[2 * i]), float(ms[2 * i + 1]), int(n[i])) for i, k in enumerate(("cold", "first_warm", "warm"))}
+
     def set_stats(self, enable):
         check(lib().elm_registration_set_stats(self._h, int(bool(enable))))
 

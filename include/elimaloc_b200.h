@@ -178,6 +178,10 @@ int elm_registration_launch_count(const elm_registration* reg, int64_t* launches
  * registration.cpp:307-347. */
 int elm_registration_set_profiling(elm_registration* reg, int enable);
 int elm_registration_profile(const elm_registration* reg, double* search_ms, double* accumulate_ms, int64_t* iterations);
+/* The same two sums split by kind of iteration: k = 0 cold iteration (search kernel, accumulate kernel), k = 1 first warm
+ * iteration of a call (reuse kernel, refresh kernel doing the bulk refresh), k = 2 later warm iterations (reuse kernel,
+ * refresh kernel).  ms[2 k] / ms[2 k + 1] = first / second kernel of the iteration, iterations[k] = iterations timed. */
+int elm_registration_profile_by_kind(const elm_registration* reg, double ms[6], int64_t iterations[3]);
 
 /* Counters of the P2P/GICP search (off by default; bench.py uses them to state the bytes the search actually has to
  * read): map points visited and queries searched since the last elm_registration_set_stats call. */
