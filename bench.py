@@ -252,6 +252,83 @@ def cpu_baseline_dict(r, sample):
                     "registration.cpp / voxel_hash_map.cpp compiled against stand-in Eigen + oneTBB headers, std::thread chunks)"}
 
 
+def traffic_from_profiles(method_name, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of this
+    round (profiles/r02_traffic_<method>.json, written by profiles/ncu_summary.py --json), else None."""
+    tp = os.path.join(ROOT, "profiles", f"r02_traffic_{method_name}.json")
+    if not os.path.exists(tp):
+        return None
+    with open(tp) as f:
+        k = json.load(f).get("kernels", {}).get(kernel)
+    return (k["dram_bytes_read"] + k["dram_bytes_write"]) if k else None
+
+
+def build_roofline(args, method, st, by_kind, counters, n_local, peak, peak_src, ms_total, world):
+    """One row per kernel of the step: launches, CUDA-event time per launch, the bytes it REQUESTS per query (what its loads
+    and stores ask the memory system for — no phantom probes), GB/s and the fraction of the measured HBM peak.  `roofline` =
+    the row with the largest share of the step, plus the SURVEY 8(d) figure of the reference algorithm for comparison."""
+    exh = algorithmic_bytes_per_search(method, st)  # what visiting all 27 (7) voxels has to read, SURVEY 8(d) units
+    rows = []
+
+    def row(kernel, kind, ms_sum, launches, req, note):
+        if not launches:
+            return
+        us = 1e3 * ms_sum / launches
+        gbs = req * n_local / (us * 1e-6) / 1e9
+        rows.append({"kernel": kernel, "iteration_kind": kind, "launches": launches, "us_per_launch": us, "requested_bytes_per_query": req,
+                     "requested_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "total_ms": ms_sum, "bytes_note": note})
+
+    cold, fw, wm = by_kind["cold"], by_kind["first_warm"], by_kind["warm"]
+    if method < 2:
+        cp = counters["cold_points_per_search"] if counters else st["sum27"]
+        wp = (counters or {}).get("warm_points_per_search") or 0.0
+        rec = 128 if method == 1 else 0  # GICP: the winner's 128-byte covariance record
+        row("icp_search_points_kernel", "cold", cold[0], cold[2], 12 + 64 + 8 * 3 + 16 * cp + 16 + 40,
+            "scan 12 + two directory buckets 64 + ~3 column descriptors 24 + 16 per candidate point + winner reload 16 + match/win/memo/ncand out 40")
+        row(f"icp_accumulate_kernel<{method}>", "cold", cold[1], cold[2], 12 + 16 + (4 + rec if method == 1 else 0), "scan 12 + streamed match 16 (+ GICP: index 4 + record 128)")
+        # warm reuse: scan 12, memo 32, ncand 4, previous match 16, candidates 16 each, out: match 4 + win 16 + memo 16
+        row(f"icp_warm_reuse_kernel<{method}>", "first_warm", fw[0], fw[2], 12 + 32 + 4 + 16, "all queries go to the refresh list: inputs only")
+        row(f"icp_warm_refresh_kernel<{method}>", "first_warm", fw[1], fw[2], 12 + 16 + 16 + 4 * 32 + 16 * st["sum27"] * 0.3 + 16 * wp + 52 + rec,
+            "bulk refresh: inputs 44 + ~4 column records 128 + octant runs (estimate: 0.3 of the 27 voxels' points) + list out + memo/win/ncand out 52")
+        row(f"icp_warm_reuse_kernel<{method}>", "warm", wm[0], wm[2], 12 + 32 + 4 + 16 + 16 * wp + 36 + rec, "scan 12 + memo 32 + ncand 4 + previous match 16 + 16 per list candidate + match/win/memo out 36 (+ GICP record 128)")
+        row(f"icp_warm_refresh_kernel<{method}>", "warm", wm[1], wm[2], 0.0, "a handful of stragglers + fold of the reuse rows + final reduction + solve: a latency chain, not a stream")
+    elif method == 2:
+        row("icp_search_means_kernel", "cold", cold[0], cold[2], 12 + 64 + 8 + 8 * st["v27"] + 4, "scan 12 + buckets 64 + candidate run descriptor 8 + 8 per candidate (13-bit mean offsets + voxel index) + match out 4")
+        row("icp_accumulate_kernel<2>", "cold", cold[1], cold[2], 12 + 4 + 96, "scan 12 + match 4 + mean and covariance 96 (one 128-byte line)")
+    else:
+        row("icp_avgicp_kernel", "cold", cold[1], cold[2], 12 + 64 + 32 + 96 * st["v7"], "scan 12 + buckets 64 + dir7 row 32 + (mean + covariance 96, one 128-byte line) per non-empty voxel of the 7")
+    if not rows:
+        return None
+    tot = sum(r["total_ms"] for r in rows)
+    for r in rows:
+        r["share_of_kernel_time"] = r["total_ms"] / tot
+    dom = max(rows, key=lambda r: r["total_ms"])
+    traffic = traffic_from_profiles(args.method, dom["kernel"].split("<")[0]) if (world == 1 and args.n_scan == N_SCAN and args.m_raw == M_RAW and not args.exhaustive) else None
+    frac_traffic = None
+    if traffic:
+        frac_traffic = traffic / (dom["us_per_launch"] * 1e-6) / 1e9 / peak
+    iters = sum(k[2] for k in by_kind.values())
+    iter_us = 1e3 * tot / max(iters, 1)
+    return {"bound": "hbm", "achieved": dom["requested_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_hbm_peak"],
+            "traffic": traffic, "frac_on_traffic": frac_traffic,
+            "kernel": dom["kernel"], "iteration_kind": dom["iteration_kind"], "kernel_ms_avg": dom["us_per_launch"] * 1e-3, "kernel_launches": dom["launches"],
+            "kernel_share_of_step": dom["share_of_kernel_time"],
+            "share_basis": "sum of the per-kernel CUDA-event times of the event-serialised pass (the PDL-overlapped timed region is shorter: see step_ms_pdl vs step_ms_serialised)",
+            "step_ms_pdl": ms_total / args.steps, "step_ms_serialised": tot / args.steps,
+            "algorithmic_bytes_per_search": dom["requested_bytes_per_query"], "searches_per_launch": n_local,
+            "accounting": "requested bytes (loads + stores the kernel issues per query), no probe bytes that are never read",
+            "search_mode": ("exhaustive-27" if args.exhaustive else "exact-pruning") + (", warm-started from iteration 2" if (method < 2 and not args.no_warm) else ""),
+            "search_counters": counters,
+            "reference_algorithm_bytes_per_search": exh,
+            "reference_algorithm_equivalent_gbs": exh * n_local / (iter_us * 1e-6) / 1e9,
+            "reference_algorithm_equivalent_note": "bytes GetCorrespondence* has to read (SURVEY 8(d): 27 slots + every stored point of the 27 voxels) / OUR mean "
+                                                   "iteration time: above the HBM peak means the exact pruning + warm start skip that much work, not that HBM is faster",
+            "iteration_us_serialised": iter_us,
+            "kernels": rows,
+            "mean_stored_points_in_27_voxels": st["sum27"], "mean_nonempty_voxels_27": st["v27"], "mean_nonempty_voxels_7": st["v7"],
+            "peak_source": peak_src}
+
+
 def main():
     args = parse()
     method = METHOD_IDS[args.method]
@@ -422,16 +499,27 @@ def main():
         reg.enqueue(d_scans[i % n_variants].data_ptr(), n_local, gmap, T_init, cfg)
     reg.fetch()
     search_ms, accum_ms, prof_iters = reg.profile()
+    by_kind = reg.profile_by_kind()
     reg.set_profiling(False)
-    # untimed pass with the search counters on: map points the search really had to visit
-    visited_per_search = None
+    # untimed passes with the search counters on: candidate points the searches really read — cold search alone (a call of
+    # one iteration), then a whole step (the warm searches are the difference)
+    counters = None
     if method < 2:
+        cfg1 = E.RegistrationConfig(icp_method=method, max_iteration=1, **synth.timing_knobs())
+        reg.set_stats(True)
+        reg.enqueue(d_scans[0].data_ptr(), n_local, gmap, T_init, cfg1)
+        reg.fetch()
+        c1 = reg.stats_raw()
         reg.set_stats(True)
         reg.enqueue(d_scans[0].data_ptr(), n_local, gmap, T_init, cfg)
         reg.fetch()
-        vis, nq = reg.stats()
+        cs = reg.stats_raw()
         reg.set_stats(False)
-        visited_per_search = vis / max(nq, 1)
+        warm_q = cs[21]
+        counters = {"cold_points_per_search": c1[0] / max(c1[1], 1),
+                    "warm_points_per_search": (cs[0] - c1[0]) / max(cs[1] - c1[1], 1) if cs[1] > c1[1] else None,
+                    "warm_searches_per_step": warm_q, "warm_searches_refreshed_per_step": cs[20],
+                    "warm_refresh_fraction_after_first": (max(cs[20] - n_local, 0) / max(warm_q - n_local, 1)) if warm_q > n_local else None}
     iters_total = args.steps * args.iters
     # ICP iterations/s of the metric's n-scan-point scan: (points searched + accumulated per second) / n-scan
     units = n_global / args.n_scan
@@ -480,43 +568,37 @@ def main():
     e2e_value = units * iters_total / (e2e_ms * 1e-3)
     state_bytes = 16 * 8 * 2 + 9 * 8 + 32 * 8 + 36 * 8 + 6 * 8 + 3 * 8 + 36 * 8 + 16  # sizeof(IcpState)
 
+    # ---- N > 1: result check inside the bench (the driver's scaling runs assert nothing otherwise): every rank must hold the
+    # bit-identical pose and fitness after a step, and they must equal ONE GPU registering the concatenated scan (1e-9)
+    parity = None
+    if world > 1:
+        reg.enqueue(d_scans[0].data_ptr(), n_local, gmap, T_init, cfg)
+        r_mine = reg.fetch()
+        mine = (r_mine[0].tobytes(), np.float64(r_mine[2]).tobytes(), r_mine[1], r_mine[4])
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        parts = [None] * world
+        dist.all_gather_object(parts, shards[0])
+        if rank == 0:
+            identical = all(a == allr[0] for a in allr)
+            single = E.Registration(device=local_rank)
+            T1, ok1, fit1, _ = single.RunRegister(np.concatenate(parts), gmap, T_init, cfg)
+            del single
+            scale = max(1.0, float(np.abs(T1).max()))
+            diff = float(np.abs(r_mine[0] - T1).max()) / scale
+            fdiff = abs(r_mine[2] - fit1) / max(abs(fit1), 1e-300)
+            parity = {"parity_ok": bool(identical and diff <= 1e-9 and fdiff <= 1e-9 and ok1 == r_mine[1]), "ranks_bit_identical": bool(identical),
+                      "pose_rel_diff_vs_one_gpu": diff, "fitness_rel_diff_vs_one_gpu": fdiff, "tolerance": 1e-9,
+                      "what": f"final pose + fitness of one step ({args.iters} iterations) on {world} ranks vs one GPU on the concatenated {sum(len(p_) for p_ in parts)}-point scan"}
+        dist.barrier()
+
     # ---- roofline of the dominant kernel (rank 0's shard)
     peak, peak_src = load_peaks()
     ex = gmap.export()
     st = neighbourhood_stats(ex["keys"], ex["counts"], shards[0], T_init, 1.0)
     roofline = None
     if st and prof_iters:
-        # Algorithmic bytes per search (SURVEY.md 8(d) units: slot 16 B, xyz 12 B, mean 24 B, cov 72 B).  For the
-        # exact-pruning P2P/GICP search the map points that must be read are the ones of the voxels that cannot be
-        # excluded (measured by the kernel's own counter); `exhaustive_*` keeps the reference algorithm's figure.
-        bps_exh = algorithmic_bytes_per_search(method, st)
-        bps = bps_exh
-        if visited_per_search is not None and not args.exhaustive:
-            bps = bps_exh - 12 * st["sum27"] + 12 * visited_per_search
-        dom_ms = (search_ms if method != 3 else accum_ms) / prof_iters
-        achieved = bps * n_local / (dom_ms * 1e-3) / 1e9
-        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        tp = os.path.join(ROOT, "profiles", f"r01_traffic_{args.method}.json")
-        if os.path.exists(tp) and not args.exhaustive and world == 1 and args.n_scan == N_SCAN and args.m_raw == M_RAW:
-            with open(tp) as f:
-                k = json.load(f)["kernels"].get("icp_search_points_kernel" if method < 2 else "")
-            if k:
-                traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic,
-                    "kernel": {0: "icp_search_points_kernel", 1: "icp_search_points_kernel", 2: "icp_search_means_kernel",
-                               3: "icp_accumulate_kernel<3>"}[method],
-                    "kernel_ms_avg": dom_ms, "kernel_launches": prof_iters,
-                    "kernel_share_of_step": min(1.0, (search_ms if method != 3 else accum_ms) / ms_total),
-                    "accumulate_kernel_ms_avg": accum_ms / prof_iters,
-                    "algorithmic_bytes_per_search": bps, "searches_per_launch": n_local,
-                    "search_mode": "exhaustive-27" if args.exhaustive else "exact-pruning",
-                    "map_points_visited_per_search": visited_per_search,
-                    "requested_bytes_per_search": (12 + 64 + 16 * visited_per_search) if visited_per_search is not None else None,
-                    "exhaustive_bytes_per_search": bps_exh,
-                    "exhaustive_equivalent_gbs": bps_exh * n_local / (dom_ms * 1e-3) / 1e9,
-                    "mean_stored_points_in_27_voxels": st["sum27"], "mean_nonempty_voxels_27": st["v27"],
-                    "mean_nonempty_voxels_7": st["v7"], "peak_source": peak_src}
+        roofline = build_roofline(args, method, st, by_kind, counters, n_local, peak, peak_src, ms_total, world)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
     cpu = None
@@ -540,7 +622,8 @@ def main():
                               l2_policy="inputs larger than L2 (map + table > 126 MB) and a different scan every step",
                               searches_per_sec=value * args.n_scan, n_scan_global=n_global, map_build_s=build_s,
                               stored_points=int(ex["counts"].sum()), voxels=int(len(ex["counts"])),
-                              iterations_run_last_step=res[4], success_last_step=res[1]),
+                              iterations_run_last_step=res[4], success_last_step=res[1], multi_gpu_parity=parity,
+                              parity_ok=(parity or {}).get("parity_ok")),
                "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": n_local * 12,
                        "d2h_bytes_per_step": state_bytes, "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": launches_per_step * args.steps,

@@ -104,6 +104,7 @@ SIGNATURES = {
     "elm_registration_profile_by_kind": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
     "elm_registration_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "elm_registration_stats_raw": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "elm_registration_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_set_binning": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_registration_set_exhaustive": (C.c_int, [C.c_void_p, C.c_int]),

@@ -92,15 +92,14 @@ struct elm_map {
     uint32_t* d_drows = nullptr;
     float4* d_pts = nullptr;
     double* d_prec = nullptr;
-    double4* d_vslots = nullptr;
-    double* d_vcov = nullptr;
-    float4* d_vcand = nullptr;
+    double* d_vrec = nullptr;                 // 128-byte record per voxel: mean[3] cov[9] pad[4]
+    unsigned long long* d_vcand8 = nullptr;   // VGICP candidate records (voxel_key.hpp: pack_vcand)
     int* d_dir7 = nullptr;
 
     elm::MapView view() const {
         elm::MapView v;
-        v.dslots = d_dslots; v.drows = d_drows; v.bmask = host.dir_bmask; v.pts = d_pts; v.prec = d_prec; v.vslots = d_vslots; v.vcov = d_vcov; v.vcand = d_vcand; v.dir7 = d_dir7;
-        v.mask = host.mask; v.voxel_size = host.voxel_size;
+        v.dslots = d_dslots; v.drows = d_drows; v.bmask = host.dir_bmask; v.pts = d_pts; v.prec = d_prec; v.vrec = d_vrec; v.vcand8 = d_vcand8; v.dir7 = d_dir7;
+        v.voxel_size = host.voxel_size;
         int e2 = 0;
         v.inv_voxel_size = (std::frexp(host.voxel_size, &e2) == 0.5) ? 1.0 / host.voxel_size : 0.0;
         return v;
@@ -123,9 +122,8 @@ struct elm_map {
         ELM_CUDA(upload(&d_dslots, reinterpret_cast<const uint4*>(host.dir_slots.data()), host.dir_slots.size()));
         ELM_CUDA(upload(&d_drows, host.dir_rows.data(), host.dir_rows.size()));
         if (d_prec) { cudaFree(d_prec); d_prec = nullptr; }
-        if (d_vslots) { cudaFree(d_vslots); d_vslots = nullptr; }
-        if (d_vcov) { cudaFree(d_vcov); d_vcov = nullptr; }
-        if (d_vcand) { cudaFree(d_vcand); d_vcand = nullptr; }
+        if (d_vrec) { cudaFree(d_vrec); d_vrec = nullptr; }
+        if (d_vcand8) { cudaFree(d_vcand8); d_vcand8 = nullptr; }
         if (d_dir7) { cudaFree(d_dir7); d_dir7 = nullptr; }
         return ELM_OK;
     }
@@ -133,20 +131,15 @@ struct elm_map {
     int publish_voxel_cov() {
         if (device < 0) return ELM_OK;
         ELM_CUDA(cudaSetDevice(device));
-        const size_t S = host.slots.size();
-        std::vector<double> vs(4 * S, 0.0), vc(12 * S, 0.0);
-        const uint64_t empty = elm::kEmptyKey;
-        for (size_t s = 0; s < S; ++s) {
-            const int32_t v = host.slot_voxel[s];
-            if (v < 0) { std::memcpy(&vs[4 * s], &empty, 8); continue; }
-            std::memcpy(&vs[4 * s], &host.vkey[v], 8);
-            for (int k = 0; k < 3; ++k) vs[4 * s + 1 + k] = host.vmean[3 * v + k];
-            for (int k = 0; k < 9; ++k) vc[12 * s + k] = host.vcov[9 * v + k];
+        const size_t V = host.V();
+        std::vector<double> rec(16 * V, 0.0);  // one 128-byte line per voxel: the accumulation reads mean + covariance in ONE DRAM burst
+        for (size_t v = 0; v < V; ++v) {
+            for (int k = 0; k < 3; ++k) rec[16 * v + k] = host.vmean[3 * v + k];
+            for (int k = 0; k < 9; ++k) rec[16 * v + 3 + k] = host.vcov[9 * v + k];
         }
-        ELM_CUDA(upload(reinterpret_cast<double**>(&d_vslots), vs.data(), 4 * S));
-        ELM_CUDA(upload(&d_vcov, vc.data(), 12 * S));
-        // candidate lists + the row descriptors 9 / 10 that point into them
-        ELM_CUDA(upload(&d_vcand, reinterpret_cast<const float4*>(host.vcand.data()), host.vcand.size() / 4));
+        ELM_CUDA(upload(&d_vrec, rec.data(), 16 * V));
+        // candidate lists + the row headers that point into them
+        ELM_CUDA(upload(&d_vcand8, reinterpret_cast<const unsigned long long*>(host.vcand8.data()), host.vcand8.size()));
         ELM_CUDA(upload(&d_dir7, host.dir7.data(), host.dir7.size()));
         ELM_CUDA(upload(&d_drows, host.dir_rows.data(), host.dir_rows.size()));
         return ELM_OK;
@@ -168,7 +161,7 @@ struct elm_map {
     ~elm_map() {
         if (device >= 0) {
             cudaSetDevice(device);
-            cudaFree(d_dslots); cudaFree(d_drows); cudaFree(d_pts); cudaFree(d_prec); cudaFree(d_vslots); cudaFree(d_vcov); cudaFree(d_vcand); cudaFree(d_dir7);
+            cudaFree(d_dslots); cudaFree(d_drows); cudaFree(d_pts); cudaFree(d_prec); cudaFree(d_vrec); cudaFree(d_vcand8); cudaFree(d_dir7);
         }
     }
 };
@@ -191,6 +184,11 @@ struct elm_registration {
     int cand_cap = 32;
     size_t match_cap = 0;
     int warm = 1;              // P2P / GICP: iterations after the first start their search from the previous match (same result)
+    // warm iterations after the first of a call as ONE kernel (icp_warm_kernel) or as the reuse + refresh pair.  Measured on B200
+    // (profiles/r02_ab_warm_single_kernel.txt): GICP 19.9k vs 18.6k iterations/s in favour of the single kernel, P2P 28.3k vs 30.8k
+    // against it (the in-lined refresh path spills into the 64-register reuse path) -> default: GICP single, P2P pair;
+    // ELM_WARM_SINGLE=0 / 1 forces one or the other (A/B switch).
+    int warm_single = [] { const char* e = getenv("ELM_WARM_SINGLE"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     // spatially binned copy of the scan for the search kernels (scan_sort.cu)
     float* d_sorted = nullptr;
     int* d_orig = nullptr;
@@ -356,7 +354,7 @@ int check_method(const elm_map* map, const elm_reg_config* cfg) {
     if (map->device < 0) return fail(ELM_ERR_CUDA, "map is host-only (device = -1): no CUDA device to run on");
     if (!map->host.vkey.empty()) {
         if (cfg->icp_method == ELM_GICP && !map->d_prec) return fail(ELM_ERR_STATE, "GICP needs elm_map_cal_point_cov first");
-        if ((cfg->icp_method == ELM_VGICP || cfg->icp_method == ELM_AVGICP) && !map->d_vslots)
+        if ((cfg->icp_method == ELM_VGICP || cfg->icp_method == ELM_AVGICP) && !map->d_vrec)
             return fail(ELM_ERR_STATE, "VGICP/AVGICP need elm_map_cal_voxel_cov first");
     }
     return ELM_OK;
@@ -413,7 +411,12 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // P2P / GICP from the second iteration of a call on: the warm pair of kernels (reuse: search + linearisation of the
     // queries whose candidate lists still hold; refresh: the rest, then reduction and solve)
     const bool use_warm = warm && r->warm && r->prune && !mapped && !fuse && prm.method <= ELM_GICP;
-    if (use_warm) {
+    if (use_warm && (r->warm_single < 0 ? prm.method == ELM_GICP : r->warm_single == 1) && r->warm_iterations_enqueued > 0) {
+        // every warm iteration after the first: ONE kernel (stragglers refreshed in place by their own warp)
+        if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
+        ELM_CUDA(elm::launch_icp_warm(map->view(), d_scan, prm, r->d_state, wk, wgrid, solve_here, r->stream));
+        r->launches += 1;
+    } else if (use_warm) {
         ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), d_scan, prm, r->d_state, wk, wgrid, r->stream));
         if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
         ELM_CUDA(elm::launch_icp_warm_refresh(map->view(), d_scan, prm, r->d_state, wk, wgrid, rgrid, solve_here, r->stream));
@@ -501,6 +504,7 @@ int elm_map_add_points(elm_map* map, const float* xyz, size_t n) try {
 
 int elm_map_cal_voxel_cov(elm_map* map) try {
     if (!map) return fail(ELM_ERR_INVALID, "null map");
+    if (map->host.V() >= (1ull << elm::kVcandVoxelBits)) return fail(ELM_ERR_RANGE, "elm_map_cal_voxel_cov: more than 2^25 voxels");
     map->host.cal_voxel_cov();
     return map->publish_voxel_cov();
 } ELM_API_CATCH
@@ -682,11 +686,13 @@ int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slo
                 const int64_t v = (elm::key_in_range(vx) && elm::key_in_range(vy) && elm::key_in_range(vz)) ? h.find(elm::pack_key(vx, vy, vz)) : -1;
                 if ((v >= 0) != (((occ.first >> L) & 1u) != 0)) { ++bad; continue; }
                 if (v < 0) continue;
-                const float* cd = &h.vcand[4 * static_cast<size_t>(run.first + c)];
-                uint32_t slot;
-                std::memcpy(&slot, &cd[3], 4);
-                if (slot >= h.slot_voxel.size() || h.slot_voxel[slot] != v) ++bad;
-                for (int k = 0; k < 3; ++k) if (cd[k] != static_cast<float>(h.vmean[3 * v + k])) ++bad;
+                float ox, oy, oz;
+                uint32_t vox;
+                elm::unpack_vcand(h.vcand8[run.first + c], ox, oy, oz, vox);
+                if (vox != static_cast<uint32_t>(v)) ++bad;
+                const double want[3] = {h.vmean[3 * v] / h.voxel_size - x, h.vmean[3 * v + 1] / h.voxel_size - y, h.vmean[3 * v + 2] / h.voxel_size - z};
+                const float got[3] = {ox, oy, oz};
+                for (int k = 0; k < 3; ++k) if (!(std::fabs(static_cast<double>(got[k]) - want[k]) <= 2.45e-4)) ++bad;  // the band of the search relies on this
                 ++c;
             }
             if (c != run.counts) ++bad;
@@ -696,7 +702,7 @@ int elm_map_directory_check(const elm_map* map, uint64_t* entries, uint64_t* slo
                 const int32_t vx = x + L / 9 - 1, vy = y + (L / 3) % 3 - 1, vz = z + L % 3 - 1;
                 const int64_t v = (elm::key_in_range(vx) && elm::key_in_range(vy) && elm::key_in_range(vz)) ? h.find(elm::pack_key(vx, vy, vz)) : -1;
                 const int32_t sl7 = h.dir7[8 * s + j];
-                if ((v < 0) != (sl7 < 0) || (v >= 0 && h.slot_voxel[sl7] != v)) ++bad;
+                if ((v < 0) != (sl7 < 0) || (v >= 0 && sl7 != v)) ++bad;
             }
         }
     }
@@ -986,6 +992,17 @@ int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, 
     if (getenv("ELM_WARM_STATS")) std::fprintf(stderr, "[warm search] %llu of %llu warm searches refreshed their runs\n", h[20], h[21]);
     *map_points_visited = h[0];
     *queries = h[1];
+    return ELM_OK;
+} ELM_API_CATCH
+
+int elm_registration_stats_raw(elm_registration* reg, uint64_t counters[32]) try {
+    if (!reg || !counters) return fail(ELM_ERR_INVALID, "bad argument");
+    if (!reg->d_stats) return fail(ELM_ERR_STATE, "stats were never enabled");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    unsigned long long h[32] = {0};
+    ELM_CUDA(cudaMemcpyAsync(h, reg->d_stats, sizeof h, cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    for (int i = 0; i < 32; ++i) counters[i] = h[i];
     return ELM_OK;
 } ELM_API_CATCH
 

@@ -344,7 +344,7 @@ std::string HostMap::add_points(const float* xyz, size_t n) {
     n_raw_seen += n;
     has_vcov = has_pcov = false;
     vmean.clear(); vcov.clear(); pmean.clear(); pcov.clear(); pnormal.clear();
-    vcand.clear(); dir7.clear();
+    vcand8.clear(); dir7.clear();
     timer.lap("compaction");
     build_table();
     timer.lap("voxel table");
@@ -721,7 +721,7 @@ void HostMap::cal_voxel_cov() {
 
 void HostMap::build_voxel_candidates() {
     const size_t S = dir_slots.size();
-    vcand.clear();
+    vcand8.clear();
     if (S == 0) return;
     std::vector<int32_t> voxel_slot(V(), -1);
     for (size_t s = 0; s < slot_voxel.size(); ++s) if (slot_voxel[s] >= 0) voxel_slot[slot_voxel[s]] = static_cast<int32_t>(s);
@@ -744,7 +744,7 @@ void HostMap::build_voxel_candidates() {
         }
     });
     for (size_t s = 0; s < S; ++s) first[s + 1] = first[s] + static_cast<uint32_t>(__builtin_popcount(masks[s]));
-    vcand.assign(4 * static_cast<size_t>(first[S]) + 4, 0.0f);  // (+1 element of padding: aligned 32-byte pair loads)
+    vcand8.assign(static_cast<size_t>(first[S]) + 4, 0ull);  // (+4 records of padding: aligned 32-byte loads)
     dir7.assign(8 * S, -1);
     parallel_for(S, 1 << 13, [&](size_t sb, size_t se) {
         int64_t v27[27];
@@ -760,15 +760,15 @@ void HostMap::build_voxel_candidates() {
                 for (int dz = 0; dz < 3; ++dz) if ((masks[s] >> (3 * c + dz)) & 1u) v27[3 * c + dz] = v++;
             }
             static const int kL7[7] = {13, 22, 4, 16, 10, 14, 12};  // centre, +x, -x, +y, -y, +z, -z
-            for (int j = 0; j < 7; ++j) if (v27[kL7[j]] >= 0) dir7[8 * s + j] = voxel_slot[v27[kL7[j]]];
-            float* out = &vcand[4 * static_cast<size_t>(first[s])];
+            for (int j = 0; j < 7; ++j) if (v27[kL7[j]] >= 0) dir7[8 * s + j] = static_cast<int32_t>(v27[kL7[j]]);
+            int32_t key[3];
+            unpack_key((static_cast<uint64_t>(dir_slots[s].key_hi) << 32) | dir_slots[s].key_lo, key[0], key[1], key[2]);
+            uint64_t* out = &vcand8[first[s]];
             for (int L = 0; L < 27; ++L) {
                 if (v27[L] < 0) continue;
                 const size_t v = static_cast<size_t>(v27[L]);
-                out[0] = static_cast<float>(vmean[3 * v]); out[1] = static_cast<float>(vmean[3 * v + 1]); out[2] = static_cast<float>(vmean[3 * v + 2]);
-                const uint32_t slot = static_cast<uint32_t>(voxel_slot[v]);
-                std::memcpy(&out[3], &slot, 4);
-                out += 4;
+                *out++ = pack_vcand(vmean[3 * v] / voxel_size - key[0], vmean[3 * v + 1] / voxel_size - key[1], vmean[3 * v + 2] / voxel_size - key[2],
+                                    static_cast<uint32_t>(v));
             }
         }
     });

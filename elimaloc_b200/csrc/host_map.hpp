@@ -64,11 +64,12 @@ struct HostMap {
     uint32_t dir_bmask = 0;
     size_t dir_entries = 0;
     // VGICP / AVGICP candidates (built by cal_voxel_cov): for every directory entry the non-empty voxels of its
-    // 27-neighbourhood in the reference's visit order (x outer, y, z inner), one float4 each {mean rounded to fp32, bits of
-    // the voxel's slot in `slots`}.  Row descriptor 10 of the entry = {first candidate, count}, descriptor 11 = {27-bit
-    // occupancy mask (bit 9 (dx+1) + 3 (dy+1) + (dz+1)), 0}.
-    std::vector<float> vcand;  // 4 per candidate
-    // AVGICP: per directory SLOT the voxel-table slots of {centre, +x, -x, +y, -y, +z, -z} (vhm.cpp:224-230) or -1, padded to 8
+    // 27-neighbourhood in the reference's visit order (x outer, y, z inner), one 8-byte record each (pack_vcand, voxel_key.hpp:
+    // the voxel's mean relative to the entry's key in 13-bit fixed point — enough for the search's pre-filter, the exact fp64
+    // mean decides near ties — and the voxel's index).  Row header of the entry: {first candidate, count}, 27-bit occupancy
+    // mask (bit 9 (dx+1) + 3 (dy+1) + (dz+1)).
+    std::vector<uint64_t> vcand8;
+    // AVGICP: per directory SLOT the voxel indices of {centre, +x, -x, +y, -y, +z, -z} (vhm.cpp:224-230) or -1, padded to 8
     std::vector<int32_t> dir7;
 
     size_t V() const { return vkey.size(); }

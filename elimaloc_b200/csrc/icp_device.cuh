@@ -13,12 +13,12 @@
 //                                inside an octant; w = bits of the point's canonical index (voxel order, then insertion order)
 //                                = its rank in the reference's visit order, which decides exact distance ties
 //   prec    double[16 P]         GICP record per stored point (same order as pts): mean[3] cov[9] normal[3] pad  (128 B, one line)
-//   vslots  double4[capacity]    VGICP/AVGICP: 32 B/slot {key bits, mean[3]}, open-addressed with linear probing, capacity = 2^k
-//                                >= 2 V (mask = capacity - 1); empty = all ones
-//   vcand   float4[C]            VGICP/AVGICP candidates: for every directory entry the non-empty voxels of its 27-neighbourhood
-//                                in visit order, {mean rounded to fp32, bits of the voxel's slot in vslots}; the row header holds
-//                                {first candidate, count} and the 27-bit occupancy mask
-//   vcov    double[12 capacity]  VGICP/AVGICP: 96 B/slot {cov[9], pad[3]}
+//   vrec    double[16 V]         VGICP/AVGICP: one 128-byte line per voxel (canonical voxel order) {mean[3], cov[9], pad[4]}: the
+//                                accumulation reads mean + covariance of a correspondence in ONE DRAM burst
+//   vcand8  uint64[C]            VGICP candidates: for every directory entry the non-empty voxels of its 27-neighbourhood in
+//                                visit order, 8 bytes each {3 x 13-bit mean relative to the entry's key, 25-bit voxel index}
+//                                (voxel_key.hpp); the row header holds {first candidate, count} and the 27-bit occupancy mask
+//   dir7    int32[8 S]           AVGICP: voxel indices of {c, +x, -x, +y, -y, +z, -z} of every directory slot or -1
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,11 +30,9 @@ struct MapView {
     const uint32_t* drows;
     const float4* pts;
     const double* prec;
-    const double4* vslots;
-    const double* vcov;
-    const float4* vcand;
-    const int* dir7;  // AVGICP: 8 ints per directory slot: voxel-table slots of {c, +x, -x, +y, -y, +z, -z} or -1
-    uint32_t mask;   // vslots
+    const double* vrec;                 // VGICP/AVGICP: 16 doubles (one 128-byte line) per voxel: mean[3] cov[9] pad[4]
+    const unsigned long long* vcand8;   // VGICP: 8-byte candidate records (voxel_key.hpp: pack_vcand)
+    const int* dir7;  // AVGICP: 8 ints per directory slot: voxel indices of {c, +x, -x, +y, -y, +z, -z} or -1
     uint32_t bmask;  // directory buckets - 1
     double voxel_size;
     double inv_voxel_size;  // 1 / voxel_size when that is exact (voxel_size a power of two: p * inv == p / vs bit for bit), else 0

@@ -8,8 +8,8 @@
 //        -> match[n] (index of the winning map point / voxel slot), win[n] (the matched point itself, streamed by the
 //           accumulation), memo[n] (warm start of the next search) — never the 168-B structs
 //   icp_accumulate_kernel<M>   AlignCloudsLocal{,PointCov,VoxelCov} accumulation        reg.cpp:28-51 / 85-132 / 171-208
-//        (AVGICP searches its 7 voxels inside this kernel, vhm.cpp:153-206), block tree reduction, and in the LAST
-//        block to finish: fixed-order reduction of all partials + the solve/update step below
+//        block tree reduction, and in the LAST block to finish: fixed-order reduction of all partials + the solve/update step
+//   icp_avgicp_kernel          AVGICP    GetCorrespondencesAllCov + AlignCloudsLocalVoxelCov in one kernel (vhm.cpp:153-206)
 //        (multi-GPU: before the solve the last block all-reduces the 32 sums over the ranks through peer-memory mailboxes)
 //   icp_solve_kernel           overlap gate, LM-damped LDLT solve, exp map, pose update, termination test
 //        (reg.cpp:349-356, 53-65, 136-151, 378-387) — separate launch only in the NCCL mode, after the ncclAllReduce
@@ -164,15 +164,6 @@ struct ExactPoint {
     __device__ __forceinline__ void operator()(const float4& q, double& x, double& y, double& z) const { x = q.x; y = q.y; z = q.z; }
     __device__ __forceinline__ uint32_t rank(const float4& q, uint32_t) const { return __float_as_uint(q.w); }
 };
-struct ExactMean {
-    const double4* vslots;
-    __device__ __forceinline__ void operator()(const float4& q, double& x, double& y, double& z) const {
-        const double2* r = reinterpret_cast<const double2*>(vslots + __float_as_uint(q.w));
-        const double2 a = __ldg(r), b = __ldg(r + 1);
-        x = a.y; y = b.x; z = b.y;
-    }
-    __device__ __forceinline__ uint32_t rank(const float4&, uint32_t idx) const { return idx; }  // candidate lists are in visit order
-};
 template <class Fetch>
 __device__ __forceinline__ void fold_exact(const Fetch& fetch, const float4& q, uint32_t idx, double px, double py, double pz, Best& b) {
     double x, y, z;
@@ -305,31 +296,69 @@ __device__ __forceinline__ uint32_t voxels_to_visit(int kx, int ky, int kz, floa
     }
     return need & ~skip;
 }
-// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115), one thread per query: ONE directory lookup, then the
-// entry's candidate list (the non-empty voxels of the neighbourhood in the reference's visit order, means rounded to fp32)
-// is scanned like a run of points; the winner's exact fp64 mean decides (strict < keeps the first of equals).
-// Returns the winning voxel's slot or -1.
-__device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, double py, double pz, int kx, int ky, int kz) {
+// exact fp64 mean of voxel v (first sector of its 128-byte record)
+__device__ __forceinline__ void voxel_mean(const MapView& map, uint32_t v, double& mx, double& my, double& mz) {
+    const double2* r = reinterpret_cast<const double2*>(map.vrec + static_cast<size_t>(v) * 16);
+    const double2 a = __ldg(r), b = __ldg(r + 1);
+    mx = a.x; my = a.y; mz = b.x;
+}
+// Nearest voxel MEAN of the 27 voxels (VGICP, vhm.cpp:92-115), one thread per query: ONE directory lookup, then the entry's
+// candidate list — the non-empty voxels of the neighbourhood in the reference's visit order, 8 bytes each: the mean relative
+// to the entry's key in 13-bit fixed point + the voxel index (voxel_key.hpp) — is scanned with fp32 distances in the entry's
+// own frame (voxel units: no large coordinates, so the only error is the quantisation, <= 4.3e-4 per candidate).  A candidate
+// can only be at least as close as the fp32 argmin if its fp32 distance is within 2 x that error of the minimum: if the
+// second-smallest value lies outside that band (1.2e-3 voxel sizes, against gaps of order 0.1-1 between voxel means) the
+// argmin is the unique exact winner and NOTHING else is read; otherwise (rare) every candidate is decided with its exact
+// fp64 mean in visit order (strict <: the first of equals, vhm.cpp:113).  Returns the winning voxel's index or -1.
+__device__ __forceinline__ int nearest_mean_27(const MapView& map, double px, double py, double pz) {
+    float fx, fy, fz;
+    const int kx = voxel_floor(px, map, &fx), ky = voxel_floor(py, map, &fy), kz = voxel_floor(pz, map, &fz);
     uint2 centre;
     const int row = dir_lookup(map, kx, ky, kz, centre);
     if (row < 0) return -1;
     const uint2 d = __ldg(reinterpret_cast<const uint2*>(map.drows + row_word(static_cast<size_t>(row), kRowCandFirst)));  // {first candidate, count}
-    Best b;
-    visit_points(map.vcand, d.x, d.y, Query(px, py, pz), b, ExactMean{map.vslots});
-    return (b.idx == 0xffffffffu) ? -1 : static_cast<int>(__float_as_uint(__ldg(map.vcand + b.idx).w));
-}
-
-// AVGICP (vhm.cpp:153-206, GetAdjacentVoxels range 1): voxel j of {centre, +x, -x, +y, -y, +z, -z} around the query's
-// directory entry: its slot in the voxel table or -1 when it holds no points.  No probing: one 32-byte row per entry,
-// shared by the 8 lanes of a point.
-__device__ __forceinline__ int neighbour7_slot(const MapView& map, int row, int j) {
-    return __ldg(map.dir7 + static_cast<size_t>(row) * 8 + j);
-}
-// exact fp64 mean of a voxel slot
-__device__ __forceinline__ void slot_mean(const MapView& map, int slot, double& mx, double& my, double& mz) {
-    const double2* r = reinterpret_cast<const double2*>(map.vslots + slot);
-    const double2 a = __ldg(r), b = __ldg(r + 1);
-    mx = a.y; my = b.x; mz = b.y;
+    if (d.y == 0) return -1;
+    const uint32_t first = d.x, end = d.x + d.y;
+    const uint32_t last_quad = (end - 1) & ~3u;
+    const float kInf = __int_as_float(0x7f800000);
+    const float step = 4.0f / static_cast<float>(kVcandAxisMax);
+    float m = kInf, s2 = kInf;
+    uint32_t mv = 0;
+    constexpr uint32_t K = 4;  // 32-byte loads (4 candidates each) in flight
+    for (uint32_t i = first & ~3u; i < end; i += 4 * K) {
+        uint32_t w[K][8];
+#pragma unroll
+        for (uint32_t u = 0; u < K; ++u)
+            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]), "=r"(w[u][4]), "=r"(w[u][5]), "=r"(w[u][6]), "=r"(w[u][7])
+                : "l"(map.vcand8 + min(i + 4 * u, last_quad)));
+#pragma unroll
+        for (uint32_t u = 0; u < K; ++u)
+#pragma unroll
+            for (uint32_t t = 0; t < 4; ++t) {
+                const uint32_t idx = i + 4 * u + t, lo = w[u][2 * t], hi = w[u][2 * t + 1];
+                const float cx = fmaf(static_cast<float>(lo & kVcandAxisMax), step, -2.0f), cy = fmaf(static_cast<float>((lo >> 13) & kVcandAxisMax), step, -2.0f),
+                            cz = fmaf(static_cast<float>(((lo >> 26) | (hi << 6)) & kVcandAxisMax), step, -2.0f);
+                const float dx = cx - fx, dy = cy - fy, dz = cz - fz;
+                float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                dd = (idx >= first && idx < end) ? dd : kInf;
+                s2 = fminf(s2, fmaxf(dd, m));
+                mv = (dd < m) ? (hi >> 7) : mv;
+                m = fminf(m, dd);
+            }
+    }
+    const float sd = sqrtf(m) + 1.2e-3f;
+    if (s2 > sd * sd * 1.00001f) return static_cast<int>(mv);  // (false for NaN / inf: those take the exact path)
+    int best = -1;
+    double best_d2 = kDblMax;
+    for (uint32_t i = first; i < end; ++i) {
+        const uint32_t v = static_cast<uint32_t>(__ldg(map.vcand8 + i) >> 39);
+        double mx, my, mz;
+        voxel_mean(map, v, mx, my, mz);
+        const double d2 = sq3_exact(mx - px, my - py, mz - pz);
+        if (d2 < best_d2) { best_d2 = d2; best = static_cast<int>(v); }
+    }
+    return best;
 }
 
 }  // namespace
@@ -690,6 +719,32 @@ __device__ __forceinline__ void linearize_point_pair(const MapView& map, int m, 
         acc[27] += fabs(rx * nx + ry * ny + rz * nz);
         acc[28] += 1.0;
     }
+}
+
+// mean[3] + cov[9] of voxel v: its 128-byte record, six 16-byte loads of ONE line
+__device__ __forceinline__ void load_voxel_record(const MapView& map, uint32_t v, double* rec) {
+    const double2* r = reinterpret_cast<const double2*>(map.vrec + static_cast<size_t>(v) * 16);
+    const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5);
+    rec[0] = r0.x; rec[1] = r0.y; rec[2] = r1.x; rec[3] = r1.y; rec[4] = r2.x; rec[5] = r2.y;
+    rec[6] = r3.x; rec[7] = r3.y; rec[8] = r4.x; rec[9] = r4.y; rec[10] = r5.x; rec[11] = r5.y;
+}
+// one (scan point, voxel record) pair -> accumulators (reg.cpp:171-208); rec = {mean[3], cov[9]}
+__device__ __forceinline__ void linearize_voxel_pair(double* acc, const double* s_Tinv, const double* s_Rinv, double th, double sx, double sy, double sz,
+                                                     const double* rec) {
+    const double mx = rec[0], my = rec[1], mz = rec[2];
+    const double lx = s_Tinv[0] * mx + s_Tinv[1] * my + s_Tinv[2] * mz + s_Tinv[3];
+    const double ly = s_Tinv[4] * mx + s_Tinv[5] * my + s_Tinv[6] * mz + s_Tinv[7];
+    const double lz = s_Tinv[8] * mx + s_Tinv[9] * my + s_Tinv[10] * mz + s_Tinv[11];
+    const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
+    const double r2 = rx * rx + ry * ry + rz * rz;
+    const double den = th + r2;
+    const double w = (th * th) / (den * den);  // reg.cpp:199
+    acc[28] += 1.0;                            // the pair counts in the denominator either way (Q7)
+    if (w < 0.01) return;                      // reg.cpp:201
+    double M[9];
+    mahalanobis_local(s_Rinv, rec + 3, M);
+    acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
+    acc[27] += sqrt(r2);  // reg.cpp:207
 }
 
 // Block tree over per-lane accumulators: warp shuffles, then the 8 warps in fixed order; thread k < 29 ADDS the block's
@@ -1635,6 +1690,173 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
     publish_partials(s_sum, prm, wk.partials, static_cast<int>(blockIdx.x));
 }
 
+// ---- ONE kernel per warm iteration (every warm iteration but the first of a call) ------------------------------------
+// The pair above costs two launches and two grid drains per iteration, and its second kernel is a pure latency chain (wait
+// for the first grid, state, work-list counts, a handful of stragglers, fold, ticket, final reduction, solve: ~20 us for
+// ~0.1 % of the queries).  Here the warp that owns a straggler refreshes it on the spot, cooperatively (warm_refresh_warp,
+// three dependent round trips; an out-of-line call would keep the spills out of the REUSE path, but ptxas 12.9 crashes on it); the block then
+// reduces and the last block of THIS grid sums the rows, all-reduces over the ranks and solves.
+__device__ __forceinline__ void warm_refresh_warp_call(const MapView& map, float4* cand, uint32_t ccap, double warm_margin, int q, double px, double py, double pz,
+                                                    uint4 m0, float4 prev, bool same_key, size_t cbase, unsigned int* s_run, WarmRefresh* out) {
+    warm_refresh_warp(map, cand, ccap, warm_margin, q, px, py, pz, m0, prev, same_key, cbase, s_run, out);
+}
+__device__ __forceinline__ void warm_refresh_call(const MapView& map, float4* out_cand, uint32_t ccap, double warm_margin, uint4 m0, float4 prev, bool same_key,
+                                               double px, double py, double pz, WarmRefresh* out) {
+    warm_refresh(map, out_cand, ccap, warm_margin, m0, prev, same_key, px, py, pz, out);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kIcpThreads, METHOD == 1 ? 3 : 4)
+icp_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int solve_here) {
+    constexpr int NACC = AccSize<METHOD>::value;
+    __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
+    __shared__ double s_red[kIcpWarps][kAcc], s_sum[kAcc], s_acc[kAcc];
+    __shared__ SolveScratch s_solve;
+    __shared__ bool s_last;
+    __shared__ int s_done;
+    __shared__ unsigned int s_run[kIcpWarps][64];
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float kInf = __int_as_float(0x7f800000);
+    uint4* const memo0 = wk.memo;
+    uint4* const memo1 = wk.memo + wk.memo_stride;
+    const uint32_t ccap = static_cast<uint32_t>(wk.cand_cap);
+    uint32_t visited = 0, searched = 0, refreshed = 0;
+    int gi = blockIdx.x * kIcpThreads + tid;
+    float sxf = 0.f, syf = 0.f, szf = 0.f;
+    if (gi < prm.n) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
+    pdl_wait();
+    uint4 m0 = make_uint4(kNone, kNone, kNone, kNone), m1 = make_uint4(0, 0, 0, 0);
+    uint32_t nc = kNone;
+    float4 prev = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
+    if (gi < prm.n) { m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi]; }
+    if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
+    if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+    if (tid < kAcc) s_sum[tid] = 0.0;
+    if (tid == 0) s_done = st->done;
+    __syncthreads();
+    if (s_done) return;  // loop already left (termination / overlap failure)
+    for (bool first = true; gi - tid < prm.n; gi += gridDim.x * kIcpThreads, first = false) {
+        const bool mine = gi < prm.n;
+        if (mine && !first) {
+            m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi];
+            sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2];
+        }
+        const size_t cbase = static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
+        constexpr size_t cstride = kIcpThreads;
+        const double sx = sxf, sy = syf, sz = szf;
+        const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+        uint32_t qkey_lo = kNone, qkey_hi = kNone;
+        bool same_key = false, refresh = false;
+        int my_match = -1;
+        float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));  // the matched point {x, y, z, index}
+        if (mine) {
+            const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
+            ++searched;
+            const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
+            if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
+            same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
+            bool reuse = false;  // REUSE: same key and  d' + |q - q0| <= R  (see icp_warm_reuse_kernel)
+            if (same_key && m0.w != kNone && nc <= ccap) {
+                const double d2_prev = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
+                const float dx = static_cast<float>(px - static_cast<double>(__uint_as_float(m1.x))), dy = static_cast<float>(py - static_cast<double>(__uint_as_float(m1.y))),
+                            dz = static_cast<float>(pz - static_cast<double>(__uint_as_float(m1.z)));
+                const float delta = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f + 1e-30f;
+                const float room = (__uint_as_float(m1.w) - delta) * 0.999999f;
+                reuse = room > 0.f && d2_prev <= static_cast<double>(room) * static_cast<double>(room);
+            }
+            if (reuse) {
+                const float4* const my_cand = wk.cand + cbase;
+                const Query Q(px, py, pz);
+                float m = kInf, s2 = kInf;
+                uint32_t mj = 0;
+                for (uint32_t j = 0; j < nc; j += 4) {
+                    float4 c[4];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) c[u] = my_cand[static_cast<size_t>(min(j + u, nc - 1)) * cstride];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        const float dx = c[u].x - Q.fx, dy = c[u].y - Q.fy, dz = c[u].z - Q.fz;
+                        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        d = (j + u < nc) ? d : kInf;
+                        s2 = fminf(s2, fmaxf(d, m)); mj = (d < m) ? j + u : mj; m = fminf(m, d);
+                    }
+                }
+                visited += nc;
+                const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);
+                const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
+                if (s2 > T) {
+                    wpt = my_cand[static_cast<size_t>(mj) * cstride];
+                } else {
+                    Best b;
+                    for (uint32_t j = 0; j < nc; ++j) {
+                        const float4 c = my_cand[static_cast<size_t>(j) * cstride];
+                        const double d2 = sq3_exact(static_cast<double>(c.x) - px, static_cast<double>(c.y) - py, static_cast<double>(c.z) - pz);
+                        const uint32_t rank = __float_as_uint(__ldg(map.pts + __float_as_uint(c.w)).w);
+                        if (closer(d2, rank, b)) { b.d2 = d2; b.rank = rank; b.idx = __float_as_uint(c.w); wpt = c; }
+                    }
+                }
+                my_match = static_cast<int>(__float_as_uint(wpt.w));
+            } else if (same_key && static_cast<int>(m0.x) < 0) {
+                // same voxel as last time and its 27-neighbourhood holds no point: still nothing to find (Q2 applies below)
+            } else {
+                refresh = true;
+                ++refreshed;
+            }
+        }
+        // stragglers: a few per warp -> one after the other by the whole warp; many (the pose jumped) -> every lane its own
+        uint32_t row_new = m0.x;
+        uint32_t rmask = __ballot_sync(kFull, refresh);
+        if (rmask) {
+            WarmRefresh r;
+            bool have = false;
+            if (__popc(rmask) <= 6) {
+                while (rmask) {
+                    const int q = __ffs(rmask) - 1;
+                    rmask &= rmask - 1;
+                    WarmRefresh t;
+                    warm_refresh_warp_call(map, wk.cand, ccap, prm.warm_margin, q, px, py, pz, m0, prev, same_key, cbase, s_run[warp], &t);
+                    if (lane == q) { r = t; have = true; }
+                    __syncwarp();
+                }
+            } else if (refresh) {
+                warm_refresh_call(map, wk.cand + cbase, ccap, prm.warm_margin, m0, prev, same_key, px, py, pz, &r);
+                have = true;
+            }
+            if (have) {
+                my_match = r.b.idx != kNone ? static_cast<int>(r.b.idx) : -1;
+                wpt = r.wpt;
+                row_new = static_cast<uint32_t>(r.row);
+                memo1[gi] = make_uint4(__float_as_uint(static_cast<float>(px)), __float_as_uint(static_cast<float>(py)), __float_as_uint(static_cast<float>(pz)), __float_as_uint(r.Rf));
+                wk.ncand[gi] = r.n_new;
+            }
+        }
+        double acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+        if (mine) {
+            if (wk.match) wk.match[gi] = my_match;
+            wk.win[gi] = wpt;
+            memo0[gi] = make_uint4(row_new, qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+            linearize_point_pair<METHOD>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+        }
+        block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);
+    }
+    if (prm.stats) {
+        for (int o = 16; o > 0; o >>= 1) {
+            visited += __shfl_xor_sync(kFull, visited, o); searched += __shfl_xor_sync(kFull, searched, o); refreshed += __shfl_xor_sync(kFull, refreshed, o);
+        }
+        if (lane == 0 && searched) {
+            atomicAdd(prm.stats, static_cast<unsigned long long>(visited));
+            atomicAdd(prm.stats + 1, static_cast<unsigned long long>(searched));
+            atomicAdd(prm.stats + 20, static_cast<unsigned long long>(refreshed));
+            atomicAdd(prm.stats + 21, static_cast<unsigned long long>(searched));
+        }
+    }
+    finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here);
+}
+
 // rows_before = rows of `partials` the reuse kernel published (its grid size)
 template <int METHOD>
 __global__ void __launch_bounds__(kIcpThreads, 2)
@@ -1742,13 +1964,12 @@ icp_search_means_kernel(MapView map, const float* __restrict__ scan, const int* 
     for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
         const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
         const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-        const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
-        match[orig ? orig[i] : i] = nearest_mean_27(map, px, py, pz, kx, ky, kz);
+        match[orig ? orig[i] : i] = nearest_mean_27(map, px, py, pz);
     }
 }
 
 
-// One thread per scan point (8 threads per point for AVGICP).  partials[gridDim.x][kAcc]; the last block to finish
+// One thread per scan point.  partials[gridDim.x][kAcc]; the last block to finish
 // sums them in a fixed order into st->acc and, when `solve_here`, runs the solve/update step.
 template <int METHOD>
 __global__ void __launch_bounds__(kIcpThreads, 2)
@@ -1779,65 +2000,19 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
 
-    // one (scan point, voxel record) pair -> accumulators   (reg.cpp:171-208)
-    auto linearize_voxel_pair = [&](double sx, double sy, double sz, int slot, double mx, double my, double mz) {
-        double C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        if (slot >= 0) {
-            const double2* r = reinterpret_cast<const double2*>(map.vcov + static_cast<size_t>(slot) * 12);
-            const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
-            const double c8 = __ldg(map.vcov + static_cast<size_t>(slot) * 12 + 8);
-            C[0] = r0.x; C[1] = r0.y; C[2] = r1.x; C[3] = r1.y; C[4] = r2.x; C[5] = r2.y; C[6] = r3.x; C[7] = r3.y; C[8] = c8;
-        }
-        const double lx = s_Tinv[0] * mx + s_Tinv[1] * my + s_Tinv[2] * mz + s_Tinv[3];
-        const double ly = s_Tinv[4] * mx + s_Tinv[5] * my + s_Tinv[6] * mz + s_Tinv[7];
-        const double lz = s_Tinv[8] * mx + s_Tinv[9] * my + s_Tinv[10] * mz + s_Tinv[11];
-        const double rx = lx - sx, ry = ly - sy, rz = lz - sz;
-        const double r2 = rx * rx + ry * ry + rz * rz;
-        const double den = prm.th + r2;
-        const double w = (prm.th * prm.th) / (den * den);  // reg.cpp:199
-        acc[28] += 1.0;                                      // the pair counts in the denominator either way (Q7)
-        if (w < 0.01) return;                                // reg.cpp:201
-        double M[9];
-        mahalanobis_local(s_Rinv, C, M);
-        acc_mahalanobis(acc, M, sx, sy, sz, rx, ry, rz, w);
-        acc[27] += sqrt(r2);  // reg.cpp:207
-    };
-
-    if (METHOD == 3) {
-        // AVGICP: 8 lanes per scan point; lane j < 7 owns voxel j of {c, +x, -x, +y, -y, +z, -z} (vhm.cpp:224-230)
-        const long long total = static_cast<long long>(prm.n) * 8;
-        for (long long t = static_cast<long long>(blockIdx.x) * kIcpThreads + tid; t < total; t += static_cast<long long>(gridDim.x) * kIcpThreads) {
-            const int i = static_cast<int>(t >> 3), j = static_cast<int>(t & 7);
-            if (j == 7) continue;
-            const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
-            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
-            uint2 centre;
-            const int row = dir_lookup(map, kx, ky, kz, centre);  // (the 8 lanes of a point read the same two sectors)
-            if (row < 0) continue;
-            const int slot = neighbour7_slot(map, row, j);
-            if (slot < 0) continue;
-            double mx, my, mz;
-            slot_mean(map, slot, mx, my, mz);
-            if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_voxel_pair(sx, sy, sz, slot, mx, my, mz);  // vhm.cpp:183
-        }
-    } else {
-        for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
-            const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
-            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
-            const int m = (METHOD == 0) ? 0 : match[i];  // (P2P needs only the streamed target)
-            if (METHOD == 2) {
-                double mx = 0.0, my = 0.0, mz = 0.0;  // default CovStruct (I, 0)  (Q2, vhm.cpp:104)
-                if (m >= 0) {
-                    const double2 a = __ldg(reinterpret_cast<const double2*>(map.vslots + m));
-                    const double2 b = __ldg(reinterpret_cast<const double2*>(map.vslots + m) + 1);
-                    mx = a.y; my = b.x; mz = b.y;
-                }
-                if (sq3_exact(mx - px, my - py, mz - pz) < prm.max_dist2) linearize_voxel_pair(sx, sy, sz, m, mx, my, mz);  // vhm.cpp:129
-            } else {
-                const float4 target = __ldg(win + i);  // coalesced: the search wrote the matched point itself
-                linearize_point_pair<METHOD == 1 ? 1 : 0>(map, m, target, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
-            }
+    static_assert(METHOD != 3, "AVGICP has its own kernel (icp_avgicp_kernel)");
+    for (int i = blockIdx.x * kIcpThreads + tid; i < prm.n; i += gridDim.x * kIcpThreads) {
+        const double sx = scan[3 * static_cast<size_t>(i)], sy = scan[3 * static_cast<size_t>(i) + 1], sz = scan[3 * static_cast<size_t>(i) + 2];
+        const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+        const int m = (METHOD == 0) ? 0 : match[i];  // (P2P needs only the streamed target)
+        if (METHOD == 2) {
+            double rec[12] = {0.0, 0.0, 0.0, 1, 0, 0, 0, 1, 0, 0, 0, 1};  // default CovStruct (mean 0, cov I)  (Q2, vhm.cpp:104)
+            if (m >= 0) load_voxel_record(map, static_cast<uint32_t>(m), rec);
+            if (sq3_exact(rec[0] - px, rec[1] - py, rec[2] - pz) < prm.max_dist2)  // vhm.cpp:129
+                linearize_voxel_pair(acc, s_Tinv, s_Rinv, prm.th, sx, sy, sz, rec);
+        } else {
+            const float4 target = __ldg(win + i);  // coalesced: the search wrote the matched point itself
+            linearize_point_pair<METHOD == 1 ? 1 : 0>(map, m, target, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
         }
     }
 
@@ -1848,6 +2023,88 @@ icp_accumulate_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
     block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);
     ELM_ATICK(11);
     finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, partials, ticket, solve_here);
+}
+
+// ======================================================================================================================
+// AVGICP: GetCorrespondencesAllCov (vhm.cpp:153-206) + AlignCloudsLocalVoxelCov (reg.cpp:154-225) in one kernel
+// ======================================================================================================================
+// A warp takes 32 scan points at a time.
+//   1  lane = POINT: transform, key, ONE directory lookup (two 32-byte buckets), the entry's 32-byte dir7 row = the voxel indices
+//      of {centre, +x, -x, +y, -y, +z, -z} (vhm.cpp:224-230); the point (exact fp64 position + source coordinates) goes to
+//      shared memory, its non-empty voxels are appended to the warp's pair list (ballot-free prefix over the lanes);
+//   2  lane = PAIR: the warp's (point, voxel) pairs — 4.8 per point on the bench map, up to 224 — are shared out round-robin,
+//      so every lane linearises the same number of pairs (before: 8 lanes per point, each repeating the transform and the
+//      lookup, 7 of 8 lanes loading, idle lanes for every empty voxel).  A pair reads ONE 128-byte line (mean + covariance),
+//      applies the distance gate on the exact mean (vhm.cpp:183) and accumulates.
+// The emission order of the reference (voxel order per point) only matters for the summation order, which is compared with
+// a tolerance; the per-lane assignment is fixed, so results are bit-reproducible from run to run.
+__global__ void __launch_bounds__(kIcpThreads, 2)
+icp_avgicp_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int solve_here) {
+    constexpr int NACC = 29;
+    __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
+    __shared__ double s_red[kIcpWarps][kAcc], s_sum[kAcc], s_acc[kAcc];
+    __shared__ SolveScratch s_solve;
+    __shared__ bool s_last;
+    __shared__ double s_p[kIcpWarps][32][3];
+    __shared__ float s_s[kIcpWarps][32][3];
+    __shared__ uint32_t s_pair[kIcpWarps][7 * 32];  // lane << 25 | voxel index
+    pdl_launch_dependents();
+    pdl_wait();
+    if (st->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
+    if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+    if (tid < kAcc) s_sum[tid] = 0.0;
+    __syncthreads();
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    for (long long base = (static_cast<long long>(blockIdx.x) * kIcpWarps + warp) * 32; base < prm.n; base += static_cast<long long>(gridDim.x) * kIcpThreads) {
+        const long long i = base + lane;
+        int vox[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        if (i < prm.n) {
+            const float sxf = scan[3 * static_cast<size_t>(i)], syf = scan[3 * static_cast<size_t>(i) + 1], szf = scan[3 * static_cast<size_t>(i) + 2];
+            const double sx = sxf, sy = syf, sz = szf;
+            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+            s_p[warp][lane][0] = px; s_p[warp][lane][1] = py; s_p[warp][lane][2] = pz;
+            s_s[warp][lane][0] = sxf; s_s[warp][lane][1] = syf; s_s[warp][lane][2] = szf;
+            const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
+            uint2 centre;
+            const int row = dir_lookup(map, kx, ky, kz, centre);
+            if (row >= 0)
+                asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                    : "=r"(vox[0]), "=r"(vox[1]), "=r"(vox[2]), "=r"(vox[3]), "=r"(vox[4]), "=r"(vox[5]), "=r"(vox[6]), "=r"(vox[7])
+                    : "l"(map.dir7 + static_cast<size_t>(row) * 8));
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) cnt += vox[j] >= 0 ? 1 : 0;
+        int off = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, off, o);
+            if (lane >= o) off += v;
+        }
+        const int total = __shfl_sync(kFull, off, 31);
+        off -= cnt;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (vox[j] >= 0) s_pair[warp][off++] = (static_cast<uint32_t>(lane) << 25) | static_cast<uint32_t>(vox[j]);
+        __syncwarp();
+        for (int t = lane; t < total; t += 32) {
+            const uint32_t pr = s_pair[warp][t];
+            const int l = static_cast<int>(pr >> 25);
+            double rec[12];
+            load_voxel_record(map, pr & 0x1ffffffu, rec);
+            const double px = s_p[warp][l][0], py = s_p[warp][l][1], pz = s_p[warp][l][2];
+            if (sq3_exact(rec[0] - px, rec[1] - py, rec[2] - pz) < prm.max_dist2)  // vhm.cpp:183
+                linearize_voxel_pair(acc, s_Tinv, s_Rinv, prm.th, static_cast<double>(s_s[warp][l][0]), static_cast<double>(s_s[warp][l][1]),
+                                     static_cast<double>(s_s[warp][l][2]), rec);
+        }
+        __syncwarp();
+    }
+    block_sum_into<NACC, false>(acc, s_red, s_sum);
+    finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here);
 }
 
 // ======================================================================================================================
@@ -1892,10 +2149,10 @@ icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __rest
         uint2 centre;
         const int row = dir_lookup(map, kx, ky, kz, centre);
         for (int j = 0; j < 7 && row >= 0; ++j) {
-            const int slot = neighbour7_slot(map, row, j);
+            const int slot = __ldg(map.dir7 + static_cast<size_t>(row) * 8 + j);
             if (slot < 0) continue;
             double mx, my, mz;
-            slot_mean(map, slot, mx, my, mz);
+            voxel_mean(map, static_cast<uint32_t>(slot), mx, my, mz);
             if (sq3_exact(mx - px, my - py, mz - pz) < max_dist2) { t[3 * c] = mx; t[3 * c + 1] = my; t[3 * c + 2] = mz; ++c; }
         }
         count[i] = c;
@@ -1909,7 +2166,7 @@ icp_export_kernel(MapView map, const float* __restrict__ scan, const int* __rest
     const int m = match[i];
     double tx = 0.0, ty = 0.0, tz = 0.0;  // Q2 default
     if (m >= 0) {
-        if (method == 2) { const double4 vm = map.vslots[m]; tx = vm.y; ty = vm.z; tz = vm.w; }
+        if (method == 2) voxel_mean(map, static_cast<uint32_t>(m), tx, ty, tz);
         else { const float4 t = map.pts[m]; tx = t.x; ty = t.y; tz = t.z; }
     }
     const bool ok = sq3_exact(tx - px, ty - py, tz - pz) < max_dist2;
@@ -1951,7 +2208,7 @@ int icp_search_grid(const IcpParams& prm, int num_sms) {
 }
 
 int icp_accumulate_grid(const IcpParams& prm, int num_sms) {
-    const long long threads = (prm.method == 3) ? static_cast<long long>(prm.n) * 8 : prm.n;
+    const long long threads = prm.n;
     long long blocks = (threads + kIcpThreads - 1) / kIcpThreads;
     const int cap = 2 * num_sms;
     return blocks < 1 ? 1 : (blocks > cap ? cap : static_cast<int>(blocks));
@@ -2013,6 +2270,13 @@ cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+cudaError_t launch_icp_warm(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int grid, int solve_here,
+                            cudaStream_t s) {
+    const cudaError_t e = prm.method == 0 ? launch_pdl(icp_warm_kernel<0>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here)
+                                          : launch_pdl(icp_warm_kernel<1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int solve_here,
                                   int grid, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
@@ -2020,7 +2284,7 @@ cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const I
         case 0: e = launch_pdl(icp_accumulate_kernel<0>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
         case 1: e = launch_pdl(icp_accumulate_kernel<1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
         case 2: e = launch_pdl(icp_accumulate_kernel<2>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
-        default: e = launch_pdl(icp_accumulate_kernel<3>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
+        default: e = launch_pdl(icp_avgicp_kernel, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here); break;
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }

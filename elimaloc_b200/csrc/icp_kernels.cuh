@@ -29,6 +29,9 @@ cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const I
                                   cudaStream_t s);
 cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
                                     int refresh_grid, int solve_here, cudaStream_t s);
+// One warm iteration as ONE launch (stragglers refreshed in place by their own warp); wk.partials needs `grid` rows.
+cudaError_t launch_icp_warm(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int grid, int solve_here,
+                            cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);
 // spatial binning of the scan (scan_sort.cu)
 int scan_bin_bits(int n);

@@ -77,4 +77,28 @@ ELM_HD int axis_half(double q, int32_t c) {
     return q >= mid ? 1 : 0;
 }
 
+
+// ---- VGICP candidate record (8 bytes) ---------------------------------------------------------------------------------
+// The mean of a voxel of an entry's 27-neighbourhood relative to the entry's key, in voxel sizes, lies in (-2, 2) (stored
+// keys truncate toward zero, so the voxel at offset o spans (o - 1, o + 1) at most).  13 bits per axis over [-2, 2]:
+// step 4 / 8191, error <= 2.45e-4 per axis (4.3e-4 on the vector) — the search's fp32 pre-filter keeps a band of 1.2e-3 voxel
+// sizes around the smallest distance and decides anything inside it with the exact fp64 means.  Bits 39..63: voxel index.
+constexpr uint32_t kVcandAxisMax = 8191;
+constexpr uint32_t kVcandVoxelBits = 25;  // voxel indices < 2^25
+ELM_HD uint64_t pack_vcand(double ox, double oy, double oz, uint32_t voxel) {
+    auto q = [](double o) {
+        double t = (o + 2.0) * (kVcandAxisMax / 4.0) + 0.5;
+        t = t < 0.0 ? 0.0 : (t > static_cast<double>(kVcandAxisMax) ? static_cast<double>(kVcandAxisMax) : t);
+        return static_cast<uint64_t>(t);
+    };
+    return q(ox) | (q(oy) << 13) | (q(oz) << 26) | (static_cast<uint64_t>(voxel) << 39);
+}
+ELM_HD void unpack_vcand(uint64_t r, float& ox, float& oy, float& oz, uint32_t& voxel) {
+    const float s = 4.0f / static_cast<float>(kVcandAxisMax);
+    ox = static_cast<float>(static_cast<uint32_t>(r) & kVcandAxisMax) * s - 2.0f;
+    oy = static_cast<float>(static_cast<uint32_t>(r >> 13) & kVcandAxisMax) * s - 2.0f;
+    oz = static_cast<float>(static_cast<uint32_t>(r >> 26) & kVcandAxisMax) * s - 2.0f;
+    voxel = static_cast<uint32_t>(r >> 39);
+}
+
 }  // namespace elm

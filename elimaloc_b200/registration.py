@@ -234,6 +234,12 @@ class Registration:
         check(lib().elm_registration_stats(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def stats_raw(self):
+        """All 32 device counters (see elm_registration_stats_raw)."""
+        buf = (C.c_uint64 * 32)()
+        check(lib().elm_registration_stats_raw(self._h, buf))
+        return [int(v) for v in buf]
+
     def set_fused(self, enable):
         """P2P / GICP: one fused kernel per iteration (default) or search + accumulate as two launches."""
         check(lib().elm_registration_set_fused(self._h, int(bool(enable))))

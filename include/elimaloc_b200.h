@@ -187,6 +187,9 @@ int elm_registration_profile_by_kind(const elm_registration* reg, double ms[6], 
  * read): map points visited and queries searched since the last elm_registration_set_stats call. */
 int elm_registration_set_stats(elm_registration* reg, int enable);
 int elm_registration_stats(elm_registration* reg, uint64_t* map_points_visited, uint64_t* queries);
+/* All 32 counters ([0] candidate points read by the searches, [1] searches, [20] warm searches handed to the refresh kernel,
+ * [21] warm searches; the rest are developer cycle counters of -DELM_PHASE_TIMING builds). */
+int elm_registration_stats_raw(elm_registration* reg, uint64_t counters[32]);
 
 /* P2P / GICP kernel structure.  Default (0): a search kernel (match[] out) followed by an accumulate+reduce+solve kernel.
  * 1: search, linearisation, block/grid reduction and the 6x6 solve in ONE kernel per ICP iteration — same results to
