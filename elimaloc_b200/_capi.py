@@ -59,6 +59,33 @@ class EkfMeasurement(C.Structure):
                 ("rot_cov", C.c_double * 9), ("source", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ImuQueue(C.Structure):
+    """elm_imu_queue"""
+    _fields_ = [("stamp", C.POINTER(C.c_double)), ("gyro", C.POINTER(C.c_double)), ("n", C.c_size_t)]
+
+
+class OdomQueue(C.Structure):
+    """elm_odom_queue"""
+    _fields_ = [("stamp", C.POINTER(C.c_double)), ("pos", C.POINTER(C.c_double)), ("quat_xyzw", C.POINTER(C.c_double)),
+                ("lin_vel", C.POINTER(C.c_double)), ("ang_vel", C.POINTER(C.c_double)), ("n", C.c_size_t)]
+
+
+class ScanPipelineConfig(C.Structure):
+    """elm_scan_pipeline_config"""
+    _fields_ = [("input_max_dist", C.c_double), ("input_voxel_ds_m", C.c_double), ("run_deskew", C.c_int32),
+                ("lidar_scan_time_end", C.c_int32), ("tf_ego_to_lidar", C.c_double * 16)]
+
+
+class ScanResult(C.Structure):
+    """elm_scan_result"""
+    _fields_ = [("T_lidar", C.c_double * 16), ("T_ego", C.c_double * 16), ("fitness_score", C.c_double), ("local_cov", C.c_double * 36),
+                ("pose_cov", C.c_double * 36), ("time_scan_cur", C.c_double), ("time_scan_end", C.c_double)] + \
+               [(n, C.c_int32) for n in ("is_success", "iterations", "n_raw", "n_after_filter", "n_registered", "deskew_ok")]
+
+
+ELM_IMU_QUEUE_LENGTH = 2000
+
+
 class ElmError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"elimaloc_b200 status {status}: {message}")
@@ -120,6 +147,15 @@ SIGNATURES = {
     "elm_ekf_get_state": (C.c_int, [C.c_void_p, C.POINTER(EkfState)]),
     "elm_ekf_set_state": (C.c_int, [C.c_void_p, C.POINTER(EkfState)]),
     "elm_ekf_get_current_state": (C.c_int, [C.c_void_p, _dp]),
+    "elm_deskew_build_tables": (C.c_int, [C.POINTER(ImuQueue), C.POINTER(OdomQueue), C.POINTER(DeskewTables), _dp, C.POINTER(C.c_size_t),
+                                          C.POINTER(C.c_size_t)]),
+    "elm_scan_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(ScanPipelineConfig)]),
+    "elm_scan_pipeline_destroy": (None, [C.c_void_p]),
+    "elm_scan_pipeline_deskew": (C.c_int, [C.c_void_p, _fp, _fp, C.c_size_t, C.c_double, C.POINTER(ImuQueue), C.POINTER(OdomQueue), _dp, _dp, _ip]),
+    "elm_scan_pipeline_register": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.POINTER(RegConfig)]),
+    "elm_scan_pipeline_ekf_update": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "elm_scan_pipeline_fetch": (C.c_int, [C.c_void_p, C.POINTER(ScanResult)]),
+    "elm_ekf_enable_state_ring": (C.c_int, [C.c_void_p, C.c_int]),
     "elm_comm_unique_id": (C.c_int, [_u8p]),
     "elm_registration_set_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
     "elm_registration_peer_export": (C.c_int, [C.c_void_p, _u8p]),

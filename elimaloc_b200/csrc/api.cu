@@ -18,6 +18,7 @@
 #include "../../include/elimaloc_b200.h"
 #include "host_map.hpp"
 #include "deskew.cuh"
+#include "deskew_tables.hpp"
 #include "ekf.cuh"
 #include "icp_kernels.cuh"
 #include "pcd_reader.hpp"
@@ -274,8 +275,11 @@ struct elm_ekf {
     elm_ekf_config cfg{};
     elm_ekf_state* d_state = nullptr;
     elm_ekf_state* h_state = nullptr;  // pinned
+    elm::EkfRing ring{nullptr, nullptr, elm::kEkfRingCap};  // PublishInThread's deque of EgoStates in HBM (optional)
+    bool ring_on = false;
     ~elm_ekf() {
         cudaSetDevice(device);
+        cudaFree(ring.e); cudaFree(ring.meta);
         cudaFree(d_state); cudaFreeHost(h_state);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -539,31 +543,7 @@ int elm_map_export(const elm_map* map, int32_t* keys, int32_t* counts, double* v
 
 int elm_shape_pcm_covariance(const double R_ego[9], const double local_cov[36], double icp_pose_std_m, double pose_cov[36]) try {
     if (!R_ego || !local_cov || !pose_cov) return fail(ELM_ERR_INVALID, "elm_shape_pcm_covariance: bad argument");
-    auto normalize = [](const double* in, double* out) {
-        double scale = 1.0, m = std::fmin(in[0], std::fmin(in[4], in[8]));
-        if (m <= 1e-9) { scale = 1e9; m = std::fmin(in[0] * scale, std::fmin(in[4] * scale, in[8] * scale)); if (m < 1e-9) m = 1e-9; }
-        for (int i = 0; i < 9; ++i) out[i] = std::fmin(in[i] * scale / m, 5.0);
-    };
-    const double sd = std::fmax(icp_pose_std_m, 0.25), ang = sd * 3.14159265358979323846 / 180.0;
-    double t[9], r[9], tn[9], rn[9];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double acc = 0.0;
-            for (int a = 0; a < 3; ++a) {
-                double rc = 0.0;
-                for (int k = 0; k < 3; ++k) rc += R_ego[3 * i + k] * local_cov[6 * k + a];
-                acc += rc * R_ego[3 * j + a];
-            }
-            t[3 * i + j] = acc;
-            r[3 * i + j] = local_cov[6 * (i + 3) + (j + 3)];
-        }
-    normalize(t, tn);
-    normalize(r, rn);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            pose_cov[6 * i + j] = tn[3 * i + j] * sd * sd;
-            pose_cov[6 * (i + 3) + (j + 3)] = rn[3 * i + j] * ang * ang;
-        }
+    elm::shape_pcm_covariance_hd(R_ego, local_cov, icp_pose_std_m, pose_cov);
     return ELM_OK;
 } ELM_API_CATCH
 
@@ -1048,6 +1028,7 @@ int elm_deskew_points_device(elm_registration* reg, const float* d_xyz, const fl
     p.table_stride = reg->dtable_cap;
     p.odom_incre_x = t->odom_incre_x; p.odom_incre_y = t->odom_incre_y; p.odom_incre_z = t->odom_incre_z;
     p.time_scan_cur = t->time_scan_cur; p.time_scan_end = t->time_scan_end;
+    p.n_dev = nullptr; p.rel_time_offset = 0.f; p.run_deskew = 1;
     if (t->imu_available) {
         ELM_CUDA(cudaStreamSynchronize(reg->stream));  // the pinned staging buffer may still feed the previous call
         const double* rows[4] = {t->imu_time, t->imu_rot_x, t->imu_rot_y, t->imu_rot_z};
@@ -1180,6 +1161,7 @@ int elm_ekf_predict_imu(elm_ekf* ekf, double timestamp, const double gyro[3], co
     if (!ekf || !gyro || !acc) return fail(ELM_ERR_INVALID, "elm_ekf_predict_imu: bad argument");
     ELM_CUDA(cudaSetDevice(ekf->device));
     ELM_CUDA(elm::launch_ekf_predict_imu(ekf->d_state, ekf->cfg, timestamp, gyro, acc, ekf->stream));
+    if (ekf->ring_on) ELM_CUDA(elm::launch_ekf_ring_push(ekf->d_state, ekf->ring, ekf->stream));
     return ELM_OK;
 } ELM_API_CATCH
 
@@ -1222,6 +1204,274 @@ int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]) try {
                                  27 * sizeof(double), cudaMemcpyHostToDevice, ekf->stream));
         ELM_CUDA(cudaStreamSynchronize(ekf->stream));
     }
+    return ELM_OK;
+} ELM_API_CATCH
+
+int elm_ekf_enable_state_ring(elm_ekf* ekf, int enable) try {
+    if (!ekf) return fail(ELM_ERR_INVALID, "null ekf");
+    ELM_CUDA(cudaSetDevice(ekf->device));
+    if (enable && !ekf->ring.e) {
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ekf->ring.e), static_cast<size_t>(ekf->ring.cap) * 8 * sizeof(double)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ekf->ring.meta), 2 * sizeof(int)));
+    }
+    if (enable) ELM_CUDA(cudaMemsetAsync(ekf->ring.meta, 0, 2 * sizeof(int), ekf->stream));
+    ekf->ring_on = enable != 0;
+    return ELM_OK;
+} ELM_API_CATCH
+
+// ---- deskew tables (a18) + the device-resident scan chain ------------------------------------------------------------------
+int elm_deskew_build_tables(const elm_imu_queue* imu, const elm_odom_queue* odom, elm_deskew_tables* tables, double* storage,
+                            size_t* imu_drop, size_t* odom_drop) try {
+    if (!imu || !odom || !tables || !storage || (imu->n && (!imu->stamp || !imu->gyro)) ||
+        (odom->n && (!odom->stamp || !odom->pos || !odom->quat_xyzw || !odom->lin_vel || !odom->ang_vel)))
+        return fail(ELM_ERR_INVALID, "elm_deskew_build_tables: bad argument");
+    elm::DeskewTableSet t;
+    t.time_scan_cur = tables->time_scan_cur; t.time_scan_end = tables->time_scan_end;
+    elm::imu_deskew_info(elm::ImuQueueView{imu->stamp, imu->gyro, imu->n}, t, imu_drop);
+    elm::odom_deskew_info(elm::OdomQueueView{odom->stamp, odom->pos, odom->quat_xyzw, odom->lin_vel, odom->ang_vel, odom->n}, t, odom_drop);
+    const size_t L = ELM_IMU_QUEUE_LENGTH;
+    std::memcpy(storage, t.imu_time.data(), L * sizeof(double)); std::memcpy(storage + L, t.imu_rot_x.data(), L * sizeof(double));
+    std::memcpy(storage + 2 * L, t.imu_rot_y.data(), L * sizeof(double)); std::memcpy(storage + 3 * L, t.imu_rot_z.data(), L * sizeof(double));
+    tables->imu_time = storage; tables->imu_rot_x = storage + L; tables->imu_rot_y = storage + 2 * L; tables->imu_rot_z = storage + 3 * L;
+    tables->imu_pointer_cur = t.imu_pointer_cur; tables->imu_available = t.imu_available ? 1 : 0; tables->odom_available = t.odom_available ? 1 : 0;
+    tables->odom_incre_x = t.odom_incre[0]; tables->odom_incre_y = t.odom_incre[1]; tables->odom_incre_z = t.odom_incre[2];
+    return ELM_OK;
+} ELM_API_CATCH
+
+struct elm_scan_pipeline {
+    elm_registration* reg = nullptr;
+    elm_scan_pipeline_config cfg{};
+    double T_lidar_to_ego[16];
+    // device buffers, all sized for the largest raw scan seen
+    float* d_raw = nullptr;     // xyz[3 cap] | time[cap]
+    float* d_flt = nullptr;     // filtered: xyz | time
+    float* d_dsk = nullptr;     // deskewed xyz
+    float* d_ds = nullptr;      // down-sampled xyz (what RunRegister sees)
+    int* d_counts = nullptr;    // [0] after the filter, [1] after the down-sampling
+    int* h_counts = nullptr;    // pinned: counts + the pre-processing error flag
+    size_t cap = 0;
+    elm::DeskewTableSet tables;
+    cudaEvent_t ev_icp = nullptr;
+    // last scan
+    size_t n_raw = 0;
+    int n_filter = 0, n_reg = 0;
+    bool deskewed = false, registered = false;
+    double max_fitness = 0.0;
+    ~elm_scan_pipeline() {
+        if (reg) cudaSetDevice(reg->device);
+        cudaFree(d_raw); cudaFree(d_flt); cudaFree(d_dsk); cudaFree(d_ds); cudaFree(d_counts); cudaFreeHost(h_counts);
+        if (ev_icp) cudaEventDestroy(ev_icp);
+    }
+};
+
+int elm_scan_pipeline_create(elm_scan_pipeline** out, elm_registration* reg, const elm_scan_pipeline_config* cfg) try {
+    if (!out || !reg || !cfg) return fail(ELM_ERR_INVALID, "elm_scan_pipeline_create: bad argument");
+    ELM_CUDA(cudaSetDevice(reg->device));
+    std::unique_ptr<elm_scan_pipeline> p(new (std::nothrow) elm_scan_pipeline());
+    if (!p) return fail(ELM_ERR_INVALID, "out of memory");
+    p->reg = reg;
+    p->cfg = *cfg;
+    {   // tf_ego_to_lidar^-1 (pcm_matching.cpp:298: Matrix4d::inverse(); a rigid transform: cofactor-free closed form would
+        // differ in the last bits, so the general inverse is used here too)
+        const double* m = cfg->tf_ego_to_lidar;
+        double inv[16];
+        const double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];
+        const double s3 = m[1] * m[6] - m[5] * m[2], s4 = m[1] * m[7] - m[5] * m[3], s5 = m[2] * m[7] - m[6] * m[3];
+        const double c5 = m[10] * m[15] - m[14] * m[11], c4 = m[9] * m[15] - m[13] * m[11], c3 = m[9] * m[14] - m[13] * m[10];
+        const double c2 = m[8] * m[15] - m[12] * m[11], c1 = m[8] * m[14] - m[12] * m[10], c0 = m[8] * m[13] - m[12] * m[9];
+        const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+        if (!(std::fabs(det) > 0.0)) return fail(ELM_ERR_INVALID, "elm_scan_pipeline_create: tf_ego_to_lidar is singular");
+        const double id = 1.0 / det;
+        inv[0] = (m[5] * c5 - m[6] * c4 + m[7] * c3) * id;   inv[1] = (-m[1] * c5 + m[2] * c4 - m[3] * c3) * id;
+        inv[2] = (m[13] * s5 - m[14] * s4 + m[15] * s3) * id; inv[3] = (-m[9] * s5 + m[10] * s4 - m[11] * s3) * id;
+        inv[4] = (-m[4] * c5 + m[6] * c2 - m[7] * c1) * id;  inv[5] = (m[0] * c5 - m[2] * c2 + m[3] * c1) * id;
+        inv[6] = (-m[12] * s5 + m[14] * s2 - m[15] * s1) * id; inv[7] = (m[8] * s5 - m[10] * s2 + m[11] * s1) * id;
+        inv[8] = (m[4] * c4 - m[5] * c2 + m[7] * c0) * id;   inv[9] = (-m[0] * c4 + m[1] * c2 - m[3] * c0) * id;
+        inv[10] = (m[12] * s4 - m[13] * s2 + m[15] * s0) * id; inv[11] = (-m[8] * s4 + m[9] * s2 - m[11] * s0) * id;
+        inv[12] = (-m[4] * c3 + m[5] * c1 - m[6] * c0) * id; inv[13] = (m[0] * c3 - m[1] * c1 + m[2] * c0) * id;
+        inv[14] = (-m[12] * s3 + m[13] * s1 - m[14] * s0) * id; inv[15] = (m[8] * s3 - m[9] * s1 + m[10] * s0) * id;
+        std::memcpy(p->T_lidar_to_ego, inv, sizeof inv);
+    }
+    ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_counts), 2 * sizeof(int)));
+    ELM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_counts), 4 * sizeof(int)));
+    ELM_CUDA(cudaEventCreateWithFlags(&p->ev_icp, cudaEventDisableTiming));
+    *out = p.release();
+    return ELM_OK;
+} ELM_API_CATCH
+
+void elm_scan_pipeline_destroy(elm_scan_pipeline* p) { delete p; }
+
+namespace {
+int ensure_prep_scratch(elm_registration* reg, size_t n) {
+    if (n > reg->prep_cap) {
+        cudaFree(reg->prep.tkeys); cudaFree(reg->prep.tmin); cudaFree(reg->prep.keep); cudaFree(reg->prep.block_count); cudaFree(reg->prep.block_offset);
+        int* err = reg->prep.error;
+        reg->prep = elm::ScanPrepScratch{};
+        reg->prep.error = err;
+        reg->prep_cap = 0;
+        const size_t cap = (n + 4095) / 4096 * 4096, slots = elm::scan_prep_table_slots(cap), blocks = (cap + 255) / 256;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.tkeys), slots * sizeof(unsigned long long)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.tmin), slots * sizeof(uint32_t)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.keep), cap));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.block_count), blocks * sizeof(uint32_t)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.block_offset), blocks * sizeof(uint32_t)));
+        reg->prep.table_slots = slots;
+        reg->prep_cap = cap;
+    }
+    if (!reg->prep.error) ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->prep.error), sizeof(int)));
+    return ELM_OK;
+}
+// FilterPointsByDistance's test on the host (pcm_matching.cpp:455-458, float arithmetic like the kernel)
+bool host_passes_distance(const float* q, double max_dist) {
+    if (!(max_dist > 0.0)) return true;
+    const float d = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    return !(static_cast<double>(d) > max_dist);
+}
+}  // namespace
+
+int elm_scan_pipeline_deskew(elm_scan_pipeline* p, const float* xyz, const float* point_time, size_t n, double stamp,
+                             const elm_imu_queue* imu, const elm_odom_queue* odom, double* time_scan_cur, double* time_scan_end,
+                             int32_t* deskew_ok) try {
+    if (!p || !imu || !odom || !deskew_ok || (n && (!xyz || !point_time))) return fail(ELM_ERR_INVALID, "elm_scan_pipeline_deskew: bad argument");
+    if (n > 0x7fffffffull / 8) return fail(ELM_ERR_INVALID, "scan too large");
+    elm_registration* reg = p->reg;
+    *deskew_ok = 0;
+    p->deskewed = p->registered = false;
+    p->n_raw = n;
+    // time base of DeskewPointCloud (:473-486) from the first / last point of the FILTERED cloud
+    size_t first = 0, last = n;
+    while (first < n && !host_passes_distance(xyz + 3 * first, p->cfg.input_max_dist)) ++first;
+    while (last > first && !host_passes_distance(xyz + 3 * (last - 1), p->cfg.input_max_dist)) --last;
+    if (first >= last) return ELM_OK;  // nothing survives the filter
+    elm::DeskewTableSet& t = p->tables;
+    float offset = 0.f;
+    t.time_scan_cur = stamp;
+    t.time_scan_end = stamp + static_cast<double>(point_time[last - 1]);
+    if (p->cfg.lidar_scan_time_end) {
+        const double front_time = static_cast<double>(point_time[first]);
+        t.time_scan_end = stamp;
+        t.time_scan_cur = t.time_scan_end + front_time;
+        offset = point_time[first];
+    }
+    if (time_scan_cur) *time_scan_cur = t.time_scan_cur;
+    if (time_scan_end) *time_scan_end = t.time_scan_end;
+    elm::imu_deskew_info(elm::ImuQueueView{imu->stamp, imu->gyro, imu->n}, t, nullptr);
+    elm::odom_deskew_info(elm::OdomQueueView{odom->stamp, odom->pos, odom->quat_xyzw, odom->lin_vel, odom->ang_vel, odom->n}, t, nullptr);
+    if (!t.imu_available || !t.odom_available) return ELM_OK;  // :493-495 "Deskew fail"
+    ELM_CUDA(cudaSetDevice(reg->device));
+    if (n > p->cap) {
+        cudaFree(p->d_raw); cudaFree(p->d_flt); cudaFree(p->d_dsk); cudaFree(p->d_ds);
+        p->d_raw = p->d_flt = p->d_dsk = p->d_ds = nullptr;
+        p->cap = 0;
+        const size_t cap = (n + 4095) / 4096 * 4096;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_raw), cap * 4 * sizeof(float)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_flt), cap * 4 * sizeof(float)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_dsk), cap * 3 * sizeof(float)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ds), cap * 3 * sizeof(float)));
+        p->cap = cap;
+    }
+    int rc = ensure_prep_scratch(reg, n);
+    if (rc) return rc;
+    // the ONE upload of the scan
+    ELM_CUDA(cudaMemcpyAsync(p->d_raw, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    ELM_CUDA(cudaMemcpyAsync(p->d_raw + 3 * p->cap, point_time, n * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
+    // FilterPointsByDistance: stable compaction, the point times travel along; count -> d_counts[0]
+    ELM_CUDA(elm::launch_scan_prep(p->d_raw, p->d_raw + 3 * p->cap, static_cast<int>(n), p->cfg.input_max_dist, 0.0, reg->prep, p->d_flt, p->d_flt + 3 * p->cap,
+                                   nullptr, p->d_counts, reg->stream));
+    // deskew tables -> device, then the point loop over the survivors (their number is read from HBM)
+    const int entries = t.imu_pointer_cur + 1;
+    if (entries > reg->dtable_cap) {
+        cudaFree(reg->d_dtable); cudaFreeHost(reg->h_dtable);
+        reg->d_dtable = nullptr; reg->h_dtable = nullptr;
+        const int cap = (entries + 255) / 256 * 256;
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&reg->d_dtable), static_cast<size_t>(cap) * 4 * sizeof(double)));
+        ELM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&reg->h_dtable), static_cast<size_t>(cap) * 4 * sizeof(double)));
+        reg->dtable_cap = cap;
+    }
+    elm::DeskewParams dp{};
+    dp.imu_pointer_cur = t.imu_pointer_cur; dp.imu_available = 1; dp.odom_available = 1; dp.table_stride = reg->dtable_cap;
+    dp.odom_incre_x = t.odom_incre[0]; dp.odom_incre_y = t.odom_incre[1]; dp.odom_incre_z = t.odom_incre[2];
+    dp.time_scan_cur = t.time_scan_cur; dp.time_scan_end = t.time_scan_end;
+    dp.n_dev = p->d_counts; dp.rel_time_offset = offset; dp.run_deskew = p->cfg.run_deskew ? 1 : 0;
+    {   // (the pinned staging buffer is rewritten only after the previous scan was fetched: elm_scan_pipeline_fetch synchronises)
+        const double* rows[4] = {t.imu_time.data(), t.imu_rot_x.data(), t.imu_rot_y.data(), t.imu_rot_z.data()};
+        for (int r = 0; r < 4; ++r) std::memcpy(reg->h_dtable + static_cast<size_t>(r) * reg->dtable_cap, rows[r], entries * sizeof(double));
+        ELM_CUDA(cudaMemcpyAsync(reg->d_dtable, reg->h_dtable, static_cast<size_t>(reg->dtable_cap) * 4 * sizeof(double), cudaMemcpyHostToDevice, reg->stream));
+    }
+    ELM_CUDA(elm::launch_deskew_points(p->d_flt, p->d_flt + 3 * p->cap, static_cast<int>(n), dp, reg->d_dtable, p->d_dsk, reg->num_sms, reg->stream));
+    p->deskewed = true;
+    *deskew_ok = 1;
+    return ELM_OK;
+} ELM_API_CATCH
+
+int elm_scan_pipeline_register(elm_scan_pipeline* p, const elm_map* map, const double sync_lidar_pose[16], const elm_reg_config* cfg) try {
+    if (!p || !map || !sync_lidar_pose || !cfg) return fail(ELM_ERR_INVALID, "elm_scan_pipeline_register: bad argument");
+    if (!p->deskewed) return fail(ELM_ERR_STATE, "elm_scan_pipeline_register without a successful elm_scan_pipeline_deskew");
+    elm_registration* reg = p->reg;
+    ELM_CUDA(cudaSetDevice(reg->device));
+    const int n = static_cast<int>(p->n_raw);
+    const float* d_scan = p->d_dsk;
+    const int* d_n = p->d_counts;
+    if (p->cfg.input_voxel_ds_m > 0.0) {  // VoxelDownsample (:256-258) of the survivors, their number read from HBM
+        ELM_CUDA(elm::launch_scan_prep(p->d_dsk, nullptr, n, 0.0, p->cfg.input_voxel_ds_m, reg->prep, p->d_ds, nullptr, nullptr, p->d_counts + 1, reg->stream,
+                                       p->d_counts));
+        d_scan = p->d_ds;
+        d_n = p->d_counts + 1;
+    }
+    // the only read-back before the result: the point counts (the ICP launches are sized on the host)
+    ELM_CUDA(cudaMemcpyAsync(p->h_counts, p->d_counts, sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaMemcpyAsync(p->h_counts + 1, d_n, sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaMemcpyAsync(p->h_counts + 2, reg->prep.error, sizeof(int), cudaMemcpyDeviceToHost, reg->stream));
+    ELM_CUDA(cudaStreamSynchronize(reg->stream));
+    if (p->h_counts[2]) return fail(ELM_ERR_RANGE, "scan point not finite or beyond +-2^20 voxels of the down-sampling grid");
+    p->n_filter = p->h_counts[0];
+    p->n_reg = p->h_counts[1];
+    p->max_fitness = cfg->max_fitness_score;
+    const int rc = elm_register_enqueue(reg, map, d_scan, static_cast<size_t>(p->n_reg), sync_lidar_pose, cfg);
+    if (rc) return rc;
+    ELM_CUDA(cudaEventRecord(p->ev_icp, reg->stream));
+    p->registered = true;
+    return ELM_OK;
+} ELM_API_CATCH
+
+int elm_scan_pipeline_ekf_update(elm_scan_pipeline* p, elm_ekf* ekf) try {
+    if (!p || !ekf) return fail(ELM_ERR_INVALID, "elm_scan_pipeline_ekf_update: bad argument");
+    if (!p->registered) return fail(ELM_ERR_STATE, "elm_scan_pipeline_ekf_update without elm_scan_pipeline_register");
+    if (!ekf->ring_on) return fail(ELM_ERR_STATE, "elm_scan_pipeline_ekf_update needs elm_ekf_enable_state_ring");
+    if (ekf->device != p->reg->device) return fail(ELM_ERR_INVALID, "filter and registration live on different devices");
+    ELM_CUDA(cudaSetDevice(ekf->device));
+    if (ekf->stream != p->reg->stream) ELM_CUDA(cudaStreamWaitEvent(ekf->stream, p->ev_icp, 0));
+    elm::EkfIcpParams ip{};
+    ip.stamp = p->tables.time_scan_end;  // PublishPcmOdom(icp_ego_pose, ros::Time(d_time_scan_end_), ...) :299
+    std::memcpy(ip.T_lidar_to_ego, p->T_lidar_to_ego, sizeof ip.T_lidar_to_ego);
+    ip.max_fitness = p->max_fitness;
+    ip.trivial = p->reg->trivial ? 1 : 0;
+    ELM_CUDA(elm::launch_ekf_update_from_icp(ekf->d_state, ekf->cfg, p->reg->d_state, ip, ekf->ring, ekf->stream));
+    return ELM_OK;
+} ELM_API_CATCH
+
+int elm_scan_pipeline_fetch(elm_scan_pipeline* p, elm_scan_result* out) try {
+    if (!p || !out) return fail(ELM_ERR_INVALID, "elm_scan_pipeline_fetch: bad argument");
+    if (!p->registered) return fail(ELM_ERR_STATE, "elm_scan_pipeline_fetch without elm_scan_pipeline_register");
+    std::memset(out, 0, sizeof *out);
+    int32_t ok = 0, it = 0;
+    double fit = 0.0;
+    const int rc = elm_register_fetch(p->reg, out->T_lidar, &ok, &fit, out->local_cov, &it);
+    if (rc) return rc;
+    out->is_success = ok; out->iterations = it; out->fitness_score = fit;
+    out->n_raw = static_cast<int32_t>(p->n_raw); out->n_after_filter = p->n_filter; out->n_registered = p->n_reg; out->deskew_ok = 1;
+    out->time_scan_cur = p->tables.time_scan_cur; out->time_scan_end = p->tables.time_scan_end;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double a = 0.0;
+            for (int k = 0; k < 4; ++k) a += out->T_lidar[4 * i + k] * p->T_lidar_to_ego[4 * k + j];
+            out->T_ego[4 * i + j] = a;
+        }
+    if (ok) {
+        const double R[9] = {out->T_ego[0], out->T_ego[1], out->T_ego[2], out->T_ego[4], out->T_ego[5], out->T_ego[6], out->T_ego[8], out->T_ego[9], out->T_ego[10]};
+        elm::shape_pcm_covariance_hd(R, out->local_cov, fit, out->pose_cov);
+    }
+    p->registered = false;
     return ELM_OK;
 } ELM_API_CATCH
 

@@ -34,13 +34,14 @@ __global__ void __launch_bounds__(256) deskew_points_kernel(const float* __restr
         t_time = s_time; t_rx = s_rx; t_ry = s_ry; t_rz = s_rz;
     }
     const int cur = p.imu_pointer_cur;
+    if (p.n_dev) n = min(n, *p.n_dev);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float x = xyz[3 * static_cast<size_t>(i)], y = xyz[3 * static_cast<size_t>(i) + 1], z = xyz[3 * static_cast<size_t>(i) + 2];
-        if (!p.imu_available) {  // :781
+        if (!p.imu_available || !p.run_deskew) {  // :781, :512-525
             out[3 * static_cast<size_t>(i)] = x; out[3 * static_cast<size_t>(i) + 1] = y; out[3 * static_cast<size_t>(i) + 2] = z;
             continue;
         }
-        const double d_rel_time = static_cast<double>(rel_time[i]);
+        const double d_rel_time = static_cast<double>(__fsub_rn(rel_time[i], p.rel_time_offset));  // (time -= front_time, :485)
         const double d_point_time = p.time_scan_cur + d_rel_time;  // :783
         const float rx_end = static_cast<float>(t_rx[cur]), ry_end = static_cast<float>(t_ry[cur]), rz_end = static_cast<float>(t_rz[cur]);
         // FindRotation: first table entry later than the point (linear scan like the reference; the table is short)

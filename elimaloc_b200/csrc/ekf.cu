@@ -9,6 +9,8 @@
 // Out of scope (off in config/localization.ini): RunPrediction, RunCanUpdate, ZUPT, NavSat/BESTPOS, CalibrateVehicleToImu.
 #include "ekf.cuh"
 
+#include "icp_device.cuh"
+
 namespace elm {
 
 namespace {
@@ -300,13 +302,20 @@ __global__ void __launch_bounds__(768) ekf_predict_imu_kernel(elm_ekf_state* s, 
     if (c.use_complementary_filter) complementary_filter(s, t, acc_in, sK, sY, sHP, sSinv, &s_flag);  // :204, :312
 }
 
-__global__ void __launch_bounds__(768) ekf_update_pose_kernel(elm_ekf_state* s, elm_ekf_config c, elm_ekf_measurement m) {
-    __shared__ double sK[N * 6], sY[6], sHP[6][N], sS[6][12];
-    __shared__ int s_go, hrow[6];
+// RunGnssUpdate for the PCM / PCM_INIT sources (:318-432) by the whole block; m may live in shared memory.  skip != 0: no update.
+struct UpdateShared {
+    double sK[N * 6], sY[6], sHP[6][N], sS[6][12];
+    int s_go, hrow[6];
+};
+__device__ void update_pose_block(elm_ekf_state* s, const elm_ekf_config& c, const elm_ekf_measurement& m, int skip, UpdateShared& sh) {
+    double* const sK = sh.sK; double* const sY = sh.sY; double (*const sHP)[N] = sh.sHP; double (*const sS)[12] = sh.sS;
+    int& s_go = sh.s_go; int* const hrow = sh.hrow;
     const int tid = threadIdx.x;
     if (tid == 0) {
         s_go = 1;
-        if (m.source == 4) {  // PCM_INIT: hard reset (:324-349)
+        if (skip) {
+            s_go = 0;
+        } else if (m.source == 4) {  // PCM_INIT: hard reset (:324-349)
             for (int k = 0; k < 3; ++k) { s->pos[k] = m.pos[k]; s->vel[k] = s->gyro[k] = s->acc[k] = s->bg[k] = s->ba[k] = s->grav[k] = 0.0; }
             for (int k = 0; k < 4; ++k) s->rot[k] = m.rot[k];
             s->grav[2] = c.imu_gravity;
@@ -347,6 +356,7 @@ __global__ void __launch_bounds__(768) ekf_update_pose_kernel(elm_ekf_state* s, 
         }
     }
     __syncthreads();
+    if (s_go == 0) return;
     if (s_go == 2) {  // covariance part of the PCM_INIT reset: top-left 15 x 15 = 100 I
         if (tid < N * N) {
             const int i = tid / N, j = tid % N;
@@ -364,12 +374,123 @@ __global__ void __launch_bounds__(768) ekf_update_pose_kernel(elm_ekf_state* s, 
     update_block<6>(s, sK, sY, hrow, sHP);  // :427
 }
 
+__global__ void __launch_bounds__(768) ekf_update_pose_kernel(elm_ekf_state* s, elm_ekf_config c, elm_ekf_measurement m) {
+    __shared__ UpdateShared sh;
+    update_pose_block(s, c, m, 0, sh);
+}
+
+// ---- the scan's registration result folded into the filter without a host round trip --------------------------------------
+// What happens between RunRegister and RunGnssUpdate in the two ROS nodes, on the IcpState that still sits in HBM:
+//   pcm_matching.cpp:283-299   success gate, icp_ego_pose = icp_lidar_pose * tf_ego_to_lidar^-1
+//   PublishPcmOdom :1047-1101  position, Quaterniond(rotation), covariance shaping (NormalizeCovariance, pcm_matching.hpp:247-273)
+//   CallbackPcmOdom            ekf_localization.cpp:147-179 (the two 3 x 3 blocks of the message covariance)
+//   GnssTimeCompensation       ekf_localization.cpp:323-394 against the ring of EgoStates the prediction kernel's companion
+//                              (ekf_ring_push_kernel = PublishInThread's deque, :398-410) keeps in HBM
+//   RunGnssUpdate (PCM)        ekf_algorithm.cpp:318-432
+__device__ double angle_diff(double ref, double rel) {  // lfun.hpp AngleDiffRad
+    double d = rel - ref;
+    while (d > kPi) d -= 2 * kPi;
+    while (d < -kPi) d += 2 * kPi;
+    return d;
+}
+__global__ void __launch_bounds__(768) ekf_update_from_icp_kernel(elm_ekf_state* s, elm_ekf_config c, const IcpState* icp, EkfIcpParams p, EkfRing ring) {
+    __shared__ UpdateShared sh;
+    __shared__ elm_ekf_measurement m;
+    __shared__ int s_skip;
+    if (threadIdx.x == 0) {
+        int skip = 0;
+        // elm_register_fetch's success rule (registration.cpp:352-356, 405-417)
+        if (p.trivial || icp->overlap_fail || icp->fitness > p.max_fitness) skip = 1;
+        if (!skip) {
+            double E[12];  // icp_lidar_pose * tf_ego_to_lidar^-1, rows 0..2
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    double a = 0.0;
+                    for (int k = 0; k < 4; ++k) a += icp->T[4 * i + k] * p.T_lidar_to_ego[4 * k + j];
+                    E[4 * i + j] = a;
+                }
+            const double R[9] = {E[0], E[1], E[2], E[4], E[5], E[6], E[8], E[9], E[10]};
+            const Q4 q = q_from_R(R);
+            double pc[36];
+            for (int i = 0; i < 36; ++i) pc[i] = 0.0;
+            shape_pcm_covariance_hd(R, icp->local_cov, icp->fitness, pc);
+            m.timestamp = p.stamp; m.source = 3; m.reserved = 0;
+            m.pos[0] = E[3]; m.pos[1] = E[7]; m.pos[2] = E[11];
+            m.rot[0] = q.w; m.rot[1] = q.x; m.rot[2] = q.y; m.rot[3] = q.z;
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { m.pos_cov[3 * i + j] = pc[6 * i + j]; m.rot_cov[3 * i + j] = pc[6 * (i + 3) + j + 3]; }
+            // GnssTimeCompensation
+            const int head = ring.meta[0], cnt = ring.meta[1];
+            if (cnt < 1) skip = 1;
+            else {
+                const double* cur = ring.e + 8 * static_cast<size_t>((head + cnt - 1) % ring.cap);
+                const double* front = ring.e + 8 * static_cast<size_t>(head);
+                if (front[0] > m.timestamp) skip = 1;
+                else {
+                    const double* closest = front;
+                    for (int k = 0; k < cnt; ++k) {
+                        const double* st = ring.e + 8 * static_cast<size_t>((head + k) % ring.cap);
+                        closest = st;
+                        if (st[0] > m.timestamp) break;
+                    }
+                    const double gap = cur[0] - m.timestamp;
+                    if (gap > 0.0) {
+                        double d[6] = {0, 0, 0, 0, 0, 0};
+                        if (fabs(cur[0] - closest[0]) > 1e-5) {
+                            const double ratio = gap / (cur[0] - closest[0]);
+                            for (int k = 0; k < 3; ++k) d[k] = (cur[1 + k] - closest[1 + k]) * ratio;
+                            for (int k = 0; k < 3; ++k) d[3 + k] = angle_diff(closest[4 + k], cur[4 + k]) * ratio;
+                        }
+                        m.timestamp = cur[0];
+                        for (int k = 0; k < 3; ++k) m.pos[k] += d[k];
+                        // AngleAxis(yaw, Z) * AngleAxis(pitch, Y) * AngleAxis(roll, X)
+                        const Q4 qz{cos(0.5 * d[5]), 0, 0, sin(0.5 * d[5])}, qy{cos(0.5 * d[4]), 0, sin(0.5 * d[4]), 0}, qx{cos(0.5 * d[3]), sin(0.5 * d[3]), 0, 0};
+                        const Q4 qn = q_unit(q_mul(q, q_mul(q_mul(qz, qy), qx)));
+                        m.rot[0] = qn.w; m.rot[1] = qn.x; m.rot[2] = qn.y; m.rot[3] = qn.z;
+                    }
+                }
+            }
+        }
+        s_skip = skip;
+    }
+    __syncthreads();
+    update_pose_block(s, c, m, s_skip, sh);
+}
+
+// PublishInThread's deque of EgoStates (ekf_localization.cpp:398-410) as a ring in HBM: after every RunPredictionImu the
+// node takes GetCurrentState and appends it unless the stamp did not advance; a stamp that went backwards clears the queue;
+// at most 1000 entries.  Entry = {timestamp, x, y, z, roll, pitch, yaw, 0}.
+__global__ void ekf_ring_push_kernel(elm_ekf_state* s, EkfRing ring) {
+    if (threadIdx.x != 0) return;
+    double ego[26];
+    ekf_current_state(*s, ego);
+    int head = ring.meta[0], cnt = ring.meta[1];
+    const double back_t = cnt > 0 ? ring.e[8 * static_cast<size_t>((head + cnt - 1) % ring.cap)] : 0.0;
+    if (cnt < 1 || back_t + 1e-5 < ego[0]) {
+        if (cnt == ring.cap) head = (head + 1) % ring.cap; else ++cnt;
+        double* e = ring.e + 8 * static_cast<size_t>((head + cnt - 1) % ring.cap);
+        for (int k = 0; k < 7; ++k) e[k] = ego[k];
+        e[7] = 0.0;
+    } else if (back_t > ego[0]) {
+        cnt = 0;
+    }
+    ring.meta[0] = head; ring.meta[1] = cnt;
+}
+
 cudaError_t launch_ekf_predict_imu(elm_ekf_state* s, const elm_ekf_config& c, double t, const double g[3], const double a[3], cudaStream_t st) {
     ekf_predict_imu_kernel<<<1, 768, 0, st>>>(s, c, t, g[0], g[1], g[2], a[0], a[1], a[2]);
     return cudaGetLastError();
 }
 cudaError_t launch_ekf_update_pose(elm_ekf_state* s, const elm_ekf_config& c, const elm_ekf_measurement& m, cudaStream_t st) {
     ekf_update_pose_kernel<<<1, 768, 0, st>>>(s, c, m);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ekf_update_from_icp(elm_ekf_state* s, const elm_ekf_config& c, const IcpState* icp, const EkfIcpParams& p, const EkfRing& ring, cudaStream_t st) {
+    ekf_update_from_icp_kernel<<<1, 768, 0, st>>>(s, c, icp, p, ring);
+    return cudaGetLastError();
+}
+cudaError_t launch_ekf_ring_push(elm_ekf_state* s, const EkfRing& ring, cudaStream_t st) {
+    ekf_ring_push_kernel<<<1, 32, 0, st>>>(s, ring);
     return cudaGetLastError();
 }
 
@@ -403,9 +524,9 @@ void ekf_init_state(const elm_ekf_config& c, elm_ekf_state& s) {  // EkfAlgorith
 
 // EkfAlgorithm::GetCurrentState (ekf_alg.cpp:778-833) on a state blob fetched from the device; returns true when the
 // cached previous EgoState was returned unchanged (delta_time < 1e-6)
-bool ekf_current_state(elm_ekf_state& s, double o[26]) {
+__host__ __device__ bool ekf_current_state(elm_ekf_state& s, double o[26]) {
     const double ts = s.prev_timestamp;
-    if (ts - s.ego_prev_timestamp < 1e-6) { std::memcpy(o, s.ego, 26 * sizeof(double)); return true; }
+    if (ts - s.ego_prev_timestamp < 1e-6) { for (int i = 0; i < 26; ++i) o[i] = s.ego[i]; return true; }
     const double* q = s.rot;
     const double tx = 2 * q[1], ty = 2 * q[2], tz = 2 * q[3];
     const double twx = tx * q[0], twy = ty * q[0], twz = tz * q[0], txx = tx * q[1], txy = ty * q[1], txz = tz * q[1], tyy = ty * q[2], tyz = tz * q[2], tzz = tz * q[3];
@@ -434,7 +555,7 @@ bool ekf_current_state(elm_ekf_state& s, double o[26]) {
     o[16] = std::fabs(o[16]); o[17] = std::fabs(o[17]); o[18] = std::fabs(o[18]);
     o[19] = std::sqrt(Pxx); o[20] = std::sqrt(Pyy); o[21] = std::sqrt(Pzz);
     o[22] = s.P[S_ROLL * N + S_ROLL]; o[23] = s.P[S_PITCH * N + S_PITCH]; o[24] = s.P[S_YAW * N + S_YAW]; o[25] = 0.0;
-    std::memcpy(s.ego, o, 26 * sizeof(double));
+    for (int i = 0; i < 26; ++i) s.ego[i] = o[i];
     s.ego_prev_timestamp = ts;
     return false;
 }

@@ -5,6 +5,8 @@
 //   ProcessVoxelBlock    pcm_matching/include/voxel_hash_map.hpp:195-250
 #include "host_map.hpp"
 
+#include "cov_math.hpp"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -35,50 +37,6 @@ void parallel_for(size_t n, size_t grain, F f) {
     for (auto& x : th) x.join();
 }
 
-// Jacobi rotations on a symmetric 3x3 held as a[6] = {xx, xy, xz, yy, yz, zz}; v = eigenvectors (columns).
-void eig_sym3(const double a_in[6], double w[3], double v[3][3]) {
-    double a[3][3] = {{a_in[0], a_in[1], a_in[2]}, {a_in[1], a_in[3], a_in[4]}, {a_in[2], a_in[4], a_in[5]}};
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
-    static const int pairs[3][2] = {{0, 1}, {0, 2}, {1, 2}};
-    for (int sweep = 0; sweep < 64; ++sweep) {
-        if (a[0][1] == 0.0 && a[0][2] == 0.0 && a[1][2] == 0.0) break;
-        for (const auto& pq : pairs) {
-            const int p = pq[0], q = pq[1];
-            const double apq = a[p][q];
-            if (apq == 0.0) continue;
-            const double tau = (a[q][q] - a[p][p]) / (2.0 * apq);
-            const double t = std::copysign(1.0, tau) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
-            const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
-            for (int k = 0; k < 3; ++k) {
-                const double x = a[k][p], y = a[k][q];
-                a[k][p] = c * x - s * y;
-                a[k][q] = s * x + c * y;
-            }
-            for (int k = 0; k < 3; ++k) {
-                const double x = a[p][k], y = a[q][k];
-                a[p][k] = c * x - s * y;
-                a[q][k] = s * x + c * y;
-            }
-            a[p][q] = a[q][p] = 0.0;
-            for (int k = 0; k < 3; ++k) {
-                const double x = v[k][p], y = v[k][q];
-                v[k][p] = c * x - s * y;
-                v[k][q] = s * x + c * y;
-            }
-        }
-    }
-    w[0] = a[0][0]; w[1] = a[1][1]; w[2] = a[2][2];
-    // ascending, first-of-equals kept in place
-    for (int i = 0; i < 2; ++i) {
-        int k = i;
-        for (int j = i + 1; j < 3; ++j) if (w[j] < w[k]) k = j;
-        if (k != i) {
-            std::swap(w[i], w[k]);
-            for (int r = 0; r < 3; ++r) std::swap(v[r][i], v[r][k]);
-        }
-    }
-}
-
 // mean + sample covariance /(n-1) of a multiset of positions, then the regularisation.
 void mean_cov_regularized(const double* pts, size_t n, double mean[3], double cov_out[9], double normal[3]) {
     double s[3] = {0, 0, 0};
@@ -96,38 +54,7 @@ void mean_cov_regularized(const double* pts, size_t n, double mean[3], double co
 
 }  // namespace
 
-void plane_regularize(const double cov[9], double out[9], double normal[3]) {
-    const double a[6] = {cov[0], 0.5 * (cov[1] + cov[3]), 0.5 * (cov[2] + cov[6]), cov[4], 0.5 * (cov[5] + cov[7]), cov[8]};
-    double w[3], v[3][3];
-    eig_sym3(a, w, v);
-    const double lmax = std::max(std::fabs(w[2]), std::fabs(w[0]));
-    const double tol = 1e-9 * std::max(lmax, 1e-300);
-    double n[3];
-    if (std::fabs(w[2] - w[0]) <= tol) {  // isotropic (or zero): Eigen's JacobiSVD leaves U = I
-        n[0] = 0; n[1] = 0; n[2] = 1;
-    } else if (std::fabs(w[1] - w[0]) <= tol) {  // rank-1-like: null space is a plane -> fixed completion
-        const double u[3] = {v[0][2], v[1][2], v[2][2]};
-        // axis least aligned with u; components within 1e-9 of each other count as tied (lowest axis wins), so that the choice
-        // does not hinge on the last bits of u when the dominant direction is a lattice diagonal
-        constexpr double kAxisTie = 1e-9;
-        int k = 0;
-        double best = std::fabs(u[0]);
-        if (std::fabs(u[1]) < best - kAxisTie) { best = std::fabs(u[1]); k = 1; }
-        if (std::fabs(u[2]) < best - kAxisTie) { best = std::fabs(u[2]); k = 2; }
-        double e[3] = {0, 0, 0};
-        e[k] = 1.0;
-        const double d = u[k];
-        double t[3] = {e[0] - d * u[0], e[1] - d * u[1], e[2] - d * u[2]};
-        const double l = std::sqrt((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]);
-        n[0] = t[0] / l; n[1] = t[1] / l; n[2] = t[2] / l;
-    } else {
-        n[0] = v[0][0]; n[1] = v[1][0]; n[2] = v[2][0];
-    }
-    const double k = 1.0 - 1e-3;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) out[i * 3 + j] = ((i == j) ? 1.0 : 0.0) - k * n[i] * n[j];
-    if (normal) { normal[0] = n[0]; normal[1] = n[1]; normal[2] = n[2]; }
-}
+void plane_regularize(const double cov[9], double out[9], double normal[3]) { plane_regularize_hd(cov, out, normal); }
 
 namespace {
 // ELM_BUILD_TIMING=1: stage times of the host builder on stderr (developer aid)

@@ -43,9 +43,10 @@ __device__ __forceinline__ bool voxel_key_of(float x, float y, float z, double v
 }
 
 __global__ void __launch_bounds__(kPrepThreads)
-prep_mark_kernel(const float* __restrict__ xyz, int n, double max_dist, double voxel_size, unsigned long long* __restrict__ tkeys,
+prep_mark_kernel(const float* __restrict__ xyz, int n, const int* __restrict__ n_dev, double max_dist, double voxel_size, unsigned long long* __restrict__ tkeys,
                  uint32_t* __restrict__ tmin, uint32_t tmask, int* __restrict__ error) {
     const int i = blockIdx.x * kPrepThreads + threadIdx.x;
+    if (n_dev) n = min(n, *n_dev);  // the real length sits in HBM (an earlier compaction's count): n is only its upper bound
     if (i >= n) return;
     const float x = xyz[3 * static_cast<size_t>(i)], y = xyz[3 * static_cast<size_t>(i) + 1], z = xyz[3 * static_cast<size_t>(i) + 2];
     if (!passes_distance(x, y, z, max_dist)) return;
@@ -77,11 +78,12 @@ __device__ __forceinline__ bool survives(const float* __restrict__ xyz, int i, d
 }
 
 __global__ void __launch_bounds__(kPrepThreads)
-prep_select_kernel(const float* __restrict__ xyz, int n, double max_dist, double voxel_size, const unsigned long long* __restrict__ tkeys,
+prep_select_kernel(const float* __restrict__ xyz, int n, const int* __restrict__ n_dev, double max_dist, double voxel_size, const unsigned long long* __restrict__ tkeys,
                    const uint32_t* __restrict__ tmin, uint32_t tmask, uint8_t* __restrict__ keep, uint32_t* __restrict__ block_count) {
     __shared__ uint32_t s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
+    if (n_dev) n = min(n, *n_dev);
     const int i = blockIdx.x * kPrepThreads + threadIdx.x;
     const bool k = i < n && survives(xyz, i, max_dist, voxel_size, tkeys, tmin, tmask);
     if (i < n) keep[i] = k ? 1 : 0;
@@ -121,9 +123,10 @@ __global__ void __launch_bounds__(1024) prep_offsets_kernel(const uint32_t* __re
 }
 
 __global__ void __launch_bounds__(kPrepThreads)
-prep_scatter_kernel(const float* __restrict__ xyz, const float* __restrict__ aux, int n, const uint8_t* __restrict__ keep,
+prep_scatter_kernel(const float* __restrict__ xyz, const float* __restrict__ aux, int n, const int* __restrict__ n_dev, const uint8_t* __restrict__ keep,
                     const uint32_t* __restrict__ block_offset, float* __restrict__ xyz_out, float* __restrict__ aux_out, int* __restrict__ index_out) {
     __shared__ uint32_t s_warp[kPrepThreads / 32];
+    if (n_dev) n = min(n, *n_dev);
     const int i = blockIdx.x * kPrepThreads + threadIdx.x;
     const bool k = i < n && keep[i];
     const uint32_t b = __ballot_sync(0xffffffffu, k);
@@ -150,7 +153,7 @@ size_t scan_prep_table_slots(size_t n) {
 }
 
 cudaError_t launch_scan_prep(const float* xyz, const float* aux, int n, double max_dist, double voxel_size, const ScanPrepScratch& w,
-                             float* xyz_out, float* aux_out, int* index_out, int* n_out, cudaStream_t s) {
+                             float* xyz_out, float* aux_out, int* index_out, int* n_out, cudaStream_t s, const int* n_dev) {
     const int blocks = (n + kPrepThreads - 1) / kPrepThreads;
     cudaError_t e = cudaMemsetAsync(w.error, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
@@ -161,11 +164,11 @@ cudaError_t launch_scan_prep(const float* xyz, const float* aux, int n, double m
         if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(w.tmin, 0xff, w.table_slots * sizeof(uint32_t), s);
         if (e != cudaSuccess) return e;
-        prep_mark_kernel<<<blocks, kPrepThreads, 0, s>>>(xyz, n, max_dist, voxel_size, w.tkeys, w.tmin, tmask, w.error);
+        prep_mark_kernel<<<blocks, kPrepThreads, 0, s>>>(xyz, n, n_dev, max_dist, voxel_size, w.tkeys, w.tmin, tmask, w.error);
     }
-    prep_select_kernel<<<blocks, kPrepThreads, 0, s>>>(xyz, n, max_dist, voxel_size, w.tkeys, w.tmin, tmask, w.keep, w.block_count);
+    prep_select_kernel<<<blocks, kPrepThreads, 0, s>>>(xyz, n, n_dev, max_dist, voxel_size, w.tkeys, w.tmin, tmask, w.keep, w.block_count);
     prep_offsets_kernel<<<1, 1024, 0, s>>>(w.block_count, blocks, w.block_offset, n_out);
-    prep_scatter_kernel<<<blocks, kPrepThreads, 0, s>>>(xyz, aux, n, w.keep, w.block_offset, xyz_out, aux_out, index_out);
+    prep_scatter_kernel<<<blocks, kPrepThreads, 0, s>>>(xyz, aux, n, n_dev, w.keep, w.block_offset, xyz_out, aux_out, index_out);
     return cudaGetLastError();
 }
 

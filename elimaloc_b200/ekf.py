@@ -66,6 +66,10 @@ class EkfAlgorithm:
     def set_state(self, s):
         check(lib().elm_ekf_set_state(self._h, C.byref(s)))
 
+    def enable_state_ring(self, enable=True):
+        """PublishInThread's deque of EgoStates kept in HBM (needed by ScanPipeline.ekf_update)."""
+        check(lib().elm_ekf_enable_state_ring(self._h, int(bool(enable))))
+
     def GetCurrentState(self):
         ego = np.zeros(26)
         check(lib().elm_ekf_get_current_state(self._h, ego.ctypes.data_as(_capi._dp)))

@@ -86,3 +86,39 @@ def timing_knobs():
     """Knobs that force every iteration to run."""
     return dict(icp_termination_threshold_m=0.0, min_overlap_ratio=0.0, max_fitness_score=1e30, lm_lambda=0.5,
                 max_search_dist=5.0, use_radar_cov=0, debug_print=0)
+
+
+class ScanWorld:
+    """BASELINE config 5 stream: constant-twist arc through the map; IMU in the body frame; raw scans with per-point motion
+    distortion (shared by tests/pipeline_harness.py and bench.py --config 5)"""
+
+    def __init__(self, box, n_points, seed=7, radius=8.0, omega=0.25, t0=100.0, height=1.6):
+        self.c = np.array([box / 2 - 4.0, box / 2 - 6.0, height])  # sensor `height` above the ground plane of Map-S
+        self.r, self.w, self.t0, self.n = radius, omega, t0, n_points
+        self.rng = np.random.default_rng(seed)
+
+    def pose(self, t):
+        a = self.w * (t - self.t0)
+        T = np.eye(4)
+        T[:3, :3] = exp_so3([0, 0, a])
+        T[:3, 3] = self.c + self.r * np.array([np.sin(a), 1 - np.cos(a), 0.0])
+        return T
+
+    def imu(self, t):
+        v = self.r * self.w
+        gyro = np.array([0.0, 0.0, self.w]) + self.rng.normal(0, 5e-4, 3)
+        acc = np.array([0.0, v * self.w, 9.81]) + self.rng.normal(0, 5e-3, 3)
+        return gyro, acc
+
+    def scan(self, stored, t_end, span=0.1):
+        Te = self.pose(t_end)
+        near = stored[np.linalg.norm(stored - Te[:3, 3].astype(np.float32), axis=1) < 14.0]
+        idx = self.rng.integers(0, len(near), self.n)
+        tt = np.sort(self.rng.random(self.n)) * span
+        pts = near[idx].astype(np.float64) + self.rng.normal(0, 0.01, (self.n, 3))
+        a = self.w * (t_end - span + tt - self.t0)
+        ca, sa = np.cos(a), np.sin(a)
+        pos = self.c[None, :] + self.r * np.stack([sa, 1 - ca, np.zeros_like(a)], axis=1)
+        d = pts - pos
+        local = np.stack([ca * d[:, 0] + sa * d[:, 1], -sa * d[:, 0] + ca * d[:, 1], d[:, 2]], axis=1)  # R(t)^T (p - pos(t))
+        return local.astype(np.float32), tt.astype(np.float32)

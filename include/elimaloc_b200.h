@@ -308,6 +308,67 @@ int elm_ekf_set_state(elm_ekf* ekf, const elm_ekf_state* in);
  * vx vy vz (local), ax ay az (local), x/y/z_cov_m (local), latitude/longitude/height std, roll/pitch/yaw cov, 0 */
 int elm_ekf_get_current_state(elm_ekf* ekf, double ego[26]);
 
+/* ---- deskew tables + the device-resident scan chain (config 5) --------------------------------------------------- */
+/* The node's two message queues as plain arrays (what PcmMatching keeps in deq_imu_ / deq_odom_):
+ *   IMU       stamp[n], gyro[3 n] = the angular velocity ImuAngular2RosAngular returns (pcm_matching.hpp)
+ *   odometry  stamp[n], position[3 n], orientation (x, y, z, w)[4 n], twist.linear[3 n] (body frame), twist.angular[3 n] */
+typedef struct elm_imu_queue { const double* stamp; const double* gyro; size_t n; } elm_imu_queue;
+typedef struct elm_odom_queue {
+    const double* stamp; const double* pos; const double* quat_xyzw; const double* lin_vel; const double* ang_vel; size_t n;
+} elm_odom_queue;
+#define ELM_IMU_QUEUE_LENGTH 2000 /* pcm_matching.hpp:113 */
+
+/* PcmMatching::ImuDeskewInfo + OdomDeskewInfo (pcm_matching.cpp:533-729) — SURVEY row a18, host arithmetic.  Fills `tables`
+ * (time_scan_cur / time_scan_end must be set by the caller: DeskewPointCloud :473-486); its four table pointers are set to
+ * storage[0 .. 4 * ELM_IMU_QUEUE_LENGTH) (caller-owned).  imu_drop / odom_drop (may be NULL): messages the node pops from the
+ * front of its queues.  Unavailable data is not an error: tables->imu_available / odom_available say so, as the members do. */
+int elm_deskew_build_tables(const elm_imu_queue* imu, const elm_odom_queue* odom, elm_deskew_tables* tables, double* storage,
+                            size_t* imu_drop, size_t* odom_drop);
+
+/* The per-scan chain of PcmMatching::CallbackPointCloud (pcm_matching.cpp:235-299) with the point data resident in HBM from
+ * the raw scan to the pose: ONE upload of the raw scan, then FilterPointsByDistance -> DeskewPointCloud's point loop ->
+ * VoxelDownsample -> RunRegister on the registration's stream; the stages hand their point counts to each other through HBM.
+ * The host reads back 12 bytes (the counts, needed to size the ICP launches) and the 1.2 KB result block.  With an elm_ekf, the
+ * result is folded into the filter by a kernel that reads the IcpState where it lies (elm_scan_pipeline_ekf_update). */
+typedef struct elm_scan_pipeline_config {
+    double input_max_dist;      /* cfg_.d_input_max_dist (FilterPointsByDistance); <= 0: off */
+    double input_voxel_ds_m;    /* cfg_.d_input_voxel_ds_m (VoxelDownsample); <= 0: off */
+    int32_t run_deskew;         /* cfg_.b_run_deskew */
+    int32_t lidar_scan_time_end;/* cfg_.b_lidar_scan_time_end: the message stamp is the scan END, point times are <= 0 */
+    double tf_ego_to_lidar[16]; /* cfg_.tf_ego_to_lidar, row-major */
+} elm_scan_pipeline_config;
+typedef struct elm_scan_result {
+    double T_lidar[16];   /* RunRegister's return value */
+    double T_ego[16];     /* icp_lidar_pose * tf_ego_to_lidar^-1 (pcm_matching.cpp:298) */
+    double fitness_score; /* valid when is_success */
+    double local_cov[36];
+    double pose_cov[36];  /* PublishPcmOdom's covariance blocks (elm_shape_pcm_covariance), valid when is_success */
+    double time_scan_cur, time_scan_end;
+    int32_t is_success, iterations, n_raw, n_after_filter, n_registered, deskew_ok;
+} elm_scan_result;
+typedef struct elm_scan_pipeline elm_scan_pipeline;
+int elm_scan_pipeline_create(elm_scan_pipeline** out, elm_registration* reg, const elm_scan_pipeline_config* cfg);
+void elm_scan_pipeline_destroy(elm_scan_pipeline* p);
+/* Stage 1 (pcm_matching.cpp:235-243, DeskewPointCloud :467-531): uploads the raw scan (xyz[3n], point_time[n] = PointXYZIT::time),
+ * derives the time base from the first / last point that passes the distance filter, builds the deskew tables on the host
+ * (a18) and enqueues filter + deskew.  deskew_ok = 0 (nothing enqueued) when the IMU or odometry data does not cover the scan,
+ * or no point survives the filter — the node drops such a scan.  time_scan_end: what GetInterpolatedPose is asked for next. */
+int elm_scan_pipeline_deskew(elm_scan_pipeline* p, const float* xyz, const float* point_time, size_t n, double stamp,
+                             const elm_imu_queue* imu, const elm_odom_queue* odom, double* time_scan_cur, double* time_scan_end,
+                             int32_t* deskew_ok);
+/* Stage 2 (pcm_matching.cpp:253-282): VoxelDownsample of the deskewed cloud and RunRegister from sync_lidar_pose, enqueued;
+ * returns after reading the point counts (12 bytes). */
+int elm_scan_pipeline_register(elm_scan_pipeline* p, const elm_map* map, const double sync_lidar_pose[16], const elm_reg_config* cfg);
+/* CallbackPcmOdom (ekf_localization.cpp:147-179) + GnssTimeCompensation (:323-394) + RunGnssUpdate, fed from the IcpState in
+ * HBM: success gate, ego pose, PublishPcmOdom's covariance shaping, time compensation against the ring of EgoStates the filter
+ * keeps in HBM (elm_ekf_enable_state_ring), update.  Asynchronous; ordered after the registration by an event. */
+int elm_scan_pipeline_ekf_update(elm_scan_pipeline* p, elm_ekf* ekf);
+/* Synchronises and returns the result of the last elm_scan_pipeline_register. */
+int elm_scan_pipeline_fetch(elm_scan_pipeline* p, elm_scan_result* out);
+/* PublishInThread's deque of EgoStates (ekf_localization.cpp:398-410) kept in HBM: when enabled every elm_ekf_predict_imu is
+ * followed by GetCurrentState + the deque's push rule on the device (1000 entries). */
+int elm_ekf_enable_state_ring(elm_ekf* ekf, int enable);
+
 /* ---- multi-GPU (one process per GPU; scan sharded over ranks, map replicated) --------------------------------- */
 /* unique_id: 128 bytes.  Rank 0 fills it with elm_comm_unique_id and hands it to the other ranks (bench.py uses
  * torch.distributed for that); every rank then calls elm_registration_set_comm.  After that each RunRegister sums the

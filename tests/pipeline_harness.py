@@ -271,42 +271,10 @@ class GpuArm:
 
 
 # ------------------------------------------------------------------------------------------------ world + loop
-class World:
-    """constant-twist arc through the map; IMU in the body frame; raw scans with per-point motion distortion"""
-
-    def __init__(self, box, n_points, seed=7, radius=8.0, omega=0.25, t0=100.0, height=1.6):
-        self.c = np.array([box / 2 - 4.0, box / 2 - 6.0, height])  # sensor `height` above the ground plane of Map-S
-        self.r, self.w, self.t0, self.n = radius, omega, t0, n_points
-        self.rng = np.random.default_rng(seed)
-
-    def pose(self, t):
-        a = self.w * (t - self.t0)
-        T = np.eye(4)
-        T[:3, :3] = synth.exp_so3([0, 0, a])
-        T[:3, 3] = self.c + self.r * np.array([np.sin(a), 1 - np.cos(a), 0.0])
-        return T
-
-    def imu(self, t):
-        v = self.r * self.w
-        gyro = np.array([0.0, 0.0, self.w]) + self.rng.normal(0, 5e-4, 3)
-        acc = np.array([0.0, v * self.w, 9.81]) + self.rng.normal(0, 5e-3, 3)
-        return gyro, acc
-
-    def scan(self, stored, t_end, span=0.1):
-        Te = self.pose(t_end)
-        near = stored[np.linalg.norm(stored - Te[:3, 3].astype(F32), axis=1) < 14.0]
-        idx = self.rng.integers(0, len(near), self.n)
-        tt = np.sort(self.rng.random(self.n)) * span
-        pts = near[idx].astype(np.float64) + self.rng.normal(0, 0.01, (self.n, 3))
-        a = self.w * (t_end - span + tt - self.t0)
-        ca, sa = np.cos(a), np.sin(a)
-        pos = self.c[None, :] + self.r * np.stack([sa, 1 - ca, np.zeros_like(a)], axis=1)
-        d = pts - pos
-        local = np.stack([ca * d[:, 0] + sa * d[:, 1], -sa * d[:, 0] + ca * d[:, 1], d[:, 2]], axis=1)  # R(t)^T (p - pos(t))
-        return local.astype(F32), tt.astype(F32)
+World = synth.ScanWorld  # constant-twist arc through the map; IMU in the body frame; raw scans with per-point motion distortion
 
 
-def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0, input_voxel_ds_m=0.0):
+def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0, input_voxel_ds_m=0.0, input_max_dist=0.0):
     """returns dict of per-scan arrays: icp pose, EKF pose (pos + quaternion) after the update, success flag, fitness.
     scan_offset shifts the scan stamps off the IMU grid (the reference selects odometry with exact `<` on the stamps);
     input_voxel_ds_m > 0 keeps the first point of every voxel of that size before the registration, as the node does
@@ -339,6 +307,9 @@ def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0, input_v
         t_cur = t_end - 0.1
         step_imu(t_end + latency)                                  # the result is applied `latency` after the scan end
         xyz, rel = world.scan(stored, t_end)
+        if input_max_dist > 0.0:                                   # FilterPointsByDistance runs first (pcm_matching.cpp:235)
+            keep = O.scan_preprocess(xyz, input_max_dist, 0.0)
+            xyz, rel = xyz[keep], rel[keep]
         t_scan_end = t_cur + float(rel[-1])                        # d_time_scan_end_ = stamp + time of the last point (pcm.cpp:474)
         st = np.array([x[0] for x in imu_log])
         gy = np.array([x[1] for x in imu_log])
@@ -362,4 +333,61 @@ def run(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0, input_v
             if meas is not None:
                 arm.ekf.RunGnssUpdate(pekf.make_measurement(meas["t"], meas["pos"], meas["quat"], pc, rc, source=pekf.PCM))
         out["ego"].append(arm.ekf_pose())                          # raw filter pose (pos, quaternion) after the update
+    return {k: np.array(v) for k, v in out.items()}
+
+
+class ChainArm(GpuArm):
+    """the product's device-resident scan chain (elm_scan_pipeline_*): tables built by the product, point data never leaves HBM,
+    the EKF update reads the IcpState where it lies"""
+    name = "chain"
+
+    def __init__(self, raw_map, ekf_cfg_kwargs, device=0, input_voxel_ds_m=0.0, input_max_dist=0.0):
+        import elimaloc_b200 as E
+        super().__init__(raw_map, ekf_cfg_kwargs, device)
+        self.ekf.enable_state_ring(True)
+        self.pipe = E.ScanPipeline(self.reg, input_max_dist=input_max_dist, input_voxel_ds_m=input_voxel_ds_m)
+
+
+def run_chain(arm, world, n_scans, imu_dt=0.01, latency=0.03, scan_offset=0.0):
+    """run() with the per-scan work done by ChainArm.pipe: the same event order, the same numpy GetInterpolatedPose; what the
+    stage-wise arms compute on the host (tables, covariance shaping, time compensation) is computed by the product here."""
+    import elimaloc_b200 as E
+    stored = arm.stored()
+    t0 = world.t0
+    T0 = world.pose(t0)
+    arm.ekf.RunGnssUpdate(pekf.make_measurement(t0, T0[:3, 3], R_to_quat_wxyz(T0[:3, :3]), np.eye(3) * 1e-9, np.eye(3) * 1e-9, source=pekf.PCM_INIT))
+    deq_odom, imu_t, imu_g = [], [], []
+    out = dict(icp=[], ego=[], ok=[], fit=[], t=[], n=[])
+    k_imu = 0
+
+    def step_imu(until):
+        nonlocal k_imu
+        while t0 + k_imu * imu_dt <= until + 1e-9:
+            t = t0 + k_imu * imu_dt
+            g, a = world.imu(t)
+            imu_t.append(t)
+            imu_g.append(g)
+            arm.ekf.RunPredictionImu(t, g, a)                      # (+ GetCurrentState and the deque push, on the device)
+            ego = arm.ekf.GetCurrentState()
+            R = rpy_to_R(ego[4], ego[5], ego[6])
+            deq_odom.append(dict(t=ego[0], pos=ego[1:4].copy(), quat=R_to_quat_wxyz(R), vel_local=ego[10:13].copy(), rate=ego[7:10].copy()))
+            k_imu += 1
+
+    for s in range(n_scans):
+        t_end = t0 + 0.1 * (s + 1) + scan_offset
+        t_cur = t_end - 0.1
+        step_imu(t_end + latency)
+        xyz, rel = world.scan(stored, t_end)
+        wxyz = np.array([o["quat"] for o in deq_odom])
+        q = E.Queues(imu_t, np.array(imu_g), [o["t"] for o in deq_odom], np.array([o["pos"] for o in deq_odom]), wxyz[:, [1, 2, 3, 0]],
+                     np.array([o["vel_local"] for o in deq_odom]), np.array([o["rate"] for o in deq_odom]))
+        ok_d, _, t_scan_end = arm.pipe.deskew(xyz, rel, t_cur, q)
+        assert ok_d
+        sync = get_interpolated_pose(deq_odom, t_scan_end)
+        arm.pipe.register(arm.map, sync.astype(np.float64), arm.cfg)
+        arm.pipe.ekf_update(arm.ekf)
+        r = arm.pipe.fetch()
+        out["icp"].append(r["T_lidar"]); out["ok"].append(r["is_success"]); out["fit"].append(r["fitness_score"]); out["t"].append(t_end)
+        out["n"].append(r["n_registered"])
+        out["ego"].append(arm.ekf_pose())
     return {k: np.array(v) for k, v in out.items()}

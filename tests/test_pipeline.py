@@ -62,3 +62,50 @@ def test_gpu_pipeline_matches_oracle_pipeline():
     assert np.abs(rg["ego"][:, :3] - ro["ego"][:, :3]).max() <= 1e-4 * scale
     assert np.abs(rg["ego"][:, 3:] - ro["ego"][:, 3:]).max() <= 1e-4
     assert np.abs(rg["fit"] - ro["fit"]).max() <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ds,max_dist", [(0.0, 0.0), (0.3, 12.5)])
+def test_device_resident_chain_matches_the_stagewise_gpu_arm(ds, max_dist):
+    """elm_scan_pipeline_* (tables built by the product, filter -> deskew -> down-sampling -> RunRegister without the points leaving
+    HBM, EKF update fed from the IcpState on the device incl. covariance shaping and time compensation against the device ring of
+    EgoStates) against the stage-wise GPU arm, whose host glue is the numpy of this harness: same trajectory.  Not bit-equal:
+    the tables come from two implementations (1e-14) and the device evaluates the glue's sin / cos / atan2 itself."""
+    n_scans = 20
+    raw = synth.map_s(GPU_WORLD["m_raw"], GPU_WORLD["box"])
+    a = H.GpuArm(raw, EKF_KW)
+    c = H.ChainArm(raw, EKF_KW, input_voxel_ds_m=ds, input_max_dist=max_dist)
+    ra = H.run(a, H.World(GPU_WORLD["box"], GPU_WORLD["n_points"], seed=GPU_WORLD["seed"]), n_scans, input_voxel_ds_m=ds, input_max_dist=max_dist)
+    rc = H.run_chain(c, H.World(GPU_WORLD["box"], GPU_WORLD["n_points"], seed=GPU_WORLD["seed"]), n_scans)
+    assert np.array_equal(ra["ok"], rc["ok"]) and rc["ok"].all()
+    if ds > 0 or max_dist > 0:
+        assert (rc["n"] < GPU_WORLD["n_points"]).all() and (rc["n"] > 100).all()  # both pre-processing stages really removed points
+    assert np.abs(ra["icp"] - rc["icp"]).max() <= 1e-6
+    assert np.abs(ra["ego"] - rc["ego"]).max() <= 1e-6
+    assert np.abs(ra["fit"] - rc["fit"]).max() <= 1e-7
+
+
+@pytest.mark.gpu
+def test_chain_refuses_what_the_node_refuses():
+    """no IMU / no odometry covering the scan -> deskew_ok = 0 and nothing is registered (pcm_matching.cpp:493-495);
+    register / fetch / ekf_update out of order -> ELM_ERR_STATE"""
+    import elimaloc_b200 as E
+    raw = synth.map_s(50_000, 20.0)
+    arm = H.ChainArm(raw, EKF_KW)
+    xyz = synth.scan_u(2000, 8.0)
+    rel = np.linspace(0, 0.1, 2000).astype(np.float32)
+    empty = E.Queues([], np.zeros((0, 3)), [], np.zeros((0, 3)), np.zeros((0, 4)), np.zeros((0, 3)), np.zeros((0, 3)))
+    assert arm.pipe.deskew(xyz, rel, 100.0, empty)[0] is False
+    with pytest.raises(E.ElmError) as e:
+        arm.pipe.register(arm.map, np.eye(4), arm.cfg)
+    assert e.value.status == E._capi.ELM_ERR_STATE
+    with pytest.raises(E.ElmError):
+        arm.pipe.fetch()
+    # odometry that starts after the scan start: refused as well
+    st = 100.0 + 0.01 * np.arange(-3, 20)
+    late = E.Queues(st, np.zeros((len(st), 3)), st[8:], np.zeros((len(st) - 8, 3)), np.tile([0, 0, 0, 1.0], (len(st) - 8, 1)), np.zeros((len(st) - 8, 3)),
+                    np.zeros((len(st) - 8, 3)))
+    assert arm.pipe.deskew(xyz, rel, 100.0, late)[0] is False
+    full = E.Queues(st, np.zeros((len(st), 3)), st, np.zeros((len(st), 3)), np.tile([0, 0, 0, 1.0], (len(st), 1)), np.zeros((len(st), 3)), np.zeros((len(st), 3)))
+    ok, t_cur, t_end = arm.pipe.deskew(xyz, rel, 100.0, full)
+    assert ok and t_cur == 100.0 and t_end == 100.0 + float(rel[-1])

@@ -4,6 +4,7 @@ the middleware, against the oracle's restatements and the numpy glue of tests/pi
 
   FilterPointsByDistance   pcm_matching.cpp:451-465     vs oracle.scan_preprocess                      identical indices
   ImuDeskewInfo / OdomDeskewInfo  :533-729              vs oracle.deskew_tables                        tables 1e-15 / float increments
+                                                        vs the PRODUCT's builders (elm_deskew_build_tables, a18)       same tolerances
   DeskewPoint over a scan  :499-511, 780-824            vs oracle.deskew_points                        bit-equal on the same tables
   GetInterpolatedPose      :933-1045                    vs pipeline_harness.get_interpolated_pose      float32 rounding
   PublishPcmOdom covariance :1047-1101                  vs oracle.shape_pcm_covariance + the product's host function   1e-12
@@ -71,6 +72,28 @@ def oracle_tables(deq, stamps, gyro, t_cur, t_end):
                            list(e["pos"]) + list(tf_rpy_from_quat(e["quat"])), e["t"])
 
 
+def product_tables(deq, stamps, gyro, t_cur, t_end):
+    """the product's own ImuDeskewInfo / OdomDeskewInfo (elimaloc_b200/csrc/deskew_tables.cpp) on the same queues"""
+    import elimaloc_b200 as E
+    wxyz = np.array([o["quat"] for o in deq]).reshape(-1, 4)
+    q = E.Queues(stamps, np.asarray(gyro).reshape(-1, 3), [o["t"] for o in deq], np.array([o["pos"] for o in deq]).reshape(-1, 3),
+                 wxyz[:, [1, 2, 3, 0]], np.array([o["vel_local"] for o in deq]).reshape(-1, 3), np.array([o["rate"] for o in deq]).reshape(-1, 3))
+    return E.build_deskew_tables(q, t_cur, t_end)
+
+
+def assert_product_tables_equal_the_nodes(pt, tab, ok, incre_tol):
+    assert bool(pt["odom_available"]) == bool(tab["odom_available"])
+    if tab["odom_available"] or tab["imu_available"]:  # (the node leaves the IMU members untouched when it returns early)
+        assert bool(pt["imu_available"]) == bool(tab["imu_available"])
+    assert ok == (pt["imu_available"] and pt["odom_available"])
+    if ok:
+        k = tab["imu_pointer_cur"]
+        assert pt["imu_pointer_cur"] == k
+        for name in ("imu_time", "imu_rot_x", "imu_rot_y", "imu_rot_z"):
+            assert np.abs(pt[name][:k + 1] - tab[name][:k + 1]).max() < 1e-14, name
+        assert np.abs(pt["odom_incre"] - tab["odom_incre"]).max() < incre_tol
+
+
 @pytest.fixture(scope="module")
 def raw_map():
     return synth.map_u(40_000, 16.0, origin=-3.0)
@@ -121,6 +144,7 @@ def test_deskew_tables_and_points(raw_map, scan_time_end):
         assert np.abs(ot[name][:k + 1] - tab[name][:k + 1]).max() < 1e-15, name
     assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 2e-7  # float32; rpy goes through a quaternion on the node's side
     assert np.abs(und - O.deskew_points(ot, xyz, rel_eff)).max() < 2e-5
+    assert_product_tables_equal_the_nodes(product_tables(deq, stamps, gyro, t_cur, t_end), tab, ok, 2e-7)
 
 
 def test_deskew_needs_imu_and_odometry(raw_map):
@@ -347,6 +371,7 @@ def test_deskew_odometry_span_incl_the_integrate_branch(raw_map, last_odom_k):
     ot = O.deskew_tables(np.array(stamps), np.array(gyro), t_cur, t_end, *span)
     assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 2e-7
     assert np.abs(und - O.deskew_points(ot, xyz, rel)).max() < 2e-5
+    assert_product_tables_equal_the_nodes(product_tables(deq, np.array(stamps), np.array(gyro), t_cur, t_end), tab, ok, 2e-7)
 
 
 @pytest.mark.parametrize("seed", range(14))
@@ -389,8 +414,9 @@ def test_randomised_deskew_streams(raw_map, seed):
     ok, und, tab = node.deskew(stamp_in, xyz, rel_in)
     sp = H.deskew_odometry_span(deq, t_start, t_end)
     ot = O.deskew_tables(np.array(stamps), np.array(gyro), t_start, t_end, *(sp if sp is not None else (None, 0.0, None, 0.0)))
+    pt = product_tables(deq, np.array(stamps), np.array(gyro), t_start, t_end)
     if sp is None:
-        assert not ok and not tab["odom_available"]
+        assert not ok and not tab["odom_available"] and not pt["odom_available"]
         return
     assert ok == (ot["imu_available"] and ot["odom_available"])
     assert tab["imu_pointer_cur"] == ot["imu_pointer_cur"]
@@ -404,3 +430,6 @@ def test_randomised_deskew_streams(raw_map, seed):
         ratio = (t_end - t_start) / max(sp[3] - sp[1], 1e-9)
         assert np.abs(ot["odom_incre"] - tab["odom_incre"]).max() < 5e-7 * max(1.0, ratio)
         assert np.array_equal(und, O.deskew_points(tab, xyz, rel_eff))
+        assert_product_tables_equal_the_nodes(pt, tab, ok, 5e-7 * max(1.0, ratio))
+    else:
+        assert not (pt["imu_available"] and pt["odom_available"])
