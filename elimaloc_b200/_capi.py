@@ -104,6 +104,8 @@ SIGNATURES = {
     "elm_map_add_points": (C.c_int, [C.c_void_p, _fp, C.c_size_t]),
     "elm_map_cal_voxel_cov": (C.c_int, [C.c_void_p]),
     "elm_map_cal_point_cov": (C.c_int, [C.c_void_p, C.c_double]),
+    "elm_map_set_gpu_build": (C.c_int, [C.c_void_p, C.c_int]),
+    "elm_map_build_times": (C.c_int, [C.c_void_p, _dp]),
     "elm_map_empty": (C.c_int, [C.c_void_p]),
     "elm_map_num_voxels": (C.c_size_t, [C.c_void_p]),
     "elm_map_num_points": (C.c_size_t, [C.c_void_p]),

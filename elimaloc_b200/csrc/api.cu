@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstddef>
@@ -21,6 +22,7 @@
 #include "deskew_tables.hpp"
 #include "ekf.cuh"
 #include "icp_kernels.cuh"
+#include "map_build.cuh"
 #include "pcd_reader.hpp"
 #include "scan_prep.cuh"
 
@@ -89,6 +91,10 @@ constexpr int kNcclSum = 0;      // ncclSum
 struct elm_map {
     elm::HostMap host;
     int device = -1;  // -1: host-only map (builder tests without a GPU)
+    // AddPoints / CalVoxelCovAll / CalPointCovAll on the GPU (map_build.cu; bit-identical to the host builder) when the map lives
+    // on a device; ELM_HOST_BUILD=1 or elm_map_set_gpu_build(map, 0) keeps the host builder
+    int gpu_build = [] { const char* e = getenv("ELM_HOST_BUILD"); return (e && e[0] == '1') ? 0 : 1; }();
+    double build_ms[3] = {0.0, 0.0, 0.0};  // last AddPoints / CalVoxelCovAll / CalPointCovAll: milliseconds in the builder proper
     uint4* d_dslots = nullptr;
     uint32_t* d_drows = nullptr;
     float4* d_pts = nullptr;
@@ -501,22 +507,68 @@ void elm_map_destroy(elm_map* map) { delete map; }
 
 int elm_map_add_points(elm_map* map, const float* xyz, size_t n) try {
     if (!map || (!xyz && n)) return fail(ELM_ERR_INVALID, "elm_map_add_points: bad argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    if (map->device >= 0 && map->gpu_build && map->host.vkey.empty() && n > 0) {
+        ELM_CUDA(cudaSetDevice(map->device));
+        elm::GpuCanonicalMap g;
+        std::string e = elm::gpu_add_points(xyz, n, map->host.voxel_size, map->host.cap, g);
+        if (!e.empty()) { cudaGetLastError(); return fail(e.find("outside") != std::string::npos ? ELM_ERR_RANGE : ELM_ERR_CUDA, "elm_map_add_points (GPU builder): " + e); }
+        map->build_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        e = map->host.adopt_canonical(g.vkey, g.vstart, g.pxyz, g.porig, n);
+        if (!e.empty()) return fail(ELM_ERR_RANGE, e);
+        return map->publish_points();
+    }
     const std::string e = map->host.add_points(xyz, n);
     if (!e.empty()) return fail(ELM_ERR_RANGE, e);
+    map->build_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return map->publish_points();
 } ELM_API_CATCH
 
 int elm_map_cal_voxel_cov(elm_map* map) try {
     if (!map) return fail(ELM_ERR_INVALID, "null map");
     if (map->host.V() >= (1ull << elm::kVcandVoxelBits)) return fail(ELM_ERR_RANGE, "elm_map_cal_voxel_cov: more than 2^25 voxels");
+    const auto t0 = std::chrono::steady_clock::now();
+    if (map->device >= 0 && map->gpu_build && map->host.V() > 0) {
+        ELM_CUDA(cudaSetDevice(map->device));
+        std::vector<double> mean, cov;
+        const std::string e = elm::gpu_cal_voxel_cov(map->host.pxyz, map->host.vstart, mean, cov);
+        if (!e.empty()) { cudaGetLastError(); return fail(ELM_ERR_CUDA, "elm_map_cal_voxel_cov (GPU builder): " + e); }
+        map->build_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        map->host.adopt_voxel_cov(mean, cov);
+        return map->publish_voxel_cov();
+    }
     map->host.cal_voxel_cov();
+    map->build_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return map->publish_voxel_cov();
 } ELM_API_CATCH
 
 int elm_map_cal_point_cov(elm_map* map, double search_dist) try {
     if (!map) return fail(ELM_ERR_INVALID, "null map");
+    const auto t0 = std::chrono::steady_clock::now();
+    if (map->device >= 0 && map->gpu_build && map->host.P() > 0 && map->d_dslots) {
+        ELM_CUDA(cudaSetDevice(map->device));
+        std::vector<double> mean, cov, nrm;
+        const std::string e = elm::gpu_cal_point_cov(map->host.pxyz, map->d_dslots, map->d_drows, map->host.dir_bmask, map->host.voxel_size, search_dist, mean, cov, nrm);
+        if (!e.empty()) { cudaGetLastError(); return fail(ELM_ERR_CUDA, "elm_map_cal_point_cov (GPU builder): " + e); }
+        map->build_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        map->host.adopt_point_cov(mean, cov, nrm);
+        return map->publish_point_cov();
+    }
     map->host.cal_point_cov(search_dist);
+    map->build_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return map->publish_point_cov();
+} ELM_API_CATCH
+
+int elm_map_set_gpu_build(elm_map* map, int enable) try {
+    if (!map) return fail(ELM_ERR_INVALID, "null map");
+    map->gpu_build = enable ? 1 : 0;
+    return ELM_OK;
+} ELM_API_CATCH
+
+int elm_map_build_times(const elm_map* map, double ms[3]) try {
+    if (!map || !ms) return fail(ELM_ERR_INVALID, "bad argument");
+    for (int i = 0; i < 3; ++i) ms[i] = map->build_ms[i];
+    return ELM_OK;
 } ELM_API_CATCH
 
 int elm_map_empty(const elm_map* map) { return (!map || map->host.vkey.empty()) ? 1 : 0; }

@@ -280,6 +280,34 @@ std::string HostMap::add_points(const float* xyz, size_t n) {
     return e;
 }
 
+std::string HostMap::adopt_canonical(std::vector<uint64_t>& nkey, std::vector<uint32_t>& nstart, std::vector<float>& nxyz, std::vector<uint32_t>& norig,
+                                     size_t n_raw) {
+    if (!vkey.empty()) return "adopt_canonical: the map is not empty";
+    if (cap > static_cast<int>(kDirCountMask)) return "max_points_per_voxel above 1023 does not fit the column descriptors";
+    StageTimer timer;
+    vkey.swap(nkey); vstart.swap(nstart); pxyz.swap(nxyz); porig.swap(norig);
+    n_raw_seen += n_raw;
+    has_vcov = has_pcov = false;
+    vmean.clear(); vcov.clear(); pmean.clear(); pcov.clear(); pnormal.clear();
+    vcand8.clear(); dir7.clear();
+    build_table();
+    timer.lap("voxel table");
+    const std::string e = build_directory();
+    timer.lap("neighbourhood directory");
+    return e;
+}
+
+void HostMap::adopt_voxel_cov(std::vector<double>& mean, std::vector<double>& cov) {
+    vmean.swap(mean); vcov.swap(cov);
+    has_vcov = true;
+    build_voxel_candidates();
+}
+
+void HostMap::adopt_point_cov(std::vector<double>& mean, std::vector<double>& cov, std::vector<double>& normal) {
+    pmean.swap(mean); pcov.swap(cov); pnormal.swap(normal);
+    has_pcov = true;
+}
+
 // ---- neighbourhood directory ------------------------------------------------------------------------------------
 namespace {
 

@@ -77,6 +77,12 @@ struct HostMap {
 
     // returns "" on success, else an error message (range violation)
     std::string add_points(const float* xyz, size_t n);
+    // the same result delivered by the GPU builder (map_build.cu) for an EMPTY map: takes the canonical arrays over and builds the
+    // derived tables (voxel table, neighbourhood directory, octant order) exactly as add_points does after its own compaction
+    std::string adopt_canonical(std::vector<uint64_t>& nkey, std::vector<uint32_t>& nstart, std::vector<float>& nxyz, std::vector<uint32_t>& norig, size_t n_raw);
+    // covariances computed elsewhere (GPU builder): take them over; cal_voxel_cov's tail (candidate lists)
+    void adopt_voxel_cov(std::vector<double>& mean, std::vector<double>& cov);
+    void adopt_point_cov(std::vector<double>& mean, std::vector<double>& cov, std::vector<double>& normal);
     void cal_voxel_cov();
     void cal_point_cov(double search_dist);
     void build_table();

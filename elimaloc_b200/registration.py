@@ -69,6 +69,16 @@ class VoxelHashMap:
         xyz = _xyz(xyz)
         check(lib().elm_map_add_points(self._h, _f(xyz), xyz.shape[0]))
 
+    def set_gpu_build(self, enable):
+        """AddPoints / CalVoxelCovAll / CalPointCovAll on the GPU (default for a map on a device) or on the host; same results."""
+        check(lib().elm_map_set_gpu_build(self._h, int(bool(enable))))
+
+    def build_times(self):
+        """milliseconds the last AddPoints / CalVoxelCovAll / CalPointCovAll spent in the builder proper"""
+        ms = np.zeros(3)
+        check(lib().elm_map_build_times(self._h, _d(ms)))
+        return dict(add_points_ms=float(ms[0]), voxel_cov_ms=float(ms[1]), point_cov_ms=float(ms[2]))
+
     def AddPointsFromPcd(self, path):
         """loadPCDFile + AddPoints (pcm_matching.cpp:69-88); returns the number of points read"""
         n = C.c_size_t(0)

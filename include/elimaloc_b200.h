@@ -84,6 +84,13 @@ int elm_map_add_points(elm_map* map, const float* xyz, size_t n);
 int elm_map_cal_voxel_cov(elm_map* map);
 /* VoxelHashMap::CalPointCovAll (voxel_hash_map.hpp:252-257): needed before GICP. */
 int elm_map_cal_point_cov(elm_map* map, double search_dist);
+/* Where the three passes above run for a map that lives on a device: 1 (default) = on the GPU (map_build.cu: stable radix sort
+ * by voxel + per-voxel replay of the spacing test in arrival order, covariance kernels; bit-identical to the host builder),
+ * 0 = host builder.  elm_map_add_points uses the GPU builder for the first call on an empty map (the node's only call,
+ * pcm_matching.cpp:87); later calls merge on the host.  The derived search tables are built on the host either way.
+ * elm_map_build_times: milliseconds the last AddPoints / CalVoxelCovAll / CalPointCovAll spent in the builder proper. */
+int elm_map_set_gpu_build(elm_map* map, int enable);
+int elm_map_build_times(const elm_map* map, double ms[3]);
 /* VoxelHashMap::Empty (voxel_hash_map.hpp:325) */
 int elm_map_empty(const elm_map* map);
 size_t elm_map_num_voxels(const elm_map* map);
