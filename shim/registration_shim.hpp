@@ -73,8 +73,23 @@ inline std::vector<float> flatten(const std::vector<PointStruct>& pts) {
     return xyz;
 }
 inline void check(int status) {
-    // the reference never throws out of these calls; failures degrade to "ICP FAIL" in the caller
-    if (status != ELM_OK) std::cout << "\033[1;33m[elimaloc_b200] " << elm_last_error() << "\033[0m" << std::endl;
+    // The reference never throws out of these calls; failures degrade to "ICP FAIL" in the caller.  Two kinds:
+    //  - configuration errors (call order, out-of-scope options, map beyond the key range, bad arguments) do not go away by
+    //    themselves: the reference would have run on default / stale data, here the call is refused — said LOUDLY, once per
+    //    kind, so that a mis-configured drop-in does not just "never localise";
+    //  - transient failures (CUDA / NCCL) stay the reference's quiet yellow line, every time.
+    if (status == ELM_OK) return;
+    const bool config = status == ELM_ERR_STATE || status == ELM_ERR_UNSUPPORTED || status == ELM_ERR_RANGE || status == ELM_ERR_INVALID;
+    if (config) {
+        static bool said[8] = {false, false, false, false, false, false, false, false};
+        if (!said[status & 7]) {
+            said[status & 7] = true;
+            std::cerr << "\033[1;31m[elimaloc_b200] CONFIGURATION ERROR (status " << status << "): " << elm_last_error()
+                      << " -- every registration will report ICP FAIL until this is fixed\033[0m" << std::endl;
+        }
+        return;
+    }
+    std::cout << "\033[1;33m[elimaloc_b200] " << elm_last_error() << "\033[0m" << std::endl;
 }
 }  // namespace elm_shim
 
@@ -142,6 +157,7 @@ struct VoxelHashMap {
         }
         return out;
     }
+    elm_map* handle() const { return h_; }  // for the scan chain of INTEGRATION.md section 6 (elm_scan_pipeline_*)
     elm_map* h_ = nullptr;
     double voxel_size_ = 1.0;
     int max_points_per_voxel_ = 30;
@@ -201,6 +217,7 @@ struct Registration {
         o_points = points;
         TransformPoints(T, o_points);
     }
+    elm_registration* handle() const { return h_; }
     RegistrationConfig config_;
     elm_registration* h_ = nullptr;
 };
