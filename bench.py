@@ -290,11 +290,18 @@ def build_roofline(args, method, st, by_kind, counters, n_local, peak, peak_src,
             "scan 12 + two directory buckets 64 + ~3 column descriptors 24 + 16 per candidate point + winner reload 16 + match/win/memo/ncand out 40")
         row(f"icp_accumulate_kernel<{method}>", "cold", cold[1], cold[2], 12 + 16 + (4 + rec if method == 1 else 0), "scan 12 + streamed match 16 (+ GICP: index 4 + record 128)")
         # warm reuse: scan 12, memo 32, ncand 4, previous match 16, candidates 16 each, out: match 4 + win 16 + memo 16
-        row(f"icp_warm_reuse_kernel<{method}>", "first_warm", fw[0], fw[2], 12 + 32 + 4 + 16, "all queries go to the refresh list: inputs only")
-        row(f"icp_warm_refresh_kernel<{method}>", "first_warm", fw[1], fw[2], 12 + 16 + 16 + 4 * 32 + 16 * st["sum27"] * 0.3 + 16 * wp + 52 + rec,
-            "bulk refresh: inputs 44 + ~4 column records 128 + octant runs (estimate: 0.3 of the 27 voxels' points) + list out + memo/win/ncand out 52")
-        row(f"icp_warm_reuse_kernel<{method}>", "warm", wm[0], wm[2], 12 + 32 + 4 + 16 + 16 * wp + 36 + rec, "scan 12 + memo 32 + ncand 4 + previous match 16 + 16 per list candidate + match/win/memo out 36 (+ GICP record 128)")
-        row(f"icp_warm_refresh_kernel<{method}>", "warm", wm[1], wm[2], 0.0, "a handful of stragglers + fold of the reuse rows + final reduction + solve: a latency chain, not a stream")
+        mode = os.environ.get("ELM_WARM_MODE", "async")[0]  # how the warm iterations after the first run (api.cu: default async)
+        row(f"icp_warm_refresh_kernel<{method}>", "first_warm", fw[0] + fw[1], fw[2], 12 + 16 + 16 + 4 * 32 + 16 * st["sum27"] * 0.3 + 16 * wp + 52 + rec,
+            "all-queries refresh (no lists yet): inputs 44 + ~4 column records 128 + octant runs (estimate: 0.3 of the 27 voxels' points) + list out + memo/win/ncand out 52")
+        warm_req = 12 + 32 + 4 + 16 + 16 * wp + 36 + rec
+        warm_note = "scan 12 + memo 32 + ncand 4 + previous match 16 + 16 per list candidate + match/win/memo out 36 (+ GICP record 128)"
+        if mode == "s":
+            row(f"icp_warm_kernel<{method}>", "warm", wm[0] + wm[1], wm[2], warm_req, warm_note + "; one launch per iteration")
+        else:
+            row(f"icp_warm_reuse_kernel<{method}>", "warm", wm[0], wm[2], warm_req, warm_note)
+            row(f"icp_warm_refresh_async_kernel<{method}>" if mode == "a" else f"icp_warm_refresh_kernel<{method}>", "warm", wm[1], wm[2], 0.0,
+                "stragglers (none on this map after the first warm iteration) + fold of the reuse rows + final reduction + solve: a latency chain, not a stream"
+                + ("; runs BESIDE the reuse kernel in the timed region, after it in this event-serialised pass" if mode == "a" else ""))
     elif method == 2:
         row("icp_search_means_kernel", "cold", cold[0], cold[2], 12 + 64 + 8 + 8 * st["v27"] + 4, "scan 12 + buckets 64 + candidate run descriptor 8 + 8 per candidate (13-bit mean offsets + voxel index) + match out 4")
         row("icp_accumulate_kernel<2>", "cold", cold[1], cold[2], 12 + 4 + 96, "scan 12 + match 4 + mean and covariance 96 (one 128-byte line)")

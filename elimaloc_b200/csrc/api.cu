@@ -188,14 +188,25 @@ struct elm_registration {
     uint32_t* d_ncand = nullptr;
     float4* d_cand = nullptr;  // per-query candidate lists of the warm search (icp_device.cuh)
     uint32_t* d_refresh = nullptr;  // work list of the warm refresh kernel: match_cap entries (a segment per tile) + match_cap / 256 counts
+    unsigned long long* d_tile_flag = nullptr;    // concurrent refresh: per-tile {epoch | stragglers}, match_cap / 256 + 1 entries
+    double* d_tile_rows = nullptr;                // ... per-tile sums, (match_cap / 256 + 1) x 32
+    unsigned long long* d_tile_ticket = nullptr;  // ... tiles handed out since the call began
+    unsigned int warm_epoch = 0;                  // epoch of the last warm iteration enqueued on this handle
+    unsigned long long ticket_base = 0, done_base = 0;  // hand-out / completion counters the next concurrent refresh starts from (reset with every call)
     int cand_cap = 32;
     size_t match_cap = 0;
     int warm = 1;              // P2P / GICP: iterations after the first start their search from the previous match (same result)
-    // warm iterations after the first of a call as ONE kernel (icp_warm_kernel) or as the reuse + refresh pair.  Measured on B200
-    // (profiles/r02_ab_warm_single_kernel.txt): GICP 19.9k vs 18.6k iterations/s in favour of the single kernel, P2P 28.3k vs 30.8k
-    // against it (the in-lined refresh path spills into the 64-register reuse path) -> default: GICP single, P2P pair;
-    // ELM_WARM_SINGLE=0 / 1 forces one or the other (A/B switch).
-    int warm_single = [] { const char* e = getenv("ELM_WARM_SINGLE"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    // How the warm iterations after the first of a call run (same results):
+    //   0 "pair"    icp_warm_reuse_kernel, then icp_warm_refresh_kernel
+    //   1 "single"  ONE kernel, icp_warm_kernel (stragglers refreshed in place by their own warp)
+    //   2 "async"   icp_warm_reuse_kernel with icp_warm_refresh_async_kernel running BESIDE it (the stragglers leave the critical path)
+    // Measured on B200 (profiles/r02_ab_warm_modes.txt): async 35.2k / 21.5k iterations/s (P2P / GICP), single 32.4k / 20.6k, pair 31.1k / 18.5k.
+    // Default (-1): async.  ELM_WARM_MODE=pair|single|async forces one (A/B switch).
+    int warm_mode = [] {
+        const char* e = getenv("ELM_WARM_MODE");
+        if (!e) return -1;
+        return e[0] == 'p' ? 0 : (e[0] == 's' ? 1 : (e[0] == 'a' ? 2 : -1));
+    }();
     // spatially binned copy of the scan for the search kernels (scan_sort.cu)
     float* d_sorted = nullptr;
     int* d_orig = nullptr;
@@ -255,7 +266,8 @@ struct elm_registration {
     elm::PeerComm peer{};          // peer.world > 0: the accumulate kernel's last block all-reduces over the ranks itself
     void* peer_opened[elm::kMaxPeers] = {};
     bool sharded() const { return comm != nullptr || peer.world > 0; }
-    elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, match_cap, d_ncand, d_cand, cand_cap, d_refresh, d_refresh ? d_refresh + match_cap : nullptr, d_partials, d_ticket}; }
+    elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, match_cap, d_ncand, d_cand, cand_cap, d_refresh, d_refresh ? d_refresh + match_cap : nullptr, d_partials, d_ticket,
+                                                   d_tile_flag, d_tile_rows, d_tile_ticket, 0u, 0ull, 0ull}; }
     double warm_margin_vox = 0.08;  // refresh margin of the warm search in voxel sizes
 
     ~elm_registration() {
@@ -267,6 +279,7 @@ struct elm_registration {
         cudaFree(d_mailbox);
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         cudaFree(d_state); cudaFreeHost(h_state); cudaFree(d_partials); cudaFree(d_match); cudaFree(d_win); cudaFree(d_memo); cudaFree(d_ncand); cudaFree(d_cand); cudaFree(d_refresh); cudaFree(d_ticket);
+        cudaFree(d_tile_flag); cudaFree(d_tile_rows); cudaFree(d_tile_ticket);
         cudaFree(d_stats);
         cudaFree(d_dtable); cudaFreeHost(h_dtable); cudaFree(d_dsk_in); cudaFree(d_dsk_out);
         cudaFree(d_sorted); cudaFree(d_orig); cudaFree(d_bin); cudaFree(d_hist); cudaFree(d_scan); cudaFree(d_count); cudaFree(d_target);
@@ -317,7 +330,9 @@ int ensure_partials(elm_registration* r, int rows) {
 int ensure_match(elm_registration* r, size_t n) {
     if (n > r->match_cap) {
         cudaFree(r->d_match); cudaFree(r->d_win); cudaFree(r->d_memo); cudaFree(r->d_ncand); cudaFree(r->d_cand); cudaFree(r->d_refresh);
+        cudaFree(r->d_tile_flag); cudaFree(r->d_tile_rows);
         r->d_match = nullptr; r->d_win = nullptr; r->d_memo = nullptr; r->d_ncand = nullptr; r->d_cand = nullptr; r->d_refresh = nullptr;
+        r->d_tile_flag = nullptr; r->d_tile_rows = nullptr;
         r->match_cap = 0;
         const size_t cap = (n + 1023) / 1024 * 1024;
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_match), cap * sizeof(int)));
@@ -326,6 +341,9 @@ int ensure_match(elm_registration* r, size_t n) {
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_ncand), cap * sizeof(uint32_t)));
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_cand), static_cast<size_t>(r->cand_cap) * cap * sizeof(float4)));
         ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_refresh), (cap + cap / 256 + 1) * sizeof(uint32_t)));
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_tile_flag), (cap / 256 + 1) * sizeof(unsigned long long)));
+        ELM_CUDA(cudaMemsetAsync(r->d_tile_flag, 0, (cap / 256 + 1) * sizeof(unsigned long long), r->stream));  // epoch 0 = never published
+        ELM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_tile_rows), (cap / 256 + 1) * elm::kAcc * sizeof(double)));
         r->match_cap = cap;
     }
     return ELM_OK;
@@ -396,8 +414,8 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // P2P / GICP: search, linearisation, reduction and solve are ONE kernel (unless the search runs on the binned copy,
     // whose order differs from the caller's: then the accumulation stays a separate launch in the caller's order)
     const bool fuse = r->fuse && prm0.method <= ELM_GICP && !(r->use_sorted && !r->sorted_all);
-    const int wgrid = elm::icp_warm_grid(prm0, r->num_sms), rgrid = elm::icp_warm_refresh_grid(prm0, r->num_sms);
-    int rc = ensure_partials(r, std::max(std::max(sgrid, agrid), wgrid + rgrid));
+    const int wgrid = elm::icp_warm_grid(prm0, r->num_sms), rgrid = elm::icp_warm_refresh_grid(prm0, r->num_sms), xgrid = elm::icp_warm_refresh_async_grid(r->num_sms);
+    int rc = ensure_partials(r, std::max(std::max(sgrid, agrid), wgrid + std::max(rgrid, xgrid)));
     if (rc) return rc;
     rc = ensure_match(r, prm0.n);
     if (rc) return rc;
@@ -421,10 +439,36 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // P2P / GICP from the second iteration of a call on: the warm pair of kernels (reuse: search + linearisation of the
     // queries whose candidate lists still hold; refresh: the rest, then reduction and solve)
     const bool use_warm = warm && r->warm && r->prune && !mapped && !fuse && prm.method <= ELM_GICP;
-    if (use_warm && (r->warm_single < 0 ? prm.method == ELM_GICP : r->warm_single == 1) && r->warm_iterations_enqueued > 0) {
+    const int warm_mode = r->warm_mode >= 0 ? r->warm_mode : 2;
+    if (use_warm && warm_mode == 1 && r->warm_iterations_enqueued > 0) {
         // every warm iteration after the first: ONE kernel (stragglers refreshed in place by their own warp)
         if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
         ELM_CUDA(elm::launch_icp_warm(map->view(), d_scan, prm, r->d_state, wk, wgrid, solve_here, r->stream));
+        r->launches += 1;
+    } else if (use_warm && warm_mode == 2 && r->warm_iterations_enqueued > 0) {
+        // ... or the reuse kernel with the refresh kernel running beside it: the reuse blocks publish every tile's work list under
+        // this iteration's epoch, the refresh blocks take the tiles as they arrive
+        if (++r->warm_epoch == 0) {  // (wrapped: forget every flag)
+            ELM_CUDA(cudaMemsetAsync(r->d_tile_flag, 0, (r->match_cap / 256 + 1) * sizeof(unsigned long long), r->stream));
+            r->warm_epoch = 1;
+        }
+        wk.epoch = r->warm_epoch;
+        wk.ticket_base = r->ticket_base;
+        wk.done_base = r->done_base;
+        {   // every block of the refresh grid draws tickets until it gets one beyond the last chunk: chunks + grid draws per iteration
+            const unsigned long long ntiles = static_cast<unsigned long long>((prm.n + elm::kIcpThreads - 1) / elm::kIcpThreads), nchunks = (ntiles + 15) / 16;
+            r->ticket_base += nchunks + static_cast<unsigned long long>(xgrid);
+            r->done_base += nchunks;
+        }
+        ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), d_scan, prm, r->d_state, wk, wgrid, r->stream));
+        if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
+        ELM_CUDA(elm::launch_icp_warm_refresh_async(map->view(), d_scan, prm, r->d_state, wk, wgrid, xgrid, solve_here, r->stream));
+        r->launches += 2;
+    } else if (use_warm && r->warm_iterations_enqueued == 0) {
+        // the first warm iteration of a call: no candidate lists exist yet, EVERY query is refreshed — the refresh kernel alone, in
+        // its all-queries mode (a reuse kernel in front of it would only fill the work list with every index: 13 us)
+        if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
+        ELM_CUDA(elm::launch_icp_warm_refresh(map->view(), d_scan, prm, r->d_state, wk, -1, rgrid, solve_here, r->stream));
         r->launches += 1;
     } else if (use_warm) {
         ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), d_scan, prm, r->d_state, wk, wgrid, r->stream));
@@ -775,6 +819,8 @@ int elm_registration_create(elm_registration** out, int device, void* stream) tr
     }
     if (cudaMalloc(reinterpret_cast<void**>(&r->d_ticket), sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(r->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&r->d_tile_ticket), 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(r->d_tile_ticket, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&r->d_state), sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMemset(r->d_state, 0, sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&r->h_state), sizeof(elm::IcpState)) != cudaSuccess) {
@@ -805,7 +851,8 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     reg->trivial = map->host.vkey.empty() || (n == 0 && !reg->sharded());
     if (reg->trivial) return ELM_OK;
     const elm::IcpParams prm = make_params(reg, cfg, n);
-    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->d_ticket, reg->stream));
+    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->d_ticket, reg->d_tile_ticket, reg->stream));
+    reg->ticket_base = reg->done_base = 0;
     reg->launches += 1;
     rc = enqueue_binning(reg, map, d_src_xyz, n, T_init, cfg->icp_method);
     if (rc) return rc;
@@ -883,7 +930,8 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     if (rc) return rc;
     if (n) ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
     const elm::IcpParams prm = make_params(reg, cfg, n);
-    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
+    ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->d_tile_ticket, reg->stream));
+    reg->ticket_base = reg->done_base = 0;
     rc = enqueue_binning(reg, map, reg->d_scan, n, T, cfg->icp_method);
     if (rc) return rc;
     rc = enqueue_linearize(reg, map, reg->d_scan, prm, false);
@@ -930,7 +978,8 @@ int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, cons
     if (rc) return rc;
     for (int k = 0; k < n_poses; ++k) {
         const double* T = T_seq + 16 * static_cast<size_t>(k);
-        ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->stream));
+        ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->d_tile_ticket, reg->stream));
+    reg->ticket_base = reg->done_base = 0;
         if (k == 0) {
             rc = enqueue_binning(reg, map, reg->d_scan, n, T, method);
             if (rc) return rc;

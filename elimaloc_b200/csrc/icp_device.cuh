@@ -93,6 +93,14 @@ struct IcpWork {
     uint32_t* refresh_count;  // [tiles] entries used in each segment
     double* partials;       // [blocks][kAcc] per-block sums of one linearisation
     unsigned int* ticket;   // blocks finished
+    // concurrent refresh (icp_warm_refresh_async_kernel runs BESIDE the reuse kernel of the same iteration):
+    unsigned long long* tile_flag;   // [tiles] {epoch << 32 | stragglers of the tile; all ones in the low word = loop already left}, published by the
+                                     // reuse kernel as soon as the tile's work list is complete
+    double* tile_rows;               // [chunks of 16 tiles][kAcc] sums of the chunk's refreshed correspondences
+    unsigned long long* tile_ticket; // [0] chunks handed out, [1] chunk rows completed since the call began (icp_begin_kernel resets both)
+    unsigned int epoch;              // this iteration's epoch (0: no flags are published)
+    unsigned long long ticket_base;  // value of tile_ticket[0] at which this iteration's hand-out starts
+    unsigned long long done_base;    // value of tile_ticket[1] before this iteration
 };
 
 // Lives in HBM for the whole ICP loop; the host reads it back once at the end.

@@ -749,7 +749,7 @@ __device__ __forceinline__ void linearize_voxel_pair(double* acc, const double* 
 
 // Block tree over per-lane accumulators: warp shuffles, then the 8 warps in fixed order; thread k < 29 ADDS the block's
 // sum of canonical slot k to s_sum[k].  Every thread of the block must call it.
-template <int NACC, bool IS_P2P>
+template <int NACC, bool IS_P2P, int WARPS = kIcpWarps>
 __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc], double* s_sum) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -766,7 +766,7 @@ __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc
     __syncthreads();
     if (tid < 29) {
         double v = 0.0;
-        for (int w = 0; w < kIcpWarps; ++w) v += s_red[w][tid];
+        for (int w = 0; w < WARPS; ++w) v += s_red[w][tid];
         s_sum[tid] += v;
     }
     __syncthreads();
@@ -791,6 +791,7 @@ __device__ __forceinline__ void publish_partials(const double* s_sum, const IcpP
         partials[static_cast<size_t>(row) * kAcc + tid] = v;
     }
 }
+template <int WARPS = kIcpWarps>
 __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)[kAcc], double* s_acc, bool* s_last, SolveScratch* s_solve,
                                             const double* s_T, IcpState* st, const IcpParams& prm, double* __restrict__ partials,
                                             unsigned int* __restrict__ ticket, int solve_here, int row0 = 0, int nrows = -1, int first_row = 0) {
@@ -816,12 +817,12 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
         const double* const rows = partials + static_cast<size_t>(nrows >= 0 ? first_row : row0) * kAcc;
         // 16 loads in flight per thread, summed in index order; rows past the end contribute +0.0 (the tail used to be one
         // dependent load per row: 9 round trips for 296 rows instead of 3)
-        constexpr int kDepth = 16;
-        for (int b = g; b < nb; b += kDepth * kIcpWarps) {
+        constexpr int kDepth = WARPS == 4 ? 32 : 16;  // (4 warps: 128 rows in ONE pass)
+        for (int b = g; b < nb; b += kDepth * WARPS) {
             double t[kDepth];
 #pragma unroll
             for (int u = 0; u < kDepth; ++u) {
-                const int row = b + u * kIcpWarps;
+                const int row = b + u * WARPS;
                 t[u] = (row < nb) ? __ldcg(rows + static_cast<size_t>(row) * kAcc + k) : 0.0;
             }
 #pragma unroll
@@ -832,7 +833,7 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
     __syncthreads();
     if (tid < kAcc) {
         double t = 0.0;
-        for (int i = 0; i < kIcpWarps; ++i) t += s_red[i][tid];
+        for (int i = 0; i < WARPS; ++i) t += s_red[i][tid];
         st->acc[tid] = t;
         s_acc[tid] = t;
     }
@@ -849,8 +850,8 @@ __device__ __forceinline__ void finish_grid(const double* s_sum, double (*s_red)
         const unsigned long long seq = s_seq;
         const int par = static_cast<int>(seq & 1);
         const unsigned long long tag = (seq & 0xffffffffull) << 32;
-        if (tid < pc.world * kAcc) {  // one thread per (destination rank, accumulator): two self-validating 8-byte stores
-            const int p = tid / kAcc, k = tid % kAcc;
+        for (int e = tid; e < pc.world * kAcc; e += WARPS * 32) {  // one (destination rank, accumulator) per thread: two self-validating 8-byte stores
+            const int p = e / kAcc, k = e % kAcc;
             const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(s_acc[k]));
             volatile unsigned long long* w = pc.box[p]->word[par][pc.rank][k];
             w[0] = (bits & 0xffffffffull) | tag;
@@ -1545,6 +1546,53 @@ __device__ __forceinline__ void warm_refresh_warp(const MapView& map, float4* ca
 //                            warm_refresh_warp), all of them in the first warm iteration of a call (one thread per query,
 //                            warm_refresh); their correspondences are linearised here, and the LAST block sums the rows of
 //                            both kernels in a fixed order, all-reduces over the ranks (multi-GPU) and solves.
+// Can the query's candidate list answer this iteration's question?  The list holds every stored point of the 27 voxels around
+// the memo's key k0 within R of q0 (memo1).  With d' = distance from the new position q to the previous match:
+//   same key:  d' + |q - q0| <= R  =>  every point of the neighbourhood within d' of q is in the list;
+//   the query MOVED INTO ANOTHER VOXEL k1: still true, and the answer is still the reference's, if R < one voxel and both
+//   neighbourhoods lie where stored keys are floor keys (every key of k0 - 1 .. k0 + 1 and k1 - 1 .. k1 + 1 >= 1: insert keys
+//   truncate toward zero, vhm.cpp:275, so only there does "within one voxel size of q" imply "inside the 27 voxels around
+//   floor(q)").  Then the ball of radius d' < vs around q lies inside BOTH neighbourhoods: the previous match is a candidate of
+//   GetCorrespondencePoints at k1, so its nearest point is within d' of q, hence within R of q0, hence in the list — and every
+//   list point within d' of q belongs to k1's 27 voxels.  Ranks are canonical indices, the same in both visit orders.
+//   (The memo keeps k0 and its row: they describe the LIST; the next refresh looks the new key up.)
+__device__ __forceinline__ bool warm_list_answers(const MapView& map, const uint4& m0, const uint4& m1, uint32_t nc, uint32_t ccap, const float4& prev,
+                                                  double px, double py, double pz, int kx, int ky, int kz, bool in_range, bool same_key) {
+    if (m0.w == kNone || nc > ccap) return false;
+    const float Rf = __uint_as_float(m1.w);
+    if (!same_key) {
+        if (!in_range || (m0.y & m0.z) == kNone) return false;
+        int ox, oy, oz;
+        unpack_key((static_cast<uint64_t>(m0.z) << 32) | m0.y, ox, oy, oz);
+        if (!(min(min(kx, ky), kz) >= 2 && min(min(ox, oy), oz) >= 2 && Rf < 0.99f * static_cast<float>(map.voxel_size))) return false;
+    }
+    const double d2_prev = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
+    const float dx = static_cast<float>(px - static_cast<double>(__uint_as_float(m1.x))), dy = static_cast<float>(py - static_cast<double>(__uint_as_float(m1.y))),
+                dz = static_cast<float>(pz - static_cast<double>(__uint_as_float(m1.z)));
+    const float delta = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f + 1e-30f;
+    const float room = (Rf - delta) * 0.999999f;  // what is left of R for d' (each side rounded against us)
+    return room > 0.f && d2_prev <= static_cast<double>(room) * static_cast<double>(room);
+}
+
+#ifdef ELM_TRACE
+// developer trace (profiles/trace_async.py): wall-clock marks of one iteration in the stats slots; FIRST = first writer, LAST = latest
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ELM_TRACE_FIRST(k) do { if (prm.stats && threadIdx.x == 0) atomicCAS(prm.stats + (k), 0ull, trace_now()); } while (0)
+#define ELM_TRACE_LAST(k) do { if (prm.stats && threadIdx.x == 0) atomicMax(prm.stats + (k), trace_now()); } while (0)
+#else
+#define ELM_TRACE_FIRST(k) do { } while (0)
+#define ELM_TRACE_LAST(k) do { } while (0)
+#endif
+// release / acquire on a 64-bit flag in global memory (tile work lists handed from the reuse kernel to the concurrent refresh kernel)
+__device__ __forceinline__ void flag_store_release(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long flag_load_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int METHOD>
 __global__ void __launch_bounds__(kIcpThreads, METHOD == 1 ? 3 : 4)
 icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, IcpWork wk) {
@@ -1571,48 +1619,72 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
     uint32_t nc = kNone;
     float4 prev = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
     if (gi < prm.n) { m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi]; }
+    ELM_TRACE_FIRST(2);
     if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
     if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
     if (tid < kAcc) s_sum[tid] = 0.0;
     if (tid == 0) s_done = st->done;
     __syncthreads();
-    if (s_done) return;  // loop already left (termination / overlap failure)
+    if (s_done) {  // loop already left (termination / overlap failure): tell the concurrent refresh kernel, which waits for this block's tiles
+        if (wk.epoch && tid == 0)
+            for (int t = blockIdx.x; t * kIcpThreads < prm.n; t += gridDim.x)
+                flag_store_release(wk.tile_flag + t, (static_cast<unsigned long long>(wk.epoch) << 32) | 0xffffffffull);
+        return;
+    }
     for (bool first = true; gi - tid < prm.n; gi += gridDim.x * kIcpThreads, first = false) {
         const bool mine = gi < prm.n;
-        double acc[NACC];
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-        bool refresh = false;
+        const int tile = (gi - tid) / kIcpThreads;
+        if (mine && !first) {
+            m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi];
+            sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2];
+        }
+        // candidate j of this query: tile-interleaved (icp_device.cuh) — the 256 queries of a tile keep their lists in one
+        // contiguous block, candidate-major inside it, so a warp reads 512 consecutive bytes per candidate
+        const float4* const my_cand = wk.cand + static_cast<size_t>(tile) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(tid);
+        constexpr size_t cstride = kIcpThreads;
+        const double sx = sxf, sy = syf, sz = szf;
+        const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
+        // ---- decision first: REUSE (same key and d' + |q - q0| <= R with d' = distance to the previous match, each side rounded
+        // against us), nothing to find (same voxel, empty neighbourhood), or REFRESH — so that the tile's work list can leave
+        // for the refresh kernel before the lists are streamed
+        uint32_t qkey_lo = kNone, qkey_hi = kNone;
+        bool reuse = false, refresh = false;
         if (mine) {
-            if (!first) {
-                m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi];
-                sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2];
-            }
-            // candidate j of this query: tile-interleaved (icp_device.cuh) — the 256 queries of a tile keep their lists in one
-            // contiguous block, candidate-major inside it, so a warp reads 512 consecutive bytes per candidate
-            const float4* const my_cand = wk.cand + static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
-            constexpr size_t cstride = kIcpThreads;
-            const double sx = sxf, sy = syf, sz = szf;
-            const double px = row_apply_exact(s_T, 0, sx, sy, sz), py = row_apply_exact(s_T, 1, sx, sy, sz), pz = row_apply_exact(s_T, 2, sx, sy, sz);
             const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
             ++searched;
-            uint32_t qkey_lo = kNone, qkey_hi = kNone;
             const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
             if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
             const bool same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
-            // REUSE: same key and  d' + |q - q0| <= R  with d' = distance to the previous match (each side rounded against us)
-            bool reuse = false;
-            if (same_key && m0.w != kNone && nc <= ccap) {
-                const double d2_prev = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
-                const float dx = static_cast<float>(px - static_cast<double>(__uint_as_float(m1.x))), dy = static_cast<float>(py - static_cast<double>(__uint_as_float(m1.y))),
-                            dz = static_cast<float>(pz - static_cast<double>(__uint_as_float(m1.z)));
-                const float delta = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f + 1e-30f;
-                const float room = (__uint_as_float(m1.w) - delta) * 0.999999f;  // what is left of R for d'
-                reuse = room > 0.f && d2_prev <= static_cast<double>(room) * static_cast<double>(room);
-            }
+            reuse = warm_list_answers(map, m0, m1, nc, ccap, prev, px, py, pz, kx, ky, kz, in_range, same_key);
+            if (!same_key) { qkey_lo = m0.y; qkey_hi = m0.z; }  // (a reused list keeps the key it was built for; a refresh writes the new one)
+            // (same voxel as last time and its 27-neighbourhood holds no point: still nothing to find, Q2 applies below)
+            refresh = !reuse && !(same_key && static_cast<int>(m0.x) < 0);
+            if (refresh) { ++refreshed; if (prm.stats) atomicAdd(prm.stats + (same_key ? 29 : 28), 1ull); }
+        }
+        // the work list of the refresh kernel: one segment per tile, filled in thread order (no atomics: the refresh kernel's
+        // summation order, hence every bit of the result, is the same from run to run)
+        const uint32_t rmask = __ballot_sync(kFull, refresh);
+        if (lane == 0) s_wcnt[tid >> 5] = __popc(rmask);
+        __syncthreads();
+        uint32_t base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kIcpWarps; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; total += s_wcnt[w]; }
+        if (refresh) {
+            wk.refresh_list[static_cast<size_t>(tile) * kIcpThreads + base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<uint32_t>(gi);
+            if (wk.epoch) __threadfence();
+        }
+        if (wk.epoch) __syncthreads();  // (block-uniform) every entry of the list is written and fenced before the flag goes out
+        if (tid == 0) {
+            wk.refresh_count[tile] = total;
+            if (wk.epoch) flag_store_release(wk.tile_flag + tile, (static_cast<unsigned long long>(wk.epoch) << 32) | total);
+        }
+        // ---- REUSE path
+        double acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+        if (mine && !refresh) {
             int my_match = -1;
             float4 wpt = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));  // the matched point {x, y, z, index}
-            bool decided = true;
             if (reuse) {
                 // one fp32 pass over the list (coalesced: candidate j of the warp's queries is 512 consecutive bytes), four loads
                 // in flight, then ONE decision (the band of visit_points): the fp32 argmin is the unique exact winner, or (a near
@@ -1647,34 +1719,13 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
                     }
                 }
                 my_match = static_cast<int>(__float_as_uint(wpt.w));  // (kNone = -1: an empty list)
-            } else if (same_key && static_cast<int>(m0.x) < 0) {
-                // same voxel as last time and its 27-neighbourhood holds no point: still nothing to find (Q2 applies below)
-            } else {
-                decided = false;  // REFRESH: the next kernel searches this query
-                refresh = true;
-                ++refreshed;
             }
-            if (decided) {
-                if (wk.match) wk.match[gi] = my_match;
-                wk.win[gi] = wpt;
-                memo0[gi] = make_uint4(m0.x, qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
-                linearize_point_pair<METHOD>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
-            }
+            if (wk.match) wk.match[gi] = my_match;
+            wk.win[gi] = wpt;
+            memo0[gi] = make_uint4(m0.x, qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+            linearize_point_pair<METHOD>(map, my_match, wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
         }
-        // the work list of the refresh kernel: one segment per tile, filled in thread order (no atomics: the refresh kernel's
-        // summation order, hence every bit of the result, is the same from run to run)
-        const uint32_t rmask = __ballot_sync(kFull, refresh);
-        if (lane == 0) s_wcnt[tid >> 5] = __popc(rmask);
-        block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);  // (two block barriers: s_wcnt is complete afterwards)
-        {
-            const int tile = (gi - tid) / kIcpThreads;
-            uint32_t base = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kIcpWarps; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; total += s_wcnt[w]; }
-            if (refresh) wk.refresh_list[static_cast<size_t>(tile) * kIcpThreads + base + __popc(rmask & ((1u << lane) - 1u))] = static_cast<uint32_t>(gi);
-            if (tid == 0) wk.refresh_count[tile] = total;
-        }
-        __syncthreads();  // (s_wcnt is rewritten by the next tile)
+        block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);  // (two block barriers: s_wcnt may be rewritten by the next tile)
     }
     if (prm.stats) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -1688,6 +1739,7 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
         }
     }
     publish_partials(s_sum, prm, wk.partials, static_cast<int>(blockIdx.x));
+    ELM_TRACE_LAST(3);
 }
 
 // ---- ONE kernel per warm iteration (every warm iteration but the first of a call) ------------------------------------
@@ -1757,15 +1809,8 @@ icp_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpS
             const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
             if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
             same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
-            bool reuse = false;  // REUSE: same key and  d' + |q - q0| <= R  (see icp_warm_reuse_kernel)
-            if (same_key && m0.w != kNone && nc <= ccap) {
-                const double d2_prev = sq3_exact(static_cast<double>(prev.x) - px, static_cast<double>(prev.y) - py, static_cast<double>(prev.z) - pz);
-                const float dx = static_cast<float>(px - static_cast<double>(__uint_as_float(m1.x))), dy = static_cast<float>(py - static_cast<double>(__uint_as_float(m1.y))),
-                            dz = static_cast<float>(pz - static_cast<double>(__uint_as_float(m1.z)));
-                const float delta = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f + 1e-30f;
-                const float room = (__uint_as_float(m1.w) - delta) * 0.999999f;
-                reuse = room > 0.f && d2_prev <= static_cast<double>(room) * static_cast<double>(room);
-            }
+            const bool reuse = warm_list_answers(map, m0, m1, nc, ccap, prev, px, py, pz, kx, ky, kz, in_range, same_key);  // (see icp_warm_reuse_kernel)
+            if (reuse && !same_key) { qkey_lo = m0.y; qkey_hi = m0.z; }  // (a reused list keeps the key it was built for)
             if (reuse) {
                 const float4* const my_cand = wk.cand + cbase;
                 const Query Q(px, py, pz);
@@ -1857,6 +1902,210 @@ icp_warm_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpS
     finish_grid(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here);
 }
 
+// ---- the refresh kernel BESIDE the reuse kernel of the same iteration -------------------------------------------------------
+// icp_warm_refresh_kernel starts its work when the reuse grid has completed; everything it does then — state, work-list counts, a
+// handful of stragglers (five dependent round trips each), fold, ticket, final reduction, solve — is a serial latency chain of
+// ~17 us per iteration.  Here the refresh blocks are small (128 threads: they fit beside three resident reuse blocks of an SM),
+// become resident while the reuse kernel runs (programmatic dependent launch) and take the tiles' work lists AS THE REUSE BLOCKS
+// PUBLISH THEM (tile_flag: release / acquire), so the stragglers are refreshed in the shadow of the reuse kernel.  Only then do
+// they wait for the reuse grid (griddepcontrol.wait), fold its rows and the tile rows in a FIXED block <- row mapping, and the last
+// block reduces, exchanges and solves.  What remains on the critical path after the reuse kernel: one fold, the ticket, the final
+// reduction over <= 148 rows and the solve.
+//   tiles are handed out dynamically (tile_ticket; blocks that are not resident yet simply find nothing left), but every sum is
+//   formed in a fixed order — a tile's stragglers in list order into tile_rows[tile], rows folded by block (index mod grid) — so
+//   results stay bit-reproducible from run to run.
+//   Before a flag of THIS iteration's epoch has been seen nothing an earlier kernel wrote may be read: the flag is written by a
+//   reuse block after ITS griddepcontrol.wait, i.e. after the previous iteration's refresh kernel has completed.
+constexpr int kAsyncWarps = 4;
+constexpr int kAsyncThreads = kAsyncWarps * 32;
+constexpr int kChunkTiles = 16;  // tiles handed out per ticket: their flags are polled side by side, their stragglers form ONE list
+template <int METHOD>
+__global__ void __launch_bounds__(kAsyncThreads, 4)
+icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* __restrict__ st, IcpWork wk, int rows_before, int solve_here) {
+    constexpr int NACC = AccSize<METHOD>::value;
+    __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
+    __shared__ double s_red[kAsyncWarps][kAcc], s_sum[kAcc], s_acc[kAcc];
+    __shared__ SolveScratch s_solve;
+    __shared__ bool s_last;
+    __shared__ unsigned int s_run[kAsyncWarps][64];
+    __shared__ unsigned long long s_word;
+    __shared__ unsigned int s_cnt[kChunkTiles], s_off[kChunkTiles + 1];
+    pdl_launch_dependents();
+    ELM_TRACE_FIRST(4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ccap = static_cast<uint32_t>(wk.cand_cap);
+    uint4* const memo0 = wk.memo;
+    uint4* const memo1 = wk.memo + wk.memo_stride;
+    const int ntiles = (prm.n + kIcpThreads - 1) / kIcpThreads;
+    const int nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
+    bool have_state = false, loop_left = false;
+    double acc[NACC];
+    auto load_state = [&]() {
+        if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
+        if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
+        have_state = true;
+        __syncthreads();
+    };
+    auto commit = [&](uint32_t gi, const WarmRefresh& r, double sx, double sy, double sz, double px, double py, double pz, uint32_t qkey_lo, uint32_t qkey_hi) {
+        const int my_match = r.b.idx != kNone ? static_cast<int>(r.b.idx) : -1;
+        if (wk.match) wk.match[gi] = my_match;
+        wk.win[gi] = r.wpt;
+        memo0[gi] = make_uint4(static_cast<uint32_t>(r.row), qkey_lo, qkey_hi, static_cast<uint32_t>(my_match));
+        memo1[gi] = make_uint4(__float_as_uint(static_cast<float>(px)), __float_as_uint(static_cast<float>(py)), __float_as_uint(static_cast<float>(pz)), __float_as_uint(r.Rf));
+        wk.ncand[gi] = r.n_new;
+        linearize_point_pair<METHOD>(map, my_match, r.wpt, sx, sy, sz, px, py, pz, s_Tinv, s_Rinv, prm.th, prm.max_dist2, acc);
+    };
+    auto load_query = [&](uint32_t gi, double& sx, double& sy, double& sz, double& px, double& py, double& pz, uint4& m0, float4& prev, bool& same_key,
+                          uint32_t& qkey_lo, uint32_t& qkey_hi, size_t& cbase) {
+        sx = scan[3 * static_cast<size_t>(gi)]; sy = scan[3 * static_cast<size_t>(gi) + 1]; sz = scan[3 * static_cast<size_t>(gi) + 2];
+        px = row_apply_exact(s_T, 0, sx, sy, sz); py = row_apply_exact(s_T, 1, sx, sy, sz); pz = row_apply_exact(s_T, 2, sx, sy, sz);
+        m0 = memo0[gi]; prev = wk.win[gi];
+        const int kx = voxel_floor(px, map), ky = voxel_floor(py, map), kz = voxel_floor(pz, map);
+        qkey_lo = qkey_hi = kNone;
+        const bool in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
+        if (in_range) { const uint64_t qk = pack_key(kx, ky, kz); qkey_lo = static_cast<uint32_t>(qk); qkey_hi = static_cast<uint32_t>(qk >> 32); }
+        same_key = in_range && m0.y == qkey_lo && m0.z == qkey_hi;
+        cbase = static_cast<size_t>(gi / kIcpThreads) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(gi % kIcpThreads);
+    };
+    // entry `it` of the chunk's combined straggler list (tiles in order, each tile's list in order)
+    auto chunk_entry = [&](int tile0, uint32_t it) {
+        int j = 0;
+        while (it >= s_off[j + 1]) ++j;
+        return wk.refresh_list[static_cast<size_t>(tile0 + j) * kIcpThreads + (it - s_off[j])];
+    };
+    // ---- chunks of tiles, as their work lists arrive
+    while (wk.epoch) {
+        __syncthreads();  // (s_word / s_cnt of the previous round have been read by everyone)
+        if (tid == 0) s_word = atomicAdd(wk.tile_ticket, 1ull) - wk.ticket_base;
+        __syncthreads();
+        const unsigned long long c64 = s_word;
+        if (c64 >= static_cast<unsigned long long>(nchunks)) break;
+        const int chunk = static_cast<int>(c64), tile0 = chunk * kChunkTiles;
+        if (tid < kChunkTiles) {
+            uint32_t cnt = 0;
+            if (tile0 + tid < ntiles) {  // one thread per tile of the chunk: the flags are awaited side by side
+                const long long t0 = clock64();
+                for (;;) {
+                    const unsigned long long f = flag_load_acquire(wk.tile_flag + tile0 + tid);
+                    if (static_cast<unsigned int>(f >> 32) == wk.epoch) { cnt = static_cast<uint32_t>(f); break; }
+                    if (clock64() - t0 > 4000000000ll) { cnt = 0xfffffffeu; break; }  // ~2 s: never hang the GPU
+                    __nanosleep(32);
+                }
+            }
+            s_cnt[tid] = cnt;
+        }
+        __syncthreads();
+        ELM_TRACE_FIRST(5);
+        uint32_t total = 0, marker = 0;
+#pragma unroll
+        for (int j = 0; j < kChunkTiles; ++j) { const uint32_t c = s_cnt[j]; marker |= (c >= 0xfffffffeu) ? c : 0u; total += (c >= 0xfffffffeu) ? 0u : c; }
+        if (marker) {  // the loop was left in an earlier iteration (or a flag never came: report it instead of hanging)
+            loop_left = true;
+            if (marker == 0xfffffffeu && tid == 0) { st->comm_error = 2; st->done = 1; }
+            break;
+        }
+        double* const crow = wk.tile_rows + static_cast<size_t>(chunk) * kAcc;
+        if (total) {
+            if (tid == 0) { uint32_t o = 0; for (int j = 0; j < kChunkTiles; ++j) { s_off[j] = o; o += s_cnt[j]; } s_off[kChunkTiles] = o; }
+            if (!have_state) load_state(); else __syncthreads();
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+            if (total <= 4 * kAsyncWarps) {  // a handful: one warp per query
+                for (uint32_t it = warp; it < total; it += kAsyncWarps) {
+                    const uint32_t gi = chunk_entry(tile0, it);
+                    double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
+                    load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);  // (every lane the same query)
+                    WarmRefresh r;
+                    warm_refresh_warp(map, wk.cand, ccap, prm.warm_margin, 0, px, py, pz, m0, prev, same_key, cbase, s_run[warp], &r);
+                    if (lane == 0) commit(gi, r, sx, sy, sz, px, py, pz, qkey_lo, qkey_hi);
+                }
+            } else {                         // many (the pose jumped): one thread per query
+                for (uint32_t it = tid; it < total; it += kAsyncThreads) {
+                    const uint32_t gi = chunk_entry(tile0, it);
+                    double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
+                    load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);
+                    WarmRefresh r;
+                    warm_refresh(map, wk.cand + cbase, ccap, prm.warm_margin, m0, prev, same_key, px, py, pz, &r);
+                    commit(gi, r, sx, sy, sz, px, py, pz, qkey_lo, qkey_hi);
+                }
+            }
+            __syncthreads();
+            if (tid < kAcc) s_sum[tid] = 0.0;
+            __syncthreads();
+            block_sum_into<NACC, METHOD == 0, kAsyncWarps>(acc, s_red, s_sum);
+            if (tid < kAcc) crow[tid] = tid < 29 ? s_sum[tid] : 0.0;
+        } else if (tid < kAcc) {
+            crow[tid] = 0.0;
+        }
+        // the chunk's row is complete: count it (the fold below waits for all chunks of this iteration)
+        if (tid < kAcc) __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(wk.tile_ticket + 1, 1ull);
+    }
+    // the pose of this iteration, fetched in the shadow of the reuse kernel: any flag of this epoch proves that the previous
+    // iteration's solve is complete and visible (blocks that handled a chunk have seen one already)
+    if (wk.epoch && !have_state && !loop_left && ntiles > 0) {
+        __syncthreads();  // (everyone has read the last ticket from s_word)
+        if (tid == 0) {
+            const long long t0 = clock64();
+            unsigned long long f;
+            for (;;) {
+                f = flag_load_acquire(wk.tile_flag);
+                if (static_cast<unsigned int>(f >> 32) == wk.epoch || clock64() - t0 > 4000000000ll) break;
+                __nanosleep(64);
+            }
+            s_word = f;
+        }
+        __syncthreads();
+        if (static_cast<unsigned int>(s_word >> 32) == wk.epoch && static_cast<uint32_t>(s_word) < 0xfffffffeu) load_state();
+    }
+    ELM_TRACE_LAST(6);
+    // ---- from here on the reuse kernel's rows are complete
+    pdl_wait();
+    ELM_TRACE_LAST(7);
+    if (loop_left) return;
+    // speculative loads of the fold (rows of the reuse grid) share their round trip with the done flag
+    __shared__ int s_flagdone;
+    double fold[4] = {0.0, 0.0, 0.0, 0.0};
+    if (tid < 29) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x);
+            if (row < rows_before) fold[u] = __ldcg(wk.partials + static_cast<size_t>(row) * kAcc + tid);
+        }
+    }
+    if (tid == 0) {
+        int d = st->done;
+        if (!d && wk.epoch) {  // every chunk row of this iteration must be complete (written by OTHER blocks of this grid)
+            const long long t0 = clock64();
+            while (flag_load_acquire(wk.tile_ticket + 1) - wk.done_base < static_cast<unsigned long long>(nchunks)) {
+                if (clock64() - t0 > 4000000000ll) { st->comm_error = 2; st->done = 1; d = 1; break; }
+                __nanosleep(32);
+            }
+        }
+        s_flagdone = d;
+    }
+    __syncthreads();
+    if (s_flagdone) return;
+    if (!have_state) load_state();
+    // fold: block b takes the reuse rows b, b + G, ... and the chunk rows b, b + G, ... in that order
+    if (tid < kAcc) {
+        double v = 0.0;
+        if (tid < 29) {
+            v = ((fold[0] + fold[1]) + fold[2]) + fold[3];
+            for (int row = static_cast<int>(blockIdx.x) + 4 * static_cast<int>(gridDim.x); row < rows_before; row += static_cast<int>(gridDim.x))
+                v += __ldcg(wk.partials + static_cast<size_t>(row) * kAcc + tid);
+            if (wk.epoch)
+                for (int c = static_cast<int>(blockIdx.x); c < nchunks; c += static_cast<int>(gridDim.x)) v += __ldcg(wk.tile_rows + static_cast<size_t>(c) * kAcc + tid);
+        }
+        s_sum[tid] = v;
+    }
+    __syncthreads();
+    ELM_TRACE_LAST(9);
+    finish_grid<kAsyncWarps>(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here, rows_before, -1, rows_before);
+    ELM_TRACE_LAST(10);
+}
+
 // rows_before = rows of `partials` the reuse kernel published (its grid size)
 template <int METHOD>
 __global__ void __launch_bounds__(kIcpThreads, 2)
@@ -1906,15 +2155,22 @@ icp_warm_refresh_kernel(MapView map, const float* __restrict__ scan, IcpParams p
     // this block's tiles: blockIdx.x, blockIdx.x + gridDim.x, ... two at a time, so that their few stragglers (a converging
     // loop: 0-2 per tile) share the block's eight warps instead of queueing tile after tile
     const int ntiles = (prm.n + kIcpThreads - 1) / kIcpThreads;
+    // rows_before < 0: EVERY query is refreshed (the first warm iteration of a call, whose lists do not exist yet) — no reuse kernel
+    // ran, there is no work list: a tile's entries are its queries
+    const bool all_queries = rows_before < 0;
+    if (all_queries) rows_before = 0;
+    auto tile_queries = [&](int t) { return static_cast<uint32_t>(min(kIcpThreads, prm.n - t * kIcpThreads)); };
     for (int tile0 = static_cast<int>(blockIdx.x); tile0 < ntiles; tile0 += 2 * static_cast<int>(gridDim.x)) {
         const int tile1 = tile0 + static_cast<int>(gridDim.x);
-        const uint32_t c0 = wk.refresh_count[tile0], c1 = tile1 < ntiles ? wk.refresh_count[tile1] : 0u;
+        const uint32_t c0 = all_queries ? tile_queries(tile0) : wk.refresh_count[tile0],
+                       c1 = tile1 < ntiles ? (all_queries ? tile_queries(tile1) : wk.refresh_count[tile1]) : 0u;
         const uint32_t* const list0 = wk.refresh_list + static_cast<size_t>(tile0) * kIcpThreads;
         const uint32_t* const list1 = wk.refresh_list + static_cast<size_t>(tile1 < ntiles ? tile1 : tile0) * kIcpThreads;
         if (c0 + c1 <= 4 * kIcpWarps) {
             // a handful: one warp per query
             for (uint32_t it = warp; it < c0 + c1; it += kIcpWarps) {
-                const uint32_t gi = it < c0 ? list0[it] : list1[it - c0];
+                const uint32_t gi = all_queries ? static_cast<uint32_t>((it < c0 ? tile0 : tile1) * kIcpThreads) + (it < c0 ? it : it - c0)
+                                                : (it < c0 ? list0[it] : list1[it - c0]);
                 double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
                 load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);  // (every lane the same query)
                 WarmRefresh r;
@@ -1926,7 +2182,7 @@ icp_warm_refresh_kernel(MapView map, const float* __restrict__ scan, IcpParams p
             for (int h = 0; h < 2; ++h) {
                 const uint32_t cnt = h ? c1 : c0;
                 if (static_cast<uint32_t>(tid) < cnt) {
-                    const uint32_t gi = (h ? list1 : list0)[tid];
+                    const uint32_t gi = all_queries ? static_cast<uint32_t>((h ? tile1 : tile0) * kIcpThreads + tid) : (h ? list1 : list0)[tid];
                     double sx, sy, sz, px, py, pz; uint4 m0; float4 prev; bool same_key; uint32_t qkey_lo, qkey_hi; size_t cbase;
                     load_query(gi, sx, sy, sz, px, py, pz, m0, prev, same_key, qkey_lo, qkey_hi, cbase);
                     WarmRefresh r;
@@ -1935,6 +2191,11 @@ icp_warm_refresh_kernel(MapView map, const float* __restrict__ scan, IcpParams p
                 }
             }
         }
+    }
+    if (all_queries && prm.stats && tid == 0) {  // (the counters the reuse kernel would have kept)
+        unsigned long long q = 0;
+        for (int t = static_cast<int>(blockIdx.x); t < ntiles; t += static_cast<int>(gridDim.x)) q += tile_queries(t);
+        atomicAdd(prm.stats + 1, q); atomicAdd(prm.stats + 20, q); atomicAdd(prm.stats + 21, q);
     }
     block_sum_into<NACC, METHOD == 0>(acc, s_red, s_sum);
     // the rows of the reuse kernel are folded into this grid's rows in parallel (block b takes the rows b, b + gridDim.x, ...
@@ -2110,8 +2371,9 @@ icp_avgicp_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, Ic
 // ======================================================================================================================
 // small fixed-size kernels
 // ======================================================================================================================
-__global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket) {
+__global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket, unsigned long long* tile_ticket) {
     if (threadIdx.x == 0) {
+        if (tile_ticket) { tile_ticket[0] = 0ull; tile_ticket[1] = 0ull; }
         for (int i = 0; i < 16; ++i) st->T[i] = T0.m[i];
         refresh_inverses(st);
         for (int i = 0; i < 36; ++i) st->local_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;  // reg.cpp:280
@@ -2232,10 +2494,10 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int dyn_sm
 }
 }  // namespace
 
-cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, cudaStream_t s) {
+cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, unsigned long long* tile_ticket, cudaStream_t s) {
     Pose16 p;
     for (int i = 0; i < 16; ++i) p.m[i] = T0[i];
-    icp_begin_kernel<<<1, 32, 0, s>>>(st, p, ticket);
+    icp_begin_kernel<<<1, 32, 0, s>>>(st, p, ticket, tile_ticket);
     return cudaGetLastError();
 }
 
@@ -2274,6 +2536,15 @@ cudaError_t launch_icp_warm(const MapView& map, const float* scan, const IcpPara
                             cudaStream_t s) {
     const cudaError_t e = prm.method == 0 ? launch_pdl(icp_warm_kernel<0>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here)
                                           : launch_pdl(icp_warm_kernel<1>, grid, kIcpThreads, 0, s, map, scan, prm, st, wk, solve_here);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+int icp_warm_refresh_async_grid(int num_sms) { return num_sms < 128 ? num_sms : 128; }
+cudaError_t launch_icp_warm_refresh_async(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
+                                          int grid, int solve_here, cudaStream_t s) {
+    const cudaError_t e = prm.method == 0
+                              ? launch_pdl(icp_warm_refresh_async_kernel<0>, grid, kAsyncThreads, 0, s, map, scan, prm, st, wk, reuse_grid, solve_here)
+                              : launch_pdl(icp_warm_refresh_async_kernel<1>, grid, kAsyncThreads, 0, s, map, scan, prm, st, wk, reuse_grid, solve_here);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ int icp_warm_grid(const IcpParams& prm, int num_sms);
 // blocks of the accumulation kernel (== rows of `partials`)
 int icp_accumulate_grid(const IcpParams& prm, int num_sms);
 
-cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, cudaStream_t s);
+cudaError_t launch_icp_begin(IcpState* st, const double T0[16], unsigned int* ticket, unsigned long long* tile_ticket, cudaStream_t s);
 // P2P / GICP / VGICP correspondence search -> wk.match[n] (+ wk.win, wk.memo for P2P / GICP); no-op for AVGICP, which searches
 // inside the accumulation.  `orig` (may be NULL): scan is in binned order and the outputs are written at orig[i].
 // fuse (P2P / GICP): the search kernel also linearises, reduces and — when solve_here — solves: one launch per iteration.
@@ -32,6 +32,11 @@ cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const
 // One warm iteration as ONE launch (stragglers refreshed in place by their own warp); wk.partials needs `grid` rows.
 cudaError_t launch_icp_warm(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int grid, int solve_here,
                             cudaStream_t s);
+// The refresh kernel running BESIDE the reuse kernel of the same iteration (wk.epoch != 0: the reuse kernel publishes every tile's
+// work list as soon as it is complete); grid = icp_warm_refresh_async_grid blocks of 128 threads; wk.partials needs reuse_grid + grid rows.
+int icp_warm_refresh_async_grid(int num_sms);
+cudaError_t launch_icp_warm_refresh_async(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
+                                          int grid, int solve_here, cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);
 // spatial binning of the scan (scan_sort.cu)
 int scan_bin_bits(int n);

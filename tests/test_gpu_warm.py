@@ -142,3 +142,31 @@ def test_warm_state_does_not_leak_between_scans(dense):
     got = reg.RunRegister(b, dense["gm"], T0, cfg)
     fresh = E.Registration(device=0).RunRegister(b, dense["gm"], T0, cfg)
     assert np.array_equal(got[0], fresh[0]) and got[2] == fresh[2]   # (same path, same order: bit for bit)
+
+
+@pytest.mark.parametrize("method", [E.P2P, E.GICP])
+def test_warm_search_across_voxel_borders(method):
+    """Queries that move into another voxel keep their candidate list where both neighbourhoods lie among keys >= 1 (stored keys are
+    floor keys there, so "within one voxel size" implies "inside the 27 voxels") and must refresh anywhere else (insert keys truncate
+    toward zero, Q1: the neighbourhood of a negative key is shifted).  Maps entirely positive, entirely negative, and straddling the
+    origin; many small steps so that a good share of the queries crosses a voxel face with a valid list; every prefix against the
+    oracle, bit for bit — and the warm searches that had to refresh after the first one are far fewer on the positive map."""
+    late = {}
+    for origin in (3.0, -20.0, -1.5):
+        raw = synth.map_u(90_000, 20.0, origin=origin)
+        gm, om = make_world(raw)
+        rng = np.random.default_rng(11)
+        c = origin + 10.0
+        T = synth.se3([c, c, c], [0.01, -0.02, 0.2])
+        scan = synth.scan_m(gm.Pointcloud(), 20000, T, noise=0.03, seed=13)
+        poses = pose_walk(T @ synth.canonical_offset(), 6, rng, 0.012, 0.0004)
+        reg = E.Registration(device=0)
+        check_sequence(reg, gm, om, scan, poses, method)
+        reg.set_stats(True)
+        reg.correspondences_sequence(scan, gm, poses, method, 5.0)
+        s = reg.stats_raw()
+        reg.set_stats(False)
+        assert s[21] == 6 * len(scan)
+        late[origin] = s[20] - len(scan)        # (the first warm search refreshes every query)
+    assert late[-20.0] > 100, late              # voxel changes force a refresh among negative keys ...
+    assert late[3.0] < 0.3 * late[-20.0], late  # ... and no longer among positive ones
