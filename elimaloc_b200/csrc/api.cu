@@ -192,7 +192,7 @@ struct elm_registration {
     double* d_tile_rows = nullptr;                // ... per-tile sums, (match_cap / 256 + 1) x 32
     unsigned long long* d_tile_ticket = nullptr;  // ... tiles handed out since the call began
     unsigned int warm_epoch = 0;                  // epoch of the last warm iteration enqueued on this handle
-    unsigned long long ticket_base = 0, done_base = 0;  // hand-out / completion counters the next concurrent refresh starts from (reset with every call)
+    int async_iterations = 0;                     // concurrent-refresh iterations enqueued since the call began (each owns a pair of tile counters)
     int cand_cap = 32;
     size_t match_cap = 0;
     int warm = 1;              // P2P / GICP: iterations after the first start their search from the previous match (same result)
@@ -267,7 +267,7 @@ struct elm_registration {
     void* peer_opened[elm::kMaxPeers] = {};
     bool sharded() const { return comm != nullptr || peer.world > 0; }
     elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, match_cap, d_ncand, d_cand, cand_cap, d_refresh, d_refresh ? d_refresh + match_cap : nullptr, d_partials, d_ticket,
-                                                   d_tile_flag, d_tile_rows, d_tile_ticket, 0u, 0ull, 0ull}; }
+                                                   d_tile_flag, d_tile_rows, d_tile_ticket, 0u}; }
     double warm_margin_vox = 0.08;  // refresh margin of the warm search in voxel sizes
 
     ~elm_registration() {
@@ -445,7 +445,7 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
         if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
         ELM_CUDA(elm::launch_icp_warm(map->view(), d_scan, prm, r->d_state, wk, wgrid, solve_here, r->stream));
         r->launches += 1;
-    } else if (use_warm && warm_mode == 2 && r->warm_iterations_enqueued > 0) {
+    } else if (use_warm && warm_mode == 2 && r->warm_iterations_enqueued > 0 && r->async_iterations < elm::kMaxAsyncIterations) {
         // ... or the reuse kernel with the refresh kernel running beside it: the reuse blocks publish every tile's work list under
         // this iteration's epoch, the refresh blocks take the tiles as they arrive
         if (++r->warm_epoch == 0) {  // (wrapped: forget every flag)
@@ -453,13 +453,7 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
             r->warm_epoch = 1;
         }
         wk.epoch = r->warm_epoch;
-        wk.ticket_base = r->ticket_base;
-        wk.done_base = r->done_base;
-        {   // every block of the refresh grid draws tickets until it gets one beyond the last chunk: chunks + grid draws per iteration
-            const unsigned long long ntiles = static_cast<unsigned long long>((prm.n + elm::kIcpThreads - 1) / elm::kIcpThreads), nchunks = (ntiles + 15) / 16;
-            r->ticket_base += nchunks + static_cast<unsigned long long>(xgrid);
-            r->done_base += nchunks;
-        }
+        wk.tile_ticket = r->d_tile_ticket + 2 * static_cast<size_t>(r->async_iterations++);
         ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), d_scan, prm, r->d_state, wk, wgrid, r->stream));
         if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
         ELM_CUDA(elm::launch_icp_warm_refresh_async(map->view(), d_scan, prm, r->d_state, wk, wgrid, xgrid, solve_here, r->stream));
@@ -819,8 +813,8 @@ int elm_registration_create(elm_registration** out, int device, void* stream) tr
     }
     if (cudaMalloc(reinterpret_cast<void**>(&r->d_ticket), sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(r->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&r->d_tile_ticket), 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(r->d_tile_ticket, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&r->d_tile_ticket), 2 * elm::kMaxAsyncIterations * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(r->d_tile_ticket, 0, 2 * elm::kMaxAsyncIterations * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&r->d_state), sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMemset(r->d_state, 0, sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&r->h_state), sizeof(elm::IcpState)) != cudaSuccess) {
@@ -852,7 +846,7 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     if (reg->trivial) return ELM_OK;
     const elm::IcpParams prm = make_params(reg, cfg, n);
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->d_ticket, reg->d_tile_ticket, reg->stream));
-    reg->ticket_base = reg->done_base = 0;
+    reg->async_iterations = 0;
     reg->launches += 1;
     rc = enqueue_binning(reg, map, d_src_xyz, n, T_init, cfg->icp_method);
     if (rc) return rc;
@@ -931,7 +925,7 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     if (n) ELM_CUDA(cudaMemcpyAsync(reg->d_scan, src_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, reg->stream));
     const elm::IcpParams prm = make_params(reg, cfg, n);
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->d_tile_ticket, reg->stream));
-    reg->ticket_base = reg->done_base = 0;
+    reg->async_iterations = 0;
     rc = enqueue_binning(reg, map, reg->d_scan, n, T, cfg->icp_method);
     if (rc) return rc;
     rc = enqueue_linearize(reg, map, reg->d_scan, prm, false);
@@ -979,7 +973,7 @@ int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, cons
     for (int k = 0; k < n_poses; ++k) {
         const double* T = T_seq + 16 * static_cast<size_t>(k);
         ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->d_tile_ticket, reg->stream));
-    reg->ticket_base = reg->done_base = 0;
+    reg->async_iterations = 0;
         if (k == 0) {
             rc = enqueue_binning(reg, map, reg->d_scan, n, T, method);
             if (rc) return rc;

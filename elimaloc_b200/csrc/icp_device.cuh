@@ -48,6 +48,7 @@ constexpr int kIdxJtr = 21, kIdxRes = 27, kIdxNcorr = 28, kIdxNtotal = 29;
 // order — bit-identical on all ranks, no broadcast, no separate collective launch.  The slots are self-validating
 // ("LL" style): every fp64 value travels as two 8-byte words {32 data bits, 32-bit sequence tag}; an 8-byte store is
 // atomic, so a word whose tag matches carries valid data — no fence, no separate flag write, ONE NVLink hop.
+constexpr int kMaxAsyncIterations = 1024;  // concurrent-refresh iterations per call that own a pair of tile counters (beyond: pair mode)
 constexpr int kMaxPeers = 8;
 struct PeerMailbox {
     unsigned long long word[2][kMaxPeers][kAcc][2];  // [parity][source rank][accumulator][low / high half]: data | tag << 32
@@ -97,10 +98,9 @@ struct IcpWork {
     unsigned long long* tile_flag;   // [tiles] {epoch << 32 | stragglers of the tile; all ones in the low word = loop already left}, published by the
                                      // reuse kernel as soon as the tile's work list is complete
     double* tile_rows;               // [chunks of 16 tiles][kAcc] sums of the chunk's refreshed correspondences
-    unsigned long long* tile_ticket; // [0] chunks handed out, [1] chunk rows completed since the call began (icp_begin_kernel resets both)
+    unsigned long long* tile_ticket; // THIS iteration's pair of counters: [0] chunks handed out, [1] chunk rows completed (icp_begin_kernel zeroes
+                                     // the pairs of all kMaxAsyncIterations iterations of a call)
     unsigned int epoch;              // this iteration's epoch (0: no flags are published)
-    unsigned long long ticket_base;  // value of tile_ticket[0] at which this iteration's hand-out starts
-    unsigned long long done_base;    // value of tile_ticket[1] before this iteration
 };
 
 // Lives in HBM for the whole ICP loop; the host reads it back once at the end.

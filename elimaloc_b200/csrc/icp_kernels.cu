@@ -1976,7 +1976,7 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
     // ---- chunks of tiles, as their work lists arrive
     while (wk.epoch) {
         __syncthreads();  // (s_word / s_cnt of the previous round have been read by everyone)
-        if (tid == 0) s_word = atomicAdd(wk.tile_ticket, 1ull) - wk.ticket_base;
+        if (tid == 0) s_word = atomicAdd(wk.tile_ticket, 1ull);
         __syncthreads();
         const unsigned long long c64 = s_word;
         if (c64 >= static_cast<unsigned long long>(nchunks)) break;
@@ -2078,7 +2078,7 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
         int d = st->done;
         if (!d && wk.epoch) {  // every chunk row of this iteration must be complete (written by OTHER blocks of this grid)
             const long long t0 = clock64();
-            while (flag_load_acquire(wk.tile_ticket + 1) - wk.done_base < static_cast<unsigned long long>(nchunks)) {
+            while (flag_load_acquire(wk.tile_ticket + 1) < static_cast<unsigned long long>(nchunks)) {
                 if (clock64() - t0 > 4000000000ll) { st->comm_error = 2; st->done = 1; d = 1; break; }
                 __nanosleep(32);
             }
@@ -2372,8 +2372,11 @@ icp_avgicp_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, Ic
 // small fixed-size kernels
 // ======================================================================================================================
 __global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket, unsigned long long* tile_ticket) {
+    // every concurrent-refresh iteration of the call owns ITS pair of counters {chunks handed out, chunk rows completed}: kernels of
+    // several iterations can be resident at once (programmatic dependent launch), a shared counter would mix their draws
+    if (tile_ticket) for (int i = threadIdx.x; i < 2 * kMaxAsyncIterations; i += blockDim.x) tile_ticket[i] = 0ull;
     if (threadIdx.x == 0) {
-        if (tile_ticket) { tile_ticket[0] = 0ull; tile_ticket[1] = 0ull; }
+        // (the tile-ticket counters are reset by every lane below)
         for (int i = 0; i < 16; ++i) st->T[i] = T0.m[i];
         refresh_inverses(st);
         for (int i = 0; i < 36; ++i) st->local_cov[i] = (i % 7 == 0) ? 1.0 : 0.0;  // reg.cpp:280
