@@ -312,7 +312,12 @@ def build_roofline(args, method, st, by_kind, counters, n_local, peak, peak_src,
     tot = sum(r["total_ms"] for r in rows)
     for r in rows:
         r["share_of_kernel_time"] = r["total_ms"] / tot
-    dom = max(rows, key=lambda r: r["total_ms"])
+    # the roofline kernel = the STREAMING kernel with the largest share of the step.  Kernels that move (almost) no bytes — the
+    # reduction / exchange / solve tail of a warm iteration — are a latency chain, not a memory kernel: they are listed in `kernels`
+    # with their time and share, and named in `latency_tail`, but a bandwidth fraction of them would be a meaningless 0
+    streaming = [r for r in rows if r["requested_bytes_per_query"] > 0]
+    dom = max(streaming or rows, key=lambda r: r["total_ms"])
+    tail = [r for r in rows if r["requested_bytes_per_query"] <= 0]
     traffic = traffic_from_profiles(args.method, dom["kernel"].split("<")[0]) if (world == 1 and args.n_scan == N_SCAN and args.m_raw == M_RAW and not args.exhaustive) else None
     frac_traffic = None
     if traffic:
@@ -334,6 +339,7 @@ def build_roofline(args, method, st, by_kind, counters, n_local, peak, peak_src,
             "reference_algorithm_equivalent_note": "bytes GetCorrespondence* has to read (SURVEY 8(d): 27 slots + every stored point of the 27 voxels) / OUR mean "
                                                    "iteration time: above the HBM peak means the exact pruning + warm start skip that much work, not that HBM is faster",
             "iteration_us_serialised": iter_us,
+            "latency_tail": [{"kernel": r["kernel"], "us_per_launch": r["us_per_launch"], "share_of_kernel_time": r["share_of_kernel_time"]} for r in tail],
             "kernels": rows,
             "mean_stored_points_in_27_voxels": st["sum27"], "mean_nonempty_voxels_27": st["v27"], "mean_nonempty_voxels_7": st["v7"],
             "peak_source": peak_src}
