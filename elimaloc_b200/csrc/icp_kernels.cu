@@ -1592,10 +1592,26 @@ __device__ __forceinline__ unsigned long long flag_load_acquire(const unsigned l
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// chain mode: ONE thread waits until *p >= target (acquire); false after ~2 s (reported as an error instead of hanging the GPU)
+// (polls with relaxed loads and fences once at the end: an acquire load per poll would invalidate the SM's L1 under the blocks that
+// are still streaming beside the waiting one)
+__device__ __forceinline__ bool flag_await(const unsigned long long* p, unsigned long long target) {
+    const long long t0 = clock64();
+    bool ok = true;
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= target) break;
+        if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+        __nanosleep(100);
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    return ok;
+}
 
 template <int METHOD>
 __global__ void __launch_bounds__(kIcpThreads, METHOD == 1 ? 3 : 4)
-icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, IcpWork wk) {
+icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* st, IcpWork wk) {
     constexpr int NACC = AccSize<METHOD>::value;
     __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
     __shared__ double s_red[kIcpWarps][kAcc], s_sum[kAcc];
@@ -1613,7 +1629,17 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
     int gi = blockIdx.x * kIcpThreads + tid;
     float sxf = 0.f, syf = 0.f, szf = 0.f;
     if (gi < prm.n) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
-    pdl_wait();
+    if (wk.chain_wait) {
+        // chain mode: the previous kernel is the refresh kernel of the previous iteration, and what this kernel needs of it (and of
+        // everything before it) is complete and visible as soon as its last block has solved and released the iteration's flag — no
+        // wait for that grid to drain and for this grid to be released (4-8 us per iteration, profiles/trace_async.py).  Every kernel
+        // this one could wait for was completely resident before this grid was launched (launch_dependents is the first thing its
+        // blocks do), so the spin cannot starve it.
+        if (tid == 0 && !flag_await(wk.chain_wait, 1ull)) { st->comm_error = 2; st->done = 1; __threadfence(); }
+        __syncthreads();
+    } else {
+        pdl_wait();
+    }
     // the first query's memo is requested BEFORE the pose is staged in shared memory: both loads share one round trip
     uint4 m0 = make_uint4(kNone, kNone, kNone, kNone), m1 = make_uint4(0, 0, 0, 0);
     uint32_t nc = kNone;
@@ -1629,6 +1655,10 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
         if (wk.epoch && tid == 0)
             for (int t = blockIdx.x; t * kIcpThreads < prm.n; t += gridDim.x)
                 flag_store_release(wk.tile_flag + t, (static_cast<unsigned long long>(wk.epoch) << 32) | 0xffffffffull);
+        if (wk.chain && tid == 0) {  // nobody solves in this iteration: block 0 lets the next reuse kernel through (it will see `done` too)
+            if (blockIdx.x == 0) flag_store_release(wk.tile_ticket + 3, 1ull);
+            atomicAdd(wk.tile_ticket + 2, 1ull);
+        }
         return;
     }
     for (bool first = true; gi - tid < prm.n; gi += gridDim.x * kIcpThreads, first = false) {
@@ -1691,7 +1721,11 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
                 // tie) the list is decided again exactly
                 const Query Q(px, py, pz);
                 float m = kInf, s2 = kInf;
+#ifdef ELM_REUSE_KEEP_BEST
+                float4 best = wpt;  // the fp32 argmin itself stays in registers: no dependent reload of the winner (one L2 round trip per tile)
+#else
                 uint32_t mj = 0;
+#endif
                 for (uint32_t j = 0; j < nc; j += 4) {
                     float4 c[4];  // (addresses past the list are clamped, not predicated: a predicated load sent c[] to local memory)
 #pragma unroll
@@ -1701,14 +1735,24 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
                         const float dx = c[u].x - Q.fx, dy = c[u].y - Q.fy, dz = c[u].z - Q.fz;
                         float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                         d = (j + u < nc) ? d : kInf;
+#ifdef ELM_REUSE_KEEP_BEST
+                        s2 = fminf(s2, fmaxf(d, m));
+                        if (d < m) best = c[u];  // (d < m implies j + u < nc: this IS candidate j + u)
+                        m = fminf(m, d);
+#else
                         s2 = fminf(s2, fmaxf(d, m)); mj = (d < m) ? j + u : mj; m = fminf(m, d);
+#endif
                     }
                 }
                 visited += nc;
                 const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);
                 const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
                 if (s2 > T) {  // (the exact distance of the unique winner is not needed: nothing is left to compare it with)
+#ifdef ELM_REUSE_KEEP_BEST
+                    wpt = best;
+#else
                     wpt = my_cand[static_cast<size_t>(mj) * cstride];
+#endif
                 } else {       // near tie (or an empty list): every candidate exactly, smallest rank (read from the map) among equals
                     Best b;
                     for (uint32_t j = 0; j < nc; ++j) {
@@ -1739,6 +1783,11 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
         }
     }
     publish_partials(s_sum, prm, wk.partials, static_cast<int>(blockIdx.x));
+    if (wk.chain) {  // everything this block wrote (matches, memos, its row of sums) is visible before the block counts itself in
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicAdd(wk.tile_ticket + 2, 1ull); }
+    }
     ELM_TRACE_LAST(3);
 }
 
@@ -2061,15 +2110,24 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
     }
     ELM_TRACE_LAST(6);
     // ---- from here on the reuse kernel's rows are complete
-    pdl_wait();
+    if (wk.chain) {  // chain mode: every reuse block has counted itself in after publishing its row (no wait for the grid to drain)
+        if (loop_left) return;
+        if (tid == 0 && !flag_await(wk.tile_ticket + 2, static_cast<unsigned long long>(rows_before))) { st->comm_error = 2; st->done = 1; __threadfence(); }
+        __syncthreads();
+    } else {
+        pdl_wait();
+    }
     ELM_TRACE_LAST(7);
     if (loop_left) return;
     // speculative loads of the fold (rows of the reuse grid) share their round trip with the done flag
     __shared__ int s_flagdone;
-    double fold[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int kFold = 8;  // (592 reuse rows over 80 refresh blocks: one round trip)
+    double fold[kFold];
+#pragma unroll
+    for (int u = 0; u < kFold; ++u) fold[u] = 0.0;
     if (tid < 29) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kFold; ++u) {
             const int row = static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x);
             if (row < rows_before) fold[u] = __ldcg(wk.partials + static_cast<size_t>(row) * kAcc + tid);
         }
@@ -2086,14 +2144,19 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
         s_flagdone = d;
     }
     __syncthreads();
-    if (s_flagdone) return;
+    if (s_flagdone) {  // (chain mode: nobody solves in this iteration; the next reuse kernel must still get through, and will see `done`)
+        if (wk.chain && blockIdx.x == 0 && tid == 0) flag_store_release(wk.tile_ticket + 3, 1ull);
+        return;
+    }
     if (!have_state) load_state();
     // fold: block b takes the reuse rows b, b + G, ... and the chunk rows b, b + G, ... in that order
     if (tid < kAcc) {
         double v = 0.0;
         if (tid < 29) {
-            v = ((fold[0] + fold[1]) + fold[2]) + fold[3];
-            for (int row = static_cast<int>(blockIdx.x) + 4 * static_cast<int>(gridDim.x); row < rows_before; row += static_cast<int>(gridDim.x))
+            v = fold[0];  // rows b, b + G, b + 2 G, ... summed in that order (rows past the end contribute +0.0)
+#pragma unroll
+            for (int u = 1; u < kFold; ++u) v += fold[u];
+            for (int row = static_cast<int>(blockIdx.x) + kFold * static_cast<int>(gridDim.x); row < rows_before; row += static_cast<int>(gridDim.x))
                 v += __ldcg(wk.partials + static_cast<size_t>(row) * kAcc + tid);
             if (wk.epoch)
                 for (int c = static_cast<int>(blockIdx.x); c < nchunks; c += static_cast<int>(gridDim.x)) v += __ldcg(wk.tile_rows + static_cast<size_t>(c) * kAcc + tid);
@@ -2103,6 +2166,8 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
     __syncthreads();
     ELM_TRACE_LAST(9);
     finish_grid<kAsyncWarps>(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here, rows_before, -1, rows_before);
+    // chain mode: the last block (its thread 0 has just solved) releases the iteration's flag; the next reuse kernel waits for it
+    if (wk.chain && tid == 0 && s_last) { __threadfence(); flag_store_release(wk.tile_ticket + 3, 1ull); }
     ELM_TRACE_LAST(10);
 }
 
@@ -2374,7 +2439,7 @@ icp_avgicp_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, Ic
 __global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket, unsigned long long* tile_ticket) {
     // every concurrent-refresh iteration of the call owns ITS pair of counters {chunks handed out, chunk rows completed}: kernels of
     // several iterations can be resident at once (programmatic dependent launch), a shared counter would mix their draws
-    if (tile_ticket) for (int i = threadIdx.x; i < 2 * kMaxAsyncIterations; i += blockDim.x) tile_ticket[i] = 0ull;
+    if (tile_ticket) for (int i = threadIdx.x; i < kTicketWords * kMaxAsyncIterations; i += blockDim.x) tile_ticket[i] = 0ull;
     if (threadIdx.x == 0) {
         // (the tile-ticket counters are reset by every lane below)
         for (int i = 0; i < 16; ++i) st->T[i] = T0.m[i];
@@ -2521,7 +2586,7 @@ cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* 
 }
 
 // One warm iteration of P2P / GICP (search + linearisation + reduction + solve) = the reuse kernel, then the refresh kernel.
-cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, const IcpWork& wk, int reuse_grid,
+cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
                                   cudaStream_t s) {
     const cudaError_t e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
                                           : launch_pdl(icp_warm_reuse_kernel<1>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
@@ -2542,7 +2607,12 @@ cudaError_t launch_icp_warm(const MapView& map, const float* scan, const IcpPara
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-int icp_warm_refresh_async_grid(int num_sms) { return num_sms < 128 ? num_sms : 128; }
+// Blocks of the concurrent refresh kernel.  A refresh block (128 threads x 128 registers) becomes resident beside THREE reuse blocks
+// of an SM, not beside four, and the fold needs every refresh block: the last one to start gates the iteration.
+int icp_warm_refresh_async_grid(int num_sms, int want) {
+    const int g = want > 0 ? want : 128;
+    return num_sms < g ? num_sms : g;
+}
 cudaError_t launch_icp_warm_refresh_async(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
                                           int grid, int solve_here, cudaStream_t s) {
     const cudaError_t e = prm.method == 0

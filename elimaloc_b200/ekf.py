@@ -46,9 +46,12 @@ class EkfAlgorithm:
         check(lib().elm_ekf_create(C.byref(self._h), C.byref(cfg), int(device), C.c_void_p(stream) if stream else None))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().elm_ekf_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().elm_ekf_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown: the module globals may already be gone)
+                pass
 
     def RunPredictionImu(self, cur_timestamp, gyro, acc):
         g = np.ascontiguousarray(gyro, dtype=np.float64)

@@ -51,9 +51,12 @@ class ScanPipeline:
         check(lib().elm_scan_pipeline_create(C.byref(self._h), registration._h, C.byref(cfg)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().elm_scan_pipeline_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().elm_scan_pipeline_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown: the module globals may already be gone)
+                pass
 
     def deskew(self, xyz, point_time, stamp, queues):
         """-> (deskew_ok, time_scan_cur, time_scan_end); enqueues upload + distance filter + deskew."""

@@ -61,9 +61,12 @@ class VoxelHashMap:
         self.max_points_per_voxel_ = int(max_points_per_voxel)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().elm_map_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().elm_map_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown: the module globals may already be gone)
+                pass
 
     def AddPoints(self, xyz):
         xyz = _xyz(xyz)
@@ -181,9 +184,12 @@ class Registration:
         self.config_ = config
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().elm_registration_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().elm_registration_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown: the module globals may already be gone)
+                pass
 
     def RunRegister(self, source_local, voxel_map, initial_guess, m_config=None, fitness_score=0.0):
         """Returns (pose 4x4, is_success, fitness_score, local_cov 6x6); fitness_score is passed through
