@@ -33,7 +33,7 @@ namespace {
 #define ELM_DEFAULT_WARM_MODE 2
 #endif
 #ifndef ELM_DEFAULT_ASYNC_GRID
-#define ELM_DEFAULT_ASYNC_GRID 128
+#define ELM_DEFAULT_ASYNC_GRID 80
 #endif
 constexpr int kDefaultWarmMode = ELM_DEFAULT_WARM_MODE;
 constexpr int kDefaultAsyncGrid = ELM_DEFAULT_ASYNC_GRID;
@@ -478,7 +478,7 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
             // kernel is then the kernel right before this one), its refresh kernel for the reuse blocks' counter
             chained = true;
             wk.chain = 1;
-            wk.chain_wait = r->chain_prev ? wk.tile_ticket - elm::kTicketWords + 3 : nullptr;
+            wk.chain_prev = r->chain_prev ? wk.tile_ticket - elm::kTicketWords : nullptr;
         }
         ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), d_scan, prm, r->d_state, wk, wgrid, r->stream));
         if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));

@@ -107,7 +107,8 @@ struct IcpWork {
     // kernel) are replaced by the counters [2] / [3] above, so consecutive kernels hand over through HBM flags instead of waiting for
     // a whole grid to drain and the dependent grid to be released
     int chain;                                // 1: the reuse blocks count themselves in [2], the refresh kernel waits for [2] and sets [3]
-    const unsigned long long* chain_wait;     // reuse kernel: wait for this word (the previous iteration's [3]) instead of the previous grid; NULL: griddepcontrol.wait
+    const unsigned long long* chain_prev;     // reuse kernel: the previous iteration's counters when that iteration was chained too (the kernel waits
+                                              // for them instead of the previous grid and requests its inputs ahead of the solve); NULL: griddepcontrol.wait
 };
 
 // Lives in HBM for the whole ICP loop; the host reads it back once at the end.

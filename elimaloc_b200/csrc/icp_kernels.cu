@@ -749,9 +749,16 @@ __device__ __forceinline__ void linearize_voxel_pair(double* acc, const double* 
 
 // Block tree over per-lane accumulators: warp shuffles, then the 8 warps in fixed order; thread k < 29 ADDS the block's
 // sum of canonical slot k to s_sum[k].  Every thread of the block must call it.
+// The warp stage is a reduce-SCATTER: at the step with lane distance o a lane keeps one half of its values (the lower half if its bit o
+// is clear) and hands the other half to its partner, so after the five steps lane l holds the warp's total of accumulator l — 31
+// 64-bit exchanges per lane where a butterfly over all NACC values needs 5 NACC (shuffles issue at one warp instruction per clock
+// per SM, and every block of the grid reaches this point at the same time: the butterfly cost ~2.6 us per P2P iteration).  Each
+// total is formed by the same pairing tree as the butterfly's (distance 16, 8, 4, 2, 1; IEEE addition commutes): bit-identical sums.
 template <int NACC, bool IS_P2P, int WARPS = kIcpWarps>
 __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc], double* s_sum) {
+    static_assert(NACC > 16 && NACC <= 32, "the first step pairs accumulator k with k + 16");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef ELM_BUTTERFLY_REDUCE
 #pragma unroll
     for (int k = 0; k < NACC; ++k) {
         double v = acc[k];
@@ -770,6 +777,34 @@ __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc
         s_sum[tid] += v;
     }
     __syncthreads();
+#else
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {  // accumulators k + 16 >= NACC do not exist: zero
+            const double hi = (k + 16 < NACC) ? acc[k + 16 < NACC ? k + 16 : 0] : 0.0;
+            const double send = up ? acc[k] : hi, keep = up ? hi : acc[k];
+            acc[k] = keep + __shfl_xor_sync(kFull, send, 16);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+            const double send = up ? acc[k] : acc[k + o], keep = up ? acc[k + o] : acc[k];
+            acc[k] = keep + __shfl_xor_sync(kFull, send, o);
+        }
+    }
+    if (lane < NACC) s_red[warp][lane] = acc[0];  // lane l: the warp's total of accumulator l
+    __syncthreads();
+    if (tid < 29) {
+        double v = 0.0;
+        for (int w = 0; w < WARPS; ++w) v += IS_P2P ? expand_p2p(s_red[w], tid) : s_red[w][tid < NACC ? tid : 0];
+        s_sum[tid] += v;
+    }
+    __syncthreads();
+#endif
 }
 
 #ifdef ELM_PHASE_TIMING
@@ -1609,14 +1644,21 @@ __device__ __forceinline__ bool flag_await(const unsigned long long* p, unsigned
     return ok;
 }
 
-template <int METHOD>
+// CHAIN = true: the chained variant (IcpWork::chain).  Instead of waiting for the previous grid it (1) waits until the per-query data of
+// the previous iteration is final — every reuse block of that iteration has counted itself in and every chunk of its refresh kernel is
+// complete — and requests its memo, its previous match and the first four entries of its candidate list (cp.async into shared memory)
+// while the previous iteration's last block is still reducing and solving, then (2) waits for that iteration's solve flag and only needs
+// the new pose: the memory round trips of the search leave the critical path of the iteration.
+template <int METHOD, bool CHAIN>
 __global__ void __launch_bounds__(kIcpThreads, METHOD == 1 ? 3 : 4)
 icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* st, IcpWork wk) {
     constexpr int NACC = AccSize<METHOD>::value;
+    constexpr int kPref = 4;  // candidates requested ahead per query (the lists hold 1.8 on average)
     __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
     __shared__ double s_red[kIcpWarps][kAcc], s_sum[kAcc];
     __shared__ int s_done;
     __shared__ unsigned int s_wcnt[kIcpWarps];
+    __shared__ __align__(16) float4 s_pref[CHAIN ? kPref : 1][CHAIN ? kIcpThreads : 1];
 
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1629,22 +1671,49 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
     int gi = blockIdx.x * kIcpThreads + tid;
     float sxf = 0.f, syf = 0.f, szf = 0.f;
     if (gi < prm.n) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
-    if (wk.chain_wait) {
-        // chain mode: the previous kernel is the refresh kernel of the previous iteration, and what this kernel needs of it (and of
-        // everything before it) is complete and visible as soon as its last block has solved and released the iteration's flag — no
-        // wait for that grid to drain and for this grid to be released (4-8 us per iteration, profiles/trace_async.py).  Every kernel
-        // this one could wait for was completely resident before this grid was launched (launch_dependents is the first thing its
-        // blocks do), so the spin cannot starve it.
-        if (tid == 0 && !flag_await(wk.chain_wait, 1ull)) { st->comm_error = 2; st->done = 1; __threadfence(); }
-        __syncthreads();
-    } else {
-        pdl_wait();
-    }
     // the first query's memo is requested BEFORE the pose is staged in shared memory: both loads share one round trip
     uint4 m0 = make_uint4(kNone, kNone, kNone, kNone), m1 = make_uint4(0, 0, 0, 0);
     uint32_t nc = kNone;
     float4 prev = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
-    if (gi < prm.n) { m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi]; }
+    bool pref = false;  // (CHAIN) the first kPref list entries of this thread's first query are in s_pref
+    if (CHAIN && wk.chain_prev) {
+        // Every kernel this one can wait for was completely resident before this grid was launched (launch_dependents is the first
+        // thing its blocks do), so the spins cannot starve it.
+        const unsigned long long* const pv = wk.chain_prev;
+        const unsigned long long rows = gridDim.x, chunks = static_cast<unsigned long long>(((prm.n + kIcpThreads - 1) / kIcpThreads + 15) / 16);
+        if (tid == 0) {
+            // (1) the previous iteration's per-query data is final ([2] reuse blocks counted in, [1] chunks of its refresh kernel complete),
+            //     or that iteration has already released its flag (loop left: its refresh kernel completes no chunks)
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned long long a, b, c;
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(pv + 2) : "memory");
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(b) : "l"(pv + 1) : "memory");
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(pv + 3) : "memory");
+                if ((a >= rows && b >= chunks) || c != 0ull) break;
+                if (clock64() - t0 > 4000000000ll) { st->comm_error = 2; st->done = 1; break; }
+                __nanosleep(100);
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+        __syncthreads();
+        if (gi < prm.n) {
+            m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi];
+            // (the list has cand_cap >= kPref slots whatever its length: entries past the end are never looked at)
+            const float4* const src = wk.cand + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(tid);
+#pragma unroll
+            for (int u = 0; u < kPref; ++u)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s_pref[u][tid])), "l"(src + static_cast<size_t>(u) * kIcpThreads) : "memory");
+            pref = ccap >= static_cast<uint32_t>(kPref);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // (2) the previous iteration's solve
+        if (tid == 0 && !flag_await(pv + 3, 1ull)) { st->comm_error = 2; st->done = 1; __threadfence(); }
+        __syncthreads();
+    } else {
+        pdl_wait();
+        if (gi < prm.n) { m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi]; }
+    }
     ELM_TRACE_FIRST(2);
     if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
     if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
@@ -1655,10 +1724,11 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
         if (wk.epoch && tid == 0)
             for (int t = blockIdx.x; t * kIcpThreads < prm.n; t += gridDim.x)
                 flag_store_release(wk.tile_flag + t, (static_cast<unsigned long long>(wk.epoch) << 32) | 0xffffffffull);
-        if (wk.chain && tid == 0) {  // nobody solves in this iteration: block 0 lets the next reuse kernel through (it will see `done` too)
+        if (CHAIN && tid == 0) {  // nobody solves in this iteration: block 0 lets the next reuse kernel through (it will see `done` too)
             if (blockIdx.x == 0) flag_store_release(wk.tile_ticket + 3, 1ull);
             atomicAdd(wk.tile_ticket + 2, 1ull);
         }
+        if (CHAIN) asm volatile("cp.async.wait_all;" ::: "memory");  // (no copy may be in flight into the shared memory of a block that has exited)
         return;
     }
     for (bool first = true; gi - tid < prm.n; gi += gridDim.x * kIcpThreads, first = false) {
@@ -1721,38 +1791,32 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
                 // tie) the list is decided again exactly
                 const Query Q(px, py, pz);
                 float m = kInf, s2 = kInf;
-#ifdef ELM_REUSE_KEEP_BEST
-                float4 best = wpt;  // the fp32 argmin itself stays in registers: no dependent reload of the winner (one L2 round trip per tile)
-#else
                 uint32_t mj = 0;
-#endif
+                if (CHAIN && pref && first) asm volatile("cp.async.wait_all;" ::: "memory");  // (this thread's own copies: no barrier needed)
                 for (uint32_t j = 0; j < nc; j += 4) {
                     float4 c[4];  // (addresses past the list are clamped, not predicated: a predicated load sent c[] to local memory)
+                    if (CHAIN && pref && first && j == 0) {
 #pragma unroll
-                    for (uint32_t u = 0; u < 4; ++u) c[u] = my_cand[static_cast<size_t>(min(j + u, nc - 1)) * cstride];
+                        for (uint32_t u = 0; u < 4; ++u) c[u] = s_pref[u][tid];  // (entries past the list: masked below like the clamped ones)
+                    } else {
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; ++u) c[u] = my_cand[static_cast<size_t>(min(j + u, nc - 1)) * cstride];
+                    }
 #pragma unroll
                     for (uint32_t u = 0; u < 4; ++u) {
                         const float dx = c[u].x - Q.fx, dy = c[u].y - Q.fy, dz = c[u].z - Q.fz;
                         float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                         d = (j + u < nc) ? d : kInf;
-#ifdef ELM_REUSE_KEEP_BEST
-                        s2 = fminf(s2, fmaxf(d, m));
-                        if (d < m) best = c[u];  // (d < m implies j + u < nc: this IS candidate j + u)
-                        m = fminf(m, d);
-#else
                         s2 = fminf(s2, fmaxf(d, m)); mj = (d < m) ? j + u : mj; m = fminf(m, d);
-#endif
                     }
                 }
                 visited += nc;
                 const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);
                 const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
                 if (s2 > T) {  // (the exact distance of the unique winner is not needed: nothing is left to compare it with)
-#ifdef ELM_REUSE_KEEP_BEST
-                    wpt = best;
-#else
-                    wpt = my_cand[static_cast<size_t>(mj) * cstride];
-#endif
+                    // (re-reading the winner is an L1 hit; keeping it in registers instead measured no gain: profiles/r02_ab_chain.txt)
+                    if (CHAIN && pref && first && mj < static_cast<uint32_t>(kPref)) wpt = s_pref[mj][tid];
+                    else wpt = my_cand[static_cast<size_t>(mj) * cstride];
                 } else {       // near tie (or an empty list): every candidate exactly, smallest rank (read from the map) among equals
                     Best b;
                     for (uint32_t j = 0; j < nc; ++j) {
@@ -1783,7 +1847,8 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
         }
     }
     publish_partials(s_sum, prm, wk.partials, static_cast<int>(blockIdx.x));
-    if (wk.chain) {  // everything this block wrote (matches, memos, its row of sums) is visible before the block counts itself in
+    if (CHAIN) {  // everything this block wrote (matches, memos, its row of sums) is visible before the block counts itself in
+        asm volatile("cp.async.wait_all;" ::: "memory");  // (threads without a query never waited for their group)
         __threadfence();
         __syncthreads();
         if (tid == 0) { __threadfence(); atomicAdd(wk.tile_ticket + 2, 1ull); }
@@ -2086,10 +2151,11 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
         } else if (tid < kAcc) {
             crow[tid] = 0.0;
         }
-        // the chunk's row is complete: count it (the fold below waits for all chunks of this iteration)
-        if (tid < kAcc) __threadfence();
+        // the chunk's row is complete: count it (the fold below waits for all chunks of this iteration; in the chained mode the NEXT
+        // reuse kernel reads what the stragglers of this chunk were given as soon as all chunks are counted: every thread fences)
+        if (wk.chain || tid < kAcc) __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(wk.tile_ticket + 1, 1ull);
+        if (tid == 0) { if (wk.chain) __threadfence(); atomicAdd(wk.tile_ticket + 1, 1ull); }
     }
     // the pose of this iteration, fetched in the shadow of the reuse kernel: any flag of this epoch proves that the previous
     // iteration's solve is complete and visible (blocks that handled a chunk have seen one already)
@@ -2133,13 +2199,18 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
         }
     }
     if (tid == 0) {
-        int d = st->done;
+        // the done flag and the chunk counter are requested together (they used to be two dependent round trips)
+        int d = *reinterpret_cast<volatile int*>(&st->done);
+        unsigned long long c = ~0ull;
+        if (wk.epoch) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(wk.tile_ticket + 1) : "memory");
         if (!d && wk.epoch) {  // every chunk row of this iteration must be complete (written by OTHER blocks of this grid)
             const long long t0 = clock64();
-            while (flag_load_acquire(wk.tile_ticket + 1) < static_cast<unsigned long long>(nchunks)) {
+            while (c < static_cast<unsigned long long>(nchunks)) {
                 if (clock64() - t0 > 4000000000ll) { st->comm_error = 2; st->done = 1; d = 1; break; }
                 __nanosleep(32);
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(wk.tile_ticket + 1) : "memory");
             }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");  // (acquire: the chunk rows read below)
         }
         s_flagdone = d;
     }
@@ -2588,8 +2659,11 @@ cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* 
 // One warm iteration of P2P / GICP (search + linearisation + reduction + solve) = the reuse kernel, then the refresh kernel.
 cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
                                   cudaStream_t s) {
-    const cudaError_t e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
-                                          : launch_pdl(icp_warm_reuse_kernel<1>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
+    cudaError_t e;
+    if (wk.chain) e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0, true>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
+                                      : launch_pdl(icp_warm_reuse_kernel<1, true>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
+    else e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0, false>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
+                             : launch_pdl(icp_warm_reuse_kernel<1, false>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,

@@ -9,6 +9,7 @@ Timing as bench.py's `value`: CUDA events on the launch stream around K enqueued
 scan every step, after 3 warm-up steps.  Prints one line per variant: iterations/s, us per iteration, the pose difference to the first
 variant (same summation grid: must be 0.0; another grid: rounding level) and one JSON line with everything at the end."""
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -31,12 +32,14 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--m-raw", type=int, default=10_000_000)
 args = ap.parse_args()
 
-METHOD = {"p2p": E.P2P, "gicp": E.GICP}
+METHOD = {"p2p": E.P2P, "gicp": E.GICP, "vgicp": E.VGICP, "avgicp": E.AVGICP}
 methods = [m for m in args.methods.split(",") if m]
 gm = E.VoxelHashMap(1.0, 30, device=0)
 gm.AddPoints(synth.map_u(args.m_raw, 100.0))
 if "gicp" in methods:
     gm.CalPointCovAll(0.4)
+if "vgicp" in methods or "avgicp" in methods:
+    gm.CalVoxelCovAll()
 T0 = synth.se3([50, 50, 50], np.deg2rad([1.0, -2.0, 30.0]))
 stream = torch.cuda.Stream(device=0)
 torch.cuda.set_stream(stream)
@@ -48,9 +51,11 @@ for mname in methods:
         ref_pose = {}
         broken = set()
         for mode in args.modes.split(","):  # (the established mode first: a broken experimental mode cannot cost the other numbers)
-            for grid in [int(v) for v in args.grids.split(",")]:
+            for gidx, grid in enumerate(int(v) for v in args.grids.split(",")):
                 if mode in broken:
                     continue
+                if mname in ("vgicp", "avgicp") and (mode != args.modes.split(",")[0] or gidx > 0):
+                    continue  # (no warm iterations: one line per size)
                 os.environ["ELM_WARM_MODE"] = mode
                 os.environ["ELM_ASYNC_GRID"] = str(grid)
                 reg = E.Registration(device=0, stream=stream.cuda_stream)
@@ -86,9 +91,10 @@ for mname in methods:
                     ref_pose[grid] = T
                 d_first = float(np.abs(T - next(iter(ref_pose.values()))).max())
                 row = dict(method=mname, n=n, mode=mode, grid=grid, it_per_s=1e6 / us_it, us_per_iteration=us_it, iterations=it, success=bool(ok),
-                           pose_diff_same_grid=d_same, pose_diff_first=d_first, lib=os.environ.get("ELIMALOC_B200_LIB", "default"))
+                           pose_diff_same_grid=d_same, pose_diff_first=d_first, lib=os.environ.get("ELIMALOC_B200_LIB", "default"),
+                           pose_sha=hashlib.sha1(np.ascontiguousarray(T).tobytes() + np.float64(fit).tobytes()).hexdigest()[:12])
                 out.append(row)
                 print(f"{mname:5s} n={n:7d} {mode:6s} grid={grid:4d}  {row['it_per_s']:9.0f} it/s  {us_it:7.2f} us/it  iters={it} ok={ok} "
-                      f"dpose(same grid)={d_same} dpose(first)={d_first:.2e}", flush=True)
+                      f"dpose(same grid)={d_same} dpose(first)={d_first:.2e} sha={row['pose_sha']}", flush=True)
                 del reg
 print(json.dumps(out))
