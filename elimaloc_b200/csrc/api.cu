@@ -27,16 +27,6 @@
 #include "scan_prep.cuh"
 
 namespace {
-// how the warm iterations after the first of a call run when ELM_WARM_MODE does not say (elm_registration::warm_mode: 2 async, 3 chain),
-// and the blocks of the concurrent refresh kernel when ELM_ASYNC_GRID does not say
-#ifndef ELM_DEFAULT_WARM_MODE
-#define ELM_DEFAULT_WARM_MODE 2
-#endif
-#ifndef ELM_DEFAULT_ASYNC_GRID
-#define ELM_DEFAULT_ASYNC_GRID 80
-#endif
-constexpr int kDefaultWarmMode = ELM_DEFAULT_WARM_MODE;
-constexpr int kDefaultAsyncGrid = ELM_DEFAULT_ASYNC_GRID;
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -202,8 +192,7 @@ struct elm_registration {
     double* d_tile_rows = nullptr;                // ... per-tile sums, (match_cap / 256 + 1) x 32
     unsigned long long* d_tile_ticket = nullptr;  // ... tiles handed out since the call began
     unsigned int warm_epoch = 0;                  // epoch of the last warm iteration enqueued on this handle
-    int async_iterations = 0;                     // concurrent-refresh iterations enqueued since the call began (each owns a set of tile counters)
-    bool chain_prev = false;                      // the last iteration enqueued on this handle was a chained one of the current call
+    int async_iterations = 0;                     // concurrent-refresh iterations enqueued since the call began (each owns a pair of tile counters)
     int cand_cap = 32;
     size_t match_cap = 0;
     int warm = 1;              // P2P / GICP: iterations after the first start their search from the previous match (same result)
@@ -211,14 +200,12 @@ struct elm_registration {
     //   0 "pair"    icp_warm_reuse_kernel, then icp_warm_refresh_kernel
     //   1 "single"  ONE kernel, icp_warm_kernel (stragglers refreshed in place by their own warp)
     //   2 "async"   icp_warm_reuse_kernel with icp_warm_refresh_async_kernel running BESIDE it (the stragglers leave the critical path)
-    //   3 "chain"   as async, and the two kernels of consecutive iterations hand over through flags in HBM (icp_device.cuh: IcpWork::chain)
-    //               instead of waiting for the previous grid to drain; single GPU / peer exchange only (the solve must sit in the kernel)
     // Measured on B200 (profiles/r02_ab_warm_modes.txt): async 35.2k / 21.5k iterations/s (P2P / GICP), single 32.4k / 20.6k, pair 31.1k / 18.5k.
     // Default (-1): async.  ELM_WARM_MODE=pair|single|async forces one (A/B switch).
     int warm_mode = [] {
         const char* e = getenv("ELM_WARM_MODE");
         if (!e) return -1;
-        return e[0] == 'p' ? 0 : (e[0] == 's' ? 1 : (e[0] == 'a' ? 2 : (e[0] == 'c' ? 3 : -1)));
+        return e[0] == 'p' ? 0 : (e[0] == 's' ? 1 : (e[0] == 'a' ? 2 : -1));
     }();
     int async_grid = [] {  // blocks of the concurrent refresh kernel (A/B switch ELM_ASYNC_GRID; 0 = the built-in default)
         const char* e = getenv("ELM_ASYNC_GRID");
@@ -285,7 +272,7 @@ struct elm_registration {
     void* peer_opened[elm::kMaxPeers] = {};
     bool sharded() const { return comm != nullptr || peer.world > 0; }
     elm::IcpWork work() const { return elm::IcpWork{d_match, d_win, d_memo, match_cap, d_ncand, d_cand, cand_cap, d_refresh, d_refresh ? d_refresh + match_cap : nullptr, d_partials, d_ticket,
-                                                   d_tile_flag, d_tile_rows, d_tile_ticket, 0u, 0, nullptr}; }
+                                                   d_tile_flag, d_tile_rows, d_tile_ticket, 0u}; }
     double warm_margin_vox = 0.08;  // refresh margin of the warm search in voxel sizes
 
     ~elm_registration() {
@@ -432,7 +419,7 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // P2P / GICP: search, linearisation, reduction and solve are ONE kernel (unless the search runs on the binned copy,
     // whose order differs from the caller's: then the accumulation stays a separate launch in the caller's order)
     const bool fuse = r->fuse && prm0.method <= ELM_GICP && !(r->use_sorted && !r->sorted_all);
-    const int wgrid = elm::icp_warm_grid(prm0, r->num_sms), rgrid = elm::icp_warm_refresh_grid(prm0, r->num_sms), xgrid = elm::icp_warm_refresh_async_grid(r->num_sms, r->async_grid > 0 ? r->async_grid : kDefaultAsyncGrid);
+    const int wgrid = elm::icp_warm_grid(prm0, r->num_sms), rgrid = elm::icp_warm_refresh_grid(prm0, r->num_sms), xgrid = elm::icp_warm_refresh_async_grid(r->num_sms, r->async_grid);
     int rc = ensure_partials(r, std::max(std::max(sgrid, agrid), wgrid + std::max(rgrid, xgrid)));
     if (rc) return rc;
     rc = ensure_match(r, prm0.n);
@@ -457,14 +444,13 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
     // P2P / GICP from the second iteration of a call on: the warm pair of kernels (reuse: search + linearisation of the
     // queries whose candidate lists still hold; refresh: the rest, then reduction and solve)
     const bool use_warm = warm && r->warm && r->prune && !mapped && !fuse && prm.method <= ELM_GICP;
-    const int warm_mode = r->warm_mode >= 0 ? r->warm_mode : kDefaultWarmMode;
-    bool chained = false;
+    const int warm_mode = r->warm_mode >= 0 ? r->warm_mode : 2;
     if (use_warm && warm_mode == 1 && r->warm_iterations_enqueued > 0) {
         // every warm iteration after the first: ONE kernel (stragglers refreshed in place by their own warp)
         if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
         ELM_CUDA(elm::launch_icp_warm(map->view(), d_scan, prm, r->d_state, wk, wgrid, solve_here, r->stream));
         r->launches += 1;
-    } else if (use_warm && warm_mode >= 2 && r->warm_iterations_enqueued > 0 && r->async_iterations < elm::kMaxAsyncIterations) {
+    } else if (use_warm && warm_mode == 2 && r->warm_iterations_enqueued > 0 && r->async_iterations < elm::kMaxAsyncIterations) {
         // ... or the reuse kernel with the refresh kernel running beside it: the reuse blocks publish every tile's work list under
         // this iteration's epoch, the refresh blocks take the tiles as they arrive
         if (++r->warm_epoch == 0) {  // (wrapped: forget every flag)
@@ -472,14 +458,7 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
             r->warm_epoch = 1;
         }
         wk.epoch = r->warm_epoch;
-        wk.tile_ticket = r->d_tile_ticket + elm::kTicketWords * static_cast<size_t>(r->async_iterations++);
-        if (warm_mode == 3 && solve_here) {
-            // chained: this reuse kernel waits for the previous iteration's solve flag (when that iteration was chained too: its refresh
-            // kernel is then the kernel right before this one), its refresh kernel for the reuse blocks' counter
-            chained = true;
-            wk.chain = 1;
-            wk.chain_prev = r->chain_prev ? wk.tile_ticket - elm::kTicketWords : nullptr;
-        }
+        wk.tile_ticket = r->d_tile_ticket + 2 * static_cast<size_t>(r->async_iterations++);
         ELM_CUDA(elm::launch_icp_warm_reuse(map->view(), d_scan, prm, r->d_state, wk, wgrid, r->stream));
         if (r->profiling) ELM_CUDA(cudaEventRecord(r->ev[r->ev_used + 1], r->stream));
         ELM_CUDA(elm::launch_icp_warm_refresh_async(map->view(), d_scan, prm, r->d_state, wk, wgrid, xgrid, solve_here, r->stream));
@@ -514,7 +493,6 @@ int enqueue_linearize(elm_registration* r, const elm_map* map, const float* d_sc
         r->ev_used += 3;
     }
     r->warm_iterations_enqueued = use_warm ? r->warm_iterations_enqueued + 1 : 0;
-    r->chain_prev = chained;
     if (use_nccl) {
         const int e = g_nccl.AllReduce(r->d_state->acc, r->d_state->acc, elm::kAcc, kNcclFloat64, kNcclSum, r->comm, r->stream);
         if (e != 0) return fail(ELM_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(e));
@@ -840,8 +818,8 @@ int elm_registration_create(elm_registration** out, int device, void* stream) tr
     }
     if (cudaMalloc(reinterpret_cast<void**>(&r->d_ticket), sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(r->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&r->d_tile_ticket), elm::kTicketWords * elm::kMaxAsyncIterations * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(r->d_tile_ticket, 0, elm::kTicketWords * elm::kMaxAsyncIterations * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&r->d_tile_ticket), 2 * elm::kMaxAsyncIterations * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(r->d_tile_ticket, 0, 2 * elm::kMaxAsyncIterations * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&r->d_state), sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMemset(r->d_state, 0, sizeof(elm::IcpState)) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&r->h_state), sizeof(elm::IcpState)) != cudaSuccess) {
@@ -874,7 +852,6 @@ int elm_register_enqueue(elm_registration* reg, const elm_map* map, const float*
     const elm::IcpParams prm = make_params(reg, cfg, n);
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T_init, reg->d_ticket, reg->d_tile_ticket, reg->stream));
     reg->async_iterations = 0;
-    reg->chain_prev = false;
     reg->launches += 1;
     rc = enqueue_binning(reg, map, d_src_xyz, n, T_init, cfg->icp_method);
     if (rc) return rc;
@@ -954,7 +931,6 @@ int elm_linearize(elm_registration* reg, const elm_map* map, const float* src_xy
     const elm::IcpParams prm = make_params(reg, cfg, n);
     ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->d_tile_ticket, reg->stream));
     reg->async_iterations = 0;
-    reg->chain_prev = false;
     rc = enqueue_binning(reg, map, reg->d_scan, n, T, cfg->icp_method);
     if (rc) return rc;
     rc = enqueue_linearize(reg, map, reg->d_scan, prm, false);
@@ -1003,7 +979,6 @@ int elm_correspondences_sequence(elm_registration* reg, const elm_map* map, cons
         const double* T = T_seq + 16 * static_cast<size_t>(k);
         ELM_CUDA(elm::launch_icp_begin(reg->d_state, T, reg->d_ticket, reg->d_tile_ticket, reg->stream));
     reg->async_iterations = 0;
-    reg->chain_prev = false;
         if (k == 0) {
             rc = enqueue_binning(reg, map, reg->d_scan, n, T, method);
             if (rc) return rc;

@@ -48,8 +48,7 @@ constexpr int kIdxJtr = 21, kIdxRes = 27, kIdxNcorr = 28, kIdxNtotal = 29;
 // order — bit-identical on all ranks, no broadcast, no separate collective launch.  The slots are self-validating
 // ("LL" style): every fp64 value travels as two 8-byte words {32 data bits, 32-bit sequence tag}; an 8-byte store is
 // atomic, so a word whose tag matches carries valid data — no fence, no separate flag write, ONE NVLink hop.
-constexpr int kMaxAsyncIterations = 1024;  // concurrent-refresh iterations per call that own a set of tile counters (beyond: pair mode)
-constexpr int kTicketWords = 4;            // counters per concurrent-refresh iteration (IcpWork::tile_ticket)
+constexpr int kMaxAsyncIterations = 1024;  // concurrent-refresh iterations per call that own a pair of tile counters (beyond: pair mode)
 constexpr int kMaxPeers = 8;
 struct PeerMailbox {
     unsigned long long word[2][kMaxPeers][kAcc][2];  // [parity][source rank][accumulator][low / high half]: data | tag << 32
@@ -99,16 +98,9 @@ struct IcpWork {
     unsigned long long* tile_flag;   // [tiles] {epoch << 32 | stragglers of the tile; all ones in the low word = loop already left}, published by the
                                      // reuse kernel as soon as the tile's work list is complete
     double* tile_rows;               // [chunks of 16 tiles][kAcc] sums of the chunk's refreshed correspondences
-    unsigned long long* tile_ticket; // THIS iteration's counters: [0] chunks handed out, [1] chunk rows completed, [2] reuse blocks finished,
-                                     // [3] solve of this iteration done (icp_begin_kernel zeroes the kTicketWords counters of all
-                                     // kMaxAsyncIterations iterations of a call)
+    unsigned long long* tile_ticket; // THIS iteration's pair of counters: [0] chunks handed out, [1] chunk rows completed (icp_begin_kernel zeroes
+                                     // the pairs of all kMaxAsyncIterations iterations of a call)
     unsigned int epoch;              // this iteration's epoch (0: no flags are published)
-    // chained iterations ("chain" mode): the two grid-completion waits of a warm iteration (reuse grid -> fold, solve -> next reuse
-    // kernel) are replaced by the counters [2] / [3] above, so consecutive kernels hand over through HBM flags instead of waiting for
-    // a whole grid to drain and the dependent grid to be released
-    int chain;                                // 1: the reuse blocks count themselves in [2], the refresh kernel waits for [2] and sets [3]
-    const unsigned long long* chain_prev;     // reuse kernel: the previous iteration's counters when that iteration was chained too (the kernel waits
-                                              // for them instead of the previous grid and requests its inputs ahead of the solve); NULL: griddepcontrol.wait
 };
 
 // Lives in HBM for the whole ICP loop; the host reads it back once at the end.

@@ -752,23 +752,82 @@ __device__ __forceinline__ void linearize_voxel_pair(double* acc, const double* 
 // The warp stage is a reduce-SCATTER: at the step with lane distance o a lane keeps one half of its values (the lower half if its bit o
 // is clear) and hands the other half to its partner, so after the five steps lane l holds the warp's total of accumulator l — 31
 // 64-bit exchanges per lane where a butterfly over all NACC values needs 5 NACC (shuffles issue at one warp instruction per clock
-// per SM, and every block of the grid reaches this point at the same time: the butterfly cost ~2.6 us per P2P iteration).  Each
-// total is formed by the same pairing tree as the butterfly's (distance 16, 8, 4, 2, 1; IEEE addition commutes): bit-identical sums.
+// per SM, and every block of the grid reaches this point at the same time).  Each total is formed by the same pairing tree as the
+// butterfly's (distance 16, 8, 4, 2, 1; IEEE addition commutes): bit-identical sums (tests/test_block_reduce_model.py; on the B200 the
+// pose checksums of both builds are equal, profiles/r02_ab_reduce_scatter_*.txt).  Measured: GICP +11 %, VGICP +3.5 %, AVGICP +2.8 %.
+// -DELM_BUTTERFLY_REDUCE keeps the butterfly everywhere, -DELM_P2P_BUTTERFLY for the 18 structured sums of P2P only (A/B switches).
+#if defined(ELM_BUTTERFLY_REDUCE)
+constexpr bool kButterflyAll = true, kButterflyP2p = true;
+#elif defined(ELM_P2P_BUTTERFLY)
+constexpr bool kButterflyAll = false, kButterflyP2p = true;
+#else
+constexpr bool kButterflyAll = false, kButterflyP2p = false;
+#endif
+// P2P: where lane l's total (accumulator l of the 18 structured sums) goes in the canonical row — expand_p2p read backwards.
+// {slot 0, slot 1, slot 2} one byte each (0xff: none), bit 24: the lane writes zeros (the structurally zero slots), bit 25: slot 1 is negated
+#define ELM_SC(a, b, c, f) (static_cast<uint32_t>(a) | (static_cast<uint32_t>(b) << 8) | (static_cast<uint32_t>(c) << 16) | (static_cast<uint32_t>(f) << 24))
+__constant__ uint32_t kP2pScatter[32] = {
+    ELM_SC(0, 6, 11, 0),          // a[0]: the I block (0,0) (1,1) (2,2)
+    ELM_SC(10, 13, 0xff, 2),      // a[1]: (1,5) = bx, (2,4) = -bx
+    ELM_SC(12, 5, 0xff, 2),       // a[2]: (2,3) = by, (0,5) = -by
+    ELM_SC(4, 8, 0xff, 2),        // a[3]: (0,4) = bz, (1,3) = -bz
+    ELM_SC(15, 0xff, 0xff, 0), ELM_SC(16, 0xff, 0xff, 0), ELM_SC(17, 0xff, 0xff, 0), ELM_SC(18, 0xff, 0xff, 0), ELM_SC(19, 0xff, 0xff, 0), ELM_SC(20, 0xff, 0xff, 0),  // a[4..9]
+    ELM_SC(21, 0xff, 0xff, 0), ELM_SC(22, 0xff, 0xff, 0), ELM_SC(23, 0xff, 0xff, 0), ELM_SC(24, 0xff, 0xff, 0), ELM_SC(25, 0xff, 0xff, 0), ELM_SC(26, 0xff, 0xff, 0),  // a[10..15]
+    ELM_SC(27, 0xff, 0xff, 0), ELM_SC(28, 0xff, 0xff, 0),                                                                                                                // a[16], a[17]
+    ELM_SC(1, 2, 3, 1), ELM_SC(7, 9, 14, 1),                                                                                                                             // zeros
+    ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0),
+    ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0), ELM_SC(0xff, 0xff, 0xff, 0)};
+#undef ELM_SC
 template <int NACC, bool IS_P2P, int WARPS = kIcpWarps>
 __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc], double* s_sum) {
     static_assert(NACC > 16 && NACC <= 32, "the first step pairs accumulator k with k + 16");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#ifdef ELM_BUTTERFLY_REDUCE
+    if (kButterflyAll || (IS_P2P && kButterflyP2p)) {
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) {
-        double v = acc[k];
+        for (int k = 0; k < NACC; ++k) {
+            double v = acc[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        acc[k] = v;
-    }
-    if (lane == 0) {
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            acc[k] = v;
+        }
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 29; ++k) s_red[warp][k] = IS_P2P ? expand_p2p(acc, k) : acc[k < NACC ? k : 0];
+            for (int k = 0; k < 29; ++k) s_red[warp][k] = IS_P2P ? expand_p2p(acc, k) : acc[k < NACC ? k : 0];
+        }
+    } else {
+        {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {  // accumulators k + 16 >= NACC do not exist: zero
+                const double hi = (k + 16 < NACC) ? acc[k + 16 < NACC ? k + 16 : 0] : 0.0;
+                const double send = up ? acc[k] : hi, keep = up ? hi : acc[k];
+                acc[k] = keep + __shfl_xor_sync(kFull, send, 16);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int k = 0; k < o; ++k) {
+                const double send = up ? acc[k] : acc[k + o], keep = up ? acc[k + o] : acc[k];
+                acc[k] = keep + __shfl_xor_sync(kFull, send, o);
+            }
+        }
+        // lane l holds the warp's total of accumulator l; the canonical slots of the row (expand_p2p for the 18 structured sums of
+        // P2P) are written by the lanes that hold their sources — no run-time switch (it compiled into jump tables: P2P -32 %)
+        const double v = acc[0];
+        double* const r = s_red[warp];
+        if (IS_P2P) {  // (predicated stores from a per-lane table: a chain of `if (lane == ..)` compiles into a jump table as well)
+            const uint32_t t = kP2pScatter[lane];
+            const uint32_t s0 = t & 0xffu, s1 = (t >> 8) & 0xffu, s2 = (t >> 16) & 0xffu;
+            const double w = (t & (1u << 24)) ? 0.0 : v;
+            const double w1 = (t & (1u << 25)) ? -w : w;
+            if (s0 != 0xffu) r[s0] = w;
+            if (s1 != 0xffu) r[s1] = w1;
+            if (s2 != 0xffu) r[s2] = w;
+        } else if (lane < NACC) {
+            r[lane] = v;
+        }
     }
     __syncthreads();
     if (tid < 29) {
@@ -777,34 +836,6 @@ __device__ __forceinline__ void block_sum_into(double* acc, double (*s_red)[kAcc
         s_sum[tid] += v;
     }
     __syncthreads();
-#else
-    {
-        const bool up = (lane & 16) != 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {  // accumulators k + 16 >= NACC do not exist: zero
-            const double hi = (k + 16 < NACC) ? acc[k + 16 < NACC ? k + 16 : 0] : 0.0;
-            const double send = up ? acc[k] : hi, keep = up ? hi : acc[k];
-            acc[k] = keep + __shfl_xor_sync(kFull, send, 16);
-        }
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int k = 0; k < o; ++k) {
-            const double send = up ? acc[k] : acc[k + o], keep = up ? acc[k + o] : acc[k];
-            acc[k] = keep + __shfl_xor_sync(kFull, send, o);
-        }
-    }
-    if (lane < NACC) s_red[warp][lane] = acc[0];  // lane l: the warp's total of accumulator l
-    __syncthreads();
-    if (tid < 29) {
-        double v = 0.0;
-        for (int w = 0; w < WARPS; ++w) v += IS_P2P ? expand_p2p(s_red[w], tid) : s_red[w][tid < NACC ? tid : 0];
-        s_sum[tid] += v;
-    }
-    __syncthreads();
-#endif
 }
 
 #ifdef ELM_PHASE_TIMING
@@ -1627,38 +1658,15 @@ __device__ __forceinline__ unsigned long long flag_load_acquire(const unsigned l
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// chain mode: ONE thread waits until *p >= target (acquire); false after ~2 s (reported as an error instead of hanging the GPU)
-// (polls with relaxed loads and fences once at the end: an acquire load per poll would invalidate the SM's L1 under the blocks that
-// are still streaming beside the waiting one)
-__device__ __forceinline__ bool flag_await(const unsigned long long* p, unsigned long long target) {
-    const long long t0 = clock64();
-    bool ok = true;
-    for (;;) {
-        unsigned long long v;
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-        if (v >= target) break;
-        if (clock64() - t0 > 4000000000ll) { ok = false; break; }
-        __nanosleep(100);
-    }
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    return ok;
-}
 
-// CHAIN = true: the chained variant (IcpWork::chain).  Instead of waiting for the previous grid it (1) waits until the per-query data of
-// the previous iteration is final — every reuse block of that iteration has counted itself in and every chunk of its refresh kernel is
-// complete — and requests its memo, its previous match and the first four entries of its candidate list (cp.async into shared memory)
-// while the previous iteration's last block is still reducing and solving, then (2) waits for that iteration's solve flag and only needs
-// the new pose: the memory round trips of the search leave the critical path of the iteration.
-template <int METHOD, bool CHAIN>
+template <int METHOD>
 __global__ void __launch_bounds__(kIcpThreads, METHOD == 1 ? 3 : 4)
-icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, IcpState* st, IcpWork wk) {
+icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, const IcpState* __restrict__ st, IcpWork wk) {
     constexpr int NACC = AccSize<METHOD>::value;
-    constexpr int kPref = 4;  // candidates requested ahead per query (the lists hold 1.8 on average)
     __shared__ double s_T[12], s_Tinv[12], s_Rinv[9];
     __shared__ double s_red[kIcpWarps][kAcc], s_sum[kAcc];
     __shared__ int s_done;
     __shared__ unsigned int s_wcnt[kIcpWarps];
-    __shared__ __align__(16) float4 s_pref[CHAIN ? kPref : 1][CHAIN ? kIcpThreads : 1];
 
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1671,49 +1679,12 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
     int gi = blockIdx.x * kIcpThreads + tid;
     float sxf = 0.f, syf = 0.f, szf = 0.f;
     if (gi < prm.n) { sxf = scan[3 * static_cast<size_t>(gi)]; syf = scan[3 * static_cast<size_t>(gi) + 1]; szf = scan[3 * static_cast<size_t>(gi) + 2]; }
+    pdl_wait();
     // the first query's memo is requested BEFORE the pose is staged in shared memory: both loads share one round trip
     uint4 m0 = make_uint4(kNone, kNone, kNone, kNone), m1 = make_uint4(0, 0, 0, 0);
     uint32_t nc = kNone;
     float4 prev = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNone));
-    bool pref = false;  // (CHAIN) the first kPref list entries of this thread's first query are in s_pref
-    if (CHAIN && wk.chain_prev) {
-        // Every kernel this one can wait for was completely resident before this grid was launched (launch_dependents is the first
-        // thing its blocks do), so the spins cannot starve it.
-        const unsigned long long* const pv = wk.chain_prev;
-        const unsigned long long rows = gridDim.x, chunks = static_cast<unsigned long long>(((prm.n + kIcpThreads - 1) / kIcpThreads + 15) / 16);
-        if (tid == 0) {
-            // (1) the previous iteration's per-query data is final ([2] reuse blocks counted in, [1] chunks of its refresh kernel complete),
-            //     or that iteration has already released its flag (loop left: its refresh kernel completes no chunks)
-            const long long t0 = clock64();
-            for (;;) {
-                unsigned long long a, b, c;
-                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(pv + 2) : "memory");
-                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(b) : "l"(pv + 1) : "memory");
-                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(pv + 3) : "memory");
-                if ((a >= rows && b >= chunks) || c != 0ull) break;
-                if (clock64() - t0 > 4000000000ll) { st->comm_error = 2; st->done = 1; break; }
-                __nanosleep(100);
-            }
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        }
-        __syncthreads();
-        if (gi < prm.n) {
-            m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi];
-            // (the list has cand_cap >= kPref slots whatever its length: entries past the end are never looked at)
-            const float4* const src = wk.cand + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(ccap) * kIcpThreads) + static_cast<size_t>(tid);
-#pragma unroll
-            for (int u = 0; u < kPref; ++u)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s_pref[u][tid])), "l"(src + static_cast<size_t>(u) * kIcpThreads) : "memory");
-            pref = ccap >= static_cast<uint32_t>(kPref);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        // (2) the previous iteration's solve
-        if (tid == 0 && !flag_await(pv + 3, 1ull)) { st->comm_error = 2; st->done = 1; __threadfence(); }
-        __syncthreads();
-    } else {
-        pdl_wait();
-        if (gi < prm.n) { m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi]; }
-    }
+    if (gi < prm.n) { m0 = memo0[gi]; m1 = memo1[gi]; nc = wk.ncand[gi]; prev = wk.win[gi]; }
     ELM_TRACE_FIRST(2);
     if (tid < 12) { s_T[tid] = st->T[tid]; s_Tinv[tid] = st->Tinv[tid]; }
     if (tid < 9) s_Rinv[tid] = st->Rinv[tid];
@@ -1724,11 +1695,6 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
         if (wk.epoch && tid == 0)
             for (int t = blockIdx.x; t * kIcpThreads < prm.n; t += gridDim.x)
                 flag_store_release(wk.tile_flag + t, (static_cast<unsigned long long>(wk.epoch) << 32) | 0xffffffffull);
-        if (CHAIN && tid == 0) {  // nobody solves in this iteration: block 0 lets the next reuse kernel through (it will see `done` too)
-            if (blockIdx.x == 0) flag_store_release(wk.tile_ticket + 3, 1ull);
-            atomicAdd(wk.tile_ticket + 2, 1ull);
-        }
-        if (CHAIN) asm volatile("cp.async.wait_all;" ::: "memory");  // (no copy may be in flight into the shared memory of a block that has exited)
         return;
     }
     for (bool first = true; gi - tid < prm.n; gi += gridDim.x * kIcpThreads, first = false) {
@@ -1792,16 +1758,10 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
                 const Query Q(px, py, pz);
                 float m = kInf, s2 = kInf;
                 uint32_t mj = 0;
-                if (CHAIN && pref && first) asm volatile("cp.async.wait_all;" ::: "memory");  // (this thread's own copies: no barrier needed)
                 for (uint32_t j = 0; j < nc; j += 4) {
                     float4 c[4];  // (addresses past the list are clamped, not predicated: a predicated load sent c[] to local memory)
-                    if (CHAIN && pref && first && j == 0) {
 #pragma unroll
-                        for (uint32_t u = 0; u < 4; ++u) c[u] = s_pref[u][tid];  // (entries past the list: masked below like the clamped ones)
-                    } else {
-#pragma unroll
-                        for (uint32_t u = 0; u < 4; ++u) c[u] = my_cand[static_cast<size_t>(min(j + u, nc - 1)) * cstride];
-                    }
+                    for (uint32_t u = 0; u < 4; ++u) c[u] = my_cand[static_cast<size_t>(min(j + u, nc - 1)) * cstride];
 #pragma unroll
                     for (uint32_t u = 0; u < 4; ++u) {
                         const float dx = c[u].x - Q.fx, dy = c[u].y - Q.fy, dz = c[u].z - Q.fz;
@@ -1814,9 +1774,7 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
                 const float sd = fmaf(sqrtf(m), 1.00000095367431640625f, Q.band);
                 const float T = fmaf(sd * sd, 1.000003814697265625f, 1e-30f);
                 if (s2 > T) {  // (the exact distance of the unique winner is not needed: nothing is left to compare it with)
-                    // (re-reading the winner is an L1 hit; keeping it in registers instead measured no gain: profiles/r02_ab_chain.txt)
-                    if (CHAIN && pref && first && mj < static_cast<uint32_t>(kPref)) wpt = s_pref[mj][tid];
-                    else wpt = my_cand[static_cast<size_t>(mj) * cstride];
+                    wpt = my_cand[static_cast<size_t>(mj) * cstride];
                 } else {       // near tie (or an empty list): every candidate exactly, smallest rank (read from the map) among equals
                     Best b;
                     for (uint32_t j = 0; j < nc; ++j) {
@@ -1847,12 +1805,6 @@ icp_warm_reuse_kernel(MapView map, const float* __restrict__ scan, IcpParams prm
         }
     }
     publish_partials(s_sum, prm, wk.partials, static_cast<int>(blockIdx.x));
-    if (CHAIN) {  // everything this block wrote (matches, memos, its row of sums) is visible before the block counts itself in
-        asm volatile("cp.async.wait_all;" ::: "memory");  // (threads without a query never waited for their group)
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicAdd(wk.tile_ticket + 2, 1ull); }
-    }
     ELM_TRACE_LAST(3);
 }
 
@@ -2151,11 +2103,10 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
         } else if (tid < kAcc) {
             crow[tid] = 0.0;
         }
-        // the chunk's row is complete: count it (the fold below waits for all chunks of this iteration; in the chained mode the NEXT
-        // reuse kernel reads what the stragglers of this chunk were given as soon as all chunks are counted: every thread fences)
-        if (wk.chain || tid < kAcc) __threadfence();
+        // the chunk's row is complete: count it (the fold below waits for all chunks of this iteration)
+        if (tid < kAcc) __threadfence();
         __syncthreads();
-        if (tid == 0) { if (wk.chain) __threadfence(); atomicAdd(wk.tile_ticket + 1, 1ull); }
+        if (tid == 0) atomicAdd(wk.tile_ticket + 1, 1ull);
     }
     // the pose of this iteration, fetched in the shadow of the reuse kernel: any flag of this epoch proves that the previous
     // iteration's solve is complete and visible (blocks that handled a chunk have seen one already)
@@ -2176,13 +2127,7 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
     }
     ELM_TRACE_LAST(6);
     // ---- from here on the reuse kernel's rows are complete
-    if (wk.chain) {  // chain mode: every reuse block has counted itself in after publishing its row (no wait for the grid to drain)
-        if (loop_left) return;
-        if (tid == 0 && !flag_await(wk.tile_ticket + 2, static_cast<unsigned long long>(rows_before))) { st->comm_error = 2; st->done = 1; __threadfence(); }
-        __syncthreads();
-    } else {
-        pdl_wait();
-    }
+    pdl_wait();
     ELM_TRACE_LAST(7);
     if (loop_left) return;
     // speculative loads of the fold (rows of the reuse grid) share their round trip with the done flag
@@ -2215,10 +2160,7 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
         s_flagdone = d;
     }
     __syncthreads();
-    if (s_flagdone) {  // (chain mode: nobody solves in this iteration; the next reuse kernel must still get through, and will see `done`)
-        if (wk.chain && blockIdx.x == 0 && tid == 0) flag_store_release(wk.tile_ticket + 3, 1ull);
-        return;
-    }
+    if (s_flagdone) return;
     if (!have_state) load_state();
     // fold: block b takes the reuse rows b, b + G, ... and the chunk rows b, b + G, ... in that order
     if (tid < kAcc) {
@@ -2237,8 +2179,6 @@ icp_warm_refresh_async_kernel(MapView map, const float* __restrict__ scan, IcpPa
     __syncthreads();
     ELM_TRACE_LAST(9);
     finish_grid<kAsyncWarps>(s_sum, s_red, s_acc, &s_last, &s_solve, s_T, st, prm, wk.partials, wk.ticket, solve_here, rows_before, -1, rows_before);
-    // chain mode: the last block (its thread 0 has just solved) releases the iteration's flag; the next reuse kernel waits for it
-    if (wk.chain && tid == 0 && s_last) { __threadfence(); flag_store_release(wk.tile_ticket + 3, 1ull); }
     ELM_TRACE_LAST(10);
 }
 
@@ -2510,7 +2450,7 @@ icp_avgicp_kernel(MapView map, const float* __restrict__ scan, IcpParams prm, Ic
 __global__ void icp_begin_kernel(IcpState* st, Pose16 T0, unsigned int* ticket, unsigned long long* tile_ticket) {
     // every concurrent-refresh iteration of the call owns ITS pair of counters {chunks handed out, chunk rows completed}: kernels of
     // several iterations can be resident at once (programmatic dependent launch), a shared counter would mix their draws
-    if (tile_ticket) for (int i = threadIdx.x; i < kTicketWords * kMaxAsyncIterations; i += blockDim.x) tile_ticket[i] = 0ull;
+    if (tile_ticket) for (int i = threadIdx.x; i < 2 * kMaxAsyncIterations; i += blockDim.x) tile_ticket[i] = 0ull;
     if (threadIdx.x == 0) {
         // (the tile-ticket counters are reset by every lane below)
         for (int i = 0; i < 16; ++i) st->T[i] = T0.m[i];
@@ -2657,13 +2597,10 @@ cudaError_t launch_icp_search(const MapView& map, const float* scan, const int* 
 }
 
 // One warm iteration of P2P / GICP (search + linearisation + reduction + solve) = the reuse kernel, then the refresh kernel.
-cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
+cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, const IcpWork& wk, int reuse_grid,
                                   cudaStream_t s) {
-    cudaError_t e;
-    if (wk.chain) e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0, true>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
-                                      : launch_pdl(icp_warm_reuse_kernel<1, true>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
-    else e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0, false>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
-                             : launch_pdl(icp_warm_reuse_kernel<1, false>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
+    const cudaError_t e = prm.method == 0 ? launch_pdl(icp_warm_reuse_kernel<0>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk)
+                                          : launch_pdl(icp_warm_reuse_kernel<1>, reuse_grid, kIcpThreads, 0, s, map, scan, prm, st, wk);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
@@ -2682,9 +2619,12 @@ cudaError_t launch_icp_warm(const MapView& map, const float* scan, const IcpPara
 }
 
 // Blocks of the concurrent refresh kernel.  A refresh block (128 threads x 128 registers) becomes resident beside THREE reuse blocks
-// of an SM, not beside four, and the fold needs every refresh block: the last one to start gates the iteration.
+// of an SM, not beside four, and the fold needs every refresh block: the last one to start gates the iteration.  With the 512 reuse
+// blocks of a 131072-point scan 80 SMs hold three of them: 80 refresh blocks are all resident at once, and they leave room for the
+// NEXT iteration's 512 reuse blocks to become resident before this iteration has finished (80 x 3 + 68 x 4 = 512).  Measured on B200
+// (profiles/r02_ab_chain.txt): 80 blocks +1.4 % at 131072 points and +4.6 % at 16384 against 128; GICP is indifferent.
 int icp_warm_refresh_async_grid(int num_sms, int want) {
-    const int g = want > 0 ? want : 128;
+    const int g = want > 0 ? want : 80;
     return num_sms < g ? num_sms : g;
 }
 cudaError_t launch_icp_warm_refresh_async(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,

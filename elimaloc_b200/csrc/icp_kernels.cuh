@@ -25,7 +25,7 @@ cudaError_t launch_icp_accumulate(const MapView& map, const float* scan, const I
 // One WARM iteration of P2P / GICP — search from the previous iteration's wk.win / wk.memo / candidate lists of the SAME scan,
 // linearisation, reduction, solve — as two launches (icp_kernels.cu); wk.partials needs reuse_grid + refresh_grid rows.
 int icp_warm_refresh_grid(const IcpParams& prm, int num_sms);
-cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
+cudaError_t launch_icp_warm_reuse(const MapView& map, const float* scan, const IcpParams& prm, const IcpState* st, const IcpWork& wk, int reuse_grid,
                                   cudaStream_t s);
 cudaError_t launch_icp_warm_refresh(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
                                     int refresh_grid, int solve_here, cudaStream_t s);
@@ -34,7 +34,7 @@ cudaError_t launch_icp_warm(const MapView& map, const float* scan, const IcpPara
                             cudaStream_t s);
 // The refresh kernel running BESIDE the reuse kernel of the same iteration (wk.epoch != 0: the reuse kernel publishes every tile's
 // work list as soon as it is complete); grid = icp_warm_refresh_async_grid blocks of 128 threads; wk.partials needs reuse_grid + grid rows.
-int icp_warm_refresh_async_grid(int num_sms, int want = 0);  // want: blocks asked for (0: 128)
+int icp_warm_refresh_async_grid(int num_sms, int want = 0);  // want: blocks asked for (0: the default, 80)
 cudaError_t launch_icp_warm_refresh_async(const MapView& map, const float* scan, const IcpParams& prm, IcpState* st, const IcpWork& wk, int reuse_grid,
                                           int grid, int solve_here, cudaStream_t s);
 cudaError_t launch_icp_solve(IcpState* st, const IcpParams& prm, cudaStream_t s);

@@ -63,3 +63,40 @@ def test_the_model_detects_another_summation_order():
     rng = np.random.default_rng(3)
     x = rng.standard_normal((32, 18)) * 10.0 ** rng.integers(-12, 12, (32, 18))
     assert not (x.sum(axis=0) == butterfly(x)[0]).all()
+
+
+def _expand_p2p(a, k):
+    """expand_p2p of icp_kernels.cu: canonical slot k (upper JtJ row-major, Jtr, residual, count) of the 18 structured P2P sums"""
+    fixed = {0: a[0], 6: a[0], 11: a[0], 4: a[3], 5: -a[2], 8: -a[3], 10: a[1], 12: a[2], 13: -a[1], 27: a[16], 28: a[17]}
+    if k in fixed:
+        return fixed[k]
+    if 15 <= k <= 20:
+        return a[4 + k - 15]
+    if 21 <= k <= 26:
+        return a[10 + k - 21]
+    return 0.0
+
+
+def test_p2p_scatter_table_is_expand_p2p_read_backwards():
+    """After the reduce-scatter lane l holds accumulator l; kP2pScatter tells every lane which canonical slots of the row it writes.
+    The table is parsed out of the kernel source: every slot 0..28 written exactly once with the value (and sign) expand_p2p gives it."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "elimaloc_b200", "csrc", "icp_kernels.cu")).read()
+    blk = src[src.index("__constant__ uint32_t kP2pScatter[32] = {"):src.index("#undef ELM_SC")]
+    ents = re.findall(r"ELM_SC\((0x[0-9a-f]+|\d+), (0x[0-9a-f]+|\d+), (0x[0-9a-f]+|\d+), (\d+)\)", blk)
+    assert len(ents) == 32
+    a = np.random.default_rng(0).standard_normal(18)
+    row = {}
+    for lane, (s0, s1, s2, f) in enumerate((int(p, 0), int(q, 0), int(r, 0), int(g)) for p, q, r, g in ents):
+        v = a[lane] if lane < 18 else 123.456          # (lanes >= 18 hold nothing of value)
+        w = 0.0 if f & 1 else v
+        w1 = -w if f & 2 else w
+        for slot, val in ((s0, w), (s1, w1), (s2, w)):
+            if slot != 0xFF:
+                assert slot not in row, f"slot {slot} written twice"
+                row[slot] = val
+    assert sorted(row) == list(range(29))
+    for k in range(29):
+        e = _expand_p2p(a, k)
+        assert row[k] == e and np.signbit(row[k]) == np.signbit(e), k
