@@ -299,9 +299,9 @@ def build_roofline(args, method, st, by_kind, counters, n_local, peak, peak_src,
             row(f"icp_warm_kernel<{method}>", "warm", wm[0] + wm[1], wm[2], warm_req, warm_note + "; one launch per iteration")
         else:
             row(f"icp_warm_reuse_kernel<{method}>", "warm", wm[0], wm[2], warm_req, warm_note)
-            row(f"icp_warm_refresh_async_kernel<{method}>" if mode in ("a", "c") else f"icp_warm_refresh_kernel<{method}>", "warm", wm[1], wm[2], 0.0,
+            row(f"icp_warm_refresh_async_kernel<{method}>" if mode == "a" else f"icp_warm_refresh_kernel<{method}>", "warm", wm[1], wm[2], 0.0,
                 "stragglers (none on this map after the first warm iteration) + fold of the reuse rows + final reduction + solve: a latency chain, not a stream"
-                + ("; runs BESIDE the reuse kernel in the timed region, after it in this event-serialised pass" if mode in ("a", "c") else ""))
+                + ("; runs BESIDE the reuse kernel in the timed region, after it in this event-serialised pass" if mode == "a" else ""))
     elif method == 2:
         row("icp_search_means_kernel", "cold", cold[0], cold[2], 12 + 64 + 8 + 8 * st["v27"] + 4, "scan 12 + buckets 64 + candidate run descriptor 8 + 8 per candidate (13-bit mean offsets + voxel index) + match out 4")
         row("icp_accumulate_kernel<2>", "cold", cold[1], cold[2], 12 + 4 + 96, "scan 12 + match 4 + mean and covariance 96 (one 128-byte line)")

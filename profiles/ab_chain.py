@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""A/B of the warm-iteration structure inside ONE process (one map build): ELM_WARM_MODE = async | chain and ELM_ASYNC_GRID = blocks of
-the concurrent refresh kernel are read when a registration handle is created, so every variant gets its own handle.
+"""A/B harness inside ONE process (one map build): ELM_WARM_MODE (pair | single | async) and ELM_ASYNC_GRID (blocks of the concurrent
+refresh kernel) are read when a registration handle is created, so every variant gets its own handle; a compile-time variant of the
+library is selected per process with ELIMALOC_B200_LIB (profiles/build_variant.sh).
 
-  python profiles/ab_chain.py [--methods p2p,gicp] [--sizes 131072,16384] [--grids 128,96,80,64,48,32] [--steps 40]
-  ELIMALOC_B200_LIB=elimaloc_b200/lib_<variant>.so python profiles/ab_chain.py ...      (a compile-time variant of the library)
+  python profiles/ab_chain.py [--methods p2p,gicp,vgicp,avgicp] [--sizes 131072,16384] [--grids 80,128] [--modes async,pair] [--steps 30]
 
+(The name is historical: calls Q and R of round 2 used it to measure the "chained" warm iterations, ELM_WARM_MODE=chain, which existed in
+commits 802062d..e950929 and were removed — DESIGN.md, table of things that did not pay.  An unknown mode falls back to the default.)
 Timing as bench.py's `value`: CUDA events on the launch stream around K enqueued RunRegister calls of 20 forced iterations, a different
-scan every step, after 3 warm-up steps.  Prints one line per variant: iterations/s, us per iteration, the pose difference to the first
-variant (same summation grid: must be 0.0; another grid: rounding level) and one JSON line with everything at the end."""
+scan every step, after 3 warm-up steps, the faster of two timed regions.  One line per variant: iterations/s, us per iteration, the pose
+difference to the established mode on the same summation grid (must be 0.0), a checksum of pose + fitness (equal across builds whose sums
+are bit-identical) and one JSON line with everything at the end."""
 import argparse
 import hashlib
 import json
