@@ -142,19 +142,28 @@ struct VoxelHashMap {
         }
         return out;
     }
-    // first point of every floor-keyed voxel (voxel_hash_map.hpp:260-283); survivors in input order (the reference emits
-    // them in hash-table order, which nothing downstream depends on beyond rounding).  Host work on a few thousand points.
+    // first point of every floor-keyed voxel (voxel_hash_map.hpp:260-283), emitted in the reference's own order: the same container
+    // (std::unordered_map), the same hash VALUES (VoxelHash, voxel_hash_map.hpp:150-155: 32-bit arithmetic, 20-bit mask), the same
+    // reserve() and the same insertion sequence give the same iteration order on the same standard library — nothing here knows how
+    // the library orders its nodes.  Host work on a few thousand points.
     std::vector<PointStruct> VoxelDownsample(const std::vector<PointStruct>& points, const double voxel_size) const {
-        struct Key { int64_t x, y, z; bool operator==(const Key& o) const { return x == o.x && y == o.y && z == o.z; } };
-        struct Hash { size_t operator()(const Key& k) const { return static_cast<size_t>(k.x * 73856093LL ^ k.y * 19349669LL ^ k.z * 83492791LL); } };
-        std::unordered_map<Key, bool, Hash> seen;
-        seen.reserve(points.size());
-        std::vector<PointStruct> out;
-        for (const PointStruct& p : points) {
-            const Key k{static_cast<int64_t>(std::floor(p.pose.x() / voxel_size)), static_cast<int64_t>(std::floor(p.pose.y() / voxel_size)),
-                        static_cast<int64_t>(std::floor(p.pose.z() / voxel_size))};
-            if (seen.emplace(k, true).second) out.push_back(p);
+        struct Key { int x, y, z; bool operator==(const Key& o) const { return x == o.x && y == o.y && z == o.z; } };
+        struct Hash {
+            size_t operator()(const Key& k) const {
+                return ((1 << 20) - 1) & (static_cast<uint32_t>(k.x) * 73856093 ^ static_cast<uint32_t>(k.y) * 19349669 ^ static_cast<uint32_t>(k.z) * 83492791);
+            }
+        };
+        std::unordered_map<Key, size_t, Hash> grid;
+        grid.reserve(points.size());
+        for (size_t i = 0; i < points.size(); ++i) {
+            const PointStruct& p = points[i];
+            const Key k{static_cast<int>(std::floor(p.pose.x() / voxel_size)), static_cast<int>(std::floor(p.pose.y() / voxel_size)),
+                        static_cast<int>(std::floor(p.pose.z() / voxel_size))};
+            if (grid.find(k) == grid.end()) grid.insert({k, i});
         }
+        std::vector<PointStruct> out;
+        out.reserve(grid.size());
+        for (const auto& kv : grid) out.emplace_back(points[kv.second]);
         return out;
     }
     elm_map* handle() const { return h_; }  // for the scan chain of INTEGRATION.md section 6 (elm_scan_pipeline_*)

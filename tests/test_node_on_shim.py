@@ -126,8 +126,10 @@ def test_unmodified_node_on_cuda_publishes_what_the_reference_node_publishes(raw
 
 
 def test_shim_host_helpers(tmp_path):
-    """VoxelDownsample and TransformPoints of the shim (host code the node calls around RunRegister) against the oracle:
-    the first point of every floor-keyed voxel in input order; the transform moves `pose` and leaves `local` alone"""
+    """VoxelDownsample and TransformPoints of the shim (host code the node calls around RunRegister): the first point of every
+    floor-keyed voxel (the oracle's survivor set) emitted in the REFERENCE's order — the survivors' indices equal, position by
+    position, what the reference's own VoxelDownsample returns (its hash-table iteration order: same container, hash values, reserve
+    and insertion sequence on the same standard library); the transform moves `pose` and leaves `local` alone"""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "shim_helpers_check")
@@ -142,7 +144,8 @@ def test_shim_host_helpers(tmp_path):
         out = subprocess.run([exe, str(tmp_path / "pts.f32"), str(len(xyz)), repr(voxel)], check=True, capture_output=True, text=True).stdout.split("\n")
         k = int(out[0])
         idx = np.array([int(v) for v in out[1:1 + k]])
-        want = O.scan_preprocess(xyz, 0.0, voxel)
+        assert np.array_equal(np.sort(idx), O.scan_preprocess(xyz, 0.0, voxel))
+        want = R.voxel_downsample(xyz, voxel)
         assert np.array_equal(idx, want)
         for line, i in zip(out[1 + k:1 + k + 5], want[:5]):
             v = [float(t) for t in line.split()]
