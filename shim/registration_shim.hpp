@@ -63,13 +63,17 @@ struct RegistrationConfig {  // registration.hpp:62-85, every field the node fil
 };
 
 namespace elm_shim {
-inline std::vector<float> flatten(const std::vector<PointStruct>& pts) {
-    std::vector<float> xyz(3 * pts.size());
+inline void flatten_into(const std::vector<PointStruct>& pts, std::vector<float>& xyz) {
+    xyz.resize(3 * pts.size());  // (a buffer that lives with its owner: no 1.5 MB allocation + first-touch page faults per scan)
     for (size_t i = 0; i < pts.size(); ++i) {  // Pcl2PointStruct widened float fields: narrowing back is lossless
         xyz[3 * i] = static_cast<float>(pts[i].pose.x());
         xyz[3 * i + 1] = static_cast<float>(pts[i].pose.y());
         xyz[3 * i + 2] = static_cast<float>(pts[i].pose.z());
     }
+}
+inline std::vector<float> flatten(const std::vector<PointStruct>& pts) {
+    std::vector<float> xyz;
+    flatten_into(pts, xyz);
     return xyz;
 }
 inline void check(int status) {
@@ -197,7 +201,8 @@ struct Registration {
         c.range_variance_m = m_config.range_variance_m;
         c.azimuth_variance_deg = m_config.azimuth_variance_deg;
         c.elevation_variance_deg = m_config.elevation_variance_deg;
-        const std::vector<float> xyz = elm_shim::flatten(source_local);
+        std::vector<float>& xyz = xyz_;  // (RunRegister is never re-entered: both call sites of the node hold mutex_pcl_)
+        elm_shim::flatten_into(source_local, xyz);
         double T0[16], T[16], cov[36];  // the ABI is row-major; coefficient access keeps this independent of Eigen's storage order
         for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T0[4 * i + j] = initial_guess(i, j);
         int32_t ok = 0;
@@ -229,4 +234,5 @@ struct Registration {
     elm_registration* handle() const { return h_; }
     RegistrationConfig config_;
     elm_registration* h_ = nullptr;
+    std::vector<float> xyz_;  // packed float xyz of the last scan (staging for elm_run_register)
 };
