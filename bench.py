@@ -14,7 +14,8 @@ synthetic Scan-U against the 10 M-raw-point Map-U (BASELINE.md section 4, config
 
   value      ICP iterations/s with the scan already resident in HBM (CUDA events around K enqueued steps)
   e2e        the same metric through the host-buffer C-ABI call elm_run_register (pinned host scan, H2D + D2H inside)
-  roofline   dominant kernel (fused search+accumulate) : algorithmic bytes / its CUDA-event time vs measured HBM peak
+  roofline   the streaming kernel with the largest share of the step (`roofline.kernels`: every kernel of the step): requested bytes / its
+             CUDA-event time vs the measured HBM peak; the reduction / solve tail of a warm iteration is listed as `latency_tail`
   cpu_baseline   the oracle (structure-faithful CPU port of the reference) on the box's host cores, bounded sample
 
 N > 1 (torchrun): the scan is sharded over ranks, the map replicated, and the 32 accumulators are all-reduced once per
